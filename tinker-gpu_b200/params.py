@@ -1,0 +1,702 @@
+"""Parameter assignment for the AMOEBA multipole/polarization path.
+
+Restates, without the Fortran library, what `tinker_f_mechanic()` leaves in the
+modules the reference's `mpoleData` / `epolarData` / `pmeData` read
+(src/elec.cpp:54-500, src/amoeba/epolar.cpp:25-511):
+
+* attach.f       1-3 / 1-4 / 1-5 connectivity
+* kmpole.f       local-frame matching + unit conversion (bohr, bohr^2/3)
+* kpolar.f       polarizability, Thole, pdamp, jpolar/thlval table, polargrp
+* kewald.f       ewaldcof bisection, 2-3-5 PME grid
+* cutoffs.f      ewald-cutoff, usolve-cutoff, list buffers
+* lattice.f      box vectors / reciprocal vectors
+* the m-, d/p-, u- and fused mdpu exclusion/scale lists the back-end kernels take.
+
+All arrays are 0-based; `zaxis[:,2]` (the y-axis atom) keeps Tinker's signed
+1-based convention because chkpole flips its sign (src/elec.cpp:92-99).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .tinkerio import XYZ, KeyFile, ForceField, parse_multipole, parse_polarize
+
+BOHR = 0.529177210544          # tinker/source/units.f:91
+COULOMB = 332.0637133          # units.f:95 (electric, dielec = 1)
+DEBYE = 4.803206802            # units.f:97
+
+LFRM = {"None": 0, "Z-Only": 1, "Z-then-X": 2, "Bisector": 3, "Z-Bisect": 4, "3-Fold": 5}
+
+PME_GRID_SIZES = [2, 4, 6, 8, 10, 12, 16, 18, 20, 24, 30, 32, 36, 40, 48, 50, 54, 60, 64, 72, 80, 90, 96, 100, 108,
+                  120, 128, 144, 150, 160, 162, 180, 192, 200, 216, 240, 250, 256, 270, 288, 300, 320, 324, 360,
+                  384, 400, 432, 450, 480, 486, 500, 512, 540, 576, 600, 640, 648, 720, 750, 768, 800, 810, 864]
+
+
+@dataclass
+class System:
+    """Flat SoA description of one AMOEBA electrostatics problem."""
+    n: int
+    xyz: np.ndarray                    # (n,3) f64
+    lvec: np.ndarray                   # (3,3) f64 rows = lvec1..3 (include/ff/box.h)
+    recip: np.ndarray                  # (3,3) f64 rows = recipa, recipb, recipc
+    pole: np.ndarray                   # (n,10) f64 local-frame, MPL_PME order
+    zaxis: np.ndarray                  # (n,4) i32 {z, x, y(signed 1-based), polaxe}
+    polarity: np.ndarray               # (n,)
+    thole: np.ndarray
+    pdamp: np.ndarray
+    jpolar: np.ndarray                 # (n,) i32 index into thlval
+    thlval: np.ndarray                 # (nj,nj)
+    mexclude: np.ndarray               # (nm,2) i32 i<k
+    mexclude_scale: np.ndarray         # (nm,)
+    dpexclude: np.ndarray              # (ndp,2)
+    dpexclude_scale: np.ndarray        # (ndp,2)  d, p
+    uexclude: np.ndarray               # (nu,2)
+    uexclude_scale: np.ndarray         # (nu,)
+    mdpuexclude: np.ndarray            # (nx,2)
+    mdpuexclude_scale: np.ndarray      # (nx,4)  m, d, p, u
+    # options
+    use_ewald: bool = True
+    use_mpole: bool = True
+    use_polar: bool = True
+    aewald: float = 0.0
+    nfft: tuple = (0, 0, 0)
+    bsorder: int = 5
+    ewald_cutoff: float = 7.0          # real-space cutoff (mpole-cutoff when not Ewald)
+    usolve_cutoff: float = 4.5         # preconditioner range actually applied (cutoff + pbuffer, precond.cu:30-31)
+    list_buffer: float = 2.0
+    poleps: float = 1.0e-6
+    politer: int = 100
+    uaccel: float = 2.0
+    pcgprec: bool = True
+    pcgguess: bool = True
+    pcgpeek: float = 1.0
+    poltyp: str = "MUTUAL"
+    electric: float = COULOMB
+    dielec: float = 1.0
+    types: np.ndarray | None = None
+    names: list | None = None
+    bonds: list | None = None
+    title: str = ""
+
+    @property
+    def volume(self) -> float:
+        return float(abs(np.linalg.det(self.lvec)))
+
+    @property
+    def orthogonal(self) -> bool:
+        off = self.lvec - np.diag(np.diag(self.lvec))
+        return bool(np.all(np.abs(off) < 1e-12))
+
+
+# ----------------------------------------------------------------------------
+# connectivity (attach.f)
+# ----------------------------------------------------------------------------
+def attach(bonds):
+    """Return i13, i14, i15 lists (sorted, de-duplicated) from i12."""
+    n = len(bonds)
+    i12 = [list(b) for b in bonds]
+    s12 = [set(b) for b in bonds]
+    i13, i14, i15 = [None] * n, [None] * n, [None] * n
+    for i in range(n):
+        s = set()
+        for j in i12[i]:
+            s.update(i12[j])
+        s.discard(i)
+        s -= s12[i]
+        i13[i] = sorted(s)
+    s13 = [set(b) for b in i13]
+    for i in range(n):
+        s = set()
+        for j in i13[i]:
+            s.update(i12[j])
+        s.discard(i)
+        s -= s12[i]
+        s -= s13[i]
+        i14[i] = sorted(s)
+    s14 = [set(b) for b in i14]
+    for i in range(n):
+        s = set()
+        for j in i14[i]:
+            s.update(i12[j])
+        s.discard(i)
+        s -= s12[i]
+        s -= s13[i]
+        s -= s14[i]
+        i15[i] = sorted(s)
+    return i13, i14, i15
+
+
+# ----------------------------------------------------------------------------
+# kmpole.f
+# ----------------------------------------------------------------------------
+def assign_multipoles(types, i12, i13, records):
+    """kmpole.f:292-432 -- four matching passes, first hit in record order wins."""
+    n = len(types)
+    by_type = {}
+    for rec in records:
+        by_type.setdefault(rec.typ, []).append(rec)
+    pole13 = np.zeros((n, 13))
+    zax = np.full(n, -1, np.int64)
+    xax = np.full(n, -1, np.int64)
+    yax = np.zeros(n, np.int64)          # 1-based, 0 = none
+    polaxe = ["None"] * n
+    found = np.zeros(n, bool)
+    s12 = [set(b) for b in i12]
+
+    def put(i, rec, z=-1, x=-1, y=0):
+        zax[i], xax[i], yax[i] = z, x, y
+        polaxe[i] = rec.axis
+        pole13[i] = rec.pole
+        found[i] = True
+
+    for i in range(n):
+        recs = by_type.get(int(types[i]), ())
+        if not recs:
+            continue
+        done = False
+        # pass 1: only 1-2 connected atoms
+        for rec in recs:
+            for ji in i12[i]:
+                if types[ji] != rec.kz:
+                    continue
+                for ki in i12[i]:
+                    if types[ki] != rec.kx or ki == ji:
+                        continue
+                    if rec.ky == 0:
+                        put(i, rec, ji, ki)
+                        done = True
+                        break
+                    for li in i12[i]:
+                        if types[li] == rec.ky and li != ji and li != ki:
+                            put(i, rec, ji, ki, li + 1)
+                            done = True
+                            break
+                    if done:
+                        break
+                if done:
+                    break
+            if done:
+                break
+        if done:
+            continue
+        # pass 2: 1-2 for z, 1-3 (through z) for x and y
+        for rec in recs:
+            for ji in i12[i]:
+                if types[ji] != rec.kz:
+                    continue
+                for ki in i13[i]:
+                    if types[ki] != rec.kx or ji not in s12[ki]:
+                        continue
+                    if rec.ky == 0:
+                        put(i, rec, ji, ki)
+                        done = True
+                        break
+                    for li in i13[i]:
+                        if types[li] == rec.ky and li != ki and ji in s12[li]:
+                            put(i, rec, ji, ki, li + 1)
+                            done = True
+                            break
+                    if done:
+                        break
+                if done:
+                    break
+            if done:
+                break
+        if done:
+            continue
+        # pass 3: only a z-defining atom
+        for rec in recs:
+            if rec.kx != 0:
+                continue
+            for ji in i12[i]:
+                if types[ji] == rec.kz:
+                    put(i, rec, ji)
+                    done = True
+                    break
+            if done:
+                break
+        if done:
+            continue
+        # pass 4: no connected atoms
+        for rec in recs:
+            if rec.kz == 0:
+                put(i, rec)
+                break
+    return pole13, zax, xax, yax, polaxe, found
+
+
+def pole13_to_pme10(pole13):
+    """Tinker pole(13) -> MPL_PME order c,x,y,z,xx,yy,zz,xy,xz,yz (src/elec.cpp:128-144),
+    after the bohr / bohr^2/3 conversion of kmpole.f:520-527."""
+    p = pole13.copy()
+    p[:, 1:4] *= BOHR
+    p[:, 4:13] *= BOHR * BOHR / 3.0
+    out = np.zeros((p.shape[0], 10))
+    out[:, 0] = p[:, 0]
+    out[:, 1:4] = p[:, 1:4]
+    out[:, 4] = p[:, 4]
+    out[:, 5] = p[:, 8]
+    out[:, 6] = p[:, 12]
+    out[:, 7] = p[:, 5]
+    out[:, 8] = p[:, 6]
+    out[:, 9] = p[:, 9]
+    return out
+
+
+# ----------------------------------------------------------------------------
+# kpolar.f : polargrp
+# ----------------------------------------------------------------------------
+def polar_groups(types, i12, polarize):
+    """polargrp (kpolar.f:577-900): ip11 = connected component over bonds whose end types
+    list each other in `polarize` group-types; ip12/13/14 = groups 1,2,3 bonds away."""
+    n = len(types)
+    grp_types = {t: set(r.group) for t, r in polarize.items()}
+    adj = [[] for _ in range(n)]
+    for i in range(n):
+        gt = grp_types.get(int(types[i]), ())
+        for j in i12[i]:
+            if int(types[j]) in gt:
+                adj[i].append(j)
+    for i in range(n):
+        for j in adj[i]:
+            if i not in adj[j]:
+                raise ValueError(f"POLARGRP  --  Check Polarization Groups for Atoms {min(i, j) + 1} and {max(i, j) + 1}")
+    gid = np.full(n, -1, np.int64)
+    groups = []
+    for i in range(n):
+        if gid[i] >= 0:
+            continue
+        stack, members = [i], []
+        gid[i] = len(groups)
+        while stack:
+            a = stack.pop()
+            members.append(a)
+            for b in adj[a]:
+                if gid[b] < 0:
+                    gid[b] = len(groups)
+                    stack.append(b)
+        groups.append(sorted(members))
+    ng = len(groups)
+    # group-level adjacency through any covalent bond
+    g12 = [set() for _ in range(ng)]
+    for i in range(n):
+        for j in i12[i]:
+            if gid[j] != gid[i]:
+                g12[gid[i]].add(int(gid[j]))
+    g13, g14 = [None] * ng, [None] * ng
+    for g in range(ng):
+        s = set()
+        for h in g12[g]:
+            s |= g12[h]
+        s.discard(g)
+        s -= g12[g]
+        g13[g] = s
+    for g in range(ng):
+        s = set()
+        for h in g13[g]:
+            s |= g12[h]
+        s.discard(g)
+        s -= g12[g]
+        s -= g13[g]
+        g14[g] = s
+
+    def expand(gsets):
+        out = [None] * ng
+        for g in range(ng):
+            m = []
+            for h in gsets[g]:
+                m.extend(groups[h])
+            out[g] = sorted(m)
+        return out
+
+    return gid, groups, expand(g12), expand(g13), expand(g14)
+
+
+# ----------------------------------------------------------------------------
+# kewald.f
+# ----------------------------------------------------------------------------
+def ewaldcof(cutoff: float, eps: float = 1.0e-8) -> float:
+    """kewald.f:312-365."""
+    ratio = eps + 1.0
+    x = 0.5
+    i = 0
+    while ratio >= eps:
+        i += 1
+        x = 2.0 * x
+        ratio = math.erfc(x * cutoff) / cutoff
+    k = i + 60
+    xlo, xhi = 0.0, x
+    for _ in range(k):
+        x = 0.5 * (xlo + xhi)
+        ratio = math.erfc(x * cutoff) / cutoff
+        if ratio >= eps:
+            xlo = x
+        else:
+            xhi = x
+    return x
+
+
+def pme_grid_default(box_len: float, dens: float = 1.2, minfft: int = 16) -> int:
+    """kewald.f:133-135,192-206."""
+    want = int(box_len * dens - 1.0e-8) + 1
+    pick = PME_GRID_SIZES[-1]
+    for k in reversed(PME_GRID_SIZES):
+        if k >= want:
+            pick = k
+    return max(pick, minfft)
+
+
+def lattice(a, b, c, alpha=90.0, beta=90.0, gamma=90.0):
+    """lattice.f: lvec rows and reciprocal vectors (recip @ r = fractional)."""
+    ar, br, gr = (math.radians(v) for v in (alpha, beta, gamma))
+    ca, cb, cg, sg = math.cos(ar), math.cos(br), math.cos(gr), math.sin(gr)
+    if abs(alpha - 90) < 1e-12:
+        ca = 0.0
+    if abs(beta - 90) < 1e-12:
+        cb = 0.0
+    if abs(gamma - 90) < 1e-12:
+        cg, sg = 0.0, 1.0
+    bt = (ca - cb * cg) / sg
+    gt = math.sqrt(max(0.0, 1.0 - cb * cb - bt * bt))
+    # columns are the cell vectors a,b,c ; rows are lvec1..3 (include/ff/box.h)
+    cell = np.array([[a, b * cg, c * cb],
+                     [0.0, b * sg, c * bt],
+                     [0.0, 0.0, c * gt]])
+    recip = np.linalg.inv(cell)      # rows = recipa, recipb, recipc
+    return cell, recip
+
+
+# ----------------------------------------------------------------------------
+# exclusion / scale lists
+# ----------------------------------------------------------------------------
+def build_scale_lists(n, i12, i13, i14, i15, gid, groups, p12, p13, p14, scales):
+    """m (src/elec.cpp mpole scaling), d/p/u (src/amoeba/epolar.cpp:128-391) and the fused
+    mdpu list (src/elec.cpp:147-500).  Pairs are stored once with i<k; later assignments
+    override earlier ones exactly as the reference's std::map insertion does."""
+    m2, m3, m4, m5 = (scales[f"MPOLE-1{k}-SCALE"] for k in (2, 3, 4, 5))
+    p2, p3, p4, p5 = (scales[f"POLAR-1{k}-SCALE"] for k in (2, 3, 4, 5))
+    p2i, p3i, p4i, p5i = (scales[f"POLAR-1{k}-INTRA"] for k in (2, 3, 4, 5))
+    d1, d2, d3, d4 = (scales[f"DIRECT-1{k}-SCALE"] for k in (1, 2, 3, 4))
+    u1, u2, u3, u4 = (scales[f"MUTUAL-1{k}-SCALE"] for k in (1, 2, 3, 4))
+
+    mdpu = {}
+
+    def put(i, k, col, val):
+        key = (i, k)
+        e = mdpu.get(key)
+        if e is None:
+            e = [1.0, 1.0, 1.0, 1.0]
+            mdpu[key] = e
+        e[col] = val
+
+    for i in range(n):
+        g = int(gid[i])
+        # m
+        for lst, sc in ((i12[i], m2), (i13[i], m3), (i14[i], m4), (i15[i], m5)):
+            if sc != 1:
+                for k in lst:
+                    if k > i:
+                        put(i, k, 0, sc)
+        # d (by polarization group distance)
+        for lst, sc in ((groups[g], d1), (p12[g], d2), (p13[g], d3), (p14[g], d4)):
+            if sc != 1:
+                for k in lst:
+                    if k > i:
+                        put(i, k, 1, sc)
+        # p (by bond distance; intra-group variant)
+        for lst, sc, sci in ((i12[i], p2, p2i), (i13[i], p3, p3i), (i14[i], p4, p4i), (i15[i], p5, p5i)):
+            if sc != 1 or sci != 1:
+                for k in lst:
+                    if k > i:
+                        put(i, k, 2, sci if gid[k] == g else sc)
+        # u
+        for lst, sc in ((groups[g], u1), (p12[g], u2), (p13[g], u3), (p14[g], u4)):
+            if sc != 1:
+                for k in lst:
+                    if k > i:
+                        put(i, k, 3, sc)
+
+    keys = sorted(mdpu)
+    ik = np.array(keys, np.int32).reshape(-1, 2)
+    sc = np.array([mdpu[k] for k in keys], np.float64).reshape(-1, 4)
+    return _split_scale_lists(ik, sc)
+
+
+def _split_scale_lists(ik, sc):
+    selm = sc[:, 0] != 1
+    seldp = (sc[:, 1] != 1) | (sc[:, 2] != 1)
+    selu = sc[:, 3] != 1
+    return dict(
+        mexclude=ik[selm].copy(), mexclude_scale=sc[selm, 0].copy(),
+        dpexclude=ik[seldp].copy(), dpexclude_scale=sc[seldp][:, 1:3].copy(),
+        uexclude=ik[selu].copy(), uexclude_scale=sc[selu, 3].copy(),
+        mdpuexclude=ik, mdpuexclude_scale=sc)
+
+
+# ----------------------------------------------------------------------------
+# top level
+# ----------------------------------------------------------------------------
+def _key_multipoles(key: KeyFile):
+    """`multipole` records given in the keyfile precede the .prm ones (kmpole.f:118-128)."""
+    out = []
+    L = key.lines
+    i = 0
+    while i < len(L):
+        if L[i][0] == "MULTIPOLE" and i + 4 < len(L) + 1:
+            nxt = [L[i + j][2] for j in range(1, 5) if i + j < len(L)]
+            if len(nxt) == 4:
+                try:
+                    rec = parse_multipole(L[i][1], nxt)
+                    if rec.typ > 0:
+                        out.append(rec)
+                except (ValueError, IndexError):
+                    pass
+        i += 1
+    return out
+
+
+def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
+    n = xyz.n
+    types = xyz.types
+    i12 = [list(b) for b in xyz.bonds]
+    i13, i14, i15 = attach(i12)
+
+    # merged keyword view: keyfile overrides .prm
+    def kget(kw, default=None):
+        v = key.get(kw)
+        if v is None and ff.keywords is not None:
+            v = ff.keywords.get(kw)
+        return default if v is None else v
+
+    def khas(kw):
+        return key.has(kw) or (ff.keywords is not None and ff.keywords.has(kw))
+
+    def kfloat(kw, default):
+        v = kget(kw)
+        if v is None or not v.split():
+            return default
+        try:
+            return float(v.split()[0].replace("D", "E").replace("d", "e"))
+        except ValueError:
+            return default
+
+    scales = dict(ff.scales)
+    for kw in list(scales):
+        if key.has(kw):
+            scales[kw] = key.get_float(kw, scales[kw])
+
+    # --- multipoles
+    records = _key_multipoles(key) + list(ff.multipoles)
+    pole13, zax, xax, yax, polaxe, found = assign_multipoles(types, i12, i13, records)
+    pole = pole13_to_pme10(pole13)
+    zaxis = np.zeros((n, 4), np.int32)
+    zaxis[:, 0] = zax
+    zaxis[:, 1] = xax
+    zaxis[:, 2] = yax
+    zaxis[:, 3] = [LFRM[a] for a in polaxe]
+
+    # --- polarizabilities (kpolar.f:436-520)
+    polarize = dict(ff.polarize)
+    for kw, rest, _ in key.lines:
+        if kw == "POLARIZE":
+            rec = parse_polarize(rest)
+            if rec.typ > 0:
+                polarize[rec.typ] = rec
+    polarity = np.zeros(n)
+    thole = np.zeros(n)
+    for i in range(n):
+        r = polarize.get(int(types[i]))
+        if r is not None:
+            polarity[i] = r.alpha
+            thole[i] = max(0.0, r.thole)
+    pdamp = polarity ** (1.0 / 6.0)
+    utypes = sorted(set(int(t) for t in types))
+    tindex = {t: k for k, t in enumerate(utypes)}
+    jpolar = np.array([tindex[int(t)] for t in types], np.int32)
+    nj = len(utypes)
+    athl = np.array([max(0.0, polarize[t].thole) if t in polarize else 0.0 for t in utypes])
+    thlval = np.minimum.outer(athl, athl)
+    mx = np.maximum.outer(athl, athl)
+    thlval = np.where(thlval == 0.0, mx, thlval)
+    polpair = list(ff.polpair)
+    for kw, rest, _ in key.lines:
+        if kw == "POLPAIR":
+            t = rest.split()
+            polpair.append((int(t[0]), int(t[1]), float(t[2]), float(t[3]) if len(t) > 3 else 0.0))
+    for ia, ib, thl, _thd in polpair:
+        if ia in tindex and ib in tindex:
+            thlval[tindex[ia], tindex[ib]] = max(thl, 0.0)
+            thlval[tindex[ib], tindex[ia]] = max(thl, 0.0)
+
+    gid, groups, p12, p13, p14 = polar_groups(types, i12, polarize)
+    lists = build_scale_lists(n, i12, i13, i14, i15, gid, groups, p12, p13, p14, scales)
+
+    # --- box (unitcell.f / lattice.f)
+    if xyz.box is not None:
+        a, b, c, al, be, ga = xyz.box
+    else:
+        a = key.get_float("A-AXIS", 0.0)
+        b = key.get_float("B-AXIS", 0.0) or a
+        c = key.get_float("C-AXIS", 0.0) or a
+        al, be, ga = key.get_float("ALPHA", 90.0), key.get_float("BETA", 90.0), key.get_float("GAMMA", 90.0)
+    use_bounds = a > 0
+
+    # --- cutoffs.f / kewald.f
+    use_ewald = khas("EWALD")
+    use_list = khas("NEIGHBOR-LIST") or khas("MPOLE-LIST")
+    ewaldcut = 7.0
+    mpolecut = 9.0 if use_bounds else 1.0e12
+    if khas("CUTOFF"):
+        ewaldcut = mpolecut = kfloat("CUTOFF", ewaldcut)
+    ewaldcut = kfloat("EWALD-CUTOFF", ewaldcut)
+    mpolecut = kfloat("MPOLE-CUTOFF", mpolecut)
+    usolvcut = kfloat("USOLVE-CUTOFF", 4.5)
+    lbuffer = kfloat("LIST-BUFFER", 2.0)
+    pbuffer = kfloat("LIST-BUFFER", 2.0)
+    if use_list and usolvcut > 0:
+        usolvcut = usolvcut - pbuffer    # cutoffs.f:227
+    # range the CUDA preconditioner actually applies: switchOff(USOLVE) + list buffer (precond.cu:30-31)
+    usolve_applied = usolvcut + pbuffer if usolvcut > 0 else 0.0
+    cutoff = ewaldcut if use_ewald else mpolecut
+
+    if not use_bounds:
+        # non-periodic: put the system in a box large enough that no image is ever within range
+        ext = float(np.max(np.abs(xyz.xyz))) if n else 1.0
+        a = b = c = 4.0 * (ext + 10.0)
+        if use_ewald:
+            a = b = c = 2.0 * (ext + ewaldcut)   # kewald.f:96-108
+        al = be = ga = 90.0
+    cell, recip = lattice(a, b, c, al, be, ga)
+    lvec = cell           # row i = lvec_i  (x = lvec1 . frac etc.)
+
+    aewald = 0.0
+    nfft = (0, 0, 0)
+    bsorder = 5
+    if use_ewald:
+        aewald = ewaldcof(ewaldcut)
+        aewald = kfloat("EWALD-ALPHA", aewald)
+        aewald = kfloat("PEWALD-ALPHA", aewald)
+        dens = 1.2 if use_bounds else 0.7
+        nfft = tuple(pme_grid_default(L, dens) for L in (a, b, c))
+        g = kget("PME-GRID")
+        if g is not None:
+            t = [int(v) for v in g.split()[:3]]
+            if len(t) == 1:
+                t = t * 3
+            # kewald.f rounds a requested size up to the 2-3-5 list
+            nfft = tuple(next((k for k in PME_GRID_SIZES if k >= v), PME_GRID_SIZES[-1]) for v in t)
+        bsorder = int(kfloat("PME-ORDER", 5))
+
+    def term(kw):
+        v = kget(kw)
+        return None if v is None else v.split()[0].upper() if v.split() else ""
+
+    use_mpole = bool(found.any())
+    use_polar = bool((polarity != 0).any())
+    only = [kw for kw in ("MULTIPOLETERM", "POLARIZETERM") if term(kw) == "ONLY"]
+    if only:
+        use_mpole = use_mpole and "MULTIPOLETERM" in only
+        use_polar = use_polar and "POLARIZETERM" in only
+    if term("MULTIPOLETERM") == "NONE":
+        use_mpole = False
+    if term("POLARIZETERM") == "NONE":
+        use_polar = False
+    poltyp = (kget("POLARIZATION", "MUTUAL").split() or ["MUTUAL"])[0].upper()
+
+    return System(
+        n=n, xyz=xyz.xyz.copy(), lvec=lvec, recip=recip, pole=pole, zaxis=zaxis,
+        polarity=polarity, thole=thole, pdamp=pdamp, jpolar=jpolar, thlval=thlval,
+        use_ewald=use_ewald, use_mpole=use_mpole, use_polar=use_polar,
+        aewald=aewald, nfft=nfft, bsorder=bsorder, ewald_cutoff=cutoff,
+        usolve_cutoff=usolve_applied, list_buffer=lbuffer,
+        poleps=kfloat("POLAR-EPS", 1.0e-6), politer=int(kfloat("POLAR-ITER", 100)),
+        poltyp=poltyp, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
+        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, **lists)
+
+
+def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017) -> System:
+    """Tile an orthogonal periodic System reps=(nx,ny,nz) times (BASELINE.md §4 synthetic boxes).
+    Index-valued arrays are offset per image; the PME grid is re-derived with the 1.2/A rule."""
+    nx, ny, nz = reps
+    m = nx * ny * nz
+    n0 = sys.n
+    a, b, c = np.diag(sys.lvec)
+    offs = np.array([(ix * a, iy * b, iz * c) for ix in range(nx) for iy in range(ny) for iz in range(nz)])
+    xyz = (sys.xyz[None, :, :] + offs[:, None, :]).reshape(-1, 3)
+    # recentre so the replicated box spans the same convention (origin-centred like Tinker boxes)
+    xyz = xyz - np.array([(nx - 1) * a, (ny - 1) * b, (nz - 1) * c]) * 0.5
+    if jitter:
+        rng = np.random.default_rng(seed)
+        # rigid per-molecule jitter would need molecule ids; per-atom jitter is what BASELINE.md specifies
+        xyz = xyz + rng.uniform(-jitter, jitter, xyz.shape)
+    shift = (np.arange(m) * n0)
+
+    def tile_idx(arr):
+        if arr.size == 0:
+            return arr.copy()
+        return (arr[None, :, :] + shift[:, None, None]).reshape(-1, arr.shape[1]).astype(np.int32)
+
+    def tile(arr):
+        return np.concatenate([arr] * m, axis=0)
+
+    z = sys.zaxis
+    zt = np.tile(z, (m, 1)).reshape(m, n0, 4)
+    sh = shift[:, None]
+    zt[:, :, 0] = np.where(z[None, :, 0] >= 0, z[None, :, 0] + sh, -1)
+    zt[:, :, 1] = np.where(z[None, :, 1] >= 0, z[None, :, 1] + sh, -1)
+    ysign = np.sign(z[:, 2])
+    zt[:, :, 2] = np.where(z[None, :, 2] != 0, ysign[None, :] * (np.abs(z[None, :, 2]) + sh), 0)
+    La, Lb, Lc = nx * a, ny * b, nz * c
+    cell, recip = lattice(La, Lb, Lc)
+    nfft = tuple(pme_grid_default(L) for L in (La, Lb, Lc)) if sys.use_ewald else (0, 0, 0)
+    bonds = None
+    if sys.bonds is not None and m * n0 <= 2_000_000:
+        bonds = [[k + s for k in bl] for s in shift for bl in sys.bonds]
+    return System(
+        n=m * n0, xyz=xyz, lvec=cell, recip=recip, pole=tile(sys.pole), zaxis=zt.reshape(-1, 4).astype(np.int32),
+        polarity=tile(sys.polarity), thole=tile(sys.thole), pdamp=tile(sys.pdamp), jpolar=tile(sys.jpolar),
+        thlval=sys.thlval.copy(),
+        mexclude=tile_idx(sys.mexclude), mexclude_scale=tile(sys.mexclude_scale),
+        dpexclude=tile_idx(sys.dpexclude), dpexclude_scale=tile(sys.dpexclude_scale),
+        uexclude=tile_idx(sys.uexclude), uexclude_scale=tile(sys.uexclude_scale),
+        mdpuexclude=tile_idx(sys.mdpuexclude), mdpuexclude_scale=tile(sys.mdpuexclude_scale),
+        use_ewald=sys.use_ewald, use_mpole=sys.use_mpole, use_polar=sys.use_polar, aewald=sys.aewald, nfft=nfft,
+        bsorder=sys.bsorder, ewald_cutoff=sys.ewald_cutoff, usolve_cutoff=sys.usolve_cutoff,
+        list_buffer=sys.list_buffer, poleps=sys.poleps, politer=sys.politer, uaccel=sys.uaccel,
+        pcgprec=sys.pcgprec, pcgguess=sys.pcgguess, pcgpeek=sys.pcgpeek, poltyp=sys.poltyp,
+        electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
+        names=(sys.names * m) if sys.names is not None else None, bonds=bonds,
+        title=f"{sys.title} x{nx}x{ny}x{nz}")
+
+
+# ----------------------------------------------------------------------------
+# blob (de)serialisation: the one file the GPU box needs per system
+# ----------------------------------------------------------------------------
+_ARRAY_FIELDS = ("xyz", "lvec", "recip", "pole", "zaxis", "polarity", "thole", "pdamp", "jpolar", "thlval",
+                 "mexclude", "mexclude_scale", "dpexclude", "dpexclude_scale", "uexclude", "uexclude_scale",
+                 "mdpuexclude", "mdpuexclude_scale", "types")
+_SCALAR_FIELDS = ("n", "use_ewald", "use_mpole", "use_polar", "aewald", "bsorder", "ewald_cutoff", "usolve_cutoff",
+                  "list_buffer", "poleps", "politer", "uaccel", "pcgprec", "pcgguess", "pcgpeek", "poltyp", "electric",
+                  "dielec", "title")
+
+
+def save_system(path: str, sys: System) -> None:
+    d = {k: getattr(sys, k) for k in _ARRAY_FIELDS if getattr(sys, k) is not None}
+    for k in _SCALAR_FIELDS:
+        d["_" + k] = np.array(getattr(sys, k))
+    d["_nfft"] = np.array(sys.nfft, np.int64)
+    np.savez_compressed(path, **d)
+
+
+def load_system(path: str) -> System:
+    z = np.load(path, allow_pickle=False)
+    kw = {k: z[k] for k in _ARRAY_FIELDS if k in z.files}
+    for k in _SCALAR_FIELDS:
+        v = z["_" + k]
+        kw[k] = v.item() if v.dtype.kind != "U" else str(v)
+    kw["nfft"] = tuple(int(v) for v in z["_nfft"])
+    kw.setdefault("types", None)
+    return System(**kw)
