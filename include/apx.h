@@ -1,0 +1,145 @@
+/* apx.h -- C ABI of the B200-native AMOEBA polarizable-electrostatics back end.
+ *
+ * Drop-in boundary.  The reference dispatches every operator of this
+ * path through TINKER_FCALL2(acc, cu, F, args...) to a free function F_cu(...) that reads
+ * process-global device arrays (include/tool/externfunc.h:10-77).  This library exposes
+ * the same operators over an opaque context instead of globals; INTEGRATION.md shows
+ * the ~200-line adapter TU that defines the reference's *_cu symbols on top of it.
+ *
+ * Each entry point cites the reference interface it replaces.  All pointers are plain
+ * host pointers unless the name ends in _dev.  Arrays are in the CALLER's atom order
+ * (the library keeps its own spatially sorted copies).  Return value: 0 on success,
+ * non-zero on error with the message available from apx_last_error() -- the C-ABI
+ * image of the reference's TINKER_THROW / FatalError (include/tool/error.h:16-45).
+ *
+ * There is no CPU fallback: every compute entry point fails if no CUDA device is usable.
+ */
+#ifndef APX_H
+#define APX_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* calc:: flags, include/tool/rcman.h:107-133 */
+enum {
+   APX_ENERGY = 0x010,
+   APX_GRAD = 0x020,
+   APX_VIRIAL = 0x040,
+   APX_ANALYZ = 0x080,
+   APX_V0 = 0x010,
+   APX_V1 = 0x070,
+   APX_V3 = 0x090,
+   APX_V4 = 0x030,
+   APX_V5 = 0x020,
+   APX_V6 = 0x060
+};
+
+/* What mpoleData / epolarData / mdpuscaleData / pmeData upload
+ * (src/elec.cpp:54-500, src/amoeba/epolar.cpp:25-511, src/pme.cpp:154-217). */
+typedef struct apx_system {
+   int n;
+   const double* xyz;      /* [n][3]  atom.h x,y,z */
+   double lvec[9];         /* box.h lvec1..3 (row major) */
+   const double* pole;     /* [n][10] local-frame multipoles, MPL_PME order (mpole.h:6-15) */
+   const int* zaxis;       /* [n][4]  LocalFrame {zaxis, xaxis, yaxis(signed, 1-based), polaxe} */
+   const double* polarity; /* [n] */
+   const double* thole;    /* [n] */
+   const double* pdamp;    /* [n] */
+   const int* jpolar;      /* [n] */
+   int njpolar;
+   const double* thlval;   /* [njpolar][njpolar] */
+   int nmdpu;              /* fused exclusion list, pairs i<k */
+   const int* mdpu_ik;     /* [nmdpu][2] */
+   const double* mdpu_scale; /* [nmdpu][4]  m, d, p, u */
+   int use_ewald, use_mpole, use_polar;
+   int poltyp_mutual;      /* 1 MUTUAL, 0 DIRECT */
+   double aewald;
+   int nfft[3];
+   int bsorder;            /* only 5 is built */
+   double cutoff;          /* switchOff(EWALD) or switchOff(MPOLE) */
+   double usolve_cutoff;   /* range the sparse preconditioner applies, <=0: diagonal */
+   double list_buffer;
+   double poleps;
+   int politer;
+   double uaccel;          /* udiag */
+   int pcgprec, pcgguess;
+   double pcgpeek;
+   double electric, dielec;
+} apx_system;
+
+typedef struct apx_ctx apx_ctx;
+
+typedef struct apx_energy_result {
+   double em, ep, esum;
+   double virial[9];
+   int nem, nep;
+   int pcg_iterations;
+   double pcg_eps;         /* final RMS residual in Debye */
+} apx_energy_result;
+
+/* timing / counters of the most recent operator call, CUDA events on the library stream */
+typedef struct apx_stats {
+   float ms_induce, ms_energy, ms_list;
+   float ms_ufield_real;   /* mean device time of the real-space ufield tile kernel, last induce() */
+   int pcg_iterations;
+   int kernel_launches;    /* launches of this library's own kernels since apx_stats_reset */
+   int list_rebuilds;
+   int ntiles_m, ntiles_u; /* 32x32 tiles in the multipole / preconditioner lists */
+   long long npairs_m;     /* pairs inside the real-space cutoff at the last list build, -1 if not counted */
+} apx_stats;
+
+const char* apx_last_error(void);
+const char* apx_version(void);            /* "apx <n> (float|double)" */
+int apx_precision_bytes(void);            /* sizeof(real): 4 mixed build, 8 double build */
+
+/* initialize()/finish(): src/rcman.cpp:20-80 (deviceData ALLOC|INIT / DEALLOC) */
+int apx_create(const apx_system* sys, int device, apx_ctx** out);
+void apx_destroy(apx_ctx* ctx);
+
+/* copyPosToXyz + nblistRefresh: src/nblist.cpp:521-531, spatialCheck_cu (src/cu/spatial.cu:943-960) */
+int apx_set_positions(apx_ctx* ctx, const double* xyz);
+/* box change (Monte-Carlo barostat): src/box.cpp boxSetCurrent */
+int apx_set_box(apx_ctx* ctx, const double lvec[9]);
+
+/* mpoleInit: chkpole_cu, rotpole_cu, rpoleToCmp_cu (src/amoeba/mpole.cpp:28-58) */
+int apx_mpole_init(apx_ctx* ctx);
+int apx_get_rpole(apx_ctx* ctx, double* rpole /* [n][10] */);
+
+/* dfield(field, fieldp): src/amoeba/field.cpp:56-64 */
+int apx_dfield(apx_ctx* ctx, double* field, double* fieldp);
+/* ufield(uind, uinp, field, fieldp): src/amoeba/field.cpp:111-117 */
+int apx_ufield(apx_ctx* ctx, const double* uind, const double* uinp, double* field, double* fieldp);
+/* sparsePrecondApply / diagPrecond: src/amoeba/induce.cpp:12-25 */
+int apx_precond(apx_ctx* ctx, const double* rsd, const double* rsdp, double* zrsd, double* zrsdp);
+
+/* induce(uind, uinp) -> induceMutualPcg1_cu: src/amoeba/induce.cpp:108-113, src/cu/amoeba/pcg.cu:14 */
+int apx_induce(apx_ctx* ctx);
+int apx_get_uind(apx_ctx* ctx, double* uind, double* uinp);
+int apx_get_udir(apx_ctx* ctx, double* udir, double* udirp);
+
+/* energy(vers) restricted to the electrostatic terms: empole+epolar or fused emplar
+ * (src/energy.cpp:87-114,262-270,319-448); includes torque() and the fixed-point reductions. */
+int apx_energy(apx_ctx* ctx, int vers, apx_energy_result* out);
+/* empole(vers), epolar(vers): src/amoeba/empole.cpp:81-138, src/amoeba/epolar.cpp:574-649 */
+int apx_empole(apx_ctx* ctx, int vers, apx_energy_result* out);
+int apx_epolar(apx_ctx* ctx, int vers, apx_energy_result* out);
+/* copyGradient: src/egvop.cpp:64-111 (fixed -> double, caller's order) */
+int apx_get_gradient(apx_ctx* ctx, double* grad /* [n][3] */);
+
+/* PME operators exposed for parity tests: gridMpole/gridUind + fftfront + pmeConv + fftback
+ * + fphiMpole/fphiUind2 (src/pme.cpp:229-351).  Output in fractional coordinates. */
+int apx_pme_mpole_fphi(apx_ctx* ctx, double* fphi /* [n][20] */);
+int apx_pme_uind_fphi(apx_ctx* ctx, const double* uind, const double* uinp, double* fdip_phi1 /* [n][10] */,
+   double* fdip_phi2 /* [n][10] */);
+
+int apx_get_stats(apx_ctx* ctx, apx_stats* out);
+int apx_stats_reset(apx_ctx* ctx);
+/* cudaStream_t the library launches on (for callers that time with their own events) */
+void* apx_stream(apx_ctx* ctx);
+int apx_synchronize(apx_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's operator interface for the AMOEBA electrostatics path,
+bound to the C ABI of libapx (include/apx.h) through ctypes.
+
+Names follow the reference front-ends so that parity tests read like the reference's own:
+`energy(vers)` (src/energy.cpp:319), `empole(vers)` (src/amoeba/empole.cpp:81), `epolar(vers)`
+(src/amoeba/epolar.cpp:574), `induce()` (src/amoeba/induce.cpp:108), `dfield()` / `ufield()`
+(src/amoeba/field.cpp:56,111), `sparsePrecondApply` (src/amoeba/induce.cpp:21), and the `calc::`
+version flags (include/tool/rcman.h:107-133).
+
+There is NO CPU fallback: constructing an `Amoeba` without the compiled library or without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .params import System
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class calc:
+    energy, grad, virial, analyz = 0x10, 0x20, 0x40, 0x80
+    v0 = energy
+    v1 = energy + grad + virial
+    v3 = energy + analyz
+    v4 = energy + grad
+    v5 = grad
+    v6 = grad + virial
+
+
+class ApxError(RuntimeError):
+    """C-ABI image of the reference's FatalError (include/tool/error.h:16-45)."""
+
+
+class _ApxSystem(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("xyz", C.POINTER(C.c_double)), ("lvec", C.c_double * 9),
+        ("pole", C.POINTER(C.c_double)), ("zaxis", C.POINTER(C.c_int)),
+        ("polarity", C.POINTER(C.c_double)), ("thole", C.POINTER(C.c_double)), ("pdamp", C.POINTER(C.c_double)),
+        ("jpolar", C.POINTER(C.c_int)), ("njpolar", C.c_int), ("thlval", C.POINTER(C.c_double)),
+        ("nmdpu", C.c_int), ("mdpu_ik", C.POINTER(C.c_int)), ("mdpu_scale", C.POINTER(C.c_double)),
+        ("use_ewald", C.c_int), ("use_mpole", C.c_int), ("use_polar", C.c_int), ("poltyp_mutual", C.c_int),
+        ("aewald", C.c_double), ("nfft", C.c_int * 3), ("bsorder", C.c_int),
+        ("cutoff", C.c_double), ("usolve_cutoff", C.c_double), ("list_buffer", C.c_double),
+        ("poleps", C.c_double), ("politer", C.c_int), ("uaccel", C.c_double),
+        ("pcgprec", C.c_int), ("pcgguess", C.c_int), ("pcgpeek", C.c_double),
+        ("electric", C.c_double), ("dielec", C.c_double),
+    ]
+
+
+class EnergyResult(C.Structure):
+    _fields_ = [("em", C.c_double), ("ep", C.c_double), ("esum", C.c_double), ("virial", C.c_double * 9),
+                ("nem", C.c_int), ("nep", C.c_int), ("pcg_iterations", C.c_int), ("pcg_eps", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
+                ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
+                ("ntiles_m", C.c_int), ("ntiles_u", C.c_int), ("npairs_m", C.c_longlong)]
+
+
+_LIBS = {}
+_DP = C.POINTER(C.c_double)
+
+
+def library_path(precision="mixed"):
+    return os.path.join(HERE, "libapx.so" if precision == "mixed" else "libapx_f64.so")
+
+
+def load_library(precision="mixed"):
+    """dlopen the C-ABI library; raises (never falls back) when it has not been built."""
+    if precision in _LIBS:
+        return _LIBS[precision]
+    path = library_path(precision)
+    if not os.path.isfile(path):
+        raise ApxError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback for the CUDA path)")
+    lib = C.CDLL(path)
+    lib.apx_last_error.restype = C.c_char_p
+    lib.apx_version.restype = C.c_char_p
+    lib.apx_stream.restype = C.c_void_p
+    lib.apx_stream.argtypes = [C.c_void_p]
+    lib.apx_create.argtypes = [C.POINTER(_ApxSystem), C.c_int, C.POINTER(C.c_void_p)]
+    lib.apx_destroy.argtypes = [C.c_void_p]
+    lib.apx_destroy.restype = None
+    for name, args in {
+        "apx_set_positions": [_DP], "apx_set_box": [_DP], "apx_mpole_init": [], "apx_get_rpole": [_DP],
+        "apx_dfield": [_DP, _DP], "apx_ufield": [_DP, _DP, _DP, _DP], "apx_precond": [_DP, _DP, _DP, _DP],
+        "apx_induce": [], "apx_get_uind": [_DP, _DP], "apx_get_udir": [_DP, _DP],
+        "apx_energy": [C.c_int, C.POINTER(EnergyResult)], "apx_empole": [C.c_int, C.POINTER(EnergyResult)],
+        "apx_epolar": [C.c_int, C.POINTER(EnergyResult)], "apx_get_gradient": [_DP],
+        "apx_pme_mpole_fphi": [_DP], "apx_pme_uind_fphi": [_DP, _DP, _DP, _DP],
+        "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
+    }.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p] + args
+        fn.restype = C.c_int
+    _LIBS[precision] = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_DP)
+
+
+class Amoeba:
+    """One electrostatics context on one GPU (the reference's initialize()/finish() pair)."""
+
+    def __init__(self, system: System, precision: str = "mixed", device: int = 0):
+        self.lib = load_library(precision)
+        self.system = system
+        self.n = system.n
+        self.precision = precision
+        s = _ApxSystem()
+        keep = []
+
+        def f64(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return _dp(a)
+
+        def i32(a):
+            a = np.ascontiguousarray(a, dtype=np.int32)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int))
+
+        s.n = system.n
+        s.xyz = f64(system.xyz)
+        s.lvec = (C.c_double * 9)(*np.asarray(system.lvec, float).ravel())
+        s.pole = f64(system.pole)
+        s.zaxis = i32(system.zaxis)
+        s.polarity = f64(system.polarity)
+        s.thole = f64(system.thole)
+        s.pdamp = f64(system.pdamp)
+        s.jpolar = i32(system.jpolar)
+        s.njpolar = int(system.thlval.shape[0])
+        s.thlval = f64(system.thlval)
+        s.nmdpu = int(system.mdpuexclude.shape[0])
+        s.mdpu_ik = i32(system.mdpuexclude.reshape(-1, 2) if s.nmdpu else np.zeros((1, 2)))
+        s.mdpu_scale = f64(system.mdpuexclude_scale.reshape(-1, 4) if s.nmdpu else np.ones((1, 4)))
+        s.use_ewald, s.use_mpole, s.use_polar = int(system.use_ewald), int(system.use_mpole), int(system.use_polar)
+        s.poltyp_mutual = 0 if system.poltyp == "DIRECT" else 1
+        s.aewald = system.aewald
+        s.nfft = (C.c_int * 3)(*[int(v) for v in system.nfft])
+        s.bsorder = system.bsorder
+        s.cutoff = float(system.ewald_cutoff)
+        s.usolve_cutoff = float(system.usolve_cutoff)
+        s.list_buffer = float(system.list_buffer)
+        s.poleps, s.politer, s.uaccel = system.poleps, system.politer, system.uaccel
+        s.pcgprec, s.pcgguess, s.pcgpeek = int(system.pcgprec), int(system.pcgguess), system.pcgpeek
+        s.electric, s.dielec = system.electric, system.dielec
+        self.ctx = C.c_void_p()
+        rc = self.lib.apx_create(C.byref(s), device, C.byref(self.ctx))
+        if rc != 0:
+            msg = self.lib.apx_last_error().decode()
+            if self.ctx:
+                self.lib.apx_destroy(self.ctx)
+                self.ctx = None
+            raise ApxError(msg)
+        self.last = None
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.apx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise ApxError(self.lib.apx_last_error().decode())
+
+    def _out(self, *shape):
+        return np.zeros(shape, dtype=np.float64)
+
+    # -- state
+    def set_positions(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._chk(self.lib.apx_set_positions(self.ctx, _dp(xyz)))
+
+    def set_box(self, lvec):
+        lvec = np.ascontiguousarray(lvec, dtype=np.float64)
+        self._chk(self.lib.apx_set_box(self.ctx, _dp(lvec)))
+
+    def mpoleInit(self):
+        self._chk(self.lib.apx_mpole_init(self.ctx))
+
+    def rpole(self):
+        out = self._out(self.n, 10)
+        self._chk(self.lib.apx_get_rpole(self.ctx, _dp(out)))
+        return out
+
+    # -- fields / solver
+    def dfield(self):
+        a, b = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_dfield(self.ctx, _dp(a), _dp(b)))
+        return a, b
+
+    def ufield(self, uind, uinp):
+        uind = np.ascontiguousarray(uind, dtype=np.float64)
+        uinp = np.ascontiguousarray(uinp, dtype=np.float64)
+        a, b = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_ufield(self.ctx, _dp(uind), _dp(uinp), _dp(a), _dp(b)))
+        return a, b
+
+    def sparsePrecondApply(self, rsd, rsdp):
+        rsd = np.ascontiguousarray(rsd, dtype=np.float64)
+        rsdp = np.ascontiguousarray(rsdp, dtype=np.float64)
+        a, b = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_precond(self.ctx, _dp(rsd), _dp(rsdp), _dp(a), _dp(b)))
+        return a, b
+
+    def induce(self):
+        self._chk(self.lib.apx_induce(self.ctx))
+        return self.uind()
+
+    def uind(self):
+        a, b = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_get_uind(self.ctx, _dp(a), _dp(b)))
+        return a, b
+
+    def udir(self):
+        a, b = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_get_udir(self.ctx, _dp(a), _dp(b)))
+        return a, b
+
+    # -- energies
+    def _energy(self, fn, vers):
+        r = EnergyResult()
+        self._chk(fn(self.ctx, int(vers), C.byref(r)))
+        out = dict(em=r.em, ep=r.ep, esum=r.esum, virial=np.array(list(r.virial)).reshape(3, 3), nem=r.nem, nep=r.nep,
+                   pcg_iterations=r.pcg_iterations, pcg_eps=r.pcg_eps)
+        if vers & calc.grad:
+            out["grad"] = self.gradient()
+        self.last = out
+        return out
+
+    def energy(self, vers=calc.v1):
+        return self._energy(self.lib.apx_energy, vers)
+
+    def empole(self, vers=calc.v1):
+        return self._energy(self.lib.apx_empole, vers)
+
+    def epolar(self, vers=calc.v1):
+        return self._energy(self.lib.apx_epolar, vers)
+
+    def gradient(self):
+        g = self._out(self.n, 3)
+        self._chk(self.lib.apx_get_gradient(self.ctx, _dp(g)))
+        return g
+
+    # -- PME operators (fractional potentials), for parity tests
+    def pme_mpole_fphi(self):
+        out = self._out(self.n, 20)
+        self._chk(self.lib.apx_pme_mpole_fphi(self.ctx, _dp(out)))
+        return out
+
+    def pme_uind_fphi(self, uind, uinp):
+        uind = np.ascontiguousarray(uind, dtype=np.float64)
+        uinp = np.ascontiguousarray(uinp, dtype=np.float64)
+        a, b = self._out(self.n, 10), self._out(self.n, 10)
+        self._chk(self.lib.apx_pme_uind_fphi(self.ctx, _dp(uind), _dp(uinp), _dp(a), _dp(b)))
+        return a, b
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.lib.apx_get_stats(self.ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def stats_reset(self):
+        self._chk(self.lib.apx_stats_reset(self.ctx))
+
+    def synchronize(self):
+        self._chk(self.lib.apx_synchronize(self.ctx))

@@ -1,0 +1,211 @@
+// Internal declarations shared by the CUDA translation units of libapx.
+// Layout of everything that lives in HBM is described in DESIGN.md §3.
+#pragma once
+#include "apx.h"
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef APX_DOUBLE
+typedef double real;
+typedef double2 real2;
+typedef double4 real4;
+typedef cufftDoubleComplex cplx;
+#define APX_PREC_NAME "double"
+#else
+typedef float real;
+typedef float2 real2;
+typedef float4 real4;
+typedef cufftComplex cplx;
+#define APX_PREC_NAME "float"
+#endif
+
+typedef unsigned long long fixed_t;   // 2^32 fixed point, as include/ff/precision.h:68-106
+#define APX_FIXED_SCALE 4294967296.0  // 0x100000000
+
+struct real3 {
+   real x, y, z;
+};
+
+#define APX_WARP 32
+#define APX_BLOCK 128                 // 4 warps per CTA for the tile kernels
+
+struct ApxError : std::runtime_error {
+   using std::runtime_error::runtime_error;
+};
+
+void apx_throw(const char* file, int line, const std::string& msg);
+#define APX_THROW(msg) apx_throw(__FILE__, __LINE__, (msg))
+#define CUDA_CHECK(expr)                                                                           \
+   do {                                                                                            \
+      cudaError_t e__ = (expr);                                                                    \
+      if (e__ != cudaSuccess)                                                                      \
+         apx_throw(__FILE__, __LINE__, std::string(#expr) + ": " + cudaGetErrorString(e__));       \
+   } while (0)
+#define CUFFT_CHECK(expr)                                                                          \
+   do {                                                                                            \
+      cufftResult r__ = (expr);                                                                    \
+      if (r__ != CUFFT_SUCCESS)                                                                    \
+         apx_throw(__FILE__, __LINE__, std::string(#expr) + ": cufft error " + std::to_string(r__)); \
+   } while (0)
+
+template <class T>
+struct DevBuf {
+   T* p = nullptr;
+   size_t cap = 0;
+   void ensure(size_t n)
+   {
+      if (n <= cap)
+         return;
+      if (p)
+         cudaFree(p);
+      p = nullptr;
+      size_t want = n + n / 8 + 64;
+      CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
+      cap = want;
+   }
+   void release()
+   {
+      if (p)
+         cudaFree(p);
+      p = nullptr;
+      cap = 0;
+   }
+   operator T*() const { return p; }
+};
+
+// Box: orthogonal fast path + general triclinic image via reciprocal vectors.
+struct Box {
+   real lx, ly, lz;         // orthogonal edge lengths
+   real ilx, ily, ilz;
+   real l[9];               // lvec rows
+   real r[9];               // recip rows
+   int orthogonal;
+   real volume;
+};
+
+// 32x32 tile list: tile t pairs the 32 atoms of sorted block iblk[t] with the 32 sorted
+// atom indices katom[32*t .. 32*t+31] (-1 = padding).  Tiles of one i-block are contiguous.
+struct TileList {
+   real cutoff = 0, buffer = 0;
+   int ntiles = 0;
+   DevBuf<int> iblk;
+   DevBuf<int> katom;
+   DevBuf<int> counts;      // per i-block number of k atoms (pass A)
+   DevBuf<int> offsets;     // per i-block first tile
+};
+
+struct PairExcl {           // exclusion pair in SORTED indices with (scale-1) factors
+   int i, k;
+   real m, d, p, u;
+};
+
+struct apx_ctx {
+   int device = 0;
+   cudaStream_t stream = nullptr;
+   int n = 0, nblk = 0, npad = 0;
+   int sm_count = 148;
+   apx_system opt;                       // scalar options (pointers invalid after create)
+   real f_elec = 0;
+   Box box;
+
+   // ---- caller-order static data
+   DevBuf<double> xyz_d;                 // [n][3] positions as given (f64)
+   DevBuf<double> xyz_ref;               // positions at the last list build
+   DevBuf<int> zaxis;                    // [n][4]
+   DevBuf<real> pole;                    // [n][10] local frame (chkpole may flip signs)
+   DevBuf<real> polarity_o, thole_o, pdamp_o;
+   DevBuf<int> jpolar_o;
+   DevBuf<real> thlval;
+   int thole_table = 0;                  // 1: per-pair lookup needed (polpair present)
+   DevBuf<int> excl_ik;                  // [nx][2] caller order
+   DevBuf<real> excl_sc;                 // [nx][4]
+   int nexcl = 0;
+   int nexcl_u = 0;                      // exclusions whose u-scale != 1 (none in stock AMOEBA)
+
+   // ---- sorted-order data (rebuilt with the list)
+   DevBuf<int> perm, inv;                // perm[s] = caller index, inv[i] = sorted slot
+   DevBuf<unsigned> sortkey, sortkey2;
+   DevBuf<int> permtmp;
+   DevBuf<char> cubtmp;
+   size_t cubtmp_bytes = 0;
+   DevBuf<real4> posd;                   // {x,y,z wrapped, pdamp}
+   DevBuf<real4> tpj;                    // {thole, polarity, 1/polarity, jpolar bits}
+   DevBuf<real4> mp0, mp1;               // rpole {c,dx,dy,dz}, {qxx,qxy,qxz,qyy}
+   DevBuf<real2> mp2;                    // {qyz,qzz}
+   DevBuf<real4> blk_ctr, blk_ext;       // block bounding boxes
+   DevBuf<PairExcl> excl_s;              // exclusions in sorted indices
+   TileList mlist, ulist;
+   int list_valid = 0;
+   DevBuf<int> flags;                    // device flags: [0] rebuild-needed, [1] pcg done, [2] iter ...
+   int* flags_h = nullptr;               // pinned mirror
+
+   // ---- fields / CG vectors, sorted order, [npad][3]
+   DevBuf<real> field, fieldp, udir, udirp, uind, uinp;
+   DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
+   DevBuf<double> scal;                  // PCG scalars (sum, sump, a, ap, sum1, sump1, epsd, epsp ...)
+   double* scal_h = nullptr;             // pinned
+   int last_iters = 6;
+
+   // ---- PME
+   int nfft1 = 0, nfft2 = 0, nfft3 = 0;
+   cufftHandle plan = 0;
+   int plan_ok = 0;
+   DevBuf<cplx> qgrid;
+   DevBuf<real> qfac;                    // influence function (expterm of pmeConv)
+   DevBuf<real> bsmod1, bsmod2, bsmod3;
+   DevBuf<real> fphi;                    // [n][20] permanent, sorted order
+   DevBuf<real> fmp;                     // [n][10]
+   DevBuf<real> fphid, fphip, fphidp;    // [n][10],[n][10],[n][20]
+   int mpole_pme_valid = 0;              // fphi/fmp correspond to current positions
+   double recip_e_h = 0;
+
+   // ---- energy / gradient accumulators (sorted order)
+   DevBuf<fixed_t> gx, gy, gz;
+   DevBuf<real> trq;                     // [npad][3] torques as real (input of the torque kernel)
+   DevBuf<fixed_t> trqf;                 // [npad][3] fixed-point torque accumulators
+   DevBuf<real4> mpx_a, mpx_b;           // scratch multipole heads for the cross virial
+   DevBuf<cplx> qgrid2;
+   DevBuf<fixed_t> ebuf;                 // [0]=em [1]=ep ; [2..7] vir  (fixed point)
+   DevBuf<double> dbuf;                  // double accumulators (recip energies, virials)
+   DevBuf<int> cnt;                      // nem, nep
+
+   // ---- io staging
+   DevBuf<double> io_a, io_b, io_c, io_d;
+   double* pin_a = nullptr;              // pinned staging for host<->device in e2e paths
+   size_t pin_bytes = 0;
+
+   // ---- stats
+   apx_stats stats;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+   int mpole_inited = 0;
+   int induced_valid = 0;
+};
+
+#define APX_COUNT_LAUNCH(ctx) ((ctx)->stats.kernel_launches++)
+
+// ---- nblist.cu
+void apx_list_refresh(apx_ctx* c, bool force);
+void apx_update_sorted_positions(apx_ctx* c);
+// ---- frames.cu
+void apx_rotpole(apx_ctx* c);
+void apx_torque(apx_ctx* c, bool do_v);
+// ---- pme.cu
+void apx_pme_setup(apx_ctx* c);
+void apx_pme_destroy(apx_ctx* c);
+void apx_pme_mpole(apx_ctx* c, bool want_ev);                   // fills fmp, fphi (and recip E/virial in dbuf)
+void apx_pme_ufield(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp, const double* beta, real* conj_out_d,
+   real* conj_out_p);                                            // recip + self part of ufield, ASSIGNS fd/fp
+void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool full20);
+void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
+// ---- field.cu
+void apx_dfield_real(apx_ctx* c, real* fd, real* fp);
+void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
+void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp, bool diag_done);
+// ---- pcg.cu
+void apx_induce_impl(apx_ctx* c);
+// ---- mplar.cu
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out);

@@ -1,0 +1,535 @@
+// Real-space field kernels over the 32x32 tile list: permanent field (dfield), mutual field of a
+// dipole pair (ufield, the CG operator) and the short-range preconditioner.
+// They stand where dfield_cu1 / ufield_cu1 / sparsePrecond_cu1 stand in the reference
+// (src/cu/amoeba/field.cu:37-137, precond.cu:13-43) but are organised differently:
+//   * a warp walks a contiguous run of tiles; the i-block's 32 atoms stay in registers across all
+//     tiles of that block and are flushed once, k-atoms travel round the warp by shuffle together
+//     with their accumulators, so a tile costs 32 lane-rotations and one k-side atomic flush;
+//   * every pair in a tile is evaluated with all exclusion scales = 1 (no per-pair bit masks);
+//     the few excluded pairs are corrected afterwards by one thread per listed pair with
+//     (scale-1) non-Ewald terms -- B_n = (s-1) lambda_n rr_n in the notation of pairmath.cuh;
+//   * because d- and p-scaling only differ on excluded pairs, the tile pass accumulates ONE
+//     permanent field; the d/p split is made by the exclusion pass.
+#include "apx_internal.h"
+#include "pairmath.cuh"
+
+#define FULL 0xffffffffu
+#define SHF(v, src) __shfl_sync(FULL, (v), (src))
+
+namespace {
+__device__ __forceinline__ int as_int(real w)
+{
+#ifdef APX_DOUBLE
+   return (int)__double_as_longlong(w);
+#else
+   return __float_as_int(w);
+#endif
+}
+
+struct WarpRange {
+   int t0, t1;
+};
+__device__ __forceinline__ WarpRange warp_tiles(int ntiles)
+{
+   int nw = gridDim.x * (blockDim.x >> 5);
+   int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   int per = (ntiles + nw - 1) / nw;
+   WarpRange r;
+   r.t0 = min(ntiles, w * per);
+   r.t1 = min(ntiles, r.t0 + per);
+   return r;
+}
+
+// -------------------------------------------------------------------------------------------
+// ufield: field of (ud, up) at every atom, Ewald real space or plain Thole-damped Coulomb
+// -------------------------------------------------------------------------------------------
+template <bool EWALD, bool TABLE>
+__global__ void __launch_bounds__(APX_BLOCK) k_ufield_tiles(int n, int ntiles, Box box, real cut2, real aewald,
+   const int* __restrict__ iblk, const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const real* __restrict__ thlval, int nj, const real* __restrict__ ud, const real* __restrict__ up, real* __restrict__ fd,
+   real* __restrict__ fp)
+{
+   const int lane = threadIdx.x & 31;
+   WarpRange wr = warp_tiles(ntiles);
+   int cur = -1, si = 0;
+   real4 pi;
+   real thi = 0;
+   int jpi = 0;
+   V3 udi, upi, fdi, fpi;
+   for (int t = wr.t0; t < wr.t1; ++t) {
+      int ib = iblk[t];
+      if (ib != cur) {
+         if (cur >= 0 && si < n) {
+            atomic_real3(fd, si, fdi);
+            atomic_real3(fp, si, fpi);
+         }
+         cur = ib;
+         si = ib * 32 + lane;
+         int sl = min(si, n - 1);
+         pi = posd[sl];
+         real4 q = tpj[sl];
+         thi = q.x;
+         jpi = as_int(q.w);
+         udi = v3(ud[3 * sl], ud[3 * sl + 1], ud[3 * sl + 2]);
+         upi = v3(up[3 * sl], up[3 * sl + 1], up[3 * sl + 2]);
+         fdi = v3(0, 0, 0);
+         fpi = v3(0, 0, 0);
+      }
+      int sk = katom[t * 32 + lane];
+      int sl = max(sk, 0);
+      real4 pk = posd[sl];
+      real4 qk = tpj[sl];
+      real thk = qk.x;
+      int jpk = as_int(qk.w);
+      V3 udk = v3(ud[3 * sl], ud[3 * sl + 1], ud[3 * sl + 2]);
+      V3 upk = v3(up[3 * sl], up[3 * sl + 1], up[3 * sl + 2]);
+      V3 fdk = v3(0, 0, 0), fpk = v3(0, 0, 0);
+      #pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+         int src = (lane + j) & 31;
+         int ks = SHF(sk, src);
+         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
+         real pdk = SHF(pk.w, src);
+         real thk_ = SHF(thk, src);
+         int jpk_ = TABLE ? SHF(jpk, src) : 0;
+         V3 a = v3(SHF(udk.x, src), SHF(udk.y, src), SHF(udk.z, src));
+         V3 b = v3(SHF(upk.x, src), SHF(upk.y, src), SHF(upk.z, src));
+         apx_image(box, dx, dy, dz);
+         real r2 = dx * dx + dy * dy + dz * dz;
+         if (ks > si && si < n && r2 <= cut2) {
+            real rinv = r_rsqrt(r2);
+            real r = r2 * rinv, rr2 = rinv * rinv;
+            real rr[3], bn[3], om[3];
+            radial_coulomb<3>(rinv, rr2, rr);
+            if (EWALD)
+               radial_ewald<3>(r, rinv, rr2, aewald, bn);
+            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
+            thole_one_minus_lambda<3>(r, pi.w, pdk, pg, om);
+            real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
+            real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
+            V3 R = v3(dx, dy, dz);
+            fdi += dipole_field(R, a, B1, B2);
+            fpi += dipole_field(R, b, B1, B2);
+            fdk += dipole_field(R, udi, B1, B2);
+            fpk += dipole_field(R, upi, B1, B2);
+         }
+         int nxt = (lane + 1) & 31;
+         fdk = v3(SHF(fdk.x, nxt), SHF(fdk.y, nxt), SHF(fdk.z, nxt));
+         fpk = v3(SHF(fpk.x, nxt), SHF(fpk.y, nxt), SHF(fpk.z, nxt));
+      }
+      if (sk >= 0) {
+         atomic_real3(fd, sk, fdk);
+         atomic_real3(fp, sk, fpk);
+      }
+   }
+   if (cur >= 0 && si < n) {
+      atomic_real3(fd, si, fdi);
+      atomic_real3(fp, si, fpi);
+   }
+}
+
+// exclusion pass for ufield (only pairs whose u-scale != 1; empty for stock AMOEBA)
+template <bool TABLE>
+__global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real* __restrict__ ud, const real* __restrict__ up,
+   real* __restrict__ fd, real* __restrict__ fp)
+{
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= nx)
+      return;
+   PairExcl p = ex[e];
+   if (p.u == 0)
+      return;
+   real4 pi = posd[p.i], pk = posd[p.k];
+   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+   apx_image(box, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
+   if (r2 > cut2)
+      return;
+   real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
+   real rr[3], om[3];
+   radial_coulomb<3>(rinv, rr2, rr);
+   real4 qi = tpj[p.i], qk = tpj[p.k];
+   real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+   thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+   real B1 = p.u * (1 - om[1]) * rr[1], B2 = p.u * (1 - om[2]) * rr[2];
+   V3 R = v3(dx, dy, dz);
+   V3 udi = v3(ud[3 * p.i], ud[3 * p.i + 1], ud[3 * p.i + 2]), upi = v3(up[3 * p.i], up[3 * p.i + 1], up[3 * p.i + 2]);
+   V3 udk = v3(ud[3 * p.k], ud[3 * p.k + 1], ud[3 * p.k + 2]), upk = v3(up[3 * p.k], up[3 * p.k + 1], up[3 * p.k + 2]);
+   atomic_real3(fd, p.i, dipole_field(R, udk, B1, B2));
+   atomic_real3(fp, p.i, dipole_field(R, upk, B1, B2));
+   atomic_real3(fd, p.k, dipole_field(R, udi, B1, B2));
+   atomic_real3(fp, p.k, dipole_field(R, upi, B1, B2));
+}
+
+// -------------------------------------------------------------------------------------------
+// dfield: permanent-multipole field; tile pass = common part, exclusion pass = d/p split
+// -------------------------------------------------------------------------------------------
+template <bool EWALD, bool TABLE>
+__global__ void __launch_bounds__(APX_BLOCK) k_dfield_tiles(int n, int ntiles, Box box, real cut2, real aewald,
+   const int* __restrict__ iblk, const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
+   const real2* __restrict__ mp2, real* __restrict__ fd)
+{
+   const int lane = threadIdx.x & 31;
+   WarpRange wr = warp_tiles(ntiles);
+   int cur = -1, si = 0;
+   real4 pi;
+   real thi = 0;
+   int jpi = 0;
+   Mpole mi;
+   V3 fi;
+   for (int t = wr.t0; t < wr.t1; ++t) {
+      int ib = iblk[t];
+      if (ib != cur) {
+         if (cur >= 0 && si < n)
+            atomic_real3(fd, si, fi);
+         cur = ib;
+         si = ib * 32 + lane;
+         int sl = min(si, n - 1);
+         pi = posd[sl];
+         real4 q = tpj[sl];
+         thi = q.x;
+         jpi = as_int(q.w);
+         real4 a = mp0[sl], b = mp1[sl];
+         real2 c2 = mp2[sl];
+         mi.c = a.x, mi.dx = a.y, mi.dy = a.z, mi.dz = a.w;
+         mi.qxx = b.x, mi.qxy = b.y, mi.qxz = b.z, mi.qyy = b.w, mi.qyz = c2.x, mi.qzz = c2.y;
+         fi = v3(0, 0, 0);
+      }
+      int sk = katom[t * 32 + lane];
+      int sl = max(sk, 0);
+      real4 pk = posd[sl];
+      real4 qk = tpj[sl];
+      real thk = qk.x;
+      int jpk = as_int(qk.w);
+      real4 ka = mp0[sl], kb = mp1[sl];
+      real2 kc = mp2[sl];
+      V3 fk = v3(0, 0, 0);
+      #pragma unroll 2
+      for (int j = 0; j < 32; ++j) {
+         int src = (lane + j) & 31;
+         int ks = SHF(sk, src);
+         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
+         real pdk = SHF(pk.w, src);
+         real thk_ = SHF(thk, src);
+         int jpk_ = TABLE ? SHF(jpk, src) : 0;
+         Mpole mk;
+         mk.c = SHF(ka.x, src), mk.dx = SHF(ka.y, src), mk.dy = SHF(ka.z, src), mk.dz = SHF(ka.w, src);
+         mk.qxx = SHF(kb.x, src), mk.qxy = SHF(kb.y, src), mk.qxz = SHF(kb.z, src), mk.qyy = SHF(kb.w, src);
+         mk.qyz = SHF(kc.x, src), mk.qzz = SHF(kc.y, src);
+         apx_image(box, dx, dy, dz);
+         real r2 = dx * dx + dy * dy + dz * dz;
+         if (ks > si && si < n && r2 <= cut2) {
+            real rinv = r_rsqrt(r2);
+            real r = r2 * rinv, rr2 = rinv * rinv;
+            real rr[4], bn[4], om[4];
+            radial_coulomb<4>(rinv, rr2, rr);
+            if (EWALD)
+               radial_ewald<4>(r, rinv, rr2, aewald, bn);
+            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
+            thole_one_minus_lambda<4>(r, pi.w, pdk, pg, om);
+            real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
+            real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
+            real B3 = (EWALD ? bn[3] : rr[3]) - om[3] * rr[3];
+            V3 R = v3(dx, dy, dz);
+            fi += mpole_field(R, mk, B1, B2, B3, (real)-1);
+            fk += mpole_field(R, mi, B1, B2, B3, (real)1);
+         }
+         int nxt = (lane + 1) & 31;
+         fk = v3(SHF(fk.x, nxt), SHF(fk.y, nxt), SHF(fk.z, nxt));
+      }
+      if (sk >= 0)
+         atomic_real3(fd, sk, fk);
+   }
+   if (cur >= 0 && si < n)
+      atomic_real3(fd, si, fi);
+}
+
+__device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, const real2* mp2, int s)
+{
+   real4 a = mp0[s], b = mp1[s];
+   real2 c = mp2[s];
+   Mpole m;
+   m.c = a.x, m.dx = a.y, m.dy = a.z, m.dz = a.w;
+   m.qxx = b.x, m.qxy = b.y, m.qxz = b.z, m.qyy = b.w, m.qyz = c.x, m.qzz = c.y;
+   return m;
+}
+
+// d-correction goes to fd, (p - d) correction to the delta array fpd
+template <bool TABLE>
+__global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0,
+   const real4* __restrict__ mp1, const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd)
+{
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= nx)
+      return;
+   PairExcl p = ex[e];
+   if (p.d == 0 && p.p == 0)
+      return;
+   real4 pi = posd[p.i], pk = posd[p.k];
+   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+   apx_image(box, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
+   if (r2 > cut2)
+      return;
+   real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
+   real rr[4], om[4];
+   radial_coulomb<4>(rinv, rr2, rr);
+   real4 qi = tpj[p.i], qk = tpj[p.k];
+   real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+   thole_one_minus_lambda<4>(r, pi.w, pk.w, pg, om);
+   real L1 = (1 - om[1]) * rr[1], L2 = (1 - om[2]) * rr[2], L3 = (1 - om[3]) * rr[3];
+   V3 R = v3(dx, dy, dz);
+   Mpole mi = load_mpole(mp0, mp1, mp2, p.i), mk = load_mpole(mp0, mp1, mp2, p.k);
+   V3 ei = mpole_field(R, mk, L1, L2, L3, (real)-1);   // unit-scale damped Coulomb field at i
+   V3 ek = mpole_field(R, mi, L1, L2, L3, (real)1);
+   if (p.d != 0) {
+      atomic_real3(fd, p.i, p.d * ei);
+      atomic_real3(fd, p.k, p.d * ek);
+   }
+   real dp = p.p - p.d;
+   if (dp != 0) {
+      atomic_real3(fpd, p.i, dp * ei);
+      atomic_real3(fpd, p.k, dp * ek);
+   }
+}
+
+// -------------------------------------------------------------------------------------------
+// sparse preconditioner: z += alpha_i alpha_k T_thole(r) r_k  over the short-range list
+// -------------------------------------------------------------------------------------------
+template <bool TABLE>
+__global__ void __launch_bounds__(APX_BLOCK) k_precond_tiles(int n, int ntiles, Box box, real cut2, const int* __restrict__ iblk,
+   const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj, const real* __restrict__ thlval,
+   int nj, const real* __restrict__ rd, const real* __restrict__ rp, real* __restrict__ zd, real* __restrict__ zp)
+{
+   const int lane = threadIdx.x & 31;
+   WarpRange wr = warp_tiles(ntiles);
+   int cur = -1, si = 0;
+   real4 pi;
+   real thi = 0, poli = 0;
+   int jpi = 0;
+   V3 rdi, rpi, zdi, zpi;
+   for (int t = wr.t0; t < wr.t1; ++t) {
+      int ib = iblk[t];
+      if (ib != cur) {
+         if (cur >= 0 && si < n) {
+            atomic_real3(zd, si, zdi);
+            atomic_real3(zp, si, zpi);
+         }
+         cur = ib;
+         si = ib * 32 + lane;
+         int sl = min(si, n - 1);
+         pi = posd[sl];
+         real4 q = tpj[sl];
+         thi = q.x;
+         poli = q.y;
+         jpi = as_int(q.w);
+         rdi = v3(rd[3 * sl], rd[3 * sl + 1], rd[3 * sl + 2]);
+         rpi = v3(rp[3 * sl], rp[3 * sl + 1], rp[3 * sl + 2]);
+         zdi = v3(0, 0, 0);
+         zpi = v3(0, 0, 0);
+      }
+      int sk = katom[t * 32 + lane];
+      int sl = max(sk, 0);
+      real4 pk = posd[sl];
+      real4 qk = tpj[sl];
+      real thk = qk.x, polk = qk.y;
+      int jpk = as_int(qk.w);
+      V3 rdk = v3(rd[3 * sl], rd[3 * sl + 1], rd[3 * sl + 2]);
+      V3 rpk = v3(rp[3 * sl], rp[3 * sl + 1], rp[3 * sl + 2]);
+      V3 zdk = v3(0, 0, 0), zpk = v3(0, 0, 0);
+      #pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+         int src = (lane + j) & 31;
+         int ks = SHF(sk, src);
+         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
+         real pdk = SHF(pk.w, src);
+         real thk_ = SHF(thk, src), polk_ = SHF(polk, src);
+         int jpk_ = TABLE ? SHF(jpk, src) : 0;
+         V3 a = v3(SHF(rdk.x, src), SHF(rdk.y, src), SHF(rdk.z, src));
+         V3 b = v3(SHF(rpk.x, src), SHF(rpk.y, src), SHF(rpk.z, src));
+         apx_image(box, dx, dy, dz);
+         real r2 = dx * dx + dy * dy + dz * dz;
+         if (ks > si && si < n && r2 <= cut2) {
+            real rinv = r_rsqrt(r2);
+            real r = r2 * rinv, rr2 = rinv * rinv;
+            real rr[3], om[3];
+            radial_coulomb<3>(rinv, rr2, rr);
+            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
+            thole_one_minus_lambda<3>(r, pi.w, pdk, pg, om);
+            real pp = poli * polk_;
+            real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
+            V3 R = v3(dx, dy, dz);
+            zdi += dipole_field(R, a, B1, B2);
+            zpi += dipole_field(R, b, B1, B2);
+            zdk += dipole_field(R, rdi, B1, B2);
+            zpk += dipole_field(R, rpi, B1, B2);
+         }
+         int nxt = (lane + 1) & 31;
+         zdk = v3(SHF(zdk.x, nxt), SHF(zdk.y, nxt), SHF(zdk.z, nxt));
+         zpk = v3(SHF(zpk.x, nxt), SHF(zpk.y, nxt), SHF(zpk.z, nxt));
+      }
+      if (sk >= 0) {
+         atomic_real3(zd, sk, zdk);
+         atomic_real3(zp, sk, zpk);
+      }
+   }
+   if (cur >= 0 && si < n) {
+      atomic_real3(zd, si, zdi);
+      atomic_real3(zp, si, zpi);
+   }
+}
+
+template <bool TABLE>
+__global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real* __restrict__ rd, const real* __restrict__ rp,
+   real* __restrict__ zd, real* __restrict__ zp)
+{
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= nx)
+      return;
+   PairExcl p = ex[e];
+   if (p.u == 0)
+      return;
+   real4 pi = posd[p.i], pk = posd[p.k];
+   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+   apx_image(box, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
+   if (r2 > cut2)
+      return;
+   real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
+   real rr[3], om[3];
+   radial_coulomb<3>(rinv, rr2, rr);
+   real4 qi = tpj[p.i], qk = tpj[p.k];
+   real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+   thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+   real pp = qi.y * qk.y * p.u;
+   real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
+   V3 R = v3(dx, dy, dz);
+   V3 rdi = v3(rd[3 * p.i], rd[3 * p.i + 1], rd[3 * p.i + 2]), rpi = v3(rp[3 * p.i], rp[3 * p.i + 1], rp[3 * p.i + 2]);
+   V3 rdk = v3(rd[3 * p.k], rd[3 * p.k + 1], rd[3 * p.k + 2]), rpk = v3(rp[3 * p.k], rp[3 * p.k + 1], rp[3 * p.k + 2]);
+   atomic_real3(zd, p.i, dipole_field(R, rdk, B1, B2));
+   atomic_real3(zp, p.i, dipole_field(R, rpk, B1, B2));
+   atomic_real3(zd, p.k, dipole_field(R, rdi, B1, B2));
+   atomic_real3(zp, p.k, dipole_field(R, rpi, B1, B2));
+}
+
+__global__ void k_diag_precond(int n3, real udiag, const real4* __restrict__ tpj, const real* __restrict__ rd,
+   const real* __restrict__ rp, real* __restrict__ zd, real* __restrict__ zp)
+{
+   int q = blockIdx.x * blockDim.x + threadIdx.x;
+   if (q >= n3)
+      return;
+   real pol = udiag * tpj[q / 3].y;
+   zd[q] = pol * rd[q];
+   zp[q] = pol * rp[q];
+}
+
+inline int tile_grid(apx_ctx* c, int ntiles)
+{
+   // 4 warps per CTA; enough CTAs to fill the machine but never more warps than tiles
+   int want = (ntiles + 3) / 4;
+   int cap = c->sm_count * 8;
+   return want < 1 ? 1 : (want < cap ? want : cap);
+}
+} // namespace
+
+void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp)
+{
+   TileList& L = c->mlist;
+   real cut = (real)c->opt.cutoff;
+   int grid = tile_grid(c, L.ntiles);
+   bool ew = c->opt.use_ewald != 0;
+   bool tb = c->thole_table != 0;
+#define LAUNCH_UF(E, T)                                                                                                   \
+   k_ufield_tiles<E, T><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, (real)c->opt.aewald, L.iblk,      \
+      L.katom, c->posd, c->tpj, c->thlval, c->opt.njpolar, ud, up, fd, fp)
+   if (L.ntiles > 0) {
+      if (ew && tb) LAUNCH_UF(true, true);
+      else if (ew) LAUNCH_UF(true, false);
+      else if (tb) LAUNCH_UF(false, true);
+      else LAUNCH_UF(false, false);
+      APX_COUNT_LAUNCH(c);
+   }
+#undef LAUNCH_UF
+   if (c->nexcl_u > 0) {
+      int g = (c->nexcl + 127) / 128;
+      if (tb)
+         k_ufield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, ud, up, fd, fp);
+      else
+         k_ufield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, ud, up, fd, fp);
+      APX_COUNT_LAUNCH(c);
+   }
+}
+
+// fd accumulates the common field + d corrections; fpd receives the (p - d) delta only
+void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
+{
+   TileList& L = c->mlist;
+   real cut = (real)c->opt.cutoff;
+   int grid = tile_grid(c, L.ntiles);
+   bool ew = c->opt.use_ewald != 0;
+   bool tb = c->thole_table != 0;
+#define LAUNCH_DF(E, T)                                                                                                   \
+   k_dfield_tiles<E, T><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, (real)c->opt.aewald, L.iblk,      \
+      L.katom, c->posd, c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd)
+   if (L.ntiles > 0) {
+      if (ew && tb) LAUNCH_DF(true, true);
+      else if (ew) LAUNCH_DF(true, false);
+      else if (tb) LAUNCH_DF(false, true);
+      else LAUNCH_DF(false, false);
+      APX_COUNT_LAUNCH(c);
+   }
+#undef LAUNCH_DF
+   if (c->nexcl > 0) {
+      int g = (c->nexcl + 127) / 128;
+      if (tb)
+         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
+      else
+         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
+      APX_COUNT_LAUNCH(c);
+   }
+}
+
+// z = M r.  If diag_done the caller already wrote the diagonal part (fused PCG update kernel).
+void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp, bool diag_done)
+{
+   bool sparse = c->opt.pcgprec && c->opt.usolve_cutoff > 0;
+   if (!diag_done) {
+      int n3 = 3 * c->n;
+      real udiag = sparse ? (real)c->opt.uaccel : (real)1;
+      k_diag_precond<<<(n3 + 255) / 256, 256, 0, c->stream>>>(n3, udiag, c->tpj, rd, rp, zd, zp);
+      APX_COUNT_LAUNCH(c);
+   }
+   if (!sparse)
+      return;
+   TileList& L = c->ulist;
+   real cut = (real)c->opt.usolve_cutoff;
+   bool tb = c->thole_table != 0;
+   if (L.ntiles > 0) {
+      int grid = tile_grid(c, L.ntiles);
+      if (tb)
+         k_precond_tiles<true><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, L.iblk, L.katom, c->posd, c->tpj,
+            c->thlval, c->opt.njpolar, rd, rp, zd, zp);
+      else
+         k_precond_tiles<false><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, L.iblk, L.katom, c->posd, c->tpj,
+            c->thlval, c->opt.njpolar, rd, rp, zd, zp);
+      APX_COUNT_LAUNCH(c);
+   }
+   if (c->nexcl_u > 0) {
+      int g = (c->nexcl + 127) / 128;
+      if (tb)
+         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, rd, rp, zd, zp);
+      else
+         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, rd, rp, zd, zp);
+      APX_COUNT_LAUNCH(c);
+   }
+}

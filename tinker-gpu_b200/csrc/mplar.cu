@@ -1,0 +1,896 @@
+// Energy / gradient / torque / virial of the permanent-multipole and polarization terms:
+// the fused real-space tile kernel (role of emplar_cu1a/b/c, src/cu/amoeba/emplar.cu:505-544, and
+// of empole_cu1 + epolar_cu1 on the ANALYZE path), Ewald self terms (include/seq/emselfamoeba.h),
+// reciprocal-space energy/force/torque/virial (src/cu/hippo/empole.cu:202-336,
+// src/cu/epolarrecip.cu:9-511), the dot-product polarization energy (src/cu/amoeba/epolar.cu:15-30)
+// and the final fixed-point reductions of energy() (src/energy.cpp:319-448).
+//
+// Differences of organisation from the reference:
+//   * one real-space pass computes permanent + polarization terms with all exclusion scales = 1;
+//     a second, tiny pass corrects listed pairs with (scale-1) undamped/Thole-only terms;
+//   * the permanent-multipole PME round trip is done ONCE per evaluation (inside induce's dfield)
+//     and its fmp/fphi are reused by the reciprocal multipole and polarization terms
+//     (the reference repeats it in empoleEwaldRecip, hippo/empole.cu:308-317);
+//   * energies/virials are reduced warp->atomic into a handful of fixed-point / double scalars
+//     instead of 524288-entry buffers that must be re-reduced every call (32 MB virial read).
+#include "apx_internal.h"
+#include "pairmath.cuh"
+#include <cmath>
+
+#define FULL 0xffffffffu
+#define SHF(v, src) __shfl_sync(FULL, (v), (src))
+
+// dbuf slots (doubles)
+enum {
+   D_EM_RECIP = 0, D_EP_RECIP = 1, D_EM_SELF = 2, D_EP_DOT = 3, D_EP_SELF = 4,
+   D_VIR_TRQ = 8,      // 6
+   D_CONV_E = 16,      // 1 + 6 (vir_m)
+   D_VIR_MREC = 24,    // 6: atom part of the multipole recip virial
+   D_VIR_PREC = 32,    // 6: polarization recip virial (atom part)
+   D_VIR_CROSS = 40,   // 6
+   D_TOTAL = 48
+};
+// ebuf slots (fixed point): 0 em_real, 1 ep_real, 2..7 virial of real-space pairs
+// cnt: 0 nem, 1 nep
+
+void apx_to_sorted(apx_ctx* c, const double* in_dev, real* out);
+void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev);
+
+namespace {
+__device__ __forceinline__ int as_int(real w)
+{
+#ifdef APX_DOUBLE
+   return (int)__double_as_longlong(w);
+#else
+   return __float_as_int(w);
+#endif
+}
+__device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, const real2* mp2, int s)
+{
+   real4 a = mp0[s], b = mp1[s];
+   real2 c = mp2[s];
+   Mpole m;
+   m.c = a.x, m.dx = a.y, m.dy = a.z, m.dz = a.w;
+   m.qxx = b.x, m.qxy = b.y, m.qxz = b.z, m.qyy = b.w, m.qyz = c.x, m.qzz = c.y;
+   return m;
+}
+__device__ __forceinline__ void atomic_fixed3(fixed_t* gx, fixed_t* gy, fixed_t* gz, int s, V3 v)
+{
+   atomic_fixed(gx + s, v.x);
+   atomic_fixed(gy + s, v.y);
+   atomic_fixed(gz + s, v.z);
+}
+__device__ __forceinline__ double warp_sum(double x)
+{
+   for (int o = 16; o > 0; o >>= 1)
+      x += __shfl_xor_sync(FULL, x, o);
+   return x;
+}
+__device__ __forceinline__ void atomic_fixed_d(fixed_t* p, double v)
+{
+   atomicAdd(p, (fixed_t)(long long)(v * APX_FIXED_SCALE));
+}
+
+struct MplarArgs {
+   int n, ntiles;
+   Box box;
+   real cut2, aewald, f;
+   const int* iblk;
+   const int* katom;
+   const real4* posd;
+   const real4* tpj;
+   const real* thlval;
+   int nj, table;
+   const real4* mp0;
+   const real4* mp1;
+   const real2* mp2;
+   const real* ud;
+   const real* up;
+   int do_m, do_p, mutual, do_e, do_v, do_a, pair_ep;
+   fixed_t* gx;
+   fixed_t* gy;
+   fixed_t* gz;
+   fixed_t* trq;      // [3*npad] fixed point
+   fixed_t* ebuf;
+   int* cnt;
+};
+
+struct WarpRange {
+   int t0, t1;
+};
+__device__ __forceinline__ WarpRange warp_tiles(int ntiles)
+{
+   int nw = gridDim.x * (blockDim.x >> 5);
+   int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+   int per = (ntiles + nw - 1) / nw;
+   WarpRange r;
+   r.t0 = min(ntiles, w * per);
+   r.t1 = min(ntiles, r.t0 + per);
+   return r;
+}
+
+template <bool DO_G, bool EWALD>
+__global__ void __launch_bounds__(APX_BLOCK) k_mplar_tiles(MplarArgs A)
+{
+   const int lane = threadIdx.x & 31;
+   const int n = A.n;
+   WarpRange wr = warp_tiles(A.ntiles);
+   int cur = -1, si = 0;
+   real4 pi;
+   real thi = 0;
+   int jpi = 0;
+   Mpole mi;
+   V3 udi, upi, gi, ti;
+   double em = 0, ep = 0, vxx = 0, vxy = 0, vxz = 0, vyy = 0, vyz = 0, vzz = 0;
+   int nem = 0;
+   for (int t = wr.t0; t < wr.t1; ++t) {
+      int ib = A.iblk[t];
+      if (ib != cur) {
+         if (DO_G && cur >= 0 && si < n) {
+            atomic_fixed3(A.gx, A.gy, A.gz, si, gi);
+            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * si, ti);
+         }
+         cur = ib;
+         si = ib * 32 + lane;
+         int sl = min(si, n - 1);
+         pi = A.posd[sl];
+         real4 q = A.tpj[sl];
+         thi = q.x;
+         jpi = as_int(q.w);
+         mi = load_mpole(A.mp0, A.mp1, A.mp2, sl);
+         udi = upi = v3(0, 0, 0);
+         if (A.do_p) {
+            udi = v3(A.ud[3 * sl], A.ud[3 * sl + 1], A.ud[3 * sl + 2]);
+            upi = v3(A.up[3 * sl], A.up[3 * sl + 1], A.up[3 * sl + 2]);
+         }
+         gi = v3(0, 0, 0);
+         ti = v3(0, 0, 0);
+      }
+      int sk = A.katom[t * 32 + lane];
+      int sl = max(sk, 0);
+      real4 pk = A.posd[sl];
+      real4 qk = A.tpj[sl];
+      real thk = qk.x;
+      int jpk = as_int(qk.w);
+      real4 ka = A.mp0[sl], kb = A.mp1[sl];
+      real2 kc = A.mp2[sl];
+      V3 udk = v3(0, 0, 0), upk = v3(0, 0, 0);
+      if (A.do_p) {
+         udk = v3(A.ud[3 * sl], A.ud[3 * sl + 1], A.ud[3 * sl + 2]);
+         upk = v3(A.up[3 * sl], A.up[3 * sl + 1], A.up[3 * sl + 2]);
+      }
+      V3 gk = v3(0, 0, 0), tk = v3(0, 0, 0);
+      for (int j = 0; j < 32; ++j) {
+         int src = (lane + j) & 31;
+         int ks = SHF(sk, src);
+         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
+         real pdk = SHF(pk.w, src);
+         real thk_ = SHF(thk, src);
+         int jpk_ = SHF(jpk, src);
+         Mpole mk;
+         mk.c = SHF(ka.x, src), mk.dx = SHF(ka.y, src), mk.dy = SHF(ka.z, src), mk.dz = SHF(ka.w, src);
+         mk.qxx = SHF(kb.x, src), mk.qxy = SHF(kb.y, src), mk.qxz = SHF(kb.z, src), mk.qyy = SHF(kb.w, src);
+         mk.qyz = SHF(kc.x, src), mk.qzz = SHF(kc.y, src);
+         V3 ukd = v3(SHF(udk.x, src), SHF(udk.y, src), SHF(udk.z, src));
+         V3 ukp = v3(SHF(upk.x, src), SHF(upk.y, src), SHF(upk.z, src));
+         apx_image(A.box, dx, dy, dz);
+         real r2 = dx * dx + dy * dy + dz * dz;
+         if (ks > si && si < n && r2 <= A.cut2) {
+            real rinv = r_rsqrt(r2);
+            real r = r2 * rinv, rr2 = rinv * rinv;
+            real rr[6], B[6];
+            radial_coulomb<6>(rinv, rr2, rr);
+            if (EWALD)
+               radial_ewald<6>(r, rinv, rr2, A.aewald, B);
+            else {
+               #pragma unroll
+               for (int q = 0; q < 6; ++q)
+                  B[q] = rr[q];
+            }
+            V3 R = v3(dx, dy, dz);
+            V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0), tqk = v3(0, 0, 0);
+            ++nem;
+            if (A.do_m) {
+               V3 g1, t1, t2;
+               real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
+               em += (double)(A.f * U);
+               if (DO_G) {
+                  g += g1;
+                  tqi += t1;
+                  tqk += t2;
+               }
+            }
+            if (A.do_p) {
+               real om[6];
+               real pg = A.table ? A.thlval[jpi * A.nj + jpk_] : min(thi, thk_);
+               thole_one_minus_lambda<6>(r, pi.w, pdk, pg, om);
+               #pragma unroll
+               for (int q = 1; q < 5; ++q)
+                  B[q] -= om[q] * rr[q];
+               if (A.pair_ep) {
+                  V3 d0, d1;
+                  real U = pair_mu<false>(R, mi, ukd, B, d0, d1) + pair_um<false>(R, udi, mk, B, d0, d1);
+                  ep += (double)((real)0.5 * A.f * U);
+               }
+               if (DO_G) {
+                  V3 ubk = (real)0.5 * (ukd + ukp), ubi = (real)0.5 * (udi + upi);
+                  V3 g1, g2, t1, t2;
+                  pair_mu<true>(R, mi, ubk, B, g1, t1);
+                  pair_um<true>(R, ubi, mk, B, g2, t2);
+                  g += g1 + g2;
+                  tqi += t1;
+                  tqk += t2;
+                  if (A.mutual)
+                     g += (real)0.5 * (pair_uu_grad(R, udi, ukp, B) + pair_uu_grad(R, upi, ukd, B));
+               }
+            }
+            if (DO_G) {
+               g = A.f * g;
+               gi -= g;
+               gk += g;
+               ti += A.f * tqi;
+               tk += A.f * tqk;
+               if (A.do_v) {
+                  vxx += (double)(R.x * g.x);
+                  vxy += (double)((real)0.5 * (R.y * g.x + R.x * g.y));
+                  vxz += (double)((real)0.5 * (R.z * g.x + R.x * g.z));
+                  vyy += (double)(R.y * g.y);
+                  vyz += (double)((real)0.5 * (R.z * g.y + R.y * g.z));
+                  vzz += (double)(R.z * g.z);
+               }
+            }
+         }
+         if (DO_G) {
+            int nxt = (lane + 1) & 31;
+            gk = v3(SHF(gk.x, nxt), SHF(gk.y, nxt), SHF(gk.z, nxt));
+            tk = v3(SHF(tk.x, nxt), SHF(tk.y, nxt), SHF(tk.z, nxt));
+         }
+      }
+      if (DO_G && sk >= 0) {
+         atomic_fixed3(A.gx, A.gy, A.gz, sk, gk);
+         atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * sk, tk);
+      }
+   }
+   if (DO_G && cur >= 0 && si < n) {
+      atomic_fixed3(A.gx, A.gy, A.gz, si, gi);
+      atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * si, ti);
+   }
+   if (A.do_e) {
+      em = warp_sum(em);
+      ep = warp_sum(ep);
+      if (lane == 0) {
+         if (em != 0.0) atomic_fixed_d(&A.ebuf[0], em);
+         if (ep != 0.0) atomic_fixed_d(&A.ebuf[1], ep);
+      }
+   }
+   if (A.do_a) {
+      for (int o = 16; o > 0; o >>= 1)
+         nem += __shfl_xor_sync(FULL, nem, o);
+      if (lane == 0 && nem)
+         atomicAdd(&A.cnt[0], nem);
+   }
+   if (DO_G && A.do_v) {
+      vxx = warp_sum(vxx), vxy = warp_sum(vxy), vxz = warp_sum(vxz);
+      vyy = warp_sum(vyy), vyz = warp_sum(vyz), vzz = warp_sum(vzz);
+      if (lane == 0) {
+         atomic_fixed_d(&A.ebuf[2], vxx);
+         atomic_fixed_d(&A.ebuf[3], vxy);
+         atomic_fixed_d(&A.ebuf[4], vxz);
+         atomic_fixed_d(&A.ebuf[5], vyy);
+         atomic_fixed_d(&A.ebuf[6], vyz);
+         atomic_fixed_d(&A.ebuf[7], vzz);
+      }
+   }
+}
+
+// exclusion pass: (scale-1) * undamped (m) or Thole-only (d,p,u) hierarchies
+template <bool DO_G>
+__global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs A)
+{
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   double em = 0, ep = 0, v[6] = {0, 0, 0, 0, 0, 0};
+   int dn = 0;
+   if (e < nx) {
+      PairExcl p = ex[e];
+      real4 pi = A.posd[p.i], pk = A.posd[p.k];
+      real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+      apx_image(A.box, dx, dy, dz);
+      real r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 <= A.cut2) {
+         real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[6], B[6];
+         radial_coulomb<6>(rinv, rr2, rr);
+         V3 R = v3(dx, dy, dz);
+         Mpole mi = load_mpole(A.mp0, A.mp1, A.mp2, p.i), mk = load_mpole(A.mp0, A.mp1, A.mp2, p.k);
+         V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0), tqk = v3(0, 0, 0);
+         if (A.do_m ? p.m == (real)-1 : p.p == (real)-1)
+            dn = -1;
+         if (A.do_m && p.m != 0) {
+            #pragma unroll
+            for (int q = 0; q < 6; ++q)
+               B[q] = p.m * rr[q];
+            V3 g1, t1, t2;
+            real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
+            em = (double)(A.f * U);
+            if (DO_G) {
+               g += g1;
+               tqi += t1;
+               tqk += t2;
+            }
+         }
+         if (A.do_p && (p.d != 0 || p.p != 0 || p.u != 0)) {
+            real om[6];
+            real4 qi = A.tpj[p.i], qk = A.tpj[p.k];
+            real pg = A.table ? A.thlval[as_int(qi.w) * A.nj + as_int(qk.w)] : min(qi.x, qk.x);
+            thole_one_minus_lambda<6>(r, pi.w, pk.w, pg, om);
+            real L[6];
+            #pragma unroll
+            for (int q = 0; q < 6; ++q)
+               L[q] = (1 - om[q]) * rr[q];
+            L[0] = 0;
+            V3 udi = v3(A.ud[3 * p.i], A.ud[3 * p.i + 1], A.ud[3 * p.i + 2]), upi = v3(A.up[3 * p.i], A.up[3 * p.i + 1], A.up[3 * p.i + 2]);
+            V3 udk = v3(A.ud[3 * p.k], A.ud[3 * p.k + 1], A.ud[3 * p.k + 2]), upk = v3(A.up[3 * p.k], A.up[3 * p.k + 1], A.up[3 * p.k + 2]);
+            // p-scaled: permanent with ud ; d-scaled: permanent with up
+            for (int pass = 0; pass < 2; ++pass) {
+               real sc = pass == 0 ? p.p : p.d;
+               if (sc == 0)
+                  continue;
+               #pragma unroll
+               for (int q = 0; q < 6; ++q)
+                  B[q] = (real)0.5 * sc * L[q];
+               V3 uk = pass == 0 ? udk : upk, ui = pass == 0 ? udi : upi;
+               V3 g1, g2, t1, t2;
+               real U = pair_mu<DO_G>(R, mi, uk, B, g1, t1) + pair_um<DO_G>(R, ui, mk, B, g2, t2);
+               if (pass == 0 && A.pair_ep)
+                  ep = (double)(A.f * U);
+               if (DO_G) {
+                  g += g1 + g2;
+                  tqi += t1;
+                  tqk += t2;
+               }
+            }
+            if (DO_G && A.mutual && p.u != 0) {
+               #pragma unroll
+               for (int q = 0; q < 6; ++q)
+                  B[q] = (real)0.5 * p.u * L[q];
+               g += pair_uu_grad(R, udi, upk, B) + pair_uu_grad(R, upi, udk, B);
+            }
+         }
+         if (DO_G) {
+            g = A.f * g;
+            atomic_fixed3(A.gx, A.gy, A.gz, p.i, (real)-1 * g);
+            atomic_fixed3(A.gx, A.gy, A.gz, p.k, g);
+            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.i, A.f * tqi);
+            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.k, A.f * tqk);
+            if (A.do_v) {
+               v[0] = (double)(R.x * g.x);
+               v[1] = (double)((real)0.5 * (R.y * g.x + R.x * g.y));
+               v[2] = (double)((real)0.5 * (R.z * g.x + R.x * g.z));
+               v[3] = (double)(R.y * g.y);
+               v[4] = (double)((real)0.5 * (R.z * g.y + R.y * g.z));
+               v[5] = (double)(R.z * g.z);
+            }
+         }
+      }
+   }
+   int lane = threadIdx.x & 31;
+   if (A.do_e) {
+      em = warp_sum(em);
+      ep = warp_sum(ep);
+      if (lane == 0) {
+         if (em != 0.0) atomic_fixed_d(&A.ebuf[0], em);
+         if (ep != 0.0) atomic_fixed_d(&A.ebuf[1], ep);
+      }
+   }
+   if (A.do_a) {
+      for (int o = 16; o > 0; o >>= 1)
+         dn += __shfl_xor_sync(FULL, dn, o);
+      if (lane == 0 && dn)
+         atomicAdd(&A.cnt[0], dn);
+   }
+   if (DO_G && A.do_v) {
+      #pragma unroll
+      for (int q = 0; q < 6; ++q) {
+         double x = warp_sum(v[q]);
+         if (lane == 0 && x != 0.0)
+            atomic_fixed_d(&A.ebuf[2 + q], x);
+      }
+   }
+}
+
+struct RecipX {
+   real a[3][3];
+   real ftc[6][6];
+   real rc[9];        // recip rows
+   int nf[3];
+};
+
+__device__ __forceinline__ void frac_to_cart10(const RecipX& X, const real* f, real* cphi)
+{
+   cphi[0] = f[0];
+   #pragma unroll
+   for (int c = 0; c < 3; ++c)
+      cphi[1 + c] = X.a[c][0] * f[1] + X.a[c][1] * f[2] + X.a[c][2] * f[3];
+   #pragma unroll
+   for (int j = 0; j < 6; ++j) {
+      real t = 0;
+      #pragma unroll
+      for (int k = 0; k < 6; ++k)
+         t += X.ftc[k][j] * f[4 + k];
+      cphi[4 + j] = t;
+   }
+}
+
+// torque and virial of a Cartesian multipole (c,d,Q) in a potential with Cartesian derivatives
+// cphi = {phi, grad(3), xx,yy,zz,xy,xz,yz}:  tau = -d x grad - 2 dual(Q Phi),
+// V = -sym(d (x) grad) - 2 sym(Q Phi)
+__device__ __forceinline__ void mpole_in_potential(const Mpole& m, const real* cp, V3& tau, double* v, real scale, bool do_v)
+{
+   real P[3][3] = {{cp[4], cp[7], cp[8]}, {cp[7], cp[5], cp[9]}, {cp[8], cp[9], cp[6]}};
+   real Q[3][3] = {{m.qxx, m.qxy, m.qxz}, {m.qxy, m.qyy, m.qyz}, {m.qxz, m.qyz, m.qzz}};
+   real M[3][3];
+   #pragma unroll
+   for (int a = 0; a < 3; ++a)
+      #pragma unroll
+      for (int b = 0; b < 3; ++b)
+         M[a][b] = Q[a][0] * P[0][b] + Q[a][1] * P[1][b] + Q[a][2] * P[2][b];
+   V3 d = v3(m.dx, m.dy, m.dz), g = v3(cp[1], cp[2], cp[3]);
+   V3 dxg = cross3(d, g);
+   tau = v3(-dxg.x - 2 * (M[1][2] - M[2][1]), -dxg.y - 2 * (M[2][0] - M[0][2]), -dxg.z - 2 * (M[0][1] - M[1][0]));
+   if (do_v) {
+      v[0] += (double)(scale * (-d.x * g.x - 2 * M[0][0]));
+      v[1] += (double)(scale * (-(real)0.5 * (d.x * g.y + d.y * g.x) - (M[0][1] + M[1][0])));
+      v[2] += (double)(scale * (-(real)0.5 * (d.x * g.z + d.z * g.x) - (M[0][2] + M[2][0])));
+      v[3] += (double)(scale * (-d.y * g.y - 2 * M[1][1]));
+      v[4] += (double)(scale * (-(real)0.5 * (d.y * g.z + d.z * g.y) - (M[1][2] + M[2][1])));
+      v[5] += (double)(scale * (-d.z * g.z - 2 * M[2][2]));
+   }
+}
+
+// index tables of the derivative of phi_k w.r.t. fractional coordinate 1,2,3 (tinker deriv1/2/3, 0-based)
+__constant__ int c_d1[10] = {1, 4, 7, 8, 10, 15, 17, 13, 14, 19};
+__constant__ int c_d2[10] = {2, 7, 5, 9, 13, 11, 18, 15, 19, 16};
+__constant__ int c_d3[10] = {3, 8, 9, 6, 14, 16, 12, 19, 17, 18};
+
+__device__ __forceinline__ void block_add(double* vals, int nv, double* out)
+{
+   // warp reduce each then one atomic per warp
+   int lane = threadIdx.x & 31;
+   for (int q = 0; q < nv; ++q) {
+      double x = warp_sum(vals[q]);
+      if (lane == 0 && x != 0.0)
+         atomicAdd(&out[q], x);
+   }
+}
+
+// reciprocal + self multipole terms per atom
+template <bool DO_G>
+__global__ void k_recip_mpole(int n, RecipX X, real f, real aewald, int do_e, int do_v, const real4* __restrict__ mp0,
+   const real4* __restrict__ mp1, const real2* __restrict__ mp2, const real* __restrict__ fmp, const real* __restrict__ fphi,
+   fixed_t* gx, fixed_t* gy, fixed_t* gz, fixed_t* trq, double* __restrict__ dbuf)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   double acc[2] = {0, 0};
+   double v[6] = {0, 0, 0, 0, 0, 0};
+   if (s < n) {
+      Mpole m = load_mpole(mp0, mp1, mp2, s);
+      const real* fm = fmp + 10 * s;
+      const real* fp = fphi + 20 * s;
+      if (do_e) {
+         real e = 0;
+         #pragma unroll
+         for (int k = 0; k < 10; ++k)
+            e += fm[k] * fp[k];
+         acc[0] = (double)((real)0.5 * f * e);
+         real a2 = 2 * aewald * aewald;
+         real cii = m.c * m.c, dii = m.dx * m.dx + m.dy * m.dy + m.dz * m.dz;
+         real qii = 2 * (m.qxy * m.qxy + m.qxz * m.qxz + m.qyz * m.qyz) + m.qxx * m.qxx + m.qyy * m.qyy + m.qzz * m.qzz;
+         real fterm = -f * aewald * (real)0.5641895835477563;
+         acc[1] = (double)(fterm * (cii + a2 * (dii / 3 + 2 * a2 * qii / 5)));
+      }
+      if (DO_G) {
+         real f1 = 0, f2 = 0, f3 = 0;
+         #pragma unroll
+         for (int k = 0; k < 10; ++k) {
+            f1 += fm[k] * fp[c_d1[k]];
+            f2 += fm[k] * fp[c_d2[k]];
+            f3 += fm[k] * fp[c_d3[k]];
+         }
+         f1 *= X.nf[0];
+         f2 *= X.nf[1];
+         f3 *= X.nf[2];
+         V3 h = v3(X.rc[0] * f1 + X.rc[3] * f2 + X.rc[6] * f3, X.rc[1] * f1 + X.rc[4] * f2 + X.rc[7] * f3,
+            X.rc[2] * f1 + X.rc[5] * f2 + X.rc[8] * f3);
+         atomic_fixed3(gx, gy, gz, s, f * h);
+         real cp[10];
+         frac_to_cart10(X, fp, cp);
+         V3 tau;
+         mpole_in_potential(m, cp, tau, v, f, do_v != 0);
+         atomic_fixed3(trq, trq + 1, trq + 2, 3 * s, f * tau);
+      }
+   }
+   if (do_e) {
+      double x = warp_sum(acc[0]), y = warp_sum(acc[1]);
+      if ((threadIdx.x & 31) == 0) {
+         atomicAdd(&dbuf[D_EM_RECIP], x);
+         atomicAdd(&dbuf[D_EM_SELF], y);
+      }
+   }
+   if (DO_G && do_v)
+      block_add(v, 6, dbuf + D_VIR_MREC);
+}
+
+// reciprocal + self polarization terms per atom (after apx_pme_uind_fphi)
+template <bool DO_G>
+__global__ void k_recip_polar(int n, RecipX X, real f, real aewald, int do_e, int do_v, int mutual, const real4* __restrict__ mp0,
+   const real4* __restrict__ mp1, const real2* __restrict__ mp2, const real* __restrict__ fmp, const real* __restrict__ fphi,
+   const real* __restrict__ ud, const real* __restrict__ up, const real* __restrict__ fphid, const real* __restrict__ fphip,
+   const real* __restrict__ fphidp, fixed_t* gx, fixed_t* gy, fixed_t* gz, fixed_t* trq, double* __restrict__ dbuf)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   double acc[2] = {0, 0};
+   double v[6] = {0, 0, 0, 0, 0, 0};
+   if (s < n) {
+      Mpole m = load_mpole(mp0, mp1, mp2, s);
+      V3 d = v3(ud[3 * s], ud[3 * s + 1], ud[3 * s + 2]), q = v3(up[3 * s], up[3 * s + 1], up[3 * s + 2]);
+      real fd[3], fq[3];
+      #pragma unroll
+      for (int k = 0; k < 3; ++k) {
+         fd[k] = X.a[0][k] * d.x + X.a[1][k] * d.y + X.a[2][k] * d.z;
+         fq[k] = X.a[0][k] * q.x + X.a[1][k] * q.y + X.a[2][k] * q.z;
+      }
+      const real* fp = fphi + 20 * s;
+      real a3 = aewald * aewald * aewald * (real)0.5641895835477563;   // a^3/sqrt(pi)
+      if (do_e) {
+         acc[0] = (double)((real)0.5 * f * (fd[0] * fp[1] + fd[1] * fp[2] + fd[2] * fp[3]));
+         acc[1] = (double)(-(real)(2.0 / 3.0) * f * a3 * (m.dx * d.x + m.dy * d.y + m.dz * d.z));
+      }
+      if (DO_G) {
+         const real* fm = fmp + 10 * s;
+         const real* pd = fphid + 10 * s;
+         const real* pp = fphip + 10 * s;
+         const real* ps = fphidp + 20 * s;
+         real f1 = 0, f2 = 0, f3 = 0;
+         #pragma unroll
+         for (int k = 0; k < 3; ++k) {
+            int j1 = c_d1[k + 1], j2 = c_d2[k + 1], j3 = c_d3[k + 1];
+            real su = fd[k] + fq[k];
+            f1 += su * fp[j1];
+            f2 += su * fp[j2];
+            f3 += su * fp[j3];
+            if (mutual) {
+               f1 += fd[k] * pp[j1] + fq[k] * pd[j1];
+               f2 += fd[k] * pp[j2] + fq[k] * pd[j2];
+               f3 += fd[k] * pp[j3] + fq[k] * pd[j3];
+            }
+         }
+         #pragma unroll
+         for (int k = 0; k < 10; ++k) {
+            f1 += fm[k] * ps[c_d1[k]];
+            f2 += fm[k] * ps[c_d2[k]];
+            f3 += fm[k] * ps[c_d3[k]];
+         }
+         f1 *= (real)0.5 * X.nf[0];
+         f2 *= (real)0.5 * X.nf[1];
+         f3 *= (real)0.5 * X.nf[2];
+         V3 h = v3(X.rc[0] * f1 + X.rc[3] * f2 + X.rc[6] * f3, X.rc[1] * f1 + X.rc[4] * f2 + X.rc[7] * f3,
+            X.rc[2] * f1 + X.rc[5] * f2 + X.rc[8] * f3);
+         atomic_fixed3(gx, gy, gz, s, f * h);
+         // permanent multipole in the averaged induced potential (0.5 * (d+p))
+         real half[10], cdp[10];
+         #pragma unroll
+         for (int k = 0; k < 10; ++k)
+            half[k] = (real)0.5 * ps[k];
+         frac_to_cart10(X, half, cdp);
+         V3 tau;
+         mpole_in_potential(m, cdp, tau, v, f, do_v != 0);
+         V3 ub = (real)0.5 * (d + q);
+         V3 dm = v3(m.dx, m.dy, m.dz);
+         tau += ((real)(4.0 / 3.0) * a3) * cross3(dm, ub);
+         atomic_fixed3(trq, trq + 1, trq + 2, 3 * s, f * tau);
+         if (do_v) {
+            // induced dipoles in the permanent potential gradient, and the mutual cross terms
+            real cp[10];
+            frac_to_cart10(X, fp, cp);
+            V3 g = v3(cp[1], cp[2], cp[3]);
+            V3 su = d + q;
+            real w = -(real)0.5 * f;
+            v[0] += (double)(w * su.x * g.x);
+            v[1] += (double)(w * (real)0.5 * (su.x * g.y + su.y * g.x));
+            v[2] += (double)(w * (real)0.5 * (su.x * g.z + su.z * g.x));
+            v[3] += (double)(w * su.y * g.y);
+            v[4] += (double)(w * (real)0.5 * (su.y * g.z + su.z * g.y));
+            v[5] += (double)(w * su.z * g.z);
+            if (mutual) {
+               V3 gd, gp;
+               gd.x = X.a[0][0] * pd[1] + X.a[0][1] * pd[2] + X.a[0][2] * pd[3];
+               gd.y = X.a[1][0] * pd[1] + X.a[1][1] * pd[2] + X.a[1][2] * pd[3];
+               gd.z = X.a[2][0] * pd[1] + X.a[2][1] * pd[2] + X.a[2][2] * pd[3];
+               gp.x = X.a[0][0] * pp[1] + X.a[0][1] * pp[2] + X.a[0][2] * pp[3];
+               gp.y = X.a[1][0] * pp[1] + X.a[1][1] * pp[2] + X.a[1][2] * pp[3];
+               gp.z = X.a[2][0] * pp[1] + X.a[2][1] * pp[2] + X.a[2][2] * pp[3];
+               // M_ab = q_a gd_b + d_a gp_b
+               v[0] += (double)(w * (q.x * gd.x + d.x * gp.x));
+               v[1] += (double)(w * (real)0.5 * (q.x * gd.y + d.x * gp.y + q.y * gd.x + d.y * gp.x));
+               v[2] += (double)(w * (real)0.5 * (q.x * gd.z + d.x * gp.z + q.z * gd.x + d.z * gp.x));
+               v[3] += (double)(w * (q.y * gd.y + d.y * gp.y));
+               v[4] += (double)(w * (real)0.5 * (q.y * gd.z + d.y * gp.z + q.z * gd.y + d.z * gp.y));
+               v[5] += (double)(w * (q.z * gd.z + d.z * gp.z));
+            }
+         }
+      }
+   }
+   if (do_e) {
+      double x = warp_sum(acc[0]), y = warp_sum(acc[1]);
+      if ((threadIdx.x & 31) == 0) {
+         atomicAdd(&dbuf[D_EP_RECIP], x);
+         atomicAdd(&dbuf[D_EP_SELF], y);
+      }
+   }
+   if (DO_G && do_v)
+      block_add(v, 6, dbuf + D_VIR_PREC);
+}
+
+// E_pol = -1/2 f sum u_d . udir_p / alpha
+__global__ void k_ep_dot(int n3, real f, const real4* __restrict__ tpj, const real* __restrict__ ud, const real* __restrict__ udirp,
+   double* __restrict__ dbuf)
+{
+   int q = blockIdx.x * blockDim.x + threadIdx.x;
+   double e = 0;
+   if (q < n3)
+      e = (double)(tpj[q / 3].z * ud[q] * udirp[q]);
+   e = warp_sum(e);
+   if ((threadIdx.x & 31) == 0 && e != 0.0)
+      atomicAdd(&dbuf[D_EP_DOT], -0.5 * (double)f * e);
+}
+
+// cmp with the induced dipoles added to the dipole slot (for the cross virial)
+__global__ void k_add_dipole(int n, const real4* __restrict__ mp0, const real* __restrict__ u, real4* __restrict__ out)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   real4 m = mp0[s];
+   m.y += u[3 * s];
+   m.z += u[3 * s + 1];
+   m.w += u[3 * s + 2];
+   out[s] = m;
+}
+
+__global__ void k_grad_out(int n, const int* __restrict__ perm, const fixed_t* __restrict__ gx, const fixed_t* __restrict__ gy,
+   const fixed_t* __restrict__ gz, double* __restrict__ out)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   int i = perm[s];
+   const double inv = 1.0 / APX_FIXED_SCALE;
+   out[3 * i] = (double)(long long)gx[s] * inv;
+   out[3 * i + 1] = (double)(long long)gy[s] * inv;
+   out[3 * i + 2] = (double)(long long)gz[s] * inv;
+}
+
+__global__ void k_trq_to_real(int n3, const fixed_t* __restrict__ in, real* __restrict__ out)
+{
+   int q = blockIdx.x * blockDim.x + threadIdx.x;
+   if (q < n3)
+      out[q] = (real)((double)(long long)in[q] * (1.0 / APX_FIXED_SCALE));
+}
+
+RecipX make_recipx(apx_ctx* c)
+{
+   RecipX X;
+   int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
+   double a[3][3];
+   for (int cc = 0; cc < 3; ++cc)
+      for (int f = 0; f < 3; ++f)
+         a[cc][f] = nf[f] * (double)c->box.r[3 * f + cc];
+   const int qi1[6] = {0, 1, 2, 0, 0, 1}, qi2[6] = {0, 1, 2, 1, 2, 2};
+   auto at = [&](int f, int cc) { return a[cc][f]; };
+   double ftc[6][6];
+   for (int i1 = 0; i1 < 3; ++i1) {
+      int k = qi1[i1];
+      for (int i2 = 0; i2 < 3; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi1[i2], k);
+      for (int i2 = 3; i2 < 6; ++i2)
+         ftc[i2][i1] = 2 * at(qi1[i2], k) * at(qi2[i2], k);
+   }
+   for (int i1 = 3; i1 < 6; ++i1) {
+      int k = qi1[i1], m = qi2[i1];
+      for (int i2 = 0; i2 < 3; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi1[i2], m);
+      for (int i2 = 3; i2 < 6; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi2[i2], m) + at(qi1[i2], m) * at(qi2[i2], k);
+   }
+   for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+         X.a[i][j] = (real)a[i][j];
+   for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j)
+         X.ftc[i][j] = (real)ftc[i][j];
+   for (int i = 0; i < 9; ++i)
+      X.rc[i] = c->box.r[i];
+   for (int i = 0; i < 3; ++i)
+      X.nf[i] = nf[i];
+   return X;
+}
+
+inline int tile_grid(apx_ctx* c, int ntiles)
+{
+   int want = (ntiles + 3) / 4;
+   int cap = c->sm_count * 8;
+   return want < 1 ? 1 : (want < cap ? want : cap);
+}
+} // namespace
+
+void apx_dfield_full(apx_ctx* c, bool want_ev);
+void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
+
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out)
+{
+   const int n = c->n, n3 = 3 * n;
+   cudaStream_t st = c->stream;
+   const bool do_e = vers & APX_ENERGY, do_g = vers & APX_GRAD, do_v = (vers & APX_VIRIAL) && do_g, do_a = vers & APX_ANALYZ;
+   do_m = do_m && c->opt.use_mpole;
+   do_p = do_p && c->opt.use_polar;
+   const bool ewald = c->opt.use_ewald != 0;
+   const bool pair_ep = do_e && do_a;          // ANALYZE: pairwise polarization energy; otherwise dot product
+   cudaEventRecord(c->ev2, st);
+   if (!c->mpole_inited)
+      apx_rotpole(c);
+   // ---- zero accumulators
+   CUDA_CHECK(cudaMemsetAsync(c->gx.p, 0, sizeof(fixed_t) * c->npad, st));
+   CUDA_CHECK(cudaMemsetAsync(c->gy.p, 0, sizeof(fixed_t) * c->npad, st));
+   CUDA_CHECK(cudaMemsetAsync(c->gz.p, 0, sizeof(fixed_t) * c->npad, st));
+   CUDA_CHECK(cudaMemsetAsync(c->trqf.p, 0, sizeof(fixed_t) * 3 * c->npad, st));
+   CUDA_CHECK(cudaMemsetAsync(c->ebuf.p, 0, sizeof(fixed_t) * 8, st));
+   CUDA_CHECK(cudaMemsetAsync(c->cnt.p, 0, sizeof(int) * 4, st));
+   // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
+   CUDA_CHECK(cudaMemsetAsync(c->dbuf.p, 0, sizeof(double) * D_TOTAL, st));
+   int iters = 0;
+   if (do_p) {
+      apx_induce_impl(c);
+      iters = c->stats.pcg_iterations;
+   } else if (ewald) {
+      apx_pme_mpole(c, true);
+   }
+   // ---- real space
+   MplarArgs A;
+   A.n = n;
+   A.ntiles = c->mlist.ntiles;
+   A.box = c->box;
+   A.cut2 = (real)(c->opt.cutoff * c->opt.cutoff);
+   A.aewald = (real)c->opt.aewald;
+   A.f = c->f_elec;
+   A.iblk = c->mlist.iblk;
+   A.katom = c->mlist.katom;
+   A.posd = c->posd;
+   A.tpj = c->tpj;
+   A.thlval = c->thlval;
+   A.nj = c->opt.njpolar;
+   A.table = c->thole_table;
+   A.mp0 = c->mp0;
+   A.mp1 = c->mp1;
+   A.mp2 = c->mp2;
+   A.ud = c->uind;
+   A.up = c->uinp;
+   A.do_m = do_m;
+   A.do_p = do_p;
+   A.mutual = c->opt.poltyp_mutual;
+   A.do_e = do_e;
+   A.do_v = do_v;
+   A.do_a = do_a;
+   A.pair_ep = pair_ep;
+   A.gx = c->gx;
+   A.gy = c->gy;
+   A.gz = c->gz;
+   A.trq = c->trqf;
+   A.ebuf = c->ebuf;
+   A.cnt = c->cnt;
+   if (A.ntiles > 0 && (do_m || do_p) && (do_g || do_e)) {
+      int grid = tile_grid(c, A.ntiles);
+      if (do_g && ewald) k_mplar_tiles<true, true><<<grid, APX_BLOCK, 0, st>>>(A);
+      else if (do_g) k_mplar_tiles<true, false><<<grid, APX_BLOCK, 0, st>>>(A);
+      else if (ewald) k_mplar_tiles<false, true><<<grid, APX_BLOCK, 0, st>>>(A);
+      else k_mplar_tiles<false, false><<<grid, APX_BLOCK, 0, st>>>(A);
+      APX_COUNT_LAUNCH(c);
+      if (c->nexcl > 0) {
+         int g = (c->nexcl + 127) / 128;
+         if (do_g) k_mplar_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A);
+         else k_mplar_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A);
+         APX_COUNT_LAUNCH(c);
+      }
+   }
+   // ---- reciprocal space + self
+   if (ewald) {
+      RecipX X = make_recipx(c);
+      int g = (n + 127) / 128;
+      if (do_m) {
+         if (do_g)
+            k_recip_mpole<true><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0, c->mp1, c->mp2, c->fmp, c->fphi,
+               c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+         else
+            k_recip_mpole<false><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0, c->mp1, c->mp2, c->fmp, c->fphi,
+               c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+         APX_COUNT_LAUNCH(c);
+      }
+      if (do_p && (do_g || pair_ep)) {
+         if (do_g)
+            apx_pme_uind_fphi(c, c->uind, c->uinp, true);
+         if (do_g)
+            k_recip_polar<true><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0, c->mp1,
+               c->mp2, c->fmp, c->fphi, c->uind, c->uinp, c->fphid, c->fphip, c->fphidp, c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+         else
+            k_recip_polar<false><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0, c->mp1,
+               c->mp2, c->fmp, c->fphi, c->uind, c->uinp, c->fphid, c->fphip, c->fphidp, c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+         APX_COUNT_LAUNCH(c);
+         if (do_v) {
+            // (M + up) x (M + ud) structure-factor product
+            k_add_dipole<<<g, 128, 0, st>>>(n, c->mp0, c->uinp, c->mpx_a);
+            k_add_dipole<<<g, 128, 0, st>>>(n, c->mp0, c->uind, c->mpx_b);
+            c->stats.kernel_launches += 2;
+            apx_pme_cross_virial(c, c->mpx_a, c->mpx_b, c->dbuf.p + D_VIR_CROSS);
+         }
+      }
+   }
+   if (do_p && do_e && !pair_ep) {
+      k_ep_dot<<<(n3 + 255) / 256, 256, 0, st>>>(n3, c->f_elec, c->tpj, c->uind, c->udirp, c->dbuf);
+      APX_COUNT_LAUNCH(c);
+   }
+   // ---- torques -> forces
+   if (do_g) {
+      k_trq_to_real<<<(n3 + 255) / 256, 256, 0, st>>>(n3, c->trqf, c->trq);
+      APX_COUNT_LAUNCH(c);
+      apx_torque(c, do_v);
+   }
+   // ---- reductions to the host (energy.cpp:334-384)
+   fixed_t eb[8];
+   double db[D_TOTAL];
+   int cn[4];
+   CUDA_CHECK(cudaMemcpyAsync(eb, c->ebuf.p, sizeof(eb), cudaMemcpyDeviceToHost, st));
+   CUDA_CHECK(cudaMemcpyAsync(db, c->dbuf.p, sizeof(db), cudaMemcpyDeviceToHost, st));
+   CUDA_CHECK(cudaMemcpyAsync(cn, c->cnt.p, sizeof(cn), cudaMemcpyDeviceToHost, st));
+   cudaEventRecord(c->ev3, st);
+   CUDA_CHECK(cudaStreamSynchronize(st));
+   cudaEventElapsedTime(&c->stats.ms_energy, c->ev2, c->ev3);
+   auto fx = [](fixed_t v) { return (double)(long long)v / APX_FIXED_SCALE; };
+   apx_energy_result r;
+   r.em = r.ep = 0;
+   r.nem = r.nep = 0;
+   if (do_e && do_m)
+      r.em = fx(eb[0]) + (ewald ? db[D_EM_RECIP] + db[D_EM_SELF] : 0.0);
+   if (do_e && do_p)
+      r.ep = pair_ep ? fx(eb[1]) + (ewald ? db[D_EP_RECIP] + db[D_EP_SELF] : 0.0) : db[D_EP_DOT];
+   r.esum = r.em + r.ep;
+   if (do_a) {
+      r.nem = do_m ? cn[0] + (ewald ? n : 0) : 0;
+      r.nep = do_p ? cn[0] + (ewald ? n : 0) : 0;
+   }
+   for (int q = 0; q < 9; ++q)
+      r.virial[q] = 0;
+   if (do_v) {
+      double v6[6];
+      for (int q = 0; q < 6; ++q) {
+         v6[q] = fx(eb[2 + q]) + db[D_VIR_TRQ + q];
+         if (ewald) {
+            if (do_m)
+               v6[q] += db[D_VIR_MREC + q] + db[D_CONV_E + 1 + q];
+            if (do_p)
+               v6[q] += db[D_VIR_PREC + q] - db[D_CONV_E + 1 + q] + db[D_VIR_CROSS + q];
+         }
+      }
+      r.virial[0] = v6[0], r.virial[1] = v6[1], r.virial[2] = v6[2];
+      r.virial[3] = v6[1], r.virial[4] = v6[3], r.virial[5] = v6[4];
+      r.virial[6] = v6[2], r.virial[7] = v6[4], r.virial[8] = v6[5];
+   }
+   r.pcg_iterations = iters;
+   r.pcg_eps = do_p ? c->scal_h[2] : 0.0;
+   if (out)
+      *out = r;
+}
+
+void apx_grad_to_caller(apx_ctx* c, double* dev_out)
+{
+   k_grad_out<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->perm, c->gx, c->gy, c->gz, dev_out);
+   APX_COUNT_LAUNCH(c);
+}

@@ -1,0 +1,383 @@
+// Spatial sort + 32x32 tile neighbor list (our own structure; plays the role of the reference's
+// Spatial / spatialDataInit_cu / spatialCheck_cu, include/ff/spatial.h:15-140, src/cu/spatial.cu:728-960).
+//
+// * atoms are wrapped into the cell and sorted along a Morton curve (30-bit key, cub radix sort);
+//   32 consecutive sorted atoms form a block with an axis-aligned bounding box;
+// * for every i-block one warp scans the k-blocks >= i-block (box-box test, 32 candidates per
+//   step), then tests each atom of a surviving block against the i-box and ballot-compacts the
+//   hits into that i-block's k-atom list; lists are padded to multiples of 32 => tiles;
+// * two passes (count, exclusive scan, fill) so the list has no fixed capacity (the reference
+//   throws when its LSTCAP=48 tiles per block overflow, spatial.cu:708-716);
+// * the list is rebuilt when any atom moved more than buffer/2 since the last build, the
+//   reference's criterion (src/nblist.cpp:521-531).
+#include "apx_internal.h"
+#include <cub/cub.cuh>
+
+namespace {
+__device__ __forceinline__ unsigned spread3(unsigned v)
+{
+   v &= 0x3ff;
+   v = (v | (v << 16)) & 0x030000ff;
+   v = (v | (v << 8)) & 0x0300f00f;
+   v = (v | (v << 4)) & 0x030c30c3;
+   v = (v | (v << 2)) & 0x09249249;
+   return v;
+}
+
+__device__ __forceinline__ void wrap_pos(const Box& b, double x, double y, double z, real& wx, real& wy, real& wz, real& fx,
+   real& fy, real& fz)
+{
+   double f1 = x * (double)b.r[0] + y * (double)b.r[1] + z * (double)b.r[2];
+   double f2 = x * (double)b.r[3] + y * (double)b.r[4] + z * (double)b.r[5];
+   double f3 = x * (double)b.r[6] + y * (double)b.r[7] + z * (double)b.r[8];
+   f1 -= floor(f1);
+   f2 -= floor(f2);
+   f3 -= floor(f3);
+   if (f1 >= 1.0) f1 = 0.0;
+   if (f2 >= 1.0) f2 = 0.0;
+   if (f3 >= 1.0) f3 = 0.0;
+   fx = (real)f1;
+   fy = (real)f2;
+   fz = (real)f3;
+   wx = (real)(f1 * (double)b.l[0] + f2 * (double)b.l[1] + f3 * (double)b.l[2]);
+   wy = (real)(f1 * (double)b.l[3] + f2 * (double)b.l[4] + f3 * (double)b.l[5]);
+   wz = (real)(f1 * (double)b.l[6] + f2 * (double)b.l[7] + f3 * (double)b.l[8]);
+}
+
+__global__ void k_sortkeys(int n, Box b, const double* __restrict__ xyz, unsigned* __restrict__ key, int* __restrict__ val)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   real wx, wy, wz, fx, fy, fz;
+   wrap_pos(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], wx, wy, wz, fx, fy, fz);
+   unsigned qx = min(1023u, (unsigned)(fx * 1024));
+   unsigned qy = min(1023u, (unsigned)(fy * 1024));
+   unsigned qz = min(1023u, (unsigned)(fz * 1024));
+   key[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+   val[i] = i;
+}
+
+// per-step: wrapped positions into sorted slots (also used at rebuild)
+__global__ void k_gather_pos(int n, int npad, Box b, const double* __restrict__ xyz, const int* __restrict__ perm,
+   const real* __restrict__ pdamp, real4* __restrict__ posd)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= npad)
+      return;
+   real4 o;
+   if (s < n) {
+      int i = perm[s];
+      real fx, fy, fz;
+      wrap_pos(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], o.x, o.y, o.z, fx, fy, fz);
+      o.w = pdamp[i];
+   } else {
+      o.x = o.y = o.z = 0;
+      o.w = 0;
+   }
+   posd[s] = o;
+}
+
+__global__ void k_gather_static(int n, int npad, const int* __restrict__ perm, int* __restrict__ inv,
+   const real* __restrict__ thole, const real* __restrict__ polarity, const int* __restrict__ jpolar, real4* __restrict__ tpj)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= npad)
+      return;
+   real4 o;
+   if (s < n) {
+      int i = perm[s];
+      inv[i] = s;
+      real pol = polarity[i];
+      o.x = thole[i];
+      o.y = pol;
+      o.z = (real)1 / (pol > (real)1e-16 ? pol : (real)1e-16);   // polarity_inv, epolar.cpp:505
+#ifdef APX_DOUBLE
+      o.w = __longlong_as_double((long long)jpolar[i]);
+#else
+      o.w = __int_as_float(jpolar[i]);
+#endif
+   } else {
+      o.x = o.y = 0;
+      o.z = 1;
+      o.w = 0;
+   }
+   tpj[s] = o;
+}
+
+__global__ void k_excl_sorted(int nx, const int* __restrict__ ik, const real* __restrict__ sc, const int* __restrict__ inv,
+   PairExcl* __restrict__ out)
+{
+   int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= nx)
+      return;
+   PairExcl p;
+   p.i = inv[ik[2 * e]];
+   p.k = inv[ik[2 * e + 1]];
+   p.m = sc[4 * e] - 1;
+   p.d = sc[4 * e + 1] - 1;
+   p.p = sc[4 * e + 2] - 1;
+   p.u = sc[4 * e + 3] - 1;
+   out[e] = p;
+}
+
+// one warp per block: bounding box centre / half extent
+__global__ void k_block_boxes(int n, int nblk, const real4* __restrict__ posd, real4* __restrict__ ctr, real4* __restrict__ ext)
+{
+   int w = (blockIdx.x * blockDim.x + threadIdx.x) / APX_WARP;
+   int lane = threadIdx.x & 31;
+   if (w >= nblk)
+      return;
+   int s = w * 32 + lane;
+   bool ok = s < n;
+   real4 p = posd[ok ? s : w * 32];      // first atom of the block always exists
+   real lox = p.x, hix = p.x, loy = p.y, hiy = p.y, loz = p.z, hiz = p.z;
+   #pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+      hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+      loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+      hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+      loz = min(loz, __shfl_xor_sync(0xffffffffu, loz, o));
+      hiz = max(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+   }
+   if (lane == 0) {
+      real4 c, e;
+      c.x = (real)0.5 * (lox + hix);
+      c.y = (real)0.5 * (loy + hiy);
+      c.z = (real)0.5 * (loz + hiz);
+      c.w = 0;
+      e.x = (real)0.5 * (hix - lox);
+      e.y = (real)0.5 * (hiy - loy);
+      e.z = (real)0.5 * (hiz - loz);
+      e.w = 0;
+      ctr[w] = c;
+      ext[w] = e;
+   }
+}
+
+__device__ __forceinline__ void image_d(const Box& b, real& dx, real& dy, real& dz)
+{
+   if (b.orthogonal) {
+      dx -= b.lx * rint(dx * b.ilx);
+      dy -= b.ly * rint(dy * b.ily);
+      dz -= b.lz * rint(dz * b.ilz);
+   } else {
+      real f1 = dx * b.r[0] + dy * b.r[1] + dz * b.r[2];
+      real f2 = dx * b.r[3] + dy * b.r[4] + dz * b.r[5];
+      real f3 = dx * b.r[6] + dy * b.r[7] + dz * b.r[8];
+      f1 -= rint(f1);
+      f2 -= rint(f2);
+      f3 -= rint(f3);
+      dx = f1 * b.l[0] + f2 * b.l[1] + f3 * b.l[2];
+      dy = f1 * b.l[3] + f2 * b.l[4] + f3 * b.l[5];
+      dz = f1 * b.l[6] + f2 * b.l[7] + f3 * b.l[8];
+   }
+}
+
+// FILL = false: count k atoms per i-block.  FILL = true: write them.
+template <bool FILL>
+__global__ void k_build(int n, int nblk, Box b, real range, const real4* __restrict__ posd, const real4* __restrict__ ctr,
+   const real4* __restrict__ ext, int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ iblk,
+   int* __restrict__ katom)
+{
+   int ib = (blockIdx.x * blockDim.x + threadIdx.x) / APX_WARP;
+   int lane = threadIdx.x & 31;
+   if (ib >= nblk)
+      return;
+   const real range2 = range * range;
+   real4 ci = ctr[ib], ei = ext[ib];
+   int total = 0;
+   int base = FILL ? offsets[ib] * 32 : 0;
+   // the i-block itself: all its atoms (pairs are filtered k>i in the kernels)
+   {
+      int s = ib * 32 + lane;
+      unsigned m = __ballot_sync(0xffffffffu, s < n);
+      if (FILL && s < n)
+         katom[base + __popc(m & ((1u << lane) - 1))] = s;
+      total += __popc(m);
+   }
+   for (int kb0 = ib + 1; kb0 < nblk; kb0 += 32) {
+      int kb = kb0 + lane;
+      bool hit = false;
+      if (kb < nblk) {
+         real4 ck = ctr[kb], ek = ext[kb];
+         real dx = ck.x - ci.x, dy = ck.y - ci.y, dz = ck.z - ci.z;
+         image_d(b, dx, dy, dz);
+         dx = max((real)0, fabs(dx) - ei.x - ek.x);
+         dy = max((real)0, fabs(dy) - ei.y - ek.y);
+         dz = max((real)0, fabs(dz) - ei.z - ek.z);
+         hit = dx * dx + dy * dy + dz * dz <= range2;
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, hit);
+      while (hm) {
+         int j = __ffs(hm) - 1;
+         hm &= hm - 1;
+         int s = (kb0 + j) * 32 + lane;
+         bool in = false;
+         if (s < n) {
+            real4 p = posd[s];
+            real dx = p.x - ci.x, dy = p.y - ci.y, dz = p.z - ci.z;
+            image_d(b, dx, dy, dz);
+            dx = max((real)0, fabs(dx) - ei.x);
+            dy = max((real)0, fabs(dy) - ei.y);
+            dz = max((real)0, fabs(dz) - ei.z);
+            in = dx * dx + dy * dy + dz * dz <= range2;
+         }
+         unsigned m = __ballot_sync(0xffffffffu, in);
+         if (FILL && in)
+            katom[base + total + __popc(m & ((1u << lane) - 1))] = s;
+         total += __popc(m);
+      }
+   }
+   if (!FILL) {
+      if (lane == 0)
+         counts[ib] = (total + 31) / 32;     // tiles for this i-block
+   } else {
+      int ntile = (total + 31) / 32;
+      for (int q = total + lane; q < ntile * 32; q += 32)
+         katom[base + q] = -1;
+      for (int t = lane; t < ntile; t += 32)
+         iblk[offsets[ib] + t] = ib;
+   }
+}
+
+__global__ void k_count_pairs(int n, int ntiles, Box b, real cut2, const real4* __restrict__ posd, const int* __restrict__ iblk,
+   const int* __restrict__ katom, unsigned long long* __restrict__ out)
+{
+   int w = (blockIdx.x * blockDim.x + threadIdx.x) / APX_WARP;
+   int lane = threadIdx.x & 31;
+   int nw = gridDim.x * blockDim.x / APX_WARP;
+   unsigned long long c = 0;
+   for (int t = w; t < ntiles; t += nw) {
+      int si = iblk[t] * 32 + lane;
+      real4 pi = posd[min(si, n - 1)];
+      int sk = katom[t * 32 + lane];
+      real4 pk = posd[max(sk, 0)];
+      for (int j = 0; j < 32; ++j) {
+         int src = (lane + j) & 31;
+         real kx = __shfl_sync(0xffffffffu, pk.x, src), ky = __shfl_sync(0xffffffffu, pk.y, src),
+              kz = __shfl_sync(0xffffffffu, pk.z, src);
+         int ks = __shfl_sync(0xffffffffu, sk, src);
+         real dx = kx - pi.x, dy = ky - pi.y, dz = kz - pi.z;
+         image_d(b, dx, dy, dz);
+         if (si < n && ks > si && dx * dx + dy * dy + dz * dz <= cut2)
+            ++c;
+      }
+   }
+   for (int o = 16; o > 0; o >>= 1)
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+   if (lane == 0 && c)
+      atomicAdd(out, c);
+}
+
+__global__ void k_check_moved(int n, const double* __restrict__ xyz, const double* __restrict__ ref, double lim2, int* flag)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   double dx = xyz[3 * i] - ref[3 * i], dy = xyz[3 * i + 1] - ref[3 * i + 1], dz = xyz[3 * i + 2] - ref[3 * i + 2];
+   if (dx * dx + dy * dy + dz * dz > lim2)
+      *flag = 1;
+}
+
+void build_one(apx_ctx* c, TileList& L)
+{
+   int n = c->n, nblk = c->nblk;
+   int nthreads = nblk * 32;
+   int grid = (nthreads + APX_BLOCK - 1) / APX_BLOCK;
+   L.counts.ensure(nblk + 1);
+   L.offsets.ensure(nblk + 1);
+   real range = L.cutoff + L.buffer;
+   k_build<false><<<grid, APX_BLOCK, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.counts, nullptr,
+      nullptr, nullptr);
+   CUDA_CHECK(cudaMemsetAsync(L.counts.p + nblk, 0, sizeof(int), c->stream));
+   size_t need = 0;
+   cub::DeviceScan::ExclusiveSum(nullptr, need, L.counts.p, L.offsets.p, nblk + 1, c->stream);
+   if (need > c->cubtmp.cap)
+      c->cubtmp.ensure(need);
+   need = c->cubtmp.cap;
+   cub::DeviceScan::ExclusiveSum(c->cubtmp.p, need, L.counts.p, L.offsets.p, nblk + 1, c->stream);
+   int ntiles = 0;
+   CUDA_CHECK(cudaMemcpyAsync(&ntiles, L.offsets.p + nblk, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   L.ntiles = ntiles;
+   L.iblk.ensure(ntiles + 1);
+   L.katom.ensure((size_t)ntiles * 32 + 32);
+   k_build<true><<<grid, APX_BLOCK, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, nullptr, L.offsets,
+      L.iblk, L.katom);
+   c->stats.kernel_launches += 2;
+}
+} // namespace
+
+void apx_update_sorted_positions(apx_ctx* c)
+{
+   int g = (c->npad + 255) / 256;
+   k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);
+   APX_COUNT_LAUNCH(c);
+}
+
+void apx_list_refresh(apx_ctx* c, bool force)
+{
+   int n = c->n;
+   bool rebuild = force || !c->list_valid;
+   if (!rebuild) {
+      // moved more than buffer/2 since the last build?  (src/nblist.cpp:521-531)
+      double lim = 0.5 * c->opt.list_buffer;
+      CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream));
+      k_check_moved<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->xyz_d, c->xyz_ref, lim * lim, c->flags);
+      APX_COUNT_LAUNCH(c);
+      CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      rebuild = c->flags_h[0] != 0;
+   }
+   if (!rebuild) {
+      apx_update_sorted_positions(c);
+      return;
+   }
+   cudaEventRecord(c->ev2, c->stream);
+   // 1. sort along the Morton curve
+   k_sortkeys<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->box, c->xyz_d, c->sortkey, c->permtmp);
+   size_t need = 0;
+   cub::DeviceRadixSort::SortPairs(nullptr, need, c->sortkey.p, c->sortkey2.p, c->permtmp.p, c->perm.p, n, 0, 30, c->stream);
+   if (need > c->cubtmp.cap)
+      c->cubtmp.ensure(need);
+   need = c->cubtmp.cap;
+   cub::DeviceRadixSort::SortPairs(c->cubtmp.p, need, c->sortkey.p, c->sortkey2.p, c->permtmp.p, c->perm.p, n, 0, 30, c->stream);
+   // 2. sorted copies of per-atom data
+   int g = (c->npad + 255) / 256;
+   k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);
+   k_gather_static<<<g, 256, 0, c->stream>>>(n, c->npad, c->perm, c->inv, c->thole_o, c->polarity_o, c->jpolar_o, c->tpj);
+   if (c->nexcl)
+      k_excl_sorted<<<(c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_ik, c->excl_sc, c->inv, c->excl_s);
+   // 3. block boxes and the two tile lists
+   k_block_boxes<<<(c->nblk * 32 + APX_BLOCK - 1) / APX_BLOCK, APX_BLOCK, 0, c->stream>>>(n, c->nblk, c->posd, c->blk_ctr, c->blk_ext);
+   c->stats.kernel_launches += 6;
+   build_one(c, c->mlist);
+   if (c->opt.use_polar && c->opt.pcgprec && c->opt.usolve_cutoff > 0)
+      build_one(c, c->ulist);
+   else
+      c->ulist.ntiles = 0;
+   CUDA_CHECK(cudaMemcpyAsync(c->xyz_ref, c->xyz_d, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, c->stream));
+   // pair count inside the cutoff (roofline accounting only)
+   {
+      unsigned long long* cnt = (unsigned long long*)c->dbuf.p;
+      CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
+      real cut2 = c->mlist.cutoff * c->mlist.cutoff;
+      int grid = min(c->sm_count * 16, (c->mlist.ntiles + 3) / 4);
+      if (grid > 0)
+         k_count_pairs<<<grid, APX_BLOCK, 0, c->stream>>>(n, c->mlist.ntiles, c->box, cut2, c->posd, c->mlist.iblk, c->mlist.katom, cnt);
+      unsigned long long h = 0;
+      CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      cudaEventRecord(c->ev3, c->stream);
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      c->stats.npairs_m = (long long)h;
+      APX_COUNT_LAUNCH(c);
+   }
+   cudaEventElapsedTime(&c->stats.ms_list, c->ev2, c->ev3);
+   c->stats.ntiles_m = c->mlist.ntiles;
+   c->stats.ntiles_u = c->ulist.ntiles;
+   c->stats.list_rebuilds++;
+   c->list_valid = 1;
+   c->mpole_inited = 0;     // sorted multipoles must be regenerated in the new order
+}

@@ -1,0 +1,756 @@
+// PME reciprocal pipeline: order-5 B-spline spreading of multipoles / induced-dipole pairs, 3-D FFT
+// (cuFFT C2C, the d-dipoles in the real and the p-dipoles in the imaginary part as the reference
+// packs them, src/acc/pme.cpp:147-183), influence-function multiply, and the gather of potential
+// derivatives -- gridMpole/gridUind/pmeConv/fphiMpole/fphiUind(2) + the cart<->frac transforms of
+// src/pme.cpp:221-351, src/cu/pme.cu:14-1007 and the recip/self field terms of
+// src/cu/amoeba/field.cu:13-24,72-104.
+//
+// Organisation: one WARP per atom.  Lanes 0..2 build the three 1-D spline tables
+// (values + 3 derivatives) in shared memory; the 125 stencil points are then covered by the 32
+// lanes so that neighbouring lanes touch neighbouring x-addresses.  Cartesian->fractional
+// conversion of the multipoles/dipoles is done inside the spread kernel, the fractional->Cartesian
+// conversion and the Ewald self term inside the gather kernel, so a ufield round trip is
+// memset + spread + FFT + multiply + FFT + gather.  The influence function is tabulated once per
+// box (the reference recomputes exp() per grid point on every call, "TODO: store vs recompute",
+// src/amoeba/field.cpp:87).
+#include "apx_internal.h"
+#include <cmath>
+
+namespace {
+struct Xform {
+   real a[3][3];     // a[c][f] = nfft_f * recip_f[c]   (cart -> frac for vectors: v_f = sum_c a[c][f] v_c)
+   real ctf[6][6];   // quadrupole cart -> frac
+   real ftc[6][6];   // potential second derivatives frac -> cart
+};
+
+// --- B-splines ---------------------------------------------------------------------------------
+// th[p][l]: l-th derivative of the order-5 spline weight of stencil point p (p = 0..4)
+__device__ void bspline5(real w, real th[5][4])
+{
+   real a2[2] = {1 - w, w};
+   real a3[3], a4[4], a5[5];
+   // order k from order k-1 :  M_k[j] = ((w + k-1-j) M_{k-1}[j-1] + (j+1-w) M_{k-1}[j]) / (k-1)
+   a3[0] = (real)0.5 * (1 - w) * a2[0];
+   a3[1] = (real)0.5 * ((w + 1) * a2[0] + (2 - w) * a2[1]);
+   a3[2] = (real)0.5 * w * a2[1];
+   const real t3 = (real)(1.0 / 3.0);
+   a4[0] = t3 * (1 - w) * a3[0];
+   a4[1] = t3 * ((w + 2) * a3[0] + (2 - w) * a3[1]);
+   a4[2] = t3 * ((w + 1) * a3[1] + (3 - w) * a3[2]);
+   a4[3] = t3 * w * a3[2];
+   a5[0] = (real)0.25 * (1 - w) * a4[0];
+   a5[1] = (real)0.25 * ((w + 3) * a4[0] + (2 - w) * a4[1]);
+   a5[2] = (real)0.25 * ((w + 2) * a4[1] + (3 - w) * a4[2]);
+   a5[3] = (real)0.25 * ((w + 1) * a4[2] + (4 - w) * a4[3]);
+   a5[4] = (real)0.25 * w * a4[3];
+   // derivative of an order-k spline = backward difference of the order-(k-1) spline
+   real d1[5] = {-a4[0], a4[0] - a4[1], a4[1] - a4[2], a4[2] - a4[3], a4[3]};
+   real e3[4] = {-a3[0], a3[0] - a3[1], a3[1] - a3[2], a3[2]};
+   real d2[5] = {-e3[0], e3[0] - e3[1], e3[1] - e3[2], e3[2] - e3[3], e3[3]};
+   real g2[3] = {-a2[0], a2[0] - a2[1], a2[1]};
+   real g3[4] = {-g2[0], g2[0] - g2[1], g2[1] - g2[2], g2[2]};
+   real d3[5] = {-g3[0], g3[0] - g3[1], g3[1] - g3[2], g3[2] - g3[3], g3[3]};
+   #pragma unroll
+   for (int p = 0; p < 5; ++p) {
+      th[p][0] = a5[p];
+      th[p][1] = d1[p];
+      th[p][2] = d2[p];
+      th[p][3] = d3[p];
+   }
+}
+
+struct Stencil {
+   int i1, i2, i3;   // first grid index along each axis
+};
+
+// lanes 0..2 fill sth[warp][dim][5][4]; every lane returns the stencil origin
+__device__ __forceinline__ Stencil make_stencil(const Box& b, real4 pos, int n1, int n2, int n3, real (*sth)[5][4], int lane)
+{
+   real f[3];
+   f[0] = pos.x * b.r[0] + pos.y * b.r[1] + pos.z * b.r[2];
+   f[1] = pos.x * b.r[3] + pos.y * b.r[4] + pos.z * b.r[5];
+   f[2] = pos.x * b.r[6] + pos.y * b.r[7] + pos.z * b.r[8];
+   int nf[3] = {n1, n2, n3};
+   int ig[3];
+   real ww[3];
+   #pragma unroll
+   for (int d = 0; d < 3; ++d) {
+      real w = f[d] + (real)0.5;
+      w -= floor(w);
+      real fr = nf[d] * w;
+      int ii = (int)floor(fr);
+      if (ii >= nf[d]) ii = nf[d] - 1;      // w == 1-ulp rounding guard
+      ww[d] = fr - ii;
+      ii -= 4;
+      ig[d] = ii < 0 ? ii + nf[d] : ii;
+   }
+   if (lane < 3) {
+      real w = lane == 0 ? ww[0] : (lane == 1 ? ww[1] : ww[2]);
+      bspline5(w, sth[lane]);
+   }
+   __syncwarp();
+   Stencil s = {ig[0], ig[1], ig[2]};
+   return s;
+}
+
+__device__ __forceinline__ int wrapi(int i, int n) { return i >= n ? i - n : i; }
+
+// --- spread ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_spread_mpole(int n, Box box, Xform X, int n1, int n2, int n3,
+   const real4* __restrict__ posd, const real4* __restrict__ mp0, const real4* __restrict__ mp1, const real2* __restrict__ mp2,
+   real* __restrict__ fmp_out, cplx* __restrict__ grid)
+{
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   int s = blockIdx.x * 4 + wib;
+   if (s >= n)
+      return;
+   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   real4 m0 = mp0[s], m1 = mp1[s];
+   real2 m2 = mp2[s];
+   // Cartesian multipole with the off-diagonal quadrupoles doubled (rpoleToCmp), then -> fractional
+   real cq[6] = {m1.x, m1.w, m2.y, 2 * m1.y, 2 * m1.z, 2 * m2.x};   // xx yy zz xy xz yz
+   real cd[3] = {m0.y, m0.z, m0.w};
+   real fm[10];
+   fm[0] = m0.x;
+   #pragma unroll
+   for (int f = 0; f < 3; ++f)
+      fm[1 + f] = X.a[0][f] * cd[0] + X.a[1][f] * cd[1] + X.a[2][f] * cd[2];
+   #pragma unroll
+   for (int j = 0; j < 6; ++j) {
+      real t = 0;
+      #pragma unroll
+      for (int k = 0; k < 6; ++k)
+         t += X.ctf[k][j] * cq[k];
+      fm[4 + j] = t;
+   }
+   if (fmp_out && lane < 10) {
+      real val = fm[0];
+      #pragma unroll
+      for (int q = 1; q < 10; ++q)
+         if (lane == q)
+            val = fm[q];
+      fmp_out[10 * s + lane] = val;
+   }
+   for (int p = lane; p < 125; p += 32) {
+      int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+      const real* t = sth[wib][0][ix];
+      const real* u = sth[wib][1][iy];
+      const real* v = sth[wib][2][iz];
+      real t0 = t[0], t1 = t[1], t2 = t[2], u0 = u[0], u1 = u[1], u2 = u[2], v0 = v[0], v1 = v[1], v2 = v[2];
+      real val = fm[0] * t0 * u0 * v0 + fm[1] * t1 * u0 * v0 + fm[2] * t0 * u1 * v0 + fm[3] * t0 * u0 * v1 + fm[4] * t2 * u0 * v0
+         + fm[5] * t0 * u2 * v0 + fm[6] * t0 * u0 * v2 + fm[7] * t1 * u1 * v0 + fm[8] * t1 * u0 * v1 + fm[9] * t0 * u1 * v1;
+      int idx = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1);
+      atomicAdd(&grid[idx].x, val);
+   }
+}
+
+// dipole pair (d -> real, p -> imaginary).  If beta != nullptr the CG direction update
+// p <- z + beta p  (pcgP3, src/cu/induce.cu:172-190) is applied on the fly and written back.
+__global__ void __launch_bounds__(128) k_spread_uind(int n, Box box, Xform X, int n1, int n2, int n3,
+   const real4* __restrict__ posd, real* __restrict__ ud, real* __restrict__ up, const real* __restrict__ zd,
+   const real* __restrict__ zp, const double* __restrict__ scal, cplx* __restrict__ grid)
+{
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   int s = blockIdx.x * 4 + wib;
+   if (s >= n)
+      return;
+   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   real d[3] = {ud[3 * s], ud[3 * s + 1], ud[3 * s + 2]};
+   real q[3] = {up[3 * s], up[3 * s + 1], up[3 * s + 2]};
+   if (zd) {
+      // scal[0],[1] = r.z of the previous iteration, scal[4],[5] = r.z of this one
+      double s0 = scal[0], s1 = scal[1];
+      real b = s0 != 0.0 ? (real)(scal[4] / s0) : (real)0;
+      real bp = s1 != 0.0 ? (real)(scal[5] / s1) : (real)0;
+      #pragma unroll
+      for (int c = 0; c < 3; ++c) {
+         d[c] = zd[3 * s + c] + b * d[c];
+         q[c] = zp[3 * s + c] + bp * q[c];
+      }
+      __syncwarp();
+      if (lane < 3) {
+         ud[3 * s + lane] = d[lane];
+         up[3 * s + lane] = q[lane];
+      }
+   }
+   real fd[3], fp[3];
+   #pragma unroll
+   for (int f = 0; f < 3; ++f) {
+      fd[f] = X.a[0][f] * d[0] + X.a[1][f] * d[1] + X.a[2][f] * d[2];
+      fp[f] = X.a[0][f] * q[0] + X.a[1][f] * q[1] + X.a[2][f] * q[2];
+   }
+   for (int p = lane; p < 125; p += 32) {
+      int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+      const real* t = sth[wib][0][ix];
+      const real* u = sth[wib][1][iy];
+      const real* v = sth[wib][2][iz];
+      real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
+      real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
+      real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
+      int idx = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1);
+#ifdef APX_DOUBLE
+      atomicAdd(&grid[idx].x, vd);
+      atomicAdd(&grid[idx].y, vp);
+#else
+      atomicAdd(reinterpret_cast<float2*>(&grid[idx]), make_float2(vd, vp));
+#endif
+   }
+}
+
+// --- influence function ------------------------------------------------------------------------
+__global__ void k_make_qfac(int n1, int n2, int n3, Box box, real pterm, real volterm, const real* __restrict__ bs1,
+   const real* __restrict__ bs2, const real* __restrict__ bs3, real* __restrict__ qfac)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int ntot = n1 * n2 * n3;
+   if (i >= ntot)
+      return;
+   int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+   int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
+   int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
+   int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
+   double h1 = (double)box.r[0] * r1 + (double)box.r[3] * r2 + (double)box.r[6] * r3;
+   double h2 = (double)box.r[1] * r1 + (double)box.r[4] * r2 + (double)box.r[7] * r3;
+   double h3 = (double)box.r[2] * r1 + (double)box.r[5] * r2 + (double)box.r[8] * r3;
+   double hsq = h1 * h1 + h2 * h2 + h3 * h3;
+   double term = -(double)pterm * hsq;
+   double e = 0;
+   if (i != 0 && term > -50.0)
+      e = exp(term) / ((double)volterm * hsq * (double)bs1[k1] * (double)bs2[k2] * (double)bs3[k3]);
+   qfac[i] = (real)e;
+}
+
+__global__ void k_conv(int ntot, const real* __restrict__ qfac, cplx* __restrict__ grid)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= ntot)
+      return;
+   real f = qfac[i];
+   cplx g = grid[i];
+   g.x *= f;
+   g.y *= f;
+   grid[i] = g;
+}
+
+// multiply + reciprocal energy / virial of |Q|^2 (pmeConv<DO_E,DO_V>); out[0]=e, out[1..6]=vxx,vxy,vxz,vyy,vyz,vzz
+__global__ void k_conv_ev(int n1, int n2, int n3, Box box, real pterm, real felec, const real* __restrict__ qfac,
+   cplx* __restrict__ grid, double* __restrict__ out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int ntot = n1 * n2 * n3;
+   double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+   if (i < ntot) {
+      real f = qfac[i];
+      cplx g = grid[i];
+      if (f != 0) {
+         int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+         int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
+         int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
+         int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
+         double h1 = (double)box.r[0] * r1 + (double)box.r[3] * r2 + (double)box.r[6] * r3;
+         double h2 = (double)box.r[1] * r1 + (double)box.r[4] * r2 + (double)box.r[7] * r3;
+         double h3 = (double)box.r[2] * r1 + (double)box.r[5] * r2 + (double)box.r[8] * r3;
+         double hsq = h1 * h1 + h2 * h2 + h3 * h3;
+         double term = -(double)pterm * hsq;
+         double struc2 = (double)g.x * g.x + (double)g.y * g.y;
+         double eterm = 0.5 * (double)felec * (double)f * struc2;
+         double vterm = (2.0 / hsq) * (1.0 - term) * eterm;
+         acc[0] = eterm;
+         acc[1] = h1 * h1 * vterm - eterm;
+         acc[2] = h1 * h2 * vterm;
+         acc[3] = h1 * h3 * vterm;
+         acc[4] = h2 * h2 * vterm - eterm;
+         acc[5] = h2 * h3 * vterm;
+         acc[6] = h3 * h3 * vterm - eterm;
+      }
+      g.x *= f;
+      g.y *= f;
+      grid[i] = g;
+   }
+   __shared__ double sh[7][8];
+   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   #pragma unroll
+   for (int q = 0; q < 7; ++q) {
+      double x = acc[q];
+      for (int o = 16; o > 0; o >>= 1)
+         x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0)
+         sh[q][w] = x;
+   }
+   __syncthreads();
+   if (threadIdx.x < 7) {
+      double x = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k)
+         x += sh[threadIdx.x][k];
+      if (x != 0.0)
+         atomicAdd(&out[threadIdx.x], x);
+   }
+}
+
+// structure-factor cross product of two transformed grids (epolarEwaldRecipSelfVirial_cu5)
+__global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real felec, const real* __restrict__ qfac,
+   const cplx* __restrict__ ga, const cplx* __restrict__ gb, double* __restrict__ out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   int ntot = n1 * n2 * n3;
+   double acc[6] = {0, 0, 0, 0, 0, 0};
+   if (i < ntot) {
+      real f = qfac[i];
+      if (f != 0) {
+         int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+         int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
+         int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
+         int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
+         double h1 = (double)box.r[0] * r1 + (double)box.r[3] * r2 + (double)box.r[6] * r3;
+         double h2 = (double)box.r[1] * r1 + (double)box.r[4] * r2 + (double)box.r[7] * r3;
+         double h3 = (double)box.r[2] * r1 + (double)box.r[5] * r2 + (double)box.r[8] * r3;
+         double hsq = h1 * h1 + h2 * h2 + h3 * h3;
+         double term = -(double)pterm * hsq;
+         cplx a = ga[i], b = gb[i];
+         double struc2 = (double)a.x * b.x + (double)a.y * b.y;
+         double eterm = 0.5 * (double)felec * (double)f * struc2;
+         double vterm = (2.0 / hsq) * (1.0 - term) * eterm;
+         acc[0] = h1 * h1 * vterm - eterm;
+         acc[1] = h1 * h2 * vterm;
+         acc[2] = h1 * h3 * vterm;
+         acc[3] = h2 * h2 * vterm - eterm;
+         acc[4] = h2 * h3 * vterm;
+         acc[5] = h3 * h3 * vterm - eterm;
+      }
+   }
+   __shared__ double sh[6][8];
+   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+   #pragma unroll
+   for (int q = 0; q < 6; ++q) {
+      double x = acc[q];
+      for (int o = 16; o > 0; o >>= 1)
+         x += __shfl_xor_sync(0xffffffffu, x, o);
+      if (lane == 0)
+         sh[q][w] = x;
+   }
+   __syncthreads();
+   if (threadIdx.x < 6) {
+      double x = 0;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k)
+         x += sh[threadIdx.x][k];
+      if (x != 0.0)
+         atomicAdd(&out[threadIdx.x], x);
+   }
+}
+
+// --- gather ------------------------------------------------------------------------------------
+// 25 lanes own one (iy,iz) row of five x-points each.
+// MODE 0: permanent multipoles: fphi[20] stored; field assigned: fd = term*dipole - grad_cart(phi)
+// MODE 1: ufield: fd = term*ud - cart(fphi_d[1..3]), fp likewise (recip + self, ASSIGNED)
+// MODE 2: energy step: fphid[10], fphip[10], fphidp[20] stored
+template <int MODE>
+__global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
+   const real4* __restrict__ posd, const cplx* __restrict__ grid, const real4* __restrict__ mp0, const real* __restrict__ ud,
+   const real* __restrict__ up, real* __restrict__ out_a, real* __restrict__ out_b, real* __restrict__ out_c)
+{
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   int s = blockIdx.x * 4 + wib;
+   if (s >= n)
+      return;
+   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   // row sums over x for derivative orders 0..3, real and imaginary parts
+   real tr[4] = {0, 0, 0, 0}, ti[4] = {0, 0, 0, 0};
+   real u[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+   if (lane < 25) {
+      int iy = lane % 5, iz = lane / 5;
+      int base = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1;
+      #pragma unroll
+      for (int ix = 0; ix < 5; ++ix) {
+         cplx g = grid[base + wrapi(st.i1 + ix, n1)];
+         const real* t = sth[wib][0][ix];
+         #pragma unroll
+         for (int l = 0; l < 4; ++l) {
+            tr[l] += g.x * t[l];
+            if (MODE != 0)
+               ti[l] += g.y * t[l];
+         }
+      }
+      #pragma unroll
+      for (int l = 0; l < 4; ++l) {
+         u[l] = sth[wib][1][iy][l];
+         v[l] = sth[wib][2][iz][l];
+      }
+   }
+#define WSUM(x)                                                                                                          \
+   for (int o = 16; o > 0; o >>= 1)                                                                                        \
+      x += __shfl_xor_sync(0xffffffffu, x, o)
+   if (MODE == 0) {
+      // 20 derivative combinations (a,b,c) in the reference's fphi order
+      real f[20];
+      f[0] = tr[0] * u[0] * v[0];
+      f[1] = tr[1] * u[0] * v[0];
+      f[2] = tr[0] * u[1] * v[0];
+      f[3] = tr[0] * u[0] * v[1];
+      f[4] = tr[2] * u[0] * v[0];
+      f[5] = tr[0] * u[2] * v[0];
+      f[6] = tr[0] * u[0] * v[2];
+      f[7] = tr[1] * u[1] * v[0];
+      f[8] = tr[1] * u[0] * v[1];
+      f[9] = tr[0] * u[1] * v[1];
+      f[10] = tr[3] * u[0] * v[0];
+      f[11] = tr[0] * u[3] * v[0];
+      f[12] = tr[0] * u[0] * v[3];
+      f[13] = tr[2] * u[1] * v[0];
+      f[14] = tr[2] * u[0] * v[1];
+      f[15] = tr[1] * u[2] * v[0];
+      f[16] = tr[0] * u[2] * v[1];
+      f[17] = tr[1] * u[0] * v[2];
+      f[18] = tr[0] * u[1] * v[2];
+      f[19] = tr[1] * u[1] * v[1];
+      #pragma unroll
+      for (int q = 0; q < 20; ++q) {
+         WSUM(f[q]);
+      }
+      if (lane < 20) {
+         real val = f[0];
+         #pragma unroll
+         for (int q = 1; q < 20; ++q)
+            if (lane == q)
+               val = f[q];
+         out_a[20 * s + lane] = val;
+      }
+      if (lane < 3) {
+         // Cartesian gradient of the reciprocal potential, component `lane`
+         real cphi = X.a[lane][0] * f[1] + X.a[lane][1] * f[2] + X.a[lane][2] * f[3];
+         real4 m0 = mp0[s];
+         real d = lane == 0 ? m0.y : (lane == 1 ? m0.z : m0.w);
+         out_b[3 * s + lane] = selfterm * d - cphi;
+      }
+   } else if (MODE == 1) {
+      real fd[3] = {tr[1] * u[0] * v[0], tr[0] * u[1] * v[0], tr[0] * u[0] * v[1]};
+      real fp[3] = {ti[1] * u[0] * v[0], ti[0] * u[1] * v[0], ti[0] * u[0] * v[1]};
+      #pragma unroll
+      for (int q = 0; q < 3; ++q) {
+         WSUM(fd[q]);
+         WSUM(fp[q]);
+      }
+      if (lane < 3) {
+         real cd = X.a[lane][0] * fd[0] + X.a[lane][1] * fd[1] + X.a[lane][2] * fd[2];
+         real cp = X.a[lane][0] * fp[0] + X.a[lane][1] * fp[1] + X.a[lane][2] * fp[2];
+         out_a[3 * s + lane] = selfterm * ud[3 * s + lane] - cd;
+         out_b[3 * s + lane] = selfterm * up[3 * s + lane] - cp;
+      }
+   } else {
+      real fd[10], fp[10], fs[20];
+      real ts[4];
+      #pragma unroll
+      for (int l = 0; l < 4; ++l)
+         ts[l] = tr[l] + ti[l];
+#define COMBO(arr, t)                                                                                                    \
+   arr[0] = t[0] * u[0] * v[0];                                                                                            \
+   arr[1] = t[1] * u[0] * v[0];                                                                                            \
+   arr[2] = t[0] * u[1] * v[0];                                                                                            \
+   arr[3] = t[0] * u[0] * v[1];                                                                                            \
+   arr[4] = t[2] * u[0] * v[0];                                                                                            \
+   arr[5] = t[0] * u[2] * v[0];                                                                                            \
+   arr[6] = t[0] * u[0] * v[2];                                                                                            \
+   arr[7] = t[1] * u[1] * v[0];                                                                                            \
+   arr[8] = t[1] * u[0] * v[1];                                                                                            \
+   arr[9] = t[0] * u[1] * v[1];
+      COMBO(fd, tr)
+      COMBO(fp, ti)
+      COMBO(fs, ts)
+      fs[10] = ts[3] * u[0] * v[0];
+      fs[11] = ts[0] * u[3] * v[0];
+      fs[12] = ts[0] * u[0] * v[3];
+      fs[13] = ts[2] * u[1] * v[0];
+      fs[14] = ts[2] * u[0] * v[1];
+      fs[15] = ts[1] * u[2] * v[0];
+      fs[16] = ts[0] * u[2] * v[1];
+      fs[17] = ts[1] * u[0] * v[2];
+      fs[18] = ts[0] * u[1] * v[2];
+      fs[19] = ts[1] * u[1] * v[1];
+      fd[0] = 0;
+      fp[0] = 0;
+      #pragma unroll
+      for (int q = 0; q < 10; ++q) {
+         WSUM(fd[q]);
+         WSUM(fp[q]);
+      }
+      #pragma unroll
+      for (int q = 0; q < 20; ++q) {
+         WSUM(fs[q]);
+      }
+      if (lane == 0) {
+         #pragma unroll
+         for (int q = 0; q < 10; ++q) {
+            out_a[10 * s + q] = fd[q];
+            out_b[10 * s + q] = fp[q];
+         }
+         #pragma unroll
+         for (int q = 0; q < 20; ++q)
+            out_c[20 * s + q] = fs[q];
+      }
+   }
+#undef WSUM
+#undef COMBO
+}
+
+// --- host side ---------------------------------------------------------------------------------
+void bspline_host(double x, int n, double* c)   // tinker/source/pmestuf.f:134-158, 1-based c
+{
+   c[1] = 1.0 - x;
+   c[2] = x;
+   for (int k = 3; k <= n; ++k) {
+      double denom = 1.0 / (k - 1);
+      c[k] = x * c[k - 1] * denom;
+      for (int i = 1; i <= k - 2; ++i)
+         c[k - i] = ((x + i) * c[k - i - 1] + (k - i - x) * c[k - i]) * denom;
+      c[1] = (1.0 - x) * c[1] * denom;
+   }
+}
+
+std::vector<double> dftmod_host(int nfft, int order)   // pmestuf.f:172-237
+{
+   std::vector<double> c(order + 2, 0.0), bsarray(nfft, 0.0), mod(nfft, 0.0);
+   bspline_host(0.0, order, c.data());
+   for (int i = 0; i < order; ++i)
+      bsarray[i + 1] = c[i + 1];
+   const double pi = M_PI;
+   double factor = 2.0 * pi / nfft;
+   for (int i = 0; i < nfft; ++i) {
+      double s1 = 0, s2 = 0;
+      for (int j = 0; j < nfft; ++j) {
+         double arg = factor * ((double)i * j);
+         s1 += bsarray[j] * cos(arg);
+         s2 += bsarray[j] * sin(arg);
+      }
+      mod[i] = s1 * s1 + s2 * s2;
+   }
+   const double eps = 1.0e-7;
+   if (mod[0] < eps)
+      mod[0] = 0.5 * mod[1];
+   for (int i = 1; i < nfft - 1; ++i)
+      if (mod[i] < eps)
+         mod[i] = 0.5 * (mod[i - 1] + mod[i + 1]);
+   if (mod[nfft - 1] < eps)
+      mod[nfft - 1] = 0.5 * mod[nfft - 2];
+   const int jcut = 50;
+   for (int i = 1; i <= nfft; ++i) {
+      int k = i - 1;
+      if (i > nfft / 2)
+         k -= nfft;
+      double zeta = 1.0;
+      if (k != 0) {
+         double sum1 = 1.0, sum2 = 1.0;
+         double fac = pi * k / nfft;
+         for (int j = 1; j <= jcut; ++j) {
+            double a1 = fac / (fac + pi * j), a2 = fac / (fac - pi * j);
+            sum1 += pow(a1, order) + pow(a2, order);
+            sum2 += pow(a1, 2 * order) + pow(a2, 2 * order);
+         }
+         zeta = sum2 / sum1;
+      }
+      mod[i - 1] *= zeta * zeta;
+   }
+   return mod;
+}
+
+Xform make_xform(apx_ctx* c)
+{
+   Xform X;
+   double a[3][3];
+   int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
+   for (int cc = 0; cc < 3; ++cc)
+      for (int f = 0; f < 3; ++f)
+         a[cc][f] = nf[f] * (double)c->box.r[3 * f + cc];
+   const int qi1[6] = {0, 1, 2, 0, 0, 1}, qi2[6] = {0, 1, 2, 1, 2, 2};
+   double ctf[6][6], ftc[6][6];
+   for (int i1 = 0; i1 < 3; ++i1) {
+      int k = qi1[i1];
+      for (int i2 = 0; i2 < 6; ++i2)
+         ctf[i2][i1] = a[qi1[i2]][k] * a[qi2[i2]][k];
+   }
+   for (int i1 = 3; i1 < 6; ++i1) {
+      int k = qi1[i1], m = qi2[i1];
+      for (int i2 = 0; i2 < 6; ++i2)
+         ctf[i2][i1] = a[qi1[i2]][k] * a[qi2[i2]][m] + a[qi2[i2]][k] * a[qi1[i2]][m];
+   }
+   // frac -> cart uses at[f][c] = a[c][f]
+   auto at = [&](int f, int cc) { return a[cc][f]; };
+   for (int i1 = 0; i1 < 3; ++i1) {
+      int k = qi1[i1];
+      for (int i2 = 0; i2 < 3; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi1[i2], k);
+      for (int i2 = 3; i2 < 6; ++i2)
+         ftc[i2][i1] = 2 * at(qi1[i2], k) * at(qi2[i2], k);
+   }
+   for (int i1 = 3; i1 < 6; ++i1) {
+      int k = qi1[i1], m = qi2[i1];
+      for (int i2 = 0; i2 < 3; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi1[i2], m);
+      for (int i2 = 3; i2 < 6; ++i2)
+         ftc[i2][i1] = at(qi1[i2], k) * at(qi2[i2], m) + at(qi1[i2], m) * at(qi2[i2], k);
+   }
+   for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+         X.a[i][j] = (real)a[i][j];
+   for (int i = 0; i < 6; ++i)
+      for (int j = 0; j < 6; ++j) {
+         X.ctf[i][j] = (real)ctf[i][j];
+         X.ftc[i][j] = (real)ftc[i][j];
+      }
+   return X;
+}
+
+inline void fft(apx_ctx* c, int dir)
+{
+#ifdef APX_DOUBLE
+   CUFFT_CHECK(cufftExecZ2Z(c->plan, c->qgrid, c->qgrid, dir));
+#else
+   CUFFT_CHECK(cufftExecC2C(c->plan, c->qgrid, c->qgrid, dir));
+#endif
+}
+inline real selfterm(apx_ctx* c)
+{
+   double a = c->opt.aewald;
+   return (real)(4.0 / 3.0 * a * a * a / sqrt(M_PI));
+}
+inline size_t ntot(apx_ctx* c) { return (size_t)c->nfft1 * c->nfft2 * c->nfft3; }
+} // namespace
+
+void apx_pme_setup(apx_ctx* c)
+{
+   if (!c->opt.use_ewald)
+      return;
+   c->nfft1 = c->opt.nfft[0];
+   c->nfft2 = c->opt.nfft[1];
+   c->nfft3 = c->opt.nfft[2];
+   if (c->opt.bsorder != 5)
+      APX_THROW("only pme-order 5 is built (the reference hard-codes MAX_BSORDER 5, include/seq/bsplgen.h)");
+   size_t K = ntot(c);
+   c->qgrid.ensure(K);
+   c->qfac.ensure(K);
+   if (!c->plan_ok) {
+#ifdef APX_DOUBLE
+      CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_Z2Z));
+#else
+      CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_C2C));
+#endif
+      CUFFT_CHECK(cufftSetStream(c->plan, c->stream));
+      c->plan_ok = 1;
+   }
+   int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
+   DevBuf<real>* bs[3] = {&c->bsmod1, &c->bsmod2, &c->bsmod3};
+   for (int d = 0; d < 3; ++d) {
+      std::vector<double> m = dftmod_host(nf[d], 5);
+      std::vector<real> mr(m.begin(), m.end());
+      bs[d]->ensure(nf[d]);
+      CUDA_CHECK(cudaMemcpyAsync(bs[d]->p, mr.data(), sizeof(real) * nf[d], cudaMemcpyHostToDevice, c->stream));
+      CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   }
+   double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
+   double volterm = M_PI * (double)c->box.volume;
+   k_make_qfac<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, (real)volterm,
+      c->bsmod1, c->bsmod2, c->bsmod3, c->qfac);
+   APX_COUNT_LAUNCH(c);
+}
+
+void apx_pme_destroy(apx_ctx* c)
+{
+   if (c->plan_ok)
+      cufftDestroy(c->plan);
+   c->plan_ok = 0;
+}
+
+static void conv(apx_ctx* c, bool want_ev, double* out)
+{
+   size_t K = ntot(c);
+   if (want_ev) {
+      double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
+      k_conv_ev<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, c->f_elec, c->qfac,
+         c->qgrid, out);
+   } else {
+      k_conv<<<(int)((K + 255) / 256), 256, 0, c->stream>>>((int)K, c->qfac, c->qgrid);
+   }
+   APX_COUNT_LAUNCH(c);
+}
+
+// permanent multipoles: fills fmp, fphi and ASSIGNS field = recip + self part of dfield.
+// dbuf[16] = recip |Q|^2 energy, dbuf[17..22] = its virial (vir_m) when want_ev.
+void apx_pme_mpole(apx_ctx* c, bool want_ev)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   size_t K = ntot(c);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, c->mp0, c->mp1, c->mp2,
+      c->fmp, c->qgrid);
+   APX_COUNT_LAUNCH(c);
+   fft(c, CUFFT_FORWARD);
+   if (want_ev)
+      CUDA_CHECK(cudaMemsetAsync(c->dbuf.p + 16, 0, 7 * sizeof(double), c->stream));
+   conv(c, want_ev, c->dbuf.p + 16);
+   fft(c, CUFFT_INVERSE);
+   k_gather<0><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, c->mp0,
+      nullptr, nullptr, c->fphi, c->field, nullptr);
+   APX_COUNT_LAUNCH(c);
+   c->mpole_pme_valid = 1;
+}
+
+// recip + self part of the mutual field; optional fused direction update (beta from scal)
+void apx_pme_ufield(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp, const double* scal_beta, real* zd, real* zp)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   size_t K = ntot(c);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up,
+      scal_beta ? zd : nullptr, zp, scal_beta, c->qgrid);
+   APX_COUNT_LAUNCH(c);
+   fft(c, CUFFT_FORWARD);
+   conv(c, false, nullptr);
+   fft(c, CUFFT_INVERSE);
+   k_gather<1><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
+      ud, up, fd, fp, nullptr);
+   APX_COUNT_LAUNCH(c);
+}
+
+// energy step: fphid, fphip (10 each) and fphidp (20) of the converged dipoles
+void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   size_t K = ntot(c);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up, nullptr,
+      nullptr, nullptr, c->qgrid);
+   APX_COUNT_LAUNCH(c);
+   fft(c, CUFFT_FORWARD);
+   conv(c, false, nullptr);
+   fft(c, CUFFT_INVERSE);
+   k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
+      ud, up, c->fphid, c->fphip, c->fphidp);
+   APX_COUNT_LAUNCH(c);
+}
+
+// structure-factor product of the grids of (M + up) and (M + ud): two spreads + two forward FFTs
+// (epolarEwaldRecipSelfVirial_cu3..5, src/cu/epolarrecip.cu:476-509)
+void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   size_t K = ntot(c);
+   c->qgrid2.ensure(K);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, mpa, c->mp1, c->mp2, nullptr,
+      c->qgrid);
+   fft(c, CUFFT_FORWARD);
+   CUDA_CHECK(cudaMemcpyAsync(c->qgrid2.p, c->qgrid.p, K * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, mpb, c->mp1, c->mp2, nullptr,
+      c->qgrid);
+   fft(c, CUFFT_FORWARD);
+   double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
+   k_cross_virial<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, c->f_elec, c->qfac,
+      c->qgrid, c->qgrid2, out6);
+   c->stats.kernel_launches += 3;
+}
