@@ -8,6 +8,7 @@ void apx_to_sorted(apx_ctx* c, const double* in_dev, real* out);
 void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev);
 void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
+void apx_grad_to_caller(apx_ctx* c, double* dev_out);
 
 static thread_local std::string g_err;
 
@@ -439,8 +440,6 @@ int apx_epolar(apx_ctx* c, int vers, apx_energy_result* out)
    apx_energy_impl(c, vers, false, true, out);
    API_END
 }
-
-void apx_grad_to_caller(apx_ctx* c, double* dev_out);
 
 int apx_get_gradient(apx_ctx* c, double* grad)
 {
