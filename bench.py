@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""Benchmark of the AMOEBA polarizable-electrostatics hot path (BASELINE.json metric) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...            # reference arm: CPU oracle on host cores
+
+One "step" = one pass of the hot path over the dhfr2 system (BASELINE.json configs[1]):
+energy(energy+grad) restricted to the electrostatic terms = mpoleInit + induce() (PCG) +
+fused real-space multipole/polarization + reciprocal space + torque + reductions
+(SURVEY.md §3.1 "HOT").  The metric carries both numbers BASELINE.json names:
+
+  value          ns/day-equivalent of the hot path alone at 2 fs per outer RESPA step
+                 (one electrostatics evaluation per step; vdW / valence / integrator are NOT
+                 in this repo yet -- SURVEY.md §8f -- so this is NOT a full-MD ns/day)
+  ms_per_induce  mean device time of one induce() call
+
+N > 1: dhfr2 is latency bound on one GPU, so ranks run independent replicas (SURVEY §8e
+"replicas only"); value is the aggregate over replicas, time is the max over ranks.
+
+`value` is measured with positions resident in HBM; `e2e` goes through the public host API
+(set_positions from host memory -> energy -> gradient back to host) inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+FS_PER_STEP = 2.0
+METRIC = "ns/day (electrostatics hot path only, 2 fs/step) & ms/induce() AMOEBA DHFR 23.5k atoms"
+WORKLOAD = "dhfr2 AMOEBA DHFR 23558 atoms, PME 64^3 order 5, ewald-cutoff 7.0, polar-eps 1e-5, energy+gradient"
+
+
+def ns_per_day(ms_per_step, replicas=1):
+    return replicas * FS_PER_STEP * 1e-6 * (86400.0e3 / ms_per_step)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([t.strip() for t in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_sample(system, full=False):
+    """Time the CPU oracle (numpy port of the reference algorithm, 1 core) on a bounded sample of the
+    same workload: a complete induce() and the real-space energy/gradient of a slice of the pair
+    list, extrapolated to the whole list.  Returns (ms_per_step_estimate, ms_induce, description)."""
+    from oracle.amoeba_ref import Oracle, V4
+    o = Oracle(system)
+    t0 = time.perf_counter()
+    o.rotpole()
+    o.induce()
+    t_ind = time.perf_counter() - t0
+    i, k, R, r = o.pairs(system.ewald_cutoff)
+    npair = i.shape[0]
+    take = npair if full else min(npair, 60000)
+    saved = o._pairs[float(system.ewald_cutoff)]
+    o._pairs[float(system.ewald_cutoff)] = (i[:take], k[:take], R[:take], r[:take])
+    t0 = time.perf_counter()
+    o._real_space(V4, True, True)
+    t_real = (time.perf_counter() - t0) * (npair / take)
+    o._pairs[float(system.ewald_cutoff)] = saved
+    t0 = time.perf_counter()
+    o.empole_recip(V4)
+    o.epolar_recip_self(V4)
+    t_rec = time.perf_counter() - t0
+    ms_step = 1e3 * (t_ind + t_real + t_rec)
+    desc = (f"oracle/amoeba_ref.py (numpy f64 port) on dhfr2: full induce() ({o.niter} iterations) + reciprocal energy/force + "
+            f"real-space energy/gradient on {take} of {npair} pairs scaled to all pairs")
+    return ms_step, 1e3 * t_ind, desc
+
+
+def run_reference(args, rank, world):
+    import tinker_gpu_b200 as tg
+    if rank != 0:
+        return
+    system = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    steps = max(1, min(args.steps, 2))
+    for _ in range(min(args.warmup, 0)):
+        pass
+    ms, ms_ind = [], []
+    desc = ""
+    for _ in range(steps):
+        a, b, desc = cpu_oracle_sample(system)
+        ms.append(a)
+        ms_ind.append(b)
+    ms_step = float(np.mean(ms))
+    val = ns_per_day(ms_step)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "ns/day", "n_gpus": args.gpus, "steps": steps,
+        "warmup": 0, "ms_per_step": ms_step, "ms_per_induce": float(np.mean(ms_ind)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference input deck example/dhfr2 (blob tests/golden/dhfr2.npz)",
+        "config": {"workload": WORKLOAD, "note": "CPU arm: the reference executable needs gfortran (absent); oracle port timed instead"},
+        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import Amoeba, calc
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    system = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    a = Amoeba(system, "mixed", device=local_rank)
+    ext = torch.cuda.ExternalStream(a.lib.apx_stream(a.ctx), device=local_rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    vers = calc.v4
+    rng = np.random.default_rng(1234 + rank)
+    xyz0 = np.array(system.xyz)
+    # per-step host inputs for the e2e leg: thermal-size displacements so list checks are real
+    disp = [xyz0 + rng.normal(scale=0.01, size=xyz0.shape) for _ in range(4)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return a.lib.apx_energy(a.ctx, vers, None)
+
+    def step_e2e(j):
+        a.set_positions(disp[j % len(disp)])
+        r = a.lib.apx_energy(a.ctx, vers, None)
+        a.gradient()
+        return r
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    a.synchronize()
+
+    # ---- resident leg (value): per-step CUDA events on the library stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    a.stats_reset()
+    ms_steps, ms_induce, ms_uf, iters = [], [], [], []
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        rc = step_resident()
+        e1.record(ext)
+        e1.synchronize()
+        if rc != 0:
+            raise SystemExit("apx_energy failed: " + a.lib.apx_last_error().decode())
+        ms_steps.append(e0.elapsed_time(e1))
+        st = a.stats()
+        ms_induce.append(st["ms_induce"])
+        ms_uf.append(st["ms_ufield_real"])
+        iters.append(st["pcg_iterations"])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = a.stats()["kernel_launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = float(np.mean(ms_steps))
+
+    # ---- e2e leg: host positions in, gradient out, every step
+    for j in range(2):
+        step_e2e(j)
+    barrier()
+    ms_e2e = []
+    for j in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        step_e2e(j)
+        e1.record(ext)
+        e1.synchronize()
+        ms_e2e.append(e0.elapsed_time(e1))
+    barrier()
+    ms_e2e_step = float(np.mean(ms_e2e))
+    rebuilds = a.stats()["list_rebuilds"]
+
+    # max over ranks (replicas): the job advances at the pace of the slowest replica
+    if dist is not None:
+        t = torch.tensor([ms_step, ms_e2e_step, float(np.mean(ms_induce))], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e_step, ms_ind = (float(v) for v in t.tolist())
+    else:
+        ms_ind = float(np.mean(ms_induce))
+
+    if rank == 0:
+        st = a.stats()
+        hbm_peak, sm_max, peak_src = load_peaks()
+        n = system.n
+        K = int(np.prod(system.nfft))
+        npairs = max(1, st["npairs_m"])
+        uf_ms = float(np.mean(ms_uf)) if ms_uf else 0.0
+        # real-space ufield tile kernel: algorithmic bytes = read (pos,pdamp,thole,ud,up) + rmw (field d,p) per atom
+        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 33 * st["ntiles_m"]
+        uf_flops = 130.0 * npairs
+        achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
+        sm_clk = (clocks or {}).get("sm_mhz") or sm_max
+        fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
+        line = {
+            "metric": METRIC, "value": ns_per_day(ms_step, world), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_induce": ms_ind,
+            "pcg_iterations": float(np.mean(iters)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 pair math + 2^32 fixed-point / f64 accumulation",
+            "data": "reference input deck example/dhfr2 parsed by our readers (blob tests/golden/dhfr2.npz)",
+            "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
+                       "l2": "flushed (256 MB write) between timed steps; working set is L2 resident within a step",
+                       "timing": "CUDA events on the library stream around each step, mean of steps, max over ranks",
+                       "hot_path_only": True},
+            "e2e": {"value": ns_per_day(ms_e2e_step, world), "unit": "ns/day", "ms_per_step": ms_e2e_step,
+                    "h2d_bytes_per_step": int(xyz0.nbytes), "d2h_bytes_per_step": int(xyz0.nbytes) + 136,
+                    "list_rebuilds": rebuilds},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_ufield_tiles (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
+                         "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "ms_per_launch": uf_ms,
+                         "note": "latency/FP32-pipe bound at this size: see roofline_fp32"},
+            "roofline_fp32": {"achieved": uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0, "peak": fp32_peak,
+                              "unit": "TFLOP/s", "frac": (uf_flops / (uf_ms * 1e-3) / 1e12 / fp32_peak) if uf_ms > 0 else 0.0,
+                              "flop_per_pair": 130, "pairs": int(npairs), "tiles": int(st["ntiles_m"])},
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu:
+            ms_cpu, ms_cpu_ind, desc = cpu_oracle_sample(system)
+            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc,
+                                    "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind}
+        print(json.dumps(line))
+    a.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

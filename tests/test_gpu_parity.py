@@ -1,0 +1,174 @@
+"""Parity of the CUDA path (through the C ABI, tinker-gpu_b200/libapx*.so) with the float64 oracle.
+
+double build : proves the algorithm (tolerances ~1e-9, limited by fixed-point 2^-32 force quanta)
+mixed build  : the shipped precision (float pair math, fixed-point / f64 accumulation); tolerances are
+               the north-star ones where float allows: energy 1e-6 relative, dipoles 1e-6 D RMS;
+               forces are asserted at 5e-5 kcal/mol/A RMS (float pair math).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_case, section
+
+pytestmark = pytest.mark.gpu
+
+DEBYE = 4.803206802
+
+
+def _amoeba(system, precision):
+    from tinker_gpu_b200.amoeba import Amoeba
+    return Amoeba(system, precision)
+
+
+def _rms(a):
+    return float(np.sqrt((np.asarray(a) ** 2).mean()))
+
+
+CASES = ["Local-Frame-1", "Local-Frame-2", "Local-Frame-3", "Local-Frame-4", "Local-Frame3-1", "Local-Frame3-2"]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("precision", ["double", "mixed"])
+def test_small_systems_vs_oracle(case, precision):
+    from tinker_gpu_b200.amoeba import calc
+    from oracle.amoeba_ref import Oracle, V1, V3
+    s = load_case(case)
+    a = _amoeba(s, precision)
+    o = Oracle(s)
+    tol = dict(e=1e-10, g=1e-7, v=1e-6, f=1e-12, u=1e-12) if precision == "double" else dict(e=2e-6, g=1e-4, v=5e-4, f=2e-6, u=5e-6)
+    o.rotpole()
+    assert np.abs(a.rpole() - o.rpole).max() < (1e-14 if precision == "double" else 1e-6)
+    if s.use_polar:
+        fd, fp = a.dfield()
+        od, op = o.dfield()
+        assert np.abs(fd - od).max() < tol["f"] and np.abs(fp - op).max() < tol["f"]
+        n = s.n
+        ud = np.array([[0.1 * (i + 1) + 0.03 * (j + 1) for j in range(3)] for i in range(n)])
+        up = np.array([[0.1 * (i + 1) - 0.03 * (j + 1) for j in range(3)] for i in range(n)])
+        f1, f2 = a.ufield(ud, up)
+        o1, o2 = o.ufield(ud, up)
+        scale = np.abs(o1).max()
+        assert np.abs(f1 - o1).max() < tol["f"] * max(1.0, scale) * 10 and np.abs(f2 - o2).max() < tol["f"] * max(1.0, scale) * 10
+        z1, z2 = a.sparsePrecondApply(ud, up)
+        p1, p2 = o.precond(ud, up)
+        assert np.abs(z1 - p1).max() < tol["f"] * 100 and np.abs(z2 - p2).max() < tol["f"] * 100
+        u1, u2 = a.induce()
+        v1, v2 = o.induce()
+        assert a.stats()["pcg_iterations"] == o.niter
+        assert np.abs(u1 - v1).max() * DEBYE < tol["u"] and np.abs(u2 - v2).max() * DEBYE < tol["u"]
+    r = a.energy(calc.v1)
+    ro = o.energy(V1)
+    assert abs(r["esum"] - ro["esum"]) < tol["e"] * abs(ro["esum"])
+    assert _rms(r["grad"] - ro["grad"]) < tol["g"]
+    assert np.abs(r["virial"] - ro["virial"]).max() < tol["v"] * max(1.0, np.abs(ro["virial"]).max())
+    # ANALYZE path: pairwise polarization energy and interaction counts
+    r3 = a.energy(calc.v3)
+    ro3 = o.energy(V3)
+    assert abs(r3["ep"] - ro3["ep"]) < tol["e"] * max(1.0, abs(ro3["ep"]))
+    nself = s.n if s.use_ewald else 0
+    if s.use_mpole:
+        assert r3["nem"] == ro3["nem"] + nself
+    if s.use_polar:
+        assert r3["nep"] == ro3["nep"] + nself
+    a.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_small_systems_vs_reference_goldens(goldens, case):
+    """The CUDA path against the reference's OWN literals (test/localframe.cpp, test/localframe3.cpp),
+    with the reference's tolerances."""
+    from tinker_gpu_b200.amoeba import calc
+    s = load_case(case)
+    a = _amoeba(s, "mixed")
+    r = a.energy(calc.v1)
+    if case.startswith("Local-Frame3"):
+        ref = section(goldens, case, "emplar")
+        assert abs(r["esum"] - ref["ref_eng"]) < 1e-4
+        assert np.abs(r["grad"] - np.array(ref["ref_g"])).max() < 2e-4
+        assert np.abs(r["virial"] - np.array(ref["ref_v"])).max() < 1e-3
+    elif case in ("Local-Frame-1", "Local-Frame-2"):
+        ref = section(goldens, case, "empole")
+        eref = ref["ref_eng"] if "ref_eng" in ref else ref["ref_ereal"] + ref["ref_erecip"] + ref["ref_eself"]
+        assert abs(r["em"] - eref) < 2e-4
+        assert np.abs(r["grad"] - np.array(ref["ref_grad"]))[:18].max() < 5e-4
+        assert np.abs(r["virial"] - np.array(ref["ref_v"])).max() < 5e-3
+    else:
+        ref = section(goldens, case, "induce")
+        u1, u2 = a.uind()
+        assert np.abs(u1 * DEBYE - np.array(ref["ref_ud_debye"])).max() < 1e-4
+        assert np.abs(u2 * DEBYE - np.array(ref["ref_up_debye"])).max() < 1e-4
+        ref = section(goldens, case, "various")
+        assert abs(r["ep"] - ref["ref_eng"]) < 1e-4
+        assert np.abs(r["grad"] - np.array(ref["ref_grad"]))[:18].max() < 2e-4
+        assert np.abs(r["virial"] - np.array(ref["ref_v"])).max() < 1e-3
+    a.close()
+
+
+@pytest.mark.parametrize("precision", ["double", "mixed"])
+def test_water_box_frames(precision):
+    """2684-atom AMOEBA water box: the reference's two MD frames (test/ref/tinkernist.*) through the
+    CUDA path -- direct and induced dipoles of every atom -- then energy/gradient vs the oracle."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    from oracle.amoeba_ref import Oracle, V1
+    s = tg.load_system(os.path.join(GOLDEN, "water30.npz"))
+    fr = np.load(os.path.join(GOLDEN, "tinkernist_frames.npz"))
+    a = _amoeba(s, precision)
+    for k in range(2):
+        a.set_positions(fr["arc"][k])
+        u1, _ = a.induce()
+        d1, _ = a.udir()
+        assert np.abs(d1 * DEBYE - fr["udir"][k]).max() < 1e-5
+        assert np.abs(u1 * DEBYE - fr["uind"][k]).max() < 2e-5      # reference test tolerance: 1e-3
+    a.set_positions(s.xyz)
+    r = a.energy(calc.v1)
+    o = Oracle(s)
+    ro = o.energy(V1)
+    u1, _ = a.uind()
+    if precision == "double":
+        assert abs(r["esum"] - ro["esum"]) < 1e-10 * abs(ro["esum"])
+        assert _rms(r["grad"] - ro["grad"]) < 1e-7
+        assert _rms(u1 - o.uind) * DEBYE < 1e-10
+    else:
+        assert abs(r["esum"] - ro["esum"]) < 1e-6 * abs(ro["esum"])       # north star: 1e-6 relative
+        assert _rms(u1 - o.uind) * DEBYE < 1e-6                            # north star: 1e-6 D RMS
+        assert _rms(r["grad"] - ro["grad"]) < 5e-5                         # float pair math, DESIGN.md section 8
+    assert r["pcg_iterations"] == o.niter
+    a.close()
+
+
+def test_dhfr2_properties():
+    """Full-size configuration (BASELINE.json configs[0]/[1]) through size-independent properties:
+    net force and net torque-free translation invariance, rebuild invariance, fixed-point determinism
+    of the force sum, and double-vs-mixed agreement."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    s = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    am = _amoeba(s, "mixed")
+    r = am.energy(calc.v4)
+    g = r["grad"]
+    # PME forces do not conserve momentum exactly; the residual must be tiny against the force scale
+    assert np.abs(g.sum(0)).max() < 1e-2 * _rms(g) * np.sqrt(s.n)
+    assert 4 <= r["pcg_iterations"] <= 12
+    # rigid translation by a non-lattice vector: same energy (new list, new sort, new PME phases)
+    am.set_positions(np.array(s.xyz) + np.array([1.2345, -2.5, 0.777]))
+    r2 = am.energy(calc.v4)
+    assert abs(r2["esum"] - r["esum"]) < 2e-5 * abs(r["esum"])       # PME grid discretisation ~1e-5
+    ad = _amoeba(s, "double")
+    rd = ad.energy(calc.v4)
+    assert abs(rd["esum"] - r["esum"]) < 1e-6 * abs(rd["esum"])
+    assert _rms(rd["grad"] - g) < 1e-4
+    ud, _ = ad.uind()
+    am.set_positions(s.xyz)
+    am.energy(calc.v4)
+    um, _ = am.uind()
+    assert _rms(ud - um) * DEBYE < 1e-6
+    am.close()
+    ad.close()
+
+
+def test_no_cpu_fallback_message():
+    from tinker_gpu_b200 import amoeba
+    assert os.path.isfile(amoeba.library_path("mixed")), "libapx.so must be built in-tree"

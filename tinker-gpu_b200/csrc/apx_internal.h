@@ -181,6 +181,9 @@ struct apx_ctx {
    // ---- stats
    apx_stats stats;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+   std::vector<cudaEvent_t> uf_ev;       // event pairs around the real-space ufield launches of one induce()
+   int uf_used = 0;
+   const int* skip = nullptr;            // device flag: kernels of speculative CG iterations return at once when set
    int mpole_inited = 0;
    int induced_valid = 0;
 };

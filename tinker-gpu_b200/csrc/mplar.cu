@@ -736,8 +736,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    const bool ewald = c->opt.use_ewald != 0;
    const bool pair_ep = do_e && do_a;          // ANALYZE: pairwise polarization energy; otherwise dot product
    cudaEventRecord(c->ev2, st);
-   if (!c->mpole_inited)
-      apx_rotpole(c);
+   apx_rotpole(c);      // mpoleInit(vers) runs on every energy() call in the reference (src/amoeba/emplar.cpp:12)
    // ---- zero accumulators
    CUDA_CHECK(cudaMemsetAsync(c->gx.p, 0, sizeof(fixed_t) * c->npad, st));
    CUDA_CHECK(cudaMemsetAsync(c->gy.p, 0, sizeof(fixed_t) * c->npad, st));

@@ -276,6 +276,12 @@ void apx_induce_impl(apx_ctx* c)
    cudaStream_t st = c->stream;
    if (!c->mpole_inited)
       apx_rotpole(c);
+   if (c->uf_ev.empty()) {
+      c->uf_ev.resize(64);
+      for (auto& e : c->uf_ev)
+         CUDA_CHECK(cudaEventCreate(&e));
+   }
+   c->uf_used = 0;
    cudaEventRecord(c->ev0, st);
    apx_dfield_full(c, true);
    c->stats.pcg_iterations = 0;
@@ -314,6 +320,7 @@ void apx_induce_impl(apx_ctx* c)
 
    int iter = 0;
    bool done = false;
+   c->skip = c->flags.p;
    int batch = std::max(1, std::min(c->last_iters, politer));
    while (!done) {
       for (int b = 0; b < batch && iter < politer; ++b) {
@@ -336,6 +343,19 @@ void apx_induce_impl(apx_ctx* c)
       CUDA_CHECK(cudaStreamSynchronize(st));
       done = c->flags_h[1] != 0 || iter >= politer;
       batch = 2;
+   }
+   c->skip = nullptr;
+   {
+      // mean device time of the real-space ufield launches that did work (speculative launches after
+      // convergence return immediately and are excluded: only the first `used+1` pairs count)
+      int used_pairs = std::min(c->uf_used / 2, (c->flags_h[2] > 0 ? c->flags_h[2] : iter) + 1);
+      float tot = 0;
+      for (int k = 0; k < used_pairs; ++k) {
+         float ms = 0;
+         cudaEventElapsedTime(&ms, c->uf_ev[2 * k], c->uf_ev[2 * k + 1]);
+         tot += ms;
+      }
+      c->stats.ms_ufield_real = used_pairs ? tot / used_pairs : 0;
    }
    int used = c->flags_h[2] > 0 ? c->flags_h[2] : iter;
    c->stats.pcg_iterations = used;

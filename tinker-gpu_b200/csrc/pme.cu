@@ -149,8 +149,10 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Box box, Xform X, i
 // p <- z + beta p  (pcgP3, src/cu/induce.cu:172-190) is applied on the fly and written back.
 __global__ void __launch_bounds__(128) k_spread_uind(int n, Box box, Xform X, int n1, int n2, int n3,
    const real4* __restrict__ posd, real* __restrict__ ud, real* __restrict__ up, const real* __restrict__ zd,
-   const real* __restrict__ zp, const double* __restrict__ scal, cplx* __restrict__ grid)
+   const real* __restrict__ zp, const double* __restrict__ scal, cplx* __restrict__ grid, const int* __restrict__ skip)
 {
+   if (skip && skip[1])
+      return;
    __shared__ real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
@@ -348,8 +350,11 @@ __global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real
 template <int MODE>
 __global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
    const real4* __restrict__ posd, const cplx* __restrict__ grid, const real4* __restrict__ mp0, const real* __restrict__ ud,
-   const real* __restrict__ up, real* __restrict__ out_a, real* __restrict__ out_b, real* __restrict__ out_c)
+   const real* __restrict__ up, real* __restrict__ out_a, real* __restrict__ out_b, real* __restrict__ out_c,
+   const int* __restrict__ skip)
 {
+   if (skip && skip[1])
+      return;
    __shared__ real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
@@ -691,7 +696,7 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
    conv(c, want_ev, c->dbuf.p + 16);
    fft(c, CUFFT_INVERSE);
    k_gather<0><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, c->mp0,
-      nullptr, nullptr, c->fphi, c->field, nullptr);
+      nullptr, nullptr, c->fphi, c->field, nullptr, nullptr);
    APX_COUNT_LAUNCH(c);
    c->mpole_pme_valid = 1;
 }
@@ -704,13 +709,13 @@ void apx_pme_ufield(apx_ctx* c, const real* ud, const real* up, real* fd, real* 
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
    k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up,
-      scal_beta ? zd : nullptr, zp, scal_beta, c->qgrid);
+      scal_beta ? zd : nullptr, zp, scal_beta, c->qgrid, c->skip);
    APX_COUNT_LAUNCH(c);
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
    fft(c, CUFFT_INVERSE);
    k_gather<1><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
-      ud, up, fd, fp, nullptr);
+      ud, up, fd, fp, nullptr, c->skip);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -722,13 +727,13 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
    k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up, nullptr,
-      nullptr, nullptr, c->qgrid);
+      nullptr, nullptr, c->qgrid, nullptr);
    APX_COUNT_LAUNCH(c);
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
    fft(c, CUFFT_INVERSE);
    k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
-      ud, up, c->fphid, c->fphip, c->fphidp);
+      ud, up, c->fphid, c->fphip, c->fphidp, nullptr);
    APX_COUNT_LAUNCH(c);
 }
 
