@@ -257,8 +257,9 @@ def run_ours(args, rank, world, local_rank):
         K = int(np.prod(system.nfft))
         npairs = max(1, st["npairs_m"])
         uf_ms = float(np.mean(ms_uf)) if ms_uf else 0.0
-        # real-space ufield tile kernel: algorithmic bytes = read (pos,pdamp,thole,ud,up) + rmw (field d,p) per atom
-        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 33 * st["ntiles_m"]
+        # real-space ufield row kernel: algorithmic bytes = read (pos,pdamp,thole,ud,up) + rmw (field d,p) per atom
+        # + one 4-byte neighbor index per directed pair
+        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 2 * npairs
         uf_flops = 130.0 * npairs
         achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max
@@ -278,13 +279,13 @@ def run_ours(args, rank, world, local_rank):
                     "list_rebuilds": rebuilds},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_ufield_tiles (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
+            "roofline": {"kernel": "k_ufield_rows (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
                          "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": None, "peak_source": peak_src, "ms_per_launch": uf_ms,
                          "note": "latency/FP32-pipe bound at this size: see roofline_fp32"},
             "roofline_fp32": {"achieved": uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0, "peak": fp32_peak,
                               "unit": "TFLOP/s", "frac": (uf_flops / (uf_ms * 1e-3) / 1e12 / fp32_peak) if uf_ms > 0 else 0.0,
-                              "flop_per_pair": 130, "pairs": int(npairs), "tiles": int(st["ntiles_m"])},
+                              "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs)},
             "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu:

@@ -81,12 +81,13 @@ typedef struct apx_energy_result {
 /* timing / counters of the most recent operator call, CUDA events on the library stream */
 typedef struct apx_stats {
    float ms_induce, ms_energy, ms_list;
-   float ms_ufield_real;   /* mean device time of the real-space ufield tile kernel, last induce() */
+   float ms_ufield_real;   /* mean device time of the real-space ufield row kernel, last induce() */
    int pcg_iterations;
    int kernel_launches;    /* launches of this library's own kernels since apx_stats_reset */
    int list_rebuilds;
-   int ntiles_m, ntiles_u; /* 32x32 tiles in the multipole / preconditioner lists */
-   long long npairs_m;     /* pairs inside the real-space cutoff at the last list build, -1 if not counted */
+   long long nverlet;      /* directed entries of the Verlet rows (cutoff + buffer) at the last list build */
+   long long npairs_m;     /* pairs inside the real-space cutoff at the last list build */
+   long long npairs_u;     /* pairs inside the preconditioner range at the last list build */
 } apx_stats;
 
 const char* apx_last_error(void);

@@ -60,7 +60,7 @@ class EnergyResult(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
                 ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
-                ("ntiles_m", C.c_int), ("ntiles_u", C.c_int), ("npairs_m", C.c_longlong)]
+                ("nverlet", C.c_longlong), ("npairs_m", C.c_longlong), ("npairs_u", C.c_longlong)]
 
 
 _LIBS = {}

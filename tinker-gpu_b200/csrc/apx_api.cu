@@ -246,10 +246,8 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    c->cnt.ensure(4);
    c->io_a.ensure(3 * np);
    c->io_b.ensure(3 * np);
-   c->mlist.cutoff = (real)std::min(sys->cutoff, 1.0e6);
-   c->mlist.buffer = (real)sys->list_buffer;
-   c->ulist.cutoff = (real)sys->usolve_cutoff;
-   c->ulist.buffer = 0;       // the reference applies the preconditioner out to cutoff+buffer of its u-list
+   c->list_cutoff = (real)std::min(sys->cutoff, 1.0e6);
+   c->list_buffer = (real)sys->list_buffer;
    apx_pme_setup(c);
    apx_list_refresh(c, true);
    API_END
@@ -279,8 +277,8 @@ void apx_destroy(apx_ctx* c)
    c->perm.release(), c->inv.release(), c->sortkey.release(), c->sortkey2.release(), c->permtmp.release(), c->cubtmp.release();
    c->posd.release(), c->tpj.release(), c->mp0.release(), c->mp1.release(), c->mp2.release(), c->mpx_a.release(), c->mpx_b.release();
    c->blk_ctr.release(), c->blk_ext.release(), c->excl_s.release(), c->flags.release(), c->scal.release();
-   c->mlist.iblk.release(), c->mlist.katom.release(), c->mlist.counts.release(), c->mlist.offsets.release();
-   c->ulist.iblk.release(), c->ulist.katom.release(), c->ulist.counts.release(), c->ulist.offsets.release();
+   c->rows.vstart.release(), c->rows.vcnt.release(), c->rows.vnbr.release(), c->rows.nbr.release();
+   c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
    cudaStreamDestroy(c->stream);

@@ -31,7 +31,7 @@ struct real3 {
 };
 
 #define APX_WARP 32
-#define APX_BLOCK 128                 // 4 warps per CTA for the tile kernels
+#define APX_BLOCK 128
 
 struct ApxError : std::runtime_error {
    using std::runtime_error::runtime_error;
@@ -87,15 +87,19 @@ struct Box {
    real volume;
 };
 
-// 32x32 tile list: tile t pairs the 32 atoms of sorted block iblk[t] with the 32 sorted
-// atom indices katom[32*t .. 32*t+31] (-1 = padding).  Tiles of one i-block are contiguous.
-struct TileList {
-   real cutoff = 0, buffer = 0;
-   int ntiles = 0;
-   DevBuf<int> iblk;
-   DevBuf<int> katom;
-   DevBuf<int> counts;      // per i-block number of k atoms (pass A)
-   DevBuf<int> offsets;     // per i-block first tile
+// Directed per-atom neighbor rows in sorted order (rows.cu).  vnbr holds the Verlet rows
+// (r <= cutoff + buffer at build time, both directions, k ascending); every step nbr receives,
+// at the same row offsets, the atoms with r <= ucut first (count cntu) and then those with
+// ucut < r <= cutoff (row length cnt).  No pair is shared between two rows, so the row kernels
+// need no atomics and their sums are order-deterministic.
+struct RowList {
+   DevBuf<int> vstart;      // [n+1] row offsets
+   DevBuf<int> vcnt;        // [n+1] Verlet row lengths (scan input)
+   DevBuf<int> vnbr;        // Verlet rows
+   DevBuf<int> nbr;         // per-step compacted rows
+   DevBuf<int> cnt, cntu;   // [n]
+   DevBuf<unsigned long long> total;   // [2]: directed pairs within cutoff / ucut at the last compaction
+   long long nverlet = 0;
 };
 
 struct PairExcl {           // exclusion pair in SORTED indices with (scale-1) factors
@@ -138,7 +142,8 @@ struct apx_ctx {
    DevBuf<real2> mp2;                    // {qyz,qzz}
    DevBuf<real4> blk_ctr, blk_ext;       // block bounding boxes
    DevBuf<PairExcl> excl_s;              // exclusions in sorted indices
-   TileList mlist, ulist;
+   real list_cutoff = 0, list_buffer = 0;
+   RowList rows;
    int list_valid = 0;
    DevBuf<int> flags;                    // device flags: [0] rebuild-needed, [1] pcg done, [2] iter ...
    int* flags_h = nullptr;               // pinned mirror
@@ -193,6 +198,9 @@ struct apx_ctx {
 // ---- nblist.cu
 void apx_list_refresh(apx_ctx* c, bool force);
 void apx_update_sorted_positions(apx_ctx* c);
+// ---- rows.cu
+void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort
+void apx_rows_compact(apx_ctx* c, bool count);    // per-step compaction to r <= cutoff
 // ---- frames.cu
 void apx_rotpole(apx_ctx* c);
 void apx_torque(apx_ctx* c, bool do_v);

@@ -1,20 +1,19 @@
-// Real-space field kernels over the 32x32 tile list: permanent field (dfield), mutual field of a
-// dipole pair (ufield, the CG operator) and the short-range preconditioner.
+// Real-space field kernels over the directed neighbor rows (rows.cu): permanent field (dfield),
+// mutual field of a dipole pair (ufield, the CG operator) and the short-range preconditioner.
 // They stand where dfield_cu1 / ufield_cu1 / sparsePrecond_cu1 stand in the reference
 // (src/cu/amoeba/field.cu:37-137, precond.cu:13-43) but are organised differently:
-//   * a warp walks a contiguous run of tiles; the i-block's 32 atoms stay in registers across all
-//     tiles of that block and are flushed once, k-atoms travel round the warp by shuffle together
-//     with their accumulators, so a tile costs 32 lane-rotations and one k-side atomic flush;
-//   * every pair in a tile is evaluated with all exclusion scales = 1 (no per-pair bit masks);
+//   * a group of G lanes owns one atom i and walks the row of its neighbours, one real pair per
+//     lane per step (the reference's 32x32 tiles keep ~8 % of their lanes busy at this density);
+//     the i-side sums are reduced by shuffles and written once -- no atomics, no k-side scatter,
+//     and the result does not depend on scheduling;
+//   * every pair is evaluated with all exclusion scales = 1 (no per-pair bit masks);
 //     the few excluded pairs are corrected afterwards by one thread per listed pair with
 //     (scale-1) non-Ewald terms -- B_n = (s-1) lambda_n rr_n in the notation of pairmath.cuh;
-//   * because d- and p-scaling only differ on excluded pairs, the tile pass accumulates ONE
+//   * because d- and p-scaling only differ on excluded pairs, the row pass accumulates ONE
 //     permanent field; the d/p split is made by the exclusion pass.
 #include "apx_internal.h"
 #include "pairmath.cuh"
-
-#define FULL 0xffffffffu
-#define SHF(v, src) __shfl_sync(FULL, (v), (src))
+#include "rows.cuh"
 
 namespace {
 __device__ __forceinline__ int as_int(real w)
@@ -26,107 +25,53 @@ __device__ __forceinline__ int as_int(real w)
 #endif
 }
 
-struct WarpRange {
-   int t0, t1;
-};
-__device__ __forceinline__ WarpRange warp_tiles(int ntiles)
-{
-   int nw = gridDim.x * (blockDim.x >> 5);
-   int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-   int per = (ntiles + nw - 1) / nw;
-   WarpRange r;
-   r.t0 = min(ntiles, w * per);
-   r.t1 = min(ntiles, r.t0 + per);
-   return r;
-}
-
 // -------------------------------------------------------------------------------------------
 // ufield: field of (ud, up) at every atom, Ewald real space or plain Thole-damped Coulomb
 // -------------------------------------------------------------------------------------------
-template <bool EWALD, bool TABLE>
-__global__ void __launch_bounds__(APX_BLOCK) k_ufield_tiles(int n, int ntiles, Box box, real cut2, real aewald,
-   const int* __restrict__ iblk, const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+template <bool EWALD, bool TABLE, int G>
+__global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
+   const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real* __restrict__ ud, const real* __restrict__ up, real* __restrict__ fd,
    real* __restrict__ fp, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
-   const int lane = threadIdx.x & 31;
-   WarpRange wr = warp_tiles(ntiles);
-   int cur = -1, si = 0;
-   real4 pi;
-   real thi = 0;
-   int jpi = 0;
-   V3 udi, upi, fdi, fpi;
-   for (int t = wr.t0; t < wr.t1; ++t) {
-      int ib = iblk[t];
-      if (ib != cur) {
-         if (cur >= 0 && si < n) {
-            atomic_real3(fd, si, fdi);
-            atomic_real3(fp, si, fpi);
-         }
-         cur = ib;
-         si = ib * 32 + lane;
-         int sl = min(si, n - 1);
-         pi = posd[sl];
-         real4 q = tpj[sl];
-         thi = q.x;
-         jpi = as_int(q.w);
-         udi = v3(ud[3 * sl], ud[3 * sl + 1], ud[3 * sl + 2]);
-         upi = v3(up[3 * sl], up[3 * sl + 1], up[3 * sl + 2]);
-         fdi = v3(0, 0, 0);
-         fpi = v3(0, 0, 0);
-      }
-      int sk = katom[t * 32 + lane];
-      int sl = max(sk, 0);
-      real4 pk = posd[sl];
-      real4 qk = tpj[sl];
-      real thk = qk.x;
-      int jpk = as_int(qk.w);
-      V3 udk = v3(ud[3 * sl], ud[3 * sl + 1], ud[3 * sl + 2]);
-      V3 upk = v3(up[3 * sl], up[3 * sl + 1], up[3 * sl + 2]);
-      V3 fdk = v3(0, 0, 0), fpk = v3(0, 0, 0);
-      #pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-         int src = (lane + j) & 31;
-         int ks = SHF(sk, src);
-         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
-         real pdk = SHF(pk.w, src);
-         real thk_ = SHF(thk, src);
-         int jpk_ = TABLE ? SHF(jpk, src) : 0;
-         V3 a = v3(SHF(udk.x, src), SHF(udk.y, src), SHF(udk.z, src));
-         V3 b = v3(SHF(upk.x, src), SHF(upk.y, src), SHF(upk.z, src));
+   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   {
+      const real4 pi = posd[i];
+      const real4 qi = tpj[i];
+      const int beg = vstart[i];
+      const int len = act ? cnt[i] : 0;
+      V3 fdi = v3(0, 0, 0), fpi = v3(0, 0, 0);
+      for (int q = l; q < len; q += G) {
+         const int k = nbr[beg + q];
+         const real4 pk = posd[k];
+         const real4 qk = tpj[k];
+         const V3 a = v3(ud[3 * k], ud[3 * k + 1], ud[3 * k + 2]);
+         const V3 b = v3(up[3 * k], up[3 * k + 1], up[3 * k + 2]);
+         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
          apx_image(box, dx, dy, dz);
-         real r2 = dx * dx + dy * dy + dz * dz;
-         if (ks > si && si < n && r2 <= cut2) {
-            real rinv = r_rsqrt(r2);
-            real r = r2 * rinv, rr2 = rinv * rinv;
-            real rr[3], bn[3], om[3];
-            radial_coulomb<3>(rinv, rr2, rr);
-            if (EWALD)
-               radial_ewald<3>(r, rinv, rr2, aewald, bn);
-            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
-            thole_one_minus_lambda<3>(r, pi.w, pdk, pg, om);
-            real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
-            real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
-            V3 R = v3(dx, dy, dz);
-            fdi += dipole_field(R, a, B1, B2);
-            fpi += dipole_field(R, b, B1, B2);
-            fdk += dipole_field(R, udi, B1, B2);
-            fpk += dipole_field(R, upi, B1, B2);
-         }
-         int nxt = (lane + 1) & 31;
-         fdk = v3(SHF(fdk.x, nxt), SHF(fdk.y, nxt), SHF(fdk.z, nxt));
-         fpk = v3(SHF(fpk.x, nxt), SHF(fpk.y, nxt), SHF(fpk.z, nxt));
+         const real r2 = dx * dx + dy * dy + dz * dz;
+         const real rinv = r_rsqrt(r2);
+         const real r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[3], bn[3], om[3];
+         radial_coulomb<3>(rinv, rr2, rr);
+         if (EWALD)
+            radial_ewald<3>(r, rinv, rr2, aewald, bn);
+         const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+         thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+         const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
+         const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
+         const V3 R = v3(dx, dy, dz);
+         fdi += dipole_field(R, a, B1, B2);
+         fpi += dipole_field(R, b, B1, B2);
       }
-      if (sk >= 0) {
-         atomic_real3(fd, sk, fdk);
-         atomic_real3(fp, sk, fpk);
+      fdi = group_sum3<G>(fdi);
+      fpi = group_sum3<G>(fpi);
+      if (l == 0 && act) {
+         fd[3 * i] += fdi.x, fd[3 * i + 1] += fdi.y, fd[3 * i + 2] += fdi.z;
+         fp[3 * i] += fpi.x, fp[3 * i + 1] += fpi.y, fp[3 * i + 2] += fpi.z;
       }
-   }
-   if (cur >= 0 && si < n) {
-      atomic_real3(fd, si, fdi);
-      atomic_real3(fp, si, fpi);
    }
 }
 
@@ -165,89 +110,8 @@ __global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __rest
 }
 
 // -------------------------------------------------------------------------------------------
-// dfield: permanent-multipole field; tile pass = common part, exclusion pass = d/p split
+// dfield: permanent-multipole field; row pass = common part, exclusion pass = d/p split
 // -------------------------------------------------------------------------------------------
-template <bool EWALD, bool TABLE>
-__global__ void __launch_bounds__(APX_BLOCK) k_dfield_tiles(int n, int ntiles, Box box, real cut2, real aewald,
-   const int* __restrict__ iblk, const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj,
-   const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
-   const real2* __restrict__ mp2, real* __restrict__ fd)
-{
-   const int lane = threadIdx.x & 31;
-   WarpRange wr = warp_tiles(ntiles);
-   int cur = -1, si = 0;
-   real4 pi;
-   real thi = 0;
-   int jpi = 0;
-   Mpole mi;
-   V3 fi;
-   for (int t = wr.t0; t < wr.t1; ++t) {
-      int ib = iblk[t];
-      if (ib != cur) {
-         if (cur >= 0 && si < n)
-            atomic_real3(fd, si, fi);
-         cur = ib;
-         si = ib * 32 + lane;
-         int sl = min(si, n - 1);
-         pi = posd[sl];
-         real4 q = tpj[sl];
-         thi = q.x;
-         jpi = as_int(q.w);
-         real4 a = mp0[sl], b = mp1[sl];
-         real2 c2 = mp2[sl];
-         mi.c = a.x, mi.dx = a.y, mi.dy = a.z, mi.dz = a.w;
-         mi.qxx = b.x, mi.qxy = b.y, mi.qxz = b.z, mi.qyy = b.w, mi.qyz = c2.x, mi.qzz = c2.y;
-         fi = v3(0, 0, 0);
-      }
-      int sk = katom[t * 32 + lane];
-      int sl = max(sk, 0);
-      real4 pk = posd[sl];
-      real4 qk = tpj[sl];
-      real thk = qk.x;
-      int jpk = as_int(qk.w);
-      real4 ka = mp0[sl], kb = mp1[sl];
-      real2 kc = mp2[sl];
-      V3 fk = v3(0, 0, 0);
-      #pragma unroll 2
-      for (int j = 0; j < 32; ++j) {
-         int src = (lane + j) & 31;
-         int ks = SHF(sk, src);
-         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
-         real pdk = SHF(pk.w, src);
-         real thk_ = SHF(thk, src);
-         int jpk_ = TABLE ? SHF(jpk, src) : 0;
-         Mpole mk;
-         mk.c = SHF(ka.x, src), mk.dx = SHF(ka.y, src), mk.dy = SHF(ka.z, src), mk.dz = SHF(ka.w, src);
-         mk.qxx = SHF(kb.x, src), mk.qxy = SHF(kb.y, src), mk.qxz = SHF(kb.z, src), mk.qyy = SHF(kb.w, src);
-         mk.qyz = SHF(kc.x, src), mk.qzz = SHF(kc.y, src);
-         apx_image(box, dx, dy, dz);
-         real r2 = dx * dx + dy * dy + dz * dz;
-         if (ks > si && si < n && r2 <= cut2) {
-            real rinv = r_rsqrt(r2);
-            real r = r2 * rinv, rr2 = rinv * rinv;
-            real rr[4], bn[4], om[4];
-            radial_coulomb<4>(rinv, rr2, rr);
-            if (EWALD)
-               radial_ewald<4>(r, rinv, rr2, aewald, bn);
-            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
-            thole_one_minus_lambda<4>(r, pi.w, pdk, pg, om);
-            real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
-            real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
-            real B3 = (EWALD ? bn[3] : rr[3]) - om[3] * rr[3];
-            V3 R = v3(dx, dy, dz);
-            fi += mpole_field(R, mk, B1, B2, B3, (real)-1);
-            fk += mpole_field(R, mi, B1, B2, B3, (real)1);
-         }
-         int nxt = (lane + 1) & 31;
-         fk = v3(SHF(fk.x, nxt), SHF(fk.y, nxt), SHF(fk.z, nxt));
-      }
-      if (sk >= 0)
-         atomic_real3(fd, sk, fk);
-   }
-   if (cur >= 0 && si < n)
-      atomic_real3(fd, si, fi);
-}
-
 __device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, const real2* mp2, int s)
 {
    real4 a = mp0[s], b = mp1[s];
@@ -256,6 +120,46 @@ __device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, 
    m.c = a.x, m.dx = a.y, m.dy = a.z, m.dz = a.w;
    m.qxx = b.x, m.qxy = b.y, m.qxz = b.z, m.qyy = b.w, m.qyz = c.x, m.qzz = c.y;
    return m;
+}
+
+template <bool EWALD, bool TABLE, int G>
+__global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
+   const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
+   const real2* __restrict__ mp2, real* __restrict__ fd)
+{
+   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   {
+      const real4 pi = posd[i];
+      const real4 qi = tpj[i];
+      const int beg = vstart[i];
+      const int len = act ? cnt[i] : 0;
+      V3 fi = v3(0, 0, 0);
+      for (int q = l; q < len; q += G) {
+         const int k = nbr[beg + q];
+         const real4 pk = posd[k];
+         const real4 qk = tpj[k];
+         const Mpole mk = load_mpole(mp0, mp1, mp2, k);
+         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+         apx_image(box, dx, dy, dz);
+         const real r2 = dx * dx + dy * dy + dz * dz;
+         const real rinv = r_rsqrt(r2);
+         const real r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[4], bn[4], om[4];
+         radial_coulomb<4>(rinv, rr2, rr);
+         if (EWALD)
+            radial_ewald<4>(r, rinv, rr2, aewald, bn);
+         const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+         thole_one_minus_lambda<4>(r, pi.w, pk.w, pg, om);
+         const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
+         const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
+         const real B3 = (EWALD ? bn[3] : rr[3]) - om[3] * rr[3];
+         fi += mpole_field(v3(dx, dy, dz), mk, B1, B2, B3, (real)-1);
+      }
+      fi = group_sum3<G>(fi);
+      if (l == 0 && act)
+         fd[3 * i] += fi.x, fd[3 * i + 1] += fi.y, fd[3 * i + 2] += fi.z;
+   }
 }
 
 // d-correction goes to fd, (p - d) correction to the delta array fpd
@@ -299,91 +203,51 @@ __global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __rest
 }
 
 // -------------------------------------------------------------------------------------------
-// sparse preconditioner: z += alpha_i alpha_k T_thole(r) r_k  over the short-range list
+// sparse preconditioner: z += alpha_i alpha_k T_thole(r) r_k  over the pairs inside usolve-cutoff
+// (the first cntu entries of every row)
 // -------------------------------------------------------------------------------------------
-template <bool TABLE>
-__global__ void __launch_bounds__(APX_BLOCK) k_precond_tiles(int n, int ntiles, Box box, real cut2, const int* __restrict__ iblk,
-   const int* __restrict__ katom, const real4* __restrict__ posd, const real4* __restrict__ tpj, const real* __restrict__ thlval,
-   int nj, const real* __restrict__ rd, const real* __restrict__ rp, real* __restrict__ zd, real* __restrict__ zp,
-   const int* __restrict__ skip)
+template <bool TABLE, int G>
+__global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, const int* __restrict__ vstart,
+   const int* __restrict__ cntu, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const real* __restrict__ thlval, int nj, const real* __restrict__ rd, const real* __restrict__ rp, real* __restrict__ zd,
+   real* __restrict__ zp, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
-   const int lane = threadIdx.x & 31;
-   WarpRange wr = warp_tiles(ntiles);
-   int cur = -1, si = 0;
-   real4 pi;
-   real thi = 0, poli = 0;
-   int jpi = 0;
-   V3 rdi, rpi, zdi, zpi;
-   for (int t = wr.t0; t < wr.t1; ++t) {
-      int ib = iblk[t];
-      if (ib != cur) {
-         if (cur >= 0 && si < n) {
-            atomic_real3(zd, si, zdi);
-            atomic_real3(zp, si, zpi);
-         }
-         cur = ib;
-         si = ib * 32 + lane;
-         int sl = min(si, n - 1);
-         pi = posd[sl];
-         real4 q = tpj[sl];
-         thi = q.x;
-         poli = q.y;
-         jpi = as_int(q.w);
-         rdi = v3(rd[3 * sl], rd[3 * sl + 1], rd[3 * sl + 2]);
-         rpi = v3(rp[3 * sl], rp[3 * sl + 1], rp[3 * sl + 2]);
-         zdi = v3(0, 0, 0);
-         zpi = v3(0, 0, 0);
-      }
-      int sk = katom[t * 32 + lane];
-      int sl = max(sk, 0);
-      real4 pk = posd[sl];
-      real4 qk = tpj[sl];
-      real thk = qk.x, polk = qk.y;
-      int jpk = as_int(qk.w);
-      V3 rdk = v3(rd[3 * sl], rd[3 * sl + 1], rd[3 * sl + 2]);
-      V3 rpk = v3(rp[3 * sl], rp[3 * sl + 1], rp[3 * sl + 2]);
-      V3 zdk = v3(0, 0, 0), zpk = v3(0, 0, 0);
-      #pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-         int src = (lane + j) & 31;
-         int ks = SHF(sk, src);
-         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
-         real pdk = SHF(pk.w, src);
-         real thk_ = SHF(thk, src), polk_ = SHF(polk, src);
-         int jpk_ = TABLE ? SHF(jpk, src) : 0;
-         V3 a = v3(SHF(rdk.x, src), SHF(rdk.y, src), SHF(rdk.z, src));
-         V3 b = v3(SHF(rpk.x, src), SHF(rpk.y, src), SHF(rpk.z, src));
+   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   {
+      const real4 pi = posd[i];
+      const real4 qi = tpj[i];
+      const int beg = vstart[i];
+      const int len = act ? cntu[i] : 0;
+      V3 zdi = v3(0, 0, 0), zpi = v3(0, 0, 0);
+      for (int q = l; q < len; q += G) {
+         const int k = nbr[beg + q];
+         const real4 pk = posd[k];
+         const real4 qk = tpj[k];
+         const V3 a = v3(rd[3 * k], rd[3 * k + 1], rd[3 * k + 2]);
+         const V3 b = v3(rp[3 * k], rp[3 * k + 1], rp[3 * k + 2]);
+         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
          apx_image(box, dx, dy, dz);
-         real r2 = dx * dx + dy * dy + dz * dz;
-         if (ks > si && si < n && r2 <= cut2) {
-            real rinv = r_rsqrt(r2);
-            real r = r2 * rinv, rr2 = rinv * rinv;
-            real rr[3], om[3];
-            radial_coulomb<3>(rinv, rr2, rr);
-            real pg = TABLE ? thlval[jpi * nj + jpk_] : min(thi, thk_);
-            thole_one_minus_lambda<3>(r, pi.w, pdk, pg, om);
-            real pp = poli * polk_;
-            real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
-            V3 R = v3(dx, dy, dz);
-            zdi += dipole_field(R, a, B1, B2);
-            zpi += dipole_field(R, b, B1, B2);
-            zdk += dipole_field(R, rdi, B1, B2);
-            zpk += dipole_field(R, rpi, B1, B2);
-         }
-         int nxt = (lane + 1) & 31;
-         zdk = v3(SHF(zdk.x, nxt), SHF(zdk.y, nxt), SHF(zdk.z, nxt));
-         zpk = v3(SHF(zpk.x, nxt), SHF(zpk.y, nxt), SHF(zpk.z, nxt));
+         const real r2 = dx * dx + dy * dy + dz * dz;
+         const real rinv = r_rsqrt(r2);
+         const real r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[3], om[3];
+         radial_coulomb<3>(rinv, rr2, rr);
+         const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
+         thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+         const real pp = qi.y * qk.y;
+         const real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
+         const V3 R = v3(dx, dy, dz);
+         zdi += dipole_field(R, a, B1, B2);
+         zpi += dipole_field(R, b, B1, B2);
       }
-      if (sk >= 0) {
-         atomic_real3(zd, sk, zdk);
-         atomic_real3(zp, sk, zpk);
+      zdi = group_sum3<G>(zdi);
+      zpi = group_sum3<G>(zpi);
+      if (l == 0 && act) {
+         zd[3 * i] += zdi.x, zd[3 * i + 1] += zdi.y, zd[3 * i + 2] += zdi.z;
+         zp[3 * i] += zpi.x, zp[3 * i + 1] += zpi.y, zp[3 * i + 2] += zpi.z;
       }
-   }
-   if (cur >= 0 && si < n) {
-      atomic_real3(zd, si, zdi);
-      atomic_real3(zp, si, zpi);
    }
 }
 
@@ -432,26 +296,23 @@ __global__ void k_diag_precond(int n3, real udiag, const real4* __restrict__ tpj
    zp[q] = pol * rp[q];
 }
 
-inline int tile_grid(apx_ctx* c, int ntiles)
-{
-   // 4 warps per CTA; enough CTAs to fill the machine but never more warps than tiles
-   int want = (ntiles + 3) / 4;
-   int cap = c->sm_count * 8;
-   return want < 1 ? 1 : (want < cap ? want : cap);
-}
 } // namespace
+
+#define UF_G 16
+#define DF_G 16
+#define PC_G 8
 
 void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp)
 {
-   TileList& L = c->mlist;
+   RowList& L = c->rows;
    real cut = (real)c->opt.cutoff;
-   int grid = tile_grid(c, L.ntiles);
    bool ew = c->opt.use_ewald != 0;
    bool tb = c->thole_table != 0;
+   int grid = rows_grid<UF_G>(c);
 #define LAUNCH_UF(E, T)                                                                                                   \
-   k_ufield_tiles<E, T><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, (real)c->opt.aewald, L.iblk,      \
-      L.katom, c->posd, c->tpj, c->thlval, c->opt.njpolar, ud, up, fd, fp, c->skip)
-   if (L.ntiles > 0) {
+   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
+      c->tpj, c->thlval, c->opt.njpolar, ud, up, fd, fp, c->skip)
+   if (L.nverlet > 0) {
       // device-time the dominant kernel: one event pair per launch, read back by induce()
       int slot = -1;
       if (c->uf_used + 2 <= (int)c->uf_ev.size()) {
@@ -483,15 +344,15 @@ void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real*
 // fd accumulates the common field + d corrections; fpd receives the (p - d) delta only
 void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
 {
-   TileList& L = c->mlist;
+   RowList& L = c->rows;
    real cut = (real)c->opt.cutoff;
-   int grid = tile_grid(c, L.ntiles);
    bool ew = c->opt.use_ewald != 0;
    bool tb = c->thole_table != 0;
+   int grid = rows_grid<DF_G>(c);
 #define LAUNCH_DF(E, T)                                                                                                   \
-   k_dfield_tiles<E, T><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, (real)c->opt.aewald, L.iblk,      \
-      L.katom, c->posd, c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd)
-   if (L.ntiles > 0) {
+   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
+      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd)
+   if (L.nverlet > 0) {
       if (ew && tb) LAUNCH_DF(true, true);
       else if (ew) LAUNCH_DF(true, false);
       else if (tb) LAUNCH_DF(false, true);
@@ -523,17 +384,17 @@ void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, rea
    }
    if (!sparse)
       return;
-   TileList& L = c->ulist;
+   RowList& L = c->rows;
    real cut = (real)c->opt.usolve_cutoff;
    bool tb = c->thole_table != 0;
-   if (L.ntiles > 0) {
-      int grid = tile_grid(c, L.ntiles);
+   if (L.nverlet > 0) {
+      int grid = rows_grid<PC_G>(c);
       if (tb)
-         k_precond_tiles<true><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, L.iblk, L.katom, c->posd, c->tpj,
-            c->thlval, c->opt.njpolar, rd, rp, zd, zp, c->skip);
+         k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, L.vstart, L.cntu, L.nbr, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, rd, rp, zd, zp, c->skip);
       else
-         k_precond_tiles<false><<<grid, APX_BLOCK, 0, c->stream>>>(c->n, L.ntiles, c->box, cut * cut, L.iblk, L.katom, c->posd, c->tpj,
-            c->thlval, c->opt.njpolar, rd, rp, zd, zp, c->skip);
+         k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, L.vstart, L.cntu, L.nbr, c->posd, c->tpj, c->thlval,
+            c->opt.njpolar, rd, rp, zd, zp, c->skip);
       APX_COUNT_LAUNCH(c);
    }
    if (c->nexcl_u > 0) {

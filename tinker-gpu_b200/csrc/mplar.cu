@@ -15,6 +15,7 @@
 //     instead of 524288-entry buffers that must be re-reduced every call (32 MB virial read).
 #include "apx_internal.h"
 #include "pairmath.cuh"
+#include "rows.cuh"
 #include <cmath>
 
 #define FULL 0xffffffffu
@@ -72,11 +73,12 @@ __device__ __forceinline__ void atomic_fixed_d(fixed_t* p, double v)
 }
 
 struct MplarArgs {
-   int n, ntiles;
+   int n;
    Box box;
    real cut2, aewald, f;
-   const int* iblk;
-   const int* katom;
+   const int* vstart;     // directed neighbor rows (rows.cu)
+   const int* rcnt;
+   const int* nbr;
    const real4* posd;
    const real4* tpj;
    const real* thlval;
@@ -92,193 +94,143 @@ struct MplarArgs {
    fixed_t* gz;
    fixed_t* trq;      // [3*npad] fixed point
    fixed_t* ebuf;
-   int* cnt;
+   int* cnt;          // [0] unordered pairs counted by the exclusion pass (signed correction)
+   int* cnt2;         // [0] DIRECTED pairs visited by the row pass (= 2 x pairs)
 };
 
-struct WarpRange {
-   int t0, t1;
-};
-__device__ __forceinline__ WarpRange warp_tiles(int ntiles)
+// One lane group per atom i, one directed pair (i,k) per lane per step.  Each unordered pair is
+// visited from both ends: a visit adds half the pair energy / virial and the complete gradient and
+// torque of ITS OWN atom i (the k-side torque expressions are dead code here and are dropped by
+// the compiler), so nothing is scattered and no atomics are needed for the per-atom sums.
+template <bool DO_G, bool EWALD, int G>
+__global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
 {
-   int nw = gridDim.x * (blockDim.x >> 5);
-   int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-   int per = (ntiles + nw - 1) / nw;
-   WarpRange r;
-   r.t0 = min(ntiles, w * per);
-   r.t1 = min(ntiles, r.t0 + per);
-   return r;
-}
-
-template <bool DO_G, bool EWALD>
-__global__ void __launch_bounds__(APX_BLOCK) k_mplar_tiles(MplarArgs A)
-{
-   const int lane = threadIdx.x & 31;
    const int n = A.n;
-   WarpRange wr = warp_tiles(A.ntiles);
-   int cur = -1, si = 0;
-   real4 pi;
-   real thi = 0;
-   int jpi = 0;
-   Mpole mi;
-   V3 udi, upi, gi, ti;
    double em = 0, ep = 0, vxx = 0, vxy = 0, vxz = 0, vyy = 0, vyz = 0, vzz = 0;
    int nem = 0;
-   for (int t = wr.t0; t < wr.t1; ++t) {
-      int ib = A.iblk[t];
-      if (ib != cur) {
-         if (DO_G && cur >= 0 && si < n) {
-            atomic_fixed3(A.gx, A.gy, A.gz, si, gi);
-            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * si, ti);
-         }
-         cur = ib;
-         si = ib * 32 + lane;
-         int sl = min(si, n - 1);
-         pi = A.posd[sl];
-         real4 q = A.tpj[sl];
-         thi = q.x;
-         jpi = as_int(q.w);
-         mi = load_mpole(A.mp0, A.mp1, A.mp2, sl);
-         udi = upi = v3(0, 0, 0);
-         if (A.do_p) {
-            udi = v3(A.ud[3 * sl], A.ud[3 * sl + 1], A.ud[3 * sl + 2]);
-            upi = v3(A.up[3 * sl], A.up[3 * sl + 1], A.up[3 * sl + 2]);
-         }
-         gi = v3(0, 0, 0);
-         ti = v3(0, 0, 0);
-      }
-      int sk = A.katom[t * 32 + lane];
-      int sl = max(sk, 0);
-      real4 pk = A.posd[sl];
-      real4 qk = A.tpj[sl];
-      real thk = qk.x;
-      int jpk = as_int(qk.w);
-      real4 ka = A.mp0[sl], kb = A.mp1[sl];
-      real2 kc = A.mp2[sl];
-      V3 udk = v3(0, 0, 0), upk = v3(0, 0, 0);
+   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   {
+      const real4 pi = A.posd[i];
+      const real4 qi = A.tpj[i];
+      const Mpole mi = load_mpole(A.mp0, A.mp1, A.mp2, i);
+      V3 udi = v3(0, 0, 0), upi = v3(0, 0, 0);
       if (A.do_p) {
-         udk = v3(A.ud[3 * sl], A.ud[3 * sl + 1], A.ud[3 * sl + 2]);
-         upk = v3(A.up[3 * sl], A.up[3 * sl + 1], A.up[3 * sl + 2]);
+         udi = v3(A.ud[3 * i], A.ud[3 * i + 1], A.ud[3 * i + 2]);
+         upi = v3(A.up[3 * i], A.up[3 * i + 1], A.up[3 * i + 2]);
       }
-      V3 gk = v3(0, 0, 0), tk = v3(0, 0, 0);
-      for (int j = 0; j < 32; ++j) {
-         int src = (lane + j) & 31;
-         int ks = SHF(sk, src);
-         real dx = SHF(pk.x, src) - pi.x, dy = SHF(pk.y, src) - pi.y, dz = SHF(pk.z, src) - pi.z;
-         real pdk = SHF(pk.w, src);
-         real thk_ = SHF(thk, src);
-         int jpk_ = SHF(jpk, src);
-         Mpole mk;
-         mk.c = SHF(ka.x, src), mk.dx = SHF(ka.y, src), mk.dy = SHF(ka.z, src), mk.dz = SHF(ka.w, src);
-         mk.qxx = SHF(kb.x, src), mk.qxy = SHF(kb.y, src), mk.qxz = SHF(kb.z, src), mk.qyy = SHF(kb.w, src);
-         mk.qyz = SHF(kc.x, src), mk.qzz = SHF(kc.y, src);
-         V3 ukd = v3(SHF(udk.x, src), SHF(udk.y, src), SHF(udk.z, src));
-         V3 ukp = v3(SHF(upk.x, src), SHF(upk.y, src), SHF(upk.z, src));
+      const int beg = A.vstart[i];
+      const int len = act ? A.rcnt[i] : 0;
+      V3 gi = v3(0, 0, 0), ti = v3(0, 0, 0);
+      real emr = 0, epr = 0, v0 = 0, v1 = 0, v2 = 0, v3_ = 0, v4 = 0, v5 = 0;
+      for (int q = l; q < len; q += G) {
+         const int k = A.nbr[beg + q];
+         const real4 pk = A.posd[k];
+         const real4 qk = A.tpj[k];
+         const Mpole mk = load_mpole(A.mp0, A.mp1, A.mp2, k);
+         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
          apx_image(A.box, dx, dy, dz);
-         real r2 = dx * dx + dy * dy + dz * dz;
-         if (ks > si && si < n && r2 <= A.cut2) {
-            real rinv = r_rsqrt(r2);
-            real r = r2 * rinv, rr2 = rinv * rinv;
-            real rr[6], B[6];
-            radial_coulomb<6>(rinv, rr2, rr);
-            if (EWALD)
-               radial_ewald<6>(r, rinv, rr2, A.aewald, B);
-            else {
-               #pragma unroll
-               for (int q = 0; q < 6; ++q)
-                  B[q] = rr[q];
+         const real r2 = dx * dx + dy * dy + dz * dz;
+         const real rinv = r_rsqrt(r2);
+         const real r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[6], B[6];
+         radial_coulomb<6>(rinv, rr2, rr);
+         if (EWALD)
+            radial_ewald<6>(r, rinv, rr2, A.aewald, B);
+         else {
+            #pragma unroll
+            for (int j = 0; j < 6; ++j)
+               B[j] = rr[j];
+         }
+         const V3 R = v3(dx, dy, dz);
+         V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0);
+         ++nem;
+         if (A.do_m) {
+            V3 g1, t1, t2;
+            real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
+            emr += U;
+            if (DO_G) {
+               g += g1;
+               tqi += t1;
             }
-            V3 R = v3(dx, dy, dz);
-            V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0), tqk = v3(0, 0, 0);
-            ++nem;
-            if (A.do_m) {
-               V3 g1, t1, t2;
-               real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
-               em += (double)(A.f * U);
-               if (DO_G) {
-                  g += g1;
-                  tqi += t1;
-                  tqk += t2;
-               }
-            }
-            if (A.do_p) {
-               real om[6];
-               real pg = A.table ? A.thlval[jpi * A.nj + jpk_] : min(thi, thk_);
-               thole_one_minus_lambda<6>(r, pi.w, pdk, pg, om);
-               #pragma unroll
-               for (int q = 1; q < 5; ++q)
-                  B[q] -= om[q] * rr[q];
-               if (A.pair_ep) {
-                  V3 d0, d1;
-                  real U = pair_mu<false>(R, mi, ukd, B, d0, d1) + pair_um<false>(R, udi, mk, B, d0, d1);
-                  ep += (double)((real)0.5 * A.f * U);
-               }
-               if (DO_G) {
-                  V3 ubk = (real)0.5 * (ukd + ukp), ubi = (real)0.5 * (udi + upi);
-                  V3 g1, g2, t1, t2;
-                  pair_mu<true>(R, mi, ubk, B, g1, t1);
-                  pair_um<true>(R, ubi, mk, B, g2, t2);
-                  g += g1 + g2;
-                  tqi += t1;
-                  tqk += t2;
-                  if (A.mutual)
-                     g += (real)0.5 * (pair_uu_grad(R, udi, ukp, B) + pair_uu_grad(R, upi, ukd, B));
-               }
+         }
+         if (A.do_p) {
+            const V3 ukd = v3(A.ud[3 * k], A.ud[3 * k + 1], A.ud[3 * k + 2]);
+            const V3 ukp = v3(A.up[3 * k], A.up[3 * k + 1], A.up[3 * k + 2]);
+            real om[6];
+            const real pg = A.table ? A.thlval[as_int(qi.w) * A.nj + as_int(qk.w)] : min(qi.x, qk.x);
+            thole_one_minus_lambda<6>(r, pi.w, pk.w, pg, om);
+            #pragma unroll
+            for (int j = 1; j < 5; ++j)
+               B[j] -= om[j] * rr[j];
+            if (A.pair_ep) {
+               V3 d0, d1;
+               epr += pair_mu<false>(R, mi, ukd, B, d0, d1) + pair_um<false>(R, udi, mk, B, d0, d1);
             }
             if (DO_G) {
-               g = A.f * g;
-               gi -= g;
-               gk += g;
-               ti += A.f * tqi;
-               tk += A.f * tqk;
-               if (A.do_v) {
-                  vxx += (double)(R.x * g.x);
-                  vxy += (double)((real)0.5 * (R.y * g.x + R.x * g.y));
-                  vxz += (double)((real)0.5 * (R.z * g.x + R.x * g.z));
-                  vyy += (double)(R.y * g.y);
-                  vyz += (double)((real)0.5 * (R.z * g.y + R.y * g.z));
-                  vzz += (double)(R.z * g.z);
-               }
+               const V3 ubk = (real)0.5 * (ukd + ukp), ubi = (real)0.5 * (udi + upi);
+               V3 g1, g2, t1, t2;
+               pair_mu<true>(R, mi, ubk, B, g1, t1);
+               pair_um<true>(R, ubi, mk, B, g2, t2);
+               g += g1 + g2;
+               tqi += t1;
+               if (A.mutual)
+                  g += (real)0.5 * (pair_uu_grad(R, udi, ukp, B) + pair_uu_grad(R, upi, ukd, B));
             }
          }
          if (DO_G) {
-            int nxt = (lane + 1) & 31;
-            gk = v3(SHF(gk.x, nxt), SHF(gk.y, nxt), SHF(gk.z, nxt));
-            tk = v3(SHF(tk.x, nxt), SHF(tk.y, nxt), SHF(tk.z, nxt));
+            gi -= g;
+            ti += tqi;
+            if (A.do_v) {
+               v0 += R.x * g.x;
+               v1 += R.y * g.x + R.x * g.y;
+               v2 += R.z * g.x + R.x * g.z;
+               v3_ += R.y * g.y;
+               v4 += R.z * g.y + R.y * g.z;
+               v5 += R.z * g.z;
+            }
          }
       }
-      if (DO_G && sk >= 0) {
-         atomic_fixed3(A.gx, A.gy, A.gz, sk, gk);
-         atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * sk, tk);
+      if (DO_G) {
+         gi = group_sum3<G>(gi);
+         ti = group_sum3<G>(ti);
+         if (l == 0 && act) {
+            atomic_fixed3(A.gx, A.gy, A.gz, i, A.f * gi);
+            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * i, A.f * ti);
+         }
+         if (A.do_v) {
+            vxx += (double)v0, vxy += (double)v1, vxz += (double)v2;
+            vyy += (double)v3_, vyz += (double)v4, vzz += (double)v5;
+         }
       }
+      em += (double)emr;
+      ep += (double)epr;
    }
-   if (DO_G && cur >= 0 && si < n) {
-      atomic_fixed3(A.gx, A.gy, A.gz, si, gi);
-      atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * si, ti);
-   }
+   // every pair was visited twice
+   const double hf = 0.5 * (double)A.f;
    if (A.do_e) {
       em = warp_sum(em);
       ep = warp_sum(ep);
-      if (lane == 0) {
-         if (em != 0.0) atomic_fixed_d(&A.ebuf[0], em);
-         if (ep != 0.0) atomic_fixed_d(&A.ebuf[1], ep);
+      if ((threadIdx.x & 31) == 0) {
+         if (em != 0.0) atomic_fixed_d(&A.ebuf[0], hf * em);
+         if (ep != 0.0) atomic_fixed_d(&A.ebuf[1], 0.5 * hf * ep);
       }
    }
    if (A.do_a) {
       for (int o = 16; o > 0; o >>= 1)
          nem += __shfl_xor_sync(FULL, nem, o);
-      if (lane == 0 && nem)
-         atomicAdd(&A.cnt[0], nem);
+      if ((threadIdx.x & 31) == 0 && nem)
+         atomicAdd(&A.cnt2[0], nem);
    }
    if (DO_G && A.do_v) {
       vxx = warp_sum(vxx), vxy = warp_sum(vxy), vxz = warp_sum(vxz);
       vyy = warp_sum(vyy), vyz = warp_sum(vyz), vzz = warp_sum(vzz);
-      if (lane == 0) {
-         atomic_fixed_d(&A.ebuf[2], vxx);
-         atomic_fixed_d(&A.ebuf[3], vxy);
-         atomic_fixed_d(&A.ebuf[4], vxz);
-         atomic_fixed_d(&A.ebuf[5], vyy);
-         atomic_fixed_d(&A.ebuf[6], vyz);
-         atomic_fixed_d(&A.ebuf[7], vzz);
+      if ((threadIdx.x & 31) == 0) {
+         atomic_fixed_d(&A.ebuf[2], hf * vxx);
+         atomic_fixed_d(&A.ebuf[3], 0.5 * hf * vxy);
+         atomic_fixed_d(&A.ebuf[4], 0.5 * hf * vxz);
+         atomic_fixed_d(&A.ebuf[5], hf * vyy);
+         atomic_fixed_d(&A.ebuf[6], 0.5 * hf * vyz);
+         atomic_fixed_d(&A.ebuf[7], hf * vzz);
       }
    }
 }
@@ -715,13 +667,9 @@ RecipX make_recipx(apx_ctx* c)
    return X;
 }
 
-inline int tile_grid(apx_ctx* c, int ntiles)
-{
-   int want = (ntiles + 3) / 4;
-   int cap = c->sm_count * 8;
-   return want < 1 ? 1 : (want < cap ? want : cap);
-}
 } // namespace
+
+#define MP_G 16
 
 void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
@@ -756,13 +704,13 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    // ---- real space
    MplarArgs A;
    A.n = n;
-   A.ntiles = c->mlist.ntiles;
    A.box = c->box;
    A.cut2 = (real)(c->opt.cutoff * c->opt.cutoff);
    A.aewald = (real)c->opt.aewald;
    A.f = c->f_elec;
-   A.iblk = c->mlist.iblk;
-   A.katom = c->mlist.katom;
+   A.vstart = c->rows.vstart;
+   A.rcnt = c->rows.cnt;
+   A.nbr = c->rows.nbr;
    A.posd = c->posd;
    A.tpj = c->tpj;
    A.thlval = c->thlval;
@@ -786,12 +734,13 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    A.trq = c->trqf;
    A.ebuf = c->ebuf;
    A.cnt = c->cnt;
-   if (A.ntiles > 0 && (do_m || do_p) && (do_g || do_e)) {
-      int grid = tile_grid(c, A.ntiles);
-      if (do_g && ewald) k_mplar_tiles<true, true><<<grid, APX_BLOCK, 0, st>>>(A);
-      else if (do_g) k_mplar_tiles<true, false><<<grid, APX_BLOCK, 0, st>>>(A);
-      else if (ewald) k_mplar_tiles<false, true><<<grid, APX_BLOCK, 0, st>>>(A);
-      else k_mplar_tiles<false, false><<<grid, APX_BLOCK, 0, st>>>(A);
+   A.cnt2 = c->cnt.p + 1;
+   if (c->rows.nverlet > 0 && (do_m || do_p) && (do_g || do_e)) {
+      int grid = rows_grid<MP_G>(c);
+      if (do_g && ewald) k_mplar_rows<true, true, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
+      else if (do_g) k_mplar_rows<true, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
+      else if (ewald) k_mplar_rows<false, true, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
+      else k_mplar_rows<false, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
       APX_COUNT_LAUNCH(c);
       if (c->nexcl > 0) {
          int g = (c->nexcl + 127) / 128;
@@ -862,8 +811,9 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       r.ep = pair_ep ? fx(eb[1]) + (ewald ? db[D_EP_RECIP] + db[D_EP_SELF] : 0.0) : db[D_EP_DOT];
    r.esum = r.em + r.ep;
    if (do_a) {
-      r.nem = do_m ? cn[0] + (ewald ? n : 0) : 0;
-      r.nep = do_p ? cn[0] + (ewald ? n : 0) : 0;
+      int npair = cn[0] + cn[1] / 2;
+      r.nem = do_m ? npair + (ewald ? n : 0) : 0;
+      r.nep = do_p ? npair + (ewald ? n : 0) : 0;
    }
    for (int q = 0; q < 9; ++q)
       r.virial[q] = 0;

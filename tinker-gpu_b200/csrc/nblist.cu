@@ -1,13 +1,11 @@
-// Spatial sort + 32x32 tile neighbor list (our own structure; plays the role of the reference's
+// Spatial sort and neighbor-list refresh (our own structure; plays the role of the reference's
 // Spatial / spatialDataInit_cu / spatialCheck_cu, include/ff/spatial.h:15-140, src/cu/spatial.cu:728-960).
 //
 // * atoms are wrapped into the cell and sorted along a Morton curve (30-bit key, cub radix sort);
 //   32 consecutive sorted atoms form a block with an axis-aligned bounding box;
-// * for every i-block one warp scans the k-blocks >= i-block (box-box test, 32 candidates per
-//   step), then tests each atom of a surviving block against the i-box and ballot-compacts the
-//   hits into that i-block's k-atom list; lists are padded to multiples of 32 => tiles;
-// * two passes (count, exclusive scan, fill) so the list has no fixed capacity (the reference
-//   throws when its LSTCAP=48 tiles per block overflow, spatial.cu:708-716);
+// * rows.cu turns the block boxes into per-atom Verlet rows (two passes: count, exclusive scan,
+//   fill, so the list has no fixed capacity -- the reference throws when its LSTCAP=48 tiles per
+//   block overflow, spatial.cu:708-716) and compacts them to the cutoff every step;
 // * the list is rebuilt when any atom moved more than buffer/2 since the last build, the
 //   reference's criterion (src/nblist.cpp:521-531).
 #include "apx_internal.h"
@@ -156,121 +154,6 @@ __global__ void k_block_boxes(int n, int nblk, const real4* __restrict__ posd, r
    }
 }
 
-__device__ __forceinline__ void image_d(const Box& b, real& dx, real& dy, real& dz)
-{
-   if (b.orthogonal) {
-      dx -= b.lx * rint(dx * b.ilx);
-      dy -= b.ly * rint(dy * b.ily);
-      dz -= b.lz * rint(dz * b.ilz);
-   } else {
-      real f1 = dx * b.r[0] + dy * b.r[1] + dz * b.r[2];
-      real f2 = dx * b.r[3] + dy * b.r[4] + dz * b.r[5];
-      real f3 = dx * b.r[6] + dy * b.r[7] + dz * b.r[8];
-      f1 -= rint(f1);
-      f2 -= rint(f2);
-      f3 -= rint(f3);
-      dx = f1 * b.l[0] + f2 * b.l[1] + f3 * b.l[2];
-      dy = f1 * b.l[3] + f2 * b.l[4] + f3 * b.l[5];
-      dz = f1 * b.l[6] + f2 * b.l[7] + f3 * b.l[8];
-   }
-}
-
-// FILL = false: count k atoms per i-block.  FILL = true: write them.
-template <bool FILL>
-__global__ void k_build(int n, int nblk, Box b, real range, const real4* __restrict__ posd, const real4* __restrict__ ctr,
-   const real4* __restrict__ ext, int* __restrict__ counts, const int* __restrict__ offsets, int* __restrict__ iblk,
-   int* __restrict__ katom)
-{
-   int ib = (blockIdx.x * blockDim.x + threadIdx.x) / APX_WARP;
-   int lane = threadIdx.x & 31;
-   if (ib >= nblk)
-      return;
-   const real range2 = range * range;
-   real4 ci = ctr[ib], ei = ext[ib];
-   int total = 0;
-   int base = FILL ? offsets[ib] * 32 : 0;
-   // the i-block itself: all its atoms (pairs are filtered k>i in the kernels)
-   {
-      int s = ib * 32 + lane;
-      unsigned m = __ballot_sync(0xffffffffu, s < n);
-      if (FILL && s < n)
-         katom[base + __popc(m & ((1u << lane) - 1))] = s;
-      total += __popc(m);
-   }
-   for (int kb0 = ib + 1; kb0 < nblk; kb0 += 32) {
-      int kb = kb0 + lane;
-      bool hit = false;
-      if (kb < nblk) {
-         real4 ck = ctr[kb], ek = ext[kb];
-         real dx = ck.x - ci.x, dy = ck.y - ci.y, dz = ck.z - ci.z;
-         image_d(b, dx, dy, dz);
-         dx = max((real)0, fabs(dx) - ei.x - ek.x);
-         dy = max((real)0, fabs(dy) - ei.y - ek.y);
-         dz = max((real)0, fabs(dz) - ei.z - ek.z);
-         hit = dx * dx + dy * dy + dz * dz <= range2;
-      }
-      unsigned hm = __ballot_sync(0xffffffffu, hit);
-      while (hm) {
-         int j = __ffs(hm) - 1;
-         hm &= hm - 1;
-         int s = (kb0 + j) * 32 + lane;
-         bool in = false;
-         if (s < n) {
-            real4 p = posd[s];
-            real dx = p.x - ci.x, dy = p.y - ci.y, dz = p.z - ci.z;
-            image_d(b, dx, dy, dz);
-            dx = max((real)0, fabs(dx) - ei.x);
-            dy = max((real)0, fabs(dy) - ei.y);
-            dz = max((real)0, fabs(dz) - ei.z);
-            in = dx * dx + dy * dy + dz * dz <= range2;
-         }
-         unsigned m = __ballot_sync(0xffffffffu, in);
-         if (FILL && in)
-            katom[base + total + __popc(m & ((1u << lane) - 1))] = s;
-         total += __popc(m);
-      }
-   }
-   if (!FILL) {
-      if (lane == 0)
-         counts[ib] = (total + 31) / 32;     // tiles for this i-block
-   } else {
-      int ntile = (total + 31) / 32;
-      for (int q = total + lane; q < ntile * 32; q += 32)
-         katom[base + q] = -1;
-      for (int t = lane; t < ntile; t += 32)
-         iblk[offsets[ib] + t] = ib;
-   }
-}
-
-__global__ void k_count_pairs(int n, int ntiles, Box b, real cut2, const real4* __restrict__ posd, const int* __restrict__ iblk,
-   const int* __restrict__ katom, unsigned long long* __restrict__ out)
-{
-   int w = (blockIdx.x * blockDim.x + threadIdx.x) / APX_WARP;
-   int lane = threadIdx.x & 31;
-   int nw = gridDim.x * blockDim.x / APX_WARP;
-   unsigned long long c = 0;
-   for (int t = w; t < ntiles; t += nw) {
-      int si = iblk[t] * 32 + lane;
-      real4 pi = posd[min(si, n - 1)];
-      int sk = katom[t * 32 + lane];
-      real4 pk = posd[max(sk, 0)];
-      for (int j = 0; j < 32; ++j) {
-         int src = (lane + j) & 31;
-         real kx = __shfl_sync(0xffffffffu, pk.x, src), ky = __shfl_sync(0xffffffffu, pk.y, src),
-              kz = __shfl_sync(0xffffffffu, pk.z, src);
-         int ks = __shfl_sync(0xffffffffu, sk, src);
-         real dx = kx - pi.x, dy = ky - pi.y, dz = kz - pi.z;
-         image_d(b, dx, dy, dz);
-         if (si < n && ks > si && dx * dx + dy * dy + dz * dz <= cut2)
-            ++c;
-      }
-   }
-   for (int o = 16; o > 0; o >>= 1)
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-   if (lane == 0 && c)
-      atomicAdd(out, c);
-}
-
 __global__ void k_check_moved(int n, const double* __restrict__ xyz, const double* __restrict__ ref, double lim2, int* flag)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,33 +164,6 @@ __global__ void k_check_moved(int n, const double* __restrict__ xyz, const doubl
       *flag = 1;
 }
 
-void build_one(apx_ctx* c, TileList& L)
-{
-   int n = c->n, nblk = c->nblk;
-   int nthreads = nblk * 32;
-   int grid = (nthreads + APX_BLOCK - 1) / APX_BLOCK;
-   L.counts.ensure(nblk + 1);
-   L.offsets.ensure(nblk + 1);
-   real range = L.cutoff + L.buffer;
-   k_build<false><<<grid, APX_BLOCK, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.counts, nullptr,
-      nullptr, nullptr);
-   CUDA_CHECK(cudaMemsetAsync(L.counts.p + nblk, 0, sizeof(int), c->stream));
-   size_t need = 0;
-   cub::DeviceScan::ExclusiveSum(nullptr, need, L.counts.p, L.offsets.p, nblk + 1, c->stream);
-   if (need > c->cubtmp.cap)
-      c->cubtmp.ensure(need);
-   need = c->cubtmp.cap;
-   cub::DeviceScan::ExclusiveSum(c->cubtmp.p, need, L.counts.p, L.offsets.p, nblk + 1, c->stream);
-   int ntiles = 0;
-   CUDA_CHECK(cudaMemcpyAsync(&ntiles, L.offsets.p + nblk, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-   CUDA_CHECK(cudaStreamSynchronize(c->stream));
-   L.ntiles = ntiles;
-   L.iblk.ensure(ntiles + 1);
-   L.katom.ensure((size_t)ntiles * 32 + 32);
-   k_build<true><<<grid, APX_BLOCK, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, nullptr, L.offsets,
-      L.iblk, L.katom);
-   c->stats.kernel_launches += 2;
-}
 } // namespace
 
 void apx_update_sorted_positions(apx_ctx* c)
@@ -333,6 +189,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
    }
    if (!rebuild) {
       apx_update_sorted_positions(c);
+      apx_rows_compact(c, false);
       return;
    }
    cudaEventRecord(c->ev2, c->stream);
@@ -350,33 +207,23 @@ void apx_list_refresh(apx_ctx* c, bool force)
    k_gather_static<<<g, 256, 0, c->stream>>>(n, c->npad, c->perm, c->inv, c->thole_o, c->polarity_o, c->jpolar_o, c->tpj);
    if (c->nexcl)
       k_excl_sorted<<<(c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_ik, c->excl_sc, c->inv, c->excl_s);
-   // 3. block boxes and the two tile lists
+   // 3. block boxes and the Verlet rows
    k_block_boxes<<<(c->nblk * 32 + APX_BLOCK - 1) / APX_BLOCK, APX_BLOCK, 0, c->stream>>>(n, c->nblk, c->posd, c->blk_ctr, c->blk_ext);
    c->stats.kernel_launches += 6;
-   build_one(c, c->mlist);
-   if (c->opt.use_polar && c->opt.pcgprec && c->opt.usolve_cutoff > 0)
-      build_one(c, c->ulist);
-   else
-      c->ulist.ntiles = 0;
+   apx_rows_build(c);
    CUDA_CHECK(cudaMemcpyAsync(c->xyz_ref, c->xyz_d, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, c->stream));
-   // pair count inside the cutoff (roofline accounting only)
+   // rows of the current step + pair counts inside the cutoffs (roofline accounting only)
    {
-      unsigned long long* cnt = (unsigned long long*)c->dbuf.p;
-      CUDA_CHECK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->stream));
-      real cut2 = c->mlist.cutoff * c->mlist.cutoff;
-      int grid = min(c->sm_count * 16, (c->mlist.ntiles + 3) / 4);
-      if (grid > 0)
-         k_count_pairs<<<grid, APX_BLOCK, 0, c->stream>>>(n, c->mlist.ntiles, c->box, cut2, c->posd, c->mlist.iblk, c->mlist.katom, cnt);
-      unsigned long long h = 0;
-      CUDA_CHECK(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+      apx_rows_compact(c, true);
+      unsigned long long h[2] = {0, 0};
+      CUDA_CHECK(cudaMemcpyAsync(h, c->rows.total.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
       cudaEventRecord(c->ev3, c->stream);
       CUDA_CHECK(cudaStreamSynchronize(c->stream));
-      c->stats.npairs_m = (long long)h;
-      APX_COUNT_LAUNCH(c);
+      c->stats.npairs_m = (long long)(h[0] / 2);
+      c->stats.npairs_u = (long long)(h[1] / 2);
    }
    cudaEventElapsedTime(&c->stats.ms_list, c->ev2, c->ev3);
-   c->stats.ntiles_m = c->mlist.ntiles;
-   c->stats.ntiles_u = c->ulist.ntiles;
+   c->stats.nverlet = c->rows.nverlet;
    c->stats.list_rebuilds++;
    c->list_valid = 1;
    c->mpole_inited = 0;     // sorted multipoles must be regenerated in the new order

@@ -1,0 +1,177 @@
+// Directed per-atom neighbor rows (struct RowList, apx_internal.h).
+//
+// The reference walks 32x32 tiles of (i-block, k-atom list) pairs and scatters the k-side results
+// with atomics (include/ff/spatial.h:15-140, src/cu/amoeba/*_cu1.cc).  At AMOEBA densities only
+// ~8 % of the lanes of such a tile hold a pair inside the 7 A cutoff, so the pair kernels here use a
+// different structure: every atom owns the full row of its neighbours (both directions of each
+// pair are stored), a group of lanes walks one row with every lane on a real pair, the i-side
+// sums are reduced with shuffles and written once, and nothing is ever scattered to the k side.
+//
+//   apx_rows_build    at list rebuild: Verlet rows (cutoff + buffer) from the block bounding boxes
+//   apx_rows_compact  every step: rows of the pairs inside the cutoff right now, the ones inside
+//                     the preconditioner range (usolve-cutoff) first
+#include "apx_internal.h"
+#include "pairmath.cuh"
+#include <cub/cub.cuh>
+
+#define FULL 0xffffffffu
+
+namespace {
+// one warp per i-block; lane j keeps the running length of the row of atom 32*ib + j
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, Box b, real range, const real4* __restrict__ posd,
+   const real4* __restrict__ ctr, const real4* __restrict__ ext, int* __restrict__ vcnt, const int* __restrict__ vstart,
+   int* __restrict__ vnbr)
+{
+   const int ib = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (ib >= nblk)
+      return;
+   const real range2 = range * range;
+   const real4 ci = ctr[ib], ei = ext[ib];
+   const int si = ib * 32 + lane;
+   const real4 pi = posd[min(si, n - 1)];
+   const int ni = min(32, n - ib * 32);          // atoms in this i-block
+   int mycount = 0;
+   const int mybase = (FILL && si < n) ? vstart[si] : 0;
+   const unsigned lt = (1u << lane) - 1;
+   for (int kb0 = 0; kb0 < nblk; kb0 += 32) {
+      int kb = kb0 + lane;
+      bool hit = false;
+      if (kb < nblk) {
+         real4 ck = ctr[kb], ek = ext[kb];
+         real dx = ck.x - ci.x, dy = ck.y - ci.y, dz = ck.z - ci.z;
+         apx_image(b, dx, dy, dz);
+         dx = max((real)0, fabs(dx) - ei.x - ek.x);
+         dy = max((real)0, fabs(dy) - ei.y - ek.y);
+         dz = max((real)0, fabs(dz) - ei.z - ek.z);
+         hit = dx * dx + dy * dy + dz * dz <= range2;
+      }
+      unsigned hm = __ballot_sync(FULL, hit);
+      while (hm) {
+         int j = __ffs(hm) - 1;
+         hm &= hm - 1;
+         int s = (kb0 + j) * 32 + lane;
+         real4 pk = posd[min(s, n - 1)];
+         bool in = false;
+         if (s < n) {
+            real dx = pk.x - ci.x, dy = pk.y - ci.y, dz = pk.z - ci.z;
+            apx_image(b, dx, dy, dz);
+            dx = max((real)0, fabs(dx) - ei.x);
+            dy = max((real)0, fabs(dy) - ei.y);
+            dz = max((real)0, fabs(dz) - ei.z);
+            in = dx * dx + dy * dy + dz * dz <= range2;
+         }
+         if (!__ballot_sync(FULL, in))
+            continue;
+         for (int q = 0; q < ni; ++q) {
+            real dx = pk.x - __shfl_sync(FULL, pi.x, q), dy = pk.y - __shfl_sync(FULL, pi.y, q),
+                 dz = pk.z - __shfl_sync(FULL, pi.z, q);
+            apx_image(b, dx, dy, dz);
+            bool ok = in && s != ib * 32 + q && dx * dx + dy * dy + dz * dz <= range2;
+            unsigned m = __ballot_sync(FULL, ok);
+            if (FILL) {
+               int off = __shfl_sync(FULL, mybase + mycount, q);
+               if (ok)
+                  vnbr[off + __popc(m & lt)] = s;
+            }
+            if (lane == q)
+               mycount += __popc(m);
+         }
+      }
+   }
+   if (!FILL && si < n)
+      vcnt[si] = mycount;
+}
+
+// one warp per atom: two sweeps over its Verlet row (positions stay in L1 between them)
+__global__ void __launch_bounds__(128) k_rows_compact(int n, Box b, real cut2, real ucut2, const real4* __restrict__ posd,
+   const int* __restrict__ vstart, const int* __restrict__ vnbr, int* __restrict__ nbr, int* __restrict__ cnt,
+   int* __restrict__ cntu, unsigned long long* __restrict__ total)
+{
+   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (i >= n)
+      return;
+   const int beg = vstart[i], end = vstart[i + 1];
+   const real4 pi = posd[i];
+   const unsigned lt = (1u << lane) - 1;
+   int out = beg;
+   int nu = 0;
+   for (int sweep = 0; sweep < 2; ++sweep) {
+      if (sweep == 0 && ucut2 <= 0)
+         continue;
+      for (int q0 = beg; q0 < end; q0 += 32) {
+         int q = q0 + lane;
+         int k = q < end ? vnbr[q] : -1;
+         bool ok = false;
+         if (k >= 0) {
+            real4 pk = posd[k];
+            real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+            apx_image(b, dx, dy, dz);
+            real r2 = dx * dx + dy * dy + dz * dz;
+            ok = sweep == 0 ? r2 <= ucut2 : (r2 > ucut2 && r2 <= cut2);
+         }
+         unsigned m = __ballot_sync(FULL, ok);
+         if (ok)
+            nbr[out + __popc(m & lt)] = k;
+         out += __popc(m);
+      }
+      if (sweep == 0)
+         nu = out - beg;
+   }
+   if (lane == 0) {
+      cnt[i] = out - beg;
+      cntu[i] = nu;
+      if (total) {
+         atomicAdd(&total[0], (unsigned long long)(out - beg));
+         atomicAdd(&total[1], (unsigned long long)nu);
+      }
+   }
+}
+} // namespace
+
+void apx_rows_build(apx_ctx* c)
+{
+   RowList& L = c->rows;
+   const int n = c->n, nblk = c->nblk;
+   const int grid = (nblk * 32 + 127) / 128;
+   const real range = c->list_cutoff + c->list_buffer;
+   L.vstart.ensure(n + 1);
+   L.vcnt.ensure(n + 1);
+   L.cnt.ensure(n);
+   L.cntu.ensure(n);
+   L.total.ensure(2);
+   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.vcnt, nullptr, nullptr);
+   CUDA_CHECK(cudaMemsetAsync(L.vcnt.p + n, 0, sizeof(int), c->stream));
+   size_t need = 0;
+   cub::DeviceScan::ExclusiveSum(nullptr, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
+   if (need > c->cubtmp.cap)
+      c->cubtmp.ensure(need);
+   need = c->cubtmp.cap;
+   cub::DeviceScan::ExclusiveSum(c->cubtmp.p, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
+   int total = 0;
+   CUDA_CHECK(cudaMemcpyAsync(&total, L.vstart.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   if (total < 0)
+      APX_THROW("neighbor rows exceed 2^31 entries");
+   L.nverlet = total;
+   L.vnbr.ensure((size_t)total + 32);
+   L.nbr.ensure((size_t)total + 32);
+   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, nullptr, L.vstart, L.vnbr);
+   c->stats.kernel_launches += 2;
+}
+
+void apx_rows_compact(apx_ctx* c, bool count)
+{
+   RowList& L = c->rows;
+   const int n = c->n;
+   const real cut = c->list_cutoff;
+   const bool sparse = c->opt.use_polar && c->opt.pcgprec && c->opt.usolve_cutoff > 0;
+   const real ucut = sparse ? (real)std::min(c->opt.usolve_cutoff, (double)cut) : (real)0;
+   if (count)
+      CUDA_CHECK(cudaMemsetAsync(L.total.p, 0, 2 * sizeof(unsigned long long), c->stream));
+   k_rows_compact<<<(n * 32 + 127) / 128, 128, 0, c->stream>>>(n, c->box, cut * cut, ucut * ucut, c->posd, L.vstart, L.vnbr, L.nbr,
+      L.cnt, L.cntu, count ? L.total.p : nullptr);
+   APX_COUNT_LAUNCH(c);
+}

@@ -1,0 +1,38 @@
+// Lane-group iteration over the directed neighbor rows (rows.cu): G consecutive lanes share one
+// atom, 128/G atoms per CTA, CTAs stride over the atoms.
+#pragma once
+#include "apx_internal.h"
+#include "pairmath.cuh"
+
+#define ROWS_BLOCK 128
+
+// for (atoms of this lane group): `i` = atom (clamped to n-1), `l` = lane in group, `act` = i is real.
+// The trip count is uniform across a warp so the body may use full-mask shuffles.
+#define ROWS_FOREACH_ATOM(G, n, i, l, act)                                                                               \
+   const int l = threadIdx.x & ((G) - 1);                                                                                \
+   for (int i_ = blockIdx.x * (ROWS_BLOCK / (G)) + threadIdx.x / (G), w_ = i_ - (threadIdx.x & 31) / (G), i = min(i_, (n) - 1),  \
+            act = i_ < (n);                                                                                              \
+        w_ < (n); i_ += gridDim.x * (ROWS_BLOCK / (G)), w_ += gridDim.x * (ROWS_BLOCK / (G)), i = min(i_, (n) - 1), act = i_ < (n))
+
+template <int G>
+__device__ __forceinline__ real group_sum(real v)
+{
+   #pragma unroll
+   for (int o = G / 2; o > 0; o >>= 1)
+      v += __shfl_xor_sync(0xffffffffu, v, o);
+   return v;
+}
+template <int G>
+__device__ __forceinline__ V3 group_sum3(V3 v)
+{
+   return v3(group_sum<G>(v.x), group_sum<G>(v.y), group_sum<G>(v.z));
+}
+
+template <int G>
+inline int rows_grid(const apx_ctx* c)
+{
+   int per = ROWS_BLOCK / G;
+   int want = (c->n + per - 1) / per;
+   int cap = c->sm_count * 32;
+   return want < 1 ? 1 : (want < cap ? want : cap);
+}
