@@ -7,7 +7,6 @@
 void apx_to_sorted(apx_ctx* c, const double* in_dev, real* out);
 void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev);
 void apx_dfield_full(apx_ctx* c, bool want_ev);
-void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
 void apx_grad_to_caller(apx_ctx* c, double* dev_out);
 
 static thread_local std::string g_err;
@@ -158,6 +157,9 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
    c->sm_count = prop.multiProcessorCount;
    CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+   CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+   CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
    CUDA_CHECK(cudaEventCreate(&c->ev0));
    CUDA_CHECK(cudaEventCreate(&c->ev1));
    CUDA_CHECK(cudaEventCreate(&c->ev2));
@@ -232,6 +234,11 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
       v->ensure(3 * np);
       CUDA_CHECK(cudaMemset(v->p, 0, sizeof(real) * 3 * np));
    }
+   DevBuf<real4>* pks[] = {&c->pk_p, &c->pk_r, &c->pk_z, &c->pk_v, &c->pk_f};
+   for (auto* v : pks) {
+      v->ensure(2 * np);
+      CUDA_CHECK(cudaMemset(v->p, 0, sizeof(real4) * 2 * np));
+   }
    c->fphi.ensure(20 * np);
    c->fmp.ensure(10 * np);
    c->fphid.ensure(10 * np);
@@ -259,6 +266,7 @@ void apx_destroy(apx_ctx* c)
       return;
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
+   cudaStreamSynchronize(c->stream2);
    apx_pme_destroy(c);
    if (c->flags_h) cudaFreeHost(c->flags_h);
    if (c->scal_h) cudaFreeHost(c->scal_h);
@@ -281,6 +289,10 @@ void apx_destroy(apx_ctx* c)
    c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
+   c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();
+   cudaEventDestroy(c->ev_fork);
+   cudaEventDestroy(c->ev_join);
+   cudaStreamDestroy(c->stream2);
    cudaStreamDestroy(c->stream);
    delete c;
 }
@@ -377,7 +389,7 @@ int apx_precond(apx_ctx* c, const double* rsd, const double* rsdp, double* zrsd,
    CUDA_CHECK(cudaStreamSynchronize(c->stream));
    h2d(c, c->io_a, rsdp, 3 * (size_t)c->n);
    apx_to_sorted(c, c->io_a, c->rsdp);
-   apx_precond_apply(c, c->rsd, c->rsdp, c->zrsd, c->zrsdp, false);
+   apx_precond_apply(c, c->rsd, c->rsdp, c->zrsd, c->zrsdp);
    out_sorted3(c, c->zrsd, zrsd);
    out_sorted3(c, c->zrsdp, zrsdp);
    API_END

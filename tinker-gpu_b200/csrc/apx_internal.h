@@ -151,6 +151,9 @@ struct apx_ctx {
    // ---- fields / CG vectors, sorted order, [npad][3]
    DevBuf<real> field, fieldp, udir, udirp, uind, uinp;
    DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
+   DevBuf<real4> pk_p, pk_r, pk_z, pk_v, pk_f;   // packed (d,p) pairs, dp.cuh: direction, residual, M r, A p, real-space field
+   cudaStream_t stream2 = nullptr;       // real-space operator of an iteration runs here, beside the PME chain
+   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
    DevBuf<double> scal;                  // PCG scalars (sum, sump, a, ap, sum1, sump1, epsd, epsp ...)
    double* scal_h = nullptr;             // pinned
    int last_iters = 6;
@@ -208,15 +211,31 @@ void apx_torque(apx_ctx* c, bool do_v);
 void apx_pme_setup(apx_ctx* c);
 void apx_pme_destroy(apx_ctx* c);
 void apx_pme_mpole(apx_ctx* c, bool want_ev);                   // fills fmp, fphi (and recip E/virial in dbuf)
-void apx_pme_ufield(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp, const double* beta, real* conj_out_d,
-   real* conj_out_p);                                            // recip + self part of ufield, ASSIGNS fd/fp
+void apx_pme_zero_grid(apx_ctx* c);
+void apx_pme_spread_dp(apx_ctx* c, const real4* U);              // grid += spread of a packed dipole pair
+void apx_pme_convolve(apx_ctx* c);                               // FFT, influence function, inverse FFT
+void apx_pme_pcg_dir_spread(apx_ctx* c, int it);
+void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot);
 void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool full20);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 // ---- field.cu
 void apx_dfield_real(apx_ctx* c, real* fd, real* fp);
-void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
-void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp, bool diag_done);
+void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F);    // F = real-space field of U (assigned)
+struct PcgTest {          // convergence test fused into the preconditioner kernel of iteration `it` (it = 0: none)
+   int it = 0, miniter = 0, politer = 0;
+   real poleps = 0, debye = 0, pcgpeek = 0;
+   const double* slot = nullptr;   // slot of iteration it (r.r in quantities 4,5)
+   double* result = nullptr;       // [0] eps, [1] iteration
+   int* flags = nullptr;
+   real* ud = nullptr;
+   real* up = nullptr;
+};
+void apx_precond_dp(apx_ctx* c, const real4* R, real4* Z, double* slot, const PcgTest* test = nullptr);   // Z = M R ; partial R.Z -> slot
+void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp);
 // ---- pcg.cu
 void apx_induce_impl(apx_ctx* c);
+void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
+void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);
+void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
 // ---- mplar.cu
 void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out);

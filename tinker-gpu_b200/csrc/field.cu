@@ -14,6 +14,7 @@
 #include "apx_internal.h"
 #include "pairmath.cuh"
 #include "rows.cuh"
+#include "dp.cuh"
 
 namespace {
 __device__ __forceinline__ int as_int(real w)
@@ -31,8 +32,7 @@ __device__ __forceinline__ int as_int(real w)
 template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
-   const real* __restrict__ thlval, int nj, const real* __restrict__ ud, const real* __restrict__ up, real* __restrict__ fd,
-   real* __restrict__ fp, const int* __restrict__ skip)
+   const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
@@ -47,8 +47,8 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real
          const int k = nbr[beg + q];
          const real4 pk = posd[k];
          const real4 qk = tpj[k];
-         const V3 a = v3(ud[3 * k], ud[3 * k + 1], ud[3 * k + 2]);
-         const V3 b = v3(up[3 * k], up[3 * k + 1], up[3 * k + 2]);
+         V3 a, b;
+         load_dp(U, k, a, b);
          real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
          apx_image(box, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
@@ -68,18 +68,15 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real
       }
       fdi = group_sum3<G>(fdi);
       fpi = group_sum3<G>(fpi);
-      if (l == 0 && act) {
-         fd[3 * i] += fdi.x, fd[3 * i + 1] += fdi.y, fd[3 * i + 2] += fdi.z;
-         fp[3 * i] += fpi.x, fp[3 * i + 1] += fpi.y, fp[3 * i + 2] += fpi.z;
-      }
+      if (l == 0 && act)
+         store_dp(F, i, fdi, fpi);
    }
 }
 
 // exclusion pass for ufield (only pairs whose u-scale != 1; empty for stock AMOEBA)
 template <bool TABLE>
 __global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
-   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real* __restrict__ ud, const real* __restrict__ up,
-   real* __restrict__ fd, real* __restrict__ fp)
+   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F)
 {
    int e = blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= nx)
@@ -101,12 +98,11 @@ __global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __rest
    thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
    real B1 = p.u * (1 - om[1]) * rr[1], B2 = p.u * (1 - om[2]) * rr[2];
    V3 R = v3(dx, dy, dz);
-   V3 udi = v3(ud[3 * p.i], ud[3 * p.i + 1], ud[3 * p.i + 2]), upi = v3(up[3 * p.i], up[3 * p.i + 1], up[3 * p.i + 2]);
-   V3 udk = v3(ud[3 * p.k], ud[3 * p.k + 1], ud[3 * p.k + 2]), upk = v3(up[3 * p.k], up[3 * p.k + 1], up[3 * p.k + 2]);
-   atomic_real3(fd, p.i, dipole_field(R, udk, B1, B2));
-   atomic_real3(fp, p.i, dipole_field(R, upk, B1, B2));
-   atomic_real3(fd, p.k, dipole_field(R, udi, B1, B2));
-   atomic_real3(fp, p.k, dipole_field(R, upi, B1, B2));
+   V3 udi, upi, udk, upk;
+   load_dp(U, p.i, udi, upi);
+   load_dp(U, p.k, udk, upk);
+   atomic_dp(F, p.i, dipole_field(R, udk, B1, B2), dipole_field(R, upk, B1, B2));
+   atomic_dp(F, p.k, dipole_field(R, udi, B1, B2), dipole_field(R, upi, B1, B2));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -207,26 +203,65 @@ __global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __rest
 // (the first cntu entries of every row)
 // -------------------------------------------------------------------------------------------
 template <bool TABLE, int G>
-__global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, const int* __restrict__ vstart,
+__global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, real udiag, const int* __restrict__ vstart,
    const int* __restrict__ cntu, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
-   const real* __restrict__ thlval, int nj, const real* __restrict__ rd, const real* __restrict__ rp, real* __restrict__ zd,
-   real* __restrict__ zp, const int* __restrict__ skip)
+   const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z, double* __restrict__ slot,
+   const int* __restrict__ skip, PcgTest T)
 {
    if (skip && skip[1])
       return;
+   // Stopping rule of induceMutualPcg1 (src/cu/amoeba/pcg.cu:147-165) on r.r of this iteration: when
+   // it is met the kernel applies the peek step u += peek*alpha*r instead of z = M r, and the last
+   // CTA raises the stop flag (so no CTA of this grid can see it early).
+   bool done = false;
+   if (T.it > 0) {
+      double e = fmax(pcg_q(T.slot, 4), pcg_q(T.slot, 5));
+      double eps = (double)T.debye * sqrt(e / n);
+      done = eps < (double)T.poleps;
+      if (T.it < T.miniter)
+         done = false;
+      if (T.it >= T.politer)
+         done = true;
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+         T.result[0] = eps;
+         T.result[1] = (double)T.it;
+      }
+   }
+   if (done) {
+      for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+         V3 rd, rp;
+         load_dp(Rv, s, rd, rp);
+         real term = T.pcgpeek * tpj[s].y;
+         T.ud[3 * s] += term * rd.x, T.ud[3 * s + 1] += term * rd.y, T.ud[3 * s + 2] += term * rd.z;
+         T.up[3 * s] += term * rp.x, T.up[3 * s + 1] += term * rp.y, T.up[3 * s + 2] += term * rp.z;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         __threadfence();
+         unsigned t = atomicAdd((unsigned*)&T.flags[3], 1u);
+         if (t == gridDim.x - 1) {
+            T.flags[2] = T.it;
+            T.flags[3] = 0;
+            __threadfence();
+            T.flags[1] = 1;
+         }
+      }
+      return;
+   }
+   double dot_d = 0, dot_p = 0;
    ROWS_FOREACH_ATOM(G, n, i, l, act)
    {
       const real4 pi = posd[i];
       const real4 qi = tpj[i];
       const int beg = vstart[i];
-      const int len = act ? cntu[i] : 0;
+      const int len = (act && cntu) ? cntu[i] : 0;
       V3 zdi = v3(0, 0, 0), zpi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
          const int k = nbr[beg + q];
          const real4 pk = posd[k];
          const real4 qk = tpj[k];
-         const V3 a = v3(rd[3 * k], rd[3 * k + 1], rd[3 * k + 2]);
-         const V3 b = v3(rp[3 * k], rp[3 * k + 1], rp[3 * k + 2]);
+         V3 a, b;
+         load_dp(Rv, k, a, b);
          real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
          apx_image(box, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
@@ -245,17 +280,27 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, con
       zdi = group_sum3<G>(zdi);
       zpi = group_sum3<G>(zpi);
       if (l == 0 && act) {
-         zd[3 * i] += zdi.x, zd[3 * i + 1] += zdi.y, zd[3 * i + 2] += zdi.z;
-         zp[3 * i] += zpi.x, zp[3 * i + 1] += zpi.y, zp[3 * i + 2] += zpi.z;
+         V3 rd, rp;
+         load_dp(Rv, i, rd, rp);
+         const real dg = udiag * qi.y;
+         zdi += dg * rd;
+         zpi += dg * rp;
+         store_dp(Z, i, zdi, zpi);
+         dot_d += (double)rd.x * zdi.x + (double)rd.y * zdi.y + (double)rd.z * zdi.z;
+         dot_p += (double)rp.x * zpi.x + (double)rp.y * zpi.y + (double)rp.z * zpi.z;
       }
    }
+   if (slot)
+      pcg_block_add2(dot_d, dot_p, slot, 0, 1);
 }
 
 template <bool TABLE>
 __global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
-   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real* __restrict__ rd, const real* __restrict__ rp,
-   real* __restrict__ zd, real* __restrict__ zp)
+   const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z,
+   const int* __restrict__ skip)
 {
+   if (skip && skip[1])
+      return;
    int e = blockIdx.x * blockDim.x + threadIdx.x;
    if (e >= nx)
       return;
@@ -277,23 +322,29 @@ __global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __res
    real pp = qi.y * qk.y * p.u;
    real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
    V3 R = v3(dx, dy, dz);
-   V3 rdi = v3(rd[3 * p.i], rd[3 * p.i + 1], rd[3 * p.i + 2]), rpi = v3(rp[3 * p.i], rp[3 * p.i + 1], rp[3 * p.i + 2]);
-   V3 rdk = v3(rd[3 * p.k], rd[3 * p.k + 1], rd[3 * p.k + 2]), rpk = v3(rp[3 * p.k], rp[3 * p.k + 1], rp[3 * p.k + 2]);
-   atomic_real3(zd, p.i, dipole_field(R, rdk, B1, B2));
-   atomic_real3(zp, p.i, dipole_field(R, rpk, B1, B2));
-   atomic_real3(zd, p.k, dipole_field(R, rdi, B1, B2));
-   atomic_real3(zp, p.k, dipole_field(R, rpi, B1, B2));
+   V3 rdi, rpi, rdk, rpk;
+   load_dp(Rv, p.i, rdi, rpi);
+   load_dp(Rv, p.k, rdk, rpk);
+   atomic_dp(Z, p.i, dipole_field(R, rdk, B1, B2), dipole_field(R, rpk, B1, B2));
+   atomic_dp(Z, p.k, dipole_field(R, rdi, B1, B2), dipole_field(R, rpi, B1, B2));
 }
 
-__global__ void k_diag_precond(int n3, real udiag, const real4* __restrict__ tpj, const real* __restrict__ rd,
-   const real* __restrict__ rp, real* __restrict__ zd, real* __restrict__ zp)
+// partial R.Z after an exclusion pass changed Z (only needed when u-scale exclusions exist)
+__global__ void k_dot_dp(int n, const real4* __restrict__ A, const real4* __restrict__ Bv, double* __restrict__ slot,
+   const int* __restrict__ skip)
 {
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   if (q >= n3)
+   if (skip && skip[1])
       return;
-   real pol = udiag * tpj[q / 3].y;
-   zd[q] = pol * rd[q];
-   zp[q] = pol * rp[q];
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   double x = 0, y = 0;
+   if (s < n) {
+      V3 ad, ap, bd, bp;
+      load_dp(A, s, ad, ap);
+      load_dp(Bv, s, bd, bp);
+      x = (double)ad.x * bd.x + (double)ad.y * bd.y + (double)ad.z * bd.z;
+      y = (double)ap.x * bp.x + (double)ap.y * bp.y + (double)ap.z * bp.z;
+   }
+   pcg_block_add2(x, y, slot, 0, 1);
 }
 
 } // namespace
@@ -302,7 +353,7 @@ __global__ void k_diag_precond(int n3, real udiag, const real4* __restrict__ tpj
 #define DF_G 16
 #define PC_G 8
 
-void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp)
+void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
 {
    RowList& L = c->rows;
    real cut = (real)c->opt.cutoff;
@@ -310,33 +361,29 @@ void apx_ufield_real(apx_ctx* c, const real* ud, const real* up, real* fd, real*
    bool tb = c->thole_table != 0;
    int grid = rows_grid<UF_G>(c);
 #define LAUNCH_UF(E, T)                                                                                                   \
-   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
-      c->tpj, c->thlval, c->opt.njpolar, ud, up, fd, fp, c->skip)
-   if (L.nverlet > 0) {
-      // device-time the dominant kernel: one event pair per launch, read back by induce()
-      int slot = -1;
-      if (c->uf_used + 2 <= (int)c->uf_ev.size()) {
-         slot = c->uf_used;
-         c->uf_used += 2;
-         cudaEventRecord(c->uf_ev[slot], c->stream);
-      }
-      if (ew && tb) LAUNCH_UF(true, true);
-      else if (ew) LAUNCH_UF(true, false);
-      else if (tb) LAUNCH_UF(false, true);
-      else LAUNCH_UF(false, false);
-      if (slot >= 0)
-         cudaEventRecord(c->uf_ev[slot + 1], c->stream);
-      APX_COUNT_LAUNCH(c);
+   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
+      c->thlval, c->opt.njpolar, U, F, c->skip)
+   // device-time the dominant kernel: one event pair per launch, read back by induce()
+   int slot = -1;
+   if (c->uf_used + 2 <= (int)c->uf_ev.size()) {
+      slot = c->uf_used;
+      c->uf_used += 2;
+      cudaEventRecord(c->uf_ev[slot], st);
    }
+   if (ew && tb) LAUNCH_UF(true, true);
+   else if (ew) LAUNCH_UF(true, false);
+   else if (tb) LAUNCH_UF(false, true);
+   else LAUNCH_UF(false, false);
+   if (slot >= 0)
+      cudaEventRecord(c->uf_ev[slot + 1], st);
+   APX_COUNT_LAUNCH(c);
 #undef LAUNCH_UF
    if (c->nexcl_u > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_ufield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, ud, up, fd, fp);
+         k_ufield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
       else
-         k_ufield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, ud, up, fd, fp);
+         k_ufield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
       APX_COUNT_LAUNCH(c);
    }
 }
@@ -372,39 +419,49 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    }
 }
 
-// z = M r.  If diag_done the caller already wrote the diagonal part (fused PCG update kernel).
-void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp, bool diag_done)
+// Z = M R: diagonal (udiag*alpha, or alpha alone without the sparse part) + short-range off-diagonal
+// blocks (sparsePrecondApply / diagPrecond, src/amoeba/induce.cpp:12-25); partial R.Z into slot.
+void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const PcgTest* test)
 {
+   PcgTest T;
+   if (test)
+      T = *test;
    bool sparse = c->opt.pcgprec && c->opt.usolve_cutoff > 0;
-   if (!diag_done) {
-      int n3 = 3 * c->n;
-      real udiag = sparse ? (real)c->opt.uaccel : (real)1;
-      k_diag_precond<<<(n3 + 255) / 256, 256, 0, c->stream>>>(n3, udiag, c->tpj, rd, rp, zd, zp);
-      APX_COUNT_LAUNCH(c);
-   }
-   if (!sparse)
-      return;
+   real udiag = sparse ? (real)c->opt.uaccel : (real)1;
    RowList& L = c->rows;
    real cut = (real)c->opt.usolve_cutoff;
    bool tb = c->thole_table != 0;
-   if (L.nverlet > 0) {
-      int grid = rows_grid<PC_G>(c);
-      if (tb)
-         k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, L.vstart, L.cntu, L.nbr, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, rd, rp, zd, zp, c->skip);
-      else
-         k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, L.vstart, L.cntu, L.nbr, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, rd, rp, zd, zp, c->skip);
-      APX_COUNT_LAUNCH(c);
-   }
-   if (c->nexcl_u > 0) {
+   bool excl = sparse && c->nexcl_u > 0;
+   int grid = rows_grid<PC_G>(c);
+   const int* cu = sparse ? L.cntu.p : nullptr;
+   double* s1 = excl ? nullptr : slot;
+   if (tb)
+      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+         c->opt.njpolar, Rv, Z, s1, c->skip, T);
+   else
+      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+         c->opt.njpolar, Rv, Z, s1, c->skip, T);
+   APX_COUNT_LAUNCH(c);
+   if (excl) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, rd, rp, zd, zp);
+         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+            Rv, Z, c->skip);
       else
-         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
-            c->opt.njpolar, rd, rp, zd, zp);
+         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+            Rv, Z, c->skip);
       APX_COUNT_LAUNCH(c);
+      if (slot) {
+         k_dot_dp<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->n, Rv, Z, slot, c->skip);
+         APX_COUNT_LAUNCH(c);
+      }
    }
+}
+
+// plain-array front end (apx_precond of the C ABI)
+void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp)
+{
+   apx_pack_dp(c, rd, rp, c->pk_r);
+   apx_precond_dp(c, c->pk_r, c->pk_z, nullptr);
+   apx_unpack_dp(c, c->pk_z, zd, zp);
 }

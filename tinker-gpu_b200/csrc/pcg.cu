@@ -1,214 +1,114 @@
 // Preconditioned conjugate-gradient solver for the mutual induced dipoles, d and p right-hand
 // sides in lock step: same recurrences, guess, peek step and stopping rule as
 // induceMutualPcg1_cu (src/cu/amoeba/pcg.cu:14-185) and the pcg* vector kernels
-// (src/cu/induce.cu:17-232), restructured for launch/HBM economy:
+// (src/cu/induce.cu:17-232), restructured for launch/HBM economy.
 //
-//   * 3 fused vector passes per iteration instead of 6 kernels + 6 cuBLAS dots + 2 copies:
-//       A  vec = p/alpha - field ; partial p.vec
-//       B  u += a p ; r -= a vec ; z = udiag*alpha*r (diagonal of the preconditioner) ; partial r.r
-//       C  partial r.z   and   D  p = z + b p  /  convergence test / peek
-//     (C and D need a grid-wide reduction between them, hence two launches);
-//   * all scalars stay on the device in per-iteration slots (no zeroing races, no cuBLAS);
+// One iteration is a chain of 4 kernels of ours around the FFT instead of the reference's
+// ~14 kernels + 6 cuBLAS dots + a blocking host read:
+//
+//   K1  k_pcg_dir_spread   (pme.cu)   p = z + b p, spread p
+//       FFT, influence function, inverse FFT
+//   K2  k_ufield_rows      (field.cu) real-space field of p -- on a second stream, beside the FFT
+//   K3  k_gather_dp<2>     (pme.cu)   recip+self field, + real-space field, Ap = p/alpha - field, p.Ap
+//   K4  k_pcg_update                  u += a p ; r -= a Ap ; r.r ; PME grid zeroed for the next spread
+//   K5  k_precond_rows     (field.cu) eps test on r.r: peek + stop flag, or z = M r (diagonal + sparse rows), r.z
+//
+//   * vectors are packed (d,p) pairs, 32 B per atom (dp.cuh);
+//   * all scalars stay on the device in per-iteration slots of 16 sub-slots each (no zeroing
+//     races, no cuBLAS, short same-address atomic chains);
 //   * NO per-iteration host synchronisation: the host enqueues a batch of iterations sized from
-//     the previous solve; kernel D raises a device flag when  eps < poleps (and iter >= miniter)
-//     and applies the peek step; every later kernel of the batch returns immediately when the
-//     flag is up.  The host reads the flag once per batch from pinned memory.
+//     the previous solve; K5 raises a device flag when eps < poleps (and iter >= miniter) and
+//     applies the peek step; every later kernel of the batch returns immediately when the flag
+//     is up.  The host reads the flag once per batch from pinned memory.
 #include "apx_internal.h"
+#include "dp.cuh"
 #include <algorithm>
 #include <cmath>
 
 namespace {
-constexpr int SLOT = 8;     // doubles per iteration: [0,1] r.z(prev) [2,3] p.Ap [6,7] r.r ; r.z(new) -> next slot [0,1]
-
-__device__ __forceinline__ void block_sum2(double a, double b, double* out_a, double* out_b)
+// udir = alpha E_d ; udirp = alpha (E_d + delta_p) ; fieldp = E_d + delta ; initial guess u = udir.
+// P receives the packed guess (or the packed field when there is no guess: r0 = E).
+__global__ void k_udir(int n, const real4* __restrict__ tpj, const real* __restrict__ fd, real* __restrict__ fpd,
+   real* __restrict__ udir, real* __restrict__ udirp, real* __restrict__ uind, real* __restrict__ uinp, real4* __restrict__ P,
+   int guess)
 {
-   __shared__ double sh[2][8];
-   int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-   for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      b += __shfl_xor_sync(0xffffffffu, b, o);
-   }
-   if (lane == 0) {
-      sh[0][w] = a;
-      sh[1][w] = b;
-   }
-   __syncthreads();
-   if (threadIdx.x == 0) {
-      double x = 0, y = 0;
-      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
-         x += sh[0][k];
-         y += sh[1][k];
-      }
-      atomicAdd(out_a, x);
-      atomicAdd(out_b, y);
-   }
-}
-
-// udir = alpha E_d ; udirp = alpha (E_d + delta_p) ; fieldp = E_d + delta ; initial guess u = udir
-__global__ void k_udir(int n3, const real4* __restrict__ tpj, const real* __restrict__ fd, real* __restrict__ fpd,
-   real* __restrict__ udir, real* __restrict__ udirp, real* __restrict__ uind, real* __restrict__ uinp, int guess)
-{
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   if (q >= n3)
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
       return;
-   real pol = tpj[q / 3].y;
-   real ed = fd[q], ep = ed + fpd[q];
-   fpd[q] = ep;
-   real a = pol * ed, b = pol * ep;
-   udir[q] = a;
-   udirp[q] = b;
-   uind[q] = guess ? a : 0;
-   uinp[q] = guess ? b : 0;
-}
-
-// r0: zero where alpha == 0 ; z = udiag alpha r (diagonal part)
-__global__ void k_rsd0(int n3, real udiag, const real4* __restrict__ tpj, real* __restrict__ rd, real* __restrict__ rp,
-   real* __restrict__ zd, real* __restrict__ zp)
-{
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   if (q >= n3)
-      return;
-   real pol = tpj[q / 3].y;
-   real a = rd[q], b = rp[q];
-   if (pol == 0) {
-      a = 0;
-      b = 0;
-      rd[q] = 0;
-      rp[q] = 0;
-   }
-   zd[q] = udiag * pol * a;
-   zp[q] = udiag * pol * b;
-}
-
-// p = z ; r.z -> slot0[0,1]
-__global__ void k_init_conj(int n3, const real* __restrict__ rd, const real* __restrict__ rp, const real* __restrict__ zd,
-   const real* __restrict__ zp, real* __restrict__ cd, real* __restrict__ cp, double* __restrict__ slot)
-{
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   double a = 0, b = 0;
-   if (q < n3) {
-      real z1 = zd[q], z2 = zp[q];
-      cd[q] = z1;
-      cp[q] = z2;
-      a = (double)rd[q] * z1;
-      b = (double)rp[q] * z2;
-   }
-   block_sum2(a, b, &slot[0], &slot[1]);
-}
-
-// pass A
-__global__ void k_pass_a(int n3, const int* __restrict__ flags, const real4* __restrict__ tpj, const real* __restrict__ cd,
-   const real* __restrict__ cp, const real* __restrict__ fd, const real* __restrict__ fp, real* __restrict__ vd,
-   real* __restrict__ vp, double* __restrict__ slot)
-{
-   if (flags[1])
-      return;
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   double a = 0, b = 0;
-   if (q < n3) {
-      real pinv = tpj[q / 3].z;
-      real c1 = cd[q], c2 = cp[q];
-      real v1 = pinv * c1 - fd[q], v2 = pinv * c2 - fp[q];
-      vd[q] = v1;
-      vp[q] = v2;
-      a = (double)c1 * v1;
-      b = (double)c2 * v2;
-   }
-   block_sum2(a, b, &slot[2], &slot[3]);
-}
-
-// pass B
-__global__ void k_pass_b(int n3, const int* __restrict__ flags, real udiag, const real4* __restrict__ tpj,
-   const real* __restrict__ cd, const real* __restrict__ cp, const real* __restrict__ vd, const real* __restrict__ vp,
-   real* __restrict__ ud, real* __restrict__ up, real* __restrict__ rd, real* __restrict__ rp, real* __restrict__ zd,
-   real* __restrict__ zp, double* __restrict__ slot)
-{
-   if (flags[1])
-      return;
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   double e1 = 0, e2 = 0;
-   if (q < n3) {
-      double pa = slot[2], pb = slot[3];
-      real a = pa != 0.0 ? (real)(slot[0] / pa) : (real)0;
-      real ap = pb != 0.0 ? (real)(slot[1] / pb) : (real)0;
-      real pol = tpj[q / 3].y;
-      ud[q] += a * cd[q];
-      up[q] += ap * cp[q];
-      real r1 = rd[q] - a * vd[q], r2 = rp[q] - ap * vp[q];
+   real pol = tpj[s].y;
+   V3 ed = v3(fd[3 * s], fd[3 * s + 1], fd[3 * s + 2]);
+   V3 ep = ed + v3(fpd[3 * s], fpd[3 * s + 1], fpd[3 * s + 2]);
+   fpd[3 * s] = ep.x, fpd[3 * s + 1] = ep.y, fpd[3 * s + 2] = ep.z;
+   V3 a = pol * ed, b = pol * ep;
+   udir[3 * s] = a.x, udir[3 * s + 1] = a.y, udir[3 * s + 2] = a.z;
+   udirp[3 * s] = b.x, udirp[3 * s + 1] = b.y, udirp[3 * s + 2] = b.z;
+   V3 z = v3(0, 0, 0);
+   V3 u0 = guess ? a : z, u1 = guess ? b : z;
+   uind[3 * s] = u0.x, uind[3 * s + 1] = u0.y, uind[3 * s + 2] = u0.z;
+   uinp[3 * s] = u1.x, uinp[3 * s + 1] = u1.y, uinp[3 * s + 2] = u1.z;
+   if (guess)
+      store_dp(P, s, a, b);
+   else {
       if (pol == 0) {
-         r1 = 0;
-         r2 = 0;
+         ed = z;
+         ep = z;
       }
-      rd[q] = r1;
-      rp[q] = r2;
-      zd[q] = udiag * pol * r1;
-      zp[q] = udiag * pol * r2;
-      e1 = (double)r1 * r1;
-      e2 = (double)r2 * r2;
+      store_dp(P, s, ed, ep);
    }
-   block_sum2(e1, e2, &slot[6], &slot[7]);
 }
 
-// pass C: r.z into the NEXT slot
-__global__ void k_pass_c(int n3, const int* __restrict__ flags, const real* __restrict__ rd, const real* __restrict__ rp,
-   const real* __restrict__ zd, const real* __restrict__ zp, double* __restrict__ slot)
+// K4: u += a p ; r -= a Ap (zero where alpha == 0) ; partial r.r ; zero the PME grid
+__global__ void __launch_bounds__(256) k_pcg_update(int n, const int* __restrict__ flags, const real4* __restrict__ tpj,
+   const real4* __restrict__ P, const real4* __restrict__ V, real4* __restrict__ R, real* __restrict__ ud, real* __restrict__ up,
+   double* __restrict__ slot, real4* __restrict__ grid4, size_t ngrid4)
 {
    if (flags[1])
       return;
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   double a = 0, b = 0;
-   if (q < n3) {
-      a = (double)rd[q] * zd[q];
-      b = (double)rp[q] * zp[q];
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   double e1 = 0, e2 = 0;
+   if (s < n) {
+      double pa = pcg_q(slot, 2), pb = pcg_q(slot, 3);
+      real a = pa != 0.0 ? (real)(pcg_q(slot, 0) / pa) : (real)0;
+      real ap = pb != 0.0 ? (real)(pcg_q(slot, 1) / pb) : (real)0;
+      V3 pd, pp, vd, vp, rd, rp;
+      load_dp(P, s, pd, pp);
+      load_dp(V, s, vd, vp);
+      load_dp(R, s, rd, rp);
+      ud[3 * s] += a * pd.x, ud[3 * s + 1] += a * pd.y, ud[3 * s + 2] += a * pd.z;
+      up[3 * s] += ap * pp.x, up[3 * s + 1] += ap * pp.y, up[3 * s + 2] += ap * pp.z;
+      rd = rd - a * vd;
+      rp = rp - ap * vp;
+      if (tpj[s].y == 0) {
+         rd = v3(0, 0, 0);
+         rp = v3(0, 0, 0);
+      }
+      store_dp(R, s, rd, rp);
+      e1 = (double)rd.x * rd.x + (double)rd.y * rd.y + (double)rd.z * rd.z;
+      e2 = (double)rp.x * rp.x + (double)rp.y * rp.y + (double)rp.z * rp.z;
    }
-   block_sum2(a, b, &slot[SLOT + 0], &slot[SLOT + 1]);
+   real4 zero4;
+   zero4.x = zero4.y = zero4.z = zero4.w = 0;
+   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < ngrid4; q += (size_t)gridDim.x * blockDim.x)
+      grid4[q] = zero4;
+   pcg_block_add2(e1, e2, slot, 4, 5);
 }
 
-// pass D: convergence test; either p = z + b p, or the peek step + raise the flag
-__global__ void k_pass_d(int n3, int n, int iter, int miniter, int politer, real poleps, real debye, real pcgpeek, int* flags,
-   double* __restrict__ result, const real4* __restrict__ tpj, real* __restrict__ cd, real* __restrict__ cp,
-   const real* __restrict__ zd, const real* __restrict__ zp, real* __restrict__ ud, real* __restrict__ up,
-   const real* __restrict__ rd, const real* __restrict__ rp, const double* __restrict__ slot)
+__global__ void k_pack_dp(int n, const real* __restrict__ d, const real* __restrict__ p, real4* __restrict__ out)
 {
-   if (flags[1])
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
       return;
-   int q = blockIdx.x * blockDim.x + threadIdx.x;
-   double e = fmax(slot[6], slot[7]);
-   double eps = (double)debye * sqrt(e / n);
-   bool done = eps < (double)poleps;
-   if (iter < miniter)
-      done = false;
-   if (iter >= politer)
-      done = true;
-   if (q < n3) {
-      if (done) {
-         real term = pcgpeek * tpj[q / 3].y;
-         ud[q] += term * rd[q];
-         up[q] += term * rp[q];
-      } else {
-         double s0 = slot[0], s1 = slot[1];
-         real b = s0 != 0.0 ? (real)(slot[SLOT] / s0) : (real)0;
-         real bp = s1 != 0.0 ? (real)(slot[SLOT + 1] / s1) : (real)0;
-         cd[q] = zd[q] + b * cd[q];
-         cp[q] = zp[q] + bp * cp[q];
-      }
-   }
-   __syncthreads();
-   if (q == 0) {
-      result[0] = eps;
-      result[1] = (double)iter;
-      if (done) {
-         __threadfence();
-         flags[2] = iter;
-      }
-   }
-   // the flag itself is raised by a 1-thread tail kernel so no thread of THIS grid can see it early
+   store_dp(out, s, v3(d[3 * s], d[3 * s + 1], d[3 * s + 2]), v3(p[3 * s], p[3 * s + 1], p[3 * s + 2]));
 }
-
-__global__ void k_raise_flag(int* flags)
+__global__ void k_unpack_dp(int n, const real4* __restrict__ in, real* __restrict__ d, real* __restrict__ p)
 {
-   if (flags[2] > 0)
-      flags[1] = 1;
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   V3 a, b;
+   load_dp(in, s, a, b);
+   d[3 * s] = a.x, d[3 * s + 1] = a.y, d[3 * s + 2] = a.z;
+   p[3 * s] = b.x, p[3 * s + 1] = b.y, p[3 * s + 2] = b.z;
 }
 
 // caller order (f64) <-> sorted order (real)
@@ -241,10 +141,21 @@ void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev)
    APX_COUNT_LAUNCH(c);
 }
 
+void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out)
+{
+   k_pack_dp<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, d, p, out);
+   APX_COUNT_LAUNCH(c);
+}
+void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p)
+{
+   k_unpack_dp<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, in, d, p);
+   APX_COUNT_LAUNCH(c);
+}
+
 // full dfield into c->field (d) and c->fieldp (p), then udir/udirp and the initial guess
 void apx_dfield_full(apx_ctx* c, bool want_ev)
 {
-   int n3 = 3 * c->n;
+   int n = c->n, n3 = 3 * c->n;
    if (c->opt.use_ewald) {
       apx_pme_mpole(c, want_ev);                 // ASSIGNS c->field = recip + self
    } else {
@@ -252,28 +163,73 @@ void apx_dfield_full(apx_ctx* c, bool want_ev)
    }
    CUDA_CHECK(cudaMemsetAsync(c->fieldp.p, 0, sizeof(real) * n3, c->stream));
    apx_dfield_real(c, c->field, c->fieldp);
-   k_udir<<<(n3 + 255) / 256, 256, 0, c->stream>>>(n3, c->tpj, c->field, c->fieldp, c->udir, c->udirp, c->uind, c->uinp,
+   k_udir<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->tpj, c->field, c->fieldp, c->udir, c->udirp, c->uind, c->uinp, c->pk_p,
       c->opt.pcgguess ? 1 : 0);
    APX_COUNT_LAUNCH(c);
 }
 
+// Real-space rows of U on the second stream while the main stream runs spread (optional) + FFTs.
+// On return the main stream has waited for the rows; c->pk_f holds the real-space field.
+static void field_of_dp(apx_ctx* c, const real4* U, bool spread)
+{
+   cudaStream_t st = c->stream;
+   CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+   CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+   apx_ufield_real_dp(c, c->stream2, U, c->pk_f);
+   CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+   if (c->opt.use_ewald) {
+      if (spread)
+         apx_pme_spread_dp(c, U);
+      apx_pme_convolve(c);
+   }
+   CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));
+}
+
+// field of the dipole pair (ud, up): ufield() of the reference (src/amoeba/field.cpp:111-117)
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp)
 {
-   int n3 = 3 * c->n;
-   if (c->opt.use_ewald) {
-      apx_pme_ufield(c, ud, up, fd, fp, nullptr, nullptr, nullptr);
-   } else {
-      CUDA_CHECK(cudaMemsetAsync(fd, 0, sizeof(real) * n3, c->stream));
-      CUDA_CHECK(cudaMemsetAsync(fp, 0, sizeof(real) * n3, c->stream));
+   apx_pack_dp(c, ud, up, c->pk_p);
+   if (c->opt.use_ewald)
+      apx_pme_zero_grid(c);
+   field_of_dp(c, c->pk_p, true);
+   if (c->opt.use_ewald)
+      apx_pme_gather_dp(c, 0, c->pk_p, c->pk_f, fd, fp, nullptr, nullptr);
+   else
+      apx_unpack_dp(c, c->pk_f, fd, fp);
+}
+
+__global__ void k_mask_dp(int n, const real4* __restrict__ tpj, real4* __restrict__ V)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s < n && tpj[s].y == 0)
+      store_dp(V, s, v3(0, 0, 0), v3(0, 0, 0));
+}
+__global__ void k_nonewald_ap(int n, const int* __restrict__ flags, const real4* __restrict__ tpj, const real4* __restrict__ P,
+   const real4* __restrict__ F, real4* __restrict__ V, double* __restrict__ slot)
+{
+   if (flags[1])
+      return;
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   double x = 0, y = 0;
+   if (s < n) {
+      V3 pd, pp, fd, fp;
+      load_dp(P, s, pd, pp);
+      load_dp(F, s, fd, fp);
+      real pinv = tpj[s].z;
+      V3 vd = pinv * pd - fd, vp = pinv * pp - fp;
+      store_dp(V, s, vd, vp);
+      x = (double)pd.x * vd.x + (double)pd.y * vd.y + (double)pd.z * vd.z;
+      y = (double)pp.x * vp.x + (double)pp.y * vp.y + (double)pp.z * vp.z;
    }
-   apx_ufield_real(c, ud, up, fd, fp);
+   pcg_block_add2(x, y, slot, 2, 3);
 }
 
 void apx_induce_impl(apx_ctx* c)
 {
    const int n = c->n, n3 = 3 * n;
-   const int g3 = (n3 + 255) / 256;
+   const int g1 = (n + 255) / 256;
    cudaStream_t st = c->stream;
+   const bool ewald = c->opt.use_ewald != 0;
    if (!c->mpole_inited)
       apx_rotpole(c);
    if (c->uf_ev.empty()) {
@@ -295,47 +251,63 @@ void apx_induce_impl(apx_ctx* c)
       cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
       return;
    }
-   const bool sparse = c->opt.pcgprec && c->opt.usolve_cutoff > 0;
-   const real udiag = sparse ? (real)c->opt.uaccel : (real)1;
    const int politer = c->opt.politer;
    const int miniter = std::min(3, n);
-   size_t nscal = (size_t)SLOT * (politer + 3) + 8;
+   size_t nscal = (size_t)PCG_SLOT * (politer + 3) + 8;
    c->scal.ensure(nscal);
    CUDA_CHECK(cudaMemsetAsync(c->scal.p, 0, nscal * sizeof(double), st));
    CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), st));
-   double* result = c->scal.p + (size_t)SLOT * (politer + 3);
+   CUDA_CHECK(cudaMemsetAsync(c->pk_z.p, 0, sizeof(real4) * 2 * c->npad, st));
+   double* result = c->scal.p + (size_t)PCG_SLOT * (politer + 3);
+   const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nfft3 * sizeof(cplx) / sizeof(real4) : 0;
 
-   // r0 = -T u0  (pcgguess) or E (no guess)
+   // r0 = -T u0  (pcgguess; k_udir left u0 packed in pk_p) or E (no guess; k_udir left E packed in pk_p)
    if (c->opt.pcgguess) {
-      apx_ufield_full(c, c->uind, c->uinp, c->rsd, c->rsdp);
+      if (ewald)
+         apx_pme_zero_grid(c);
+      field_of_dp(c, c->pk_p, true);
+      if (ewald)
+         apx_pme_gather_dp(c, 1, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_r, nullptr);
+      else {
+         CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p, c->pk_f.p, sizeof(real4) * 2 * n, cudaMemcpyDeviceToDevice, st));
+         k_mask_dp<<<g1, 256, 0, st>>>(n, c->tpj, c->pk_r);
+         APX_COUNT_LAUNCH(c);
+      }
    } else {
-      CUDA_CHECK(cudaMemcpyAsync(c->rsd.p, c->field.p, sizeof(real) * n3, cudaMemcpyDeviceToDevice, st));
-      CUDA_CHECK(cudaMemcpyAsync(c->rsdp.p, c->fieldp.p, sizeof(real) * n3, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p, c->pk_p.p, sizeof(real4) * 2 * n, cudaMemcpyDeviceToDevice, st));
    }
-   k_rsd0<<<g3, 256, 0, st>>>(n3, udiag, c->tpj, c->rsd, c->rsdp, c->zrsd, c->zrsdp);
-   APX_COUNT_LAUNCH(c);
-   apx_precond_apply(c, c->rsd, c->rsdp, c->zrsd, c->zrsdp, true);
-   k_init_conj<<<g3, 256, 0, st>>>(n3, c->rsd, c->rsdp, c->zrsd, c->zrsdp, c->conj, c->conjp, c->scal.p);
-   APX_COUNT_LAUNCH(c);
+   // z0 = M r0, r0.z0 -> slot of iteration 1 ; p starts at zero so that K1 makes p = z0
+   CUDA_CHECK(cudaMemsetAsync(c->pk_p.p, 0, sizeof(real4) * 2 * c->npad, st));
+   apx_precond_dp(c, c->pk_r, c->pk_z, c->scal.p);
+   if (ewald)
+      apx_pme_zero_grid(c);
 
    int iter = 0;
    bool done = false;
    c->skip = c->flags.p;
    int batch = std::max(1, std::min(c->last_iters, politer));
+   PcgTest T;
+   T.miniter = miniter, T.politer = politer;
+   T.poleps = (real)c->opt.poleps, T.debye = (real)4.803206802, T.pcgpeek = (real)c->opt.pcgpeek;
+   T.result = result, T.flags = c->flags, T.ud = c->uind, T.up = c->uinp;
    while (!done) {
       for (int b = 0; b < batch && iter < politer; ++b) {
          ++iter;
-         double* slot = c->scal.p + (size_t)SLOT * (iter - 1);
-         apx_ufield_full(c, c->conj, c->conjp, c->field, c->fieldp);
-         k_pass_a<<<g3, 256, 0, st>>>(n3, c->flags, c->tpj, c->conj, c->conjp, c->field, c->fieldp, c->vec, c->vecp, slot);
-         k_pass_b<<<g3, 256, 0, st>>>(n3, c->flags, udiag, c->tpj, c->conj, c->conjp, c->vec, c->vecp, c->uind, c->uinp, c->rsd, c->rsdp,
-            c->zrsd, c->zrsdp, slot);
-         apx_precond_apply(c, c->rsd, c->rsdp, c->zrsd, c->zrsdp, true);
-         k_pass_c<<<g3, 256, 0, st>>>(n3, c->flags, c->rsd, c->rsdp, c->zrsd, c->zrsdp, slot);
-         k_pass_d<<<g3, 256, 0, st>>>(n3, n, iter, miniter, politer, (real)c->opt.poleps, (real)4.803206802, (real)c->opt.pcgpeek,
-            c->flags, result, c->tpj, c->conj, c->conjp, c->zrsd, c->zrsdp, c->uind, c->uinp, c->rsd, c->rsdp, slot);
-         k_raise_flag<<<1, 1, 0, st>>>(c->flags);
-         c->stats.kernel_launches += 5;
+         double* slot = c->scal.p + (size_t)PCG_SLOT * (iter - 1);
+         apx_pme_pcg_dir_spread(c, iter);
+         field_of_dp(c, c->pk_p, false);
+         if (ewald)
+            apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot);
+         else {
+            k_nonewald_ap<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_f, c->pk_v, slot);
+            APX_COUNT_LAUNCH(c);
+         }
+         k_pcg_update<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_v, c->pk_r, c->uind, c->uinp, slot, (real4*)c->qgrid.p,
+            ngrid4);
+         APX_COUNT_LAUNCH(c);
+         T.it = iter;
+         T.slot = slot;
+         apx_precond_dp(c, c->pk_r, c->pk_z, slot + PCG_SLOT, &T);
       }
       CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -345,10 +317,11 @@ void apx_induce_impl(apx_ctx* c)
       batch = 2;
    }
    c->skip = nullptr;
+   int used = c->flags_h[2] > 0 ? c->flags_h[2] : iter;
    {
       // mean device time of the real-space ufield launches that did work (speculative launches after
-      // convergence return immediately and are excluded: only the first `used+1` pairs count)
-      int used_pairs = std::min(c->uf_used / 2, (c->flags_h[2] > 0 ? c->flags_h[2] : iter) + 1);
+      // convergence return immediately and are excluded): 1 for r0 + one per iteration
+      int used_pairs = std::min(c->uf_used / 2, used + (c->opt.pcgguess ? 1 : 0));
       float tot = 0;
       for (int k = 0; k < used_pairs; ++k) {
          float ms = 0;
@@ -357,7 +330,6 @@ void apx_induce_impl(apx_ctx* c)
       }
       c->stats.ms_ufield_real = used_pairs ? tot / used_pairs : 0;
    }
-   int used = c->flags_h[2] > 0 ? c->flags_h[2] : iter;
    c->stats.pcg_iterations = used;
    c->last_iters = used;
    c->stats.ms_induce = 0;

@@ -14,6 +14,7 @@
 // box (the reference recomputes exp() per grid point on every call, "TODO: store vs recompute",
 // src/amoeba/field.cpp:87).
 #include "apx_internal.h"
+#include "dp.cuh"
 #include <cmath>
 
 namespace {
@@ -145,49 +146,21 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Box box, Xform X, i
    }
 }
 
-// dipole pair (d -> real, p -> imaginary).  If beta != nullptr the CG direction update
-// p <- z + beta p  (pcgP3, src/cu/induce.cu:172-190) is applied on the fly and written back.
-__global__ void __launch_bounds__(128) k_spread_uind(int n, Box box, Xform X, int n1, int n2, int n3,
-   const real4* __restrict__ posd, real* __restrict__ ud, real* __restrict__ up, const real* __restrict__ zd,
-   const real* __restrict__ zp, const double* __restrict__ scal, cplx* __restrict__ grid, const int* __restrict__ skip)
+// dipole pair (d -> real, p -> imaginary) of one atom onto its 125 stencil points
+__device__ __forceinline__ void spread_dipoles(const Xform& X, const Stencil& st, const real (*sth)[5][4], int lane, int n1, int n2,
+   int n3, V3 d, V3 q, cplx* __restrict__ grid)
 {
-   if (skip && skip[1])
-      return;
-   __shared__ real sth[4][3][5][4];
-   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-   int s = blockIdx.x * 4 + wib;
-   if (s >= n)
-      return;
-   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
-   real d[3] = {ud[3 * s], ud[3 * s + 1], ud[3 * s + 2]};
-   real q[3] = {up[3 * s], up[3 * s + 1], up[3 * s + 2]};
-   if (zd) {
-      // scal[0],[1] = r.z of the previous iteration, scal[4],[5] = r.z of this one
-      double s0 = scal[0], s1 = scal[1];
-      real b = s0 != 0.0 ? (real)(scal[4] / s0) : (real)0;
-      real bp = s1 != 0.0 ? (real)(scal[5] / s1) : (real)0;
-      #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-         d[c] = zd[3 * s + c] + b * d[c];
-         q[c] = zp[3 * s + c] + bp * q[c];
-      }
-      __syncwarp();
-      if (lane < 3) {
-         ud[3 * s + lane] = d[lane];
-         up[3 * s + lane] = q[lane];
-      }
-   }
    real fd[3], fp[3];
    #pragma unroll
    for (int f = 0; f < 3; ++f) {
-      fd[f] = X.a[0][f] * d[0] + X.a[1][f] * d[1] + X.a[2][f] * d[2];
-      fp[f] = X.a[0][f] * q[0] + X.a[1][f] * q[1] + X.a[2][f] * q[2];
+      fd[f] = X.a[0][f] * d.x + X.a[1][f] * d.y + X.a[2][f] * d.z;
+      fp[f] = X.a[0][f] * q.x + X.a[1][f] * q.y + X.a[2][f] * q.z;
    }
    for (int p = lane; p < 125; p += 32) {
       int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
-      const real* t = sth[wib][0][ix];
-      const real* u = sth[wib][1][iy];
-      const real* v = sth[wib][2][iz];
+      const real* t = sth[0][ix];
+      const real* u = sth[1][iy];
+      const real* v = sth[2][iz];
       real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
       real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
       real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
@@ -198,6 +171,55 @@ __global__ void __launch_bounds__(128) k_spread_uind(int n, Box box, Xform X, in
 #else
       atomicAdd(reinterpret_cast<float2*>(&grid[idx]), make_float2(vd, vp));
 #endif
+   }
+}
+
+// spread of a packed (d,p) dipole pair array (dp.cuh)
+__global__ void __launch_bounds__(128) k_spread_dp(int n, Box box, Xform X, int n1, int n2, int n3, const real4* __restrict__ posd,
+   const real4* __restrict__ U, cplx* __restrict__ grid)
+{
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   int s = blockIdx.x * 4 + wib;
+   if (s >= n)
+      return;
+   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   V3 d, q;
+   load_dp(U, s, d, q);
+   spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, d, q, grid);
+}
+
+// First kernel of a PCG iteration: direction update p = z + b p (pcgP3, src/cu/induce.cu:172-190;
+// b = r.z(new) / r.z(old) re-derived by every warp from the sub-slotted sums, b = 0 and p = 0 on
+// the first iteration) written back packed and spread onto the PME grid in the same pass.
+__global__ void __launch_bounds__(128) k_pcg_dir_spread(int n, Box box, Xform X, int n1, int n2, int n3, int do_spread,
+   const real4* __restrict__ posd, real4* __restrict__ P, const real4* __restrict__ Z, const double* __restrict__ slot_prev,
+   const double* __restrict__ slot_cur, const int* __restrict__ flags, cplx* __restrict__ grid)
+{
+   if (flags[1])
+      return;
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   const int s = blockIdx.x * 4 + wib;
+   if (s >= n)
+      return;
+   real b = 0, bp = 0;
+   if (slot_prev) {
+      double s0 = pcg_q(slot_prev, 0), s1 = pcg_q(slot_prev, 1);
+      b = s0 != 0.0 ? (real)(pcg_q(slot_cur, 0) / s0) : (real)0;
+      bp = s1 != 0.0 ? (real)(pcg_q(slot_cur, 1) / s1) : (real)0;
+   }
+   V3 zd, zp, pd, pp;
+   load_dp(Z, s, zd, zp);
+   load_dp(P, s, pd, pp);
+   pd = zd + b * pd;
+   pp = zp + bp * pp;
+   __syncwarp();
+   if (lane == 0)
+      store_dp(P, s, pd, pp);
+   if (do_spread) {
+      Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+      spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, pd, pp, grid);
    }
 }
 
@@ -345,7 +367,7 @@ __global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real
 // --- gather ------------------------------------------------------------------------------------
 // 25 lanes own one (iy,iz) row of five x-points each.
 // MODE 0: permanent multipoles: fphi[20] stored; field assigned: fd = term*dipole - grad_cart(phi)
-// MODE 1: ufield: fd = term*ud - cart(fphi_d[1..3]), fp likewise (recip + self, ASSIGNED)
+// (the ufield gather with its fused epilogues is k_gather_dp below)
 // MODE 2: energy step: fphid[10], fphip[10], fphidp[20] stored
 template <int MODE>
 __global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
@@ -429,20 +451,6 @@ __global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1,
          real d = lane == 0 ? m0.y : (lane == 1 ? m0.z : m0.w);
          out_b[3 * s + lane] = selfterm * d - cphi;
       }
-   } else if (MODE == 1) {
-      real fd[3] = {tr[1] * u[0] * v[0], tr[0] * u[1] * v[0], tr[0] * u[0] * v[1]};
-      real fp[3] = {ti[1] * u[0] * v[0], ti[0] * u[1] * v[0], ti[0] * u[0] * v[1]};
-      #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-         WSUM(fd[q]);
-         WSUM(fp[q]);
-      }
-      if (lane < 3) {
-         real cd = X.a[lane][0] * fd[0] + X.a[lane][1] * fd[1] + X.a[lane][2] * fd[2];
-         real cp = X.a[lane][0] * fp[0] + X.a[lane][1] * fp[1] + X.a[lane][2] * fp[2];
-         out_a[3 * s + lane] = selfterm * ud[3 * s + lane] - cd;
-         out_b[3 * s + lane] = selfterm * up[3 * s + lane] - cp;
-      }
    } else {
       real fd[10], fp[10], fs[20];
       real ts[4];
@@ -497,6 +505,86 @@ __global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1,
    }
 #undef WSUM
 #undef COMBO
+}
+
+// Gather of the reciprocal mutual field of a packed dipole pair U, fused with what follows it:
+//   field = selfterm*U - grad_cart(phi) + F        (F = real-space field from the row kernel, may be null)
+//   EPI 0: plain output  fd, fp [n][3]                               (ufield operator)
+//   EPI 1: residual      R = field, zero where alpha == 0            (r0 = -T u0)
+//   EPI 2: PCG           V = U/alpha - field ; partial U.V -> slot   (pcgP1 + dots, src/cu/induce.cu)
+template <int EPI>
+__global__ void __launch_bounds__(128) k_gather_dp(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
+   const real4* __restrict__ posd, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
+   const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
+   double* __restrict__ slot, const int* __restrict__ skip)
+{
+   if (skip && skip[1])
+      return;
+   __shared__ real sth[4][3][5][4];
+   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+   const int s = blockIdx.x * 4 + wib;
+   double dot_d = 0, dot_p = 0;
+   if (s < n) {
+      Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+      real tr0 = 0, tr1 = 0, ti0 = 0, ti1 = 0;
+      real u0 = 0, u1 = 0, v0 = 0, v1 = 0;
+      if (lane < 25) {
+         int iy = lane % 5, iz = lane / 5;
+         int base = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1;
+         #pragma unroll
+         for (int ix = 0; ix < 5; ++ix) {
+            cplx g = grid[base + wrapi(st.i1 + ix, n1)];
+            const real* t = sth[wib][0][ix];
+            tr0 += g.x * t[0], tr1 += g.x * t[1];
+            ti0 += g.y * t[0], ti1 += g.y * t[1];
+         }
+         u0 = sth[wib][1][iy][0], u1 = sth[wib][1][iy][1];
+         v0 = sth[wib][2][iz][0], v1 = sth[wib][2][iz][1];
+      }
+      real fd[3] = {tr1 * u0 * v0, tr0 * u1 * v0, tr0 * u0 * v1};
+      real fp[3] = {ti1 * u0 * v0, ti0 * u1 * v0, ti0 * u0 * v1};
+      #pragma unroll
+      for (int q = 0; q < 3; ++q) {
+         #pragma unroll
+         for (int o = 16; o > 0; o >>= 1) {
+            fd[q] += __shfl_xor_sync(0xffffffffu, fd[q], o);
+            fp[q] += __shfl_xor_sync(0xffffffffu, fp[q], o);
+         }
+      }
+      if (lane == 0) {
+         V3 ud, up;
+         load_dp(U, s, ud, up);
+         V3 cd = v3(X.a[0][0] * fd[0] + X.a[0][1] * fd[1] + X.a[0][2] * fd[2], X.a[1][0] * fd[0] + X.a[1][1] * fd[1] + X.a[1][2] * fd[2],
+            X.a[2][0] * fd[0] + X.a[2][1] * fd[1] + X.a[2][2] * fd[2]);
+         V3 cp = v3(X.a[0][0] * fp[0] + X.a[0][1] * fp[1] + X.a[0][2] * fp[2], X.a[1][0] * fp[0] + X.a[1][1] * fp[1] + X.a[1][2] * fp[2],
+            X.a[2][0] * fp[0] + X.a[2][1] * fp[1] + X.a[2][2] * fp[2]);
+         V3 ed = selfterm * ud - cd, ep = selfterm * up - cp;
+         if (F) {
+            V3 a, b;
+            load_dp(F, s, a, b);
+            ed += a;
+            ep += b;
+         }
+         if (EPI == 0) {
+            out_d[3 * s] = ed.x, out_d[3 * s + 1] = ed.y, out_d[3 * s + 2] = ed.z;
+            out_p[3 * s] = ep.x, out_p[3 * s + 1] = ep.y, out_p[3 * s + 2] = ep.z;
+         } else if (EPI == 1) {
+            if (tpj[s].y == 0) {
+               ed = v3(0, 0, 0);
+               ep = v3(0, 0, 0);
+            }
+            store_dp(OUT, s, ed, ep);
+         } else {
+            real pinv = tpj[s].z;
+            V3 vd = pinv * ud - ed, vp = pinv * up - ep;
+            store_dp(OUT, s, vd, vp);
+            dot_d = (double)ud.x * vd.x + (double)ud.y * vd.y + (double)ud.z * vd.z;
+            dot_p = (double)up.x * vp.x + (double)up.y * vp.y + (double)up.z * vp.z;
+         }
+      }
+   }
+   if (EPI == 2)
+      pcg_block_add2(dot_d, dot_p, slot, 2, 3);
 }
 
 // --- host side ---------------------------------------------------------------------------------
@@ -701,21 +789,54 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
    c->mpole_pme_valid = 1;
 }
 
-// recip + self part of the mutual field; optional fused direction update (beta from scal)
-void apx_pme_ufield(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp, const double* scal_beta, real* zd, real* zp)
+// ---- mutual-field operator on packed dipole pairs (dp.cuh) ----
+void apx_pme_zero_grid(apx_ctx* c)
+{
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, ntot(c) * sizeof(cplx), c->stream));
+}
+
+// grid must be zero on entry
+void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
    int n = c->n;
    Xform X = make_xform(c);
-   size_t K = ntot(c);
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up,
-      scal_beta ? zd : nullptr, zp, scal_beta, c->qgrid, c->skip);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, U, c->qgrid);
    APX_COUNT_LAUNCH(c);
+}
+
+// forward FFT, influence function, inverse FFT
+void apx_pme_convolve(apx_ctx* c)
+{
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
    fft(c, CUFFT_INVERSE);
-   k_gather<1><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
-      ud, up, fd, fp, nullptr, c->skip);
+}
+
+// PCG iteration head: direction update + spread (k_pcg_dir_spread); it = 1, 2, ...
+void apx_pme_pcg_dir_spread(apx_ctx* c, int it)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   const double* prev = it >= 2 ? c->scal.p + (size_t)PCG_SLOT * (it - 2) : nullptr;
+   const double* cur = c->scal.p + (size_t)PCG_SLOT * (it - 1);
+   k_pcg_dir_spread<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->opt.use_ewald ? 1 : 0, c->posd,
+      c->pk_p, c->pk_z, prev, cur, c->flags, c->qgrid);
+   APX_COUNT_LAUNCH(c);
+}
+
+// epi 0: fd/fp plain out ; 1: OUT = residual ; 2: OUT = Ap with partial dots into slot
+void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot)
+{
+   int n = c->n;
+   Xform X = make_xform(c);
+   int g = (n + 3) / 4;
+#define GATHER_DP(E)                                                                                                       \
+   k_gather_dp<E><<<g, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->tpj, c->qgrid, U, F,  \
+      fd, fp, OUT, slot, c->skip)
+   if (epi == 0) GATHER_DP(0);
+   else if (epi == 1) GATHER_DP(1);
+   else GATHER_DP(2);
+#undef GATHER_DP
    APX_COUNT_LAUNCH(c);
 }
 
@@ -726,8 +847,8 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    Xform X = make_xform(c);
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_uind<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, (real*)ud, (real*)up, nullptr,
-      nullptr, nullptr, c->qgrid, nullptr);
+   apx_pack_dp(c, ud, up, c->pk_p);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, c->pk_p, c->qgrid);
    APX_COUNT_LAUNCH(c);
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
