@@ -134,6 +134,12 @@ int apx_pme_mpole_fphi(apx_ctx* ctx, double* fphi /* [n][20] */);
 int apx_pme_uind_fphi(apx_ctx* ctx, const double* uind, const double* uinp, double* fdip_phi1 /* [n][10] */,
    double* fdip_phi2 /* [n][10] */);
 
+/* PME convolution alone: grid <- IFFT(influence * FFT(grid)), grid = [nfft3][nfft2][nfft1] complex
+   (re,im interleaved), unnormalised like fftfront/pmeConv/fftback of src/pme.cpp:229-351.
+   apx_set_native_fft(ctx, 0) forces cuFFT instead of the fused 64^3 kernels (fft64.cu). */
+int apx_pme_convolve_grid(apx_ctx* ctx, const double* grid_in, double* grid_out);
+int apx_set_native_fft(apx_ctx* ctx, int on);
+
 int apx_get_stats(apx_ctx* ctx, apx_stats* out);
 int apx_stats_reset(apx_ctx* ctx);
 /* cudaStream_t the library launches on (for callers that time with their own events) */

@@ -169,6 +169,40 @@ def test_dhfr2_properties():
     ad.close()
 
 
+def test_pme_convolution_native_fft():
+    """The fused 64^3 FFT -> influence function -> inverse FFT kernels (fft64.cu) against numpy's FFT
+    and against the cuFFT path of the same library, on a random complex grid (dhfr2 grid, 64^3)."""
+    import tinker_gpu_b200 as tg
+    s = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    assert tuple(s.nfft) == (64, 64, 64)
+    am = _amoeba(s, "mixed")
+    rng = np.random.default_rng(7)
+    shape = (64, 64, 64)
+    g = rng.normal(size=shape) + 1j * rng.normal(size=shape)
+    # influence function from the response to a unit impulse through the cuFFT path
+    am.set_native_fft(False)
+    imp = np.zeros(shape, dtype=np.complex128)
+    imp[0, 0, 0] = 1.0
+    qfac = np.fft.fftn(am.pme_convolve_grid(imp)).real / imp.size
+    ref = np.fft.ifftn(qfac * np.fft.fftn(g)) * g.size          # unnormalised inverse, like cuFFT
+    out_cufft = am.pme_convolve_grid(g)
+    am.set_native_fft(True)
+    out_native = am.pme_convolve_grid(g)
+    scale = np.abs(ref).max()
+    assert np.abs(out_cufft - ref).max() < 2e-5 * scale
+    assert np.abs(out_native - ref).max() < 2e-5 * scale
+    assert np.abs(out_native - out_cufft).max() < 5e-6 * scale
+    # and the whole energy step must not care which FFT ran
+    from tinker_gpu_b200.amoeba import calc
+    r1 = am.energy(calc.v4)
+    am.set_native_fft(False)
+    r0 = am.energy(calc.v4)
+    assert abs(r1["esum"] - r0["esum"]) < 2e-7 * abs(r0["esum"])
+    assert _rms(r1["grad"] - r0["grad"]) < 2e-5
+    assert r1["pcg_iterations"] == r0["pcg_iterations"]
+    am.close()
+
+
 def test_no_cpu_fallback_message():
     from tinker_gpu_b200 import amoeba
     assert os.path.isfile(amoeba.library_path("mixed")), "libapx.so must be built in-tree"

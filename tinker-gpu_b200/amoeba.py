@@ -94,6 +94,7 @@ def load_library(precision="mixed"):
         "apx_energy": [C.c_int, C.POINTER(EnergyResult)], "apx_empole": [C.c_int, C.POINTER(EnergyResult)],
         "apx_epolar": [C.c_int, C.POINTER(EnergyResult)], "apx_get_gradient": [_DP],
         "apx_pme_mpole_fphi": [_DP], "apx_pme_uind_fphi": [_DP, _DP, _DP, _DP],
+        "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int],
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
     }.items():
         fn = getattr(lib, name)
@@ -269,6 +270,16 @@ class Amoeba:
         a, b = self._out(self.n, 10), self._out(self.n, 10)
         self._chk(self.lib.apx_pme_uind_fphi(self.ctx, _dp(uind), _dp(uinp), _dp(a), _dp(b)))
         return a, b
+
+    def pme_convolve_grid(self, grid):
+        """grid: complex array [nfft3][nfft2][nfft1] -> IFFT(influence * FFT(grid)), unnormalised."""
+        g = np.ascontiguousarray(grid, dtype=np.complex128)
+        out = np.empty_like(g)
+        self._chk(self.lib.apx_pme_convolve_grid(self.ctx, _dp(g.view(np.float64)), _dp(out.view(np.float64))))
+        return out
+
+    def set_native_fft(self, on):
+        self._chk(self.lib.apx_set_native_fft(self.ctx, int(bool(on))))
 
     def stats(self):
         s = Stats()

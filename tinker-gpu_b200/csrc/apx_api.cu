@@ -3,6 +3,7 @@
 #include "apx_internal.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 void apx_to_sorted(apx_ctx* c, const double* in_dev, real* out);
 void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev);
@@ -156,8 +157,11 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    cudaDeviceProp prop;
    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
    c->sm_count = prop.multiProcessorCount;
-   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-   CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+   // the latency-bound PME chain outranks the throughput-bound real-space rows it overlaps with
+   int prio_lo = 0, prio_hi = 0;
+   CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+   CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
+   CUDA_CHECK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_lo));
    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
    CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
    CUDA_CHECK(cudaEventCreate(&c->ev0));
@@ -169,6 +173,8 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    memset(&c->stats, 0, sizeof(c->stats));
    c->stats.npairs_m = -1;
    c->f_elec = (real)(sys->electric / sys->dielec);
+   if (const char* e = getenv("APX_NO_NATIVE_FFT"))
+      c->native_fft = atoi(e) ? 0 : 1;
    set_box(c, sys->lvec);
    if (sys->cutoff > 0.5 * std::min(std::min(sys->lvec[0], sys->lvec[4]), sys->lvec[8]) + 1e-9 && sys->cutoff < 1e6)
       APX_THROW("real-space cutoff exceeds half the box edge (minimum image would fail)");
@@ -289,7 +295,7 @@ void apx_destroy(apx_ctx* c)
    c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
-   c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();
+   c->theta.release(), c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();
    cudaEventDestroy(c->ev_fork);
    cudaEventDestroy(c->ev_join);
    cudaStreamDestroy(c->stream2);
@@ -520,6 +526,36 @@ int apx_stats_reset(apx_ctx* c)
    API_BEGIN
    c->stats.kernel_launches = 0;
    c->stats.list_rebuilds = 0;
+   API_END
+}
+
+int apx_set_native_fft(apx_ctx* c, int on)
+{
+   API_BEGIN
+   c->native_fft = on ? 1 : 0;
+   API_END
+}
+
+int apx_pme_convolve_grid(apx_ctx* c, const double* in, double* out)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (!c->opt.use_ewald)
+      APX_THROW("PME operator called on a non-Ewald system");
+   size_t K = (size_t)c->nfft1 * c->nfft2 * c->nfft3;
+   std::vector<cplx> h(K);
+   for (size_t i = 0; i < K; ++i) {
+      h[i].x = (real)in[2 * i];
+      h[i].y = (real)in[2 * i + 1];
+   }
+   CUDA_CHECK(cudaMemcpyAsync(c->qgrid.p, h.data(), K * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+   apx_pme_convolve(c);
+   CUDA_CHECK(cudaMemcpyAsync(h.data(), c->qgrid.p, K * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   for (size_t i = 0; i < K; ++i) {
+      out[2 * i] = (double)h[i].x;
+      out[2 * i + 1] = (double)h[i].y;
+   }
    API_END
 }
 

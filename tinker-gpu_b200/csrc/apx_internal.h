@@ -162,9 +162,11 @@ struct apx_ctx {
    int nfft1 = 0, nfft2 = 0, nfft3 = 0;
    cufftHandle plan = 0;
    int plan_ok = 0;
+   int native_fft = 1;                   // use fft64.cu when the grid is 64^3 (mixed build); 0 = always cuFFT
    DevBuf<cplx> qgrid;
    DevBuf<real> qfac;                    // influence function (expterm of pmeConv)
    DevBuf<real> bsmod1, bsmod2, bsmod3;
+   DevBuf<real4> theta;                  // [n][16] per-step spline tables + stencil origins (pme.cu)
    DevBuf<real> fphi;                    // [n][20] permanent, sorted order
    DevBuf<real> fmp;                     // [n][10]
    DevBuf<real> fphid, fphip, fphidp;    // [n][10],[n][10],[n][20]
@@ -210,6 +212,7 @@ void apx_torque(apx_ctx* c, bool do_v);
 // ---- pme.cu
 void apx_pme_setup(apx_ctx* c);
 void apx_pme_destroy(apx_ctx* c);
+void apx_pme_fill_theta(apx_ctx* c);                             // after every change of posd
 void apx_pme_mpole(apx_ctx* c, bool want_ev);                   // fills fmp, fphi (and recip E/virial in dbuf)
 void apx_pme_zero_grid(apx_ctx* c);
 void apx_pme_spread_dp(apx_ctx* c, const real4* U);              // grid += spread of a packed dipole pair
@@ -218,6 +221,10 @@ void apx_pme_pcg_dir_spread(apx_ctx* c, int it);
 void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot);
 void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool full20);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
+// ---- fft64.cu
+bool apx_fft64_usable(const apx_ctx* c);
+void apx_fft64_setup(apx_ctx* c);
+void apx_fft64_convolve(apx_ctx* c);                             // grid <- IFFT(qfac * FFT(grid))
 // ---- field.cu
 void apx_dfield_real(apx_ctx* c, real* fd, real* fp);
 void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F);    // F = real-space field of U (assigned)

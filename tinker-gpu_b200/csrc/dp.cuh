@@ -37,6 +37,29 @@ __device__ __forceinline__ double pcg_q(const double* __restrict__ slot, int q)
    return s;
 }
 
+// The same sums for a whole CTA: the first warp adds the sub-slots of quantities q0..q0+NQ-1 and
+// leaves them in shared memory.  Every thread of the CTA must call this (it synchronises).
+template <int NQ>
+__device__ __forceinline__ void pcg_q_block(const double* __restrict__ slot, int q0, double* out)
+{
+   __shared__ double sq_[NQ];
+   if (threadIdx.x < 32) {
+      #pragma unroll
+      for (int j = 0; j < NQ; ++j) {
+         double v = (int)threadIdx.x < PCG_NSUB ? slot[(q0 + j) * PCG_NSUB + threadIdx.x] : 0.0;
+         #pragma unroll
+         for (int o = PCG_NSUB / 2; o > 0; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+         if (threadIdx.x == 0)
+            sq_[j] = v;
+      }
+   }
+   __syncthreads();
+   #pragma unroll
+   for (int j = 0; j < NQ; ++j)
+      out[j] = sq_[j];
+}
+
 // block-wide sum of two doubles -> one atomic pair per CTA into sub-slot (blockIdx % PCG_NSUB)
 __device__ __forceinline__ void pcg_block_add2(double a, double b, double* __restrict__ slot, int qa, int qb)
 {

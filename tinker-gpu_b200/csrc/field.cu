@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, rea
    // CTA raises the stop flag (so no CTA of this grid can see it early).
    bool done = false;
    if (T.it > 0) {
-      double e = fmax(pcg_q(T.slot, 4), pcg_q(T.slot, 5));
+      double rr2_[2];
+      pcg_q_block<2>(T.slot, 4, rr2_);
+      double e = fmax(rr2_[0], rr2_[1]);
       double eps = (double)T.debye * sqrt(e / n);
       done = eps < (double)T.poleps;
       if (T.it < T.miniter)

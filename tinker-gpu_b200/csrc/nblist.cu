@@ -171,6 +171,7 @@ void apx_update_sorted_positions(apx_ctx* c)
    int g = (c->npad + 255) / 256;
    k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);
    APX_COUNT_LAUNCH(c);
+   apx_pme_fill_theta(c);
 }
 
 void apx_list_refresh(apx_ctx* c, bool force)
@@ -211,6 +212,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
    k_block_boxes<<<(c->nblk * 32 + APX_BLOCK - 1) / APX_BLOCK, APX_BLOCK, 0, c->stream>>>(n, c->nblk, c->posd, c->blk_ctr, c->blk_ext);
    c->stats.kernel_launches += 6;
    apx_rows_build(c);
+   apx_pme_fill_theta(c);
    CUDA_CHECK(cudaMemcpyAsync(c->xyz_ref, c->xyz_d, sizeof(double) * 3 * n, cudaMemcpyDeviceToDevice, c->stream));
    // rows of the current step + pair counts inside the cutoffs (roofline accounting only)
    {

@@ -51,12 +51,34 @@ __device__ __forceinline__ V3 qmul(const Mpole& m, V3 v)
 
 #ifdef APX_DOUBLE
 __device__ __forceinline__ real r_exp(real x) { return exp(x); }
-__device__ __forceinline__ real r_erfc(real x) { return erfc(x); }
 __device__ __forceinline__ real r_rsqrt(real x) { return rsqrt(x); }
+__device__ __forceinline__ real r_div(real a, real b) { return a / b; }
+// erfc(x) given e = exp(-x*x)
+__device__ __forceinline__ real r_erfc_e(real x, real) { return erfc(x); }
 #else
-__device__ __forceinline__ real r_exp(real x) { return expf(x); }
-__device__ __forceinline__ real r_erfc(real x) { return erfcf(x); }
+// Mixed build: hardware exp2 / reciprocal approximations (the reference's CUDA build is compiled
+// with --use_fast_math, src/cu/CMakeLists.txt:28-35, which makes the same substitutions).
+__device__ __forceinline__ real r_exp(real x) { return __expf(x); }
 __device__ __forceinline__ real r_rsqrt(real x) { return rsqrtf(x); }
+__device__ __forceinline__ real r_div(real a, real b) { return __fdividef(a, b); }
+// erfc(x) = exp(-x^2) * t * P9(t), t = 1/(1 + x/2): our own Chebyshev fit of erfcx(x)/t on
+// 0 <= x <= 4.6 (a*cutoff is 3.8 for the 7 A Ewald cutoff); relative error 3e-9 in exact
+// arithmetic, 3e-7 in float -- the same as erfcf's documented 4 ulp -- and < 3e-7 up to x = 6.
+__device__ __forceinline__ real r_erfc_e(real x, real e)
+{
+   const real t = __fdividef(1.0f, fmaf(0.5f, x, 1.0f));
+   real p = 3.5327550404e-02f;
+   p = fmaf(p, t, -2.5197705174e-01f);
+   p = fmaf(p, t, 7.4152748764e-01f);
+   p = fmaf(p, t, -1.1026462441e+00f);
+   p = fmaf(p, t, 7.9686896115e-01f);
+   p = fmaf(p, t, -3.1024419607e-01f);
+   p = fmaf(p, t, 3.0320297180e-01f);
+   p = fmaf(p, t, 2.2082756977e-01f);
+   p = fmaf(p, t, 2.8517960792e-01f);
+   p = fmaf(p, t, 2.8193334191e-01f);
+   return p * t * e;
+}
 #endif
 
 // minimum image
@@ -95,10 +117,10 @@ template <int N>
 __device__ __forceinline__ void radial_ewald(real r, real rinv, real rr2, real aewald, real* bn)
 {
    real ra = aewald * r;
-   bn[0] = r_erfc(ra) * rinv;
+   real ex = r_exp(-ra * ra);
+   bn[0] = r_erfc_e(ra, ex) * rinv;
    real a2 = 2 * aewald * aewald;
    real pref = (real)0.5641895835477563 / aewald;   // 1/(sqrt(pi) a)
-   real ex = r_exp(-ra * ra);
    #pragma unroll
    for (int j = 1; j < N; ++j) {
       pref *= a2;
@@ -115,7 +137,7 @@ __device__ __forceinline__ void thole_one_minus_lambda(real r, real pdi, real pd
    real dmp = pdi * pdk;
    real ex = 0, x = 0;
    if (dmp != 0) {
-      real q = r / dmp;
+      real q = r_div(r, dmp);
       x = pgamma * q * q * q;
       ex = r_exp(-x);
    }

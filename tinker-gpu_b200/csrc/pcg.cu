@@ -66,10 +66,11 @@ __global__ void __launch_bounds__(256) k_pcg_update(int n, const int* __restrict
       return;
    int s = blockIdx.x * blockDim.x + threadIdx.x;
    double e1 = 0, e2 = 0;
+   double q4[4];
+   pcg_q_block<4>(slot, 0, q4);
    if (s < n) {
-      double pa = pcg_q(slot, 2), pb = pcg_q(slot, 3);
-      real a = pa != 0.0 ? (real)(pcg_q(slot, 0) / pa) : (real)0;
-      real ap = pb != 0.0 ? (real)(pcg_q(slot, 1) / pb) : (real)0;
+      real a = q4[2] != 0.0 ? (real)(q4[0] / q4[2]) : (real)0;
+      real ap = q4[3] != 0.0 ? (real)(q4[1] / q4[3]) : (real)0;
       V3 pd, pp, vd, vp, rd, rp;
       load_dp(P, s, pd, pp);
       load_dp(V, s, vd, vp);

@@ -64,9 +64,17 @@ struct Stencil {
    int i1, i2, i3;   // first grid index along each axis
 };
 
-// lanes 0..2 fill sth[warp][dim][5][4]; every lane returns the stencil origin
-__device__ __forceinline__ Stencil make_stencil(const Box& b, real4 pos, int n1, int n2, int n3, real (*sth)[5][4], int lane)
+// Per-atom spline table, filled once per step (the positions do not change inside the CG loop):
+// 16 real4 per atom -- [5*d + p] = {theta and its first three derivatives} of stencil point p along
+// axis d (15 entries), [15] = the three stencil origins as integer bit patterns (bsplineFill of the
+// reference, src/cu/pme.cu, keeps the same information as thetai1..3 + igrid).
+__global__ void k_theta_fill(int n, Box b, int n1, int n2, int n3, const real4* __restrict__ posd, real4* __restrict__ theta)
 {
+   int t = blockIdx.x * blockDim.x + threadIdx.x;
+   int s = t >> 2, d = t & 3;
+   if (s >= n)
+      return;
+   real4 pos = posd[s];
    real f[3];
    f[0] = pos.x * b.r[0] + pos.y * b.r[1] + pos.z * b.r[2];
    f[1] = pos.x * b.r[3] + pos.y * b.r[4] + pos.z * b.r[5];
@@ -75,38 +83,71 @@ __device__ __forceinline__ Stencil make_stencil(const Box& b, real4 pos, int n1,
    int ig[3];
    real ww[3];
    #pragma unroll
-   for (int d = 0; d < 3; ++d) {
-      real w = f[d] + (real)0.5;
+   for (int q = 0; q < 3; ++q) {
+      real w = f[q] + (real)0.5;
       w -= floor(w);
-      real fr = nf[d] * w;
+      real fr = nf[q] * w;
       int ii = (int)floor(fr);
-      if (ii >= nf[d]) ii = nf[d] - 1;      // w == 1-ulp rounding guard
-      ww[d] = fr - ii;
+      if (ii >= nf[q]) ii = nf[q] - 1;      // w == 1-ulp rounding guard
+      ww[q] = fr - ii;
       ii -= 4;
-      ig[d] = ii < 0 ? ii + nf[d] : ii;
+      ig[q] = ii < 0 ? ii + nf[q] : ii;
    }
-   if (lane < 3) {
-      real w = lane == 0 ? ww[0] : (lane == 1 ? ww[1] : ww[2]);
-      bspline5(w, sth[lane]);
+   if (d < 3) {
+      real th[5][4];
+      bspline5(d == 0 ? ww[0] : (d == 1 ? ww[1] : ww[2]), th);
+      #pragma unroll
+      for (int p = 0; p < 5; ++p) {
+         real4 o;
+         o.x = th[p][0], o.y = th[p][1], o.z = th[p][2], o.w = th[p][3];
+         theta[16 * (size_t)s + 5 * d + p] = o;
+      }
+   } else {
+      real4 o;
+#ifdef APX_DOUBLE
+      o.x = __longlong_as_double((long long)ig[0]), o.y = __longlong_as_double((long long)ig[1]);
+      o.z = __longlong_as_double((long long)ig[2]);
+#else
+      o.x = __int_as_float(ig[0]), o.y = __int_as_float(ig[1]), o.z = __int_as_float(ig[2]);
+#endif
+      o.w = 0;
+      theta[16 * (size_t)s + 15] = o;
    }
+}
+
+// lanes 0..14 copy the table of atom s into sth[dim][5][4]; every lane returns the stencil origin
+__device__ __forceinline__ Stencil load_stencil(const real4* __restrict__ theta, int s, real (*sth)[5][4], int lane)
+{
+   real4 v = theta[16 * (size_t)s + (lane & 15)];
+   if (lane < 15)
+      *reinterpret_cast<real4*>(&sth[0][0][0] + 4 * lane) = v;
+   Stencil st;
+#ifdef APX_DOUBLE
+   st.i1 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, v.x, 15));
+   st.i2 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, v.y, 15));
+   st.i3 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, v.z, 15));
+#else
+   st.i1 = __float_as_int(__shfl_sync(0xffffffffu, v.x, 15));
+   st.i2 = __float_as_int(__shfl_sync(0xffffffffu, v.y, 15));
+   st.i3 = __float_as_int(__shfl_sync(0xffffffffu, v.z, 15));
+#endif
    __syncwarp();
-   Stencil s = {ig[0], ig[1], ig[2]};
-   return s;
+   return st;
 }
 
 __device__ __forceinline__ int wrapi(int i, int n) { return i >= n ? i - n : i; }
 
 // --- spread ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_spread_mpole(int n, Box box, Xform X, int n1, int n2, int n3,
-   const real4* __restrict__ posd, const real4* __restrict__ mp0, const real4* __restrict__ mp1, const real2* __restrict__ mp2,
+__global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, int n2, int n3,
+   const real4* __restrict__ theta, const real4* __restrict__ mp0, const real4* __restrict__ mp1, const real2* __restrict__ mp2,
    real* __restrict__ fmp_out, cplx* __restrict__ grid)
 {
-   __shared__ real sth[4][3][5][4];
+   __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
    if (s >= n)
       return;
-   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   Stencil st = load_stencil(theta, s, sth[wib], lane);
    real4 m0 = mp0[s], m1 = mp1[s];
    real2 m2 = mp2[s];
    // Cartesian multipole with the off-diagonal quadrupoles doubled (rpoleToCmp), then -> fractional
@@ -134,15 +175,14 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Box box, Xform X, i
       fmp_out[10 * s + lane] = val;
    }
    for (int p = lane; p < 125; p += 32) {
-      int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+      const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
       const real* t = sth[wib][0][ix];
       const real* u = sth[wib][1][iy];
       const real* v = sth[wib][2][iz];
-      real t0 = t[0], t1 = t[1], t2 = t[2], u0 = u[0], u1 = u[1], u2 = u[2], v0 = v[0], v1 = v[1], v2 = v[2];
-      real val = fm[0] * t0 * u0 * v0 + fm[1] * t1 * u0 * v0 + fm[2] * t0 * u1 * v0 + fm[3] * t0 * u0 * v1 + fm[4] * t2 * u0 * v0
+      const real t0 = t[0], t1 = t[1], t2 = t[2], u0 = u[0], u1 = u[1], u2 = u[2], v0 = v[0], v1 = v[1], v2 = v[2];
+      const real val = fm[0] * t0 * u0 * v0 + fm[1] * t1 * u0 * v0 + fm[2] * t0 * u1 * v0 + fm[3] * t0 * u0 * v1 + fm[4] * t2 * u0 * v0
          + fm[5] * t0 * u2 * v0 + fm[6] * t0 * u0 * v2 + fm[7] * t1 * u1 * v0 + fm[8] * t1 * u0 * v1 + fm[9] * t0 * u1 * v1;
-      int idx = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1);
-      atomicAdd(&grid[idx].x, val);
+      atomicAdd(&grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)].x, val);
    }
 }
 
@@ -156,34 +196,36 @@ __device__ __forceinline__ void spread_dipoles(const Xform& X, const Stencil& st
       fd[f] = X.a[0][f] * d.x + X.a[1][f] * d.y + X.a[2][f] * d.z;
       fp[f] = X.a[0][f] * q.x + X.a[1][f] * q.y + X.a[2][f] * q.z;
    }
+   // 125 points over 32 lanes, x fastest: neighbouring lanes hit neighbouring addresses, so one warp
+   // atomic touches ~13 32-byte sectors (a lane-per-row layout touches 25 and was measured 1.5x slower)
    for (int p = lane; p < 125; p += 32) {
-      int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+      const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
       const real* t = sth[0][ix];
       const real* u = sth[1][iy];
       const real* v = sth[2][iz];
-      real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
-      real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
-      real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
-      int idx = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1);
+      const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
+      const real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
+      const real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
+      cplx* g = &grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
 #ifdef APX_DOUBLE
-      atomicAdd(&grid[idx].x, vd);
-      atomicAdd(&grid[idx].y, vp);
+      atomicAdd(&g->x, vd);
+      atomicAdd(&g->y, vp);
 #else
-      atomicAdd(reinterpret_cast<float2*>(&grid[idx]), make_float2(vd, vp));
+      atomicAdd(reinterpret_cast<float2*>(g), make_float2(vd, vp));
 #endif
    }
 }
 
 // spread of a packed (d,p) dipole pair array (dp.cuh)
-__global__ void __launch_bounds__(128) k_spread_dp(int n, Box box, Xform X, int n1, int n2, int n3, const real4* __restrict__ posd,
+__global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, const real4* __restrict__ theta,
    const real4* __restrict__ U, cplx* __restrict__ grid)
 {
-   __shared__ real sth[4][3][5][4];
+   __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
    if (s >= n)
       return;
-   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   Stencil st = load_stencil(theta, s, sth[wib], lane);
    V3 d, q;
    load_dp(U, s, d, q);
    spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, d, q, grid);
@@ -192,23 +234,26 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Box box, Xform X, int 
 // First kernel of a PCG iteration: direction update p = z + b p (pcgP3, src/cu/induce.cu:172-190;
 // b = r.z(new) / r.z(old) re-derived by every warp from the sub-slotted sums, b = 0 and p = 0 on
 // the first iteration) written back packed and spread onto the PME grid in the same pass.
-__global__ void __launch_bounds__(128) k_pcg_dir_spread(int n, Box box, Xform X, int n1, int n2, int n3, int do_spread,
-   const real4* __restrict__ posd, real4* __restrict__ P, const real4* __restrict__ Z, const double* __restrict__ slot_prev,
+__global__ void __launch_bounds__(128) k_pcg_dir_spread(int n, Xform X, int n1, int n2, int n3, int do_spread,
+   const real4* __restrict__ theta, real4* __restrict__ P, const real4* __restrict__ Z, const double* __restrict__ slot_prev,
    const double* __restrict__ slot_cur, const int* __restrict__ flags, cplx* __restrict__ grid)
 {
    if (flags[1])
       return;
-   __shared__ real sth[4][3][5][4];
+   __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    const int s = blockIdx.x * 4 + wib;
-   if (s >= n)
-      return;
    real b = 0, bp = 0;
    if (slot_prev) {
-      double s0 = pcg_q(slot_prev, 0), s1 = pcg_q(slot_prev, 1);
-      b = s0 != 0.0 ? (real)(pcg_q(slot_cur, 0) / s0) : (real)0;
-      bp = s1 != 0.0 ? (real)(pcg_q(slot_cur, 1) / s1) : (real)0;
+      double o[2], c2[2];
+      pcg_q_block<2>(slot_prev, 0, o);
+      __syncthreads();
+      pcg_q_block<2>(slot_cur, 0, c2);
+      b = o[0] != 0.0 ? (real)(c2[0] / o[0]) : (real)0;
+      bp = o[1] != 0.0 ? (real)(c2[1] / o[1]) : (real)0;
    }
+   if (s >= n)
+      return;
    V3 zd, zp, pd, pp;
    load_dp(Z, s, zd, zp);
    load_dp(P, s, pd, pp);
@@ -218,7 +263,7 @@ __global__ void __launch_bounds__(128) k_pcg_dir_spread(int n, Box box, Xform X,
    if (lane == 0)
       store_dp(P, s, pd, pp);
    if (do_spread) {
-      Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+      Stencil st = load_stencil(theta, s, sth[wib], lane);
       spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, pd, pp, grid);
    }
 }
@@ -370,19 +415,19 @@ __global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real
 // (the ufield gather with its fused epilogues is k_gather_dp below)
 // MODE 2: energy step: fphid[10], fphip[10], fphidp[20] stored
 template <int MODE>
-__global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
-   const real4* __restrict__ posd, const cplx* __restrict__ grid, const real4* __restrict__ mp0, const real* __restrict__ ud,
+__global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, int n3, real selfterm,
+   const real4* __restrict__ theta, const cplx* __restrict__ grid, const real4* __restrict__ mp0, const real* __restrict__ ud,
    const real* __restrict__ up, real* __restrict__ out_a, real* __restrict__ out_b, real* __restrict__ out_c,
    const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
-   __shared__ real sth[4][3][5][4];
+   __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
    if (s >= n)
       return;
-   Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
+   Stencil st = load_stencil(theta, s, sth[wib], lane);
    // row sums over x for derivative orders 0..3, real and imaginary parts
    real tr[4] = {0, 0, 0, 0}, ti[4] = {0, 0, 0, 0};
    real u[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
@@ -513,36 +558,31 @@ __global__ void __launch_bounds__(128) k_gather(int n, Box box, Xform X, int n1,
 //   EPI 1: residual      R = field, zero where alpha == 0            (r0 = -T u0)
 //   EPI 2: PCG           V = U/alpha - field ; partial U.V -> slot   (pcgP1 + dots, src/cu/induce.cu)
 template <int EPI>
-__global__ void __launch_bounds__(128) k_gather_dp(int n, Box box, Xform X, int n1, int n2, int n3, real selfterm,
-   const real4* __restrict__ posd, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
+__global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n2, int n3, real selfterm,
+   const real4* __restrict__ theta, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
    const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
    double* __restrict__ slot, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
-   __shared__ real sth[4][3][5][4];
+   __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    const int s = blockIdx.x * 4 + wib;
    double dot_d = 0, dot_p = 0;
    if (s < n) {
-      Stencil st = make_stencil(box, posd[s], n1, n2, n3, sth[wib], lane);
-      real tr0 = 0, tr1 = 0, ti0 = 0, ti1 = 0;
-      real u0 = 0, u1 = 0, v0 = 0, v1 = 0;
-      if (lane < 25) {
-         int iy = lane % 5, iz = lane / 5;
-         int base = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1;
-         #pragma unroll
-         for (int ix = 0; ix < 5; ++ix) {
-            cplx g = grid[base + wrapi(st.i1 + ix, n1)];
-            const real* t = sth[wib][0][ix];
-            tr0 += g.x * t[0], tr1 += g.x * t[1];
-            ti0 += g.y * t[0], ti1 += g.y * t[1];
-         }
-         u0 = sth[wib][1][iy][0], u1 = sth[wib][1][iy][1];
-         v0 = sth[wib][2][iz][0], v1 = sth[wib][2][iz][1];
+      Stencil st = load_stencil(theta, s, sth[wib], lane);
+      // 125 points over 32 lanes, x fastest (coalesced 40-byte runs)
+      real fd[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
+      for (int p = lane; p < 125; p += 32) {
+         const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+         const cplx g = grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
+         const real* t = sth[wib][0][ix];
+         const real* u = sth[wib][1][iy];
+         const real* v = sth[wib][2][iz];
+         const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
+         fd[0] += g.x * w100, fd[1] += g.x * w010, fd[2] += g.x * w001;
+         fp[0] += g.y * w100, fp[1] += g.y * w010, fp[2] += g.y * w001;
       }
-      real fd[3] = {tr1 * u0 * v0, tr0 * u1 * v0, tr0 * u0 * v1};
-      real fp[3] = {ti1 * u0 * v0, ti0 * u1 * v0, ti0 * u0 * v1};
       #pragma unroll
       for (int q = 0; q < 3; ++q) {
          #pragma unroll
@@ -731,6 +771,7 @@ void apx_pme_setup(apx_ctx* c)
       CUFFT_CHECK(cufftSetStream(c->plan, c->stream));
       c->plan_ok = 1;
    }
+   apx_fft64_setup(c);
    int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
    DevBuf<real>* bs[3] = {&c->bsmod1, &c->bsmod2, &c->bsmod3};
    for (int d = 0; d < 3; ++d) {
@@ -744,6 +785,17 @@ void apx_pme_setup(apx_ctx* c)
    double volterm = M_PI * (double)c->box.volume;
    k_make_qfac<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, (real)volterm,
       c->bsmod1, c->bsmod2, c->bsmod3, c->qfac);
+   APX_COUNT_LAUNCH(c);
+}
+
+// spline tables of the current positions; called whenever posd changes (nblist.cu)
+void apx_pme_fill_theta(apx_ctx* c)
+{
+   if (!c->opt.use_ewald)
+      return;
+   int n = c->n;
+   c->theta.ensure(16 * (size_t)c->npad);
+   k_theta_fill<<<(4 * n + 127) / 128, 128, 0, c->stream>>>(n, c->box, c->nfft1, c->nfft2, c->nfft3, c->posd, c->theta);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -775,7 +827,7 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
    Xform X = make_xform(c);
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, c->mp0, c->mp1, c->mp2,
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->mp0, c->mp1, c->mp2,
       c->fmp, c->qgrid);
    APX_COUNT_LAUNCH(c);
    fft(c, CUFFT_FORWARD);
@@ -783,7 +835,7 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
       CUDA_CHECK(cudaMemsetAsync(c->dbuf.p + 16, 0, 7 * sizeof(double), c->stream));
    conv(c, want_ev, c->dbuf.p + 16);
    fft(c, CUFFT_INVERSE);
-   k_gather<0><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, c->mp0,
+   k_gather<0><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, c->mp0,
       nullptr, nullptr, c->fphi, c->field, nullptr, nullptr);
    APX_COUNT_LAUNCH(c);
    c->mpole_pme_valid = 1;
@@ -800,13 +852,17 @@ void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
    int n = c->n;
    Xform X = make_xform(c);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, U, c->qgrid);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid);
    APX_COUNT_LAUNCH(c);
 }
 
 // forward FFT, influence function, inverse FFT
 void apx_pme_convolve(apx_ctx* c)
 {
+   if (apx_fft64_usable(c)) {
+      apx_fft64_convolve(c);
+      return;
+   }
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
    fft(c, CUFFT_INVERSE);
@@ -819,7 +875,7 @@ void apx_pme_pcg_dir_spread(apx_ctx* c, int it)
    Xform X = make_xform(c);
    const double* prev = it >= 2 ? c->scal.p + (size_t)PCG_SLOT * (it - 2) : nullptr;
    const double* cur = c->scal.p + (size_t)PCG_SLOT * (it - 1);
-   k_pcg_dir_spread<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->opt.use_ewald ? 1 : 0, c->posd,
+   k_pcg_dir_spread<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->opt.use_ewald ? 1 : 0, c->theta,
       c->pk_p, c->pk_z, prev, cur, c->flags, c->qgrid);
    APX_COUNT_LAUNCH(c);
 }
@@ -831,7 +887,7 @@ void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real
    Xform X = make_xform(c);
    int g = (n + 3) / 4;
 #define GATHER_DP(E)                                                                                                       \
-   k_gather_dp<E><<<g, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->tpj, c->qgrid, U, F,  \
+   k_gather_dp<E><<<g, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->tpj, c->qgrid, U, F,  \
       fd, fp, OUT, slot, c->skip)
    if (epi == 0) GATHER_DP(0);
    else if (epi == 1) GATHER_DP(1);
@@ -848,12 +904,10 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
    apx_pack_dp(c, ud, up, c->pk_p);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, c->pk_p, c->qgrid);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid);
    APX_COUNT_LAUNCH(c);
-   fft(c, CUFFT_FORWARD);
-   conv(c, false, nullptr);
-   fft(c, CUFFT_INVERSE);
-   k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->posd, c->qgrid, nullptr,
+   apx_pme_convolve(c);
+   k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, nullptr,
       ud, up, c->fphid, c->fphip, c->fphidp, nullptr);
    APX_COUNT_LAUNCH(c);
 }
@@ -867,12 +921,12 @@ void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6)
    size_t K = ntot(c);
    c->qgrid2.ensure(K);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, mpa, c->mp1, c->mp2, nullptr,
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, mpa, c->mp1, c->mp2, nullptr,
       c->qgrid);
    fft(c, CUFFT_FORWARD);
    CUDA_CHECK(cudaMemcpyAsync(c->qgrid2.p, c->qgrid.p, K * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, c->box, X, c->nfft1, c->nfft2, c->nfft3, c->posd, mpb, c->mp1, c->mp2, nullptr,
+   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, mpb, c->mp1, c->mp2, nullptr,
       c->qgrid);
    fft(c, CUFFT_FORWARD);
    double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
