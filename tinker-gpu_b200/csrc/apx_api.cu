@@ -175,6 +175,8 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    c->f_elec = (real)(sys->electric / sys->dielec);
    if (const char* e = getenv("APX_NO_NATIVE_FFT"))
       c->native_fft = atoi(e) ? 0 : 1;
+   if (const char* e = getenv("APX_NO_GRAPH"))
+      c->use_graph = atoi(e) ? 0 : 1;
    set_box(c, sys->lvec);
    if (sys->cutoff > 0.5 * std::min(std::min(sys->lvec[0], sys->lvec[4]), sys->lvec[8]) + 1e-9 && sys->cutoff < 1e6)
       APX_THROW("real-space cutoff exceeds half the box edge (minimum image would fail)");
@@ -232,8 +234,6 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    c->mpx_b.ensure(np);
    c->blk_ctr.ensure(c->nblk);
    c->blk_ext.ensure(c->nblk);
-   c->flags.ensure(8);
-   CUDA_CHECK(cudaMemset(c->flags.p, 0, 8 * sizeof(int)));
    DevBuf<real>* vecs[] = {&c->field, &c->fieldp, &c->udir, &c->udirp, &c->uind, &c->uinp, &c->rsd, &c->rsdp, &c->zrsd, &c->zrsdp,
       &c->conj, &c->conjp, &c->vec, &c->vecp, &c->trq};
    for (auto* v : vecs) {
@@ -250,13 +250,35 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    c->fphid.ensure(10 * np);
    c->fphip.ensure(10 * np);
    c->fphidp.ensure(20 * np);
-   c->gx.ensure(np);
-   c->gy.ensure(np);
-   c->gz.ensure(np);
-   c->trqf.ensure(3 * np);
-   c->ebuf.ensure(8);
-   c->dbuf.ensure(64);
-   c->cnt.ensure(4);
+   {
+      // arenas (apx_internal.h): typed views into two allocations; cap = 0 marks "not owned"
+      auto carve = [](char*& cur, size_t bytes) {
+         char* r = cur;
+         cur += (bytes + 255) / 256 * 256;
+         return r;
+      };
+      size_t pad = 256 * 8;
+      c->arena_e_bytes = sizeof(fixed_t) * (6 * np + 8) + sizeof(double) * 64 + sizeof(int) * 4 + pad;
+      c->arena_e.ensure(c->arena_e_bytes);
+      char* cur = c->arena_e.p;
+      c->gx.p = (fixed_t*)carve(cur, sizeof(fixed_t) * np);
+      c->gy.p = (fixed_t*)carve(cur, sizeof(fixed_t) * np);
+      c->gz.p = (fixed_t*)carve(cur, sizeof(fixed_t) * np);
+      c->trqf.p = (fixed_t*)carve(cur, sizeof(fixed_t) * 3 * np);
+      c->ebuf.p = (fixed_t*)carve(cur, sizeof(fixed_t) * 8);
+      c->dbuf.p = (double*)carve(cur, sizeof(double) * 64);
+      c->cnt.p = (int*)carve(cur, sizeof(int) * 4);
+      c->arena_e_bytes = (size_t)(cur - c->arena_e.p);
+      size_t nscal = (size_t)96 * (sys->politer + 3) + 8;     // PCG_SLOT doubles per iteration (dp.cuh)
+      c->arena_p_bytes = sizeof(double) * nscal + sizeof(int) * 8 + pad;
+      c->arena_p.ensure(c->arena_p_bytes);
+      cur = c->arena_p.p;
+      c->scal.p = (double*)carve(cur, sizeof(double) * nscal);
+      c->flags.p = (int*)carve(cur, sizeof(int) * 8);
+      c->arena_p_bytes = (size_t)(cur - c->arena_p.p);
+      CUDA_CHECK(cudaMemset(c->arena_e.p, 0, c->arena_e_bytes));
+      CUDA_CHECK(cudaMemset(c->arena_p.p, 0, c->arena_p_bytes));
+   }
    c->io_a.ensure(3 * np);
    c->io_b.ensure(3 * np);
    c->list_cutoff = (real)std::min(sys->cutoff, 1.0e6);
@@ -273,7 +295,12 @@ void apx_destroy(apx_ctx* c)
    cudaSetDevice(c->device);
    cudaStreamSynchronize(c->stream);
    cudaStreamSynchronize(c->stream2);
+   apx_pcg_graphs_invalidate(c);
    apx_pme_destroy(c);
+   // views into the arenas are not owned
+   c->gx.p = c->gy.p = c->gz.p = c->trqf.p = c->ebuf.p = nullptr;
+   c->dbuf.p = nullptr, c->cnt.p = nullptr, c->scal.p = nullptr, c->flags.p = nullptr;
+   c->arena_e.release(), c->arena_p.release();
    if (c->flags_h) cudaFreeHost(c->flags_h);
    if (c->scal_h) cudaFreeHost(c->scal_h);
    if (c->pin_a) cudaFreeHost(c->pin_a);
@@ -320,6 +347,7 @@ int apx_set_box(apx_ctx* c, const double lvec[9])
    API_BEGIN
    CUDA_CHECK(cudaSetDevice(c->device));
    set_box(c, lvec);
+   apx_pcg_graphs_invalidate(c);
    apx_pme_setup(c);
    c->mpole_inited = 0;
    apx_list_refresh(c, true);
@@ -533,6 +561,7 @@ int apx_set_native_fft(apx_ctx* c, int on)
 {
    API_BEGIN
    c->native_fft = on ? 1 : 0;
+   apx_pcg_graphs_invalidate(c);
    API_END
 }
 

@@ -188,6 +188,21 @@ struct apx_ctx {
    double* pin_a = nullptr;              // pinned staging for host<->device in e2e paths
    size_t pin_bytes = 0;
 
+   // ---- accumulator arenas: the buffers below live back to back so one memset clears them
+   //      energy(): gx gy gz trqf ebuf dbuf cnt ;  induce(): scal flags
+   DevBuf<char> arena_e, arena_p;
+   size_t arena_e_bytes = 0, arena_p_bytes = 0;
+
+   // ---- CUDA graphs of PCG iteration batches (pcg.cu), rebuilt when pointers / box / options change
+   struct PcgGraph {
+      int it0, nit;
+      cudaGraphExec_t exec;
+      int launches;
+   };
+   std::vector<PcgGraph> graphs;
+   int use_graph = 1;
+   int capturing = 0;
+
    // ---- stats
    apx_stats stats;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
@@ -217,7 +232,6 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev);                   // fills fmp, fp
 void apx_pme_zero_grid(apx_ctx* c);
 void apx_pme_spread_dp(apx_ctx* c, const real4* U);              // grid += spread of a packed dipole pair
 void apx_pme_convolve(apx_ctx* c);                               // FFT, influence function, inverse FFT
-void apx_pme_pcg_dir_spread(apx_ctx* c, int it);
 void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot);
 void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool full20);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
@@ -241,6 +255,7 @@ void apx_precond_dp(apx_ctx* c, const real4* R, real4* Z, double* slot, const Pc
 void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp);
 // ---- pcg.cu
 void apx_induce_impl(apx_ctx* c);
+void apx_pcg_graphs_invalidate(apx_ctx* c);
 void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);

@@ -122,7 +122,7 @@ template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
-   const real2* __restrict__ mp2, real* __restrict__ fd)
+   const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign)
 {
    ROWS_FOREACH_ATOM(G, n, i, l, act)
    {
@@ -153,8 +153,15 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int n, Box box, real
          fi += mpole_field(v3(dx, dy, dz), mk, B1, B2, B3, (real)-1);
       }
       fi = group_sum3<G>(fi);
-      if (l == 0 && act)
-         fd[3 * i] += fi.x, fd[3 * i + 1] += fi.y, fd[3 * i + 2] += fi.z;
+      if (l == 0 && act) {
+         // fd already holds the reciprocal + self field (Ewald) or is assigned here; the (p - d)
+         // delta array starts at zero for the exclusion pass that follows
+         if (assign)
+            fd[3 * i] = fi.x, fd[3 * i + 1] = fi.y, fd[3 * i + 2] = fi.z;
+         else
+            fd[3 * i] += fi.x, fd[3 * i + 1] += fi.y, fd[3 * i + 2] += fi.z;
+         fpd[3 * i] = 0, fpd[3 * i + 1] = 0, fpd[3 * i + 2] = 0;
+      }
    }
 }
 
@@ -367,7 +374,7 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       c->thlval, c->opt.njpolar, U, F, c->skip)
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
-   if (c->uf_used + 2 <= (int)c->uf_ev.size()) {
+   if (!c->capturing && c->uf_used + 2 <= (int)c->uf_ev.size()) {
       slot = c->uf_used;
       c->uf_used += 2;
       cudaEventRecord(c->uf_ev[slot], st);
@@ -400,14 +407,13 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    int grid = rows_grid<DF_G>(c);
 #define LAUNCH_DF(E, T)                                                                                                   \
    k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
-      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd)
-   if (L.nverlet > 0) {
-      if (ew && tb) LAUNCH_DF(true, true);
-      else if (ew) LAUNCH_DF(true, false);
-      else if (tb) LAUNCH_DF(false, true);
-      else LAUNCH_DF(false, false);
-      APX_COUNT_LAUNCH(c);
-   }
+      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, ew ? 0 : 1)
+   // (rows may all be empty for a tiny system: the kernel still initialises fd / fpd)
+   if (ew && tb) LAUNCH_DF(true, true);
+   else if (ew) LAUNCH_DF(true, false);
+   else if (tb) LAUNCH_DF(false, true);
+   else LAUNCH_DF(false, false);
+   APX_COUNT_LAUNCH(c);
 #undef LAUNCH_DF
    if (c->nexcl > 0) {
       int g = (c->nexcl + 127) / 128;

@@ -686,14 +686,9 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    cudaEventRecord(c->ev2, st);
    apx_rotpole(c);      // mpoleInit(vers) runs on every energy() call in the reference (src/amoeba/emplar.cpp:12)
    // ---- zero accumulators
-   CUDA_CHECK(cudaMemsetAsync(c->gx.p, 0, sizeof(fixed_t) * c->npad, st));
-   CUDA_CHECK(cudaMemsetAsync(c->gy.p, 0, sizeof(fixed_t) * c->npad, st));
-   CUDA_CHECK(cudaMemsetAsync(c->gz.p, 0, sizeof(fixed_t) * c->npad, st));
-   CUDA_CHECK(cudaMemsetAsync(c->trqf.p, 0, sizeof(fixed_t) * 3 * c->npad, st));
-   CUDA_CHECK(cudaMemsetAsync(c->ebuf.p, 0, sizeof(fixed_t) * 8, st));
-   CUDA_CHECK(cudaMemsetAsync(c->cnt.p, 0, sizeof(int) * 4, st));
+   // gx gy gz trqf ebuf dbuf cnt are contiguous (arena_e, apx_api.cu): one memset
+   CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, st));
    // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
-   CUDA_CHECK(cudaMemsetAsync(c->dbuf.p, 0, sizeof(double) * D_TOTAL, st));
    int iters = 0;
    if (do_p) {
       apx_induce_impl(c);

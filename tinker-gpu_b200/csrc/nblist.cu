@@ -193,6 +193,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
       apx_rows_compact(c, false);
       return;
    }
+   apx_pcg_graphs_invalidate(c);      // row buffers may be reallocated below
    cudaEventRecord(c->ev2, c->stream);
    // 1. sort along the Morton curve
    k_sortkeys<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->box, c->xyz_d, c->sortkey, c->permtmp);

@@ -6,9 +6,10 @@
 // One iteration is a chain of 4 kernels of ours around the FFT instead of the reference's
 // ~14 kernels + 6 cuBLAS dots + a blocking host read:
 //
-//   K1  k_pcg_dir_spread   (pme.cu)   p = z + b p, spread p
-//       FFT, influence function, inverse FFT
-//   K2  k_ufield_rows      (field.cu) real-space field of p -- on a second stream, beside the FFT
+//   K1  k_pcg_dir                     p = z + b p
+//       k_spread_dp (pme.cu), FFT, influence function, inverse FFT (fft64.cu / cuFFT)
+//   K2  k_ufield_rows      (field.cu) real-space field of p -- on a second, lower-priority stream,
+//                                     beside the spread and the FFTs
 //   K3  k_gather_dp<2>     (pme.cu)   recip+self field, + real-space field, Ap = p/alpha - field, p.Ap
 //   K4  k_pcg_update                  u += a p ; r -= a Ap ; r.r ; PME grid zeroed for the next spread
 //   K5  k_precond_rows     (field.cu) eps test on r.r: peek + stop flag, or z = M r (diagonal + sparse rows), r.z
@@ -55,6 +56,35 @@ __global__ void k_udir(int n, const real4* __restrict__ tpj, const real* __restr
       }
       store_dp(P, s, ed, ep);
    }
+}
+
+// K1: direction update p = z + b p (pcgP3, src/cu/induce.cu:172-190); b = r.z(new) / r.z(old) from the
+// sub-slotted sums, b = 0 with p = 0 on the first iteration
+__global__ void __launch_bounds__(256) k_pcg_dir(int n, const int* __restrict__ flags, real4* __restrict__ P,
+   const real4* __restrict__ Z, const double* __restrict__ slot_prev, const double* __restrict__ slot_cur)
+{
+   if (flags[1])
+      return;
+   real b = 0, bp = 0;
+   if (slot_prev) {
+      double o[2], c2[2];
+      pcg_q_block<2>(slot_prev, 0, o);
+      __syncthreads();
+      pcg_q_block<2>(slot_cur, 0, c2);
+      b = o[0] != 0.0 ? (real)(c2[0] / o[0]) : (real)0;
+      bp = o[1] != 0.0 ? (real)(c2[1] / o[1]) : (real)0;
+   }
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   V3 zd, zp, pd, pp;
+   load_dp(Z, s, zd, zp);
+   if (slot_prev) {
+      load_dp(P, s, pd, pp);
+      zd += b * pd;
+      zp += bp * pp;
+   }
+   store_dp(P, s, zd, zp);
 }
 
 // K4: u += a p ; r -= a Ap (zero where alpha == 0) ; partial r.r ; zero the PME grid
@@ -156,14 +186,10 @@ void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p)
 // full dfield into c->field (d) and c->fieldp (p), then udir/udirp and the initial guess
 void apx_dfield_full(apx_ctx* c, bool want_ev)
 {
-   int n = c->n, n3 = 3 * c->n;
-   if (c->opt.use_ewald) {
+   int n = c->n;
+   if (c->opt.use_ewald)
       apx_pme_mpole(c, want_ev);                 // ASSIGNS c->field = recip + self
-   } else {
-      CUDA_CHECK(cudaMemsetAsync(c->field.p, 0, sizeof(real) * n3, c->stream));
-   }
-   CUDA_CHECK(cudaMemsetAsync(c->fieldp.p, 0, sizeof(real) * n3, c->stream));
-   apx_dfield_real(c, c->field, c->fieldp);
+   apx_dfield_real(c, c->field, c->fieldp);      // adds to (Ewald) or assigns (no Ewald) field; zeroes fieldp first
    k_udir<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->tpj, c->field, c->fieldp, c->udir, c->udirp, c->uind, c->uinp, c->pk_p,
       c->opt.pcgguess ? 1 : 0);
    APX_COUNT_LAUNCH(c);
@@ -225,11 +251,19 @@ __global__ void k_nonewald_ap(int n, const int* __restrict__ flags, const real4*
    pcg_block_add2(x, y, slot, 2, 3);
 }
 
+void apx_pcg_graphs_invalidate(apx_ctx* c)
+{
+   for (auto& g : c->graphs)
+      cudaGraphExecDestroy(g.exec);
+   c->graphs.clear();
+}
+
 void apx_induce_impl(apx_ctx* c)
 {
    const int n = c->n, n3 = 3 * n;
    const int g1 = (n + 255) / 256;
    cudaStream_t st = c->stream;
+   (void)n3;
    const bool ewald = c->opt.use_ewald != 0;
    if (!c->mpole_inited)
       apx_rotpole(c);
@@ -254,11 +288,8 @@ void apx_induce_impl(apx_ctx* c)
    }
    const int politer = c->opt.politer;
    const int miniter = std::min(3, n);
-   size_t nscal = (size_t)PCG_SLOT * (politer + 3) + 8;
-   c->scal.ensure(nscal);
-   CUDA_CHECK(cudaMemsetAsync(c->scal.p, 0, nscal * sizeof(double), st));
-   CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 4 * sizeof(int), st));
-   CUDA_CHECK(cudaMemsetAsync(c->pk_z.p, 0, sizeof(real4) * 2 * c->npad, st));
+   static_assert(PCG_SLOT == 96, "arena_p in apx_api.cu is sized for 96 doubles per iteration");
+   CUDA_CHECK(cudaMemsetAsync(c->arena_p.p, 0, c->arena_p_bytes, st));      // scal + flags
    double* result = c->scal.p + (size_t)PCG_SLOT * (politer + 3);
    const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nfft3 * sizeof(cplx) / sizeof(real4) : 0;
 
@@ -277,8 +308,7 @@ void apx_induce_impl(apx_ctx* c)
    } else {
       CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p, c->pk_p.p, sizeof(real4) * 2 * n, cudaMemcpyDeviceToDevice, st));
    }
-   // z0 = M r0, r0.z0 -> slot of iteration 1 ; p starts at zero so that K1 makes p = z0
-   CUDA_CHECK(cudaMemsetAsync(c->pk_p.p, 0, sizeof(real4) * 2 * c->npad, st));
+   // z0 = M r0, r0.z0 -> slot of iteration 1 (whose K1 sets p = z0)
    apx_precond_dp(c, c->pk_r, c->pk_z, c->scal.p);
    if (ewald)
       apx_pme_zero_grid(c);
@@ -291,24 +321,59 @@ void apx_induce_impl(apx_ctx* c)
    T.miniter = miniter, T.politer = politer;
    T.poleps = (real)c->opt.poleps, T.debye = (real)4.803206802, T.pcgpeek = (real)c->opt.pcgpeek;
    T.result = result, T.flags = c->flags, T.ud = c->uind, T.up = c->uinp;
-   while (!done) {
-      for (int b = 0; b < batch && iter < politer; ++b) {
-         ++iter;
-         double* slot = c->scal.p + (size_t)PCG_SLOT * (iter - 1);
-         apx_pme_pcg_dir_spread(c, iter);
-         field_of_dp(c, c->pk_p, false);
-         if (ewald)
-            apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot);
-         else {
-            k_nonewald_ap<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_f, c->pk_v, slot);
-            APX_COUNT_LAUNCH(c);
-         }
-         k_pcg_update<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_v, c->pk_r, c->uind, c->uinp, slot, (real4*)c->qgrid.p,
-            ngrid4);
+   auto enqueue_iteration = [&](int it) {
+      double* slot = c->scal.p + (size_t)PCG_SLOT * (it - 1);
+      k_pcg_dir<<<g1, 256, 0, st>>>(n, c->flags, c->pk_p, c->pk_z, it >= 2 ? slot - PCG_SLOT : nullptr, slot);
+      APX_COUNT_LAUNCH(c);
+      field_of_dp(c, c->pk_p, true);
+      if (ewald)
+         apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot);
+      else {
+         k_nonewald_ap<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_f, c->pk_v, slot);
          APX_COUNT_LAUNCH(c);
-         T.it = iter;
-         T.slot = slot;
-         apx_precond_dp(c, c->pk_r, c->pk_z, slot + PCG_SLOT, &T);
+      }
+      k_pcg_update<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_v, c->pk_r, c->uind, c->uinp, slot, (real4*)c->qgrid.p,
+         ngrid4);
+      APX_COUNT_LAUNCH(c);
+      T.it = it;
+      T.slot = slot;
+      apx_precond_dp(c, c->pk_r, c->pk_z, slot + PCG_SLOT, &T);
+   };
+   while (!done) {
+      int nit = std::min(batch, politer - iter);
+      if (c->use_graph) {
+         // one CUDA graph per (first iteration, batch length): the fork/join with the second stream and
+         // every launch of the batch replay as a single submission
+         apx_ctx::PcgGraph* G = nullptr;
+         for (auto& g : c->graphs)
+            if (g.it0 == iter + 1 && g.nit == nit)
+               G = &g;
+         if (!G) {
+            int before = c->stats.kernel_launches;
+            c->capturing = 1;
+            CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            for (int b = 0; b < nit; ++b)
+               enqueue_iteration(iter + 1 + b);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            c->capturing = 0;
+            if (e != cudaSuccess)
+               APX_THROW(std::string("PCG graph capture failed: ") + cudaGetErrorString(e));
+            apx_ctx::PcgGraph ng;
+            ng.it0 = iter + 1, ng.nit = nit;
+            ng.launches = c->stats.kernel_launches - before;
+            c->stats.kernel_launches = before;
+            CUDA_CHECK(cudaGraphInstantiate(&ng.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            c->graphs.push_back(ng);
+            G = &c->graphs.back();
+         }
+         CUDA_CHECK(cudaGraphLaunch(G->exec, st));
+         c->stats.kernel_launches += G->launches;
+         iter += nit;
+      } else {
+         for (int b = 0; b < nit; ++b)
+            enqueue_iteration(++iter);
       }
       CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -218,8 +218,10 @@ __device__ __forceinline__ void spread_dipoles(const Xform& X, const Stencil& st
 
 // spread of a packed (d,p) dipole pair array (dp.cuh)
 __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, const real4* __restrict__ theta,
-   const real4* __restrict__ U, cplx* __restrict__ grid)
+   const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
 {
+   if (skip && skip[1])
+      return;
    __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
    int s = blockIdx.x * 4 + wib;
@@ -229,43 +231,6 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n
    V3 d, q;
    load_dp(U, s, d, q);
    spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, d, q, grid);
-}
-
-// First kernel of a PCG iteration: direction update p = z + b p (pcgP3, src/cu/induce.cu:172-190;
-// b = r.z(new) / r.z(old) re-derived by every warp from the sub-slotted sums, b = 0 and p = 0 on
-// the first iteration) written back packed and spread onto the PME grid in the same pass.
-__global__ void __launch_bounds__(128) k_pcg_dir_spread(int n, Xform X, int n1, int n2, int n3, int do_spread,
-   const real4* __restrict__ theta, real4* __restrict__ P, const real4* __restrict__ Z, const double* __restrict__ slot_prev,
-   const double* __restrict__ slot_cur, const int* __restrict__ flags, cplx* __restrict__ grid)
-{
-   if (flags[1])
-      return;
-   __shared__ __align__(16) real sth[4][3][5][4];
-   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-   const int s = blockIdx.x * 4 + wib;
-   real b = 0, bp = 0;
-   if (slot_prev) {
-      double o[2], c2[2];
-      pcg_q_block<2>(slot_prev, 0, o);
-      __syncthreads();
-      pcg_q_block<2>(slot_cur, 0, c2);
-      b = o[0] != 0.0 ? (real)(c2[0] / o[0]) : (real)0;
-      bp = o[1] != 0.0 ? (real)(c2[1] / o[1]) : (real)0;
-   }
-   if (s >= n)
-      return;
-   V3 zd, zp, pd, pp;
-   load_dp(Z, s, zd, zp);
-   load_dp(P, s, pd, pp);
-   pd = zd + b * pd;
-   pp = zp + bp * pp;
-   __syncwarp();
-   if (lane == 0)
-      store_dp(P, s, pd, pp);
-   if (do_spread) {
-      Stencil st = load_stencil(theta, s, sth[wib], lane);
-      spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, pd, pp, grid);
-   }
 }
 
 // --- influence function ------------------------------------------------------------------------
@@ -852,7 +817,7 @@ void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
    int n = c->n;
    Xform X = make_xform(c);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid, c->skip);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -866,18 +831,6 @@ void apx_pme_convolve(apx_ctx* c)
    fft(c, CUFFT_FORWARD);
    conv(c, false, nullptr);
    fft(c, CUFFT_INVERSE);
-}
-
-// PCG iteration head: direction update + spread (k_pcg_dir_spread); it = 1, 2, ...
-void apx_pme_pcg_dir_spread(apx_ctx* c, int it)
-{
-   int n = c->n;
-   Xform X = make_xform(c);
-   const double* prev = it >= 2 ? c->scal.p + (size_t)PCG_SLOT * (it - 2) : nullptr;
-   const double* cur = c->scal.p + (size_t)PCG_SLOT * (it - 1);
-   k_pcg_dir_spread<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->opt.use_ewald ? 1 : 0, c->theta,
-      c->pk_p, c->pk_z, prev, cur, c->flags, c->qgrid);
-   APX_COUNT_LAUNCH(c);
 }
 
 // epi 0: fd/fp plain out ; 1: OUT = residual ; 2: OUT = Ap with partial dots into slot
@@ -904,7 +857,7 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
    apx_pack_dp(c, ud, up, c->pk_p);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid);
+   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid, nullptr);
    APX_COUNT_LAUNCH(c);
    apx_pme_convolve(c);
    k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, nullptr,
