@@ -368,7 +368,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    real cut = (real)c->opt.cutoff;
    bool ew = c->opt.use_ewald != 0;
    bool tb = c->thole_table != 0;
-   int grid = rows_grid<UF_G>(c);
+   // 8 CTAs per SM: the rows run beside the PME spread/FFT chain of the other stream and must leave
+   // room for its CTAs (a grid that fills every SM first delays the spread by the length of a wave)
+   int grid = rows_grid<UF_G>(c, 8);
 #define LAUNCH_UF(E, T)                                                                                                   \
    k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
       c->thlval, c->opt.njpolar, U, F, c->skip)

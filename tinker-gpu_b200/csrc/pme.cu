@@ -186,23 +186,71 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, in
    }
 }
 
-// dipole pair (d -> real, p -> imaginary) of one atom onto its 125 stencil points
-__device__ __forceinline__ void spread_dipoles(const Xform& X, const Stencil& st, const real (*sth)[5][4], int lane, int n1, int n2,
-   int n3, V3 d, V3 q, cplx* __restrict__ grid)
+// ---- lane-group kernels for the induced-dipole grids: LG lanes share one atom, 128/LG atoms per
+// CTA.  A whole warp per atom (as the multipole kernels above use) spends most of its issue slots on
+// index arithmetic and the 5-step shuffle reductions; with 8 lanes per atom each lane keeps 16
+// stencil points in flight and a reduction is 3 steps.
+#define PME_LG 8
+#define PME_APB (128 / PME_LG)      // atoms per CTA
+
+// the LG lanes of a group copy their atom's 15 spline records into sth and return the stencil origin
+template <int LG>
+__device__ __forceinline__ Stencil load_stencil_lg(const real4* __restrict__ theta, int s, real (*sth)[5][4], int l)
 {
+   real4 org;
+   #pragma unroll
+   for (int q = l; q < 16; q += LG) {
+      real4 v = theta[16 * (size_t)s + q];
+      if (q < 15)
+         *reinterpret_cast<real4*>(&sth[0][0][0] + 4 * q) = v;
+      else
+         org = v;
+   }
+   // record 15 is read by lane (15 % LG) of the group
+   const int src = (threadIdx.x & 31 & ~(LG - 1)) + (15 % LG);
+   Stencil st;
+#ifdef APX_DOUBLE
+   st.i1 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, org.x, src));
+   st.i2 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, org.y, src));
+   st.i3 = (int)__double_as_longlong(__shfl_sync(0xffffffffu, org.z, src));
+#else
+   st.i1 = __float_as_int(__shfl_sync(0xffffffffu, org.x, src));
+   st.i2 = __float_as_int(__shfl_sync(0xffffffffu, org.y, src));
+   st.i3 = __float_as_int(__shfl_sync(0xffffffffu, org.z, src));
+#endif
+   __syncwarp();
+   return st;
+}
+
+// spread of a packed (d,p) dipole pair array (dp.cuh): d -> real part, p -> imaginary part
+template <int LG>
+__global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, const real4* __restrict__ theta,
+   const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
+{
+   if (skip && skip[1])
+      return;
+   __shared__ __align__(16) real sth[128 / LG][3][5][4];
+   const int l = threadIdx.x & (LG - 1), gib = threadIdx.x / LG;
+   const int s_ = blockIdx.x * (128 / LG) + gib;
+   const bool act = s_ < n;
+   const int s = act ? s_ : n - 1;
+   Stencil st = load_stencil_lg<LG>(theta, s, sth[gib], l);
+   if (!act)
+      return;
+   V3 d, q;
+   load_dp(U, s, d, q);
    real fd[3], fp[3];
    #pragma unroll
    for (int f = 0; f < 3; ++f) {
       fd[f] = X.a[0][f] * d.x + X.a[1][f] * d.y + X.a[2][f] * d.z;
       fp[f] = X.a[0][f] * q.x + X.a[1][f] * q.y + X.a[2][f] * q.z;
    }
-   // 125 points over 32 lanes, x fastest: neighbouring lanes hit neighbouring addresses, so one warp
-   // atomic touches ~13 32-byte sectors (a lane-per-row layout touches 25 and was measured 1.5x slower)
-   for (int p = lane; p < 125; p += 32) {
+   // x fastest across the lanes: neighbouring lanes hit neighbouring addresses
+   for (int p = l; p < 125; p += LG) {
       const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
-      const real* t = sth[0][ix];
-      const real* u = sth[1][iy];
-      const real* v = sth[2][iz];
+      const real* t = sth[gib][0][ix];
+      const real* u = sth[gib][1][iy];
+      const real* v = sth[gib][2][iz];
       const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
       const real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
       const real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
@@ -214,23 +262,6 @@ __device__ __forceinline__ void spread_dipoles(const Xform& X, const Stencil& st
       atomicAdd(reinterpret_cast<float2*>(g), make_float2(vd, vp));
 #endif
    }
-}
-
-// spread of a packed (d,p) dipole pair array (dp.cuh)
-__global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, const real4* __restrict__ theta,
-   const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
-{
-   if (skip && skip[1])
-      return;
-   __shared__ __align__(16) real sth[4][3][5][4];
-   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-   int s = blockIdx.x * 4 + wib;
-   if (s >= n)
-      return;
-   Stencil st = load_stencil(theta, s, sth[wib], lane);
-   V3 d, q;
-   load_dp(U, s, d, q);
-   spread_dipoles(X, st, sth[wib], lane, n1, n2, n3, d, q, grid);
 }
 
 // --- influence function ------------------------------------------------------------------------
@@ -522,7 +553,7 @@ __global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, 
 //   EPI 0: plain output  fd, fp [n][3]                               (ufield operator)
 //   EPI 1: residual      R = field, zero where alpha == 0            (r0 = -T u0)
 //   EPI 2: PCG           V = U/alpha - field ; partial U.V -> slot   (pcgP1 + dots, src/cu/induce.cu)
-template <int EPI>
+template <int EPI, int LG>
 __global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n2, int n3, real selfterm,
    const real4* __restrict__ theta, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
    const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
@@ -530,62 +561,61 @@ __global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n
 {
    if (skip && skip[1])
       return;
-   __shared__ __align__(16) real sth[4][3][5][4];
-   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-   const int s = blockIdx.x * 4 + wib;
+   __shared__ __align__(16) real sth[128 / LG][3][5][4];
+   const int l = threadIdx.x & (LG - 1), gib = threadIdx.x / LG;
+   const int s_ = blockIdx.x * (128 / LG) + gib;
+   const bool act = s_ < n;
+   const int s = act ? s_ : n - 1;
    double dot_d = 0, dot_p = 0;
-   if (s < n) {
-      Stencil st = load_stencil(theta, s, sth[wib], lane);
-      // 125 points over 32 lanes, x fastest (coalesced 40-byte runs)
-      real fd[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
-      for (int p = lane; p < 125; p += 32) {
-         const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
-         const cplx g = grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
-         const real* t = sth[wib][0][ix];
-         const real* u = sth[wib][1][iy];
-         const real* v = sth[wib][2][iz];
-         const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
-         fd[0] += g.x * w100, fd[1] += g.x * w010, fd[2] += g.x * w001;
-         fp[0] += g.y * w100, fp[1] += g.y * w010, fp[2] += g.y * w001;
-      }
+   Stencil st = load_stencil_lg<LG>(theta, s, sth[gib], l);
+   real fd[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
+   for (int p = l; p < 125; p += LG) {
+      const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
+      const cplx g = grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
+      const real* t = sth[gib][0][ix];
+      const real* u = sth[gib][1][iy];
+      const real* v = sth[gib][2][iz];
+      const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
+      fd[0] += g.x * w100, fd[1] += g.x * w010, fd[2] += g.x * w001;
+      fp[0] += g.y * w100, fp[1] += g.y * w010, fp[2] += g.y * w001;
+   }
+   #pragma unroll
+   for (int q = 0; q < 3; ++q) {
       #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-         #pragma unroll
-         for (int o = 16; o > 0; o >>= 1) {
-            fd[q] += __shfl_xor_sync(0xffffffffu, fd[q], o);
-            fp[q] += __shfl_xor_sync(0xffffffffu, fp[q], o);
-         }
+      for (int o = LG / 2; o > 0; o >>= 1) {
+         fd[q] += __shfl_xor_sync(0xffffffffu, fd[q], o);
+         fp[q] += __shfl_xor_sync(0xffffffffu, fp[q], o);
       }
-      if (lane == 0) {
-         V3 ud, up;
-         load_dp(U, s, ud, up);
-         V3 cd = v3(X.a[0][0] * fd[0] + X.a[0][1] * fd[1] + X.a[0][2] * fd[2], X.a[1][0] * fd[0] + X.a[1][1] * fd[1] + X.a[1][2] * fd[2],
-            X.a[2][0] * fd[0] + X.a[2][1] * fd[1] + X.a[2][2] * fd[2]);
-         V3 cp = v3(X.a[0][0] * fp[0] + X.a[0][1] * fp[1] + X.a[0][2] * fp[2], X.a[1][0] * fp[0] + X.a[1][1] * fp[1] + X.a[1][2] * fp[2],
-            X.a[2][0] * fp[0] + X.a[2][1] * fp[1] + X.a[2][2] * fp[2]);
-         V3 ed = selfterm * ud - cd, ep = selfterm * up - cp;
-         if (F) {
-            V3 a, b;
-            load_dp(F, s, a, b);
-            ed += a;
-            ep += b;
+   }
+   if (l == 0 && act) {
+      V3 ud, up;
+      load_dp(U, s, ud, up);
+      V3 cd = v3(X.a[0][0] * fd[0] + X.a[0][1] * fd[1] + X.a[0][2] * fd[2], X.a[1][0] * fd[0] + X.a[1][1] * fd[1] + X.a[1][2] * fd[2],
+         X.a[2][0] * fd[0] + X.a[2][1] * fd[1] + X.a[2][2] * fd[2]);
+      V3 cp = v3(X.a[0][0] * fp[0] + X.a[0][1] * fp[1] + X.a[0][2] * fp[2], X.a[1][0] * fp[0] + X.a[1][1] * fp[1] + X.a[1][2] * fp[2],
+         X.a[2][0] * fp[0] + X.a[2][1] * fp[1] + X.a[2][2] * fp[2]);
+      V3 ed = selfterm * ud - cd, ep = selfterm * up - cp;
+      if (F) {
+         V3 a, b;
+         load_dp(F, s, a, b);
+         ed += a;
+         ep += b;
+      }
+      if (EPI == 0) {
+         out_d[3 * s] = ed.x, out_d[3 * s + 1] = ed.y, out_d[3 * s + 2] = ed.z;
+         out_p[3 * s] = ep.x, out_p[3 * s + 1] = ep.y, out_p[3 * s + 2] = ep.z;
+      } else if (EPI == 1) {
+         if (tpj[s].y == 0) {
+            ed = v3(0, 0, 0);
+            ep = v3(0, 0, 0);
          }
-         if (EPI == 0) {
-            out_d[3 * s] = ed.x, out_d[3 * s + 1] = ed.y, out_d[3 * s + 2] = ed.z;
-            out_p[3 * s] = ep.x, out_p[3 * s + 1] = ep.y, out_p[3 * s + 2] = ep.z;
-         } else if (EPI == 1) {
-            if (tpj[s].y == 0) {
-               ed = v3(0, 0, 0);
-               ep = v3(0, 0, 0);
-            }
-            store_dp(OUT, s, ed, ep);
-         } else {
-            real pinv = tpj[s].z;
-            V3 vd = pinv * ud - ed, vp = pinv * up - ep;
-            store_dp(OUT, s, vd, vp);
-            dot_d = (double)ud.x * vd.x + (double)ud.y * vd.y + (double)ud.z * vd.z;
-            dot_p = (double)up.x * vp.x + (double)up.y * vp.y + (double)up.z * vp.z;
-         }
+         store_dp(OUT, s, ed, ep);
+      } else {
+         real pinv = tpj[s].z;
+         V3 vd = pinv * ud - ed, vp = pinv * up - ep;
+         store_dp(OUT, s, vd, vp);
+         dot_d = (double)ud.x * vd.x + (double)ud.y * vd.y + (double)ud.z * vd.z;
+         dot_p = (double)up.x * vp.x + (double)up.y * vp.y + (double)up.z * vp.z;
       }
    }
    if (EPI == 2)
@@ -817,7 +847,7 @@ void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
    int n = c->n;
    Xform X = make_xform(c);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid, c->skip);
+   k_spread_dp<PME_LG><<<(n + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid, c->skip);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -838,9 +868,9 @@ void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real
 {
    int n = c->n;
    Xform X = make_xform(c);
-   int g = (n + 3) / 4;
+   int g = (n + PME_APB - 1) / PME_APB;
 #define GATHER_DP(E)                                                                                                       \
-   k_gather_dp<E><<<g, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->tpj, c->qgrid, U, F,  \
+   k_gather_dp<E, PME_LG><<<g, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->tpj, c->qgrid, U, F,  \
       fd, fp, OUT, slot, c->skip)
    if (epi == 0) GATHER_DP(0);
    else if (epi == 1) GATHER_DP(1);
@@ -857,7 +887,7 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    size_t K = ntot(c);
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
    apx_pack_dp(c, ud, up, c->pk_p);
-   k_spread_dp<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid, nullptr);
+   k_spread_dp<PME_LG><<<(n + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid, nullptr);
    APX_COUNT_LAUNCH(c);
    apx_pme_convolve(c);
    k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, nullptr,

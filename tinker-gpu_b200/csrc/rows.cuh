@@ -29,10 +29,10 @@ __device__ __forceinline__ V3 group_sum3(V3 v)
 }
 
 template <int G>
-inline int rows_grid(const apx_ctx* c)
+inline int rows_grid(const apx_ctx* c, int ctas_per_sm = 32)
 {
    int per = ROWS_BLOCK / G;
    int want = (c->n + per - 1) / per;
-   int cap = c->sm_count * 32;
+   int cap = c->sm_count * ctas_per_sm;
    return want < 1 ? 1 : (want < cap ? want : cap);
 }
