@@ -87,6 +87,20 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_ncu_traffic(kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same command (profiles/*_ncu_full.json; cold-cache replays)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for fn in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if fn.endswith("_ncu_full.json"):
+            d = json.load(open(os.path.join(pdir, fn)))
+            for k, v in d.items():
+                if k.startswith(kernel_prefix):
+                    best = (v["dram_bytes"], fn)
+    return best
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -263,6 +277,7 @@ def run_ours(args, rank, world, local_rank):
         uf_flops = 130.0 * npairs
         achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max
+        traffic = load_ncu_traffic("k_ufield_rows")
         fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         line = {
             "metric": METRIC, "value": ns_per_day(ms_step, world), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
@@ -281,7 +296,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "roofline": {"kernel": "k_ufield_rows (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
                          "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "ms_per_launch": uf_ms,
+                         "traffic": traffic[0] if traffic else None,
+                         "traffic_source": ("profiles/" + traffic[1] + " (ncu --set full, cold-cache replay)") if traffic else None,
+                         "algorithmic_bytes": uf_bytes, "peak_source": peak_src, "ms_per_launch": uf_ms,
                          "note": "latency/FP32-pipe bound at this size: see roofline_fp32"},
             "roofline_fp32": {"achieved": uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0, "peak": fp32_peak,
                               "unit": "TFLOP/s", "frac": (uf_flops / (uf_ms * 1e-3) / 1e12 / fp32_peak) if uf_ms > 0 else 0.0,
