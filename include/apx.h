@@ -98,6 +98,23 @@ int apx_precision_bytes(void);            /* sizeof(real): 4 mixed build, 8 doub
 int apx_create(const apx_system* sys, int device, apx_ctx** out);
 void apx_destroy(apx_ctx* ctx);
 
+/* ---- several GPUs of one node (no counterpart in the reference, which is single-GPU).
+ * Every rank (one per GPU) creates a context over the SAME system and positions; the library splits
+ * the box into z-slabs, exchanges halo dipoles and PME planes and reduces energies/forces, so every
+ * entry point below is then COLLECTIVE: all ranks call it, in the same order, and all receive the
+ * complete result.  transport "nccl": handle = the 128-byte id from apx_nccl_unique_id() of rank 0,
+ * nccl_lib = path of the libnccl.so.2 the process uses (NULL: default search).  transport "local":
+ * handle = apx_local_hub_create(world); the ranks are host threads of one process sharing a GPU. */
+int apx_create_dist(const apx_system* sys, int device, int rank, int world, const char* transport, const void* handle,
+   const char* nccl_lib, apx_ctx** out);
+int apx_nccl_unique_id(const char* nccl_lib, void* out128);
+void* apx_local_hub_create(int world);
+void apx_local_hub_destroy(void* hub);
+int apx_get_dist_info(apx_ctx* ctx, int* info8 /* rank, world, a0, a1, halo atoms, planes, halo planes lo, hi */);
+/* host-only: halo plan of `rank` from the sorted atoms' PME z-coordinates and the ranks' sorted ranges */
+int apx_dist_plan(int n, const float* w3_sorted, const int* bounds, int world, int rank, double range_frac, int* send_idx,
+   int* send_off, int* recv_idx, int* recv_off);
+
 /* copyPosToXyz + nblistRefresh: src/nblist.cpp:521-531, spatialCheck_cu (src/cu/spatial.cu:943-960) */
 int apx_set_positions(apx_ctx* ctx, const double* xyz);
 /* box change (Monte-Carlo barostat): src/box.cpp boxSetCurrent */

@@ -85,6 +85,15 @@ def load_library(precision="mixed"):
     lib.apx_stream.restype = C.c_void_p
     lib.apx_stream.argtypes = [C.c_void_p]
     lib.apx_create.argtypes = [C.POINTER(_ApxSystem), C.c_int, C.POINTER(C.c_void_p)]
+    lib.apx_create_dist.argtypes = [C.POINTER(_ApxSystem), C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_char_p,
+                                    C.POINTER(C.c_void_p)]
+    lib.apx_nccl_unique_id.argtypes = [C.c_char_p, C.c_void_p]
+    lib.apx_local_hub_create.argtypes = [C.c_int]
+    lib.apx_local_hub_create.restype = C.c_void_p
+    lib.apx_local_hub_destroy.argtypes = [C.c_void_p]
+    lib.apx_local_hub_destroy.restype = None
+    lib.apx_dist_plan.argtypes = [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_double,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.apx_destroy.argtypes = [C.c_void_p]
     lib.apx_destroy.restype = None
     for name, args in {
@@ -96,6 +105,7 @@ def load_library(precision="mixed"):
         "apx_pme_mpole_fphi": [_DP], "apx_pme_uind_fphi": [_DP, _DP, _DP, _DP],
         "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int],
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
+        "apx_get_dist_info": [C.POINTER(C.c_int)],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p] + args
@@ -108,10 +118,65 @@ def _dp(a):
     return a.ctypes.data_as(_DP)
 
 
-class Amoeba:
-    """One electrostatics context on one GPU (the reference's initialize()/finish() pair)."""
+def nccl_library_path():
+    """libnccl.so.2 bundled with torch (the one torch.distributed has already loaded), else the system one."""
+    try:
+        import nvidia.nccl as _n
+        p = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+        if os.path.isfile(p):
+            return p
+    except Exception:
+        pass
+    return "libnccl.so.2"
 
-    def __init__(self, system: System, precision: str = "mixed", device: int = 0):
+
+def nccl_unique_id(precision="mixed"):
+    """128-byte NCCL id made by rank 0; broadcast it to the other ranks and pass it as `handle`."""
+    lib = load_library(precision)
+    buf = C.create_string_buffer(128)
+    if lib.apx_nccl_unique_id(nccl_library_path().encode(), buf) != 0:
+        raise ApxError("ncclGetUniqueId failed")
+    return buf.raw
+
+
+class LocalHub:
+    """Rendezvous of the in-process transport: `world` ranks = host threads sharing one GPU."""
+
+    def __init__(self, world, precision="mixed"):
+        self.lib = load_library(precision)
+        self.world = world
+        self.handle = self.lib.apx_local_hub_create(world)
+        if not self.handle:
+            raise ApxError("apx_local_hub_create failed")
+
+    def close(self):
+        if self.handle:
+            self.lib.apx_local_hub_destroy(self.handle)
+            self.handle = None
+
+
+def dist_plan(w3_sorted, bounds, world, rank, range_frac, precision="mixed"):
+    """Host-only halo plan of `rank` (apx_dist_plan): returns (send_idx, send_off, recv_idx, recv_off)."""
+    lib = load_library(precision)
+    w = np.ascontiguousarray(w3_sorted, dtype=np.float32)
+    b = np.ascontiguousarray(bounds, dtype=np.int32)
+    n = w.shape[0]
+    si, ri = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    so, ro = np.zeros(world + 1, np.int32), np.zeros(world + 1, np.int32)
+    ip = C.POINTER(C.c_int)
+    lib.apx_dist_plan(n, w.ctypes.data_as(C.POINTER(C.c_float)), b.ctypes.data_as(ip), world, rank, float(range_frac),
+                      si.ctypes.data_as(ip), so.ctypes.data_as(ip), ri.ctypes.data_as(ip), ro.ctypes.data_as(ip))
+    return si[:so[-1]].copy(), so, ri[:ro[-1]].copy(), ro
+
+
+class Amoeba:
+    """One electrostatics context on one GPU (the reference's initialize()/finish() pair).
+
+    dist=(rank, world, transport, handle): this context is one rank of a spatially decomposed system on
+    `world` GPUs (transport "nccl": handle = nccl_unique_id() of rank 0; "local": handle = LocalHub).
+    Every method is then collective (all ranks call it in the same order)."""
+
+    def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None):
         self.lib = load_library(precision)
         self.system = system
         self.n = system.n
@@ -155,7 +220,18 @@ class Amoeba:
         s.pcgprec, s.pcgguess, s.pcgpeek = int(system.pcgprec), int(system.pcgguess), system.pcgpeek
         s.electric, s.dielec = system.electric, system.dielec
         self.ctx = C.c_void_p()
-        rc = self.lib.apx_create(C.byref(s), device, C.byref(self.ctx))
+        if dist is None:
+            rc = self.lib.apx_create(C.byref(s), device, C.byref(self.ctx))
+        else:
+            rank, world, transport, handle = dist
+            if transport == "local":
+                self._hub = handle
+                h = C.c_void_p(handle.handle)
+                rc = self.lib.apx_create_dist(C.byref(s), device, rank, world, b"local", h, None, C.byref(self.ctx))
+            else:
+                self._idbuf = C.create_string_buffer(bytes(handle), 128)
+                rc = self.lib.apx_create_dist(C.byref(s), device, rank, world, b"nccl", C.cast(self._idbuf, C.c_void_p),
+                                              nccl_library_path().encode(), C.byref(self.ctx))
         if rc != 0:
             msg = self.lib.apx_last_error().decode()
             if self.ctx:
@@ -285,6 +361,11 @@ class Amoeba:
         s = Stats()
         self._chk(self.lib.apx_get_stats(self.ctx, C.byref(s)))
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def dist_info(self):
+        a = (C.c_int * 8)()
+        self._chk(self.lib.apx_get_dist_info(self.ctx, a))
+        return dict(zip(("rank", "world", "a0", "a1", "halo_atoms", "planes", "halo_lo", "halo_hi"), list(a)))
 
     def stats_reset(self):
         self._chk(self.lib.apx_stats_reset(self.ctx))

@@ -9,6 +9,9 @@ void apx_to_sorted(apx_ctx* c, const double* in_dev, real* out);
 void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev);
 void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_grad_to_caller(apx_ctx* c, double* dev_out);
+struct ApxComm;
+ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id);
+ApxComm* apx_make_local_comm(int rank, int world, void* hub);
 
 static thread_local std::string g_err;
 
@@ -117,6 +120,8 @@ void d2h(apx_ctx* c, double* dst, const double* src_dev, size_t count)
 
 void out_sorted3(apx_ctx* c, const real* src_sorted, double* host_out)
 {
+   if (c->dist.on)      // collective: every rank returns the whole array
+      apx_dist_share_owned(c, const_cast<real*>(src_sorted), 3 * sizeof(real));
    c->io_a.ensure(3 * (size_t)c->n);
    apx_from_sorted(c, src_sorted, c->io_a);
    d2h(c, host_out, c->io_a, 3 * (size_t)c->n);
@@ -138,9 +143,9 @@ const char* apx_last_error(void) { return g_err.c_str(); }
 const char* apx_version(void) { return "apx 0.1 (" APX_PREC_NAME ")"; }
 int apx_precision_bytes(void) { return (int)sizeof(real); }
 
-int apx_create(const apx_system* sys, int device, apx_ctx** out)
+static void create_impl(const apx_system* sys, int device, int rank, int world, const char* transport, const void* handle,
+   const char* nccl_lib, apx_ctx** out)
 {
-   API_BEGIN
    if (!sys || !out)
       APX_THROW("null argument");
    require_gpu(device);
@@ -148,6 +153,24 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    apx_ctx* c = new apx_ctx();
    *out = c;
    c->device = device;
+   if (world > 1) {
+      if (rank < 0 || rank >= world || world > 8)
+         APX_THROW("rank/world out of range (1..8 GPUs)");
+      if (!sys->use_ewald)
+         APX_THROW("the multi-GPU decomposition is built for PME systems");
+      if (fabs(sys->lvec[2]) + fabs(sys->lvec[5]) + fabs(sys->lvec[6]) + fabs(sys->lvec[7]) > 1e-12)
+         APX_THROW("z-slab decomposition needs the third cell vector along z");
+      c->dist.on = 1;
+      c->dist.rank = rank;
+      c->dist.world = world;
+      std::string t = transport ? transport : "nccl";
+      if (t == "nccl")
+         c->dist.comm = apx_make_nccl_comm(rank, world, nccl_lib, handle);
+      else if (t == "local")
+         c->dist.comm = apx_make_local_comm(rank, world, const_cast<void*>(handle));
+      else
+         APX_THROW("unknown transport " + t);
+   }
    c->opt = *sys;
    c->n = sys->n;
    if (c->n <= 0)
@@ -283,8 +306,31 @@ int apx_create(const apx_system* sys, int device, apx_ctx** out)
    c->io_b.ensure(3 * np);
    c->list_cutoff = (real)std::min(sys->cutoff, 1.0e6);
    c->list_buffer = (real)sys->list_buffer;
+   c->a0 = 0, c->a1 = c->n;
    apx_pme_setup(c);
    apx_list_refresh(c, true);
+}
+
+int apx_create(const apx_system* sys, int device, apx_ctx** out)
+{
+   API_BEGIN
+   create_impl(sys, device, 0, 1, nullptr, nullptr, nullptr, out);
+   API_END
+}
+
+int apx_create_dist(const apx_system* sys, int device, int rank, int world, const char* transport, const void* handle,
+   const char* nccl_lib, apx_ctx** out)
+{
+   API_BEGIN
+   create_impl(sys, device, rank, world, transport, handle, nccl_lib, out);
+   API_END
+}
+
+int apx_get_dist_info(apx_ctx* c, int* info /* [8]: rank, world, a0, a1, halo atoms, pz, hl, hu */)
+{
+   API_BEGIN
+   info[0] = c->dist.rank, info[1] = c->dist.world, info[2] = c->a0, info[3] = c->a1;
+   info[4] = (int)c->dist.halo_atoms, info[5] = c->dist.pz, info[6] = c->dist.hl, info[7] = c->dist.hu;
    API_END
 }
 
@@ -297,6 +343,7 @@ void apx_destroy(apx_ctx* c)
    cudaStreamSynchronize(c->stream2);
    apx_pcg_graphs_invalidate(c);
    apx_pme_destroy(c);
+   apx_dist_destroy(c);
    // views into the arenas are not owned
    c->gx.p = c->gy.p = c->gz.p = c->trqf.p = c->ebuf.p = nullptr;
    c->dbuf.p = nullptr, c->cnt.p = nullptr, c->scal.p = nullptr, c->flags.p = nullptr;
@@ -502,6 +549,8 @@ int apx_pme_mpole_fphi(apx_ctx* c, double* fphi)
    if (!c->opt.use_ewald)
       APX_THROW("PME operator called on a non-Ewald system");
    apx_pme_mpole(c, false);
+   if (c->dist.on)
+      apx_dist_share_owned(c, c->fphi.p, 20 * sizeof(real));
    const int n = c->n;
    std::vector<real> h(20 * (size_t)n);
    std::vector<int> perm(n);
@@ -527,6 +576,10 @@ int apx_pme_uind_fphi(apx_ctx* c, const double* uind, const double* uinp, double
    h2d(c, c->io_a, uinp, 3 * (size_t)c->n);
    apx_to_sorted(c, c->io_a, c->conjp);
    apx_pme_uind_fphi(c, c->conj, c->conjp, true);
+   if (c->dist.on) {
+      apx_dist_share_owned(c, c->fphid.p, 10 * sizeof(real));
+      apx_dist_share_owned(c, c->fphip.p, 10 * sizeof(real));
+   }
    const int n = c->n;
    std::vector<real> a(10 * (size_t)n), b(10 * (size_t)n);
    std::vector<int> perm(n);
@@ -571,6 +624,8 @@ int apx_pme_convolve_grid(apx_ctx* c, const double* in, double* out)
    CUDA_CHECK(cudaSetDevice(c->device));
    if (!c->opt.use_ewald)
       APX_THROW("PME operator called on a non-Ewald system");
+   if (c->dist.on)
+      APX_THROW("apx_pme_convolve_grid takes a whole grid: single-GPU contexts only");
    size_t K = (size_t)c->nfft1 * c->nfft2 * c->nfft3;
    std::vector<cplx> h(K);
    for (size_t i = 0; i < K; ++i) {

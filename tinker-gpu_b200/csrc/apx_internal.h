@@ -98,6 +98,7 @@ struct RowList {
    DevBuf<int> vnbr;        // Verlet rows
    DevBuf<int> nbr;         // per-step compacted rows
    DevBuf<int> cnt, cntu;   // [n]
+   DevBuf<real4> sctr, sext;  // bounding boxes of super-blocks (32 blocks)
    DevBuf<unsigned long long> total;   // [2]: directed pairs within cutoff / ucut at the last compaction
    long long nverlet = 0;
 };
@@ -107,8 +108,32 @@ struct PairExcl {           // exclusion pair in SORTED indices with (scale-1) f
    real m, d, p, u;
 };
 
+// ---- multi-GPU spatial decomposition (dist.cu).  Every rank keeps the whole atom
+// set in the same sorted order ("replicated data") but owns the contiguous sorted range [a0,a1) of
+// one z-slab and the matching planes of the PME grid ("partitioned work").
+struct ApxComm;
+struct DistState {
+   int on = 0, rank = 0, world = 1;
+   ApxComm* comm = nullptr;
+   std::vector<int> bounds;              // [world+1] first sorted index of every rank's slab
+   // halo of per-atom vectors: atoms of other ranks within list range of my slab (and vice versa)
+   DevBuf<int> send_idx, recv_idx;       // concatenated by peer
+   std::vector<int> send_off, recv_off;  // [world+1]
+   DevBuf<real4> sendbuf, recvbuf;       // 2 real4 per atom (packed (d,p) pair)
+   // PME slab decomposition: planes [z0, z0+pz) owned, hl / hu halo planes below / above
+   int pz = 0, z0 = 0, hl = 0, hu = 0, py = 0, y0 = 0;
+   cufftHandle plan2d = 0, plan1d = 0;
+   int plans_ok = 0;
+   DevBuf<cplx> tbuf, sbuf, tbuf2, hbuf;  // transposed grid [n3][py][n1], pack buffer, cross-virial copy, halo planes
+   long long halo_atoms = 0;
+};
+
 struct apx_ctx {
    int device = 0;
+   DistState dist;
+   int a0 = 0, a1 = 0;                   // owned sorted range (single GPU: [0, n))
+   int zbase = 0, nzl = 0;               // local PME planes: global plane zg lives at (zg - zbase) mod nfft3, nzl planes held
+   int qy0 = 0, qny = 0;                 // influence function / transformed grid cover k2 in [qy0, qy0+qny) (single GPU: all)
    cudaStream_t stream = nullptr;
    int n = 0, nblk = 0, npad = 0;
    int sm_count = 148;
@@ -133,6 +158,7 @@ struct apx_ctx {
    // ---- sorted-order data (rebuilt with the list)
    DevBuf<int> perm, inv;                // perm[s] = caller index, inv[i] = sorted slot
    DevBuf<unsigned> sortkey, sortkey2;
+   DevBuf<real> w3;                      // PME z-coordinate of every atom (caller order), slab decomposition only
    DevBuf<int> permtmp;
    DevBuf<char> cubtmp;
    size_t cubtmp_bytes = 0;
@@ -218,6 +244,18 @@ struct apx_ctx {
 // ---- nblist.cu
 void apx_list_refresh(apx_ctx* c, bool force);
 void apx_update_sorted_positions(apx_ctx* c);
+// ---- dist.cu
+void apx_dist_after_sort(apx_ctx* c);                              // ownership bounds + halo plan (at list rebuild)
+void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st);         // V[halo atoms] <- owners' values
+void apx_dist_allreduce_f64(apx_ctx* c, double* p, size_t n);
+void apx_dist_allreduce_u64(apx_ctx* c, unsigned long long* p, size_t n);
+void apx_dist_allreduce_i32(apx_ctx* c, int* p, size_t n);
+void apx_dist_share_owned(apx_ctx* c, void* base, size_t bytes_per_atom);   // every rank receives the owned ranges of the others
+void apx_dist_pme_setup(apx_ctx* c);
+void apx_dist_pme_destroy(apx_ctx* c);
+void apx_dist_fft_forward(apx_ctx* c, cplx* tb);                   // local grid (halo-reduced) -> transformed slab tb
+void apx_dist_fft_inverse(apx_ctx* c, cplx* tb);                   // tb -> local grid including halo planes
+void apx_dist_destroy(apx_ctx* c);
 // ---- rows.cu
 void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort
 void apx_rows_compact(apx_ctx* c, bool count);    // per-step compaction to r <= cutoff

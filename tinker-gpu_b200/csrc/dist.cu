@@ -1,0 +1,679 @@
+// Multi-GPU spatial decomposition of the AMOEBA electrostatics path (the reference is
+// single-GPU, so nothing here has a counterpart in it).
+//
+//   * z-slabs: GPU g owns the atoms whose PME grid coordinate w3 lies in [g/G, (g+1)/G) -- one
+//     contiguous range [a0,a1) of the common sorted order (nblist.cu puts the slab in the top bits
+//     of the sort key) -- and the nfft3/G planes of the PME grid those atoms sit on.  Per-atom
+//     static data (positions, rotated multipoles, polarizabilities) is replicated: it is O(N)
+//     streaming work per step and needs no exchange.  Everything that costs -- neighbor rows,
+//     pair kernels, spreading, gathering, FFT, solver vectors -- is done for owned atoms/planes only.
+//   * halo exchange per operator application: the packed (d,p) vectors of the atoms within
+//     cutoff+buffer of a neighbour's slab go to that neighbour (pack kernel -> grouped send/recv ->
+//     unpack kernel).  Both sides derive the same index lists from the replicated coordinates, so
+//     no index traffic is needed.
+//   * slab-decomposed 3-D FFT: halo planes of the spread grid are summed into their owners, 2-D
+//     FFTs over the owned planes, an all-to-all transpose to [k3][k2 local][k1], 1-D FFTs along z,
+//     the influence function, and the way back; the potential's halo planes are then returned for
+//     the gather.
+//   * scalars of the solver: one small all-reduce per dot-product pair (3 per iteration).
+//
+// Two transports implement the same interface (ApxComm): NCCL over NVLink (one process per GPU,
+// symbols resolved at run time from the libnccl the host process already uses), and an in-process
+// transport for several ranks driven by host threads on ONE GPU, which lets the whole decomposition be
+// parity-tested against the single-GPU path on a one-GPU box.
+#include "apx_internal.h"
+#include "dp.cuh"
+#include <nccl.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <mutex>
+
+// ------------------------------------------------------------------------------------------------
+// transports
+// ------------------------------------------------------------------------------------------------
+struct ApxComm {
+   struct Op {
+      int peer;
+      void* ptr;
+      size_t bytes;
+   };
+   int rank = 0, world = 1;
+   virtual ~ApxComm() {}
+   // dtype: 0 = f64, 1 = u64, 2 = i32 ; in place, sum
+   virtual void allreduce(void* p, size_t n, int dtype, cudaStream_t st) = 0;
+   // messages between the same pair of ranks are matched in the order they are listed
+   virtual void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) = 0;
+};
+
+namespace {
+// ---- NCCL, bound with dlsym so that libapx carries no link-time dependency on a particular libnccl
+struct NcclApi {
+   void* handle = nullptr;
+   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*GroupStart)() = nullptr;
+   ncclResult_t (*GroupEnd)() = nullptr;
+   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi* nccl_api(const char* path)
+{
+   static NcclApi api;
+   static std::mutex m;
+   std::lock_guard<std::mutex> lk(m);
+   if (api.handle)
+      return &api;
+   const char* names[] = {path && path[0] ? path : "libnccl.so.2", "libnccl.so.2", "libnccl.so"};
+   for (const char* nm : names) {
+      api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (api.handle)
+         break;
+   }
+   if (!api.handle)
+      APX_THROW(std::string("cannot load NCCL: ") + dlerror());
+#define BIND(field, sym)                                                                                                 \
+   api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym));                                            \
+   if (!api.field)                                                                                                       \
+      APX_THROW(std::string("NCCL symbol missing: ") + sym)
+   BIND(GetUniqueId, "ncclGetUniqueId");
+   BIND(CommInitRank, "ncclCommInitRank");
+   BIND(CommDestroy, "ncclCommDestroy");
+   BIND(AllReduce, "ncclAllReduce");
+   BIND(Send, "ncclSend");
+   BIND(Recv, "ncclRecv");
+   BIND(GroupStart, "ncclGroupStart");
+   BIND(GroupEnd, "ncclGroupEnd");
+   BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+   return &api;
+}
+
+#define NCCL_CHECK(api, expr)                                                                                            \
+   do {                                                                                                                  \
+      ncclResult_t r__ = (expr);                                                                                         \
+      if (r__ != ncclSuccess)                                                                                            \
+         apx_throw(__FILE__, __LINE__, std::string(#expr) + ": " + (api)->GetErrorString(r__));                          \
+   } while (0)
+
+struct NcclComm : ApxComm {
+   NcclApi* api = nullptr;
+   ncclComm_t comm = nullptr;
+   ~NcclComm() override
+   {
+      if (comm)
+         api->CommDestroy(comm);
+   }
+   void allreduce(void* p, size_t n, int dtype, cudaStream_t st) override
+   {
+      ncclDataType_t t = dtype == 0 ? ncclFloat64 : (dtype == 1 ? ncclUint64 : ncclInt32);
+      NCCL_CHECK(api, api->AllReduce(p, p, n, t, ncclSum, comm, st));
+   }
+   void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) override
+   {
+      NCCL_CHECK(api, api->GroupStart());
+      for (const Op& o : sends)
+         NCCL_CHECK(api, api->Send(o.ptr, o.bytes, ncclChar, o.peer, comm, st));
+      for (const Op& o : recvs)
+         NCCL_CHECK(api, api->Recv(o.ptr, o.bytes, ncclChar, o.peer, comm, st));
+      NCCL_CHECK(api, api->GroupEnd());
+   }
+};
+
+// ---- in-process transport: `world` ranks = host threads of one process on one device
+struct LocalHub {
+   int world = 1;
+   std::mutex m;
+   std::condition_variable cv;
+   int count = 0;
+   long gen = 0;
+   bool broken = false;
+   std::vector<std::vector<ApxComm::Op>> box;     // [src * world + dst]
+   std::vector<cudaEvent_t> ready, done;          // per rank
+   std::vector<void*> stage;
+   std::vector<size_t> stage_cap;
+   explicit LocalHub(int w) : world(w), box((size_t)w * w), ready(w, nullptr), done(w, nullptr), stage(w, nullptr), stage_cap(w, 0) {}
+   void barrier()
+   {
+      std::unique_lock<std::mutex> lk(m);
+      if (broken)
+         APX_THROW("local transport: a peer rank failed");
+      long g = gen;
+      if (++count == world) {
+         count = 0;
+         ++gen;
+         cv.notify_all();
+         return;
+      }
+      if (!cv.wait_for(lk, std::chrono::seconds(120), [&] { return gen != g || broken; })) {
+         broken = true;
+         cv.notify_all();
+         APX_THROW("local transport: ranks did not reach the same collective within 120 s");
+      }
+      if (broken)
+         APX_THROW("local transport: a peer rank failed");
+   }
+};
+
+struct StagePtrs {
+   const void* p[16];
+};
+template <class T>
+__global__ void k_sum_stages(size_t n, int world, StagePtrs sp, T* __restrict__ out)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   T v = 0;
+   for (int r = 0; r < world; ++r)        // fixed order: every rank gets the same bits
+      v += static_cast<const T*>(sp.p[r])[i];
+   out[i] = v;
+}
+
+struct LocalComm : ApxComm {
+   LocalHub* hub = nullptr;
+   void allreduce(void* p, size_t n, int dtype, cudaStream_t st) override
+   {
+      const size_t bytes = n * (dtype == 2 ? 4 : 8);
+      if (world > 16)
+         APX_THROW("local transport supports at most 16 ranks");
+      if (hub->stage_cap[rank] < bytes) {
+         if (hub->stage[rank])
+            cudaFree(hub->stage[rank]);
+         CUDA_CHECK(cudaMalloc(&hub->stage[rank], bytes + bytes / 4 + 256));
+         hub->stage_cap[rank] = bytes + bytes / 4 + 256;
+      }
+      CUDA_CHECK(cudaMemcpyAsync(hub->stage[rank], p, bytes, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaEventRecord(hub->ready[rank], st));
+      hub->barrier();
+      StagePtrs sp;
+      for (int r = 0; r < world; ++r) {
+         sp.p[r] = hub->stage[r];
+         if (r != rank)
+            CUDA_CHECK(cudaStreamWaitEvent(st, hub->ready[r], 0));
+      }
+      const unsigned g = (unsigned)((n + 255) / 256);
+      if (dtype == 0)
+         k_sum_stages<double><<<g, 256, 0, st>>>(n, world, sp, (double*)p);
+      else if (dtype == 1)
+         k_sum_stages<unsigned long long><<<g, 256, 0, st>>>(n, world, sp, (unsigned long long*)p);
+      else
+         k_sum_stages<int><<<g, 256, 0, st>>>(n, world, sp, (int*)p);
+      CUDA_CHECK(cudaEventRecord(hub->done[rank], st));
+      hub->barrier();
+      for (int r = 0; r < world; ++r)
+         if (r != rank)
+            CUDA_CHECK(cudaStreamWaitEvent(st, hub->done[r], 0));
+   }
+   void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) override
+   {
+      for (int d = 0; d < world; ++d)
+         hub->box[(size_t)rank * world + d].clear();
+      for (const Op& o : sends)
+         hub->box[(size_t)rank * world + o.peer].push_back(o);
+      CUDA_CHECK(cudaEventRecord(hub->ready[rank], st));
+      hub->barrier();
+      std::vector<int> taken(world, 0);
+      std::vector<char> waited(world, 0);
+      for (const Op& o : recvs) {
+         auto& b = hub->box[(size_t)o.peer * world + rank];
+         if (taken[o.peer] >= (int)b.size() || b[taken[o.peer]].bytes != o.bytes)
+            APX_THROW("local transport: unmatched message");
+         if (!waited[o.peer]) {
+            CUDA_CHECK(cudaStreamWaitEvent(st, hub->ready[o.peer], 0));
+            waited[o.peer] = 1;
+         }
+         CUDA_CHECK(cudaMemcpyAsync(o.ptr, b[taken[o.peer]].ptr, o.bytes, cudaMemcpyDeviceToDevice, st));
+         taken[o.peer]++;
+      }
+      CUDA_CHECK(cudaEventRecord(hub->done[rank], st));
+      hub->barrier();
+      // my send buffers may be rewritten only after the receivers have copied them
+      std::fill(waited.begin(), waited.end(), 0);
+      for (const Op& o : sends)
+         if (!waited[o.peer]) {
+            CUDA_CHECK(cudaStreamWaitEvent(st, hub->done[o.peer], 0));
+            waited[o.peer] = 1;
+         }
+   }
+};
+
+// self-addressed messages never reach a transport
+void comm_exchange(apx_ctx* c, const std::vector<ApxComm::Op>& sends, const std::vector<ApxComm::Op>& recvs, cudaStream_t st)
+{
+   ApxComm* cm = c->dist.comm;
+   std::vector<ApxComm::Op> s2, r2, ss, rs;
+   for (auto& o : sends)
+      (o.peer == cm->rank ? ss : s2).push_back(o);
+   for (auto& o : recvs)
+      (o.peer == cm->rank ? rs : r2).push_back(o);
+   if (ss.size() != rs.size())
+      APX_THROW("self messages do not pair up");
+   for (size_t k = 0; k < ss.size(); ++k)
+      if (ss[k].bytes)
+         CUDA_CHECK(cudaMemcpyAsync(rs[k].ptr, ss[k].ptr, ss[k].bytes, cudaMemcpyDeviceToDevice, st));
+   cm->exchange(s2, r2, st);
+}
+
+double frac_dist_to_slab(double w, int r, int world)
+{
+   // periodic distance (in units of the cell's third fractional coordinate) from w to [r/G, (r+1)/G)
+   const double lo = (double)r / world, hi = (double)(r + 1) / world;
+   if (w >= lo && w < hi)
+      return 0.0;
+   auto pd = [](double x) {
+      x = fabs(x);
+      x -= floor(x);
+      return std::min(x, 1.0 - x);
+   };
+   return std::min(pd(w - lo), pd(w - hi));
+}
+} // namespace
+
+// Halo plan shared by every rank: for sorted atom s with grid coordinate w3s[s], owned by the rank whose
+// bounds contain s, rank r needs it when its distance to r's slab is <= range_frac.  Fills, for
+// `rank`, the atoms it sends to every peer and the atoms it receives from every peer (sorted
+// indices, ascending, concatenated by peer; *_off has world+1 entries).  Pure host code.
+static void plan_halo(int n, const float* w3s, const int* bounds, int world, int rank, double range_frac, std::vector<int>& send_idx,
+   std::vector<int>& send_off, std::vector<int>& recv_idx, std::vector<int>& recv_off)
+{
+   std::vector<std::vector<int>> snd(world), rcv(world);
+   for (int owner = 0; owner < world; ++owner)
+      for (int s = bounds[owner]; s < bounds[owner + 1]; ++s) {
+         const double w = w3s[s];
+         if (owner == rank) {
+            for (int r = 0; r < world; ++r)
+               if (r != rank && frac_dist_to_slab(w, r, world) <= range_frac)
+                  snd[r].push_back(s);
+         } else if (frac_dist_to_slab(w, rank, world) <= range_frac) {
+            rcv[owner].push_back(s);
+         }
+      }
+   send_idx.clear(), recv_idx.clear();
+   send_off.assign(world + 1, 0), recv_off.assign(world + 1, 0);
+   for (int r = 0; r < world; ++r) {
+      send_idx.insert(send_idx.end(), snd[r].begin(), snd[r].end());
+      recv_idx.insert(recv_idx.end(), rcv[r].begin(), rcv[r].end());
+      send_off[r + 1] = (int)send_idx.size();
+      recv_off[r + 1] = (int)recv_idx.size();
+   }
+}
+
+namespace {
+__global__ void k_halo_pack(int m, const int* __restrict__ idx, const real4* __restrict__ V, real4* __restrict__ buf)
+{
+   int j = blockIdx.x * blockDim.x + threadIdx.x;
+   if (j >= 2 * m)
+      return;
+   buf[j] = V[2 * (size_t)idx[j >> 1] + (j & 1)];
+}
+__global__ void k_halo_unpack(int m, const int* __restrict__ idx, const real4* __restrict__ buf, real4* __restrict__ V)
+{
+   int j = blockIdx.x * blockDim.x + threadIdx.x;
+   if (j >= 2 * m)
+      return;
+   V[2 * (size_t)idx[j >> 1] + (j & 1)] = buf[j];
+}
+
+__global__ void k_grid_add(size_t m, const cplx* __restrict__ src, cplx* __restrict__ dst)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= m)
+      return;
+   cplx a = dst[i], b = src[i];
+   a.x += b.x;
+   a.y += b.y;
+   dst[i] = a;
+}
+
+// planes [z][y][x] of this rank -> blocks [r][z][y local to r][x] for the transpose, and back
+__global__ void k_transpose_pack(int pz, int n2, int n1, int py, const cplx* __restrict__ planes, cplx* __restrict__ buf)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   size_t tot = (size_t)pz * n2 * n1;
+   if (i >= tot)
+      return;
+   int x = (int)(i % n1);
+   int y = (int)((i / n1) % n2);
+   int z = (int)(i / ((size_t)n1 * n2));
+   int r = y / py, yl = y - r * py;
+   buf[(((size_t)r * pz + z) * py + yl) * n1 + x] = planes[i];
+}
+__global__ void k_transpose_unpack(int pz, int n2, int n1, int py, const cplx* __restrict__ buf, cplx* __restrict__ planes)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   size_t tot = (size_t)pz * n2 * n1;
+   if (i >= tot)
+      return;
+   int x = (int)(i % n1);
+   int y = (int)((i / n1) % n2);
+   int z = (int)(i / ((size_t)n1 * n2));
+   int r = y / py, yl = y - r * py;
+   planes[i] = buf[(((size_t)r * pz + z) * py + yl) * n1 + x];
+}
+
+inline void exec_fft(cufftHandle plan, cplx* p, int dir)
+{
+#ifdef APX_DOUBLE
+   CUFFT_CHECK(cufftExecZ2Z(plan, p, p, dir));
+#else
+   CUFFT_CHECK(cufftExecC2C(plan, p, p, dir));
+#endif
+}
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// ownership + halo plan, at every list rebuild (after the sort)
+// ------------------------------------------------------------------------------------------------
+void apx_dist_after_sort(apx_ctx* c)
+{
+   DistState& D = c->dist;
+   const int n = c->n, G = D.world;
+   std::vector<unsigned> keys(n);
+   std::vector<int> perm(n);
+   std::vector<real> w3(n);
+   CUDA_CHECK(cudaMemcpyAsync(keys.data(), c->sortkey2.p, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaMemcpyAsync(perm.data(), c->perm.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaMemcpyAsync(w3.data(), c->w3.p, sizeof(real) * n, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   D.bounds.assign(G + 1, -1);
+   D.bounds[G] = n;
+   for (int s = n - 1; s >= 0; --s)
+      D.bounds[keys[s] >> 27] = s;           // first index of every non-empty slab
+   for (int g = G - 1; g >= 0; --g)
+      if (D.bounds[g] < 0)
+         D.bounds[g] = D.bounds[g + 1];
+   D.bounds[0] = 0;
+   c->a0 = D.bounds[D.rank];
+   c->a1 = D.bounds[D.rank + 1];
+   std::vector<float> w3s(n);
+   for (int s = 0; s < n; ++s)
+      w3s[s] = (float)w3[perm[s]];
+   // list range in units of the third fractional coordinate: planes of constant w3 are 1/|recip_c| apart
+   const double r3 = sqrt((double)c->box.r[6] * c->box.r[6] + (double)c->box.r[7] * c->box.r[7] + (double)c->box.r[8] * c->box.r[8]);
+   const double range_frac = ((double)c->list_cutoff + (double)c->list_buffer) * r3 * (1.0 + 1e-6) + 1e-7;
+   std::vector<int> si, ri;
+   plan_halo(n, w3s.data(), D.bounds.data(), G, D.rank, range_frac, si, D.send_off, ri, D.recv_off);
+   D.send_idx.ensure(si.size() + 1);
+   D.recv_idx.ensure(ri.size() + 1);
+   if (!si.empty())
+      CUDA_CHECK(cudaMemcpyAsync(D.send_idx.p, si.data(), sizeof(int) * si.size(), cudaMemcpyHostToDevice, c->stream));
+   if (!ri.empty())
+      CUDA_CHECK(cudaMemcpyAsync(D.recv_idx.p, ri.data(), sizeof(int) * ri.size(), cudaMemcpyHostToDevice, c->stream));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   D.sendbuf.ensure(2 * si.size() + 2);
+   D.recvbuf.ensure(2 * ri.size() + 2);
+   D.halo_atoms = (long long)ri.size();
+}
+
+// V[halo atoms] <- the owners' values; V is a packed (d,p) array (2 real4 per atom, dp.cuh)
+void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st)
+{
+   DistState& D = c->dist;
+   const int G = D.world;
+   const int ns = D.send_off[G], nr = D.recv_off[G];
+   if (ns > 0) {
+      k_halo_pack<<<(2 * ns + 255) / 256, 256, 0, st>>>(ns, D.send_idx, V, D.sendbuf);
+      APX_COUNT_LAUNCH(c);
+   }
+   std::vector<ApxComm::Op> sends, recvs;
+   for (int r = 0; r < G; ++r) {
+      if (D.send_off[r + 1] > D.send_off[r])
+         sends.push_back({r, D.sendbuf.p + 2 * (size_t)D.send_off[r], sizeof(real4) * 2 * (size_t)(D.send_off[r + 1] - D.send_off[r])});
+      if (D.recv_off[r + 1] > D.recv_off[r])
+         recvs.push_back({r, D.recvbuf.p + 2 * (size_t)D.recv_off[r], sizeof(real4) * 2 * (size_t)(D.recv_off[r + 1] - D.recv_off[r])});
+   }
+   comm_exchange(c, sends, recvs, st);
+   if (nr > 0) {
+      k_halo_unpack<<<(2 * nr + 255) / 256, 256, 0, st>>>(nr, D.recv_idx, D.recvbuf, V);
+      APX_COUNT_LAUNCH(c);
+   }
+}
+
+void apx_dist_allreduce_f64(apx_ctx* c, double* p, size_t n) { c->dist.comm->allreduce(p, n, 0, c->stream); }
+void apx_dist_allreduce_u64(apx_ctx* c, unsigned long long* p, size_t n) { c->dist.comm->allreduce(p, n, 1, c->stream); }
+void apx_dist_allreduce_i32(apx_ctx* c, int* p, size_t n) { c->dist.comm->allreduce(p, n, 2, c->stream); }
+
+// every rank receives the owned ranges of the others (sorted-order arrays with a fixed stride per atom)
+void apx_dist_share_owned(apx_ctx* c, void* base, size_t bpa)
+{
+   DistState& D = c->dist;
+   std::vector<ApxComm::Op> sends, recvs;
+   char* b = static_cast<char*>(base);
+   for (int r = 0; r < D.world; ++r) {
+      if (r == D.rank)
+         continue;
+      if (c->a1 > c->a0)
+         sends.push_back({r, b + bpa * (size_t)c->a0, bpa * (size_t)(c->a1 - c->a0)});
+      if (D.bounds[r + 1] > D.bounds[r])
+         recvs.push_back({r, b + bpa * (size_t)D.bounds[r], bpa * (size_t)(D.bounds[r + 1] - D.bounds[r])});
+   }
+   comm_exchange(c, sends, recvs, c->stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// slab-decomposed PME grid
+// ------------------------------------------------------------------------------------------------
+void apx_dist_pme_setup(apx_ctx* c)
+{
+   DistState& D = c->dist;
+   const int G = D.world, n1 = c->nfft1, n2 = c->nfft2, n3 = c->nfft3;
+   if (n3 % G || n2 % G)
+      APX_THROW("slab PME: nfft2 and nfft3 must be multiples of the number of GPUs");
+   D.pz = n3 / G;
+   D.z0 = D.rank * D.pz;
+   D.py = n2 / G;
+   D.y0 = D.rank * D.py;
+   // an atom's stencil covers planes ii-4 .. ii with ii the plane of its w3; between list rebuilds it
+   // may drift buffer/2, i.e. m planes, in either direction
+   const double r3 = sqrt((double)c->box.r[6] * c->box.r[6] + (double)c->box.r[7] * c->box.r[7] + (double)c->box.r[8] * c->box.r[8]);
+   const int m = (int)ceil(0.5 * c->opt.list_buffer * n3 * r3) + 1;
+   D.hl = 4 + m;
+   D.hu = m;
+   if (D.hl > D.pz || D.pz + D.hl + D.hu > n3)
+      APX_THROW("slab PME: slabs of " + std::to_string(D.pz) + " planes are thinner than the " + std::to_string(D.hl)
+         + "-plane halo; use fewer GPUs or a finer grid");
+   c->zbase = ((D.z0 - D.hl) % n3 + n3) % n3;
+   c->nzl = D.pz + D.hl + D.hu;
+   c->qy0 = D.y0;
+   c->qny = D.py;
+   if (D.plans_ok) {
+      cufftDestroy(D.plan2d);
+      cufftDestroy(D.plan1d);
+      D.plans_ok = 0;
+   }
+#ifdef APX_DOUBLE
+   const cufftType ty = CUFFT_Z2Z;
+#else
+   const cufftType ty = CUFFT_C2C;
+#endif
+   int dims2[2] = {n2, n1};
+   CUFFT_CHECK(cufftPlanMany(&D.plan2d, 2, dims2, nullptr, 1, n2 * n1, nullptr, 1, n2 * n1, ty, D.pz));
+   int dims1[1] = {n3};
+   int emb[1] = {n3};
+   CUFFT_CHECK(cufftPlanMany(&D.plan1d, 1, dims1, emb, D.py * n1, 1, emb, D.py * n1, 1, ty, D.py * n1));
+   CUFFT_CHECK(cufftSetStream(D.plan2d, c->stream));
+   CUFFT_CHECK(cufftSetStream(D.plan1d, c->stream));
+   D.plans_ok = 1;
+   const size_t slab = (size_t)n3 * D.py * n1;
+   D.tbuf.ensure(slab);
+   D.sbuf.ensure(slab);
+   D.hbuf.ensure((size_t)(D.hl + D.hu) * n2 * n1);
+}
+
+void apx_dist_pme_destroy(apx_ctx* c)
+{
+   DistState& D = c->dist;
+   if (D.plans_ok) {
+      cufftDestroy(D.plan2d);
+      cufftDestroy(D.plan1d);
+      D.plans_ok = 0;
+   }
+}
+
+// local grid (spread contributions of my atoms on my planes + halo planes) -> tb = [k3][k2 local][k1]
+void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
+{
+   DistState& D = c->dist;
+   const int G = D.world, n1 = c->nfft1, n2 = c->nfft2;
+   const size_t plane = (size_t)n1 * n2;
+   const int prev = (D.rank + G - 1) % G, next = (D.rank + 1) % G;
+   cudaStream_t st = c->stream;
+   cplx* g = c->qgrid.p;
+   // 1. halo planes go to the slabs they belong to and are summed there
+   {
+      std::vector<ApxComm::Op> sends = {{prev, g, D.hl * plane * sizeof(cplx)}, {next, g + (size_t)(D.hl + D.pz) * plane, D.hu * plane * sizeof(cplx)}};
+      std::vector<ApxComm::Op> recvs = {{next, D.hbuf.p, D.hl * plane * sizeof(cplx)}, {prev, D.hbuf.p + D.hl * plane, D.hu * plane * sizeof(cplx)}};
+      comm_exchange(c, sends, recvs, st);
+      size_t m1 = D.hl * plane, m2 = D.hu * plane;
+      k_grid_add<<<(unsigned)((m1 + 255) / 256), 256, 0, st>>>(m1, D.hbuf.p, g + (size_t)D.pz * plane);         // my top hl planes
+      k_grid_add<<<(unsigned)((m2 + 255) / 256), 256, 0, st>>>(m2, D.hbuf.p + D.hl * plane, g + (size_t)D.hl * plane);   // my bottom hu planes
+   }
+   cplx* mine = g + (size_t)D.hl * plane;
+   // 2. 2-D transforms of my planes, 3. transpose, 4. 1-D transforms along z
+   exec_fft(D.plan2d, mine, CUFFT_FORWARD);
+   const size_t tot = (size_t)D.pz * plane, blk = (size_t)D.pz * D.py * n1;
+   k_transpose_pack<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D.pz, n2, n1, D.py, mine, D.sbuf);
+   {
+      std::vector<ApxComm::Op> sends, recvs;
+      for (int r = 0; r < G; ++r) {
+         sends.push_back({r, D.sbuf.p + r * blk, blk * sizeof(cplx)});
+         recvs.push_back({r, tb + r * blk, blk * sizeof(cplx)});
+      }
+      comm_exchange(c, sends, recvs, st);
+   }
+   exec_fft(D.plan1d, tb, CUFFT_FORWARD);
+   c->stats.kernel_launches += 3;
+}
+
+// tb -> potential on my planes and on the halo planes my atoms' stencils reach
+void apx_dist_fft_inverse(apx_ctx* c, cplx* tb)
+{
+   DistState& D = c->dist;
+   const int G = D.world, n1 = c->nfft1, n2 = c->nfft2;
+   const size_t plane = (size_t)n1 * n2;
+   const int prev = (D.rank + G - 1) % G, next = (D.rank + 1) % G;
+   cudaStream_t st = c->stream;
+   cplx* g = c->qgrid.p;
+   cplx* mine = g + (size_t)D.hl * plane;
+   exec_fft(D.plan1d, tb, CUFFT_INVERSE);
+   const size_t tot = (size_t)D.pz * plane, blk = (size_t)D.pz * D.py * n1;
+   {
+      std::vector<ApxComm::Op> sends, recvs;
+      for (int r = 0; r < G; ++r) {
+         sends.push_back({r, tb + r * blk, blk * sizeof(cplx)});
+         recvs.push_back({r, D.sbuf.p + r * blk, blk * sizeof(cplx)});
+      }
+      comm_exchange(c, sends, recvs, st);
+   }
+   k_transpose_unpack<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(D.pz, n2, n1, D.py, D.sbuf, mine);
+   exec_fft(D.plan2d, mine, CUFFT_INVERSE);
+   {
+      // my top hl planes are the low halo of the next slab, my bottom hu planes the high halo of the previous one
+      std::vector<ApxComm::Op> sends = {{next, g + (size_t)D.pz * plane, D.hl * plane * sizeof(cplx)}, {prev, mine, D.hu * plane * sizeof(cplx)}};
+      std::vector<ApxComm::Op> recvs = {{prev, g, D.hl * plane * sizeof(cplx)}, {next, g + (size_t)(D.hl + D.pz) * plane, D.hu * plane * sizeof(cplx)}};
+      comm_exchange(c, sends, recvs, st);
+   }
+   c->stats.kernel_launches += 1;
+}
+
+void apx_dist_destroy(apx_ctx* c)
+{
+   DistState& D = c->dist;
+   apx_dist_pme_destroy(c);
+   delete D.comm;
+   D.comm = nullptr;
+   D.send_idx.release(), D.recv_idx.release(), D.sendbuf.release(), D.recvbuf.release();
+   D.tbuf.release(), D.sbuf.release(), D.tbuf2.release(), D.hbuf.release();
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI (declared in include/apx.h)
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_dist_err;
+const char* apx_dist_error() { return g_dist_err.c_str(); }
+
+ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id)
+{
+   NcclApi* api = nccl_api(lib);
+   NcclComm* cm = new NcclComm();
+   cm->api = api;
+   cm->rank = rank;
+   cm->world = world;
+   ncclUniqueId id;
+   memcpy(&id, unique_id, sizeof(id));
+   NCCL_CHECK(api, api->CommInitRank(&cm->comm, world, id, rank));
+   return cm;
+}
+
+ApxComm* apx_make_local_comm(int rank, int world, void* hub_)
+{
+   LocalHub* hub = static_cast<LocalHub*>(hub_);
+   if (!hub || hub->world != world)
+      APX_THROW("local transport: hub was created for a different number of ranks");
+   LocalComm* cm = new LocalComm();
+   cm->hub = hub;
+   cm->rank = rank;
+   cm->world = world;
+   CUDA_CHECK(cudaEventCreateWithFlags(&hub->ready[rank], cudaEventDisableTiming));
+   CUDA_CHECK(cudaEventCreateWithFlags(&hub->done[rank], cudaEventDisableTiming));
+   return cm;
+}
+
+extern "C" {
+#pragma GCC visibility push(default)
+int apx_nccl_unique_id(const char* lib, void* out128)
+{
+   try {
+      NcclApi* api = nccl_api(lib);
+      ncclUniqueId id;
+      NCCL_CHECK(api, api->GetUniqueId(&id));
+      static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+      memcpy(out128, &id, sizeof(id));
+   } catch (const std::exception& e) {
+      g_dist_err = e.what();
+      return 1;
+   }
+   return 0;
+}
+
+void* apx_local_hub_create(int world) { return world >= 1 && world <= 16 ? new LocalHub(world) : nullptr; }
+
+void apx_local_hub_destroy(void* h)
+{
+   LocalHub* hub = static_cast<LocalHub*>(h);
+   if (!hub)
+      return;
+   for (void* p : hub->stage)
+      if (p)
+         cudaFree(p);
+   for (auto e : hub->ready)
+      if (e)
+         cudaEventDestroy(e);
+   for (auto e : hub->done)
+      if (e)
+         cudaEventDestroy(e);
+   delete hub;
+}
+
+// host-only: the halo plan of `rank` (no GPU needed; CPU tests run it under gloo with 2 ranks)
+int apx_dist_plan(int n, const float* w3_sorted, const int* bounds, int world, int rank, double range_frac, int* send_idx,
+   int* send_off, int* recv_idx, int* recv_off)
+{
+   std::vector<int> si, so, ri, ro;
+   plan_halo(n, w3_sorted, bounds, world, rank, range_frac, si, so, ri, ro);
+   std::copy(si.begin(), si.end(), send_idx);
+   std::copy(ri.begin(), ri.end(), recv_idx);
+   std::copy(so.begin(), so.end(), send_off);
+   std::copy(ro.begin(), ro.end(), recv_off);
+   return 0;
+}
+#pragma GCC visibility pop
+}

@@ -30,13 +30,13 @@ __device__ __forceinline__ int as_int(real w)
 // ufield: field of (ud, up) at every atom, Ewald real space or plain Thole-damped Coulomb
 // -------------------------------------------------------------------------------------------
 template <bool EWALD, bool TABLE, int G>
-__global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
+__global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
-   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
       const real4 pi = posd[i];
       const real4 qi = tpj[i];
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int n, Box box, real
 
 // exclusion pass for ufield (only pairs whose u-scale != 1; empty for stock AMOEBA)
 template <bool TABLE>
-__global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_ufield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F)
 {
    int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,6 +83,9 @@ __global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __rest
       return;
    PairExcl p = ex[e];
    if (p.u == 0)
+      return;
+   const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;   // each GPU corrects its own atoms
+   if (!own_i && !own_k)
       return;
    real4 pi = posd[p.i], pk = posd[p.k];
    real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
@@ -101,8 +104,10 @@ __global__ void k_ufield_excl(int nx, Box box, real cut2, const PairExcl* __rest
    V3 udi, upi, udk, upk;
    load_dp(U, p.i, udi, upi);
    load_dp(U, p.k, udk, upk);
-   atomic_dp(F, p.i, dipole_field(R, udk, B1, B2), dipole_field(R, upk, B1, B2));
-   atomic_dp(F, p.k, dipole_field(R, udi, B1, B2), dipole_field(R, upi, B1, B2));
+   if (own_i)
+      atomic_dp(F, p.i, dipole_field(R, udk, B1, B2), dipole_field(R, upk, B1, B2));
+   if (own_k)
+      atomic_dp(F, p.k, dipole_field(R, udi, B1, B2), dipole_field(R, upi, B1, B2));
 }
 
 // -------------------------------------------------------------------------------------------
@@ -119,12 +124,12 @@ __device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, 
 }
 
 template <bool EWALD, bool TABLE, int G>
-__global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int n, Box box, real aewald, const int* __restrict__ vstart,
+__global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
    const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign)
 {
-   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
       const real4 pi = posd[i];
       const real4 qi = tpj[i];
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int n, Box box, real
 
 // d-correction goes to fd, (p - d) correction to the delta array fpd
 template <bool TABLE>
-__global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0,
    const real4* __restrict__ mp1, const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd)
 {
@@ -176,6 +181,9 @@ __global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __rest
       return;
    PairExcl p = ex[e];
    if (p.d == 0 && p.p == 0)
+      return;
+   const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;
+   if (!own_i && !own_k)
       return;
    real4 pi = posd[p.i], pk = posd[p.k];
    real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
@@ -195,13 +203,13 @@ __global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __rest
    V3 ei = mpole_field(R, mk, L1, L2, L3, (real)-1);   // unit-scale damped Coulomb field at i
    V3 ek = mpole_field(R, mi, L1, L2, L3, (real)1);
    if (p.d != 0) {
-      atomic_real3(fd, p.i, p.d * ei);
-      atomic_real3(fd, p.k, p.d * ek);
+      if (own_i) atomic_real3(fd, p.i, p.d * ei);
+      if (own_k) atomic_real3(fd, p.k, p.d * ek);
    }
    real dp = p.p - p.d;
    if (dp != 0) {
-      atomic_real3(fpd, p.i, dp * ei);
-      atomic_real3(fpd, p.k, dp * ek);
+      if (own_i) atomic_real3(fpd, p.i, dp * ei);
+      if (own_k) atomic_real3(fpd, p.k, dp * ek);
    }
 }
 
@@ -210,7 +218,7 @@ __global__ void k_dfield_excl(int nx, Box box, real cut2, const PairExcl* __rest
 // (the first cntu entries of every row)
 // -------------------------------------------------------------------------------------------
 template <bool TABLE, int G>
-__global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, real udiag, const int* __restrict__ vstart,
+__global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int ntot, Box box, real udiag, const int* __restrict__ vstart,
    const int* __restrict__ cntu, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z, double* __restrict__ slot,
    const int* __restrict__ skip, PcgTest T)
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, rea
       double rr2_[2];
       pcg_q_block<2>(T.slot, 4, rr2_);
       double e = fmax(rr2_[0], rr2_[1]);
-      double eps = (double)T.debye * sqrt(e / n);
+      double eps = (double)T.debye * sqrt(e / ntot);
       done = eps < (double)T.poleps;
       if (T.it < T.miniter)
          done = false;
@@ -237,7 +245,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, rea
       }
    }
    if (done) {
-      for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+      for (int s = a0 + blockIdx.x * blockDim.x + threadIdx.x; s < a1; s += gridDim.x * blockDim.x) {
          V3 rd, rp;
          load_dp(Rv, s, rd, rp);
          real term = T.pcgpeek * tpj[s].y;
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, rea
       return;
    }
    double dot_d = 0, dot_p = 0;
-   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
       const real4 pi = posd[i];
       const real4 qi = tpj[i];
@@ -304,7 +312,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int n, Box box, rea
 }
 
 template <bool TABLE>
-__global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_precond_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z,
    const int* __restrict__ skip)
 {
@@ -315,6 +323,9 @@ __global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __res
       return;
    PairExcl p = ex[e];
    if (p.u == 0)
+      return;
+   const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;
+   if (!own_i && !own_k)
       return;
    real4 pi = posd[p.i], pk = posd[p.k];
    real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
@@ -334,8 +345,10 @@ __global__ void k_precond_excl(int nx, Box box, real cut2, const PairExcl* __res
    V3 rdi, rpi, rdk, rpk;
    load_dp(Rv, p.i, rdi, rpi);
    load_dp(Rv, p.k, rdk, rpk);
-   atomic_dp(Z, p.i, dipole_field(R, rdk, B1, B2), dipole_field(R, rpk, B1, B2));
-   atomic_dp(Z, p.k, dipole_field(R, rdi, B1, B2), dipole_field(R, rpi, B1, B2));
+   if (own_i)
+      atomic_dp(Z, p.i, dipole_field(R, rdk, B1, B2), dipole_field(R, rpk, B1, B2));
+   if (own_k)
+      atomic_dp(Z, p.k, dipole_field(R, rdi, B1, B2), dipole_field(R, rpi, B1, B2));
 }
 
 // partial R.Z after an exclusion pass changed Z (only needed when u-scale exclusions exist)
@@ -372,7 +385,7 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    // room for its CTAs (a grid that fills every SM first delays the spread by the length of a wave)
    int grid = rows_grid<UF_G>(c, 8);
 #define LAUNCH_UF(E, T)                                                                                                   \
-   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
+   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
       c->thlval, c->opt.njpolar, U, F, c->skip)
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
@@ -392,9 +405,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    if (c->nexcl_u > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_ufield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
+         k_ufield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
       else
-         k_ufield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
+         k_ufield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
       APX_COUNT_LAUNCH(c);
    }
 }
@@ -408,7 +421,7 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    bool tb = c->thole_table != 0;
    int grid = rows_grid<DF_G>(c);
 #define LAUNCH_DF(E, T)                                                                                                   \
-   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
+   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
       c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, ew ? 0 : 1)
    // (rows may all be empty for a tiny system: the kernel still initialises fd / fpd)
    if (ew && tb) LAUNCH_DF(true, true);
@@ -420,10 +433,10 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    if (c->nexcl > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       else
-         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       APX_COUNT_LAUNCH(c);
    }
@@ -446,23 +459,23 @@ void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const P
    const int* cu = sparse ? L.cntu.p : nullptr;
    double* s1 = excl ? nullptr : slot;
    if (tb)
-      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
          c->opt.njpolar, Rv, Z, s1, c->skip, T);
    else
-      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
          c->opt.njpolar, Rv, Z, s1, c->skip, T);
    APX_COUNT_LAUNCH(c);
    if (excl) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
             Rv, Z, c->skip);
       else
-         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
             Rv, Z, c->skip);
       APX_COUNT_LAUNCH(c);
       if (slot) {
-         k_dot_dp<<<(c->n + 127) / 128, 128, 0, c->stream>>>(c->n, Rv, Z, slot, c->skip);
+         k_dot_dp<<<(c->a1 - c->a0 + 127) / 128, 128, 0, c->stream>>>(c->a1 - c->a0, Rv + 2 * c->a0, Z + 2 * c->a0, slot, c->skip);
          APX_COUNT_LAUNCH(c);
       }
    }
@@ -472,6 +485,8 @@ void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const P
 void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp)
 {
    apx_pack_dp(c, rd, rp, c->pk_r);
+   if (c->dist.on)
+      apx_dist_halo(c, c->pk_r, c->stream);
    apx_precond_dp(c, c->pk_r, c->pk_z, nullptr);
    apx_unpack_dp(c, c->pk_z, zd, zp);
 }

@@ -6,6 +6,7 @@
 // Frame geometry is evaluated in double from the caller-order f64 coordinates (frames never use
 // periodic images: molecules are whole), results land directly in the SORTED SoA multipole arrays.
 #include "apx_internal.h"
+#include <algorithm>
 
 namespace {
 struct v3 {
@@ -139,11 +140,11 @@ __device__ __forceinline__ v3 tip_force_plane(v3 a, v3 b, double la, double dphi
 }
 
 template <bool DO_V>
-__global__ void k_torque(int n, const double* __restrict__ xyz, const int* __restrict__ perm, const int* __restrict__ inv,
+__global__ void k_torque(int a0, int n, const double* __restrict__ xyz, const int* __restrict__ perm, const int* __restrict__ inv,
    const int* __restrict__ zaxis, const real* __restrict__ trq, fixed_t* __restrict__ gx, fixed_t* __restrict__ gy,
    fixed_t* __restrict__ gz, double* __restrict__ vir)
 {
-   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   int s = a0 + blockIdx.x * blockDim.x + threadIdx.x;      // owned atoms a0 <= s < n
    double v[6] = {0, 0, 0, 0, 0, 0};
    if (s < n) {
       int i = perm[s];
@@ -288,11 +289,11 @@ void apx_rotpole(apx_ctx* c)
 // dbuf layout: see mplar.cu (vir_trq accumulates into dbuf[8..13])
 void apx_torque(apx_ctx* c, bool do_v)
 {
-   int n = c->n;
+   int no = std::max(1, c->a1 - c->a0);
    double* vir = c->dbuf.p + 8;
    if (do_v)
-      k_torque<true><<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->xyz_d, c->perm, c->inv, c->zaxis, c->trq, c->gx, c->gy, c->gz, vir);
+      k_torque<true><<<(no + 127) / 128, 128, 0, c->stream>>>(c->a0, c->a1, c->xyz_d, c->perm, c->inv, c->zaxis, c->trq, c->gx, c->gy, c->gz, vir);
    else
-      k_torque<false><<<(n + 127) / 128, 128, 0, c->stream>>>(n, c->xyz_d, c->perm, c->inv, c->zaxis, c->trq, c->gx, c->gy, c->gz, vir);
+      k_torque<false><<<(no + 127) / 128, 128, 0, c->stream>>>(c->a0, c->a1, c->xyz_d, c->perm, c->inv, c->zaxis, c->trq, c->gx, c->gy, c->gz, vir);
    APX_COUNT_LAUNCH(c);
 }

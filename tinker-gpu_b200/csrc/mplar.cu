@@ -17,6 +17,7 @@
 #include "pairmath.cuh"
 #include "rows.cuh"
 #include <cmath>
+#include <algorithm>
 
 #define FULL 0xffffffffu
 #define SHF(v, src) __shfl_sync(FULL, (v), (src))
@@ -73,7 +74,7 @@ __device__ __forceinline__ void atomic_fixed_d(fixed_t* p, double v)
 }
 
 struct MplarArgs {
-   int n;
+   int a0, a1;           // owned sorted range
    Box box;
    real cut2, aewald, f;
    const int* vstart;     // directed neighbor rows (rows.cu)
@@ -105,10 +106,9 @@ struct MplarArgs {
 template <bool DO_G, bool EWALD, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
 {
-   const int n = A.n;
    double em = 0, ep = 0, vxx = 0, vxy = 0, vxz = 0, vyy = 0, vyz = 0, vzz = 0;
    int nem = 0;
-   ROWS_FOREACH_ATOM(G, n, i, l, act)
+   ROWS_FOREACH_ATOM(G, A.a0, A.a1, i, l, act)
    {
       const real4 pi = A.posd[i];
       const real4 qi = A.tpj[i];
@@ -248,14 +248,17 @@ __global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs 
       real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
       apx_image(A.box, dx, dy, dz);
       real r2 = dx * dx + dy * dy + dz * dz;
-      if (r2 <= A.cut2) {
+      // several GPUs: a pair is handled by the owner(s) of its atoms, each writing only to its own
+      // atom; the owner of p.i also books the pair's energy, virial and count
+      const bool own_i = p.i >= A.a0 && p.i < A.a1, own_k = p.k >= A.a0 && p.k < A.a1;
+      if (r2 <= A.cut2 && (own_i || own_k)) {
          real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
          real rr[6], B[6];
          radial_coulomb<6>(rinv, rr2, rr);
          V3 R = v3(dx, dy, dz);
          Mpole mi = load_mpole(A.mp0, A.mp1, A.mp2, p.i), mk = load_mpole(A.mp0, A.mp1, A.mp2, p.k);
          V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0), tqk = v3(0, 0, 0);
-         if (A.do_m ? p.m == (real)-1 : p.p == (real)-1)
+         if (own_i && (A.do_m ? p.m == (real)-1 : p.p == (real)-1))
             dn = -1;
          if (A.do_m && p.m != 0) {
             #pragma unroll
@@ -263,7 +266,8 @@ __global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs 
                B[q] = p.m * rr[q];
             V3 g1, t1, t2;
             real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
-            em = (double)(A.f * U);
+            if (own_i)
+               em = (double)(A.f * U);
             if (DO_G) {
                g += g1;
                tqi += t1;
@@ -293,7 +297,7 @@ __global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs 
                V3 uk = pass == 0 ? udk : upk, ui = pass == 0 ? udi : upi;
                V3 g1, g2, t1, t2;
                real U = pair_mu<DO_G>(R, mi, uk, B, g1, t1) + pair_um<DO_G>(R, ui, mk, B, g2, t2);
-               if (pass == 0 && A.pair_ep)
+               if (pass == 0 && A.pair_ep && own_i)
                   ep = (double)(A.f * U);
                if (DO_G) {
                   g += g1 + g2;
@@ -310,11 +314,15 @@ __global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs 
          }
          if (DO_G) {
             g = A.f * g;
-            atomic_fixed3(A.gx, A.gy, A.gz, p.i, (real)-1 * g);
-            atomic_fixed3(A.gx, A.gy, A.gz, p.k, g);
-            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.i, A.f * tqi);
-            atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.k, A.f * tqk);
-            if (A.do_v) {
+            if (own_i) {
+               atomic_fixed3(A.gx, A.gy, A.gz, p.i, (real)-1 * g);
+               atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.i, A.f * tqi);
+            }
+            if (own_k) {
+               atomic_fixed3(A.gx, A.gy, A.gz, p.k, g);
+               atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.k, A.f * tqk);
+            }
+            if (A.do_v && own_i) {
                v[0] = (double)(R.x * g.x);
                v[1] = (double)((real)0.5 * (R.y * g.x + R.x * g.y));
                v[2] = (double)((real)0.5 * (R.z * g.x + R.x * g.z));
@@ -673,10 +681,13 @@ RecipX make_recipx(apx_ctx* c)
 
 void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
+void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p);
 
 void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out)
 {
-   const int n = c->n, n3 = 3 * n;
+   const int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0, n3 = 3 * no;      // per-atom passes run on the owned range
+   const bool dist = c->dist.on != 0;
    cudaStream_t st = c->stream;
    const bool do_e = vers & APX_ENERGY, do_g = vers & APX_GRAD, do_v = (vers & APX_VIRIAL) && do_g, do_a = vers & APX_ANALYZ;
    do_m = do_m && c->opt.use_mpole;
@@ -696,9 +707,16 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    } else if (ewald) {
       apx_pme_mpole(c, true);
    }
+   if (dist && do_p) {
+      // converged dipoles of the neighbours owned by other GPUs
+      apx_pack_dp(c, c->uind, c->uinp, c->pk_p);
+      apx_dist_halo(c, c->pk_p, st);
+      apx_unpack_dp_all(c, c->pk_p, c->uind, c->uinp);
+   }
    // ---- real space
    MplarArgs A;
-   A.n = n;
+   A.a0 = c->a0;
+   A.a1 = c->a1;
    A.box = c->box;
    A.cut2 = (real)(c->opt.cutoff * c->opt.cutoff);
    A.aewald = (real)c->opt.aewald;
@@ -747,44 +765,57 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    // ---- reciprocal space + self
    if (ewald) {
       RecipX X = make_recipx(c);
-      int g = (n + 127) / 128;
+      int g = std::max(1, (no + 127) / 128);
+      const size_t o = (size_t)a0;
       if (do_m) {
          if (do_g)
-            k_recip_mpole<true><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0, c->mp1, c->mp2, c->fmp, c->fphi,
-               c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+            k_recip_mpole<true><<<g, 128, 0, st>>>(no, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0 + o, c->mp1 + o, c->mp2 + o,
+               c->fmp + 10 * o, c->fphi + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
          else
-            k_recip_mpole<false><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0, c->mp1, c->mp2, c->fmp, c->fphi,
-               c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+            k_recip_mpole<false><<<g, 128, 0, st>>>(no, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0 + o, c->mp1 + o, c->mp2 + o,
+               c->fmp + 10 * o, c->fphi + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
          APX_COUNT_LAUNCH(c);
       }
       if (do_p && (do_g || pair_ep)) {
          if (do_g)
             apx_pme_uind_fphi(c, c->uind, c->uinp, true);
          if (do_g)
-            k_recip_polar<true><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0, c->mp1,
-               c->mp2, c->fmp, c->fphi, c->uind, c->uinp, c->fphid, c->fphip, c->fphidp, c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+            k_recip_polar<true><<<g, 128, 0, st>>>(no, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0 + o,
+               c->mp1 + o, c->mp2 + o, c->fmp + 10 * o, c->fphi + 20 * o, c->uind + 3 * o, c->uinp + 3 * o, c->fphid + 10 * o,
+               c->fphip + 10 * o, c->fphidp + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
          else
-            k_recip_polar<false><<<g, 128, 0, st>>>(n, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0, c->mp1,
-               c->mp2, c->fmp, c->fphi, c->uind, c->uinp, c->fphid, c->fphip, c->fphidp, c->gx, c->gy, c->gz, c->trqf, c->dbuf);
+            k_recip_polar<false><<<g, 128, 0, st>>>(no, X, c->f_elec, (real)c->opt.aewald, pair_ep, do_v, c->opt.poltyp_mutual, c->mp0 + o,
+               c->mp1 + o, c->mp2 + o, c->fmp + 10 * o, c->fphi + 20 * o, c->uind + 3 * o, c->uinp + 3 * o, c->fphid + 10 * o,
+               c->fphip + 10 * o, c->fphidp + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
          APX_COUNT_LAUNCH(c);
          if (do_v) {
             // (M + up) x (M + ud) structure-factor product
-            k_add_dipole<<<g, 128, 0, st>>>(n, c->mp0, c->uinp, c->mpx_a);
-            k_add_dipole<<<g, 128, 0, st>>>(n, c->mp0, c->uind, c->mpx_b);
+            k_add_dipole<<<g, 128, 0, st>>>(no, c->mp0 + o, c->uinp + 3 * o, c->mpx_a + o);
+            k_add_dipole<<<g, 128, 0, st>>>(no, c->mp0 + o, c->uind + 3 * o, c->mpx_b + o);
             c->stats.kernel_launches += 2;
             apx_pme_cross_virial(c, c->mpx_a, c->mpx_b, c->dbuf.p + D_VIR_CROSS);
          }
       }
    }
    if (do_p && do_e && !pair_ep) {
-      k_ep_dot<<<(n3 + 255) / 256, 256, 0, st>>>(n3, c->f_elec, c->tpj, c->uind, c->udirp, c->dbuf);
+      k_ep_dot<<<std::max(1, (n3 + 255) / 256), 256, 0, st>>>(n3, c->f_elec, c->tpj + a0, c->uind + 3 * (size_t)a0, c->udirp + 3 * (size_t)a0,
+         c->dbuf);
       APX_COUNT_LAUNCH(c);
    }
    // ---- torques -> forces
    if (do_g) {
-      k_trq_to_real<<<(n3 + 255) / 256, 256, 0, st>>>(n3, c->trqf, c->trq);
+      k_trq_to_real<<<std::max(1, (n3 + 255) / 256), 256, 0, st>>>(n3, c->trqf + 3 * (size_t)a0, c->trq + 3 * (size_t)a0);
       APX_COUNT_LAUNCH(c);
       apx_torque(c, do_v);
+   }
+   if (dist) {
+      // every GPU holds partial sums: forces on frame atoms may belong to a neighbour's slab
+      if (do_g)
+         apx_dist_allreduce_u64(c, c->gx.p, (size_t)(c->gz.p + c->npad - c->gx.p));
+      apx_dist_allreduce_u64(c, c->ebuf.p, 8);
+      apx_dist_allreduce_f64(c, c->dbuf.p, D_TOTAL);
+      if (do_a)
+         apx_dist_allreduce_i32(c, c->cnt.p, 4);
    }
    // ---- reductions to the host (energy.cpp:334-384)
    fixed_t eb[8];

@@ -42,17 +42,33 @@ __device__ __forceinline__ void wrap_pos(const Box& b, double x, double y, doubl
    wz = (real)(f1 * (double)b.l[6] + f2 * (double)b.l[7] + f3 * (double)b.l[8]);
 }
 
-__global__ void k_sortkeys(int n, Box b, const double* __restrict__ xyz, unsigned* __restrict__ key, int* __restrict__ val)
+// nslab > 1 (several GPUs): the key's top bits are the z-slab of the atom in PME grid coordinates
+// (w3 = f3 + 1/2 mod 1, the coordinate k_theta_fill uses), below them a 27-bit Morton code -- every
+// GPU's atoms are then one contiguous sorted range and sit on that GPU's planes of the grid
+__global__ void k_sortkeys(int n, Box b, int nslab, const double* __restrict__ xyz, unsigned* __restrict__ key, int* __restrict__ val,
+   real* __restrict__ w3)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n)
       return;
    real wx, wy, wz, fx, fy, fz;
    wrap_pos(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], wx, wy, wz, fx, fy, fz);
-   unsigned qx = min(1023u, (unsigned)(fx * 1024));
-   unsigned qy = min(1023u, (unsigned)(fy * 1024));
-   unsigned qz = min(1023u, (unsigned)(fz * 1024));
-   key[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+   if (nslab <= 1) {
+      unsigned qx = min(1023u, (unsigned)(fx * 1024));
+      unsigned qy = min(1023u, (unsigned)(fy * 1024));
+      unsigned qz = min(1023u, (unsigned)(fz * 1024));
+      key[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+   } else {
+      real w = fz + (real)0.5;
+      w -= floor(w);
+      if (w >= 1) w = 0;
+      unsigned slab = min((unsigned)(nslab - 1), (unsigned)(w * nslab));
+      unsigned qx = min(511u, (unsigned)(fx * 512));
+      unsigned qy = min(511u, (unsigned)(fy * 512));
+      unsigned qz = min(511u, (unsigned)(fz * 512));
+      key[i] = (slab << 27) | spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+      w3[i] = w;
+   }
    val[i] = i;
 }
 
@@ -196,13 +212,21 @@ void apx_list_refresh(apx_ctx* c, bool force)
    apx_pcg_graphs_invalidate(c);      // row buffers may be reallocated below
    cudaEventRecord(c->ev2, c->stream);
    // 1. sort along the Morton curve
-   k_sortkeys<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->box, c->xyz_d, c->sortkey, c->permtmp);
+   const int nslab = c->dist.on ? c->dist.world : 1;
+   if (nslab > 1)
+      c->w3.ensure(n);
+   k_sortkeys<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->box, nslab, c->xyz_d, c->sortkey, c->permtmp, c->w3);
    size_t need = 0;
    cub::DeviceRadixSort::SortPairs(nullptr, need, c->sortkey.p, c->sortkey2.p, c->permtmp.p, c->perm.p, n, 0, 30, c->stream);
    if (need > c->cubtmp.cap)
       c->cubtmp.ensure(need);
    need = c->cubtmp.cap;
    cub::DeviceRadixSort::SortPairs(c->cubtmp.p, need, c->sortkey.p, c->sortkey2.p, c->permtmp.p, c->perm.p, n, 0, 30, c->stream);
+   // ownership of the sorted order: everything on one GPU, or this GPU's slab + the halo plan
+   if (c->dist.on)
+      apx_dist_after_sort(c);
+   else
+      c->a0 = 0, c->a1 = n;
    // 2. sorted copies of per-atom data
    int g = (c->npad + 255) / 256;
    k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);

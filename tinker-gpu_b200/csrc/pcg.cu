@@ -172,12 +172,20 @@ void apx_from_sorted(apx_ctx* c, const real* in, double* out_dev)
    APX_COUNT_LAUNCH(c);
 }
 
+// (owned range only; apx_unpack_dp_all also writes the halo atoms)
 void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out)
 {
-   k_pack_dp<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, d, p, out);
+   const int a0 = c->a0, no = c->a1 - c->a0;
+   k_pack_dp<<<(no + 255) / 256, 256, 0, c->stream>>>(no, d + 3 * a0, p + 3 * a0, out + 2 * a0);
    APX_COUNT_LAUNCH(c);
 }
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p)
+{
+   const int a0 = c->a0, no = c->a1 - c->a0;
+   k_unpack_dp<<<(no + 255) / 256, 256, 0, c->stream>>>(no, in + 2 * a0, d + 3 * a0, p + 3 * a0);
+   APX_COUNT_LAUNCH(c);
+}
+void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p)
 {
    k_unpack_dp<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, in, d, p);
    APX_COUNT_LAUNCH(c);
@@ -186,12 +194,12 @@ void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p)
 // full dfield into c->field (d) and c->fieldp (p), then udir/udirp and the initial guess
 void apx_dfield_full(apx_ctx* c, bool want_ev)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    if (c->opt.use_ewald)
       apx_pme_mpole(c, want_ev);                 // ASSIGNS c->field = recip + self
    apx_dfield_real(c, c->field, c->fieldp);      // adds to (Ewald) or assigns (no Ewald) field; zeroes fieldp first
-   k_udir<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->tpj, c->field, c->fieldp, c->udir, c->udirp, c->uind, c->uinp, c->pk_p,
-      c->opt.pcgguess ? 1 : 0);
+   k_udir<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->tpj + a0, c->field + 3 * a0, c->fieldp + 3 * a0, c->udir + 3 * a0,
+      c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0, c->opt.pcgguess ? 1 : 0);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -200,6 +208,8 @@ void apx_dfield_full(apx_ctx* c, bool want_ev)
 static void field_of_dp(apx_ctx* c, const real4* U, bool spread)
 {
    cudaStream_t st = c->stream;
+   if (c->dist.on)
+      apx_dist_halo(c, const_cast<real4*>(U), st);      // neighbours' dipoles from the GPUs that own them
    CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
    CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
    apx_ufield_real_dp(c, c->stream2, U, c->pk_f);
@@ -261,9 +271,10 @@ void apx_pcg_graphs_invalidate(apx_ctx* c)
 void apx_induce_impl(apx_ctx* c)
 {
    const int n = c->n, n3 = 3 * n;
-   const int g1 = (n + 255) / 256;
+   const int a0 = c->a0, no = c->a1 - c->a0;      // owned range: every per-atom pass below runs on it
+   const int g1 = (no + 255) / 256;
+   const bool dist = c->dist.on != 0;
    cudaStream_t st = c->stream;
-   (void)n3;
    const bool ewald = c->opt.use_ewald != 0;
    if (!c->mpole_inited)
       apx_rotpole(c);
@@ -279,8 +290,9 @@ void apx_induce_impl(apx_ctx* c)
    c->induced_valid = 1;
    if (!c->opt.poltyp_mutual) {
       // DIRECT polarization: u = alpha E
-      CUDA_CHECK(cudaMemcpyAsync(c->uind.p, c->udir.p, sizeof(real) * n3, cudaMemcpyDeviceToDevice, st));
-      CUDA_CHECK(cudaMemcpyAsync(c->uinp.p, c->udirp.p, sizeof(real) * n3, cudaMemcpyDeviceToDevice, st));
+      (void)n3;
+      CUDA_CHECK(cudaMemcpyAsync(c->uind.p + 3 * a0, c->udir.p + 3 * a0, sizeof(real) * 3 * no, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(c->uinp.p + 3 * a0, c->udirp.p + 3 * a0, sizeof(real) * 3 * no, cudaMemcpyDeviceToDevice, st));
       cudaEventRecord(c->ev1, st);
       CUDA_CHECK(cudaStreamSynchronize(st));
       cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
@@ -291,7 +303,7 @@ void apx_induce_impl(apx_ctx* c)
    static_assert(PCG_SLOT == 96, "arena_p in apx_api.cu is sized for 96 doubles per iteration");
    CUDA_CHECK(cudaMemsetAsync(c->arena_p.p, 0, c->arena_p_bytes, st));      // scal + flags
    double* result = c->scal.p + (size_t)PCG_SLOT * (politer + 3);
-   const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nfft3 * sizeof(cplx) / sizeof(real4) : 0;
+   const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nzl * sizeof(cplx) / sizeof(real4) : 0;
 
    // r0 = -T u0  (pcgguess; k_udir left u0 packed in pk_p) or E (no guess; k_udir left E packed in pk_p)
    if (c->opt.pcgguess) {
@@ -301,15 +313,19 @@ void apx_induce_impl(apx_ctx* c)
       if (ewald)
          apx_pme_gather_dp(c, 1, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_r, nullptr);
       else {
-         CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p, c->pk_f.p, sizeof(real4) * 2 * n, cudaMemcpyDeviceToDevice, st));
-         k_mask_dp<<<g1, 256, 0, st>>>(n, c->tpj, c->pk_r);
+         CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_f.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
+         k_mask_dp<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->pk_r + 2 * a0);
          APX_COUNT_LAUNCH(c);
       }
    } else {
-      CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p, c->pk_p.p, sizeof(real4) * 2 * n, cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_p.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
    }
    // z0 = M r0, r0.z0 -> slot of iteration 1 (whose K1 sets p = z0)
+   if (dist)
+      apx_dist_halo(c, c->pk_r, st);
    apx_precond_dp(c, c->pk_r, c->pk_z, c->scal.p);
+   if (dist)
+      apx_dist_allreduce_f64(c, c->scal.p, 2 * PCG_NSUB);
    if (ewald)
       apx_pme_zero_grid(c);
 
@@ -323,25 +339,33 @@ void apx_induce_impl(apx_ctx* c)
    T.result = result, T.flags = c->flags, T.ud = c->uind, T.up = c->uinp;
    auto enqueue_iteration = [&](int it) {
       double* slot = c->scal.p + (size_t)PCG_SLOT * (it - 1);
-      k_pcg_dir<<<g1, 256, 0, st>>>(n, c->flags, c->pk_p, c->pk_z, it >= 2 ? slot - PCG_SLOT : nullptr, slot);
+      k_pcg_dir<<<g1, 256, 0, st>>>(no, c->flags, c->pk_p + 2 * a0, c->pk_z + 2 * a0, it >= 2 ? slot - PCG_SLOT : nullptr, slot);
       APX_COUNT_LAUNCH(c);
       field_of_dp(c, c->pk_p, true);
       if (ewald)
          apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot);
       else {
-         k_nonewald_ap<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_f, c->pk_v, slot);
+         k_nonewald_ap<<<g1, 256, 0, st>>>(no, c->flags, c->tpj + a0, c->pk_p + 2 * a0, c->pk_f + 2 * a0, c->pk_v + 2 * a0, slot);
          APX_COUNT_LAUNCH(c);
       }
-      k_pcg_update<<<g1, 256, 0, st>>>(n, c->flags, c->tpj, c->pk_p, c->pk_v, c->pk_r, c->uind, c->uinp, slot, (real4*)c->qgrid.p,
-         ngrid4);
+      if (dist)
+         apx_dist_allreduce_f64(c, slot + 2 * PCG_NSUB, 2 * PCG_NSUB);        // p.Ap over all GPUs
+      k_pcg_update<<<g1, 256, 0, st>>>(no, c->flags, c->tpj + a0, c->pk_p + 2 * a0, c->pk_v + 2 * a0, c->pk_r + 2 * a0,
+         c->uind + 3 * a0, c->uinp + 3 * a0, slot, (real4*)c->qgrid.p, ngrid4);
       APX_COUNT_LAUNCH(c);
+      if (dist) {
+         apx_dist_allreduce_f64(c, slot + 4 * PCG_NSUB, 2 * PCG_NSUB);        // r.r
+         apx_dist_halo(c, c->pk_r, st);                                       // residuals of the preconditioner's neighbours
+      }
       T.it = it;
       T.slot = slot;
       apx_precond_dp(c, c->pk_r, c->pk_z, slot + PCG_SLOT, &T);
+      if (dist)
+         apx_dist_allreduce_f64(c, slot + PCG_SLOT, 2 * PCG_NSUB);            // r.z entering the next iteration
    };
    while (!done) {
       int nit = std::min(batch, politer - iter);
-      if (c->use_graph) {
+      if (c->use_graph && !dist) {
          // one CUDA graph per (first iteration, batch length): the fork/join with the second stream and
          // every launch of the batch replay as a single submission
          apx_ctx::PcgGraph* G = nullptr;

@@ -136,9 +136,16 @@ __device__ __forceinline__ Stencil load_stencil(const real4* __restrict__ theta,
 }
 
 __device__ __forceinline__ int wrapi(int i, int n) { return i >= n ? i - n : i; }
+// local plane of global plane (i3 + iz): a GPU holds planes zbase .. zbase+nzl-1 (mod n3) of the grid;
+// on one GPU zbase = 0 and nzl = n3
+__device__ __forceinline__ int zlocal(int i, int n3, int zbase)
+{
+   int z = wrapi(i, n3) - zbase;
+   return z < 0 ? z + n3 : z;
+}
 
 // --- spread ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, int n2, int n3,
+__global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
    const real4* __restrict__ theta, const real4* __restrict__ mp0, const real4* __restrict__ mp1, const real2* __restrict__ mp2,
    real* __restrict__ fmp_out, cplx* __restrict__ grid)
 {
@@ -182,7 +189,9 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, in
       const real t0 = t[0], t1 = t[1], t2 = t[2], u0 = u[0], u1 = u[1], u2 = u[2], v0 = v[0], v1 = v[1], v2 = v[2];
       const real val = fm[0] * t0 * u0 * v0 + fm[1] * t1 * u0 * v0 + fm[2] * t0 * u1 * v0 + fm[3] * t0 * u0 * v1 + fm[4] * t2 * u0 * v0
          + fm[5] * t0 * u2 * v0 + fm[6] * t0 * u0 * v2 + fm[7] * t1 * u1 * v0 + fm[8] * t1 * u0 * v1 + fm[9] * t0 * u1 * v1;
-      atomicAdd(&grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)].x, val);
+      const int zl = zlocal(st.i3 + iz, n3, zbase);
+      if (zl < nzl)
+         atomicAdd(&grid[((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)].x, val);
    }
 }
 
@@ -224,7 +233,8 @@ __device__ __forceinline__ Stencil load_stencil_lg(const real4* __restrict__ the
 
 // spread of a packed (d,p) dipole pair array (dp.cuh): d -> real part, p -> imaginary part
 template <int LG>
-__global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, const real4* __restrict__ theta,
+__global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
+   const real4* __restrict__ theta,
    const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
 {
    if (skip && skip[1])
@@ -254,7 +264,10 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n
       const real w100 = t[1] * u[0] * v[0], w010 = t[0] * u[1] * v[0], w001 = t[0] * u[0] * v[1];
       const real vd = fd[0] * w100 + fd[1] * w010 + fd[2] * w001;
       const real vp = fp[0] * w100 + fp[1] * w010 + fp[2] * w001;
-      cplx* g = &grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
+      const int zl = zlocal(st.i3 + iz, n3, zbase);
+      if (zl >= nzl)
+         continue;
+      cplx* g = &grid[((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
 #ifdef APX_DOUBLE
       atomicAdd(&g->x, vd);
       atomicAdd(&g->y, vp);
@@ -265,14 +278,16 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n
 }
 
 // --- influence function ------------------------------------------------------------------------
-__global__ void k_make_qfac(int n1, int n2, int n3, Box box, real pterm, real volterm, const real* __restrict__ bs1,
+// (all three kernels below index a slab [k3][k2 in y0..y0+ny)[k1] of the transformed grid: the whole
+//  grid on one GPU, the rows this GPU holds after the transpose of the slab FFT otherwise)
+__global__ void k_make_qfac(int n1, int n2, int n3, int y0, int ny, Box box, real pterm, real volterm, const real* __restrict__ bs1,
    const real* __restrict__ bs2, const real* __restrict__ bs3, real* __restrict__ qfac)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   int ntot = n1 * n2 * n3;
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   size_t ntot = (size_t)n1 * ny * n3;
    if (i >= ntot)
       return;
-   int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+   int k3 = (int)(i / ((size_t)n1 * ny)), j = (int)(i - (size_t)k3 * n1 * ny), k2 = y0 + j / n1, k1 = j % n1;
    int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
    int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
    int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
@@ -282,14 +297,14 @@ __global__ void k_make_qfac(int n1, int n2, int n3, Box box, real pterm, real vo
    double hsq = h1 * h1 + h2 * h2 + h3 * h3;
    double term = -(double)pterm * hsq;
    double e = 0;
-   if (i != 0 && term > -50.0)
+   if ((k1 | k2 | k3) != 0 && term > -50.0)
       e = exp(term) / ((double)volterm * hsq * (double)bs1[k1] * (double)bs2[k2] * (double)bs3[k3]);
    qfac[i] = (real)e;
 }
 
-__global__ void k_conv(int ntot, const real* __restrict__ qfac, cplx* __restrict__ grid)
+__global__ void k_conv(size_t ntot, const real* __restrict__ qfac, cplx* __restrict__ grid)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= ntot)
       return;
    real f = qfac[i];
@@ -300,17 +315,17 @@ __global__ void k_conv(int ntot, const real* __restrict__ qfac, cplx* __restrict
 }
 
 // multiply + reciprocal energy / virial of |Q|^2 (pmeConv<DO_E,DO_V>); out[0]=e, out[1..6]=vxx,vxy,vxz,vyy,vyz,vzz
-__global__ void k_conv_ev(int n1, int n2, int n3, Box box, real pterm, real felec, const real* __restrict__ qfac,
+__global__ void k_conv_ev(int n1, int n2, int n3, int y0, int ny, Box box, real pterm, real felec, const real* __restrict__ qfac,
    cplx* __restrict__ grid, double* __restrict__ out)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   int ntot = n1 * n2 * n3;
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   size_t ntot = (size_t)n1 * ny * n3;
    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
    if (i < ntot) {
       real f = qfac[i];
       cplx g = grid[i];
       if (f != 0) {
-         int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+         int k3 = (int)(i / ((size_t)n1 * ny)), j = (int)(i - (size_t)k3 * n1 * ny), k2 = y0 + j / n1, k1 = j % n1;
          int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
          int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
          int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
@@ -355,16 +370,16 @@ __global__ void k_conv_ev(int n1, int n2, int n3, Box box, real pterm, real fele
 }
 
 // structure-factor cross product of two transformed grids (epolarEwaldRecipSelfVirial_cu5)
-__global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real felec, const real* __restrict__ qfac,
+__global__ void k_cross_virial(int n1, int n2, int n3, int y0, int ny, Box box, real pterm, real felec, const real* __restrict__ qfac,
    const cplx* __restrict__ ga, const cplx* __restrict__ gb, double* __restrict__ out)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   int ntot = n1 * n2 * n3;
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   size_t ntot = (size_t)n1 * ny * n3;
    double acc[6] = {0, 0, 0, 0, 0, 0};
    if (i < ntot) {
       real f = qfac[i];
       if (f != 0) {
-         int k3 = i / (n1 * n2), j = i - k3 * n1 * n2, k2 = j / n1, k1 = j - k2 * n1;
+         int k3 = (int)(i / ((size_t)n1 * ny)), j = (int)(i - (size_t)k3 * n1 * ny), k2 = y0 + j / n1, k1 = j % n1;
          int r1 = k1 < (n1 + 1) / 2 ? k1 : k1 - n1;
          int r2 = k2 < (n2 + 1) / 2 ? k2 : k2 - n2;
          int r3 = k3 < (n3 + 1) / 2 ? k3 : k3 - n3;
@@ -411,7 +426,7 @@ __global__ void k_cross_virial(int n1, int n2, int n3, Box box, real pterm, real
 // (the ufield gather with its fused epilogues is k_gather_dp below)
 // MODE 2: energy step: fphid[10], fphip[10], fphidp[20] stored
 template <int MODE>
-__global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, int n3, real selfterm,
+__global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl, real selfterm,
    const real4* __restrict__ theta, const cplx* __restrict__ grid, const real4* __restrict__ mp0, const real* __restrict__ ud,
    const real* __restrict__ up, real* __restrict__ out_a, real* __restrict__ out_b, real* __restrict__ out_c,
    const int* __restrict__ skip)
@@ -429,7 +444,8 @@ __global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, 
    real u[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
    if (lane < 25) {
       int iy = lane % 5, iz = lane / 5;
-      int base = (wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1;
+      const int zl = min(zlocal(st.i3 + iz, n3, zbase), nzl - 1);
+      size_t base = ((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1;
       #pragma unroll
       for (int ix = 0; ix < 5; ++ix) {
          cplx g = grid[base + wrapi(st.i1 + ix, n1)];
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(128) k_gather(int n, Xform X, int n1, int n2, 
 //   EPI 1: residual      R = field, zero where alpha == 0            (r0 = -T u0)
 //   EPI 2: PCG           V = U/alpha - field ; partial U.V -> slot   (pcgP1 + dots, src/cu/induce.cu)
 template <int EPI, int LG>
-__global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n2, int n3, real selfterm,
+__global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl, real selfterm,
    const real4* __restrict__ theta, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
    const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
    double* __restrict__ slot, const int* __restrict__ skip)
@@ -571,7 +587,8 @@ __global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n
    real fd[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
    for (int p = l; p < 125; p += LG) {
       const int iz = p / 25, iy = (p / 5) % 5, ix = p % 5;
-      const cplx g = grid[(wrapi(st.i3 + iz, n3) * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
+      const int zl = min(zlocal(st.i3 + iz, n3, zbase), nzl - 1);
+      const cplx g = grid[((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
       const real* t = sth[gib][0][ix];
       const real* u = sth[gib][1][iy];
       const real* v = sth[gib][2][iz];
@@ -742,7 +759,11 @@ inline real selfterm(apx_ctx* c)
    double a = c->opt.aewald;
    return (real)(4.0 / 3.0 * a * a * a / sqrt(M_PI));
 }
-inline size_t ntot(apx_ctx* c) { return (size_t)c->nfft1 * c->nfft2 * c->nfft3; }
+// elements of the grid this GPU holds in real space (all planes, or its slab + halo planes) and of
+// the transformed slab it multiplies by the influence function
+inline size_t nlocal(apx_ctx* c) { return (size_t)c->nfft1 * c->nfft2 * c->nzl; }
+inline size_t nconv(apx_ctx* c) { return (size_t)c->nfft1 * c->qny * c->nfft3; }
+inline cplx* conv_grid(apx_ctx* c) { return c->dist.on ? c->dist.tbuf.p : c->qgrid.p; }
 } // namespace
 
 void apx_pme_setup(apx_ctx* c)
@@ -754,19 +775,24 @@ void apx_pme_setup(apx_ctx* c)
    c->nfft3 = c->opt.nfft[2];
    if (c->opt.bsorder != 5)
       APX_THROW("only pme-order 5 is built (the reference hard-codes MAX_BSORDER 5, include/seq/bsplgen.h)");
-   size_t K = ntot(c);
-   c->qgrid.ensure(K);
-   c->qfac.ensure(K);
-   if (!c->plan_ok) {
+   if (c->dist.on) {
+      apx_dist_pme_setup(c);      // sets zbase, nzl, qy0, qny, the slab-FFT plans and buffers
+   } else {
+      c->zbase = 0, c->nzl = c->nfft3;
+      c->qy0 = 0, c->qny = c->nfft2;
+      if (!c->plan_ok) {
 #ifdef APX_DOUBLE
-      CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_Z2Z));
+         CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_Z2Z));
 #else
-      CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_C2C));
+         CUFFT_CHECK(cufftPlan3d(&c->plan, c->nfft3, c->nfft2, c->nfft1, CUFFT_C2C));
 #endif
-      CUFFT_CHECK(cufftSetStream(c->plan, c->stream));
-      c->plan_ok = 1;
+         CUFFT_CHECK(cufftSetStream(c->plan, c->stream));
+         c->plan_ok = 1;
+      }
+      apx_fft64_setup(c);
    }
-   apx_fft64_setup(c);
+   c->qgrid.ensure(nlocal(c));
+   c->qfac.ensure(nconv(c));
    int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
    DevBuf<real>* bs[3] = {&c->bsmod1, &c->bsmod2, &c->bsmod3};
    for (int d = 0; d < 3; ++d) {
@@ -778,19 +804,22 @@ void apx_pme_setup(apx_ctx* c)
    }
    double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
    double volterm = M_PI * (double)c->box.volume;
-   k_make_qfac<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, (real)volterm,
-      c->bsmod1, c->bsmod2, c->bsmod3, c->qfac);
+   size_t K = nconv(c);
+   k_make_qfac<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->qy0, c->qny, c->box, (real)pterm,
+      (real)volterm, c->bsmod1, c->bsmod2, c->bsmod3, c->qfac);
    APX_COUNT_LAUNCH(c);
 }
 
-// spline tables of the current positions; called whenever posd changes (nblist.cu)
+// spline tables of the current positions (owned atoms); called whenever posd changes (nblist.cu)
 void apx_pme_fill_theta(apx_ctx* c)
 {
    if (!c->opt.use_ewald)
       return;
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    c->theta.ensure(16 * (size_t)c->npad);
-   k_theta_fill<<<(4 * n + 127) / 128, 128, 0, c->stream>>>(n, c->box, c->nfft1, c->nfft2, c->nfft3, c->posd, c->theta);
+   if (no > 0)
+      k_theta_fill<<<(4 * no + 127) / 128, 128, 0, c->stream>>>(no, c->box, c->nfft1, c->nfft2, c->nfft3, c->posd + a0,
+         c->theta + 16 * (size_t)a0);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -799,39 +828,60 @@ void apx_pme_destroy(apx_ctx* c)
    if (c->plan_ok)
       cufftDestroy(c->plan);
    c->plan_ok = 0;
+   apx_dist_pme_destroy(c);
 }
 
 static void conv(apx_ctx* c, bool want_ev, double* out)
 {
-   size_t K = ntot(c);
+   size_t K = nconv(c);
+   cplx* g = conv_grid(c);
    if (want_ev) {
       double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
-      k_conv_ev<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, c->f_elec, c->qfac,
-         c->qgrid, out);
+      k_conv_ev<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->qy0, c->qny, c->box, (real)pterm,
+         c->f_elec, c->qfac, g, out);
    } else {
-      k_conv<<<(int)((K + 255) / 256), 256, 0, c->stream>>>((int)K, c->qfac, c->qgrid);
+      k_conv<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(K, c->qfac, g);
    }
    APX_COUNT_LAUNCH(c);
+}
+
+// forward transform of the spread grid / inverse transform back to real space (with the halo planes
+// of the slab decomposition when the grid is shared by several GPUs)
+static void fft_forward(apx_ctx* c)
+{
+   if (c->dist.on)
+      apx_dist_fft_forward(c, c->dist.tbuf);
+   else
+      fft(c, CUFFT_FORWARD);
+}
+static void fft_inverse(apx_ctx* c)
+{
+   if (c->dist.on)
+      apx_dist_fft_inverse(c, c->dist.tbuf);
+   else
+      fft(c, CUFFT_INVERSE);
 }
 
 // permanent multipoles: fills fmp, fphi and ASSIGNS field = recip + self part of dfield.
 // dbuf[16] = recip |Q|^2 energy, dbuf[17..22] = its virial (vir_m) when want_ev.
 void apx_pme_mpole(apx_ctx* c, bool want_ev)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
-   size_t K = ntot(c);
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->mp0, c->mp1, c->mp2,
-      c->fmp, c->qgrid);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
+   if (no > 0)
+      k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
+         c->mp0 + a0, c->mp1 + a0, c->mp2 + a0, c->fmp + 10 * (size_t)a0, c->qgrid);
    APX_COUNT_LAUNCH(c);
-   fft(c, CUFFT_FORWARD);
+   fft_forward(c);
    if (want_ev)
       CUDA_CHECK(cudaMemsetAsync(c->dbuf.p + 16, 0, 7 * sizeof(double), c->stream));
    conv(c, want_ev, c->dbuf.p + 16);
-   fft(c, CUFFT_INVERSE);
-   k_gather<0><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, c->mp0,
-      nullptr, nullptr, c->fphi, c->field, nullptr, nullptr);
+   fft_inverse(c);
+   if (no > 0)
+      k_gather<0><<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),
+         c->theta + 16 * (size_t)a0, c->qgrid, c->mp0 + a0, nullptr, nullptr, c->fphi + 20 * (size_t)a0, c->field + 3 * (size_t)a0, nullptr,
+         nullptr);
    APX_COUNT_LAUNCH(c);
    c->mpole_pme_valid = 1;
 }
@@ -839,42 +889,49 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
 // ---- mutual-field operator on packed dipole pairs (dp.cuh) ----
 void apx_pme_zero_grid(apx_ctx* c)
 {
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, ntot(c) * sizeof(cplx), c->stream));
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
 }
 
 // grid must be zero on entry
 void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
-   k_spread_dp<PME_LG><<<(n + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, U, c->qgrid, c->skip);
+   if (no > 0)
+      k_spread_dp<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
+         c->theta + 16 * (size_t)a0, U + 2 * (size_t)a0, c->qgrid, c->skip);
    APX_COUNT_LAUNCH(c);
 }
 
 // forward FFT, influence function, inverse FFT
 void apx_pme_convolve(apx_ctx* c)
 {
-   if (apx_fft64_usable(c)) {
+   if (!c->dist.on && apx_fft64_usable(c)) {
       apx_fft64_convolve(c);
       return;
    }
-   fft(c, CUFFT_FORWARD);
+   fft_forward(c);
    conv(c, false, nullptr);
-   fft(c, CUFFT_INVERSE);
+   fft_inverse(c);
 }
 
 // epi 0: fd/fp plain out ; 1: OUT = residual ; 2: OUT = Ap with partial dots into slot
 void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
-   int g = (n + PME_APB - 1) / PME_APB;
+   int g = (no + PME_APB - 1) / PME_APB;
+   if (g < 1)
+      g = 1;
 #define GATHER_DP(E)                                                                                                       \
-   k_gather_dp<E, PME_LG><<<g, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->tpj, c->qgrid, U, F,  \
-      fd, fp, OUT, slot, c->skip)
-   if (epi == 0) GATHER_DP(0);
-   else if (epi == 1) GATHER_DP(1);
-   else GATHER_DP(2);
+   k_gather_dp<E, PME_LG><<<g, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),           \
+      c->theta + 16 * (size_t)a0, c->tpj + a0, c->qgrid, U + 2 * (size_t)a0, F ? F + 2 * (size_t)a0 : nullptr,                 \
+      fd ? fd + 3 * (size_t)a0 : nullptr, fp ? fp + 3 * (size_t)a0 : nullptr, OUT ? OUT + 2 * (size_t)a0 : nullptr, slot, c->skip)
+   if (no > 0) {
+      if (epi == 0) GATHER_DP(0);
+      else if (epi == 1) GATHER_DP(1);
+      else GATHER_DP(2);
+   }
 #undef GATHER_DP
    APX_COUNT_LAUNCH(c);
 }
@@ -882,16 +939,19 @@ void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real
 // energy step: fphid, fphip (10 each) and fphidp (20) of the converged dipoles
 void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
-   size_t K = ntot(c);
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
    apx_pack_dp(c, ud, up, c->pk_p);
-   k_spread_dp<PME_LG><<<(n + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, c->pk_p, c->qgrid, nullptr);
+   if (no > 0)
+      k_spread_dp<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
+         c->theta + 16 * (size_t)a0, c->pk_p + 2 * (size_t)a0, c->qgrid, nullptr);
    APX_COUNT_LAUNCH(c);
    apx_pme_convolve(c);
-   k_gather<2><<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, selfterm(c), c->theta, c->qgrid, nullptr,
-      ud, up, c->fphid, c->fphip, c->fphidp, nullptr);
+   if (no > 0)
+      k_gather<2><<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),
+         c->theta + 16 * (size_t)a0, c->qgrid, nullptr, ud + 3 * (size_t)a0, up + 3 * (size_t)a0, c->fphid + 10 * (size_t)a0,
+         c->fphip + 10 * (size_t)a0, c->fphidp + 20 * (size_t)a0, nullptr);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -899,21 +959,24 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
 // (epolarEwaldRecipSelfVirial_cu3..5, src/cu/epolarrecip.cu:476-509)
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6)
 {
-   int n = c->n;
+   const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
-   size_t K = ntot(c);
-   c->qgrid2.ensure(K);
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, mpa, c->mp1, c->mp2, nullptr,
-      c->qgrid);
-   fft(c, CUFFT_FORWARD);
-   CUDA_CHECK(cudaMemcpyAsync(c->qgrid2.p, c->qgrid.p, K * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
-   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, K * sizeof(cplx), c->stream));
-   k_spread_mpole<<<(n + 3) / 4, 128, 0, c->stream>>>(n, X, c->nfft1, c->nfft2, c->nfft3, c->theta, mpb, c->mp1, c->mp2, nullptr,
-      c->qgrid);
-   fft(c, CUFFT_FORWARD);
+   size_t K = nconv(c);
+   DevBuf<cplx>& second = c->dist.on ? c->dist.tbuf2 : c->qgrid2;
+   second.ensure(K);
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
+   if (no > 0)
+      k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
+         mpa + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid);
+   fft_forward(c);
+   CUDA_CHECK(cudaMemcpyAsync(second.p, conv_grid(c), K * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+   CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
+   if (no > 0)
+      k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
+         mpb + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid);
+   fft_forward(c);
    double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
-   k_cross_virial<<<(int)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->box, (real)pterm, c->f_elec, c->qfac,
-      c->qgrid, c->qgrid2, out6);
+   k_cross_virial<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->qy0, c->qny, c->box, (real)pterm,
+      c->f_elec, c->qfac, conv_grid(c), second, out6);
    c->stats.kernel_launches += 3;
 }

@@ -13,83 +13,128 @@
 #include "apx_internal.h"
 #include "pairmath.cuh"
 #include <cub/cub.cuh>
+#include <algorithm>
 
 #define FULL 0xffffffffu
 
 namespace {
-// one warp per i-block; lane j keeps the running length of the row of atom 32*ib + j
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, Box b, real range, const real4* __restrict__ posd,
-   const real4* __restrict__ ctr, const real4* __restrict__ ext, int* __restrict__ vcnt, const int* __restrict__ vstart,
-   int* __restrict__ vnbr)
+#define RB_W 4      // warps sharing one i-block: each takes 32/RB_W of its atoms
+
+// bounding boxes of super-blocks (32 consecutive blocks = 1024 sorted atoms): first level of the
+// search, so a warp looks at nblk/32 boxes instead of nblk before it descends
+__global__ void k_super_boxes(int nblk, int nsb, const real4* __restrict__ ctr, const real4* __restrict__ ext,
+   real4* __restrict__ sctr, real4* __restrict__ sext)
 {
-   const int ib = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int sb = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const int lane = threadIdx.x & 31;
-   if (ib >= nblk)
+   if (sb >= nsb)
+      return;
+   const int kb = min(sb * 32 + lane, nblk - 1);
+   const real4 c = ctr[kb], e = ext[kb];
+   real lox = c.x - e.x, hix = c.x + e.x, loy = c.y - e.y, hiy = c.y + e.y, loz = c.z - e.z, hiz = c.z + e.z;
+   #pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      lox = min(lox, __shfl_xor_sync(FULL, lox, o));
+      hix = max(hix, __shfl_xor_sync(FULL, hix, o));
+      loy = min(loy, __shfl_xor_sync(FULL, loy, o));
+      hiy = max(hiy, __shfl_xor_sync(FULL, hiy, o));
+      loz = min(loz, __shfl_xor_sync(FULL, loz, o));
+      hiz = max(hiz, __shfl_xor_sync(FULL, hiz, o));
+   }
+   if (lane == 0) {
+      real4 oc, oe;
+      oc.x = (real)0.5 * (lox + hix), oc.y = (real)0.5 * (loy + hiy), oc.z = (real)0.5 * (loz + hiz), oc.w = 0;
+      oe.x = (real)0.5 * (hix - lox), oe.y = (real)0.5 * (hiy - loy), oe.z = (real)0.5 * (hiz - loz), oe.w = 0;
+      sctr[sb] = oc;
+      sext[sb] = oe;
+   }
+}
+
+__device__ __forceinline__ bool boxes_within(const Box& b, real4 ci, real4 ei, real4 ck, real4 ek, real range2)
+{
+   real dx = ck.x - ci.x, dy = ck.y - ci.y, dz = ck.z - ci.z;
+   apx_image(b, dx, dy, dz);
+   dx = max((real)0, fabs(dx) - ei.x - ek.x);
+   dy = max((real)0, fabs(dy) - ei.y - ek.y);
+   dz = max((real)0, fabs(dz) - ei.z - ek.z);
+   return dx * dx + dy * dy + dz * dz <= range2;
+}
+
+// RB_W warps per i-block; lane j of a warp keeps the running length of the row of atom 32*ib + j
+// (only the atoms of this warp's share, and only atoms inside the owned range [a0,a1))
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, int a0, int a1, Box b, real range,
+   const real4* __restrict__ posd, const real4* __restrict__ ctr, const real4* __restrict__ ext, const real4* __restrict__ sctr,
+   const real4* __restrict__ sext, int* __restrict__ vcnt, const int* __restrict__ vstart, int* __restrict__ vnbr)
+{
+   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int ib = a0 / 32 + gw / RB_W, sub = gw % RB_W;
+   const int lane = threadIdx.x & 31;
+   if (ib >= nblk || ib * 32 >= a1)
       return;
    const real range2 = range * range;
    const real4 ci = ctr[ib], ei = ext[ib];
    const int si = ib * 32 + lane;
    const real4 pi = posd[min(si, n - 1)];
-   const int ni = min(32, n - ib * 32);          // atoms in this i-block
+   // atoms of this i-block handled by this warp
+   const int q0 = max(sub * (32 / RB_W), a0 - ib * 32);
+   const int q1 = min(min((sub + 1) * (32 / RB_W), n - ib * 32), a1 - ib * 32);
+   if (q0 >= q1)
+      return;
    int mycount = 0;
    const int mybase = (FILL && si < n) ? vstart[si] : 0;
    const unsigned lt = (1u << lane) - 1;
-   for (int kb0 = 0; kb0 < nblk; kb0 += 32) {
-      int kb = kb0 + lane;
-      bool hit = false;
-      if (kb < nblk) {
-         real4 ck = ctr[kb], ek = ext[kb];
-         real dx = ck.x - ci.x, dy = ck.y - ci.y, dz = ck.z - ci.z;
-         apx_image(b, dx, dy, dz);
-         dx = max((real)0, fabs(dx) - ei.x - ek.x);
-         dy = max((real)0, fabs(dy) - ei.y - ek.y);
-         dz = max((real)0, fabs(dz) - ei.z - ek.z);
-         hit = dx * dx + dy * dy + dz * dz <= range2;
-      }
-      unsigned hm = __ballot_sync(FULL, hit);
-      while (hm) {
-         int j = __ffs(hm) - 1;
-         hm &= hm - 1;
-         int s = (kb0 + j) * 32 + lane;
-         real4 pk = posd[min(s, n - 1)];
-         bool in = false;
-         if (s < n) {
-            real dx = pk.x - ci.x, dy = pk.y - ci.y, dz = pk.z - ci.z;
-            apx_image(b, dx, dy, dz);
-            dx = max((real)0, fabs(dx) - ei.x);
-            dy = max((real)0, fabs(dy) - ei.y);
-            dz = max((real)0, fabs(dz) - ei.z);
-            in = dx * dx + dy * dy + dz * dz <= range2;
-         }
-         if (!__ballot_sync(FULL, in))
-            continue;
-         for (int q = 0; q < ni; ++q) {
-            real dx = pk.x - __shfl_sync(FULL, pi.x, q), dy = pk.y - __shfl_sync(FULL, pi.y, q),
-                 dz = pk.z - __shfl_sync(FULL, pi.z, q);
-            apx_image(b, dx, dy, dz);
-            bool ok = in && s != ib * 32 + q && dx * dx + dy * dy + dz * dz <= range2;
-            unsigned m = __ballot_sync(FULL, ok);
-            if (FILL) {
-               int off = __shfl_sync(FULL, mybase + mycount, q);
-               if (ok)
-                  vnbr[off + __popc(m & lt)] = s;
+   for (int sb0 = 0; sb0 < nsb; sb0 += 32) {
+      const int sb = sb0 + lane;
+      unsigned sm = __ballot_sync(FULL, sb < nsb && boxes_within(b, ci, ei, sctr[min(sb, nsb - 1)], sext[min(sb, nsb - 1)], range2));
+      while (sm) {
+         const int kb0 = (sb0 + __ffs(sm) - 1) * 32;
+         sm &= sm - 1;
+         const int kb = kb0 + lane;
+         unsigned hm = __ballot_sync(FULL, kb < nblk && boxes_within(b, ci, ei, ctr[min(kb, nblk - 1)], ext[min(kb, nblk - 1)], range2));
+         while (hm) {
+            int j = __ffs(hm) - 1;
+            hm &= hm - 1;
+            int s = (kb0 + j) * 32 + lane;
+            real4 pk = posd[min(s, n - 1)];
+            bool in = false;
+            if (s < n) {
+               real dx = pk.x - ci.x, dy = pk.y - ci.y, dz = pk.z - ci.z;
+               apx_image(b, dx, dy, dz);
+               dx = max((real)0, fabs(dx) - ei.x);
+               dy = max((real)0, fabs(dy) - ei.y);
+               dz = max((real)0, fabs(dz) - ei.z);
+               in = dx * dx + dy * dy + dz * dz <= range2;
             }
-            if (lane == q)
-               mycount += __popc(m);
+            if (!__ballot_sync(FULL, in))
+               continue;
+            for (int q = q0; q < q1; ++q) {
+               real dx = pk.x - __shfl_sync(FULL, pi.x, q), dy = pk.y - __shfl_sync(FULL, pi.y, q),
+                    dz = pk.z - __shfl_sync(FULL, pi.z, q);
+               apx_image(b, dx, dy, dz);
+               bool ok = in && s != ib * 32 + q && dx * dx + dy * dy + dz * dz <= range2;
+               unsigned m = __ballot_sync(FULL, ok);
+               if (FILL) {
+                  int off = __shfl_sync(FULL, mybase + mycount, q);
+                  if (ok)
+                     vnbr[off + __popc(m & lt)] = s;
+               }
+               if (lane == q)
+                  mycount += __popc(m);
+            }
          }
       }
    }
-   if (!FILL && si < n)
+   if (!FILL && lane >= q0 && lane < q1)
       vcnt[si] = mycount;
 }
 
 // one warp per atom: two sweeps over its Verlet row (positions stay in L1 between them)
-__global__ void __launch_bounds__(128) k_rows_compact(int n, Box b, real cut2, real ucut2, const real4* __restrict__ posd,
+__global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real cut2, real ucut2, const real4* __restrict__ posd,
    const int* __restrict__ vstart, const int* __restrict__ vnbr, int* __restrict__ nbr, int* __restrict__ cnt,
    int* __restrict__ cntu, unsigned long long* __restrict__ total)
 {
-   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int i = a0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);     // owned atoms a0 <= i < n
    const int lane = threadIdx.x & 31;
    if (i >= n)
       return;
@@ -134,16 +179,22 @@ __global__ void __launch_bounds__(128) k_rows_compact(int n, Box b, real cut2, r
 void apx_rows_build(apx_ctx* c)
 {
    RowList& L = c->rows;
-   const int n = c->n, nblk = c->nblk;
-   const int grid = (nblk * 32 + 127) / 128;
+   const int n = c->n, nblk = c->nblk, nsb = (nblk + 31) / 32;
+   const int a0 = c->a0, a1 = c->a1;
+   const int nib = a1 > a0 ? (a1 + 31) / 32 - a0 / 32 : 0;      // i-blocks that hold owned atoms
+   const int grid = std::max(1, (nib * RB_W * 32 + 127) / 128);
    const real range = c->list_cutoff + c->list_buffer;
    L.vstart.ensure(n + 1);
    L.vcnt.ensure(n + 1);
    L.cnt.ensure(n);
    L.cntu.ensure(n);
    L.total.ensure(2);
-   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.vcnt, nullptr, nullptr);
-   CUDA_CHECK(cudaMemsetAsync(L.vcnt.p + n, 0, sizeof(int), c->stream));
+   L.sctr.ensure(nsb);
+   L.sext.ensure(nsb);
+   k_super_boxes<<<(nsb * 32 + 127) / 128, 128, 0, c->stream>>>(nblk, nsb, c->blk_ctr, c->blk_ext, L.sctr, L.sext);
+   CUDA_CHECK(cudaMemsetAsync(L.vcnt.p, 0, sizeof(int) * (n + 1), c->stream));
+   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.sctr, L.sext,
+      L.vcnt, nullptr, nullptr);
    size_t need = 0;
    cub::DeviceScan::ExclusiveSum(nullptr, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
    if (need > c->cubtmp.cap)
@@ -158,20 +209,22 @@ void apx_rows_build(apx_ctx* c)
    L.nverlet = total;
    L.vnbr.ensure((size_t)total + 32);
    L.nbr.ensure((size_t)total + 32);
-   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, c->box, range, c->posd, c->blk_ctr, c->blk_ext, nullptr, L.vstart, L.vnbr);
-   c->stats.kernel_launches += 2;
+   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.sctr, L.sext,
+      nullptr, L.vstart, L.vnbr);
+   c->stats.kernel_launches += 3;
 }
 
 void apx_rows_compact(apx_ctx* c, bool count)
 {
    RowList& L = c->rows;
-   const int n = c->n;
+   const int no = c->a1 - c->a0;
    const real cut = c->list_cutoff;
    const bool sparse = c->opt.use_polar && c->opt.pcgprec && c->opt.usolve_cutoff > 0;
    const real ucut = sparse ? (real)std::min(c->opt.usolve_cutoff, (double)cut) : (real)0;
    if (count)
       CUDA_CHECK(cudaMemsetAsync(L.total.p, 0, 2 * sizeof(unsigned long long), c->stream));
-   k_rows_compact<<<(n * 32 + 127) / 128, 128, 0, c->stream>>>(n, c->box, cut * cut, ucut * ucut, c->posd, L.vstart, L.vnbr, L.nbr,
-      L.cnt, L.cntu, count ? L.total.p : nullptr);
+   if (no > 0)
+      k_rows_compact<<<(no * 32 + 127) / 128, 128, 0, c->stream>>>(c->a0, c->a1, c->box, cut * cut, ucut * ucut, c->posd, L.vstart, L.vnbr,
+         L.nbr, L.cnt, L.cntu, count ? L.total.p : nullptr);
    APX_COUNT_LAUNCH(c);
 }

@@ -6,13 +6,14 @@
 
 #define ROWS_BLOCK 128
 
-// for (atoms of this lane group): `i` = atom (clamped to n-1), `l` = lane in group, `act` = i is real.
+// for (atoms a0 <= i < a1 of this lane group): `i` = atom (clamped to a1-1), `l` = lane in group,
+// `act` = i is real.  [a0,a1) is the sorted range this GPU owns (the whole system on one GPU).
 // The trip count is uniform across a warp so the body may use full-mask shuffles.
-#define ROWS_FOREACH_ATOM(G, n, i, l, act)                                                                               \
+#define ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)                                                                          \
    const int l = threadIdx.x & ((G) - 1);                                                                                \
-   for (int i_ = blockIdx.x * (ROWS_BLOCK / (G)) + threadIdx.x / (G), w_ = i_ - (threadIdx.x & 31) / (G), i = min(i_, (n) - 1),  \
-            act = i_ < (n);                                                                                              \
-        w_ < (n); i_ += gridDim.x * (ROWS_BLOCK / (G)), w_ += gridDim.x * (ROWS_BLOCK / (G)), i = min(i_, (n) - 1), act = i_ < (n))
+   for (int i_ = (a0) + blockIdx.x * (ROWS_BLOCK / (G)) + threadIdx.x / (G), w_ = i_ - (threadIdx.x & 31) / (G),           \
+            i = min(i_, (a1) - 1), act = i_ < (a1);                                                                      \
+        w_ < (a1); i_ += gridDim.x * (ROWS_BLOCK / (G)), w_ += gridDim.x * (ROWS_BLOCK / (G)), i = min(i_, (a1) - 1), act = i_ < (a1))
 
 template <int G>
 __device__ __forceinline__ real group_sum(real v)
@@ -32,7 +33,7 @@ template <int G>
 inline int rows_grid(const apx_ctx* c, int ctas_per_sm = 32)
 {
    int per = ROWS_BLOCK / G;
-   int want = (c->n + per - 1) / per;
+   int want = (c->a1 - c->a0 + per - 1) / per;
    int cap = c->sm_count * ctas_per_sm;
    return want < 1 ? 1 : (want < cap ? want : cap);
 }

@@ -617,7 +617,7 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, **lists)
 
 
-def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017) -> System:
+def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep_bonds: bool = True) -> System:
     """Tile an orthogonal periodic System reps=(nx,ny,nz) times (BASELINE.md §4 synthetic boxes).
     Index-valued arrays are offset per image; the PME grid is re-derived with the 1.2/A rule."""
     nx, ny, nz = reps
@@ -653,7 +653,7 @@ def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017) -> S
     cell, recip = lattice(La, Lb, Lc)
     nfft = tuple(pme_grid_default(L) for L in (La, Lb, Lc)) if sys.use_ewald else (0, 0, 0)
     bonds = None
-    if sys.bonds is not None and m * n0 <= 2_000_000:
+    if keep_bonds and sys.bonds is not None and m * n0 <= 2_000_000:
         bonds = [[k + s for k in bl] for s in shift for bl in sys.bonds]
     return System(
         n=m * n0, xyz=xyz, lvec=cell, recip=recip, pole=tile(sys.pole), zaxis=zt.reshape(-1, 4).astype(np.int32),
