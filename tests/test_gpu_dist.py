@@ -67,11 +67,16 @@ def test_dhfr2_four_ranks_and_moving_atoms():
     from tinker_gpu_b200.amoeba import Amoeba, calc
     from tinker_gpu_b200.distributed import run_local_ranks
     s = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
-    rng = np.random.default_rng(7)
     x0 = np.array(s.xyz)
-    d = rng.normal(scale=0.3, size=x0.shape)
-    d *= np.minimum(1.0, 0.95 / np.linalg.norm(d, axis=1))[:, None]
-    x1 = x0 + d                                                           # every atom < buffer/2: same list
+    # a smooth displacement field of up to 0.95 A (< buffer/2: same list) plus thermal-size noise.  Uncorrelated
+    # 1 A kicks would squeeze bonded atoms to ~0.3 A, where the excluded-pair cancellation loses all float
+    # digits and the single-GPU and decomposed summation orders differ by more than any tolerance.
+    L = float(np.asarray(s.lvec)[0, 0])
+    ph = 2.0 * np.pi * x0 / L
+    d = 0.5 * np.stack([np.sin(ph[:, 1]), np.sin(ph[:, 2]), np.sin(ph[:, 0])], axis=1)
+    d += np.random.default_rng(7).normal(scale=0.02, size=x0.shape)
+    assert np.linalg.norm(d, axis=1).max() < 0.95
+    x1 = x0 + d
     x2 = x0 + np.array([0.0, 0.0, 3.3])                                   # rebuild, atoms change slabs
     a = Amoeba(s, "mixed")
     refs = []

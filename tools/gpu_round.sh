@@ -3,7 +3,7 @@
 # usage (under gpurun): bash tools/gpu_round.sh <tag> [pytest-args]
 tag=${1:-run}
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q ${2:-} > gpurun_out/${tag}_pytest.log 2>&1
+timeout 1200 python -m pytest tests -m gpu -q ${2:-} > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$?"
 tail -12 gpurun_out/${tag}_pytest.log
 timeout 500 python bench.py --steps 20 --warmup 5 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
