@@ -225,6 +225,12 @@ class Oracle:
         self._excl = None
         self.rpole = None
         self.niter = 0
+        # induced-dipole predictor (ulspredSave / ulspredSum, src/amoeba/induce.cpp:27-69)
+        self.polpred = str(getattr(s, "polpred", "NONE") or "NONE").upper()
+        self.maxualt = {"ASPC": 16, "GEAR": 6}.get(self.polpred, 0)
+        self.nualt = 0
+        self.udalt = np.zeros((self.maxualt, self.n, 3))
+        self.upalt = np.zeros((self.maxualt, self.n, 3))
 
     # ------------------------------------------------------------------ geometry
     def set_xyz(self, xyz):
@@ -739,8 +745,19 @@ class Oracle:
             self.uind, self.uinp = self.udir.copy(), self.udirp.copy()
             self.niter = 0
             return self.uind, self.uinp
-        ud, up = self.udir.copy(), self.udirp.copy()
-        rd, rp_ = self.ufield(ud, up)
+        # pcg.cu:26-31: the predictor replaces the direct guess once its history ring is full
+        predict = self.maxualt > 0 and self.nualt >= self.maxualt
+        if predict:
+            ud, up = self.ulspred_sum()
+            fd, fp = self.ufield(ud, up)
+            rd = (self.udir - ud) * pinv + fd          # pcgRsd0V2, src/cu/induce.cu:46-58
+            rp_ = (self.udirp - up) * pinv + fp
+        elif s.pcgguess:
+            ud, up = self.udir.copy(), self.udirp.copy()
+            rd, rp_ = self.ufield(ud, up)
+        else:
+            ud, up = np.zeros((n, 3)), np.zeros((n, 3))
+            rd, rp_ = fd.copy(), fp.copy()
         zero = (s.polarity == 0)
         rd[zero] = 0
         rp_[zero] = 0
@@ -785,6 +802,36 @@ class Oracle:
                 up += s.pcgpeek * pol * rp_
         self.niter = it
         self.uind, self.uinp = ud, up
+        self.ulspred_save(ud, up)
+        return ud, up
+
+    # ------------------------------------------------------------------ dipole predictors
+    ASPC = (62. / 17., -310. / 51., 2170. / 323., -2329. / 400., 1701. / 409., -806. / 323., 1024. / 809., -479. / 883.,
+            257. / 1316., -434. / 7429., 191. / 13375., -62. / 22287., 3. / 7217., -3. / 67015., 2. / 646323., -1. / 9694845.)
+    GEAR = (6., -15., 20., -15., 6., -1.)
+
+    def ulspred_save(self, ud, up):
+        """ulspredSave (src/amoeba/induce.cpp:29-63): ring of the last maxualt solutions."""
+        m = self.maxualt
+        if m == 0:
+            return
+        pos = self.nualt % m
+        self.udalt[pos] = ud
+        self.upalt[pos] = up
+        self.nualt += 1
+        if self.nualt > 2 * m:
+            self.nualt -= m
+
+    def ulspred_sum(self):
+        """ulspredSumASPC_cu / ulspredSumGEAR_cu (src/cu/upredict.cu:34-207): slot k holds the solution
+        of age (nualt-1-k) mod maxualt and gets the coefficient of that age."""
+        m = self.maxualt
+        coef = self.ASPC if self.polpred == "ASPC" else self.GEAR
+        ud, up = np.zeros((self.n, 3)), np.zeros((self.n, 3))
+        for k in range(m):
+            c = coef[(self.nualt - 1 - k) % m]
+            ud += c * self.udalt[k]
+            up += c * self.upalt[k]
         return ud, up
 
     # ------------------------------------------------------------------ torque -> gradient
