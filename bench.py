@@ -17,6 +17,12 @@ fused real-space multipole/polarization + reciprocal space + torque + reductions
 N > 1: dhfr2 is latency bound on one GPU, so ranks run independent replicas (SURVEY §8e
 "replicas only"); value is the aggregate over replicas, time is the max over ranks.
 
+--workload selects the other BASELINE.json configurations (synthetic boxes built at run time by
+replicating the committed cells): water96k (configs[2], polar-eps 1e-8), water1m
+(configs[3]) and dhfr424k (configs[4]).  For those, N > 1 runs ONE system spatially decomposed over
+the N GPUs (dist.cu: z-slabs, halo exchange of dipoles per CG iteration, slab FFT with all-to-all
+transposes over NCCL) -- "scaling": "strong"; --replicas forces independent replicas instead.
+
 `value` is measured with positions resident in HBM; `e2e` goes through the public host API
 (set_positions from host memory -> energy -> gradient back to host) inside the timed region.
 """
@@ -36,6 +42,27 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 FS_PER_STEP = 2.0
 METRIC = "ns/day (electrostatics hot path only, 2 fs/step) & ms/induce() AMOEBA DHFR 23.5k atoms"
 WORKLOAD = "dhfr2 AMOEBA DHFR 23558 atoms, PME 64^3 order 5, ewald-cutoff 7.0, polar-eps 1e-5, energy+gradient"
+# name -> (cell blob, replication, polar-eps override, jitter, description)   
+WORKLOADS = {
+    "dhfr2": ("dhfr2.npz", None, None, 0.0, WORKLOAD),
+    "water96k": ("water30.npz", (3, 3, 4), 1e-8, 0.05,
+                 "synthetic AMOEBA water box 96624 atoms (water30 cell x3x3x4, jitter 0.05 A), PME 108x108x144, polar-eps 1e-8"),
+    "water1m": ("water30.npz", (8, 8, 6), None, 0.05,
+                "synthetic AMOEBA water box 1030656 atoms (water30 cell x8x8x6, jitter 0.05 A), PME 288x288x216, polar-eps 1e-5"),
+    "dhfr424k": ("dhfr2.npz", (3, 3, 2), None, 0.05,
+                 "replicated dhfr2 cells 424044 atoms (x3x3x2, jitter 0.05 A), dense PME 240x240x150, polar-eps 1e-5"),
+}
+
+
+def make_system(name):
+    import tinker_gpu_b200 as tg
+    blob, reps, eps, jitter, _ = WORKLOADS[name]
+    s = tg.load_system(os.path.join(GOLDEN, blob))
+    if reps is not None:
+        s = tg.replicate(s, reps, jitter=jitter, keep_bonds=False)
+    if eps is not None:
+        s.poleps = eps
+    return s
 
 
 def ns_per_day(ms_per_step, replicas=1):
@@ -181,12 +208,18 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    system = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
-    a = Amoeba(system, "mixed", device=local_rank)
+    system = make_system(args.workload)
+    decomposed = world > 1 and args.workload != "dhfr2" and not args.replicas
+    replicas = 1 if decomposed else world
+    if decomposed:
+        from tinker_gpu_b200.distributed import nccl_context
+        a = nccl_context(system, "mixed")
+    else:
+        a = Amoeba(system, "mixed", device=local_rank)
     ext = torch.cuda.ExternalStream(a.lib.apx_stream(a.ctx), device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     vers = calc.v4
-    rng = np.random.default_rng(1234 + rank)
+    rng = np.random.default_rng(1234 + (0 if decomposed else rank))     # decomposed: every rank passes the same positions
     xyz0 = np.array(system.xyz)
     # per-step host inputs for the e2e leg: thermal-size displacements so list checks are real
     disp = [xyz0 + rng.normal(scale=0.01, size=xyz0.shape) for _ in range(4)]
@@ -277,19 +310,25 @@ def run_ours(args, rank, world, local_rank):
         uf_flops = 130.0 * npairs
         achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max
-        traffic = load_ncu_traffic("k_ufield_rows")
+        traffic = load_ncu_traffic("k_ufield_rows") if args.workload == "dhfr2" else None
         fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
+        wl_desc = WORKLOADS[args.workload][4]
+        metric = METRIC if args.workload == "dhfr2" else METRIC.replace("AMOEBA DHFR 23.5k atoms", wl_desc.split(",")[0])
+        par = "single GPU" if world == 1 else (f"spatial decomposition over {world} GPUs (z-slabs, NCCL halo exchange + slab FFT all-to-all)"
+                                                if decomposed else f"replicas x{world}")
         line = {
-            "metric": METRIC, "value": ns_per_day(ms_step, world), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": ns_per_day(ms_step, replicas), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_induce": ms_ind,
-            "pcg_iterations": float(np.mean(iters)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "pcg_iterations": float(np.mean(iters)), "higher_is_better": True, "scaling": "strong" if decomposed else "weak",
+            "vs_baseline": None,
             "dtype": "f32 pair math + 2^32 fixed-point / f64 accumulation",
-            "data": "reference input deck example/dhfr2 parsed by our readers (blob tests/golden/dhfr2.npz)",
-            "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                       "l2": "flushed (256 MB write) between timed steps; working set is L2 resident within a step",
+            "data": ("reference input deck example/dhfr2 parsed by our readers (blob tests/golden/dhfr2.npz)" if args.workload == "dhfr2"
+                     else "synthetic: committed reference cell replicated at run time (BASELINE.md section 4), seeded jitter"),
+            "config": {"workload": wl_desc + ", energy+gradient" * (args.workload != "dhfr2"), "atoms": int(n), "parallelism": par,
+                       "l2": "flushed (256 MB write) between timed steps",
                        "timing": "CUDA events on the library stream around each step, mean of steps, max over ranks",
                        "hot_path_only": True},
-            "e2e": {"value": ns_per_day(ms_e2e_step, world), "unit": "ns/day", "ms_per_step": ms_e2e_step,
+            "e2e": {"value": ns_per_day(ms_e2e_step, replicas), "unit": "ns/day", "ms_per_step": ms_e2e_step,
                     "h2d_bytes_per_step": int(xyz0.nbytes), "d2h_bytes_per_step": int(xyz0.nbytes) + 136,
                     "list_rebuilds": rebuilds},
             "gpu_launches": int(launches),
@@ -305,7 +344,7 @@ def run_ours(args, rank, world, local_rank):
                               "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs)},
             "wall_s_timed_region": t_wall,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and args.workload == "dhfr2":
             ms_cpu, ms_cpu_ind, desc = cpu_oracle_sample(system)
             line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc,
                                     "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind}
@@ -322,6 +361,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--workload", default="dhfr2", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas also for the large workloads")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

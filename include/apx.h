@@ -66,6 +66,8 @@ typedef struct apx_system {
    int pcgprec, pcgguess;
    double pcgpeek;
    double electric, dielec;
+   int polpred;            /* UPred (include/ff/amoeba/mpole.h:38): 0 NONE, 1 ASPC, 2 GEAR; 3 LSQR is rejected like
+                              ulspredSum_cu does (src/cu/upredict.cu:204-206) */
 } apx_system;
 
 typedef struct apx_ctx apx_ctx;
@@ -134,6 +136,12 @@ int apx_precond(apx_ctx* ctx, const double* rsd, const double* rsdp, double* zrs
 /* induce(uind, uinp) -> induceMutualPcg1_cu: src/amoeba/induce.cpp:108-113, src/cu/amoeba/pcg.cu:14 */
 int apx_induce(apx_ctx* ctx);
 int apx_get_uind(apx_ctx* ctx, double* uind, double* uinp);
+/* induced-dipole predictor, ulspredSave / ulspredSum (src/amoeba/induce.cpp:27-69, src/cu/upredict.cu):
+ * every apx_induce() stores its solution in a ring of maxualt (ASPC 16, GEAR 6) entries and, once the ring
+ * is full, starts from the extrapolated dipoles instead of the direct guess.  apx_upred_set switches the
+ * predictor kind and empties the ring (nualt = 0, as epolarData(RcOp::INIT) does, src/amoeba/epolar.cpp:446-447). */
+int apx_upred_set(apx_ctx* ctx, int polpred);
+int apx_upred_count(apx_ctx* ctx, int* nualt, int* maxualt);
 int apx_get_udir(apx_ctx* ctx, double* udir, double* udirp);
 
 /* energy(vers) restricted to the electrostatic terms: empole+epolar or fused emplar

@@ -169,6 +169,34 @@ def test_dhfr2_properties():
     ad.close()
 
 
+@pytest.mark.parametrize("precision", ["double", "mixed"])
+def test_dhfr2_vs_oracle_fixture(precision):
+    """BASELINE.json configs[0]: dhfr2 energy + gradient + virial + induced dipoles against the float64 oracle run
+    on the same input (tests/golden/dhfr2_oracle.npz, made by tests/golden/make_oracle_fixtures.py: 10 CPU-minutes,
+    so the GPU box only loads its result).  North-star tolerances: energy 1e-6 relative, dipoles 1e-6 D RMS;
+    forces 5e-5 kcal/mol/A RMS for the float pair math, 1e-7 for the double build."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    fx = np.load(os.path.join(GOLDEN, "dhfr2_oracle.npz"))
+    s = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    a = _amoeba(s, precision)
+    r = a.energy(calc.v1)
+    ud, up = a.uind()
+    d1, d2 = a.udir()
+    tol = dict(e=1e-9, g=1e-7, u=1e-9, v=1e-7) if precision == "double" else dict(e=1e-6, g=5e-5, u=1e-6, v=2e-5)
+    eref = float(fx["em"]) + float(fx["ep"])
+    assert abs(r["em"] - float(fx["em"])) < tol["e"] * abs(eref)
+    assert abs(r["ep"] - float(fx["ep"])) < tol["e"] * abs(eref)
+    assert abs(r["esum"] - eref) < tol["e"] * abs(eref)
+    assert _rms(r["grad"] - fx["grad"]) < tol["g"]
+    assert _rms(ud - fx["uind"]) * DEBYE < tol["u"] and _rms(up - fx["uinp"]) * DEBYE < tol["u"]
+    assert _rms(d1 - fx["udir"]) * DEBYE < tol["u"] and _rms(d2 - fx["udirp"]) * DEBYE < tol["u"]
+    assert np.abs(r["virial"] - fx["virial"]).max() < tol["v"] * np.abs(fx["virial"]).max()
+    assert r["pcg_iterations"] == int(fx["niter"])
+    assert a.stats()["npairs_m"] == int(fx["npairs"])
+    a.close()
+
+
 def test_pme_convolution_native_fft():
     """The fused 64^3 FFT -> influence function -> inverse FFT kernels (fft64.cu) against numpy's FFT
     and against the cuFFT path of the same library, on a random complex grid (dhfr2 grid, 64^3)."""

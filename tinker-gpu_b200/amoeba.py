@@ -32,6 +32,9 @@ class calc:
     v6 = grad + virial
 
 
+UPRED = {"NONE": 0, "ASPC": 1, "GEAR": 2, "LSQR": 3}     # UPred, include/ff/amoeba/mpole.h:38
+
+
 class ApxError(RuntimeError):
     """C-ABI image of the reference's FatalError (include/tool/error.h:16-45)."""
 
@@ -48,7 +51,7 @@ class _ApxSystem(C.Structure):
         ("cutoff", C.c_double), ("usolve_cutoff", C.c_double), ("list_buffer", C.c_double),
         ("poleps", C.c_double), ("politer", C.c_int), ("uaccel", C.c_double),
         ("pcgprec", C.c_int), ("pcgguess", C.c_int), ("pcgpeek", C.c_double),
-        ("electric", C.c_double), ("dielec", C.c_double),
+        ("electric", C.c_double), ("dielec", C.c_double), ("polpred", C.c_int),
     ]
 
 
@@ -106,6 +109,7 @@ def load_library(precision="mixed"):
         "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int],
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
         "apx_get_dist_info": [C.POINTER(C.c_int)],
+        "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p] + args
@@ -219,6 +223,7 @@ class Amoeba:
         s.poleps, s.politer, s.uaccel = system.poleps, system.politer, system.uaccel
         s.pcgprec, s.pcgguess, s.pcgpeek = int(system.pcgprec), int(system.pcgguess), system.pcgpeek
         s.electric, s.dielec = system.electric, system.dielec
+        s.polpred = UPRED[str(getattr(system, "polpred", "NONE") or "NONE").upper()]
         self.ctx = C.c_void_p()
         if dist is None:
             rc = self.lib.apx_create(C.byref(s), device, C.byref(self.ctx))
@@ -298,6 +303,15 @@ class Amoeba:
     def induce(self):
         self._chk(self.lib.apx_induce(self.ctx))
         return self.uind()
+
+    def upred_set(self, polpred):
+        """Select the induced-dipole predictor ("NONE", "ASPC", "GEAR") and empty its history ring."""
+        self._chk(self.lib.apx_upred_set(self.ctx, UPRED[str(polpred).upper()]))
+
+    def upred_count(self):
+        a, b = C.c_int(), C.c_int()
+        self._chk(self.lib.apx_upred_count(self.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def uind(self):
         a, b = self._out(self.n, 3), self._out(self.n, 3)

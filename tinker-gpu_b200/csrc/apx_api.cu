@@ -307,6 +307,7 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    c->list_cutoff = (real)std::min(sys->cutoff, 1.0e6);
    c->list_buffer = (real)sys->list_buffer;
    c->a0 = 0, c->a1 = c->n;
+   apx_upred_configure(c, sys->polpred);
    apx_pme_setup(c);
    apx_list_refresh(c, true);
 }
@@ -607,6 +608,25 @@ int apx_stats_reset(apx_ctx* c)
    API_BEGIN
    c->stats.kernel_launches = 0;
    c->stats.list_rebuilds = 0;
+   API_END
+}
+
+int apx_upred_set(apx_ctx* c, int polpred)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   apx_upred_configure(c, polpred);
+   API_END
+}
+
+int apx_upred_count(apx_ctx* c, int* nualt, int* maxualt)
+{
+   API_BEGIN
+   if (nualt)
+      *nualt = c->nualt;
+   if (maxualt)
+      *maxualt = c->maxualt;
    API_END
 }
 

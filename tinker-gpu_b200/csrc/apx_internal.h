@@ -184,6 +184,11 @@ struct apx_ctx {
    double* scal_h = nullptr;             // pinned
    int last_iters = 6;
 
+   // ---- induced-dipole predictor (pcg.cu): ring of packed (d,p) solutions in CALLER order, so a list
+   //      rebuild (new sorted order) or a change of slab ownership does not disturb the history
+   DevBuf<real4> upred_hist;             // [maxualt][n][2]
+   int nualt = 0, maxualt = 0;
+
    // ---- PME
    int nfft1 = 0, nfft2 = 0, nfft3 = 0;
    cufftHandle plan = 0;
@@ -294,6 +299,7 @@ void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, rea
 // ---- pcg.cu
 void apx_induce_impl(apx_ctx* c);
 void apx_pcg_graphs_invalidate(apx_ctx* c);
+void apx_upred_configure(apx_ctx* c, int polpred);             // sets opt.polpred, sizes and empties the ring
 void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);

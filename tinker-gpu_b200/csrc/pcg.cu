@@ -142,6 +142,60 @@ __global__ void k_unpack_dp(int n, const real4* __restrict__ in, real* __restric
    p[3 * s] = b.x, p[3 * s + 1] = b.y, p[3 * s + 2] = b.z;
 }
 
+// ---- induced-dipole predictors (ulspredSave / ulspredSum, src/amoeba/induce.cpp:27-69, src/cu/upredict.cu).
+// The reference keeps 16 (ASPC) or 6 (GEAR) separate [n][3] arrays per dipole set and passes all of them
+// to one kernel; here the ring is one buffer of packed (d,p) pairs in caller order, the coefficient of
+// every ring slot arrives by value, and the extrapolated guess is written in the three layouts the
+// solver wants (uind, uinp, packed direction buffer) in the same pass.
+struct UpredCoef {
+   real c[16];
+   int m;
+};
+__global__ void k_upred_save(int n, const int* __restrict__ perm, const real* __restrict__ ud, const real* __restrict__ up,
+   real4* __restrict__ slot)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   store_dp(slot, perm[s], v3(ud[3 * s], ud[3 * s + 1], ud[3 * s + 2]), v3(up[3 * s], up[3 * s + 1], up[3 * s + 2]));
+}
+__global__ void k_upred_sum(int n, int ntot, const int* __restrict__ perm, const real4* __restrict__ hist, UpredCoef K,
+   real* __restrict__ ud, real* __restrict__ up, real4* __restrict__ P)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   const int i = perm[s];
+   V3 a = v3(0, 0, 0), b = v3(0, 0, 0);
+   for (int k = 0; k < K.m; ++k) {
+      V3 hd, hp;
+      load_dp(hist + (size_t)2 * ntot * k, i, hd, hp);
+      a += K.c[k] * hd;
+      b += K.c[k] * hp;
+   }
+   ud[3 * s] = a.x, ud[3 * s + 1] = a.y, ud[3 * s + 2] = a.z;
+   up[3 * s] = b.x, up[3 * s + 1] = b.y, up[3 * s + 2] = b.z;
+   store_dp(P, s, a, b);
+}
+// r0 = (udir - u0)/alpha + field(u0)   (pcgRsd0V2 + pcgRsd0, src/cu/induce.cu:46-58,17-33); R holds field(u0)
+__global__ void k_rsd0_pred(int n, const real4* __restrict__ tpj, const real* __restrict__ udir, const real* __restrict__ udirp,
+   const real* __restrict__ ud, const real* __restrict__ up, real4* __restrict__ R)
+{
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   V3 rd, rp;
+   load_dp(R, s, rd, rp);
+   const real pinv = tpj[s].z;
+   rd += pinv * v3(udir[3 * s] - ud[3 * s], udir[3 * s + 1] - ud[3 * s + 1], udir[3 * s + 2] - ud[3 * s + 2]);
+   rp += pinv * v3(udirp[3 * s] - up[3 * s], udirp[3 * s + 1] - up[3 * s + 1], udirp[3 * s + 2] - up[3 * s + 2]);
+   if (tpj[s].y == 0) {
+      rd = v3(0, 0, 0);
+      rp = v3(0, 0, 0);
+   }
+   store_dp(R, s, rd, rp);
+}
+
 // caller order (f64) <-> sorted order (real)
 __global__ void k_to_sorted(int n, const int* __restrict__ perm, const double* __restrict__ in, real* __restrict__ out)
 {
@@ -261,6 +315,41 @@ __global__ void k_nonewald_ap(int n, const int* __restrict__ flags, const real4*
    pcg_block_add2(x, y, slot, 2, 3);
 }
 
+void apx_upred_configure(apx_ctx* c, int polpred)
+{
+   if (polpred == 3)       // LSQR: the reference's CUDA back end has no such kernel either (upredict.cu:204-206)
+      APX_THROW("polar-predict LSQR is not available on the GPU (ulspredSumLSQR_cu missing in the reference as well)");
+   if (polpred < 0 || polpred > 2)
+      APX_THROW("unknown polar-predict kind");
+   c->opt.polpred = polpred;
+   c->maxualt = polpred == 1 ? 16 : (polpred == 2 ? 6 : 0);      // src/amoeba/epolar.cpp:449-468
+   c->nualt = 0;
+   if (c->maxualt)
+      c->upred_hist.ensure((size_t)2 * c->n * c->maxualt);
+}
+
+// ulspredSave: the converged dipoles go into ring slot nualt % maxualt
+static void upred_save(apx_ctx* c)
+{
+   const int m = c->maxualt;
+   if (!m)
+      return;
+   int a0 = c->a0, no = c->a1 - c->a0;
+   if (c->dist.on) {
+      // atoms change slabs at list rebuilds: every rank keeps the history of ALL atoms
+      apx_dist_share_owned(c, c->uind.p, 3 * sizeof(real));
+      apx_dist_share_owned(c, c->uinp.p, 3 * sizeof(real));
+      a0 = 0, no = c->n;
+   }
+   const int pos = c->nualt % m;
+   k_upred_save<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->perm + a0, c->uind + 3 * a0, c->uinp + 3 * a0,
+      c->upred_hist + (size_t)2 * c->n * pos);
+   APX_COUNT_LAUNCH(c);
+   c->nualt++;
+   if (c->nualt > 2 * m)
+      c->nualt -= m;
+}
+
 void apx_pcg_graphs_invalidate(apx_ctx* c)
 {
    for (auto& g : c->graphs)
@@ -305,8 +394,24 @@ void apx_induce_impl(apx_ctx* c)
    double* result = c->scal.p + (size_t)PCG_SLOT * (politer + 3);
    const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nzl * sizeof(cplx) / sizeof(real4) : 0;
 
+   // the predictor replaces the direct guess once its ring is full (pcg.cu:26-31)
+   const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;
+   if (predict) {
+      static const double aspc[16] = {62. / 17., -310. / 51., 2170. / 323., -2329. / 400., 1701. / 409., -806. / 323., 1024. / 809.,
+         -479. / 883., 257. / 1316., -434. / 7429., 191. / 13375., -62. / 22287., 3. / 7217., -3. / 67015., 2. / 646323.,
+         -1. / 9694845.};
+      static const double gear[6] = {6., -15., 20., -15., 6., -1.};
+      UpredCoef K;
+      K.m = c->maxualt;
+      for (int k = 0; k < K.m; ++k) {
+         int age = ((c->nualt - 1 - k) % K.m + K.m) % K.m;      // ring slot k holds the solution of this age
+         K.c[k] = (real)(c->opt.polpred == 1 ? aspc[age] : gear[age]);
+      }
+      k_upred_sum<<<g1, 256, 0, st>>>(no, n, c->perm + a0, c->upred_hist, K, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0);
+      APX_COUNT_LAUNCH(c);
+   }
    // r0 = -T u0  (pcgguess; k_udir left u0 packed in pk_p) or E (no guess; k_udir left E packed in pk_p)
-   if (c->opt.pcgguess) {
+   if (c->opt.pcgguess || predict) {
       if (ewald)
          apx_pme_zero_grid(c);
       field_of_dp(c, c->pk_p, true);
@@ -315,6 +420,11 @@ void apx_induce_impl(apx_ctx* c)
       else {
          CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_f.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
          k_mask_dp<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->pk_r + 2 * a0);
+         APX_COUNT_LAUNCH(c);
+      }
+      if (predict) {
+         k_rsd0_pred<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->udir + 3 * a0, c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0,
+            c->pk_r + 2 * a0);
          APX_COUNT_LAUNCH(c);
       }
    } else {
@@ -411,7 +521,7 @@ void apx_induce_impl(apx_ctx* c)
    {
       // mean device time of the real-space ufield launches that did work (speculative launches after
       // convergence return immediately and are excluded): 1 for r0 + one per iteration
-      int used_pairs = std::min(c->uf_used / 2, used + (c->opt.pcgguess ? 1 : 0));
+      int used_pairs = std::min(c->uf_used / 2, used + ((c->opt.pcgguess || predict) ? 1 : 0));
       float tot = 0;
       for (int k = 0; k < used_pairs; ++k) {
          float ms = 0;
@@ -425,6 +535,7 @@ void apx_induce_impl(apx_ctx* c)
    c->stats.ms_induce = 0;
    cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
    c->scal_h[2] = c->scal_h[0];
+   upred_save(c);
    if (used >= politer && !(c->scal_h[0] < c->opt.poleps))
       APX_THROW("INDUCE  --  Warning, Induced Dipoles are not Converged");   // pcg.cu:180-184
 }

@@ -74,6 +74,7 @@ class System:
     pcgguess: bool = True
     pcgpeek: float = 1.0
     poltyp: str = "MUTUAL"
+    polpred: str = "NONE"              # polar-predict keyword: NONE | ASPC | GEAR (predict.f:48-60)
     electric: float = COULOMB
     dielec: float = 1.0
     types: np.ndarray | None = None
@@ -605,6 +606,9 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
     if term("POLARIZETERM") == "NONE":
         use_polar = False
     poltyp = (kget("POLARIZATION", "MUTUAL").split() or ["MUTUAL"])[0].upper()
+    polpred = "NONE"
+    if khas("POLAR-PREDICT"):          # predict.f:48-60: a bare keyword selects ASPC
+        polpred = ((kget("POLAR-PREDICT") or "").split() or ["ASPC"])[0].upper()[:4]
 
     return System(
         n=n, xyz=xyz.xyz.copy(), lvec=lvec, recip=recip, pole=pole, zaxis=zaxis,
@@ -613,7 +617,7 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         aewald=aewald, nfft=nfft, bsorder=bsorder, ewald_cutoff=cutoff,
         usolve_cutoff=usolve_applied, list_buffer=lbuffer,
         poleps=kfloat("POLAR-EPS", 1.0e-6), politer=int(kfloat("POLAR-ITER", 100)),
-        poltyp=poltyp, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
+        poltyp=poltyp, polpred=polpred, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
         types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, **lists)
 
 
@@ -667,7 +671,7 @@ def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep
         bsorder=sys.bsorder, ewald_cutoff=sys.ewald_cutoff, usolve_cutoff=sys.usolve_cutoff,
         list_buffer=sys.list_buffer, poleps=sys.poleps, politer=sys.politer, uaccel=sys.uaccel,
         pcgprec=sys.pcgprec, pcgguess=sys.pcgguess, pcgpeek=sys.pcgpeek, poltyp=sys.poltyp,
-        electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
+        polpred=sys.polpred, electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
         names=(sys.names * m) if sys.names is not None else None, bonds=bonds,
         title=f"{sys.title} x{nx}x{ny}x{nz}")
 
@@ -688,6 +692,7 @@ def save_system(path: str, sys: System) -> None:
     for k in _SCALAR_FIELDS:
         d["_" + k] = np.array(getattr(sys, k))
     d["_nfft"] = np.array(sys.nfft, np.int64)
+    d["_polpred"] = np.array(sys.polpred)
     np.savez_compressed(path, **d)
 
 
@@ -697,6 +702,8 @@ def load_system(path: str) -> System:
     for k in _SCALAR_FIELDS:
         v = z["_" + k]
         kw[k] = v.item() if v.dtype.kind != "U" else str(v)
+    if "_polpred" in z.files:
+        kw["polpred"] = str(z["_polpred"])
     kw["nfft"] = tuple(int(v) for v in z["_nfft"])
     kw.setdefault("types", None)
     return System(**kw)
