@@ -20,9 +20,25 @@ def main():
     ap.add_argument("--system", default=os.path.join(ROOT, "tests", "golden", "dhfr2.npz"))
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trace.txt"))
+    ap.add_argument("--workload", default=None, help="bench.py workload name instead of --system")
     args = ap.parse_args()
-    s = tg.load_system(args.system)
-    a = Amoeba(s, "mixed", device=0)
+    if args.workload:
+        import bench
+        s = bench.make_system(args.workload)
+    else:
+        s = tg.load_system(args.system)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    if world > 1:
+        # one process per GPU under torchrun: the spatially decomposed path over NCCL; rank 0 reports its own timeline
+        import torch.distributed as dist
+        from tinker_gpu_b200.distributed import nccl_context
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        a = nccl_context(s, "mixed")
+    else:
+        a = Amoeba(s, "mixed", device=lr)
     for _ in range(5):
         a.lib.apx_energy(a.ctx, calc.v4, None)
     a.synchronize()
@@ -65,13 +81,16 @@ def main():
     lines.append(f"{'sum of kernel durations (streams overlap)':62s} {'':4s} {s_all:9.1f}")
     # timeline of the last iteration-ish: first 60 activities with start offsets
     lines.append("# timeline (start us, dur us, name)")
-    for e in seg[: min(len(seg), 400)]:
+    for e in seg[: min(len(seg), 700)]:
         lines.append(f"{e.time_range.start - t0:9.1f} {e.time_range.end - e.time_range.start:7.1f}  {e.name[:70]}")
-    os.makedirs(os.path.dirname(args.out), exist_ok=True)
-    with open(args.out, "w") as f:
-        f.write("\n".join(lines) + "\n")
-    print("\n".join(lines[:45]))
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        with open(args.out, "w") as f:
+            f.write("\n".join(lines) + "\n")
+        print("\n".join(lines[:45]))
     a.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
