@@ -81,6 +81,7 @@ class System:
     names: list | None = None
     bonds: list | None = None
     title: str = ""
+    vdw: object | None = None          # vdwparams.VdwTerm: buffered 14-7 term, optional
 
     @property
     def volume(self) -> float:
@@ -606,6 +607,8 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
     if term("POLARIZETERM") == "NONE":
         use_polar = False
     poltyp = (kget("POLARIZATION", "MUTUAL").split() or ["MUTUAL"])[0].upper()
+    from .vdwparams import build_vdw
+    vdw = build_vdw(n, types, ff.atom_class, i12, i13, i14, i15, key, ff, use_bounds, float(abs(np.linalg.det(lvec))), lbuffer)
     polpred = "NONE"
     if khas("POLAR-PREDICT"):          # predict.f:48-60: a bare keyword selects ASPC
         polpred = ((kget("POLAR-PREDICT") or "").split() or ["ASPC"])[0].upper()[:4]
@@ -618,7 +621,7 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         usolve_cutoff=usolve_applied, list_buffer=lbuffer,
         poleps=kfloat("POLAR-EPS", 1.0e-6), politer=int(kfloat("POLAR-ITER", 100)),
         poltyp=poltyp, polpred=polpred, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
-        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, **lists)
+        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, vdw=vdw, **lists)
 
 
 def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep_bonds: bool = True) -> System:
@@ -673,7 +676,14 @@ def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep
         pcgprec=sys.pcgprec, pcgguess=sys.pcgguess, pcgpeek=sys.pcgpeek, poltyp=sys.poltyp,
         polpred=sys.polpred, electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
         names=(sys.names * m) if sys.names is not None else None, bonds=bonds,
-        title=f"{sys.title} x{nx}x{ny}x{nz}")
+        title=f"{sys.title} x{nx}x{ny}x{nz}", vdw=_replicate_vdw(sys, m))
+
+
+def _replicate_vdw(sys, m):
+    if sys.vdw is None:
+        return None
+    from .vdwparams import replicate_vdw
+    return replicate_vdw(sys.vdw, sys.n, m, float(m))
 
 
 # ----------------------------------------------------------------------------
@@ -693,6 +703,9 @@ def save_system(path: str, sys: System) -> None:
         d["_" + k] = np.array(getattr(sys, k))
     d["_nfft"] = np.array(sys.nfft, np.int64)
     d["_polpred"] = np.array(sys.polpred)
+    if sys.vdw is not None:
+        from .vdwparams import vdw_to_dict
+        d.update(vdw_to_dict(sys.vdw))
     np.savez_compressed(path, **d)
 
 
@@ -706,4 +719,6 @@ def load_system(path: str) -> System:
         kw["polpred"] = str(z["_polpred"])
     kw["nfft"] = tuple(int(v) for v in z["_nfft"])
     kw.setdefault("types", None)
+    from .vdwparams import vdw_from_npz
+    kw["vdw"] = vdw_from_npz(z)
     return System(**kw)
