@@ -70,6 +70,24 @@ typedef struct apx_system {
                               ulspredSum_cu does (src/cu/upredict.cu:204-206) */
 } apx_system;
 
+/* What evdwData(RcOp::ALLOC|INIT) uploads for the buffered 14-7 term, Vdw::HAL (src/evdw.cpp:62-470):
+ * the "next" row after the electrostatics path. */
+typedef struct apx_vdw {
+   int n;
+   const int* ired;          /* [n]  vdw::ired, 0-based: the atom a reduced hydrogen site hangs off (itself otherwise) */
+   const double* kred;       /* [n]  vdw::kred */
+   const int* jvdw;          /* [n]  compressed class index (src/evdw.cpp:176-188) */
+   int njvdw;
+   const double* radmin;     /* [njvdw][njvdw] */
+   const double* epsilon;    /* [njvdw][njvdw] */
+   int nvexclude;            /* pairs i<k whose vdW scale is not 1 (src/evdw.cpp:196-262) */
+   const int* vexclude;      /* [nvexclude][2] */
+   const double* vexclude_scale;
+   double cutoff, taper;     /* switchOff / switchCut(Switch::VDW) */
+   double ghal, dhal;
+   double elrc_vol, vlrc_vol; /* long-range correction x volume (src/evdw.cpp:443-452) */
+} apx_vdw;
+
 typedef struct apx_ctx apx_ctx;
 
 typedef struct apx_energy_result {
@@ -78,6 +96,8 @@ typedef struct apx_energy_result {
    int nem, nep;
    int pcg_iterations;
    double pcg_eps;         /* final RMS residual in Debye */
+   double ev;              /* energy_ev, 0 unless a vdW term is attached */
+   int nev;
 } apx_energy_result;
 
 /* timing / counters of the most recent operator call, CUDA events on the library stream */
@@ -90,6 +110,8 @@ typedef struct apx_stats {
    long long nverlet;      /* directed entries of the Verlet rows (cutoff + buffer) at the last list build */
    long long npairs_m;     /* pairs inside the real-space cutoff at the last list build */
    long long npairs_u;     /* pairs inside the preconditioner range at the last list build */
+   float ms_ehal;          /* device time of the vdW row kernel of the last evaluation */
+   long long nverlet_vdw;  /* directed entries of the vdW Verlet rows */
 } apx_stats;
 
 const char* apx_last_error(void);
@@ -150,6 +172,11 @@ int apx_energy(apx_ctx* ctx, int vers, apx_energy_result* out);
 /* empole(vers), epolar(vers): src/amoeba/empole.cpp:81-138, src/amoeba/epolar.cpp:574-649 */
 int apx_empole(apx_ctx* ctx, int vers, apx_energy_result* out);
 int apx_epolar(apx_ctx* ctx, int vers, apx_energy_result* out);
+/* evdwData(ALLOC|INIT): src/evdw.cpp:62-470.  Once attached, apx_energy() also evaluates the vdW term -- on its own
+ * stream, beside the induced-dipole solver -- and esum / virial / gradient include it (energy(vers), src/energy.cpp:319-448). */
+int apx_vdw_attach(apx_ctx* ctx, const apx_vdw* vdw);
+/* evdw(vers) -> ehal_cu: src/evdw.cpp:472-530, src/cu/ehal.cu:125-160 (vdW alone: ev, nev, virial, gradient) */
+int apx_evdw(apx_ctx* ctx, int vers, apx_energy_result* out);
 /* copyGradient: src/egvop.cpp:64-111 (fixed -> double, caller's order) */
 int apx_get_gradient(apx_ctx* ctx, double* grad /* [n][3] */);
 

@@ -57,13 +57,23 @@ class _ApxSystem(C.Structure):
 
 class EnergyResult(C.Structure):
     _fields_ = [("em", C.c_double), ("ep", C.c_double), ("esum", C.c_double), ("virial", C.c_double * 9),
-                ("nem", C.c_int), ("nep", C.c_int), ("pcg_iterations", C.c_int), ("pcg_eps", C.c_double)]
+                ("nem", C.c_int), ("nep", C.c_int), ("pcg_iterations", C.c_int), ("pcg_eps", C.c_double),
+                ("ev", C.c_double), ("nev", C.c_int)]
+
+
+class _ApxVdw(C.Structure):
+    _fields_ = [("n", C.c_int), ("ired", C.POINTER(C.c_int)), ("kred", C.POINTER(C.c_double)), ("jvdw", C.POINTER(C.c_int)),
+                ("njvdw", C.c_int), ("radmin", C.POINTER(C.c_double)), ("epsilon", C.POINTER(C.c_double)),
+                ("nvexclude", C.c_int), ("vexclude", C.POINTER(C.c_int)), ("vexclude_scale", C.POINTER(C.c_double)),
+                ("cutoff", C.c_double), ("taper", C.c_double), ("ghal", C.c_double), ("dhal", C.c_double),
+                ("elrc_vol", C.c_double), ("vlrc_vol", C.c_double)]
 
 
 class Stats(C.Structure):
     _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
                 ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
-                ("nverlet", C.c_longlong), ("npairs_m", C.c_longlong), ("npairs_u", C.c_longlong)]
+                ("nverlet", C.c_longlong), ("npairs_m", C.c_longlong), ("npairs_u", C.c_longlong),
+                ("ms_ehal", C.c_float), ("nverlet_vdw", C.c_longlong)]
 
 
 _LIBS = {}
@@ -109,6 +119,7 @@ def load_library(precision="mixed"):
         "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int],
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
         "apx_get_dist_info": [C.POINTER(C.c_int)],
+        "apx_vdw_attach": [C.POINTER(_ApxVdw)], "apx_evdw": [C.c_int, C.POINTER(EnergyResult)],
         "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     }.items():
         fn = getattr(lib, name)
@@ -180,7 +191,8 @@ class Amoeba:
     `world` GPUs (transport "nccl": handle = nccl_unique_id() of rank 0; "local": handle = LocalHub).
     Every method is then collective (all ranks call it in the same order)."""
 
-    def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None):
+    def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None, vdw: bool = False):
+        """vdw=True also attaches the buffered 14-7 term of `system.vdw` (evdwData): energy() then returns the sum."""
         self.lib = load_library(precision)
         self.system = system
         self.n = system.n
@@ -244,6 +256,33 @@ class Amoeba:
                 self.ctx = None
             raise ApxError(msg)
         self.last = None
+        if vdw:
+            self.attach_vdw(system.vdw)
+
+    def attach_vdw(self, v):
+        """evdwData(RcOp::ALLOC|INIT), src/evdw.cpp:62-470."""
+        if v is None:
+            raise ApxError("system has no buffered 14-7 vdW term")
+        keep = [np.ascontiguousarray(v.ired, np.int32), np.ascontiguousarray(v.kred, np.float64),
+                np.ascontiguousarray(v.jvdw, np.int32), np.ascontiguousarray(v.radmin, np.float64),
+                np.ascontiguousarray(v.epsilon, np.float64),
+                np.ascontiguousarray(v.vexclude.reshape(-1, 2) if v.vexclude.size else np.zeros((1, 2)), np.int32),
+                np.ascontiguousarray(v.vexclude_scale if v.vexclude.size else np.ones(1), np.float64)]
+        s = _ApxVdw()
+        s.n = self.n
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        s.ired, s.kred, s.jvdw = keep[0].ctypes.data_as(ip), keep[1].ctypes.data_as(dp), keep[2].ctypes.data_as(ip)
+        s.njvdw = int(v.radmin.shape[0])
+        s.radmin, s.epsilon = keep[3].ctypes.data_as(dp), keep[4].ctypes.data_as(dp)
+        s.nvexclude = int(v.vexclude.shape[0]) if v.vexclude.size else 0
+        s.vexclude, s.vexclude_scale = keep[5].ctypes.data_as(ip), keep[6].ctypes.data_as(dp)
+        s.cutoff, s.taper, s.ghal, s.dhal = float(v.cutoff), float(v.taper), float(v.ghal), float(v.dhal)
+        s.elrc_vol, s.vlrc_vol = float(v.elrc_vol), float(v.vlrc_vol)
+        self._chk(self.lib.apx_vdw_attach(self.ctx, C.byref(s)))
+
+    def evdw(self, vers=calc.v1):
+        """evdw(vers) alone (src/evdw.cpp:472-530)."""
+        return self._energy(self.lib.apx_evdw, vers)
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -328,7 +367,7 @@ class Amoeba:
         r = EnergyResult()
         self._chk(fn(self.ctx, int(vers), C.byref(r)))
         out = dict(em=r.em, ep=r.ep, esum=r.esum, virial=np.array(list(r.virial)).reshape(3, 3), nem=r.nem, nep=r.nep,
-                   pcg_iterations=r.pcg_iterations, pcg_eps=r.pcg_eps)
+                   pcg_iterations=r.pcg_iterations, pcg_eps=r.pcg_eps, ev=r.ev, nev=r.nev)
         if vers & calc.grad:
             out["grad"] = self.gradient()
         self.last = out

@@ -344,6 +344,7 @@ void apx_destroy(apx_ctx* c)
    cudaStreamSynchronize(c->stream2);
    apx_pcg_graphs_invalidate(c);
    apx_pme_destroy(c);
+   apx_vdw_destroy(c);
    apx_dist_destroy(c);
    // views into the arenas are not owned
    c->gx.p = c->gy.p = c->gz.p = c->trqf.p = c->ebuf.p = nullptr;
@@ -511,7 +512,39 @@ int apx_energy(apx_ctx* c, int vers, apx_energy_result* out)
    API_BEGIN
    CUDA_CHECK(cudaSetDevice(c->device));
    ensure_ready(c);
-   apx_energy_impl(c, vers, true, true, out);
+   apx_energy_impl(c, vers, true, true, out, true);
+   API_END
+}
+
+int apx_vdw_attach(apx_ctx* c, const apx_vdw* v)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   apx_vdw_attach_impl(c, v);
+   API_END
+}
+
+// evdw(vers) alone: zero the accumulators, ehal, reductions (src/evdw.cpp:472-530)
+int apx_evdw(apx_ctx* c, int vers, apx_energy_result* out)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (!c->vdw.on)
+      APX_THROW("apx_evdw: no vdW term attached (apx_vdw_attach)");
+   ensure_ready(c);
+   CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, c->stream));
+   apx_vdw_launch(c, vers);
+   apx_vdw_join(c);
+   if (c->dist.on && (vers & APX_GRAD))
+      apx_dist_allreduce_u64(c, c->gx.p, (size_t)(c->gz.p + c->npad - c->gx.p));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   apx_energy_result r;
+   memset(&r, 0, sizeof(r));
+   apx_vdw_collect(c, vers, &r);
+   r.esum = r.ev;
+   if (out)
+      *out = r;
    API_END
 }
 

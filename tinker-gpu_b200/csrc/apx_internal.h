@@ -128,8 +128,40 @@ struct DistState {
    long long halo_atoms = 0;
 };
 
+// ---- buffered 14-7 vdW term (ehal.cu)
+struct VdwExcl {            // pair in SORTED indices whose scale is neither 0 nor 1: (scale - 1) correction
+   int i, k;
+   real s;
+};
+struct VdwState {
+   int on = 0, nj = 0;
+   DevBuf<int> ired_o, jvdw_o;           // caller order
+   DevBuf<real> kred_o;
+   DevBuf<real2> tab;                    // [nj*nj] {radmin, epsilon}
+   DevBuf<int> exoff, exlist;            // CSR (caller indices) of partners with scale 0: never listed
+   DevBuf<int> xs_ik;                    // pairs with another scale, caller order
+   DevBuf<real> xs_sc;
+   DevBuf<VdwExcl> xs_s;
+   int nxs = 0;
+   real exrange = 0;                     // no excluded pair is farther apart than this (bonded topology)
+   DevBuf<real4> pred;                   // sorted reduced sites {x,y,z wrapped, jvdw bits}
+   DevBuf<int> ired_s;                   // sorted slot of the parent atom
+   DevBuf<real> kred_s;
+   DevBuf<real4> ctr, ext;               // block boxes of the reduced sites
+   RowList rows;
+   DevBuf<fixed_t> vbuf;                 // [0] ev, [1..6] virial xx yx zx yy zy zz
+   DevBuf<int> vcnt;                     // nev
+   fixed_t h_vbuf[8] = {0};              // host copies, valid after the main stream is synchronised
+   int h_vcnt[2] = {0, 0};
+   real cut = 0, off = 0, ghal = 0, dhal = 0;
+   double elrc_vol = 0, vlrc_vol = 0;
+   cudaStream_t stream = nullptr;        // ehal runs here, beside induce() on the main stream
+   cudaEvent_t ev_go = nullptr, ev_done = nullptr, t0 = nullptr, t1 = nullptr;
+};
+
 struct apx_ctx {
    int device = 0;
+   VdwState vdw;
    DistState dist;
    int a0 = 0, a1 = 0;                   // owned sorted range (single GPU: [0, n))
    int zbase = 0, nzl = 0;               // local PME planes: global plane zg lives at (zg - zbase) mod nfft3, nzl planes held
@@ -261,8 +293,18 @@ void apx_dist_pme_destroy(apx_ctx* c);
 void apx_dist_fft_forward(apx_ctx* c, cplx* tb);                   // local grid (halo-reduced) -> transformed slab tb
 void apx_dist_fft_inverse(apx_ctx* c, cplx* tb);                   // tb -> local grid including halo planes
 void apx_dist_destroy(apx_ctx* c);
+// ---- ehal.cu
+void apx_vdw_attach_impl(apx_ctx* c, const apx_vdw* v);
+void apx_vdw_refresh(apx_ctx* c, bool rebuilt);                    // reduced sites (every step), rows (at list rebuild)
+void apx_vdw_launch(apx_ctx* c, int vers);                         // enqueue ehal on the vdW stream (forked from the main stream)
+void apx_vdw_join(apx_ctx* c);                                     // main stream waits for it
+void apx_vdw_collect(apx_ctx* c, int vers, apx_energy_result* r);  // after the main stream is synchronised: ev, nev, virial into r
+void apx_vdw_destroy(apx_ctx* c);
+void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext);
 // ---- rows.cu
 void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort
+void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bctr, const real4* bext, real range, const int* exoff,
+   const int* exlist, real exrange, bool want_compact);
 void apx_rows_compact(apx_ctx* c, bool count);    // per-step compaction to r <= cutoff
 // ---- frames.cu
 void apx_rotpole(apx_ctx* c);
@@ -304,4 +346,4 @@ void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
 // ---- mplar.cu
-void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out);
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw = false);

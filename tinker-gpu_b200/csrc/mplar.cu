@@ -683,7 +683,7 @@ void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p);
 
-void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out)
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw)
 {
    const int n = c->n;
    const int a0 = c->a0, no = c->a1 - c->a0, n3 = 3 * no;      // per-atom passes run on the owned range
@@ -699,6 +699,10 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    // ---- zero accumulators
    // gx gy gz trqf ebuf dbuf cnt are contiguous (arena_e, apx_api.cu): one memset
    CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, st));
+   // ---- vdW term on its own stream, beside everything below (joins before the reductions)
+   do_vdw = do_vdw && c->vdw.on;
+   if (do_vdw)
+      apx_vdw_launch(c, vers);
    // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
    int iters = 0;
    if (do_p) {
@@ -808,6 +812,8 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       APX_COUNT_LAUNCH(c);
       apx_torque(c, do_v);
    }
+   if (do_vdw)
+      apx_vdw_join(c);
    if (dist) {
       // every GPU holds partial sums: forces on frame atoms may belong to a neighbour's slab
       if (do_g)
@@ -860,6 +866,12 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    }
    r.pcg_iterations = iters;
    r.pcg_eps = do_p ? c->scal_h[2] : 0.0;
+   r.ev = 0;
+   r.nev = 0;
+   if (do_vdw) {
+      apx_vdw_collect(c, vers, &r);
+      r.esum += r.ev;
+   }
    if (out)
       *out = r;
 }

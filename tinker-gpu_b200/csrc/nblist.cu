@@ -9,6 +9,7 @@
 // * the list is rebuilt when any atom moved more than buffer/2 since the last build, the
 //   reference's criterion (src/nblist.cpp:521-531).
 #include "apx_internal.h"
+#include "wrap.cuh"
 #include <cub/cub.cuh>
 
 namespace {
@@ -20,26 +21,6 @@ __device__ __forceinline__ unsigned spread3(unsigned v)
    v = (v | (v << 4)) & 0x030c30c3;
    v = (v | (v << 2)) & 0x09249249;
    return v;
-}
-
-__device__ __forceinline__ void wrap_pos(const Box& b, double x, double y, double z, real& wx, real& wy, real& wz, real& fx,
-   real& fy, real& fz)
-{
-   double f1 = x * (double)b.r[0] + y * (double)b.r[1] + z * (double)b.r[2];
-   double f2 = x * (double)b.r[3] + y * (double)b.r[4] + z * (double)b.r[5];
-   double f3 = x * (double)b.r[6] + y * (double)b.r[7] + z * (double)b.r[8];
-   f1 -= floor(f1);
-   f2 -= floor(f2);
-   f3 -= floor(f3);
-   if (f1 >= 1.0) f1 = 0.0;
-   if (f2 >= 1.0) f2 = 0.0;
-   if (f3 >= 1.0) f3 = 0.0;
-   fx = (real)f1;
-   fy = (real)f2;
-   fz = (real)f3;
-   wx = (real)(f1 * (double)b.l[0] + f2 * (double)b.l[1] + f3 * (double)b.l[2]);
-   wy = (real)(f1 * (double)b.l[3] + f2 * (double)b.l[4] + f3 * (double)b.l[5]);
-   wz = (real)(f1 * (double)b.l[6] + f2 * (double)b.l[7] + f3 * (double)b.l[8]);
 }
 
 // nslab > 1 (several GPUs): the key's top bits are the z-slab of the atom in PME grid coordinates
@@ -182,6 +163,12 @@ __global__ void k_check_moved(int n, const double* __restrict__ xyz, const doubl
 
 } // namespace
 
+void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext)
+{
+   k_block_boxes<<<(c->nblk * 32 + APX_BLOCK - 1) / APX_BLOCK, APX_BLOCK, 0, c->stream>>>(c->n, c->nblk, pos, ctr, ext);
+   APX_COUNT_LAUNCH(c);
+}
+
 void apx_update_sorted_positions(apx_ctx* c)
 {
    int g = (c->npad + 255) / 256;
@@ -207,6 +194,8 @@ void apx_list_refresh(apx_ctx* c, bool force)
    if (!rebuild) {
       apx_update_sorted_positions(c);
       apx_rows_compact(c, false);
+      if (c->vdw.on)
+         apx_vdw_refresh(c, false);
       return;
    }
    apx_pcg_graphs_invalidate(c);      // row buffers may be reallocated below
@@ -254,4 +243,6 @@ void apx_list_refresh(apx_ctx* c, bool force)
    c->stats.list_rebuilds++;
    c->list_valid = 1;
    c->mpole_inited = 0;     // sorted multipoles must be regenerated in the new order
+   if (c->vdw.on)
+      apx_vdw_refresh(c, true);
 }

@@ -65,7 +65,8 @@ __device__ __forceinline__ bool boxes_within(const Box& b, real4 ci, real4 ei, r
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, int a0, int a1, Box b, real range,
    const real4* __restrict__ posd, const real4* __restrict__ ctr, const real4* __restrict__ ext, const real4* __restrict__ sctr,
-   const real4* __restrict__ sext, int* __restrict__ vcnt, const int* __restrict__ vstart, int* __restrict__ vnbr)
+   const real4* __restrict__ sext, int* __restrict__ vcnt, const int* __restrict__ vstart, int* __restrict__ vnbr,
+   const int* __restrict__ perm, const int* __restrict__ exoff, const int* __restrict__ exlist, real exr2)
 {
    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const int ib = a0 / 32 + gw / RB_W, sub = gw % RB_W;
@@ -112,7 +113,20 @@ __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, in
                real dx = pk.x - __shfl_sync(FULL, pi.x, q), dy = pk.y - __shfl_sync(FULL, pi.y, q),
                     dz = pk.z - __shfl_sync(FULL, pi.z, q);
                apx_image(b, dx, dy, dz);
-               bool ok = in && s != ib * 32 + q && dx * dx + dy * dy + dz * dz <= range2;
+               const real r2q = dx * dx + dy * dy + dz * dz;
+               bool ok = in && s != ib * 32 + q && r2q <= range2;
+               if (exoff && __any_sync(FULL, ok && r2q <= exr2)) {
+                  // pairs that never interact (vdW 1-2/1-3 with scale 0) are left out of the rows for good:
+                  // exclusion is topology, so it is tested at list build, not in the pair kernel
+                  const int ci = perm[ib * 32 + q];
+                  const int eb = exoff[ci], ee = exoff[ci + 1];
+                  if (ok && r2q <= exr2) {
+                     const int ck = perm[s];
+                     for (int e = eb; e < ee; ++e)
+                        if (exlist[e] == ck)
+                           ok = false;
+                  }
+               }
                unsigned m = __ballot_sync(FULL, ok);
                if (FILL) {
                   int off = __shfl_sync(FULL, mybase + mycount, q);
@@ -178,12 +192,19 @@ __global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real
 
 void apx_rows_build(apx_ctx* c)
 {
-   RowList& L = c->rows;
+   apx_rows_build_on(c, c->rows, c->posd, c->blk_ctr, c->blk_ext, c->list_cutoff + c->list_buffer, nullptr, nullptr, 0, true);
+}
+
+// Verlet rows of the positions `pos` (sorted order, block boxes ctr/ext) within `range`.  exoff/exlist: optional CSR (caller
+// indices) of partners that are never listed; only pairs closer than exrange are tested against it.
+void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bctr, const real4* bext, real range, const int* exoff,
+   const int* exlist, real exrange, bool want_compact)
+{
    const int n = c->n, nblk = c->nblk, nsb = (nblk + 31) / 32;
    const int a0 = c->a0, a1 = c->a1;
    const int nib = a1 > a0 ? (a1 + 31) / 32 - a0 / 32 : 0;      // i-blocks that hold owned atoms
    const int grid = std::max(1, (nib * RB_W * 32 + 127) / 128);
-   const real range = c->list_cutoff + c->list_buffer;
+   const real exr2 = exrange * exrange;
    L.vstart.ensure(n + 1);
    L.vcnt.ensure(n + 1);
    L.cnt.ensure(n);
@@ -191,10 +212,10 @@ void apx_rows_build(apx_ctx* c)
    L.total.ensure(2);
    L.sctr.ensure(nsb);
    L.sext.ensure(nsb);
-   k_super_boxes<<<(nsb * 32 + 127) / 128, 128, 0, c->stream>>>(nblk, nsb, c->blk_ctr, c->blk_ext, L.sctr, L.sext);
+   k_super_boxes<<<(nsb * 32 + 127) / 128, 128, 0, c->stream>>>(nblk, nsb, bctr, bext, L.sctr, L.sext);
    CUDA_CHECK(cudaMemsetAsync(L.vcnt.p, 0, sizeof(int) * (n + 1), c->stream));
-   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.sctr, L.sext,
-      L.vcnt, nullptr, nullptr);
+   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+      L.vcnt, nullptr, nullptr, c->perm, exoff, exlist, exr2);
    size_t need = 0;
    cub::DeviceScan::ExclusiveSum(nullptr, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
    if (need > c->cubtmp.cap)
@@ -208,9 +229,10 @@ void apx_rows_build(apx_ctx* c)
       APX_THROW("neighbor rows exceed 2^31 entries");
    L.nverlet = total;
    L.vnbr.ensure((size_t)total + 32);
-   L.nbr.ensure((size_t)total + 32);
-   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, c->posd, c->blk_ctr, c->blk_ext, L.sctr, L.sext,
-      nullptr, L.vstart, L.vnbr);
+   if (want_compact)
+      L.nbr.ensure((size_t)total + 32);
+   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+      nullptr, L.vstart, L.vnbr, c->perm, exoff, exlist, exr2);
    c->stats.kernel_launches += 3;
 }
 

@@ -12,7 +12,7 @@ import threading
 from .amoeba import Amoeba, LocalHub, nccl_unique_id
 
 
-def run_local_ranks(system, world, fn, precision="mixed", device=0):
+def run_local_ranks(system, world, fn, precision="mixed", device=0, vdw=False):
     hub = LocalHub(world, precision)
     out = [None] * world
     err = [None] * world
@@ -20,7 +20,7 @@ def run_local_ranks(system, world, fn, precision="mixed", device=0):
     def work(rank):
         a = None
         try:
-            a = Amoeba(system, precision, device=device, dist=(rank, world, "local", hub))
+            a = Amoeba(system, precision, device=device, dist=(rank, world, "local", hub), vdw=vdw)
             out[rank] = fn(a, rank)
         except BaseException as e:      # noqa: BLE001 -- reported to the caller below
             err[rank] = e
@@ -43,14 +43,14 @@ def run_local_ranks(system, world, fn, precision="mixed", device=0):
     return out
 
 
-def nccl_context(system, precision="mixed"):
+def nccl_context(system, precision="mixed", vdw=False):
     """One rank of a torchrun job (RANK/WORLD_SIZE/LOCAL_RANK set, process group initialised)."""
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     dev = torch.cuda.current_device()
     if world == 1:
-        return Amoeba(system, precision, device=dev)
+        return Amoeba(system, precision, device=dev, vdw=vdw)
     ident = [nccl_unique_id(precision) if rank == 0 else None]
     dist.broadcast_object_list(ident, src=0)
-    return Amoeba(system, precision, device=dev, dist=(rank, world, "nccl", ident[0]))
+    return Amoeba(system, precision, device=dev, dist=(rank, world, "nccl", ident[0]), vdw=vdw)
