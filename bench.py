@@ -213,9 +213,9 @@ def run_ours(args, rank, world, local_rank):
     replicas = 1 if decomposed else world
     if decomposed:
         from tinker_gpu_b200.distributed import nccl_context
-        a = nccl_context(system, "mixed")
+        a = nccl_context(system, "mixed", vdw=args.vdw)
     else:
-        a = Amoeba(system, "mixed", device=local_rank)
+        a = Amoeba(system, "mixed", device=local_rank, vdw=args.vdw)
     ext = torch.cuda.ExternalStream(a.lib.apx_stream(a.ctx), device=local_rank)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     vers = calc.v4
@@ -316,6 +316,8 @@ def run_ours(args, rank, world, local_rank):
         metric = METRIC if args.workload == "dhfr2" else METRIC.replace("AMOEBA DHFR 23.5k atoms", wl_desc.split(",")[0])
         par = "single GPU" if world == 1 else (f"spatial decomposition over {world} GPUs (z-slabs, NCCL halo exchange + slab FFT all-to-all)"
                                                 if decomposed else f"replicas x{world}")
+        if args.vdw:
+            metric = metric.replace("electrostatics hot path only", "electrostatics hot path + buffered 14-7 vdW")
         line = {
             "metric": metric, "value": ns_per_day(ms_step, replicas), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "ms_per_induce": ms_ind,
@@ -344,6 +346,9 @@ def run_ours(args, rank, world, local_rank):
                               "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs)},
             "wall_s_timed_region": t_wall,
         }
+        if args.vdw:
+            line["vdw"] = {"ms_ehal_kernel": st["ms_ehal"], "directed_row_entries": int(st["nverlet_vdw"]),
+                           "cutoff": float(system.vdw.cutoff), "note": "ehal runs on its own stream beside induce()"}
         if not args.no_cpu and args.workload == "dhfr2":
             ms_cpu, ms_cpu_ind, desc = cpu_oracle_sample(system)
             line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc,
@@ -362,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--workload", default="dhfr2", choices=sorted(WORKLOADS))
+    ap.add_argument("--vdw", action="store_true", help="also evaluate the buffered 14-7 vdW term (SURVEY 8f rank 1) in every step")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas also for the large workloads")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

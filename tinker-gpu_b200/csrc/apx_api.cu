@@ -198,6 +198,12 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    c->f_elec = (real)(sys->electric / sys->dielec);
    if (const char* e = getenv("APX_NO_NATIVE_FFT"))
       c->native_fft = atoi(e) ? 0 : 1;
+   if (const char* e = getenv("APX_NO_RECORDS"))
+      c->use_records = atoi(e) ? 0 : 1;
+   if (const char* e = getenv("APX_UF_CTAS"))
+      c->uf_ctas = std::max(1, atoi(e));
+   if (const char* e = getenv("APX_UF_SMEM"))
+      c->uf_smem_kb = std::max(0, std::min(40, atoi(e)));
    if (const char* e = getenv("APX_NO_GRAPH"))
       c->use_graph = atoi(e) ? 0 : 1;
    set_box(c, sys->lvec);
@@ -304,6 +310,7 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    }
    c->io_a.ensure(3 * np);
    c->io_b.ensure(3 * np);
+   c->uf_rec.ensure(3 * np);
    c->list_cutoff = (real)std::min(sys->cutoff, 1.0e6);
    c->list_buffer = (real)sys->list_buffer;
    c->a0 = 0, c->a1 = c->n;

@@ -137,7 +137,7 @@ struct VdwState {
    int on = 0, nj = 0;
    DevBuf<int> ired_o, jvdw_o;           // caller order
    DevBuf<real> kred_o;
-   DevBuf<real2> tab;                    // [nj*nj] {radmin, epsilon}
+   DevBuf<real2> tab;                    // [nj*nj] {1/radmin, epsilon}
    DevBuf<int> exoff, exlist;            // CSR (caller indices) of partners with scale 0: never listed
    DevBuf<int> xs_ik;                    // pairs with another scale, caller order
    DevBuf<real> xs_sc;
@@ -210,6 +210,9 @@ struct apx_ctx {
    DevBuf<real> field, fieldp, udir, udirp, uind, uinp;
    DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
    DevBuf<real4> pk_p, pk_r, pk_z, pk_v, pk_f;   // packed (d,p) pairs, dp.cuh: direction, residual, M r, A p, real-space field
+   DevBuf<real4> uf_rec;                 // [npad][3] interleaved neighbour records of the ufield rows (field.cu)
+   int use_records = 1;                  // APX_NO_RECORDS=1: the separate-array kernel instead
+   int uf_ctas = 8, uf_smem_kb = 0;      // residency of the ufield rows beside the PME chain (APX_UF_CTAS, APX_UF_SMEM)
    cudaStream_t stream2 = nullptr;       // real-space operator of an iteration runs here, beside the PME chain
    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
    DevBuf<double> scal;                  // PCG scalars (sum, sump, a, ap, sum1, sump1, epsd, epsp ...)

@@ -95,23 +95,40 @@ struct HalPrm {
    real cut, off, off2, ghal, dhal, c1d, c1g, rswinv;      // c1d = (1+dhal)^7, c1g = 1+ghal, rswinv = 1/(cut-off)
 };
 
-// pair_hal_v2 (include/seq/pair_hal.h:52-92) with vlambda = 1; rv = radmin (1 for classes without vdW, whose eps is 0).
-// rho enters in the 7th power, so r and rho are formed with correctly rounded sqrt / division: a 2-ulp rsqrt
-// would cost 1e-6 of every repulsive pair energy.
-template <bool DO_G>
-__device__ __forceinline__ void pair_hal(const HalPrm& P, real r, real rv, real eps, real& e, real& de)
+#ifdef APX_DOUBLE
+__device__ __forceinline__ real r_rcp(real x) { return 1.0 / x; }
+__device__ __forceinline__ void r_sqrt_pair(real r2, real& r, real& rinv)
 {
-   const real rho = r / rv;
+   r = sqrt(r2);
+   rinv = 1.0 / r;
+}
+#else
+__device__ __forceinline__ real r_rcp(real x) { return __frcp_rn(x); }
+// r enters the energy in the 7th power: the 2-ulp hardware rsqrt gets one Newton step (two FMAs)
+__device__ __forceinline__ void r_sqrt_pair(real r2, real& r, real& rinv)
+{
+   const real y = rsqrtf(r2);
+   rinv = y * fmaf(-0.5f * r2 * y, y, 1.5f);
+   r = r2 * rinv;
+}
+#endif
+
+// pair_hal_v2 (include/seq/pair_hal.h:52-92) with vlambda = 1; rvinv = 1/radmin rounded once on the host
+// (1 for classes without vdW, whose eps is 0)
+template <bool DO_G>
+__device__ __forceinline__ void pair_hal(const HalPrm& P, real r, real rvinv, real eps, real& e, real& de)
+{
+   const real rho = r * rvinv;
    const real rho2 = rho * rho, rho6 = rho2 * rho2 * rho2, rho7 = rho6 * rho;
    const real a = rho + P.dhal, a2 = a * a, a6 = a2 * a2 * a2, a7 = a6 * a;
-   const real s1 = (real)1 / a7;
-   const real s2 = (real)1 / (rho7 + P.ghal);
+   const real s1 = r_rcp(a7);
+   const real s2 = r_rcp(rho7 + P.ghal);
    const real t1 = P.c1d * s1, t2 = P.c1g * s2;
    e = eps * t1 * (t2 - 2);
    if (DO_G) {
       const real dt1 = -7 * a6 * t1 * s1;
       const real dt2 = -7 * rho6 * t2 * s2;
-      de = eps * (dt1 * (t2 - 2) + t1 * dt2) / rv;
+      de = eps * (dt1 * (t2 - 2) + t1 * dt2) * rvinv;
    }
    if (r > P.cut) {
       // switchTaper5 (include/math/switch.h:23-32)
@@ -182,8 +199,8 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ehal_rows(int a0, int a1, Box bo
          const real r2 = dx * dx + dy * dy + dz * dz;
          if (r2 <= P.off2) {
             const real2 t = stab[ji + bits_int(pk.w)];
-            const real r = sqrt(r2);
-            const real rinv = (real)1 / r;
+            real r, rinv;
+            r_sqrt_pair(r2, r, rinv);
             real e, de = 0;
             pair_hal<DO_G>(P, r, t.x, t.y, e, de);
             ei += e;
@@ -270,7 +287,8 @@ __global__ void k_ehal_excl(int nx, const VdwExcl* __restrict__ ex, int a0, int 
    if (r2 > P.off2)
       return;
    const real2 t = tab[bits_int(pi.w) * nj + bits_int(pk.w)];
-   const real r = sqrt(r2), rinv = (real)1 / r;
+   real r, rinv;
+   r_sqrt_pair(r2, r, rinv);
    real e, de = 0;
    pair_hal<DO_G>(P, r, t.x, p.s * t.y, e, de);
    const double share = (own_i ? 0.5 : 0.0) + (own_k ? 0.5 : 0.0);
@@ -350,7 +368,7 @@ void apx_vdw_attach_impl(apx_ctx* c, const apx_vdw* v)
    {
       std::vector<real2> t((size_t)V.nj * V.nj);
       for (size_t q = 0; q < t.size(); ++q) {
-         t[q].x = v->radmin[q] > 0 ? (real)v->radmin[q] : (real)1;
+         t[q].x = v->radmin[q] > 0 ? (real)(1.0 / v->radmin[q]) : (real)1;
          t[q].y = (real)v->epsilon[q];
       }
       V.tab.ensure(t.size() + 1);

@@ -73,6 +73,69 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int a0, int a1, Box 
    }
 }
 
+// ---- record form of the same operator ------------------------------------------------------
+// ncu (profiles/r01j_ncu_full_summary.txt, 1 M atoms) shows the kernel above bound by L1 sector traffic
+// (l1tex 86 % of peak, FMA pipe 37 %): every neighbour costs four 32-byte sectors -- posd, tpj and the two
+// halves of the packed dipoles live in three different arrays.  k_uf_records interleaves what a pair needs
+// into ONE 48-byte record per atom, rec[3s] = (x,y,z,pdamp), rec[3s+1] = (d.x,d.y,d.z,p.x),
+// rec[3s+2] = (p.y,p.z,thole,polarity): two sectors and three 16-byte loads per neighbour.
+__global__ void k_uf_records(int n, const real4* __restrict__ posd, const real4* __restrict__ tpj, const real4* __restrict__ U,
+   real4* __restrict__ rec, const int* __restrict__ skip)
+{
+   if (skip && skip[1])
+      return;
+   int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= n)
+      return;
+   const real4 q = tpj[s];
+   real4 b = U[2 * s + 1];
+   b.z = q.x;
+   b.w = q.y;
+   rec[3 * s] = posd[s];
+   rec[3 * s + 1] = U[2 * s];
+   rec[3 * s + 2] = b;
+}
+
+template <bool EWALD, int G>
+__global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows_rec(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
+   const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ rec, real4* __restrict__ F,
+   const int* __restrict__ skip)
+{
+   if (skip && skip[1])
+      return;
+   ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
+   {
+      const real4 pi = rec[3 * i];
+      const real thi = rec[3 * i + 2].z;
+      const int beg = vstart[i];
+      const int len = act ? cnt[i] : 0;
+      V3 fdi = v3(0, 0, 0), fpi = v3(0, 0, 0);
+      for (int q = l; q < len; q += G) {
+         const int k = nbr[beg + q];
+         const real4 pk = rec[3 * k], ua = rec[3 * k + 1], ub = rec[3 * k + 2];
+         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+         apx_image(box, dx, dy, dz);
+         const real r2 = dx * dx + dy * dy + dz * dz;
+         const real rinv = r_rsqrt(r2);
+         const real r = r2 * rinv, rr2 = rinv * rinv;
+         real rr[3], bn[3], om[3];
+         radial_coulomb<3>(rinv, rr2, rr);
+         if (EWALD)
+            radial_ewald<3>(r, rinv, rr2, aewald, bn);
+         thole_one_minus_lambda<3>(r, pi.w, pk.w, min(thi, ub.z), om);
+         const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
+         const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
+         const V3 R = v3(dx, dy, dz);
+         fdi += dipole_field(R, v3(ua.x, ua.y, ua.z), B1, B2);
+         fpi += dipole_field(R, v3(ua.w, ub.x, ub.y), B1, B2);
+      }
+      fdi = group_sum3<G>(fdi);
+      fpi = group_sum3<G>(fpi);
+      if (l == 0 && act)
+         store_dp(F, i, fdi, fpi);
+   }
+}
+
 // exclusion pass for ufield (only pairs whose u-scale != 1; empty for stock AMOEBA)
 template <bool TABLE>
 __global__ void k_ufield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
@@ -383,9 +446,12 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    bool tb = c->thole_table != 0;
    // 8 CTAs per SM: the rows run beside the PME spread/FFT chain of the other stream and must leave
    // room for its CTAs (a grid that fills every SM first delays the spread by the length of a wave)
-   int grid = rows_grid<UF_G>(c, 8);
+   int grid = rows_grid<UF_G>(c, c->uf_ctas);
+   // unused dynamic shared memory caps how many of these long-lived CTAs one SM can hold, whatever order the
+   // hardware fills the SMs in: the FFT CTAs of the other stream (512 threads, 33 KB) must always find room
+   const size_t uf_smem = (size_t)c->uf_smem_kb * 1024;
 #define LAUNCH_UF(E, T)                                                                                                   \
-   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
+   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
       c->thlval, c->opt.njpolar, U, F, c->skip)
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
@@ -394,7 +460,16 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       c->uf_used += 2;
       cudaEventRecord(c->uf_ev[slot], st);
    }
-   if (ew && tb) LAUNCH_UF(true, true);
+   if (!tb && c->use_records) {
+      // records of every atom a row can reach: the whole system (halo atoms included on several GPUs)
+      c->uf_rec.ensure(3 * (size_t)c->npad);
+      k_uf_records<<<(c->n + 255) / 256, 256, 0, st>>>(c->n, c->posd, c->tpj, U, c->uf_rec, c->skip);
+      APX_COUNT_LAUNCH(c);
+      if (ew)
+         k_ufield_rows_rec<true, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->uf_rec, F, c->skip);
+      else
+         k_ufield_rows_rec<false, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->uf_rec, F, c->skip);
+   } else if (ew && tb) LAUNCH_UF(true, true);
    else if (ew) LAUNCH_UF(true, false);
    else if (tb) LAUNCH_UF(false, true);
    else LAUNCH_UF(false, false);
