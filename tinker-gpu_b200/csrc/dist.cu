@@ -57,6 +57,7 @@ struct NcclApi {
    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
    ncclResult_t (*GroupStart)() = nullptr;
@@ -87,6 +88,7 @@ NcclApi* nccl_api(const char* path)
    BIND(CommInitRank, "ncclCommInitRank");
    BIND(CommDestroy, "ncclCommDestroy");
    BIND(AllReduce, "ncclAllReduce");
+   BIND(AllGather, "ncclAllGather");
    BIND(Send, "ncclSend");
    BIND(Recv, "ncclRecv");
    BIND(GroupStart, "ncclGroupStart");
@@ -125,6 +127,161 @@ struct NcclComm : ApxComm {
          NCCL_CHECK(api, api->Recv(o.ptr, o.bytes, ncclChar, o.peer, comm, st));
       NCCL_CHECK(api, api->GroupEnd());
    }
+};
+
+// ---- peer-memory transport for the bulk exchanges (one process per GPU, NVLink / NVSwitch)
+//
+// NCCL's grouped send/recv moved the 36 MB transpose blocks of the 1 M-atom box at ~300 GB/s and small
+// halo messages at ~55 GB/s (profiles/r01g_trace_water1m_n2.txt): four such exchanges per CG operator sit
+// on the critical path.  Here every rank exposes a receive window through CUDA IPC; a sender copies
+// straight into the receiver's window over NVLink (cudaMemcpyAsync to the mapped peer pointer: copy
+// engines, no SMs), then raises a sequence flag in the receiver's memory; the receiver's stream waits
+// on the flag with a one-thread kernel, moves the data from the window to its destination and
+// acknowledges, so that the window can be reused two exchanges later (two slots per sender).
+// Everything is stream ordered; the host never blocks.  Small all-reduces stay on NCCL, which also
+// carries the IPC handles at start-up.  APX_DIST_P2P=0 keeps NCCL send/recv for everything.
+__global__ void k_flag_wait(const volatile unsigned* flag, unsigned want)
+{
+   // sequence numbers only grow; unsigned difference handles wrap-around
+   while ((int)(*flag - want) < 0)
+      __nanosleep(200);
+   __threadfence_system();
+}
+__global__ void k_flag_set(volatile unsigned* flag, unsigned value)
+{
+   __threadfence_system();
+   *flag = value;
+}
+
+struct P2pComm : NcclComm {
+   size_t window = 0;                       // bytes one sender may put into one slot
+   char* win = nullptr;                     // my receive windows: [sender][slot][window]
+   unsigned* flg = nullptr;                 // my flags: ready[sender][slot], then ack[receiver][slot]
+   std::vector<char*> peer_win;             // peers' windows / flags mapped into this process
+   std::vector<unsigned*> peer_flg;
+   unsigned seq = 0;
+   bool ok = false;
+   static size_t al(size_t b) { return (b + 255) / 256 * 256; }
+   unsigned* ready_of(unsigned* base, int sender, int slot) const { return base + (sender * 2 + slot); }
+   unsigned* ack_of(unsigned* base, int receiver, int slot) const { return base + 2 * world + (receiver * 2 + slot); }
+   char* slot_of(char* base, int sender, int slot) const { return base + ((size_t)sender * 2 + slot) * window; }
+
+   void setup(size_t window_bytes)
+   {
+      struct Handles {
+         cudaIpcMemHandle_t w, f;
+      };
+      window = al(window_bytes);
+      CUDA_CHECK(cudaMalloc(&win, (size_t)world * 2 * window));
+      CUDA_CHECK(cudaMalloc(&flg, sizeof(unsigned) * 4 * world));
+      CUDA_CHECK(cudaMemset(flg, 0, sizeof(unsigned) * 4 * world));
+      Handles mine;
+      CUDA_CHECK(cudaIpcGetMemHandle(&mine.w, win));
+      CUDA_CHECK(cudaIpcGetMemHandle(&mine.f, flg));
+      Handles* dev = nullptr;
+      CUDA_CHECK(cudaMalloc(&dev, sizeof(Handles) * (world + 1)));
+      CUDA_CHECK(cudaMemcpy(dev + world, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
+      NCCL_CHECK(api, api->AllGather(dev + world, dev, sizeof(Handles), ncclChar, comm, nullptr));
+      CUDA_CHECK(cudaStreamSynchronize(nullptr));
+      std::vector<Handles> all(world);
+      CUDA_CHECK(cudaMemcpy(all.data(), dev, sizeof(Handles) * world, cudaMemcpyDeviceToHost));
+      cudaFree(dev);
+      peer_win.assign(world, nullptr);
+      peer_flg.assign(world, nullptr);
+      for (int r = 0; r < world; ++r) {
+         if (r == rank) {
+            peer_win[r] = win;
+            peer_flg[r] = flg;
+            continue;
+         }
+         void* a = nullptr;
+         void* b = nullptr;
+         CUDA_CHECK(cudaIpcOpenMemHandle(&a, all[r].w, cudaIpcMemLazyEnablePeerAccess));
+         CUDA_CHECK(cudaIpcOpenMemHandle(&b, all[r].f, cudaIpcMemLazyEnablePeerAccess));
+         peer_win[r] = static_cast<char*>(a);
+         peer_flg[r] = static_cast<unsigned*>(b);
+      }
+      ok = true;
+   }
+   ~P2pComm() override
+   {
+      if (!ok)
+         return;
+      cudaDeviceSynchronize();
+      for (int r = 0; r < world; ++r)
+         if (r != rank) {
+            if (peer_win[r]) cudaIpcCloseMemHandle(peer_win[r]);
+            if (peer_flg[r]) cudaIpcCloseMemHandle(peer_flg[r]);
+         }
+      // every peer must have unmapped before the owner frees: the NCCL communicator is still alive here
+      int* d = nullptr;
+      if (cudaMalloc(&d, sizeof(int)) == cudaSuccess) {
+         cudaMemset(d, 0, sizeof(int));
+         api->AllReduce(d, d, 1, ncclInt32, ncclSum, comm, nullptr);
+         cudaStreamSynchronize(nullptr);
+         cudaFree(d);
+      }
+      cudaFree(win);
+      cudaFree(flg);
+   }
+   void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) override
+   {
+      if (!ok) {
+         NcclComm::exchange(sends, recvs, st);
+         return;
+      }
+      // per-peer totals decide the path of that pair; both ends see the same byte counts
+      std::vector<size_t> tot_s(world, 0), tot_r(world, 0);
+      for (const Op& o : sends)
+         tot_s[o.peer] += al(o.bytes);
+      for (const Op& o : recvs)
+         tot_r[o.peer] += al(o.bytes);
+      std::vector<Op> ns, nr;
+      for (const Op& o : sends)
+         if (tot_s[o.peer] > window)
+            ns.push_back(o);
+      for (const Op& o : recvs)
+         if (tot_r[o.peer] > window)
+            nr.push_back(o);
+      ++seq;
+      const int slot = (int)(seq & 1u);
+      // 1. my data into the peers' windows
+      for (int p = 0; p < world; ++p) {
+         if (p == rank || tot_s[p] == 0 || tot_s[p] > window)
+            continue;
+         if (seq > 2)      // the peer has emptied this slot (what I wrote two exchanges ago)
+            k_flag_wait<<<1, 1, 0, st>>>(ack_of(flg, p, slot), last_used[p][slot]);
+         size_t off = 0;
+         char* dst = slot_of(peer_win[p], rank, slot);
+         for (const Op& o : sends)
+            if (o.peer == p) {
+               if (o.bytes)
+                  CUDA_CHECK(cudaMemcpyAsync(dst + off, o.ptr, o.bytes, cudaMemcpyDefault, st));
+               off += al(o.bytes);
+            }
+         k_flag_set<<<1, 1, 0, st>>>(ready_of(peer_flg[p], rank, slot), seq);
+         last_used[p][slot] = seq;
+      }
+      // 2. oversized pairs through NCCL
+      if (!ns.empty() || !nr.empty())
+         NcclComm::exchange(ns, nr, st);
+      // 3. the peers' data out of my windows
+      for (int p = 0; p < world; ++p) {
+         if (p == rank || tot_r[p] == 0 || tot_r[p] > window)
+            continue;
+         k_flag_wait<<<1, 1, 0, st>>>(ready_of(flg, p, slot), seq);
+         size_t off = 0;
+         const char* src = slot_of(win, p, slot);
+         for (const Op& o : recvs)
+            if (o.peer == p) {
+               if (o.bytes)
+                  CUDA_CHECK(cudaMemcpyAsync(o.ptr, src + off, o.bytes, cudaMemcpyDeviceToDevice, st));
+               off += al(o.bytes);
+            }
+         k_flag_set<<<1, 1, 0, st>>>(ack_of(peer_flg[p], rank, slot), seq);
+      }
+   }
+   unsigned last_used[16][2] = {};
 };
 
 // ---- in-process transport: `world` ranks = host threads of one process on one device
@@ -603,13 +760,22 @@ const char* apx_dist_error() { return g_dist_err.c_str(); }
 ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id)
 {
    NcclApi* api = nccl_api(lib);
-   NcclComm* cm = new NcclComm();
+   int p2p = 1;
+   if (const char* e = getenv("APX_DIST_P2P"))
+      p2p = atoi(e);
+   P2pComm* cm = new P2pComm();
    cm->api = api;
    cm->rank = rank;
    cm->world = world;
    ncclUniqueId id;
    memcpy(&id, unique_id, sizeof(id));
    NCCL_CHECK(api, api->CommInitRank(&cm->comm, world, id, rank));
+   if (p2p && world <= 16) {
+      size_t mb = 64;
+      if (const char* e = getenv("APX_DIST_WINDOW_MB"))
+         mb = (size_t)std::max(1, atoi(e));
+      cm->setup(mb << 20);
+   }
    return cm;
 }
 
