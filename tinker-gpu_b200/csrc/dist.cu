@@ -139,7 +139,7 @@ struct NcclComm : ApxComm {
 // on the flag with a one-thread kernel, moves the data from the window to its destination and
 // acknowledges, so that the window can be reused two exchanges later (two slots per sender).
 // Everything is stream ordered; the host never blocks.  Small all-reduces stay on NCCL, which also
-// carries the IPC handles at start-up.  APX_DIST_P2P=0 keeps NCCL send/recv for everything.
+// carries the IPC handles at start-up.  APX_DIST_P2P=0/1 forces NCCL send/recv / the windows (default: windows at 2 GPUs).
 __global__ void k_flag_wait(const volatile unsigned* flag, unsigned want)
 {
    // sequence numbers only grow; unsigned difference handles wrap-around
@@ -760,7 +760,10 @@ const char* apx_dist_error() { return g_dist_err.c_str(); }
 ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id)
 {
    NcclApi* api = nccl_api(lib);
-   int p2p = 1;
+   // measured on the 1 M-atom box (profiles/r01p..., r01s...): 2 GPUs 21.5 ms (peer windows) vs 22.3 (NCCL); 4 GPUs 15.3 vs
+   // 13.0 -- the per-peer copies of one exchange are issued on ONE stream and serialise, where NCCL's grouped send/recv
+   // runs all peers at once.  Until the copies become one push kernel for all peers, the windows are the default at 2 GPUs.
+   int p2p = world == 2 ? 1 : 0;
    if (const char* e = getenv("APX_DIST_P2P"))
       p2p = atoi(e);
    P2pComm* cm = new P2pComm();
