@@ -193,6 +193,7 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    CUDA_CHECK(cudaEventCreate(&c->ev3));
    CUDA_CHECK(cudaMallocHost(&c->flags_h, 8 * sizeof(int)));
    CUDA_CHECK(cudaMallocHost(&c->scal_h, 8 * sizeof(double)));
+   CUDA_CHECK(cudaMallocHost(&c->red_h, 4096));
    memset(&c->stats, 0, sizeof(c->stats));
    c->stats.npairs_m = -1;
    c->f_elec = (real)(sys->electric / sys->dielec);
@@ -359,6 +360,7 @@ void apx_destroy(apx_ctx* c)
    c->arena_e.release(), c->arena_p.release();
    if (c->flags_h) cudaFreeHost(c->flags_h);
    if (c->scal_h) cudaFreeHost(c->scal_h);
+   if (c->red_h) cudaFreeHost(c->red_h);
    if (c->pin_a) cudaFreeHost(c->pin_a);
    cudaEventDestroy(c->ev0);
    cudaEventDestroy(c->ev1);

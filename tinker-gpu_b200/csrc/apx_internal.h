@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <map>
 #include <vector>
 
 #ifdef APX_DOUBLE
@@ -268,6 +269,15 @@ struct apx_ctx {
    std::vector<PcgGraph> graphs;
    int use_graph = 1;
    int capturing = 0;
+   // ---- CUDA graphs of the fixed launch sequences around the solver (pcg.cu: apx_graph_begin/end): mpoleInit + zeroing,
+   //      the permanent-field / first-residual prologue of induce(), the energy/force epilogue.  Keyed by what varies.
+   struct StepGraph {
+      cudaGraphExec_t exec = nullptr;
+      int launches = 0, warm = 0;
+   };
+   std::map<int, StepGraph> step_graphs;
+   int graph_key_open = -1, graph_launches_before = 0;
+   unsigned char* red_h = nullptr;       // pinned: one copy brings every reduced scalar of a step to the host
 
    // ---- stats
    apx_stats stats;
@@ -344,6 +354,10 @@ void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, rea
 // ---- pcg.cu
 void apx_induce_impl(apx_ctx* c);
 void apx_pcg_graphs_invalidate(apx_ctx* c);
+// if (apx_graph_begin(c, key)) { enqueue the region on c->stream; apx_graph_end(c, key); }
+// first call: runs eagerly (lazy allocations happen); second: captured, instantiated, launched; later: replayed.
+bool apx_graph_begin(apx_ctx* c, int key);
+void apx_graph_end(apx_ctx* c, int key);
 void apx_upred_configure(apx_ctx* c, int polpred);             // sets opt.polpred, sizes and empties the ring
 void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);

@@ -522,8 +522,9 @@ void apx_vdw_join(apx_ctx* c)
       apx_dist_allreduce_u64(c, V.vbuf.p, 8);
       apx_dist_allreduce_i32(c, V.vcnt.p, 2);
    }
-   CUDA_CHECK(cudaMemcpyAsync(V.h_vbuf, V.vbuf.p, sizeof(V.h_vbuf), cudaMemcpyDeviceToHost, c->stream));
-   CUDA_CHECK(cudaMemcpyAsync(V.h_vcnt, V.vcnt.p, sizeof(V.h_vcnt), cudaMemcpyDeviceToHost, c->stream));
+   // pinned landing zone behind the electrostatics scalars (apx_ctx::red_h)
+   CUDA_CHECK(cudaMemcpyAsync(c->red_h + 2048, V.vbuf.p, sizeof(fixed_t) * 8, cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaMemcpyAsync(c->red_h + 2048 + 64, V.vcnt.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));
 }
 
 // call with the main stream synchronised after apx_vdw_join
@@ -531,8 +532,8 @@ void apx_vdw_collect(apx_ctx* c, int vers, apx_energy_result* r)
 {
    VdwState& V = c->vdw;
    const bool do_e = vers & APX_ENERGY, do_g = vers & APX_GRAD, do_v = (vers & APX_VIRIAL) && do_g, do_a = vers & APX_ANALYZ;
-   const fixed_t* hb = V.h_vbuf;
-   const int* hc = V.h_vcnt;
+   const fixed_t* hb = reinterpret_cast<const fixed_t*>(c->red_h + 2048);
+   const int* hc = reinterpret_cast<const int*>(c->red_h + 2048 + 64);
    cudaEventElapsedTime(&c->stats.ms_ehal, V.t0, V.t1);
    auto fx = [](fixed_t v) { return (double)(long long)v / APX_FIXED_SCALE; };
    const double vol = fabs((double)c->box.volume);

@@ -455,7 +455,12 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       c->thlval, c->opt.njpolar, U, F, c->skip)
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
-   if (!c->capturing && c->uf_used + 2 <= (int)c->uf_ev.size()) {
+   const bool ext = c->capturing && c->graph_key_open >= 0 && (c->graph_key_open & 0x2000) && c->uf_ev.size() >= 2;
+   if (ext) {
+      // inside the captured prologue of induce(): external event nodes, so every replay times this launch (slots 0,1)
+      slot = 0;
+      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[0], st, cudaEventRecordExternal));
+   } else if (!c->capturing && c->uf_used + 2 <= (int)c->uf_ev.size()) {
       slot = c->uf_used;
       c->uf_used += 2;
       cudaEventRecord(c->uf_ev[slot], st);
@@ -473,7 +478,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    else if (ew) LAUNCH_UF(true, false);
    else if (tb) LAUNCH_UF(false, true);
    else LAUNCH_UF(false, false);
-   if (slot >= 0)
+   if (slot >= 0 && ext)
+      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[1], st, cudaEventRecordExternal));
+   else if (slot >= 0)
       cudaEventRecord(c->uf_ev[slot + 1], st);
    APX_COUNT_LAUNCH(c);
 #undef LAUNCH_UF

@@ -695,10 +695,15 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    const bool ewald = c->opt.use_ewald != 0;
    const bool pair_ep = do_e && do_a;          // ANALYZE: pairwise polarization energy; otherwise dot product
    cudaEventRecord(c->ev2, st);
-   apx_rotpole(c);      // mpoleInit(vers) runs on every energy() call in the reference (src/amoeba/emplar.cpp:12)
-   // ---- zero accumulators
-   // gx gy gz trqf ebuf dbuf cnt are contiguous (arena_e, apx_api.cu): one memset
-   CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, st));
+   if (apx_graph_begin(c, 0x1000)) {
+      apx_rotpole(c);      // mpoleInit(vers) runs on every energy() call in the reference (src/amoeba/emplar.cpp:12)
+      // ---- zero accumulators
+      // gx gy gz trqf ebuf dbuf cnt are contiguous (arena_e, apx_api.cu): one memset
+      CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, st));
+      apx_graph_end(c, 0x1000);
+   }
+   c->mpole_inited = 1;
+   c->mpole_pme_valid = 0;
    // ---- vdW term on its own stream, beside everything below (joins before the reductions)
    do_vdw = do_vdw && c->vdw.on;
    if (do_vdw)
@@ -717,7 +722,10 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       apx_dist_halo(c, c->pk_p, st);
       apx_unpack_dp_all(c, c->pk_p, c->uind, c->uinp);
    }
-   // ---- real space
+   // ---- real space, reciprocal space, torques: one fixed launch sequence per (vers, terms) -> one CUDA graph
+   const int ekey = 0x4000 | (vers & 0xff) | (do_m ? 0x100 : 0) | (do_p ? 0x200 : 0);
+   const bool eager = apx_graph_begin(c, ekey);
+   if (eager) {
    MplarArgs A;
    A.a0 = c->a0;
    A.a1 = c->a1;
@@ -812,6 +820,8 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       APX_COUNT_LAUNCH(c);
       apx_torque(c, do_v);
    }
+   apx_graph_end(c, ekey);
+   }
    if (do_vdw)
       apx_vdw_join(c);
    if (dist) {
@@ -824,14 +834,14 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
          apx_dist_allreduce_i32(c, c->cnt.p, 4);
    }
    // ---- reductions to the host (energy.cpp:334-384)
-   fixed_t eb[8];
-   double db[D_TOTAL];
-   int cn[4];
-   CUDA_CHECK(cudaMemcpyAsync(eb, c->ebuf.p, sizeof(eb), cudaMemcpyDeviceToHost, st));
-   CUDA_CHECK(cudaMemcpyAsync(db, c->dbuf.p, sizeof(db), cudaMemcpyDeviceToHost, st));
-   CUDA_CHECK(cudaMemcpyAsync(cn, c->cnt.p, sizeof(cn), cudaMemcpyDeviceToHost, st));
+   // ebuf, dbuf and cnt sit back to back at the end of the accumulator arena: ONE copy into pinned memory
+   const size_t tail = (size_t)((char*)(c->cnt.p + 4) - (char*)c->ebuf.p);
+   CUDA_CHECK(cudaMemcpyAsync(c->red_h, c->ebuf.p, tail, cudaMemcpyDeviceToHost, st));
    cudaEventRecord(c->ev3, st);
    CUDA_CHECK(cudaStreamSynchronize(st));
+   const fixed_t* eb = reinterpret_cast<const fixed_t*>(c->red_h);
+   const double* db = reinterpret_cast<const double*>(c->red_h + ((char*)c->dbuf.p - (char*)c->ebuf.p));
+   const int* cn = reinterpret_cast<const int*>(c->red_h + ((char*)c->cnt.p - (char*)c->ebuf.p));
    cudaEventElapsedTime(&c->stats.ms_energy, c->ev2, c->ev3);
    auto fx = [](fixed_t v) { return (double)(long long)v / APX_FIXED_SCALE; };
    apx_energy_result r;

@@ -355,6 +355,49 @@ void apx_pcg_graphs_invalidate(apx_ctx* c)
    for (auto& g : c->graphs)
       cudaGraphExecDestroy(g.exec);
    c->graphs.clear();
+   for (auto& kv : c->step_graphs)
+      if (kv.second.exec)
+         cudaGraphExecDestroy(kv.second.exec);
+   c->step_graphs.clear();
+}
+
+bool apx_graph_begin(apx_ctx* c, int key)
+{
+   c->graph_key_open = -1;
+   if (!c->use_graph || c->dist.on || c->capturing)
+      return true;
+   apx_ctx::StepGraph& G = c->step_graphs[key];
+   if (G.exec) {
+      CUDA_CHECK(cudaGraphLaunch(G.exec, c->stream));
+      c->stats.kernel_launches += G.launches;
+      return false;
+   }
+   if (!G.warm) {
+      G.warm = 1;      // eager once: plans, workspaces and scratch buffers get allocated outside any capture
+      return true;
+   }
+   c->graph_key_open = key;
+   c->graph_launches_before = c->stats.kernel_launches;
+   c->capturing = 1;
+   CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+   return true;
+}
+
+void apx_graph_end(apx_ctx* c, int key)
+{
+   if (c->graph_key_open != key)
+      return;
+   c->graph_key_open = -1;
+   cudaGraph_t graph = nullptr;
+   cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+   c->capturing = 0;
+   if (e != cudaSuccess)
+      APX_THROW(std::string("step graph capture failed: ") + cudaGetErrorString(e));
+   apx_ctx::StepGraph& G = c->step_graphs[key];
+   G.launches = c->stats.kernel_launches - c->graph_launches_before;
+   CUDA_CHECK(cudaGraphInstantiate(&G.exec, graph, 0));
+   cudaGraphDestroy(graph);
+   CUDA_CHECK(cudaGraphLaunch(G.exec, c->stream));      // the captured work has not run yet
 }
 
 void apx_induce_impl(apx_ctx* c)
@@ -374,12 +417,13 @@ void apx_induce_impl(apx_ctx* c)
    }
    c->uf_used = 0;
    cudaEventRecord(c->ev0, st);
-   apx_dfield_full(c, true);
+   const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;   // the predictor replaces the direct guess once its ring is full
    c->stats.pcg_iterations = 0;
    c->induced_valid = 1;
    if (!c->opt.poltyp_mutual) {
       // DIRECT polarization: u = alpha E
       (void)n3;
+      apx_dfield_full(c, true);
       CUDA_CHECK(cudaMemcpyAsync(c->uind.p + 3 * a0, c->udir.p + 3 * a0, sizeof(real) * 3 * no, cudaMemcpyDeviceToDevice, st));
       CUDA_CHECK(cudaMemcpyAsync(c->uinp.p + 3 * a0, c->udirp.p + 3 * a0, sizeof(real) * 3 * no, cudaMemcpyDeviceToDevice, st));
       cudaEventRecord(c->ev1, st);
@@ -390,55 +434,65 @@ void apx_induce_impl(apx_ctx* c)
    const int politer = c->opt.politer;
    const int miniter = std::min(3, n);
    static_assert(PCG_SLOT == 96, "arena_p in apx_api.cu is sized for 96 doubles per iteration");
-   CUDA_CHECK(cudaMemsetAsync(c->arena_p.p, 0, c->arena_p_bytes, st));      // scal + flags
    double* result = c->scal.p + (size_t)PCG_SLOT * (politer + 3);
    const size_t ngrid4 = ewald ? (size_t)c->nfft1 * c->nfft2 * c->nzl * sizeof(cplx) / sizeof(real4) : 0;
-
-   // the predictor replaces the direct guess once its ring is full (pcg.cu:26-31)
-   const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;
-   if (predict) {
-      static const double aspc[16] = {62. / 17., -310. / 51., 2170. / 323., -2329. / 400., 1701. / 409., -806. / 323., 1024. / 809.,
-         -479. / 883., 257. / 1316., -434. / 7429., 191. / 13375., -62. / 22287., 3. / 7217., -3. / 67015., 2. / 646323.,
-         -1. / 9694845.};
-      static const double gear[6] = {6., -15., 20., -15., 6., -1.};
-      UpredCoef K;
-      K.m = c->maxualt;
-      for (int k = 0; k < K.m; ++k) {
-         int age = ((c->nualt - 1 - k) % K.m + K.m) % K.m;      // ring slot k holds the solution of this age
-         K.c[k] = (real)(c->opt.polpred == 1 ? aspc[age] : gear[age]);
+   // graph region: permanent field, direct dipoles, first residual, first preconditioner application -- a fixed launch
+   // sequence unless the predictor supplies this step's coefficients by value
+   const bool graphable = !predict;
+   const int gkey = 0x2000 | (c->opt.pcgguess ? 1 : 0);
+   if (!graphable || apx_graph_begin(c, gkey)) {
+      apx_dfield_full(c, true);
+      CUDA_CHECK(cudaMemsetAsync(c->arena_p.p, 0, c->arena_p_bytes, st));      // scal + flags
+      // the predictor replaces the direct guess once its ring is full (pcg.cu:26-31)
+      if (predict) {
+         static const double aspc[16] = {62. / 17., -310. / 51., 2170. / 323., -2329. / 400., 1701. / 409., -806. / 323., 1024. / 809.,
+            -479. / 883., 257. / 1316., -434. / 7429., 191. / 13375., -62. / 22287., 3. / 7217., -3. / 67015., 2. / 646323.,
+            -1. / 9694845.};
+         static const double gear[6] = {6., -15., 20., -15., 6., -1.};
+         UpredCoef K;
+         K.m = c->maxualt;
+         for (int k = 0; k < K.m; ++k) {
+            int age = ((c->nualt - 1 - k) % K.m + K.m) % K.m;      // ring slot k holds the solution of this age
+            K.c[k] = (real)(c->opt.polpred == 1 ? aspc[age] : gear[age]);
+         }
+         k_upred_sum<<<g1, 256, 0, st>>>(no, n, c->perm + a0, c->upred_hist, K, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0);
+         APX_COUNT_LAUNCH(c);
       }
-      k_upred_sum<<<g1, 256, 0, st>>>(no, n, c->perm + a0, c->upred_hist, K, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0);
-      APX_COUNT_LAUNCH(c);
-   }
-   // r0 = -T u0  (pcgguess; k_udir left u0 packed in pk_p) or E (no guess; k_udir left E packed in pk_p)
-   if (c->opt.pcgguess || predict) {
+      // r0 = -T u0  (pcgguess; k_udir left u0 packed in pk_p) or E (no guess; k_udir left E packed in pk_p)
+      if (c->opt.pcgguess || predict) {
+         if (ewald)
+            apx_pme_zero_grid(c);
+         field_of_dp(c, c->pk_p, true);
+         if (ewald)
+            apx_pme_gather_dp(c, 1, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_r, nullptr);
+         else {
+            CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_f.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
+            k_mask_dp<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->pk_r + 2 * a0);
+            APX_COUNT_LAUNCH(c);
+         }
+         if (predict) {
+            k_rsd0_pred<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->udir + 3 * a0, c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0,
+               c->pk_r + 2 * a0);
+            APX_COUNT_LAUNCH(c);
+         }
+      } else {
+         CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_p.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
+      }
+      // z0 = M r0, r0.z0 -> slot of iteration 1 (whose K1 sets p = z0)
+      if (dist)
+         apx_dist_halo(c, c->pk_r, st);
+      apx_precond_dp(c, c->pk_r, c->pk_z, c->scal.p);
+      if (dist)
+         apx_dist_allreduce_f64(c, c->scal.p, 2 * PCG_NSUB);
       if (ewald)
          apx_pme_zero_grid(c);
-      field_of_dp(c, c->pk_p, true);
-      if (ewald)
-         apx_pme_gather_dp(c, 1, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_r, nullptr);
-      else {
-         CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_f.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
-         k_mask_dp<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->pk_r + 2 * a0);
-         APX_COUNT_LAUNCH(c);
-      }
-      if (predict) {
-         k_rsd0_pred<<<g1, 256, 0, st>>>(no, c->tpj + a0, c->udir + 3 * a0, c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0,
-            c->pk_r + 2 * a0);
-         APX_COUNT_LAUNCH(c);
-      }
-   } else {
-      CUDA_CHECK(cudaMemcpyAsync(c->pk_r.p + 2 * a0, c->pk_p.p + 2 * a0, sizeof(real4) * 2 * no, cudaMemcpyDeviceToDevice, st));
+      if (graphable)
+         apx_graph_end(c, gkey);
    }
-   // z0 = M r0, r0.z0 -> slot of iteration 1 (whose K1 sets p = z0)
-   if (dist)
-      apx_dist_halo(c, c->pk_r, st);
-   apx_precond_dp(c, c->pk_r, c->pk_z, c->scal.p);
-   if (dist)
-      apx_dist_allreduce_f64(c, c->scal.p, 2 * PCG_NSUB);
    if (ewald)
-      apx_pme_zero_grid(c);
-
+      c->mpole_pme_valid = 1;
+   if (graphable && c->use_graph && !dist && (c->opt.pcgguess) && c->uf_used == 0)
+      c->uf_used = 2;      // the r0 operator launch inside the graph was timed through external event nodes
    int iter = 0;
    bool done = false;
    c->skip = c->flags.p;
