@@ -268,7 +268,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = a.stats()["kernel_launches"]
-    clocks = sampler.stop() if rank == 0 else None
     ms_step = float(np.mean(ms_steps))
 
     # ---- e2e leg: host positions in, gradient out, every step
@@ -286,6 +285,7 @@ def run_ours(args, rank, world, local_rank):
         e1.synchronize()
         ms_e2e.append(e0.elapsed_time(e1))
     barrier()
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (resident + e2e)
     ms_e2e_step = float(np.mean(ms_e2e))
     rebuilds = a.stats()["list_rebuilds"]
 
@@ -335,12 +335,15 @@ def run_ours(args, rank, world, local_rank):
                     "list_rebuilds": rebuilds},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_ufield_rows (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
+            "roofline": {"kernel": "k_ufield_rows_rec (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
                          "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                          "traffic": traffic[0] if traffic else None,
                          "traffic_source": ("profiles/" + traffic[1] + " (ncu --set full, cold-cache replay)") if traffic else None,
                          "algorithmic_bytes": uf_bytes, "peak_source": peak_src, "ms_per_launch": uf_ms,
-                         "note": "latency/FP32-pipe bound at this size: see roofline_fp32"},
+                         "note": ("not an HBM-bound kernel: ncu shows it bound by L1 sector traffic of the neighbour gathers and instruction "
+                                  "issue (l1tex 74 %, issue 53 %, profiles/r01j_water1m_ncu_full_summary.txt); see roofline_fp32. "
+                                  "The streaming kernels of the path (k_conv, k_pcg_update, k_pcg_dir) run at 78-90 % of this peak "
+                                  "on the 1M-atom box (DESIGN.md section 5)")},
             "roofline_fp32": {"achieved": uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0, "peak": fp32_peak,
                               "unit": "TFLOP/s", "frac": (uf_flops / (uf_ms * 1e-3) / 1e12 / fp32_peak) if uf_ms > 0 else 0.0,
                               "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs)},

@@ -153,7 +153,91 @@ __global__ void k_flag_set(volatile unsigned* flag, unsigned value)
    *flag = value;
 }
 
+// ---- one kernel per direction for ALL peers of an exchange (APX_DIST_P2P=2)
+// k_xfer moves a table of messages with the SMs: a CTA first waits (thread 0 spins) until the flag of its message's
+// peer has reached `want`, copies its share of the message with 16-byte loads/stores -- to the peer's window over
+// NVLink when pushing, out of the local window when pulling -- and the last CTA of every peer raises that peer's flag
+// (ready flag in the receiver's memory after a push, acknowledge flag in the sender's memory after a pull).
+#define XFER_MAX_MSG 40
+struct XferMsg {
+   const char* src;
+   char* dst;
+   size_t bytes;
+   int peer;            // index into the per-peer tables
+   int cta0, nctas;     // CTAs [cta0, cta0 + nctas) move this message
+};
+struct XferTable {
+   XferMsg m[XFER_MAX_MSG];
+   int nmsg;
+   const volatile unsigned* wait_flag[16];    // per peer: spin until >= wait_val (nullptr: no wait)
+   unsigned wait_val[16];
+   volatile unsigned* set_flag[16];           // per peer: written by the last CTA serving that peer
+   unsigned set_val;
+   int peer_ctas[16];                         // CTAs serving each peer
+   unsigned* counters;                        // [16] arrival counters, self-resetting
+};
+__global__ void __launch_bounds__(256) k_xfer(const __grid_constant__ XferTable T)
+{
+   __shared__ int s_msg;
+   if (threadIdx.x == 0) {
+      int k = 0;
+      while (k < T.nmsg - 1 && (int)blockIdx.x >= T.m[k].cta0 + T.m[k].nctas)
+         ++k;
+      s_msg = k;
+      const int p = T.m[k].peer;
+      if (T.wait_flag[p]) {
+         while ((int)(*T.wait_flag[p] - T.wait_val[p]) < 0)
+            __nanosleep(100);
+         __threadfence_system();
+      }
+   }
+   __syncthreads();
+   const XferMsg M = T.m[s_msg];
+   const int part = (int)blockIdx.x - M.cta0;
+   // 16-byte lanes when both ends allow it (windows are 256-byte aligned; user arrays of 3-float atoms may not be),
+   // 4-byte words otherwise; loads bypass L1 (the window was written by another GPU while this kernel was waiting)
+   const bool a16 = (((size_t)M.src | (size_t)M.dst) & 15) == 0;
+   const bool a4 = (((size_t)M.src | (size_t)M.dst | M.bytes) & 3) == 0;
+   if (a16) {
+      const size_t n16 = M.bytes / 16;
+      const size_t per = (n16 + M.nctas - 1) / M.nctas;
+      const size_t b0 = per * part, b1 = b0 + per < n16 ? b0 + per : n16;
+      const uint4* s = reinterpret_cast<const uint4*>(M.src);
+      uint4* d = reinterpret_cast<uint4*>(M.dst);
+      for (size_t q = b0 + threadIdx.x; q < b1; q += blockDim.x)
+         d[q] = __ldcg(s + q);
+      if (part == M.nctas - 1)
+         for (size_t q = n16 * 16 + threadIdx.x; q < M.bytes; q += blockDim.x)
+            M.dst[q] = __ldcg(M.src + q);
+   } else if (a4) {
+      const size_t n4 = M.bytes / 4;
+      const size_t per = (n4 + M.nctas - 1) / M.nctas;
+      const size_t b0 = per * part, b1 = b0 + per < n4 ? b0 + per : n4;
+      const unsigned* s = reinterpret_cast<const unsigned*>(M.src);
+      unsigned* d = reinterpret_cast<unsigned*>(M.dst);
+      for (size_t q = b0 + threadIdx.x; q < b1; q += blockDim.x)
+         d[q] = __ldcg(s + q);
+   } else {
+      const size_t per = (M.bytes + M.nctas - 1) / M.nctas;
+      const size_t b0 = per * part, b1 = b0 + per < M.bytes ? b0 + per : M.bytes;
+      for (size_t q = b0 + threadIdx.x; q < b1; q += blockDim.x)
+         M.dst[q] = __ldcg(M.src + q);
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      const int p = M.peer;
+      const unsigned old = atomicInc(&T.counters[p], (unsigned)T.peer_ctas[p] - 1);
+      if (old == (unsigned)T.peer_ctas[p] - 1) {
+         __threadfence_system();
+         *T.set_flag[p] = T.set_val;
+      }
+   }
+}
+
 struct P2pComm : NcclComm {
+   int fused = 0;                           // 1: k_xfer push/pull kernels instead of copy-engine copies + flag kernels
+   unsigned* counters = nullptr;            // [32] device arrival counters (push: 0..15, pull: 16..31)
    size_t window = 0;                       // bytes one sender may put into one slot
    char* win = nullptr;                     // my receive windows: [sender][slot][window]
    unsigned* flg = nullptr;                 // my flags: ready[sender][slot], then ack[receiver][slot]
@@ -175,6 +259,8 @@ struct P2pComm : NcclComm {
       CUDA_CHECK(cudaMalloc(&win, (size_t)world * 2 * window));
       CUDA_CHECK(cudaMalloc(&flg, sizeof(unsigned) * 4 * world));
       CUDA_CHECK(cudaMemset(flg, 0, sizeof(unsigned) * 4 * world));
+      CUDA_CHECK(cudaMalloc(&counters, sizeof(unsigned) * 32));
+      CUDA_CHECK(cudaMemset(counters, 0, sizeof(unsigned) * 32));
       Handles mine;
       CUDA_CHECK(cudaIpcGetMemHandle(&mine.w, win));
       CUDA_CHECK(cudaIpcGetMemHandle(&mine.f, flg));
@@ -223,6 +309,7 @@ struct P2pComm : NcclComm {
       }
       cudaFree(win);
       cudaFree(flg);
+      cudaFree(counters);
    }
    void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) override
    {
@@ -245,6 +332,10 @@ struct P2pComm : NcclComm {
             nr.push_back(o);
       ++seq;
       const int slot = (int)(seq & 1u);
+      if (fused && sends.size() <= XFER_MAX_MSG && recvs.size() <= XFER_MAX_MSG) {
+         exchange_fused(sends, recvs, tot_s, tot_r, ns, nr, slot, st);
+         return;
+      }
       // 1. my data into the peers' windows
       for (int p = 0; p < world; ++p) {
          if (p == rank || tot_s[p] == 0 || tot_s[p] > window)
@@ -282,6 +373,80 @@ struct P2pComm : NcclComm {
       }
    }
    unsigned last_used[16][2] = {};
+
+   static int ctas_for(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>(24, bytes / (128 * 1024))); }
+
+   void exchange_fused(const std::vector<Op>& sends, const std::vector<Op>& recvs, const std::vector<size_t>& tot_s,
+      const std::vector<size_t>& tot_r, const std::vector<Op>& ns, const std::vector<Op>& nr, int slot, cudaStream_t st)
+   {
+      // push: everything I send, all peers in one kernel
+      XferTable P;
+      memset(&P, 0, sizeof(P));
+      int grid = 0;
+      std::vector<size_t> off(world, 0);
+      for (const Op& o : sends) {
+         const int p = o.peer;
+         if (p == rank || tot_s[p] > window)
+            continue;
+         XferMsg& M = P.m[P.nmsg++];
+         M.src = static_cast<const char*>(o.ptr);
+         M.dst = slot_of(peer_win[p], rank, slot) + off[p];
+         M.bytes = o.bytes;
+         M.peer = p;
+         M.cta0 = grid;
+         M.nctas = ctas_for(o.bytes);
+         grid += M.nctas;
+         P.peer_ctas[p] += M.nctas;
+         off[p] += al(o.bytes);
+      }
+      if (P.nmsg) {
+         for (int p = 0; p < world; ++p) {
+            if (!P.peer_ctas[p])
+               continue;
+            P.wait_flag[p] = ack_of(flg, p, slot);      // the peer emptied this slot (my write two exchanges ago)
+            P.wait_val[p] = last_used[p][slot];
+            P.set_flag[p] = ready_of(peer_flg[p], rank, slot);
+            last_used[p][slot] = seq;
+         }
+         P.set_val = seq;
+         P.counters = counters;
+         k_xfer<<<grid, 256, 0, st>>>(P);
+      }
+      if (!ns.empty() || !nr.empty())
+         NcclComm::exchange(ns, nr, st);
+      // pull: everything I receive, out of my windows
+      XferTable Q;
+      memset(&Q, 0, sizeof(Q));
+      grid = 0;
+      std::fill(off.begin(), off.end(), 0);
+      for (const Op& o : recvs) {
+         const int p = o.peer;
+         if (p == rank || tot_r[p] > window)
+            continue;
+         XferMsg& M = Q.m[Q.nmsg++];
+         M.src = slot_of(win, p, slot) + off[p];
+         M.dst = static_cast<char*>(o.ptr);
+         M.bytes = o.bytes;
+         M.peer = p;
+         M.cta0 = grid;
+         M.nctas = ctas_for(o.bytes);
+         grid += M.nctas;
+         Q.peer_ctas[p] += M.nctas;
+         off[p] += al(o.bytes);
+      }
+      if (Q.nmsg) {
+         for (int p = 0; p < world; ++p) {
+            if (!Q.peer_ctas[p])
+               continue;
+            Q.wait_flag[p] = ready_of(flg, p, slot);
+            Q.wait_val[p] = seq;
+            Q.set_flag[p] = ack_of(peer_flg[p], rank, slot);
+         }
+         Q.set_val = seq;
+         Q.counters = counters + 16;
+         k_xfer<<<grid, 256, 0, st>>>(Q);
+      }
+   }
 };
 
 // ---- in-process transport: `world` ranks = host threads of one process on one device
@@ -774,6 +939,7 @@ ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* un
    memcpy(&id, unique_id, sizeof(id));
    NCCL_CHECK(api, api->CommInitRank(&cm->comm, world, id, rank));
    if (p2p && world <= 16) {
+      cm->fused = p2p >= 2 ? 1 : 0;
       size_t mb = 64;
       if (const char* e = getenv("APX_DIST_WINDOW_MB"))
          mb = (size_t)std::max(1, atoi(e));

@@ -129,16 +129,6 @@ __device__ __forceinline__ void add_fixed(fixed_t* g, int s, double v)
    atomicAdd(&g[s], (fixed_t)(long long)(v * APX_FIXED_SCALE));
 }
 
-// Force on the atom at the tip of unit axis `a` (length la) produced by the torque components
-// about the two directions perpendicular to it inside the (a,b) plane and out of it.
-__device__ __forceinline__ v3 tip_force_plane(v3 a, v3 b, double la, double dphi_b, double dphi_n, v3 nrm_ab, v3 nrm_aw)
-{
-   // nrm_ab = unit(b x a) ; nrm_aw = unit(w x a) ; used by Z-Only / Z-then-X / Bisector
-   double c = dot(a, b);
-   double s = sqrt(1.0 - c * c);
-   return (dphi_b / (la * s)) * nrm_ab + (dphi_n / la) * nrm_aw;
-}
-
 template <bool DO_V>
 __global__ void k_torque(int a0, int n, const double* __restrict__ xyz, const int* __restrict__ perm, const int* __restrict__ inv,
    const int* __restrict__ zaxis, const real* __restrict__ trq, fixed_t* __restrict__ gx, fixed_t* __restrict__ gy,
