@@ -139,7 +139,7 @@ struct NcclComm : ApxComm {
 // on the flag with a one-thread kernel, moves the data from the window to its destination and
 // acknowledges, so that the window can be reused two exchanges later (two slots per sender).
 // Everything is stream ordered; the host never blocks.  Small all-reduces stay on NCCL, which also
-// carries the IPC handles at start-up.  APX_DIST_P2P=0/1 forces NCCL send/recv / the windows (default: windows at 2 GPUs).
+// carries the IPC handles at start-up.  APX_DIST_P2P=0 forces NCCL send/recv, 1 these copy-engine windows, 2 the fused kernels below.
 __global__ void k_flag_wait(const volatile unsigned* flag, unsigned want)
 {
    // sequence numbers only grow; unsigned difference handles wrap-around
@@ -204,11 +204,17 @@ __global__ void __launch_bounds__(256) k_xfer(const __grid_constant__ XferTable 
       const size_t b0 = per * part, b1 = b0 + per < n16 ? b0 + per : n16;
       const uint4* s = reinterpret_cast<const uint4*>(M.src);
       uint4* d = reinterpret_cast<uint4*>(M.dst);
-      for (size_t q = b0 + threadIdx.x; q < b1; q += blockDim.x)
+      size_t q = b0 + threadIdx.x;
+      for (; q + 3 * blockDim.x < b1; q += 4 * blockDim.x) {      // four independent 16-byte transfers in flight per thread
+         const uint4 v0 = __ldcg(s + q), v1 = __ldcg(s + q + blockDim.x), v2 = __ldcg(s + q + 2 * blockDim.x),
+                     v3 = __ldcg(s + q + 3 * blockDim.x);
+         d[q] = v0, d[q + blockDim.x] = v1, d[q + 2 * blockDim.x] = v2, d[q + 3 * blockDim.x] = v3;
+      }
+      for (; q < b1; q += blockDim.x)
          d[q] = __ldcg(s + q);
       if (part == M.nctas - 1)
-         for (size_t q = n16 * 16 + threadIdx.x; q < M.bytes; q += blockDim.x)
-            M.dst[q] = __ldcg(M.src + q);
+         for (size_t r = n16 * 16 + threadIdx.x; r < M.bytes; r += blockDim.x)
+            M.dst[r] = __ldcg(M.src + r);
    } else if (a4) {
       const size_t n4 = M.bytes / 4;
       const size_t per = (n4 + M.nctas - 1) / M.nctas;
@@ -374,7 +380,8 @@ struct P2pComm : NcclComm {
    }
    unsigned last_used[16][2] = {};
 
-   static int ctas_for(size_t bytes) { return (int)std::max<size_t>(1, std::min<size_t>(24, bytes / (128 * 1024))); }
+   int xfer_cap = 128;
+   int ctas_for(size_t bytes) const { return (int)std::max<size_t>(1, std::min<size_t>((size_t)xfer_cap, bytes / (64 * 1024))); }
 
    void exchange_fused(const std::vector<Op>& sends, const std::vector<Op>& recvs, const std::vector<size_t>& tot_s,
       const std::vector<size_t>& tot_r, const std::vector<Op>& ns, const std::vector<Op>& nr, int slot, cudaStream_t st)
@@ -925,10 +932,10 @@ const char* apx_dist_error() { return g_dist_err.c_str(); }
 ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id)
 {
    NcclApi* api = nccl_api(lib);
-   // measured on the 1 M-atom box (profiles/r01p..., r01s...): 2 GPUs 21.5 ms (peer windows) vs 22.3 (NCCL); 4 GPUs 15.3 vs
-   // 13.0 -- the per-peer copies of one exchange are issued on ONE stream and serialise, where NCCL's grouped send/recv
-   // runs all peers at once.  Until the copies become one push kernel for all peers, the windows are the default at 2 GPUs.
-   int p2p = world == 2 ? 1 : 0;
+   // measured on the 1 M-atom box (profiles/r01p..., r01s..., r01v..x): 2 GPUs 22.3 ms over NCCL, 21.5 with copy-engine
+   // windows (mode 1), 21.3 with the fused push/pull kernels (mode 2); 4 GPUs 13.0 (NCCL), 15.3 (mode 1: the per-peer copies
+   // of one exchange serialise on one stream), 13.0 (mode 2).  Default: mode 2 at 2 GPUs, NCCL beyond (8 GPUs not yet run).
+   int p2p = world == 2 ? 2 : 0;
    if (const char* e = getenv("APX_DIST_P2P"))
       p2p = atoi(e);
    P2pComm* cm = new P2pComm();
@@ -940,6 +947,8 @@ ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* un
    NCCL_CHECK(api, api->CommInitRank(&cm->comm, world, id, rank));
    if (p2p && world <= 16) {
       cm->fused = p2p >= 2 ? 1 : 0;
+      if (const char* e = getenv("APX_DIST_XFER_CTAS"))
+         cm->xfer_cap = std::max(1, std::min(1024, atoi(e)));
       size_t mb = 64;
       if (const char* e = getenv("APX_DIST_WINDOW_MB"))
          mb = (size_t)std::max(1, atoi(e));
