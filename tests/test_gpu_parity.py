@@ -234,3 +234,35 @@ def test_pme_convolution_native_fft():
 def test_no_cpu_fallback_message():
     from tinker_gpu_b200 import amoeba
     assert os.path.isfile(amoeba.library_path("mixed")), "libapx.so must be built in-tree"
+
+
+def test_step_graphs_survive_rebuilds():
+    """The whole-step CUDA graphs are kept across list rebuilds (buffers did not move) and dropped when they must be:
+    a context that has replayed its graphs through drifting positions, a rebuild and a box-filling translation gives
+    the same energies and forces as a fresh context at each of those positions."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    s = tg.load_system(os.path.join(GOLDEN, "water30.npz"))
+    x0 = np.array(s.xyz)
+    rng = np.random.default_rng(9)
+    # a rigid drift of 0.14 A per frame (physics unchanged, rebuild once the shift passes buffer/2 = 1 A) plus thermal-size
+    # noise; uncorrelated drifts would stretch the bonds and amplify float round-off beyond any useful tolerance
+    drift = np.array([0.11, 0.07, 0.05])
+    frames = [x0 + drift * j + rng.normal(scale=0.004, size=x0.shape) for j in range(12)] + [x0 + np.array([3.1, -2.2, 7.7])]
+    a = _amoeba(s, "mixed")
+    got = []
+    for x in frames:
+        a.set_positions(x)
+        got.append(a.energy(calc.v4))
+    nreb = a.stats()["list_rebuilds"]
+    a.close()
+    assert nreb >= 2                                  # the drift passes 1 A at frame 8, then the translation
+    for j in (0, 5, 11, 12):
+        b = _amoeba(s, "mixed")
+        b.set_positions(frames[j])
+        ref = b.energy(calc.v4)
+        b.close()
+        # the two contexts sorted their atoms at different frames: float sums in another order
+        assert abs(got[j]["esum"] - ref["esum"]) < 5e-7 * abs(ref["esum"]), j
+        assert _rms(got[j]["grad"] - ref["grad"]) < 3e-5, j
+        assert got[j]["pcg_iterations"] == ref["pcg_iterations"]
