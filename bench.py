@@ -365,7 +365,9 @@ def run_ours(args, rank, world, local_rank):
         if not args.no_cpu and args.workload == "dhfr2":
             ms_cpu, ms_cpu_ind, desc = cpu_oracle_sample(system)
             line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc,
-                                    "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind}
+                                    "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
+                                    "note": "vectorised-numpy port on one core, about two orders of magnitude slower than the reference's "
+                                            "compiled host build would be (it cannot be linked here: no Fortran compiler); reported, not a target"}
         print(json.dumps(line))
     a.close()
     if dist is not None:

@@ -136,3 +136,18 @@ def test_replica_aggregation_world2_gloo(tmp_path):
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
     assert float(line[1]) == 15.0
     assert abs(float(line[2]) - 2 * 2.0e-6 * 86400e3 / 15.0) < 1e-12
+
+
+def test_bench_workloads_build():
+    """bench.py --workload: the synthetic boxes of BASELINE.md section 4 come out with the stated sizes and grids, and the
+    slab decomposition's divisibility rule holds for the GPU counts the 1 M-atom box is meant for."""
+    import bench
+    w = bench.make_system("water96k")
+    assert w.n == 96624 and w.nfft == (108, 108, 144) and w.poleps == 1e-8
+    assert w.vdw is not None and w.vdw.ired.max() < w.n
+    m = bench.make_system("water1m")
+    assert m.n == 1030656 and m.nfft == (288, 288, 216)
+    for g in (2, 4, 8):
+        assert m.nfft[1] % g == 0 and m.nfft[2] % g == 0
+    d = bench.make_system("dhfr424k")
+    assert d.n == 424044 and d.nfft == (240, 240, 150)
