@@ -81,6 +81,7 @@ class System:
     names: list | None = None
     bonds: list | None = None
     title: str = ""
+    mass: np.ndarray | None = None     # (n,) atomic masses (atomid::mass), used by the ANALYZE moments
     vdw: object | None = None          # vdwparams.VdwTerm: buffered 14-7 term, optional
 
     @property
@@ -621,7 +622,8 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         usolve_cutoff=usolve_applied, list_buffer=lbuffer,
         poleps=kfloat("POLAR-EPS", 1.0e-6), politer=int(kfloat("POLAR-ITER", 100)),
         poltyp=poltyp, polpred=polpred, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
-        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, vdw=vdw, **lists)
+        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, vdw=vdw,
+        mass=np.array([ff.atom_mass.get(int(t), 0.0) for t in types]), **lists)
 
 
 def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep_bonds: bool = True) -> System:
@@ -676,7 +678,7 @@ def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep
         pcgprec=sys.pcgprec, pcgguess=sys.pcgguess, pcgpeek=sys.pcgpeek, poltyp=sys.poltyp,
         polpred=sys.polpred, electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
         names=(sys.names * m) if sys.names is not None else None, bonds=bonds,
-        title=f"{sys.title} x{nx}x{ny}x{nz}", vdw=_replicate_vdw(sys, m))
+        title=f"{sys.title} x{nx}x{ny}x{nz}", vdw=_replicate_vdw(sys, m), mass=tile(sys.mass) if sys.mass is not None else None)
 
 
 def _replicate_vdw(sys, m):
@@ -691,7 +693,7 @@ def _replicate_vdw(sys, m):
 # ----------------------------------------------------------------------------
 _ARRAY_FIELDS = ("xyz", "lvec", "recip", "pole", "zaxis", "polarity", "thole", "pdamp", "jpolar", "thlval",
                  "mexclude", "mexclude_scale", "dpexclude", "dpexclude_scale", "uexclude", "uexclude_scale",
-                 "mdpuexclude", "mdpuexclude_scale", "types")
+                 "mdpuexclude", "mdpuexclude_scale", "types", "mass")
 _SCALAR_FIELDS = ("n", "use_ewald", "use_mpole", "use_polar", "aewald", "bsorder", "ewald_cutoff", "usolve_cutoff",
                   "list_buffer", "poleps", "politer", "uaccel", "pcgprec", "pcgguess", "pcgpeek", "poltyp", "electric",
                   "dielec", "title")
@@ -719,6 +721,7 @@ def load_system(path: str) -> System:
         kw["polpred"] = str(z["_polpred"])
     kw["nfft"] = tuple(int(v) for v in z["_nfft"])
     kw.setdefault("types", None)
+    kw.setdefault("mass", None)
     from .vdwparams import vdw_from_npz
     kw["vdw"] = vdw_from_npz(z)
     return System(**kw)
