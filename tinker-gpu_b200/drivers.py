@@ -188,7 +188,7 @@ def main(argv=None):
     ap.add_argument("xyz")
     ap.add_argument("-k", "--key", default=None)
     ap.add_argument("rest", nargs="*")
-    args = ap.parse_args(argv)
+    args = ap.parse_intermixed_args(argv)
     import tinker_gpu_b200 as tg
     s = tg.load_tinker(args.xyz, args.key)
     if args.program == "analyze":
