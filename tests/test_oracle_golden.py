@@ -100,3 +100,29 @@ def test_tinkernist_frames():
     u1, _ = o.induce()
     assert np.abs(o.udir * DEBYE - fr["udir"][0]).max() < 1e-5
     assert np.abs(u1 * DEBYE - fr["uind"][0]).max() < 1e-5     # reference test tolerance is 1e-3
+
+
+def test_oracle_triclinic_gradient_is_consistent():
+    """No electrostatics golden of the reference lives in a non-orthogonal cell, so the oracle's triclinic branch is held
+    to its own energy: analytic gradient = central difference (fixture made from test/file/local_frame/local_frame2.xyz
+    with the cell of test/localframe2.cpp)."""
+    import os
+    import numpy as np
+    import tinker_gpu_b200 as tg
+    from conftest import GOLDEN
+    from oracle.amoeba_ref import Oracle, V0, V1
+    s = tg.load_system(os.path.join(GOLDEN, "lf_triclinic.npz"))
+    assert abs(s.lvec[0][1]) > 1 and abs(s.lvec[1][2]) > 1          # really triclinic
+    o = Oracle(s)
+    r = o.energy(V1)
+    x0 = o.xyz.copy()
+    h = 1e-5
+    for i, c in ((0, 0), (3, 1), (10, 2), (17, 0)):
+        xp, xm = x0.copy(), x0.copy()
+        xp[i, c] += h
+        xm[i, c] -= h
+        o.set_xyz(xp)
+        ep = o.energy(V0)["esum"]
+        o.set_xyz(xm)
+        em = o.energy(V0)["esum"]
+        assert abs((ep - em) / (2 * h) - r["grad"][i, c]) < 2e-6 * max(1.0, abs(r["grad"][i, c]))
