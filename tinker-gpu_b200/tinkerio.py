@@ -179,6 +179,7 @@ class ForceField:
     atom_class: dict = field(default_factory=dict)     # type -> class
     atom_name: dict = field(default_factory=dict)
     atom_mass: dict = field(default_factory=dict)
+    atom_atomic: dict = field(default_factory=dict)    # type -> atomic number (atomid::atomic)
     multipoles: list = field(default_factory=list)      # in file order (order matters in kmpole.f)
     polarize: dict = field(default_factory=dict)
     polpair: list = field(default_factory=list)         # (ia, ib, thole, dthole)
@@ -286,6 +287,8 @@ def read_prm(path: str) -> ForceField:
                 tail = t[2].split()
                 if len(tail) >= 2:
                     ff.atom_mass[typ] = _f(tail[1])
+                if tail and tail[0].lstrip("-").isdigit():
+                    ff.atom_atomic[typ] = int(tail[0])
         elif kw == "MULTIPOLE":
             ff.multipoles.append(parse_multipole(rest, raw[i:i + 4]))
             i += 4
