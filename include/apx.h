@@ -88,6 +88,57 @@ typedef struct apx_vdw {
    double elrc_vol, vlrc_vol; /* long-range correction x volume (src/evdw.cpp:443-452) */
 } apx_vdw;
 
+/* What ebondData ... etortorData upload for the AMOEBA valence terms (src/bonded/ebond.cpp, eangle.cpp, estrbnd.cpp,
+ * eurey.cpp, eopbend.cpp, etors.cpp, epitors.cpp, etortor.cpp): SURVEY.md 8f rank 3.  Atom indices are 0-based and
+ * already resolved (the reference keeps indirections through iang / ibnd / ibitor).  Term order everywhere:
+ * bond, angle, strbnd, urey, opbend, torsion, pitors, tortor. */
+typedef struct apx_valence {
+   int n;
+   int nbond;
+   const int* ibnd;          /* [nbond][2] */
+   const double *bk, *bl;
+   int nangle;
+   const int* iang;          /* [nangle][4]; [3] = out-of-plane atom of an in-plane angle */
+   const double *ak, *anat;  /* anat in degrees */
+   const int* angtyp;        /* 0 HARMONIC, 1 IN-PLANE */
+   int nstrbnd;
+   const int* isb;           /* [nstrbnd][3] atoms a, b, c */
+   const double* sbk;        /* [nstrbnd][2] */
+   const double* sb_anat;    /* ideal angle of the parent angle */
+   const double* sb_bl;      /* [nstrbnd][2] ideal a-b and c-b lengths */
+   int nurey;
+   const int* iury;          /* [nurey][3] */
+   const double *uk, *ul;
+   int nopbend;
+   const int* iopb;          /* [nopbend][4] a, b (centre), c, d (out of plane) */
+   const double* opbk;
+   int opbtyp;               /* 0 W-D-C, 1 ALLINGER */
+   int ntors;
+   const int* itors;         /* [ntors][4] */
+   const double* tors_v;     /* [ntors][6] amplitudes of folds 1..6 */
+   const double* tors_phase; /* [ntors][6] phases in degrees */
+   int npitors;
+   const int* ipit;          /* [npitors][6] */
+   const double* kpit;
+   int ntortor;
+   const int* itt;           /* [ntortor][5] atoms in table order */
+   const int* tt_chk;        /* chirality probe atom (src/bonded/etortor.cpp:86-132) or -1 */
+   const int* tt_grid;
+   int ngrid;
+   const int *tnx, *tny, *tt_off, *tt_xoff, *tt_yoff;
+   const double *ttx, *tty, *tbf, *tbx, *tby, *tbxy;
+   double consts[20];        /* bndunit cbnd qbnd angunit cang qang pang sang stbnunit ureyunit cury qury opbunit copb qopb popb
+                                sopb torsunit ptorunit ttorunit */
+   int use[8];               /* use_bond ... use_tortor */
+} apx_valence;
+
+typedef struct apx_valence_result {
+   double e[8];              /* energy_eb, ea, eba, eub, eopb, et, ept, ett */
+   int count[8];
+   double esum;              /* energy_valence */
+   double virial[9];         /* virial_valence */
+} apx_valence_result;
+
 typedef struct apx_ctx apx_ctx;
 
 typedef struct apx_energy_result {

@@ -69,6 +69,67 @@ class _ApxVdw(C.Structure):
                 ("elrc_vol", C.c_double), ("vlrc_vol", C.c_double)]
 
 
+_IP = C.POINTER(C.c_int)
+
+
+class _ApxValence(C.Structure):
+    """include/apx.h: apx_valence."""
+    _fields_ = [("n", C.c_int),
+                ("nbond", C.c_int), ("ibnd", _IP), ("bk", C.POINTER(C.c_double)), ("bl", C.POINTER(C.c_double)),
+                ("nangle", C.c_int), ("iang", _IP), ("ak", C.POINTER(C.c_double)), ("anat", C.POINTER(C.c_double)), ("angtyp", _IP),
+                ("nstrbnd", C.c_int), ("isb", _IP), ("sbk", C.POINTER(C.c_double)), ("sb_anat", C.POINTER(C.c_double)),
+                ("sb_bl", C.POINTER(C.c_double)),
+                ("nurey", C.c_int), ("iury", _IP), ("uk", C.POINTER(C.c_double)), ("ul", C.POINTER(C.c_double)),
+                ("nopbend", C.c_int), ("iopb", _IP), ("opbk", C.POINTER(C.c_double)), ("opbtyp", C.c_int),
+                ("ntors", C.c_int), ("itors", _IP), ("tors_v", C.POINTER(C.c_double)), ("tors_phase", C.POINTER(C.c_double)),
+                ("npitors", C.c_int), ("ipit", _IP), ("kpit", C.POINTER(C.c_double)),
+                ("ntortor", C.c_int), ("itt", _IP), ("tt_chk", _IP), ("tt_grid", _IP),
+                ("ngrid", C.c_int), ("tnx", _IP), ("tny", _IP), ("tt_off", _IP), ("tt_xoff", _IP), ("tt_yoff", _IP),
+                ("ttx", C.POINTER(C.c_double)), ("tty", C.POINTER(C.c_double)), ("tbf", C.POINTER(C.c_double)),
+                ("tbx", C.POINTER(C.c_double)), ("tby", C.POINTER(C.c_double)), ("tbxy", C.POINTER(C.c_double)),
+                ("consts", C.c_double * 20), ("use", C.c_int * 8)]
+
+
+class ValenceResult(C.Structure):
+    _fields_ = [("e", C.c_double * 8), ("count", C.c_int * 8), ("esum", C.c_double), ("virial", C.c_double * 9)]
+
+
+def valence_struct(v, n):
+    """apx_valence over the arrays of a valparams.ValenceTerms; returns (struct, arrays to keep alive)."""
+    keep = []
+
+    def f64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+        if a.size == 0:
+            a = np.zeros(1)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_double))
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32).ravel()
+        if a.size == 0:
+            a = np.zeros(1, np.int32)
+        keep.append(a)
+        return a.ctypes.data_as(_IP)
+
+    s = _ApxValence()
+    s.n = int(n)
+    s.nbond, s.ibnd, s.bk, s.bl = len(v.ibnd), i32(v.ibnd), f64(v.bk), f64(v.bl)
+    s.nangle, s.iang, s.ak, s.anat, s.angtyp = len(v.iang), i32(v.iang), f64(v.ak), f64(v.anat), i32(v.angtyp)
+    s.nstrbnd, s.isb, s.sbk, s.sb_anat, s.sb_bl = len(v.isb), i32(v.isb), f64(v.sbk), f64(v.sb_anat), f64(v.sb_bl)
+    s.nurey, s.iury, s.uk, s.ul = len(v.iury), i32(v.iury), f64(v.uk), f64(v.ul)
+    s.nopbend, s.iopb, s.opbk, s.opbtyp = len(v.iopb), i32(v.iopb), f64(v.opbk), int(v.opbtyp)
+    s.ntors, s.itors, s.tors_v, s.tors_phase = len(v.itors), i32(v.itors), f64(v.tors_v), f64(v.tors_phase)
+    s.npitors, s.ipit, s.kpit = len(v.ipit), i32(v.ipit), f64(v.kpit)
+    s.ntortor, s.itt, s.tt_chk, s.tt_grid = len(v.itt), i32(v.itt), i32(v.tt_chk), i32(v.tt_grid)
+    s.ngrid, s.tnx, s.tny = len(v.tnx), i32(v.tnx), i32(v.tny)
+    s.tt_off, s.tt_xoff, s.tt_yoff = i32(v.tt_off), i32(v.tt_xoff), i32(v.tt_yoff)
+    s.ttx, s.tty, s.tbf, s.tbx, s.tby, s.tbxy = f64(v.ttx), f64(v.tty), f64(v.tbf), f64(v.tbx), f64(v.tby), f64(v.tbxy)
+    s.consts = (C.c_double * 20)(*[float(x) for x in v.consts])
+    s.use = (C.c_int * 8)(*[int(x) for x in v.use])
+    return s, keep
+
+
 class Stats(C.Structure):
     _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
                 ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
@@ -120,6 +181,8 @@ def load_library(precision="mixed"):
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
         "apx_get_dist_info": [C.POINTER(C.c_int)],
         "apx_vdw_attach": [C.POINTER(_ApxVdw)], "apx_evdw": [C.c_int, C.POINTER(EnergyResult)],
+        "apx_valence_attach": [C.POINTER(_ApxValence)], "apx_evalence": [C.c_int, C.POINTER(ValenceResult)],
+        "apx_get_valence_gradient": [_DP],
         "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     }.items():
         fn = getattr(lib, name)
@@ -279,6 +342,25 @@ class Amoeba:
         s.cutoff, s.taper, s.ghal, s.dhal = float(v.cutoff), float(v.taper), float(v.ghal), float(v.dhal)
         s.elrc_vol, s.vlrc_vol = float(v.elrc_vol), float(v.vlrc_vol)
         self._chk(self.lib.apx_vdw_attach(self.ctx, C.byref(s)))
+
+    def attach_valence(self, v):
+        """ebondData ... etortorData (src/bonded/*.cpp): the valence terms of `v` (valparams.ValenceTerms) join energy()."""
+        if v is None:
+            raise ApxError("system has no valence terms")
+        s, keep = valence_struct(v, self.n)
+        self._chk(self.lib.apx_valence_attach(self.ctx, C.byref(s)))
+
+    def evalence(self, vers=calc.v1):
+        """The bonded terms alone (evalence_cu1, src/cu/evalence.cu): per-term energies and counts, virial_valence; the
+        gradient is read with valence_gradient()."""
+        r = ValenceResult()
+        self._chk(self.lib.apx_evalence(self.ctx, int(vers), C.byref(r)))
+        return r
+
+    def valence_gradient(self):
+        g = self._out(self.n, 3)
+        self._chk(self.lib.apx_get_valence_gradient(self.ctx, _dp(g)))
+        return g
 
     def evdw(self, vers=calc.v1):
         """evdw(vers) alone (src/evdw.cpp:472-530)."""

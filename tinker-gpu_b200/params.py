@@ -83,6 +83,7 @@ class System:
     title: str = ""
     mass: np.ndarray | None = None     # (n,) atomic masses (atomid::mass), used by the ANALYZE moments
     vdw: object | None = None          # vdwparams.VdwTerm: buffered 14-7 term, optional
+    valence: object | None = None      # valparams.ValenceTerms: bonded terms, optional
 
     @property
     def volume(self) -> float:
@@ -610,6 +611,10 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
     poltyp = (kget("POLARIZATION", "MUTUAL").split() or ["MUTUAL"])[0].upper()
     from .vdwparams import build_vdw
     vdw = build_vdw(n, types, ff.atom_class, i12, i13, i14, i15, key, ff, use_bounds, float(abs(np.linalg.det(lvec))), lbuffer)
+    valence = None
+    if any(len(b) for b in i12) and ff.keywords is not None:
+        from .valparams import build_valence
+        valence = build_valence(n, types, ff.atom_class, ff.atom_atomic, i12, key, ff)
     polpred = "NONE"
     if khas("POLAR-PREDICT"):          # predict.f:48-60: a bare keyword selects ASPC
         polpred = ((kget("POLAR-PREDICT") or "").split() or ["ASPC"])[0].upper()[:4]
@@ -622,7 +627,7 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         usolve_cutoff=usolve_applied, list_buffer=lbuffer,
         poleps=kfloat("POLAR-EPS", 1.0e-6), politer=int(kfloat("POLAR-ITER", 100)),
         poltyp=poltyp, polpred=polpred, electric=kfloat("ELECTRIC", COULOMB), dielec=kfloat("DIELECTRIC", 1.0),
-        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, vdw=vdw,
+        types=types.copy(), names=list(xyz.names), bonds=i12, title=xyz.title, vdw=vdw, valence=valence,
         mass=np.array([ff.atom_mass.get(int(t), 0.0) for t in types]), **lists)
 
 
@@ -678,7 +683,15 @@ def replicate(sys: System, reps, jitter: float = 0.0, seed: int = 20261017, keep
         pcgprec=sys.pcgprec, pcgguess=sys.pcgguess, pcgpeek=sys.pcgpeek, poltyp=sys.poltyp,
         polpred=sys.polpred, electric=sys.electric, dielec=sys.dielec, types=tile(sys.types) if sys.types is not None else None,
         names=(sys.names * m) if sys.names is not None else None, bonds=bonds,
-        title=f"{sys.title} x{nx}x{ny}x{nz}", vdw=_replicate_vdw(sys, m), mass=tile(sys.mass) if sys.mass is not None else None)
+        title=f"{sys.title} x{nx}x{ny}x{nz}", vdw=_replicate_vdw(sys, m), mass=tile(sys.mass) if sys.mass is not None else None,
+        valence=_replicate_valence(sys, m))
+
+
+def _replicate_valence(sys, m):
+    if sys.valence is None:
+        return None
+    from .valparams import replicate_valence
+    return replicate_valence(sys.valence, sys.n, m)
 
 
 def _replicate_vdw(sys, m):
@@ -708,6 +721,9 @@ def save_system(path: str, sys: System) -> None:
     if sys.vdw is not None:
         from .vdwparams import vdw_to_dict
         d.update(vdw_to_dict(sys.vdw))
+    if sys.valence is not None:
+        from .valparams import valence_to_dict
+        d.update(valence_to_dict(sys.valence))
     np.savez_compressed(path, **d)
 
 
@@ -724,4 +740,6 @@ def load_system(path: str) -> System:
     kw.setdefault("mass", None)
     from .vdwparams import vdw_from_npz
     kw["vdw"] = vdw_from_npz(z)
+    from .valparams import valence_from_npz
+    kw["valence"] = valence_from_npz(z)
     return System(**kw)
