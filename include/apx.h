@@ -149,6 +149,9 @@ typedef struct apx_energy_result {
    double pcg_eps;         /* final RMS residual in Debye */
    double ev;              /* energy_ev, 0 unless a vdW term is attached */
    int nev;
+   double evalence;        /* energy_valence, 0 unless valence terms are attached (then part of esum and virial) */
+   double eval_term[8];    /* eb, ea, eba, eub, eopb, et, ept, ett */
+   int nval_term[8];
 } apx_energy_result;
 
 /* timing / counters of the most recent operator call, CUDA events on the library stream */
@@ -228,6 +231,38 @@ int apx_epolar(apx_ctx* ctx, int vers, apx_energy_result* out);
 int apx_vdw_attach(apx_ctx* ctx, const apx_vdw* vdw);
 /* evdw(vers) -> ehal_cu: src/evdw.cpp:472-530, src/cu/ehal.cu:125-160 (vdW alone: ev, nev, virial, gradient) */
 int apx_evdw(apx_ctx* ctx, int vers, apx_energy_result* out);
+/* ebondData ... etortorData (src/bonded/*.cpp).  Once attached, apx_energy() also evaluates the valence terms -- one
+ * fused launch on its own stream (evalence_cu1, src/cu/evalence.cu) -- and esum / virial / gradient include them. */
+int apx_valence_attach(apx_ctx* ctx, const apx_valence* val);
+/* the valence terms alone: per-term energies and counts, virial_valence (energy(vers) with only bonded terms active,
+ * test/bond.cpp ... test/tortor.cpp); gradient through apx_get_valence_gradient */
+int apx_evalence(apx_ctx* ctx, int vers, apx_valence_result* out);
+int apx_get_valence_gradient(apx_ctx* ctx, double* grad /* [n][3] */);
+
+/* ---- DYNAMIC: velocity Verlet / r-RESPA + Bussi thermostat on the device (src/md/integrator.cpp:70-222,
+ * src/md/propagator.cpp:170-187, src/mdpt.cpp:41-71).  Positions and velocities stay in HBM between steps. */
+typedef struct apx_md_config {
+   double dt;              /* outer time step in ps */
+   int nrespa;             /* mdstuf::nrespa: 1 = velocity Verlet, >1 = r-RESPA with the valence terms on the inner level */
+   int thermostat;         /* 0 none (NVE), 1 Bussi (ThermostatEnum::BUSSI) */
+   double kelvin, tautemp; /* bath::kelvin, bath::tautemp (ps) */
+   int nfree;              /* mdstuf::nfree; <= 0: 3n - 3 */
+   unsigned long long seed;
+} apx_md_config;
+typedef struct apx_md_report {
+   double epot, ekin, temp;   /* after the last step: potential, kinetic energy (kcal/mol), temperature (K) */
+   double e_valence, e_nonbonded;
+   double last_scale;         /* velocity scale the thermostat applied in the last step */
+   int steps, pcg_iterations, list_rebuilds;
+   long long total_steps;
+   float ms_device;           /* device time of these steps (CUDA events on the library stream) */
+} apx_md_report;
+/* mdData + integrator kick-off: masses, starting velocities (NULL: at rest), gradients at the current positions */
+int apx_md_init(apx_ctx* ctx, const double* mass, const double* vel, const apx_md_config* cfg);
+/* nsteps x BasicIntegrator::dynamic(istep, dt) */
+int apx_md_steps(apx_ctx* ctx, int nsteps, apx_md_report* out);
+int apx_md_get_state(apx_ctx* ctx, double* xyz /* [n][3] or NULL */, double* vel /* [n][3] or NULL */);
+
 /* copyGradient: src/egvop.cpp:64-111 (fixed -> double, caller's order) */
 int apx_get_gradient(apx_ctx* ctx, double* grad /* [n][3] */);
 

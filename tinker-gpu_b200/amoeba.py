@@ -58,7 +58,8 @@ class _ApxSystem(C.Structure):
 class EnergyResult(C.Structure):
     _fields_ = [("em", C.c_double), ("ep", C.c_double), ("esum", C.c_double), ("virial", C.c_double * 9),
                 ("nem", C.c_int), ("nep", C.c_int), ("pcg_iterations", C.c_int), ("pcg_eps", C.c_double),
-                ("ev", C.c_double), ("nev", C.c_int)]
+                ("ev", C.c_double), ("nev", C.c_int),
+                ("evalence", C.c_double), ("eval_term", C.c_double * 8), ("nval_term", C.c_int * 8)]
 
 
 class _ApxVdw(C.Structure):
@@ -130,6 +131,18 @@ def valence_struct(v, n):
     return s, keep
 
 
+class MdConfig(C.Structure):
+    """include/apx.h: apx_md_config."""
+    _fields_ = [("dt", C.c_double), ("nrespa", C.c_int), ("thermostat", C.c_int), ("kelvin", C.c_double),
+                ("tautemp", C.c_double), ("nfree", C.c_int), ("seed", C.c_ulonglong)]
+
+
+class MdReport(C.Structure):
+    _fields_ = [("epot", C.c_double), ("ekin", C.c_double), ("temp", C.c_double), ("e_valence", C.c_double),
+                ("e_nonbonded", C.c_double), ("last_scale", C.c_double), ("steps", C.c_int), ("pcg_iterations", C.c_int),
+                ("list_rebuilds", C.c_int), ("total_steps", C.c_longlong), ("ms_device", C.c_float)]
+
+
 class Stats(C.Structure):
     _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
                 ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
@@ -183,6 +196,8 @@ def load_library(precision="mixed"):
         "apx_vdw_attach": [C.POINTER(_ApxVdw)], "apx_evdw": [C.c_int, C.POINTER(EnergyResult)],
         "apx_valence_attach": [C.POINTER(_ApxValence)], "apx_evalence": [C.c_int, C.POINTER(ValenceResult)],
         "apx_get_valence_gradient": [_DP],
+        "apx_md_init": [_DP, _DP, C.POINTER(MdConfig)], "apx_md_steps": [C.c_int, C.POINTER(MdReport)],
+        "apx_md_get_state": [_DP, _DP],
         "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     }.items():
         fn = getattr(lib, name)
@@ -361,6 +376,25 @@ class Amoeba:
         g = self._out(self.n, 3)
         self._chk(self.lib.apx_get_valence_gradient(self.ctx, _dp(g)))
         return g
+
+    def md_init(self, mass, vel=None, dt=0.002, nrespa=1, thermostat=None, kelvin=298.0, tautemp=0.2, nfree=0, seed=123456789):
+        """mdData + integrator kick-off (RespaIntegrator::KickOff, src/md/integrator.cpp:205-222).  dt, tautemp in ps."""
+        cfg = MdConfig(float(dt), int(nrespa), {None: 0, "NONE": 0, "BUSSI": 1}[thermostat if thermostat is None else str(thermostat).upper()],
+                       float(kelvin), float(tautemp), int(nfree), int(seed))
+        m = np.ascontiguousarray(mass, np.float64)
+        v = None if vel is None else np.ascontiguousarray(vel, np.float64)
+        self._chk(self.lib.apx_md_init(self.ctx, _dp(m), None if v is None else _dp(v), C.byref(cfg)))
+
+    def md_steps(self, nsteps):
+        """nsteps x BasicIntegrator::dynamic (src/md/integrator.cpp:70-170); returns the report of the last step."""
+        r = MdReport()
+        self._chk(self.lib.apx_md_steps(self.ctx, int(nsteps), C.byref(r)))
+        return r
+
+    def md_state(self):
+        x, v = self._out(self.n, 3), self._out(self.n, 3)
+        self._chk(self.lib.apx_md_get_state(self.ctx, _dp(x), _dp(v)))
+        return x, v
 
     def evdw(self, vers=calc.v1):
         """evdw(vers) alone (src/evdw.cpp:472-530)."""

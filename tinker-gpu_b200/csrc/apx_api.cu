@@ -353,6 +353,8 @@ void apx_destroy(apx_ctx* c)
    apx_pcg_graphs_invalidate(c);
    apx_pme_destroy(c);
    apx_vdw_destroy(c);
+   apx_valence_destroy(c);
+   apx_md_destroy(c);
    apx_dist_destroy(c);
    // views into the arenas are not owned
    c->gx.p = c->gy.p = c->gz.p = c->trqf.p = c->ebuf.p = nullptr;
@@ -521,7 +523,76 @@ int apx_energy(apx_ctx* c, int vers, apx_energy_result* out)
    API_BEGIN
    CUDA_CHECK(cudaSetDevice(c->device));
    ensure_ready(c);
-   apx_energy_impl(c, vers, true, true, out, true);
+   apx_energy_impl(c, vers, true, true, out, true, true);
+   API_END
+}
+
+int apx_valence_attach(apx_ctx* c, const apx_valence* v)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   if (!v)
+      APX_THROW("apx_valence_attach: null description");
+   apx_valence_attach_impl(c, v);
+   API_END
+}
+
+// the bonded terms alone (energy(vers) with only valence potentials switched on)
+int apx_evalence(apx_ctx* c, int vers, apx_valence_result* out)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (!apx_valence_on(c))
+      APX_THROW("apx_evalence: no valence terms attached (apx_valence_attach)");
+   apx_valence_enqueue(c, vers, c->stream, true);
+   apx_valence_fetch(c, c->stream);
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   apx_valence_result r;
+   apx_valence_collect(c, vers, &r);
+   if (out)
+      *out = r;
+   API_END
+}
+
+int apx_get_valence_gradient(apx_ctx* c, double* grad)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (!apx_valence_on(c))
+      APX_THROW("apx_get_valence_gradient: no valence terms attached");
+   c->io_a.ensure(3 * (size_t)c->n);
+   apx_valence_grad_out(c, c->io_a, false);
+   d2h(c, grad, c->io_a, 3 * (size_t)c->n);
+   API_END
+}
+
+int apx_md_init(apx_ctx* c, const double* mass, const double* vel, const apx_md_config* cfg)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (!mass || !cfg)
+      APX_THROW("apx_md_init: masses and configuration are required");
+   ensure_ready(c);
+   apx_md_init_impl(c, mass, vel, cfg);
+   API_END
+}
+
+int apx_md_steps(apx_ctx* c, int nsteps, apx_md_report* out)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   if (nsteps < 0)
+      APX_THROW("apx_md_steps: negative step count");
+   apx_md_steps_impl(c, nsteps, out);
+   API_END
+}
+
+int apx_md_get_state(apx_ctx* c, double* xyz, double* vel)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   apx_md_get_state_impl(c, xyz, vel);
    API_END
 }
 

@@ -160,9 +160,14 @@ struct VdwState {
    cudaEvent_t ev_go = nullptr, ev_done = nullptr, t0 = nullptr, t1 = nullptr;
 };
 
+struct ValState;           // evalence.cu
+struct MdState;            // md.cu
+
 struct apx_ctx {
    int device = 0;
    VdwState vdw;
+   ValState* val = nullptr;              // valence terms, when attached
+   MdState* md = nullptr;                // integrator state, after apx_md_init
    DistState dist;
    int a0 = 0, a1 = 0;                   // owned sorted range (single GPU: [0, n))
    int zbase = 0, nzl = 0;               // local PME planes: global plane zg lives at (zg - zbase) mod nfft3, nzl planes held
@@ -314,6 +319,24 @@ void apx_vdw_join(apx_ctx* c);                                     // main strea
 void apx_vdw_collect(apx_ctx* c, int vers, apx_energy_result* r);  // after the main stream is synchronised: ev, nev, virial into r
 void apx_vdw_destroy(apx_ctx* c);
 void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext);
+// ---- evalence.cu
+void apx_valence_attach_impl(apx_ctx* c, const apx_valence* v);
+bool apx_valence_on(const apx_ctx* c);
+void apx_valence_enqueue(apx_ctx* c, int vers, cudaStream_t st, bool zero_grad);   // zero + one fused launch on st
+void apx_valence_launch(apx_ctx* c, int vers);                     // on its own stream, forked from the main stream
+void apx_valence_join(apx_ctx* c);                                 // main stream waits, scalars go to pinned memory
+void apx_valence_fetch(apx_ctx* c, cudaStream_t st);
+void apx_valence_collect(apx_ctx* c, int vers, apx_valence_result* r);   // after the stream is synchronised
+void apx_valence_set_in_total(apx_ctx* c, int on);
+bool apx_valence_in_total(const apx_ctx* c);
+fixed_t* apx_valence_grad_buffer(apx_ctx* c);                      // [3][n] caller order
+void apx_valence_grad_out(apx_ctx* c, double* dev_out, bool accumulate);
+void apx_valence_destroy(apx_ctx* c);
+// ---- md.cu
+void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const apx_md_config* cfg);
+void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out);
+void apx_md_get_state_impl(apx_ctx* c, double* xyz, double* vel);
+void apx_md_destroy(apx_ctx* c);
 // ---- rows.cu
 void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort
 void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bctr, const real4* bext, real range, const int* exoff,
@@ -363,4 +386,5 @@ void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);
 void apx_unpack_dp(apx_ctx* c, const real4* in, real* d, real* p);
 void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real* fp);
 // ---- mplar.cu
-void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw = false);
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw = false, bool do_val = false);
+void apx_energy_impl_md(apx_ctx* c, int vers, apx_energy_result* out);      // slow level of the integrator: electrostatics + vdW

@@ -683,7 +683,7 @@ void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p);
 
-void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw)
+void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val)
 {
    const int n = c->n;
    const int a0 = c->a0, no = c->a1 - c->a0, n3 = 3 * no;      // per-atom passes run on the owned range
@@ -708,6 +708,10 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    do_vdw = do_vdw && c->vdw.on;
    if (do_vdw)
       apx_vdw_launch(c, vers);
+   // ---- valence terms, likewise (evalence.cu)
+   do_val = do_val && apx_valence_on(c);
+   if (do_val)
+      apx_valence_launch(c, vers);
    // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
    int iters = 0;
    if (do_p) {
@@ -824,6 +828,8 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    }
    if (do_vdw)
       apx_vdw_join(c);
+   if (do_val)
+      apx_valence_join(c);
    if (dist) {
       // every GPU holds partial sums: forces on frame atoms may belong to a neighbour's slab
       if (do_g)
@@ -882,12 +888,34 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       apx_vdw_collect(c, vers, &r);
       r.esum += r.ev;
    }
+   r.evalence = 0;
+   for (int t = 0; t < 8; ++t)
+      r.eval_term[t] = 0, r.nval_term[t] = 0;
+   if (do_val) {
+      apx_valence_result vr;
+      apx_valence_collect(c, vers, &vr);
+      r.evalence = vr.esum;
+      r.esum += vr.esum;
+      for (int t = 0; t < 8; ++t)
+         r.eval_term[t] = vr.e[t], r.nval_term[t] = vr.count[t];
+      if (do_v)
+         for (int q = 0; q < 9; ++q)
+            r.virial[q] += vr.virial[q];
+   }
+   apx_valence_set_in_total(c, do_val && do_g ? 1 : 0);
    if (out)
       *out = r;
+}
+
+void apx_energy_impl_md(apx_ctx* c, int vers, apx_energy_result* out)
+{
+   apx_energy_impl(c, vers, true, true, out, true, false);
 }
 
 void apx_grad_to_caller(apx_ctx* c, double* dev_out)
 {
    k_grad_out<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->n, c->perm, c->gx, c->gy, c->gz, dev_out);
    APX_COUNT_LAUNCH(c);
+   if (apx_valence_in_total(c))      // the last energy() included the valence terms: their gradient is kept in caller order
+      apx_valence_grad_out(c, dev_out, true);
 }

@@ -30,8 +30,11 @@ ALL_TERM_KEYWORDS = ("BONDTERM", "ANGLETERM", "STRBNDTERM", "UREYTERM", "ANGANGT
                      "TORTORTERM", "VDWTERM", "REPULSTERM", "DISPERSIONTERM", "CHARGETERM", "CHGDPLTERM",
                      "DIPOLETERM", "MULTIPOLETERM", "POLARIZETERM", "CHGTRNTERM", "CHGFLXTERM", "RXNFIELDTERM",
                      "SOLVATETERM", "METALTERM", "RESTRAINTERM", "EXTRATERM", "VALENCETERM")
-_UNSUPPORTED = ("BOND3", "BOND4", "BOND5", "ANGLE3", "ANGLE4", "ANGLE5", "ANGLEF", "TORSION4", "TORSION5", "ELECTNEG",
-                "IMPROPER", "IMPTORS", "STRTORS", "ANGTORS", "ANGANG", "OPDIST")
+# parameter records of terms / special cases that are not built: {keyword: number of leading class fields}.  A record only
+# matters when every class it names occurs in the system (ANGLEF is a fall-back of kangle.f: an angle that needs it is
+# reported as undefined instead)
+_UNSUPPORTED = {"BOND3": 2, "BOND4": 2, "BOND5": 2, "ANGLE3": 3, "ANGLE4": 3, "ANGLE5": 3, "TORSION4": 4, "TORSION5": 4,
+                "ELECTNEG": 3, "IMPROPER": 4, "IMPTORS": 4, "STRTORS": 4, "ANGTORS": 4, "ANGANG": 1, "OPDIST": 4}
 
 
 @dataclass
@@ -254,10 +257,17 @@ def _tortor_tables(lines):
 def build_valence(n, types, atom_class, atomic, i12, key, ff) -> ValenceTerms:
     """Assign all valence parameters of a system (kbond.f ... ktortor.f)."""
     srcs = ((ff.keywords.lines if ff.keywords is not None else []), key.lines)
+    present = {int(atom_class[int(t)]) for t in types}
     for src in srcs:
         for kw, rest, _ in src:
             if kw in _UNSUPPORTED:
-                raise NotImplementedError(f"valence keyword {kw} is not built (SURVEY.md section 8f rank 3 covers AMOEBA)")
+                try:
+                    ks = [abs(int(t)) for t in rest.split()[:_UNSUPPORTED[kw]]]
+                except ValueError:
+                    continue
+                if all(k == 0 or k in present for k in ks):
+                    raise NotImplementedError(f"valence record {kw} {rest.strip()} applies to this system but the term is "
+                                              "not built (SURVEY.md section 8f rank 3 covers the AMOEBA terms)")
 
     def kget(kw):
         v = key.get(kw)
