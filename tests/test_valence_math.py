@@ -48,8 +48,9 @@ def run(lib, xyz, v, real_bytes, terms=None):
 
 
 def load(blob):
-    z = np.load(os.path.join(G, blob))
-    return z["xyz"], vp.valence_from_npz(z)
+    import tinker_gpu_b200 as tg
+    s = tg.load_system(os.path.join(G, blob))
+    return s.xyz, s.valence
 
 
 @pytest.mark.parametrize("term", list(vr.TERMS))
@@ -79,7 +80,7 @@ def test_float_matches_reference_golden(host, term):
 
 def test_dhfr2_all_terms(host):
     """Full-size deck: all 48k interactions, double and float against the oracle; net force vanishes."""
-    xyz, v = load("val_dhfr2.npz")
+    xyz, v = load("dhfr2.npz")
     r = vr.valence(xyz, v)
     e8, g, vir = run(host, xyz, v, 8)
     assert abs(e8.sum() - r["esum"]) <= 1e-9 * abs(r["esum"])

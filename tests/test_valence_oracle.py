@@ -18,8 +18,9 @@ GOLD = json.load(open(os.path.join(G, "valence_goldens.json")))
 
 
 def load(blob):
-    z = np.load(os.path.join(G, blob))
-    return z["xyz"], vp.valence_from_npz(z)
+    import tinker_gpu_b200 as tg
+    s = tg.load_system(os.path.join(G, blob))
+    return s.xyz, s.valence
 
 
 @pytest.mark.parametrize("term", list(vr.TERMS))
@@ -63,7 +64,7 @@ def test_term_switches_follow_prmkey():
 def test_dhfr2_lists():
     """Every bonded interaction of the 23 558-atom DHFR deck gets parameters (build_valence raises otherwise);
     water contributes 2 bonds, 1 angle and 1 Urey-Bradley term per molecule."""
-    xyz, v = load("val_dhfr2.npz")
+    xyz, v = load("dhfr2.npz")
     assert len(xyz) == 23558
     nwat = 7023
     assert v.count("urey") == nwat

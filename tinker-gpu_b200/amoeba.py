@@ -269,8 +269,10 @@ class Amoeba:
     `world` GPUs (transport "nccl": handle = nccl_unique_id() of rank 0; "local": handle = LocalHub).
     Every method is then collective (all ranks call it in the same order)."""
 
-    def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None, vdw: bool = False):
-        """vdw=True also attaches the buffered 14-7 term of `system.vdw` (evdwData): energy() then returns the sum."""
+    def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None, vdw: bool = False,
+                 valence: bool = False):
+        """vdw=True also attaches the buffered 14-7 term of `system.vdw` (evdwData), valence=True the bonded terms of
+        `system.valence` (ebondData ... etortorData): energy() then returns the sum."""
         self.lib = load_library(precision)
         self.system = system
         self.n = system.n
@@ -336,6 +338,8 @@ class Amoeba:
         self.last = None
         if vdw:
             self.attach_vdw(system.vdw)
+        if valence:
+            self.attach_valence(system.valence)
 
     def attach_vdw(self, v):
         """evdwData(RcOp::ALLOC|INIT), src/evdw.cpp:62-470."""
@@ -483,7 +487,8 @@ class Amoeba:
         r = EnergyResult()
         self._chk(fn(self.ctx, int(vers), C.byref(r)))
         out = dict(em=r.em, ep=r.ep, esum=r.esum, virial=np.array(list(r.virial)).reshape(3, 3), nem=r.nem, nep=r.nep,
-                   pcg_iterations=r.pcg_iterations, pcg_eps=r.pcg_eps, ev=r.ev, nev=r.nev)
+                   pcg_iterations=r.pcg_iterations, pcg_eps=r.pcg_eps, ev=r.ev, nev=r.nev,
+                   evalence=r.evalence, eval_term=np.array(list(r.eval_term)), nval_term=np.array(list(r.nval_term)))
         if vers & calc.grad:
             out["grad"] = self.gradient()
         self.last = out

@@ -83,6 +83,69 @@ def write_xyz(path: str, sysxyz: XYZ) -> None:
             fh.write(f"{i + 1:6d}  {sysxyz.names[i]:<3s}{x:12.6f}{y:12.6f}{z:12.6f}{sysxyz.types[i]:6d}{conn}\n")
 
 
+def append_arc_frame(path: str, sysxyz: XYZ) -> None:
+    """One more frame at the end of a Tinker archive (mdsave.f:256-266 -> prtxyz): the .xyz record repeated."""
+    import tempfile
+    with tempfile.NamedTemporaryFile("r", suffix=".xyz") as tmp:
+        write_xyz(tmp.name, sysxyz)
+        frame = open(tmp.name).read()
+    with open(path, "a") as fh:
+        fh.write(frame)
+
+
+def _fortran_d(v: float, width: int = 26, digits: int = 16) -> str:
+    """Fortran D<width>.<digits> edit descriptor: 0.dddddD+ee."""
+    if v == 0.0:
+        body = "0." + "0" * digits + "D+00"
+    else:
+        m, e = f"{abs(v):.{digits - 1}E}".split("E")
+        mant = m.replace(".", "")
+        body = ("-" if v < 0 else "") + "0." + mant + "D" + f"{int(e) + 1:+03d}"
+    return body.rjust(width)
+
+
+def write_dyn(path: str, title: str, box6, xyz, vel, acc, aalt=None) -> None:
+    """Restart file of a trajectory (tinker/source/prtdyn.f): positions, velocities, accelerations, alternate
+    accelerations, each as 3D26.16 per atom."""
+    n = len(xyz)
+    aalt = np.zeros_like(np.asarray(xyz)) if aalt is None else aalt
+    with open(path, "w") as fh:
+        fh.write(" Number of Atoms and Title :\n")
+        fh.write(f"{n:6d}  {title}\n")
+        fh.write(" Periodic Box Dimensions :\n")
+        b = list(box6) if box6 is not None else [0.0] * 6
+        fh.write("".join(_fortran_d(v) for v in b[:3]) + "\n")
+        fh.write("".join(_fortran_d(v) for v in b[3:]) + "\n")
+        for label, arr in ((" Current Atomic Positions :", xyz), (" Current Atomic Velocities :", vel),
+                           (" Current Atomic Accelerations :", acc), (" Alternate Atomic Accelerations :", aalt)):
+            fh.write(label + "\n")
+            for row in np.asarray(arr, float):
+                fh.write("".join(_fortran_d(v) for v in row) + "\n")
+
+
+def read_dyn(path: str):
+    """-> dict(n, title, box, xyz, vel, acc, aalt) of a .dyn restart file (tinker/source/readdyn.f)."""
+    with open(path) as fh:
+        lines = fh.read().splitlines()
+
+    def nums(ln):
+        return [float(t.replace("D", "E").replace("d", "e")) for t in ln.split()]
+    head = lines[1].split(None, 1)
+    n = int(head[0])
+    out = dict(n=n, title=head[1].strip() if len(head) > 1 else "", box=None)
+    k = 2
+    if lines[k].strip().startswith("Periodic Box"):
+        out["box"] = nums(lines[k + 1]) + nums(lines[k + 2])
+        k += 3
+    for name in ("xyz", "vel", "acc", "aalt"):
+        if k >= len(lines):
+            break
+        k += 1          # section label
+        out[name] = np.array([nums(lines[k + i]) for i in range(n)])
+        k += n
+    return out
+
+
 @dataclass
 class KeyFile:
     """Keyword lines of a .key (and of the .prm it names), upper-cased keys."""
