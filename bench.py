@@ -4,7 +4,11 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N ...            # reference arm: CPU oracle on host cores
 
-One "step" = one pass of the hot path over the dhfr2 system (BASELINE.json configs[1]):
+Default (--mode dynamics, BASELINE.json configs[1]): one "step" = one 2 fs r-RESPA MD step of dhfr2 on the device integrator
+(csrc/md.cu): 4 valence evaluations + kick/drift, neighbour-list check, induce() + electrostatics + vdW, Bussi thermostat;
+`value` = ns/day with the state resident in HBM, `md.batch` the same without L2 flushes, `e2e` the plugin call with host buffers.
+
+--mode energy (the round-1 metric, default for the large boxes): one "step" = one pass of the hot path over the system:
 energy(energy+grad) restricted to the electrostatic terms = mpoleInit + induce() (PCG) +
 fused real-space multipole/polarization + reciprocal space + torque + reductions
 (SURVEY.md §3.1 "HOT").  The metric carries both numbers BASELINE.json names:
@@ -164,6 +168,226 @@ def cpu_oracle_sample(system, full=False):
     desc = (f"oracle/amoeba_ref.py (numpy f64 port) on dhfr2: full induce() ({o.niter} iterations) + reciprocal energy/force + "
             f"real-space energy/gradient on {take} of {npair} pairs scaled to all pairs")
     return ms_step, 1e3 * t_ind, desc
+
+
+MD_METRIC = "ns/day & ms/induce() AMOEBA DHFR 23.5k atoms (dynamic, 2 fs RESPA, NVT)"
+MD_WORKLOAD = ("example/dhfr2 AMOEBA DHFR 23558 atoms (amoebabio09): dynamic 2 fs r-RESPA (4 inner valence steps), NVT Bussi 298 K, "
+               "PME 64^3 order 5, ewald-cutoff 7.0, vdw-cutoff 12.0, polar-eps 1e-5")
+MD_DT_PS, MD_NRESPA, MD_KELVIN, MD_TAU, MD_SEED = 0.002, 4, 298.0, 0.2, 20261017
+
+
+def cpu_dynamics_sample(system):
+    """One MD step of the CPU oracle on a bounded sample: the electrostatics sample of cpu_oracle_sample (full induce(),
+    reciprocal space, a slice of the real-space pairs scaled up) + the full vdW oracle + nrespa evaluations of the
+    valence oracle.  The integrator's own cost is negligible beside these.  Returns (ms_step, ms_induce, description)."""
+    from oracle import valence_ref
+    from oracle.vdw_ref import VdwOracle
+    ms_elec, ms_ind, desc = cpu_oracle_sample(system)
+    t0 = time.perf_counter()
+    VdwOracle(system).ehal()
+    ms_vdw = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    valence_ref.valence(system.xyz, system.valence)
+    ms_val = 1e3 * (time.perf_counter() - t0)
+    return (ms_elec + ms_vdw + MD_NRESPA * ms_val, ms_ind,
+            desc + f"; + oracle/vdw_ref.py all pairs within 12 A ({ms_vdw:.0f} ms) + {MD_NRESPA} x oracle/valence_ref.py ({ms_val:.0f} ms each)")
+
+
+def run_reference_dynamics(args, rank, world):
+    import tinker_gpu_b200 as tg
+    if rank != 0:
+        return
+    system = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    steps = max(1, min(args.steps, 2))
+    ms, ms_ind, desc = [], [], ""
+    for _ in range(steps):
+        a, b, desc = cpu_dynamics_sample(system)
+        ms.append(a)
+        ms_ind.append(b)
+    ms_step = float(np.mean(ms))
+    val = ns_per_day(ms_step)
+    print(json.dumps({
+        "impl": "reference", "metric": MD_METRIC, "value": val, "unit": "ns/day", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        "ms_per_step": ms_step, "ms_per_induce": float(np.mean(ms_ind)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "reference input deck example/dhfr2 (blob tests/golden/dhfr2.npz)",
+        "config": {"workload": MD_WORKLOAD,
+                   "note": "CPU arm: the reference executable needs gfortran (absent); the oracle ports are timed instead, one core"},
+        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_dynamics(args, rank, world, local_rank):
+    """BASELINE.json configs[1]: dhfr2 dynamic, 2 fs RESPA, on the device integrator (csrc/md.cu).  One step = one outer
+    RESPA step: 4 valence evaluations + kick/drift, list check, induce + electrostatics + vdW, thermostat."""
+    import ctypes as C
+    import torch
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import Amoeba, MdReport, calc
+    from tinker_gpu_b200.drivers import maxwell_velocities
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    system = make_system("dhfr2")
+    n = system.n
+    a = Amoeba(system, "mixed", device=local_rank, vdw=True, valence=True)
+    ext = torch.cuda.ExternalStream(a.lib.apx_stream(a.ctx), device=local_rank)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    nfree = 3 * n - 3
+    vel = maxwell_velocities(system.mass, MD_KELVIN, MD_SEED + rank, nfree)
+    a.md_init(system.mass, vel, dt=MD_DT_PS, nrespa=MD_NRESPA, thermostat="BUSSI", kelvin=MD_KELVIN, tautemp=MD_TAU, nfree=nfree,
+              seed=MD_SEED + rank)
+    rep = MdReport()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def md(k):
+        if a.lib.apx_md_steps(a.ctx, k, C.byref(rep)) != 0:
+            raise SystemExit("apx_md_steps failed: " + a.lib.apx_last_error().decode())
+
+    md(max(args.warmup, 3) + 3)      # eager pass, graph capture, replay: the step graphs exist before anything is timed
+    a.synchronize()
+
+    # ---- resident leg (value): one MD step per timed region, CUDA events on the library stream, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    a.stats_reset()
+    ms_steps, ms_induce, ms_uf, iters = [], [], [], []
+    rebuilds = 0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        md(1)
+        e1.record(ext)
+        e1.synchronize()
+        ms_steps.append(e0.elapsed_time(e1))
+        st = a.stats()
+        ms_induce.append(st["ms_induce"])
+        ms_uf.append(st["ms_ufield_real"])
+        iters.append(st["pcg_iterations"])
+        rebuilds += rep.list_rebuilds
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = a.stats()["kernel_launches"]
+    ms_step = float(np.mean(ms_steps))
+    temp, epot, ekin = rep.temp, rep.epot, rep.ekin
+
+    # ---- production batch: K steps in one C-ABI call, no flushes (what `dynamic` does between saves); device time from the library
+    md(args.steps)
+    ms_batch = rep.ms_device / max(1, args.steps)
+    x_md, v_md = a.md_state()
+
+    # ---- e2e leg: the reference-facing plugin call energy(vers) with HOST buffers every step -- positions in from host memory,
+    #      electrostatics + vdW + valence energy and gradient, gradient back to host (what an integrator on the host side of the
+    #      C ABI pays per force evaluation)
+    a.attach_valence(system.valence)     # (already attached; keeps the call sequence of a host-driven run explicit)
+    rng = np.random.default_rng(1234 + rank)
+    drift = np.array([0.06, 0.04, 0.035])
+    nframes = 2 + args.steps
+    frames = [x_md + drift * float(j) + rng.normal(scale=0.002, size=x_md.shape) for j in range(nframes)]
+
+    def step_e2e(j):
+        a.set_positions(frames[j % nframes])
+        rc = a.lib.apx_energy(a.ctx, calc.v4, None)
+        a.gradient()
+        return rc
+
+    for j in range(2):
+        step_e2e(j)
+    barrier()
+    reb0 = a.stats()["list_rebuilds"]
+    ms_e2e = []
+    for j in range(2, 2 + args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        if step_e2e(j) != 0:
+            raise SystemExit("apx_energy failed: " + a.lib.apx_last_error().decode())
+        e1.record(ext)
+        e1.synchronize()
+        ms_e2e.append(e0.elapsed_time(e1))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e_step = float(np.mean(ms_e2e))
+    reb_e2e = a.stats()["list_rebuilds"] - reb0
+
+    if dist is not None:
+        t = torch.tensor([ms_step, ms_e2e_step, float(np.mean(ms_induce)), ms_batch], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e_step, ms_ind, ms_batch = (float(v) for v in t.tolist())
+    else:
+        ms_ind = float(np.mean(ms_induce))
+
+    if rank == 0:
+        st = a.stats()
+        hbm_peak, sm_max, peak_src = load_peaks()
+        npairs = max(1, st["npairs_m"])
+        uf_ms = float(np.mean(ms_uf)) if ms_uf else 0.0
+        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 2 * npairs
+        uf_flops = 130.0 * npairs
+        achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
+        sm_clk = (clocks or {}).get("sm_mhz") or sm_max
+        traffic = load_ncu_traffic("k_ufield_rows")
+        fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
+        line = {
+            "metric": MD_METRIC, "value": ns_per_day(ms_step, world), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3) + 3, "ms_per_step": ms_step, "ms_per_induce": ms_ind,
+            "pcg_iterations": float(np.mean(iters)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 pair math + 2^32 fixed-point accumulation; f64 valence terms, positions and velocities",
+            "data": "reference input deck example/dhfr2 parsed by our readers (blob tests/golden/dhfr2.npz); Maxwell velocities at 298 K, seeded",
+            "config": {"workload": MD_WORKLOAD, "atoms": int(n), "parallelism": "single GPU" if world == 1 else f"replicas x{world}",
+                       "l2": "flushed (256 MB write) between timed steps",
+                       "timing": "CUDA events on the library stream around each MD step (one apx_md_steps(1) call), mean of steps, max over ranks",
+                       "hot_path_only": False,
+                       "terms": "multipole + polarization (PCG) + buffered 14-7 vdW every outer step; 8 valence terms on the inner level"},
+            "md": {"temperature_K": temp, "epot": epot, "ekin": ekin, "list_rebuilds_in_timed_steps": int(rebuilds),
+                   "batch": {"value": ns_per_day(ms_batch, world), "unit": "ns/day", "ms_per_step": ms_batch,
+                             "note": f"{args.steps} steps in ONE apx_md_steps call, no L2 flush: the rate a production run sees"}},
+            "e2e": {"value": ns_per_day(ms_e2e_step, world), "unit": "ns/day", "ms_per_step": ms_e2e_step,
+                    "h2d_bytes_per_step": int(x_md.nbytes), "d2h_bytes_per_step": int(x_md.nbytes) + 136 + 128,
+                    "list_rebuilds": int(reb_e2e),
+                    "note": "reference-facing plugin call with host buffers: set_positions (H2D) -> energy(energy+grad) of electrostatics + "
+                            "vdW + valence -> gradient (D2H), one per 2 fs step; positions drift 0.08 A/step so list rebuilds fall inside"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_ufield_rows_rec (real-space CG operator, 1 launch per PCG iteration)", "bound": "hbm",
+                         "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                         "traffic": traffic[0] if traffic else None,
+                         "traffic_source": ("profiles/" + traffic[1] + " (ncu --set full, cold-cache replay)") if traffic else None,
+                         "algorithmic_bytes": uf_bytes, "peak_source": peak_src, "ms_per_launch": uf_ms,
+                         "note": ("not an HBM-bound kernel: ncu shows it bound by L1 sector traffic of the neighbour gathers and instruction "
+                                  "issue (profiles/r01j_water1m_ncu_full_summary.txt); see roofline_fp32 and DESIGN.md section 5")},
+            "roofline_fp32": {"achieved": uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0, "peak": fp32_peak,
+                              "unit": "TFLOP/s", "frac": (uf_flops / (uf_ms * 1e-3) / 1e12 / fp32_peak) if uf_ms > 0 else 0.0,
+                              "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs)},
+            "vdw": {"ms_ehal_kernel": st["ms_ehal"], "directed_row_entries": int(st["nverlet_vdw"])},
+            "wall_s_timed_region": t_wall,
+        }
+        if not args.no_cpu:
+            ms_cpu, ms_cpu_ind, desc = cpu_dynamics_sample(system)
+            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": "port", "sample": desc,
+                                    "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
+                                    "note": "vectorised-numpy / torch-f64 ports on one core, about two orders of magnitude slower than the "
+                                            "reference's compiled host build would be (it cannot be linked here: no Fortran compiler); "
+                                            "reported, not a target"}
+        print(json.dumps(line))
+    a.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def run_reference(args, rank, world):
@@ -384,12 +608,21 @@ def main():
     ap.add_argument("--workload", default="dhfr2", choices=sorted(WORKLOADS))
     ap.add_argument("--vdw", action="store_true", help="also evaluate the buffered 14-7 vdW term (SURVEY 8f rank 1) in every step")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas also for the large workloads")
+    ap.add_argument("--mode", default=None, choices=["dynamics", "energy"],
+                    help="dynamics: full MD steps on the device integrator (default for dhfr2, BASELINE configs[1]); "
+                         "energy: one electrostatics energy+gradient per step (default for the large boxes)")
     args = ap.parse_args()
+    if args.mode is None:
+        args.mode = "dynamics" if (args.workload == "dhfr2" and not args.vdw) else "energy"
+    if args.mode == "dynamics" and args.workload != "dhfr2":
+        ap.error("--mode dynamics is built for the dhfr2 workload")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        (run_reference_dynamics if args.mode == "dynamics" else run_reference)(args, rank, world)
+    elif args.mode == "dynamics":
+        run_dynamics(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 
