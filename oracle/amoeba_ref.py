@@ -652,14 +652,15 @@ class Oracle:
         pga = s.thlval[s.jpolar[i], s.jpolar[k]]
         return s.pdamp[i], s.pdamp[k], pga
 
-    def dfield(self):
-        """Permanent field (d and p scalings) at every atom; dfield() of src/amoeba/field.cpp:56-64."""
+    def dfield(self, real_only=False):
+        """Permanent field (d and p scalings) at every atom; dfield() of src/amoeba/field.cpp:56-64.
+        real_only: the real-space pair sum alone (what dfieldEwaldReal adds, for the check against oracle/_ref)."""
         s = self.s
         n = self.n
         rp = self._ensure_rpole()
         fd = np.zeros((n, 3))
         fp = np.zeros((n, 3))
-        if s.use_ewald:
+        if s.use_ewald and not real_only:
             cmp_ = self.rpole_to_cmp(rp)
             fmp = self.cmp_to_fmp(cmp_)
             grid, e, v = self.pme_convolve(self.grid_mpole(fmp), want_ev=True)
@@ -685,13 +686,13 @@ class Oracle:
             np.add.at(out, i, ei)
         return fd, fp
 
-    def ufield(self, ud, up):
+    def ufield(self, ud, up, real_only=False):
         """Mutual field of dipoles (ud, up); ufield() of src/amoeba/field.cpp:111-117."""
         s = self.s
         n = self.n
         fd = np.zeros((n, 3))
         fp = np.zeros((n, 3))
-        if s.use_ewald:
+        if s.use_ewald and not real_only:
             a = self.pme_setup()["a"]
             grid, _, _ = self.pme_convolve(self.grid_uind(ud @ a, up @ a))
             f1 = self.fphi_gather(grid.real, 10)

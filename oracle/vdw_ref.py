@@ -92,25 +92,9 @@ class VdwOracle:
         k = np.concatenate(out_k) if out_k else np.zeros(0, int)
         return i, k
 
-    def ehal(self, want_grad=True):
-        """Returns dict(ev, nev, grad (n,3) on the real atoms, virial (3,3))."""
+    def pair_terms(self, r, rv, eps):
+        """Buffered 14-7 energy and dE/dr of every pair, tapered between `taper` and `cutoff` (include/seq/pair_hal.h:49-86)."""
         v = self.v
-        n = self.n
-        xr = self.reduced()
-        i, k = self.pairs(xr)
-        scale = np.ones(i.shape[0])
-        if v.vexclude.shape[0]:
-            code = i.astype(np.int64) * n + k
-            ex = v.vexclude[:, 0].astype(np.int64) * n + v.vexclude[:, 1]
-            order = np.argsort(ex)
-            pos = np.searchsorted(ex[order], code)
-            pos = np.minimum(pos, ex.shape[0] - 1)
-            hit = ex[order][pos] == code
-            scale[hit] = v.vexclude_scale[order][pos[hit]]
-        d = self.image(xr[i] - xr[k])                     # xr = xi - xk, as ehal_cu1
-        r = np.sqrt((d * d).sum(1))
-        rv = v.radmin[v.jvdw[i], v.jvdw[k]]
-        eps = v.epsilon[v.jvdw[i], v.jvdw[k]] * scale
         ghal, dhal = v.ghal, v.dhal
         rho = r / np.where(rv > 0, rv, 1.0)
         rho6 = rho ** 6
@@ -131,6 +115,29 @@ class VdwOracle:
             dtaper = 30.0 * (x * (1.0 - x)) ** 2 / (cut - off)
             de[sw] = e[sw] * dtaper + de[sw] * taper
             e[sw] = e[sw] * taper
+        return e, de
+
+    def ehal(self, want_grad=True):
+        """Returns dict(ev, nev, grad (n,3) on the real atoms, virial (3,3))."""
+        v = self.v
+        n = self.n
+        xr = self.reduced()
+        i, k = self.pairs(xr)
+        scale = np.ones(i.shape[0])
+        if v.vexclude.shape[0]:
+            code = i.astype(np.int64) * n + k
+            ex = v.vexclude[:, 0].astype(np.int64) * n + v.vexclude[:, 1]
+            order = np.argsort(ex)
+            pos = np.searchsorted(ex[order], code)
+            pos = np.minimum(pos, ex.shape[0] - 1)
+            hit = ex[order][pos] == code
+            scale[hit] = v.vexclude_scale[order][pos[hit]]
+        d = self.image(xr[i] - xr[k])                     # xr = xi - xk, as ehal_cu1
+        r = np.sqrt((d * d).sum(1))
+        rv = v.radmin[v.jvdw[i], v.jvdw[k]]
+        eps = v.epsilon[v.jvdw[i], v.jvdw[k]] * scale
+        ghal, dhal = v.ghal, v.dhal
+        e, de = self.pair_terms(r, rv, eps)
         ev = float(e.sum())
         nev = int(((scale != 0) & (e != 0)).sum())
         out = dict(ev=ev, nev=nev, npairs=int(i.shape[0]))

@@ -1,0 +1,144 @@
+"""oracle/_ref: the reference's OWN arithmetic for the path (its include/seq pair and valence headers compiled in place by
+oracle/Makefile) against the oracle restatements and against the CPU build of the CUDA library's valence math.  This is
+what ties the oracle -- and through the oracle the CUDA path -- to the reference at full dhfr2 size, where the reference
+tree holds no golden.  Skipped where neither /root/reference nor a prebuilt oracle/_ref exists."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, REFERENCE, ROOT
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_bridge
+    if os.path.isdir(REFERENCE):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    if not (ref_bridge.available("valence") and ref_bridge.available("realspace")):
+        pytest.skip("oracle/_ref not built (no reference tree here)")
+    return ref_bridge
+
+
+def _load(blob):
+    import tinker_gpu_b200 as tg
+    return tg.load_system(os.path.join(GOLDEN, blob))
+
+
+@pytest.mark.parametrize("blob", ["val_trpcage.npz", "val_trpcage_angle.npz", "val_water10.npz", "dhfr2.npz"])
+def test_valence_oracle_equals_reference_arithmetic(ref, blob):
+    """dk_bond ... dk_tortor of include/seq/*.h in double against the autograd oracle: every term energy, the gradient and
+    the virial (incl. the reference's own pi-torsion virial expression), up to the 48 013 interactions of dhfr2."""
+    from oracle import valence_ref as vr
+    s = _load(blob)
+    r = ref.valence(s)
+    o = vr.valence(s.xyz, s.valence)
+    for k, t in enumerate(vr.TERMS):
+        assert abs(r["energy"][k] - o["energy"].get(t, 0.0)) <= 1e-11 * max(1.0, abs(o["energy"].get(t, 0.0))), t
+    assert np.abs(r["grad"] - o["grad"]).max() < 1e-10
+    assert np.abs(r["virial"] - o["virial"]).max() < 1e-8
+
+
+@pytest.mark.parametrize("blob", sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "lf_*.npz"))))
+def test_realspace_oracle_equals_reference_arithmetic_small(ref, blob):
+    """pair_mpole / pair_polar / pair_dfield / pair_ufield (EWALD pass + NON_EWALD (scale-1) pass, as the reference's loops
+    do) against the oracle's tensor-contraction formulation on every local-frame deck: orthogonal, monoclinic, triclinic
+    cells, Ewald and non-Ewald, with 1-2...1-5 and group scaling."""
+    from oracle.amoeba_ref import Oracle, V4
+    s = _load(blob)
+    o = Oracle(s)
+    o.rotpole()
+    if s.use_polar:
+        o.induce()
+    r = ref.realspace(o, o.uind if s.use_polar else None, o.uinp if s.use_polar else None)
+    rs = o._real_space(V4, s.use_mpole, s.use_polar)
+    fd, fp = o.dfield(real_only=True)
+    tol = 1e-11
+    if s.use_mpole:
+        assert abs(r["em"] - rs["em"]) <= tol * max(1.0, abs(rs["em"]))
+        assert np.abs(r["gm"] - rs["gm"]).max() <= tol * max(1.0, np.abs(rs["gm"]).max())
+        assert np.abs(r["tm"] - rs["tm"]).max() <= tol * max(1.0, np.abs(rs["tm"]).max())
+    assert np.abs(r["fd"] - fd).max() <= tol and np.abs(r["fp"] - fp).max() <= tol
+    if s.use_polar:
+        ufd, ufp = o.ufield(o.uind, o.uinp, real_only=True)
+        assert abs(r["ep"] - rs["ep"]) <= tol * max(1.0, abs(rs["ep"]))
+        assert np.abs(r["gp"] - rs["gp"]).max() <= tol * max(1.0, np.abs(rs["gp"]).max())
+        assert np.abs(r["tp"] - rs["tp"]).max() <= tol * max(1.0, np.abs(rs["tp"]).max())
+        assert np.abs(r["ufd"] - ufd).max() <= tol and np.abs(r["ufp"] - ufp).max() <= tol
+
+
+def test_realspace_dhfr2_fixture_equals_reference_arithmetic(ref):
+    """Full size: the oracle's real-space energies, gradient, torque and fields over the 1 644 163 pairs of dhfr2 (fixture
+    tests/golden/dhfr2_oracle_real.npz, ~10 oracle minutes, made by make_ref_fixtures.py) against the reference's pair
+    functions run here in about a second.  With test_gpu_parity.py::test_dhfr2_vs_oracle_fixture holding the CUDA path to
+    the same oracle run, dhfr2 parity is pinned to the reference's arithmetic for everything but the PME reciprocal part."""
+    from oracle.amoeba_ref import Oracle
+    s = _load("dhfr2.npz")
+    z = np.load(os.path.join(GOLDEN, "dhfr2_oracle.npz"))
+    f = np.load(os.path.join(GOLDEN, "dhfr2_oracle_real.npz"))
+    o = Oracle(s)
+    o.rotpole()
+    r = ref.realspace(o, z["uind"], z["uinp"])
+    assert r["npair"] == int(f["npairs"]) == int(z["npairs"])
+    assert abs(r["em"] - float(z["em_real"])) <= 1e-11 * abs(float(z["em_real"]))
+    assert abs(r["em"] - float(f["em_real"])) <= 1e-11 * abs(float(f["em_real"]))
+    assert abs(r["ep"] - float(f["ep_real"])) <= 1e-11 * abs(float(f["ep_real"]))
+    g, t = r["gm"] + r["gp"], r["tm"] + r["tp"]
+    assert np.abs(g - f["g_real"]).max() <= 1e-10 * np.abs(f["g_real"]).max()
+    assert np.abs(t - f["t_real"]).max() <= 1e-10 * np.abs(f["t_real"]).max()
+    for a, b in (("fd", "fd_real"), ("fp", "fp_real"), ("ufd", "ufd_real"), ("ufp", "ufp_real")):
+        assert np.abs(r[a] - f[b]).max() <= 1e-12, a
+
+
+def test_cuda_valence_math_equals_reference_arithmetic(ref, tmp_path):
+    """The interaction math the CUDA kernel executes (csrc/valmath.cuh, compiled for the CPU by tests/valmath_host.cpp,
+    double) against the reference's functions on dhfr2."""
+    import ctypes as C
+    import importlib
+    am = importlib.import_module("tinker-gpu_b200.amoeba")
+    so = str(tmp_path / "valmath_host.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tinker-gpu_b200", "csrc"), os.path.join(ROOT, "tests", "valmath_host.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.valmath_host_eval.argtypes = [C.c_int, C.POINTER(am._ApxValence), dp, C.c_int, dp, dp, dp]
+    s = _load("dhfr2.npz")
+    st, keep = am.valence_struct(s.valence, s.n)
+    x = np.ascontiguousarray(s.xyz, np.float64)
+    e8, g, v6 = np.zeros(8), np.zeros((s.n, 3)), np.zeros(6)
+    lib.valmath_host_eval(8, C.byref(st), x.ctypes.data_as(dp), 1, e8.ctypes.data_as(dp), g.ctypes.data_as(dp), v6.ctypes.data_as(dp))
+    r = ref.valence(s)
+    assert np.abs(e8 - r["energy"]).max() <= 1e-9
+    assert np.abs(g - r["grad"]).max() <= 1e-9
+    vir = np.array([[v6[0], v6[1], v6[2]], [v6[1], v6[3], v6[4]], [v6[2], v6[4], v6[5]]])
+    assert np.abs(vir - r["virial"]).max() <= 1e-7
+
+
+def test_bspline_tables_equal_reference(ref):
+    """Order-5 B-spline weights and derivatives (the PME spreading / gathering stencil) from bsplgen<4> of
+    include/seq/bsplgen.h against the oracle's tables, over the whole range of fractional offsets."""
+    from oracle.amoeba_ref import Oracle
+    w = np.concatenate([np.linspace(0.0, 1.0, 2001)[:-1], np.random.default_rng(1).uniform(0, 1, 500)])
+    assert np.abs(ref.bspline5(w) - Oracle.bspline_theta(w, 5)).max() < 1e-15
+
+
+def test_vdw_pair_terms_equal_reference(ref):
+    """pair_hal_v2 (include/seq/pair_hal.h) against the vdW oracle's pair function over every class pair of dhfr2 at
+    distances from contact to beyond the taper: energy and dE/dr, tapered region included."""
+    from oracle.vdw_ref import VdwOracle
+    s = _load("dhfr2.npz")
+    o = VdwOracle(s)
+    v = s.vdw
+    rng = np.random.default_rng(2)
+    m = 200000
+    a, b = rng.integers(0, v.radmin.shape[0], m), rng.integers(0, v.radmin.shape[0], m)
+    r = rng.uniform(1.2, v.cutoff, m)
+    r[:2000] = rng.uniform(v.taper, v.cutoff, 2000)
+    rv, eps = v.radmin[a, b], v.epsilon[a, b]
+    ok = rv > 0
+    e0, de0 = o.pair_terms(r[ok], rv[ok], eps[ok])
+    e1, de1 = ref.hal(r[ok], rv[ok], eps[ok], v.taper, v.cutoff, v.ghal, v.dhal)
+    assert np.abs(e1 - e0).max() <= 1e-12 * max(1.0, np.abs(e0).max())
+    assert np.abs(de1 - de0).max() <= 1e-12 * max(1.0, np.abs(de0).max())

@@ -77,6 +77,25 @@ def test_dhfr2_vs_oracle(precision):
     a.close()
 
 
+def test_dhfr2_vs_reference_arithmetic():
+    """The same comparison against the reference's OWN functions (include/seq/bond.h ... tortor.h compiled in place into
+    oracle/_ref, which travels to the GPU box): the CUDA kernel and dk_bond ... dk_tortor on the 48 013 interactions of dhfr2."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import Amoeba, calc
+    from oracle import ref_bridge
+    if not ref_bridge.available("valence"):
+        pytest.skip("oracle/_ref not built")
+    s = tg.load_system(os.path.join(GOLDEN, "dhfr2.npz"))
+    ref = ref_bridge.valence(s)
+    a = Amoeba(s, "mixed")
+    a.attach_valence(s.valence)
+    r = a.evalence(calc.v1)
+    assert np.abs(np.array(list(r.e)) - ref["energy"]).max() < 1e-5
+    assert np.abs(a.valence_gradient() - ref["grad"]).max() < 1e-7
+    assert np.abs(np.array(list(r.virial)).reshape(3, 3) - ref["virial"]).max() < 1e-5
+    a.close()
+
+
 def test_energy_includes_valence():
     """energy(vers) = electrostatics + vdW + valence once the terms are attached (src/energy.cpp:180-215, 319-448);
     esum, gradient and virial are the sums of the separately evaluated parts."""

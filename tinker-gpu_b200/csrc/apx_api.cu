@@ -199,6 +199,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    c->f_elec = (real)(sys->electric / sys->dielec);
    if (const char* e = getenv("APX_NO_NATIVE_FFT"))
       c->native_fft = atoi(e) ? 0 : 1;
+   if (const char* e = getenv("APX_ROWS_ONEPASS"))
+      c->rows_onepass = atoi(e);
    if (const char* e = getenv("APX_NO_RECORDS"))
       c->use_records = atoi(e) ? 0 : 1;
    if (const char* e = getenv("APX_UF_CTAS"))
@@ -379,6 +381,7 @@ void apx_destroy(apx_ctx* c)
    c->posd.release(), c->tpj.release(), c->mp0.release(), c->mp1.release(), c->mp2.release(), c->mpx_a.release(), c->mpx_b.release();
    c->blk_ctr.release(), c->blk_ext.release(), c->excl_s.release(), c->flags.release(), c->scal.release();
    c->rows.vstart.release(), c->rows.vcnt.release(), c->rows.vnbr.release(), c->rows.nbr.release();
+   c->rows.prev_o.release(), c->rows.capstart.release(), c->rows.vpad.release(), c->rows.oflow.release();
    c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();

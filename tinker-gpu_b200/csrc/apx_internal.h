@@ -102,6 +102,14 @@ struct RowList {
    DevBuf<real4> sctr, sext;  // bounding boxes of super-blocks (32 blocks)
    DevBuf<unsigned long long> total;   // [2]: directed pairs within cutoff / ucut at the last compaction
    long long nverlet = 0;
+   // one-pass rebuild (rows.cu): row lengths of the previous build in CALLER order give every row a padded slot, so the
+   // search runs once (fill + count) and a bandwidth-bound copy packs the rows; overflow falls back to an exact fill
+   DevBuf<int> prev_o;      // [n] row length at the last build, caller order
+   DevBuf<int> capstart;    // [n+1] offsets of the padded slots
+   DevBuf<int> vpad;        // padded rows
+   DevBuf<int> oflow;       // [1]
+   long long prev_total = 0;
+   int have_prev = 0;
 };
 
 struct PairExcl {           // exclusion pair in SORTED indices with (scale-1) factors
@@ -217,6 +225,8 @@ struct apx_ctx {
    DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
    DevBuf<real4> pk_p, pk_r, pk_z, pk_v, pk_f;   // packed (d,p) pairs, dp.cuh: direction, residual, M r, A p, real-space field
    DevBuf<real4> uf_rec;                 // [npad][3] interleaved neighbour records of the ufield rows (field.cu)
+   int rows_onepass = 1;                 // APX_ROWS_ONEPASS: 1 = one-pass list rebuild with padded rows (default), 2 = the same with zero slack
+                                         // (every grown row overflows: tests the fall-back), 0 = always count + fill
    int use_records = 1;                  // APX_NO_RECORDS=1: the separate-array kernel instead
    int uf_ctas = 8, uf_smem_kb = 0;      // residency of the ufield rows beside the PME chain (APX_UF_CTAS, APX_UF_SMEM)
    cudaStream_t stream2 = nullptr;       // real-space operator of an iteration runs here, beside the PME chain

@@ -565,6 +565,7 @@ void apx_vdw_destroy(apx_ctx* c)
    V.xs_ik.release(), V.xs_sc.release(), V.xs_s.release(), V.pred.release(), V.ired_s.release(), V.kred_s.release();
    V.ctr.release(), V.ext.release(), V.vbuf.release(), V.vcnt.release();
    V.rows.vstart.release(), V.rows.vcnt.release(), V.rows.vnbr.release(), V.rows.nbr.release(), V.rows.cnt.release();
+   V.rows.prev_o.release(), V.rows.capstart.release(), V.rows.vpad.release(), V.rows.oflow.release();
    V.rows.cntu.release(), V.rows.sctr.release(), V.rows.sext.release(), V.rows.total.release();
    V.on = 0;
 }

@@ -62,12 +62,15 @@ __device__ __forceinline__ bool boxes_within(const Box& b, real4 ci, real4 ei, r
 
 // RB_W warps per i-block; lane j of a warp keeps the running length of the row of atom 32*ib + j
 // (only the atoms of this warp's share, and only atoms inside the owned range [a0,a1))
-template <bool FILL>
+// MODE 0: count only (vcnt).  MODE 1: fill exact rows at vstart.  MODE 2: fill padded slots [vstart[s], vstart[s+1]) AND count:
+// a row that outgrows its slot raises *oflow and stops writing, the count stays exact.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, int a0, int a1, Box b, real range,
    const real4* __restrict__ posd, const real4* __restrict__ ctr, const real4* __restrict__ ext, const real4* __restrict__ sctr,
    const real4* __restrict__ sext, int* __restrict__ vcnt, const int* __restrict__ vstart, int* __restrict__ vnbr,
-   const int* __restrict__ perm, const int* __restrict__ exoff, const int* __restrict__ exlist, real exr2)
+   const int* __restrict__ perm, const int* __restrict__ exoff, const int* __restrict__ exlist, real exr2, int* __restrict__ oflow)
 {
+   constexpr bool FILL = MODE != 0;
    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
    const int ib = a0 / 32 + gw / RB_W, sub = gw % RB_W;
    const int lane = threadIdx.x & 31;
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, in
       return;
    int mycount = 0;
    const int mybase = (FILL && si < n) ? vstart[si] : 0;
+   const int mycap = (MODE == 2 && si < n) ? vstart[si + 1] - vstart[si] : 0;
    const unsigned lt = (1u << lane) - 1;
    for (int sb0 = 0; sb0 < nsb; sb0 += 32) {
       const int sb = sb0 + lane;
@@ -128,10 +132,20 @@ __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, in
                   }
                }
                unsigned m = __ballot_sync(FULL, ok);
-               if (FILL) {
+               if (MODE == 1) {
                   int off = __shfl_sync(FULL, mybase + mycount, q);
                   if (ok)
                      vnbr[off + __popc(m & lt)] = s;
+               }
+               if (MODE == 2) {
+                  const int off = __shfl_sync(FULL, mybase + mycount, q);
+                  const int room = __shfl_sync(FULL, mycap - mycount, q);
+                  if (__popc(m) <= room) {
+                     if (ok)
+                        vnbr[off + __popc(m & lt)] = s;
+                  } else if (lane == 0) {
+                     *oflow = 1;
+                  }
                }
                if (lane == q)
                   mycount += __popc(m);
@@ -139,8 +153,43 @@ __global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, in
          }
       }
    }
-   if (!FILL && lane >= q0 && lane < q1)
+   if (MODE != 1 && lane >= q0 && lane < q1)
       vcnt[si] = mycount;
+}
+
+// padded slot sizes from the previous build's row lengths (caller order): +12.5 % + 16 entries (slack 0: exactly the old length)
+__global__ void k_rows_caps(int n, const int* __restrict__ perm, const int* __restrict__ prev_o, int slack, int* __restrict__ cap)
+{
+   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s > n)
+      return;
+   int c = 0;
+   if (s < n) {
+      c = prev_o[perm[s]];
+      if (slack)
+         c += (c >> 3) + 16;
+   }
+   cap[s] = c;
+}
+
+__global__ void k_rows_save_counts(int n, const int* __restrict__ perm, const int* __restrict__ vcnt, int* __restrict__ prev_o)
+{
+   const int s = blockIdx.x * blockDim.x + threadIdx.x;
+   if (s < n)
+      prev_o[perm[s]] = vcnt[s];
+}
+
+// pack the padded rows: one warp per row, coalesced copy
+__global__ void __launch_bounds__(128) k_rows_pack(int n, const int* __restrict__ capstart, const int* __restrict__ vstart, const int* __restrict__ vpad,
+   int* __restrict__ vnbr)
+{
+   const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+   const int lane = threadIdx.x & 31;
+   if (s >= n)
+      return;
+   const int src = capstart[s], dst = vstart[s], len = vstart[s + 1] - dst;
+   for (int q = lane; q < len; q += 32)
+      vnbr[dst + q] = vpad[src + q];
 }
 
 // one warp per atom: two sweeps over its Verlet row (positions stay in L1 between them)
@@ -214,16 +263,38 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
    L.sext.ensure(nsb);
    k_super_boxes<<<(nsb * 32 + 127) / 128, 128, 0, c->stream>>>(nblk, nsb, bctr, bext, L.sctr, L.sext);
    CUDA_CHECK(cudaMemsetAsync(L.vcnt.p, 0, sizeof(int) * (n + 1), c->stream));
-   k_rows_build<false><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
-      L.vcnt, nullptr, nullptr, c->perm, exoff, exlist, exr2);
-   size_t need = 0;
-   cub::DeviceScan::ExclusiveSum(nullptr, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
-   if (need > c->cubtmp.cap)
-      c->cubtmp.ensure(need);
-   need = c->cubtmp.cap;
-   cub::DeviceScan::ExclusiveSum(c->cubtmp.p, need, L.vcnt.p, L.vstart.p, n + 1, c->stream);
-   int total = 0;
+   auto scan = [&](int* in, int* out) {
+      size_t need = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n + 1, c->stream);
+      if (need > c->cubtmp.cap)
+         c->cubtmp.ensure(need);
+      need = c->cubtmp.cap;
+      cub::DeviceScan::ExclusiveSum(c->cubtmp.p, need, in, out, n + 1, c->stream);
+   };
+   // ---- one search pass: padded slots sized from the previous build, fill + count, then a packing copy (APX_ROWS_ONEPASS)
+   const bool onepass = c->rows_onepass && L.have_prev && !c->dist.on && a0 == 0 && a1 == n;
+   bool filled = false;
+   if (onepass) {
+      const int slack = c->rows_onepass == 2 ? 0 : 1;
+      L.capstart.ensure(n + 1);
+      L.oflow.ensure(1);
+      L.vpad.ensure((size_t)(slack ? L.prev_total + L.prev_total / 8 + 16ll * n : L.prev_total) + 64);
+      k_rows_caps<<<(n + 256) / 256, 256, 0, c->stream>>>(n, c->perm, L.prev_o, slack, L.vcnt);      // vcnt as scratch for the slot sizes
+      scan(L.vcnt.p, L.capstart.p);
+      CUDA_CHECK(cudaMemsetAsync(L.vcnt.p, 0, sizeof(int) * (n + 1), c->stream));
+      CUDA_CHECK(cudaMemsetAsync(L.oflow.p, 0, sizeof(int), c->stream));
+      k_rows_build<2><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext, L.vcnt, L.capstart,
+         L.vpad, c->perm, exoff, exlist, exr2, L.oflow);
+      c->stats.kernel_launches += 2;
+   } else {
+      k_rows_build<0><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+         L.vcnt, nullptr, nullptr, c->perm, exoff, exlist, exr2, nullptr);
+   }
+   scan(L.vcnt.p, L.vstart.p);
+   int total = 0, oflow = 0;
    CUDA_CHECK(cudaMemcpyAsync(&total, L.vstart.p + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+   if (onepass)
+      CUDA_CHECK(cudaMemcpyAsync(&oflow, L.oflow.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
    CUDA_CHECK(cudaStreamSynchronize(c->stream));
    if (total < 0)
       APX_THROW("neighbor rows exceed 2^31 entries");
@@ -231,8 +302,21 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
    L.vnbr.ensure((size_t)total + 32);
    if (want_compact)
       L.nbr.ensure((size_t)total + 32);
-   k_rows_build<true><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
-      nullptr, L.vstart, L.vnbr, c->perm, exoff, exlist, exr2);
+   if (onepass && !oflow) {
+      k_rows_pack<<<(n * 32 + 127) / 128, 128, 0, c->stream>>>(n, L.capstart, L.vstart, L.vpad, L.vnbr);
+      c->stats.kernel_launches += 1;
+      filled = true;
+   }
+   if (!filled)      // two-pass path, or a row outgrew its slot: the counts are exact either way
+      k_rows_build<1><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+         nullptr, L.vstart, L.vnbr, c->perm, exoff, exlist, exr2, nullptr);
+   if (c->rows_onepass && !c->dist.on && a0 == 0 && a1 == n) {
+      L.prev_o.ensure(n);
+      k_rows_save_counts<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->perm, L.vcnt, L.prev_o);
+      L.prev_total = total;
+      L.have_prev = 1;
+      c->stats.kernel_launches += 1;
+   }
    c->stats.kernel_launches += 3;
 }
 
