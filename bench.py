@@ -301,7 +301,6 @@ def run_dynamics(args, rank, world, local_rank):
     # ---- e2e leg: the reference-facing plugin call energy(vers) with HOST buffers every step -- positions in from host memory,
     #      electrostatics + vdW + valence energy and gradient, gradient back to host (what an integrator on the host side of the
     #      C ABI pays per force evaluation)
-    a.attach_valence(system.valence)     # (already attached; keeps the call sequence of a host-driven run explicit)
     rng = np.random.default_rng(1234 + rank)
     drift = np.array([0.06, 0.04, 0.035])
     nframes = 2 + args.steps
