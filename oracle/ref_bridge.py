@@ -79,3 +79,120 @@ def hal(r, rv, eps, evcut, evoff, ghal, dhal):
     e, de = np.zeros(len(r)), np.zeros(len(r))
     lib.ref_hal(len(r), _dp(r), _dp(rv), _dp(eps), float(evcut), float(evoff), float(ghal), float(dhal), _dp(e), _dp(de))
     return e, de
+
+
+class RefPME:
+    """The reference's host PME operators (src/acc/pme.cpp compiled in place into oracle/_ref/libref_pme.so) set up on the
+    coordinates, box and grid of an Oracle; the FFT between the operators is numpy's.  Grids are complex [n3][n2][n1]."""
+
+    def __init__(self, oracle):
+        self.lib = lib = C.CDLL(os.path.join(HERE, "_ref", "libref_pme.so"))
+        s = oracle.s
+        self.n = oracle.n
+        self.nfft = tuple(int(v) for v in s.nfft)
+        p = oracle.pme_setup()
+        b1, b2, b3 = (np.ascontiguousarray(b, np.float64) for b in p["bsmod"])
+        xyz = np.ascontiguousarray(oracle.xyz, np.float64)
+        lv = np.ascontiguousarray(oracle.lvec, np.float64).ravel()
+        rc = np.ascontiguousarray(oracle.recip, np.float64).ravel()
+        nf = (C.c_int * 3)(*self.nfft)
+        lib.ref_pme_open.argtypes = [C.c_int, _DP, _DP, _DP, C.POINTER(C.c_int), C.c_int, C.c_double, _DP, _DP, _DP, C.c_double, C.c_double]
+        lib.ref_pme_open(self.n, _dp(xyz), _dp(lv), _dp(rc), nf, int(s.bsorder), float(s.aewald), _dp(b1), _dp(b2), _dp(b3),
+                         float(s.electric), float(s.dielec))
+        for name, k in (("ref_pme_qgrid_get", 1), ("ref_pme_qgrid_set", 1), ("ref_pme_rpole_to_cmp", 2), ("ref_pme_cmp_to_fmp", 2),
+                        ("ref_pme_cuind_to_fuind", 4), ("ref_pme_fphi_to_cphi", 2), ("ref_pme_grid_mpole", 1), ("ref_pme_grid_uind", 2),
+                        ("ref_pme_conv", 2), ("ref_pme_fphi_mpole", 1), ("ref_pme_fphi_uind", 3), ("ref_pme_fphi_uind2", 2)):
+            getattr(lib, name).argtypes = [_DP] * k
+            getattr(lib, name).restype = None
+
+    def _grid_out(self):
+        n1, n2, n3 = self.nfft
+        g = np.zeros((n3, n2, n1, 2))
+        self.lib.ref_pme_qgrid_get(_dp(g))
+        return g[..., 0] + 1j * g[..., 1]
+
+    def _grid_in(self, q):
+        g = np.ascontiguousarray(np.stack([q.real, q.imag], -1), np.float64)
+        self.lib.ref_pme_qgrid_set(_dp(g))
+
+    def _call(self, name, ins, out_shapes):
+        ins = [np.ascontiguousarray(a, np.float64) for a in ins]
+        outs = [np.zeros(sh) for sh in out_shapes]
+        getattr(self.lib, name)(*[_dp(a) for a in ins + outs])
+        return outs[0] if len(outs) == 1 else outs
+
+    def rpole_to_cmp(self, rp):
+        return self._call("ref_pme_rpole_to_cmp", [rp], [(self.n, 10)])
+
+    def cmp_to_fmp(self, cmp_):
+        return self._call("ref_pme_cmp_to_fmp", [cmp_], [(self.n, 10)])
+
+    def cuind_to_fuind(self, ud, up):
+        return self._call("ref_pme_cuind_to_fuind", [ud, up], [(self.n, 3), (self.n, 3)])
+
+    def fphi_to_cphi(self, fphi):
+        return self._call("ref_pme_fphi_to_cphi", [fphi], [(self.n, 10)])
+
+    def grid_mpole(self, fmp):
+        a = np.ascontiguousarray(fmp, np.float64)
+        self.lib.ref_pme_grid_mpole(_dp(a))
+        return self._grid_out()
+
+    def grid_uind(self, fud, fup):
+        a, b = np.ascontiguousarray(fud, np.float64), np.ascontiguousarray(fup, np.float64)
+        self.lib.ref_pme_grid_uind(_dp(a), _dp(b))
+        return self._grid_out()
+
+    def convolve(self, qgrid, want_ev=False):
+        """fftfront (numpy) + pmeConv (reference) + fftback (numpy): (grid, e, virial 3x3)."""
+        self._grid_in(np.fft.fftn(qgrid))
+        e, v6 = np.zeros(1), np.zeros(6)
+        self.lib.ref_pme_conv(_dp(e) if want_ev else None, _dp(v6) if want_ev else None)
+        out = np.fft.ifftn(self._grid_out()) * qgrid.size
+        self._grid_in(out)
+        v = np.array([[v6[0], v6[1], v6[2]], [v6[1], v6[3], v6[4]], [v6[2], v6[4], v6[5]]])
+        return out, (float(e[0]) if want_ev else None), (v if want_ev else None)
+
+    def fphi_mpole(self, grid=None):
+        if grid is not None:
+            self._grid_in(grid)
+        return self._call("ref_pme_fphi_mpole", [], [(self.n, 20)])
+
+    def fphi_uind(self, grid=None):
+        if grid is not None:
+            self._grid_in(grid)
+        return self._call("ref_pme_fphi_uind", [], [(self.n, 10), (self.n, 10), (self.n, 20)])
+
+    def fphi_uind2(self, grid=None):
+        if grid is not None:
+            self._grid_in(grid)
+        return self._call("ref_pme_fphi_uind2", [], [(self.n, 10), (self.n, 10)])
+
+
+def hal_pairs(vdw_oracle, pairs=None):
+    """ev, gradient on the reduced sites and virial of the 14-7 term from the reference's pair_hal_v2 over the vdW oracle's own
+    pair list (pairs = (i, k) to reuse a list found earlier)."""
+    lib = C.CDLL(os.path.join(HERE, "_ref", "libref_realspace.so"))
+    lib.ref_hal_pairs.argtypes = [C.c_int, C.c_longlong, _IP, _IP, _DP, _DP, _DP, C.c_double, C.c_double, C.c_double, C.c_double, _DP, _DP, _DP]
+    o, v = vdw_oracle, vdw_oracle.v
+    xr = o.reduced()
+    i, k = o.pairs(xr) if pairs is None else pairs
+    scale = np.ones(i.shape[0])
+    if v.vexclude.shape[0]:
+        code = i.astype(np.int64) * o.n + k
+        ex = v.vexclude[:, 0].astype(np.int64) * o.n + v.vexclude[:, 1]
+        order = np.argsort(ex)
+        pos = np.minimum(np.searchsorted(ex[order], code), ex.shape[0] - 1)
+        hit = ex[order][pos] == code
+        scale[hit] = v.vexclude_scale[order][pos[hit]]
+    keep = scale != 0
+    i, k, scale = i[keep], k[keep], scale[keep]
+    d = np.ascontiguousarray(o.image(xr[i] - xr[k]), np.float64)
+    rv = np.ascontiguousarray(v.radmin[v.jvdw[i], v.jvdw[k]], np.float64)
+    eps = np.ascontiguousarray(v.epsilon[v.jvdw[i], v.jvdw[k]] * scale, np.float64)
+    i32, k32 = np.ascontiguousarray(i, np.int32), np.ascontiguousarray(k, np.int32)
+    ev = C.c_double()
+    g, v9 = np.zeros((o.n, 3)), np.zeros(9)
+    lib.ref_hal_pairs(o.n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(d), _dp(rv), _dp(eps), float(v.taper), float(v.cutoff),
+                      float(v.ghal), float(v.dhal), C.byref(ev), _dp(g), _dp(v9))
+    return dict(ev=ev.value, gred=g, virial=v9.reshape(3, 3), npairs=len(i32))

@@ -1,0 +1,120 @@
+"""The oracle's solver and energy assembly driven by the REFERENCE'S OWN operators (oracle/_ref) -- TEST INFRASTRUCTURE ONLY.
+
+RefOracle keeps the control flow of oracle/amoeba_ref.py (the PCG loop of induceMutualPcg1, the sparse preconditioner, the
+per-atom reciprocal energy / force assembly, numpy's FFT) and replaces every O(pairs) and O(grid) operator by the reference's
+compiled code: pair_dfield / pair_ufield / pair_mpole / pair_polar (include/seq/*.h) for the real-space sweeps and
+gridMpole / gridUind / pmeConv / fphiMpole / fphiUind2 ... (src/acc/pme.cpp) for the reciprocal ones.  Two uses: it pins the
+oracle's converged dipoles and energies at dhfr2 size to the reference's arithmetic (tests/test_ref_arith.py), and it is the
+CPU baseline bench.py times ("reference arithmetic, one core") -- about 20x faster than the vectorised-numpy operators.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import ref_bridge
+from .amoeba_ref import SQRTPI, Oracle
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int)
+
+
+class RefOracle(Oracle):
+    def __init__(self, system, chunk=20000):
+        super().__init__(system, chunk)
+        self._rs = C.CDLL(os.path.join(ref_bridge.HERE, "_ref", "libref_realspace.so"))
+        self._rs.ref_field_real.argtypes = [C.c_int, C.c_int, C.c_longlong, _IP, _IP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, C.c_double, C.c_int,
+                                            _DP, _DP]
+        self._refpme = None
+        self._plist = None
+
+    def set_xyz(self, xyz):
+        super().set_xyz(xyz)
+        self._refpme = None
+        self._plist = None
+
+    # ---- shared inputs of the pair sweeps
+    def _pairs_c(self):
+        if self._plist is None:
+            i, k, R, r = self.pairs(self.s.ewald_cutoff)
+            self._plist = (np.ascontiguousarray(i, np.int32), np.ascontiguousarray(k, np.int32), np.ascontiguousarray(R, np.float64),
+                           np.ascontiguousarray(self._scales(i, k), np.float64),
+                           np.ascontiguousarray(self._pair_params(i, k)[2], np.float64), np.ascontiguousarray(self.s.pdamp, np.float64))
+        return self._plist
+
+    def _rpme(self):
+        if self._refpme is None:
+            self._refpme = ref_bridge.RefPME(self)
+        return self._refpme
+
+    def _field_real(self, mode, ud=None, up=None):
+        i, k, R, sc, pga, pd = self._pairs_c()
+        rp = np.ascontiguousarray(self._ensure_rpole(), np.float64)
+        fd, fp = np.zeros((self.n, 3)), np.zeros((self.n, 3))
+        dp = ref_bridge._dp
+        u1 = None if ud is None else np.ascontiguousarray(ud, np.float64)
+        u2 = None if up is None else np.ascontiguousarray(up, np.float64)
+        self._rs.ref_field_real(mode, self.n, len(i), i.ctypes.data_as(_IP), k.ctypes.data_as(_IP), dp(R), dp(sc), dp(rp), dp(pd), dp(pga),
+                                None if u1 is None else dp(u1), None if u2 is None else dp(u2), float(self.s.aewald), int(bool(self.s.use_ewald)),
+                                dp(fd), dp(fp))
+        return fd, fp
+
+    # ---- operators
+    def grid_mpole(self, fmp):
+        return self._rpme().grid_mpole(fmp)
+
+    def grid_uind(self, fud, fup):
+        return self._rpme().grid_uind(fud, fup)
+
+    def pme_convolve(self, qgrid, want_ev=False):
+        return self._rpme().convolve(qgrid, want_ev)
+
+    def fphi_gather(self, grid, nder):
+        P = self._rpme()
+        if nder == 20:
+            return P.fphi_mpole(np.asarray(grid, complex))
+        return super().fphi_gather(grid, nder)
+
+    def cmp_to_fmp(self, cmp_):
+        return self._rpme().cmp_to_fmp(cmp_)
+
+    def fphi_to_cphi(self, fphi):
+        return self._rpme().fphi_to_cphi(fphi)
+
+    def dfield(self, real_only=False):
+        s = self.s
+        rp = self._ensure_rpole()
+        fd, fp = self._field_real(0)
+        if s.use_ewald and not real_only:
+            cmp_ = self.rpole_to_cmp(rp)
+            fmp = self.cmp_to_fmp(cmp_)
+            grid, e, v = self.pme_convolve(self.grid_mpole(fmp), want_ev=True)
+            self._recip_m = dict(e=e, v=v, cmp=cmp_, fmp=fmp)
+            fphi = self._rpme().fphi_mpole()            # the convolved grid is already in place
+            cphi = self.fphi_to_cphi(fphi)
+            self._recip_m.update(fphi=fphi, cphi=cphi)
+            rec = -cphi[:, 1:4] + (4.0 / 3.0 * s.aewald ** 3 / SQRTPI) * rp[:, 1:4]
+            fd += rec
+            fp += rec
+        return fd, fp
+
+    def ufield(self, ud, up, real_only=False):
+        s = self.s
+        fd, fp = self._field_real(1, ud, up)
+        if s.use_ewald and not real_only:
+            P = self._rpme()
+            a = self.pme_setup()["a"]
+            fud, fup = P.cuind_to_fuind(ud, up)
+            P.convolve(P.grid_uind(fud, fup))
+            f1, f2 = P.fphi_uind2()
+            term = 4.0 / 3.0 * s.aewald ** 3 / SQRTPI
+            fd += term * ud - f1[:, 1:4] @ a.T
+            fp += term * up - f2[:, 1:4] @ a.T
+        return fd, fp
+
+    def _real_space(self, vers, do_m, do_p):
+        r = ref_bridge.realspace(self, self.uind if do_p else None, self.uinp if do_p else None)
+        i, k, R, sc, pga, pd = self._pairs_c()
+        z3 = np.zeros((3, 3))
+        return dict(em=r["em"] if do_m else 0.0, ep=r["ep"] if do_p else 0.0, nem=int((sc[:, 0] != 0).sum()), nep=int((sc[:, 2] != 0).sum()),
+                    gm=r["gm"], gp=r["gp"], tm=r["tm"], tp=r["tp"], vm=z3, vp=z3.copy())

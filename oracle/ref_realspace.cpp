@@ -145,3 +145,79 @@ extern "C" int ref_hal(long long m, const double* r, const double* rv, const dou
    }
    return 0;
 }
+
+// Real-space fields alone (the two pair sweeps of the induced-dipole solver): mode 0 = permanent field of the multipoles with
+// the d / p scalings (dfieldEwaldReal), mode 1 = mutual field of the dipoles ud / up with the u scaling (ufieldEwaldReal).
+// Same two-pass treatment of scaled pairs as above.  fd, fp are zeroed here.
+extern "C" int ref_field_real(int mode, int n, long long npair, const int* pi, const int* pk, const double* R, const double* scale,
+   const double* rpole, const double* pdamp, const double* pga, const double* ud, const double* up, double aewald, int ewald, double* fd, double* fp)
+{
+   std::memset(fd, 0, sizeof(double) * 3 * (size_t)n);
+   std::memset(fp, 0, sizeof(double) * 3 * (size_t)n);
+   for (long long p = 0; p < npair; ++p) {
+      const int i = pi[p], k = pk[p];
+      const real xr = R[3 * p], yr = R[3 * p + 1], zr = R[3 * p + 2];
+      const real r2 = xr * xr + yr * yr + zr * zr;
+      const double* s = scale + 4 * p;
+      const real pdi = pdamp[i], pdk = pdamp[k], pg = pga[p];
+      for (int pass = 0; pass < 2; ++pass) {
+         real ds, ps, us, aw;
+         bool ew;
+         if (ewald && pass == 0)
+            ds = ps = us = 1, aw = aewald, ew = true;
+         else if (ewald)
+            ds = s[1] - 1, ps = s[2] - 1, us = s[3] - 1, aw = 0, ew = false;
+         else if (pass == 0)
+            ds = s[1], ps = s[2], us = s[3], aw = 0, ew = false;
+         else
+            break;
+         if (pass == 1 && (mode == 0 ? (ds == 0 && ps == 0) : us == 0))
+            continue;
+         real3 fid = make_real3(0, 0, 0), fip = make_real3(0, 0, 0), fkd = make_real3(0, 0, 0), fkp = make_real3(0, 0, 0);
+         if (mode == 0) {
+            const Atom A = load(rpole, i), B = load(rpole, k);
+            if (ew)
+               pair_dfield<EWALD>(r2, xr, yr, zr, ds, ps, MP(A), pdi, pg, MP(B), pdk, pg, aw, fid, fip, fkd, fkp);
+            else
+               pair_dfield<NON_EWALD>(r2, xr, yr, zr, ds, ps, MP(A), pdi, pg, MP(B), pdk, pg, aw, fid, fip, fkd, fkp);
+         } else {
+            const double *a = ud + 3 * i, *b = up + 3 * i, *c = ud + 3 * k, *d = up + 3 * k;
+            if (ew)
+               pair_ufield<EWALD>(r2, xr, yr, zr, us, (real)a[0], (real)a[1], (real)a[2], (real)b[0], (real)b[1], (real)b[2], pdi, pg, (real)c[0], (real)c[1],
+                  (real)c[2], (real)d[0], (real)d[1], (real)d[2], pdk, pg, aw, fid, fip, fkd, fkp);
+            else
+               pair_ufield<NON_EWALD>(r2, xr, yr, zr, us, (real)a[0], (real)a[1], (real)a[2], (real)b[0], (real)b[1], (real)b[2], pdi, pg, (real)c[0],
+                  (real)c[1], (real)c[2], (real)d[0], (real)d[1], (real)d[2], pdk, pg, aw, fid, fip, fkd, fkp);
+         }
+         fd[3 * i] += fid.x, fd[3 * i + 1] += fid.y, fd[3 * i + 2] += fid.z;
+         fp[3 * i] += fip.x, fp[3 * i + 1] += fip.y, fp[3 * i + 2] += fip.z;
+         fd[3 * k] += fkd.x, fd[3 * k + 1] += fkd.y, fd[3 * k + 2] += fkd.z;
+         fp[3 * k] += fkp.x, fp[3 * k + 1] += fkp.y, fp[3 * k + 2] += fkp.z;
+      }
+   }
+   return 0;
+}
+
+// Buffered 14-7 energy, force on the reduced sites and virial over a given pair list (pair_hal_v2, as ehal_acc does pair by
+// pair): d[p] = x_i - x_k after the minimum-image shift, rv / eps the pair parameters (eps already times the pair's scale).
+extern "C" int ref_hal_pairs(int n, long long npair, const int* pi, const int* pk, const double* d, const double* rv, const double* eps, double evcut,
+   double evoff, double ghal, double dhal, double* ev, double* gred, double* vir9)
+{
+   *ev = 0;
+   std::memset(gred, 0, sizeof(double) * 3 * (size_t)n);
+   double v[9] = {0};
+   for (long long p = 0; p < npair; ++p) {
+      const double x = d[3 * p], y = d[3 * p + 1], z = d[3 * p + 2];
+      const real r = std::sqrt(x * x + y * y + z * z);
+      real e, de;
+      pair_hal_v2<true, 1>(r, 1, (real)rv[p], (real)eps[p], (real)evcut, (real)evoff, 1, (real)ghal, (real)dhal, 5, (real)0.7, e, de);
+      *ev += e;
+      const double f = de / r, fx = f * x, fy = f * y, fz = f * z;
+      const int i = pi[p], k = pk[p];
+      gred[3 * i] += fx, gred[3 * i + 1] += fy, gred[3 * i + 2] += fz;
+      gred[3 * k] -= fx, gred[3 * k + 1] -= fy, gred[3 * k + 2] -= fz;
+      v[0] += x * fx, v[1] += x * fy, v[2] += x * fz, v[3] += y * fx, v[4] += y * fy, v[5] += y * fz, v[6] += z * fx, v[7] += z * fy, v[8] += z * fz;
+   }
+   std::memcpy(vir9, v, sizeof(v));
+   return 0;
+}
