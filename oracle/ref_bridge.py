@@ -196,3 +196,32 @@ def hal_pairs(vdw_oracle, pairs=None):
     lib.ref_hal_pairs(o.n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(d), _dp(rv), _dp(eps), float(v.taper), float(v.cutoff),
                       float(v.ghal), float(v.dhal), C.byref(ev), _dp(g), _dp(v9))
     return dict(ev=ev.value, gred=g, virial=v9.reshape(3, 3), npairs=len(i32))
+
+
+def _frames_lib():
+    lib = C.CDLL(os.path.join(HERE, "_ref", "libref_pme.so"))
+    lib.ref_frames_rotpole.argtypes = [C.c_int, _DP, _IP, _DP, _DP, _DP]
+    lib.ref_frames_torque.argtypes = [C.c_int, _DP, _IP, _DP, _DP, _DP]
+    return lib
+
+
+def rotpole(xyz, zaxis, pole):
+    """(pole after chkpole, rpole) from the reference's chkpole_acc + rotpole_acc (src/acc/amoeba/rotpole.cpp)."""
+    n = len(xyz)
+    x = np.ascontiguousarray(xyz, np.float64)
+    z = np.ascontiguousarray(zaxis, np.int32)
+    p = np.ascontiguousarray(pole, np.float64)
+    pc, rp = np.zeros((n, 10)), np.zeros((n, 10))
+    _frames_lib().ref_frames_rotpole(n, _dp(x), z.ctypes.data_as(_IP), _dp(p), _dp(pc), _dp(rp))
+    return pc, rp
+
+
+def torque(xyz, zaxis, trq):
+    """(gradient on the frame atoms, torque virial 3x3) from the reference's torque_acc (src/acc/amoeba/torque.cpp)."""
+    n = len(xyz)
+    x = np.ascontiguousarray(xyz, np.float64)
+    z = np.ascontiguousarray(zaxis, np.int32)
+    t = np.ascontiguousarray(trq, np.float64)
+    g, v6 = np.zeros((n, 3)), np.zeros(6)
+    _frames_lib().ref_frames_torque(n, _dp(x), z.ctypes.data_as(_IP), _dp(t), _dp(g), _dp(v6))
+    return g, np.array([[v6[0], v6[1], v6[2]], [v6[1], v6[3], v6[4]], [v6[2], v6[4], v6[5]]])

@@ -3,7 +3,8 @@
 RefOracle keeps the control flow of oracle/amoeba_ref.py (the PCG loop of induceMutualPcg1, the sparse preconditioner, the
 per-atom reciprocal energy / force assembly, numpy's FFT) and replaces every O(pairs) and O(grid) operator by the reference's
 compiled code: pair_dfield / pair_ufield / pair_mpole / pair_polar (include/seq/*.h) for the real-space sweeps and
-gridMpole / gridUind / pmeConv / fphiMpole / fphiUind2 ... (src/acc/pme.cpp) for the reciprocal ones.  Two uses: it pins the
+gridMpole / gridUind / pmeConv / fphiMpole / fphiUind2 ... (src/acc/pme.cpp) for the reciprocal ones, chkpole / rotpole / torque
+(src/acc/amoeba/rotpole.cpp, torque.cpp) for the local frames.  Two uses: it pins the
 oracle's converged dipoles and energies at dhfr2 size to the reference's arithmetic (tests/test_ref_arith.py), and it is the
 CPU baseline bench.py times ("reference arithmetic, one core") -- about 20x faster than the vectorised-numpy operators.
 """
@@ -58,6 +59,19 @@ class RefOracle(Oracle):
                                 None if u1 is None else dp(u1), None if u2 is None else dp(u2), float(self.s.aewald), int(bool(self.s.use_ewald)),
                                 dp(fd), dp(fp))
         return fd, fp
+
+    # ---- local frames (src/acc/amoeba/rotpole.cpp, torque.cpp)
+    def chkpole(self):
+        self.pole, _ = ref_bridge.rotpole(self.xyz, self.zaxis, self.pole)
+
+    def rotpole(self):
+        self.pole, self.rpole = ref_bridge.rotpole(self.xyz, self.zaxis, self.pole)
+        return self.rpole
+
+    def torque(self, trq, grad, do_v=False):
+        g, v = ref_bridge.torque(self.xyz, self.zaxis, trq)
+        grad += g
+        return v
 
     # ---- operators
     def grid_mpole(self, fmp):

@@ -16,6 +16,7 @@
 #include "ff/box.h"
 #include "ff/elec.h"
 #include "ff/energybuffer.h"
+#include "ff/hippo/erepel.h"
 #include "ff/modamoeba.h"
 #include "ff/pme.h"
 #include "tool/accasync.h"
@@ -50,6 +51,10 @@ void fphiMpole_acc(PMEUnit, real (*)[20]);
 void fphiUind_acc(PMEUnit, real (*)[10], real (*)[10], real (*)[20]);
 void fphiUind2_acc(PMEUnit, real (*)[10], real (*)[10]);
 void rpoleToCmp_acc();
+// ---- src/acc/amoeba/rotpole.cpp, torque.cpp (compiled unmodified into this library as well)
+void chkpole_acc();
+void rotpole_acc();
+void torque_acc(int vers, grad_prec* gx, grad_prec* gy, grad_prec* gz);
 }
 
 using namespace tinker;
@@ -128,4 +133,50 @@ void ref_pme_fphi_uind(double* f1, double* f2, double* fdp)
    fphiUind_acc(g_unit, reinterpret_cast<real(*)[10]>(f1), reinterpret_cast<real(*)[10]>(f2), reinterpret_cast<real(*)[20]>(fdp));
 }
 void ref_pme_fphi_uind2(double* f1, double* f2) { fphiUind2_acc(g_unit, reinterpret_cast<real(*)[10]>(f1), reinterpret_cast<real(*)[10]>(f2)); }
+}
+
+// ---- local frames: chkpole + rotpole (src/acc/amoeba/rotpole.cpp over include/seq/rotpole.h) and torque -> force on the frame
+//      atoms with the torque virial (src/acc/amoeba/torque.cpp:20-395).  zaxis[i] = {z, x, y (signed, from ONE), polaxe}.
+extern "C" {
+static void frames_bind(int natoms, const double* xyz, const int* zax, std::vector<real>& px, std::vector<real>& py, std::vector<real>& pz)
+{
+   n = natoms;
+   px.resize(n), py.resize(n), pz.resize(n);
+   for (int i = 0; i < n; ++i)
+      px[i] = xyz[3 * i], py[i] = xyz[3 * i + 1], pz[i] = xyz[3 * i + 2];
+   x = px.data(), y = py.data(), z = pz.data();
+   zaxis = reinterpret_cast<LocalFrame*>(const_cast<int*>(zax));
+}
+
+int ref_frames_rotpole(int natoms, const double* xyz, const int* zax, const double* pole_in, double* pole_chk, double* rpole_out)
+{
+   std::vector<real> px, py, pz, p(pole_in, pole_in + 10 * (size_t)natoms), rp(10 * (size_t)natoms, 0);
+   frames_bind(natoms, xyz, zax, px, py, pz);
+   pole = reinterpret_cast<real(*)[MPL_TOTAL]>(p.data());
+   rpole = reinterpret_cast<real(*)[MPL_TOTAL]>(rp.data());
+   chkpole_acc();
+   rotpole_acc();
+   std::memcpy(pole_chk, p.data(), sizeof(double) * p.size());
+   std::memcpy(rpole_out, rp.data(), sizeof(double) * rp.size());
+   pole = nullptr, rpole = nullptr;
+   return 0;
+}
+
+int ref_frames_torque(int natoms, const double* xyz, const int* zax, const double* trq, double* grad, double* vir6)
+{
+   std::vector<real> px, py, pz, tx(natoms), ty(natoms), tz(natoms), gx(natoms, 0), gy(natoms, 0), gz(natoms, 0);
+   frames_bind(natoms, xyz, zax, px, py, pz);
+   for (int i = 0; i < natoms; ++i)
+      tx[i] = trq[3 * i], ty[i] = trq[3 * i + 1], tz[i] = trq[3 * i + 2];
+   trqx = tx.data(), trqy = ty.data(), trqz = tz.data();
+   v_prec vb[1][8] = {{0}};
+   vir_trq = vb;
+   torque_acc(calc::grad | calc::virial, gx.data(), gy.data(), gz.data());
+   for (int i = 0; i < natoms; ++i)
+      grad[3 * i] = gx[i], grad[3 * i + 1] = gy[i], grad[3 * i + 2] = gz[i];
+   for (int q = 0; q < 6; ++q)
+      vir6[q] = vb[0][q];
+   trqx = trqy = trqz = nullptr, vir_trq = nullptr;
+   return 0;
+}
 }

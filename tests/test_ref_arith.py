@@ -213,3 +213,23 @@ def test_dhfr2_energy_and_dipoles_by_reference_operators(ref):
     assert np.sqrt(((r.uind - z["uind"]) ** 2).mean()) * 4.803206802 <= 1e-12          # Debye
     assert np.sqrt(((r.uinp - z["uinp"]) ** 2).mean()) * 4.803206802 <= 1e-12
     assert np.abs(e["grad"] - z["grad"]).max() <= 1e-10
+
+
+@pytest.mark.parametrize("blob", ["lf_local_frame_2.npz", "lf_local_frame3_2.npz", "lf_triclinic.npz", "dhfr2.npz"])
+def test_local_frames_equal_reference(ref, blob):
+    """chkpole + rotpole and torque -> force / torque virial: the reference's host translation units
+    src/acc/amoeba/rotpole.cpp and torque.cpp (compiled unmodified) against the oracle, on decks that use all five frame types
+    (None, Z-Only, Z-then-X, Bisector, Z-Bisect, 3-Fold) and on dhfr2."""
+    from oracle.amoeba_ref import Oracle
+    s = _load(blob)
+    o = Oracle(s)
+    pc, rp = ref.rotpole(s.xyz, s.zaxis, s.pole)
+    o.chkpole()
+    assert np.array_equal(pc, o.pole)
+    assert np.abs(rp - o.rotpole()).max() <= 1e-14
+    trq = np.random.default_rng(3).normal(size=(s.n, 3))
+    g1, v1 = ref.torque(s.xyz, s.zaxis, trq)
+    g0 = np.zeros((s.n, 3))
+    v0 = o.torque(trq, g0, True)
+    assert np.abs(g1 - g0).max() <= 1e-11 * max(1.0, np.abs(g0).max())
+    assert np.abs(v1 - v0).max() <= 1e-11 * max(1.0, np.abs(v0).max())
