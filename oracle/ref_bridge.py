@@ -52,12 +52,20 @@ def realspace(oracle, ud=None, up=None):
     out = {nm: np.zeros((n, 3)) for nm in ("gm", "tm", "gp", "tp", "fd", "fp", "ufd", "ufp")}
     u1 = None if ud is None else np.ascontiguousarray(ud, np.float64)
     u2 = None if up is None else np.ascontiguousarray(up, np.float64)
+    vm6, vp6 = np.zeros(6), np.zeros(6)
+    lib.ref_realspace_virial.argtypes = [_DP, _DP]
+    lib.ref_realspace_virial.restype = None
+    lib.ref_realspace_virial(_dp(vm6), _dp(vp6))
     rc = lib.ref_realspace_eval(n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(R), _dp(sc), _dp(rp), _dp(pd), _dp(pga),
                                 None if u1 is None else _dp(u1), None if u2 is None else _dp(u2), float(oracle.f), float(s.aewald),
                                 int(bool(s.use_ewald)), C.byref(em), C.byref(ep), *[_dp(out[nm]) for nm in ("gm", "tm", "gp", "tp", "fd", "fp", "ufd", "ufp")])
+    lib.ref_realspace_virial(None, None)
     if rc != 0:
         raise RuntimeError(f"ref_realspace_eval failed ({rc})")
-    out.update(em=em.value, ep=ep.value, npair=len(i32))
+
+    def sym(v):
+        return np.array([[v[0], v[1], v[2]], [v[1], v[3], v[4]], [v[2], v[4], v[5]]])
+    out.update(em=em.value, ep=ep.value, npair=len(i32), vm=sym(vm6), vp=sym(vp6))
     return out
 
 
@@ -225,3 +233,39 @@ def torque(xyz, zaxis, trq):
     g, v6 = np.zeros((n, 3)), np.zeros(6)
     _frames_lib().ref_frames_torque(n, _dp(x), z.ctypes.data_as(_IP), _dp(t), _dp(g), _dp(v6))
     return g, np.array([[v6[0], v6[1], v6[2]], [v6[1], v6[3], v6[4]], [v6[2], v6[4], v6[5]]])
+
+
+_FFT_CB = C.CFUNCTYPE(None, C.c_int)
+
+
+def _recip_call(P, name, ins):
+    """Run one of the reference's reciprocal assembly routines; its fftfront / fftback come back here as a callback that
+    transforms the grid held by the library in place with numpy (unnormalised both ways, as FFTW / cuFFT are)."""
+    lib = P.lib
+
+    def fft(forward):
+        g = P._grid_out()
+        P._grid_in(np.fft.fftn(g) if forward else np.fft.ifftn(g) * g.size)
+    cb = _FFT_CB(fft)
+    fn = getattr(lib, name)
+    fn.argtypes = [_FFT_CB] + [_DP] * (len(ins) + 4)
+    fn.restype = C.c_int
+    n = P.n
+    e, g, t, v6 = np.zeros(1), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros(6)
+    arrs = [np.ascontiguousarray(a, np.float64) for a in ins]
+    rc = fn(cb, *[_dp(a) for a in arrs], _dp(e), _dp(g), _dp(t), _dp(v6))
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc})")
+    v = np.array([[v6[0], v6[1], v6[2]], [v6[1], v6[3], v6[4]], [v6[2], v6[4], v6[5]]])
+    return dict(e=float(e[0]), g=g, t=t, v=v)
+
+
+def recip_mpole(P, rpole):
+    """empoleChgpenEwaldRecip_acc(calc::v1, 0) (src/acc/hippo/empole.cpp:260-388): reciprocal multipole energy, gradient,
+    torque, virial.  P: a RefPME set up on the system."""
+    return _recip_call(P, "ref_recip_mpole", [rpole])
+
+
+def recip_polar(P, uind, uinp):
+    """epolarEwaldRecipSelf_acc(calc::v1, uind, uinp) (src/acc/amoeba/epolarewald.cpp:358-667); call recip_mpole first."""
+    return _recip_call(P, "ref_recip_polar", [uind, uinp])

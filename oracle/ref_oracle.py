@@ -1,8 +1,9 @@
 """The oracle's solver and energy assembly driven by the REFERENCE'S OWN operators (oracle/_ref) -- TEST INFRASTRUCTURE ONLY.
 
-RefOracle keeps the control flow of oracle/amoeba_ref.py (the PCG loop of induceMutualPcg1, the sparse preconditioner, the
-per-atom reciprocal energy / force assembly, numpy's FFT) and replaces every O(pairs) and O(grid) operator by the reference's
-compiled code: pair_dfield / pair_ufield / pair_mpole / pair_polar (include/seq/*.h) for the real-space sweeps and
+RefOracle keeps the control flow of oracle/amoeba_ref.py (the PCG loop of induceMutualPcg1, the sparse preconditioner,
+numpy's FFT) and replaces every O(pairs), O(grid) and per-atom assembly operator by the reference's compiled code:
+empoleChgpenEwaldRecip_acc / epolarEwaldRecipSelf_acc (src/acc/hippo/empole.cpp, src/acc/amoeba/epolarewald.cpp) for the
+reciprocal energy / gradient / torque / virial, pair_dfield / pair_ufield / pair_mpole / pair_polar (include/seq/*.h) for the real-space sweeps and
 gridMpole / gridUind / pmeConv / fphiMpole / fphiUind2 ... (src/acc/pme.cpp) for the reciprocal ones, chkpole / rotpole / torque
 (src/acc/amoeba/rotpole.cpp, torque.cpp) for the local frames.  Two uses: it pins the
 oracle's converged dipoles and energies at dhfr2 size to the reference's arithmetic (tests/test_ref_arith.py), and it is the
@@ -126,9 +127,16 @@ class RefOracle(Oracle):
             fp += term * up - f2[:, 1:4] @ a.T
         return fd, fp
 
+    # ---- per-atom reciprocal energy / gradient / torque / virial assembly (src/acc/hippo/empole.cpp:260-388,
+    #      src/acc/amoeba/epolarewald.cpp:358-667, compiled unmodified; always evaluated as calc::v1)
+    def empole_recip(self, vers):
+        return ref_bridge.recip_mpole(self._rpme(), self._ensure_rpole())
+
+    def epolar_recip_self(self, vers):
+        return ref_bridge.recip_polar(self._rpme(), self.uind, self.uinp)
+
     def _real_space(self, vers, do_m, do_p):
         r = ref_bridge.realspace(self, self.uind if do_p else None, self.uinp if do_p else None)
         i, k, R, sc, pga, pd = self._pairs_c()
-        z3 = np.zeros((3, 3))
         return dict(em=r["em"] if do_m else 0.0, ep=r["ep"] if do_p else 0.0, nem=int((sc[:, 0] != 0).sum()), nep=int((sc[:, 2] != 0).sum()),
-                    gm=r["gm"], gp=r["gp"], tm=r["tm"], tp=r["tp"], vm=z3, vp=z3.copy())
+                    gm=r["gm"], gp=r["gp"], tm=r["tm"], tp=r["tp"], vm=r["vm"], vp=r["vp"])

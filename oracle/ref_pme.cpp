@@ -18,7 +18,12 @@
 #include "ff/energybuffer.h"
 #include "ff/hippo/erepel.h"
 #include "ff/modamoeba.h"
+#include "ff/modhippo.h"
+#include "ff/nblist.h"
 #include "ff/pme.h"
+#include "ff/switch.h"
+#include "math/parallelacc.h"
+#include "tool/gpucard.h"
 #include "tool/accasync.h"
 #include "tool/darray.h"
 #include <cmath>
@@ -40,6 +45,19 @@ void deviceMemoryDeallocate(void* ptr) { std::free(ptr); }
 void deviceMemoryCopyinBytesAsync(void* dst, const void* src, size_t nbytes, int) { std::memcpy(dst, src, nbytes); }
 PME::~PME() {}      // the buffers belong to the vectors below
 
+int gpuGridSize(int) { return 1; }
+NBList::~NBList() {}
+static real g_cutoff = 0;
+real switchOff(Switch) { return g_cutoff; }
+real switchCut(Switch) { return g_cutoff; }
+template <class T>
+void scaleArray_acc(T* dst, T scal, size_t nelem, int)
+{
+   for (size_t i = 0; i < nelem; ++i)
+      dst[i] *= scal;
+}
+template void scaleArray_acc<double>(double*, double, size_t, int);
+
 // ---- the operators of src/acc/pme.cpp
 void pmeConv_acc(PMEUnit, EnergyBuffer, VirialBuffer);
 void cmpToFmp_acc(PMEUnit, const real (*)[10], real (*)[10]);
@@ -51,17 +69,42 @@ void fphiMpole_acc(PMEUnit, real (*)[20]);
 void fphiUind_acc(PMEUnit, real (*)[10], real (*)[10], real (*)[20]);
 void fphiUind2_acc(PMEUnit, real (*)[10], real (*)[10]);
 void rpoleToCmp_acc();
+// ---- src/acc/hippo/empole.cpp, src/acc/amoeba/epolarewald.cpp: reciprocal energy / force / torque / virial assembly
+void empoleChgpenEwaldRecip_acc(int vers, int use_cf);
+void epolarEwaldRecipSelf_acc(int vers, const real (*uind)[3], const real (*uinp)[3]);
 // ---- src/acc/amoeba/rotpole.cpp, torque.cpp (compiled unmodified into this library as well)
 void chkpole_acc();
 void rotpole_acc();
 void torque_acc(int vers, grad_prec* gx, grad_prec* gy, grad_prec* gz);
 }
 
+// ---- front-end dispatchers of src/pme.cpp (TINKER_FCALL wrappers in the reference): forwarded to the *_acc functions; the FFT
+//      (src/host/fft.cpp uses FFTW) is a callback into the caller, which transforms the grid in place
+extern "C" typedef void (*ref_fft_fn)(int forward);
+static ref_fft_fn g_fft = nullptr;
+static tinker::real* g_cur = nullptr;      // the grid ref_pme_qgrid_get / _set address: that of the unit being transformed
+namespace tinker {
+void fftfront(PMEUnit pu) { real* keep = g_cur; g_cur = pu->qgrid, g_fft(1), g_cur = keep; }
+void fftback(PMEUnit pu) { real* keep = g_cur; g_cur = pu->qgrid, g_fft(0), g_cur = keep; }
+void pmeConv(PMEUnit pu) { pmeConv_acc(pu, nullptr, nullptr); }
+void pmeConv(PMEUnit pu, VirialBuffer v) { pmeConv_acc(pu, nullptr, v); }
+void pmeConv(PMEUnit pu, EnergyBuffer e) { pmeConv_acc(pu, e, nullptr); }
+void pmeConv(PMEUnit pu, EnergyBuffer e, VirialBuffer v) { pmeConv_acc(pu, e, v); }
+void cmpToFmp(PMEUnit pu, const real (*c)[10], real (*f)[10]) { cmpToFmp_acc(pu, c, f); }
+void cuindToFuind(PMEUnit pu, const real (*a)[3], const real (*b)[3], real (*c)[3], real (*d)[3]) { cuindToFuind_acc(pu, a, b, c, d); }
+void fphiToCphi(PMEUnit pu, const real (*f)[20], real (*c)[10]) { fphiToCphi_acc(pu, f, c); }
+void gridMpole(PMEUnit pu, real (*f)[10]) { gridMpole_acc(pu, f); }
+void gridUind(PMEUnit pu, real (*a)[3], real (*b)[3]) { gridUind_acc(pu, a, b); }
+void fphiMpole(PMEUnit pu) { fphiMpole_acc(pu, fphi); }
+void fphiUind(PMEUnit pu, real (*a)[10], real (*b)[10], real (*c)[20]) { fphiUind_acc(pu, a, b, c); }
+void fphiUind2(PMEUnit pu, real (*a)[10], real (*b)[10]) { fphiUind2_acc(pu, a, b); }
+}
+
 using namespace tinker;
 
 namespace {
-PMEUnit g_unit;
-std::vector<real> g_x, g_y, g_z, g_qgrid, g_b1, g_b2, g_b3, g_rpole, g_cmp;
+PMEUnit g_unit, g_unit2;      // g_unit2: the second grid of the polarization virial (pvpme_unit, epolarewald.cpp:593)
+std::vector<real> g_x, g_y, g_z, g_qgrid, g_qgrid2, g_b1, g_b2, g_b3, g_rpole, g_cmp;
 size_t g_k = 0;
 }
 
@@ -89,6 +132,13 @@ int ref_pme_open(int natoms, const double* xyz, const double* lvec9, const doubl
    g_b1.assign(bsmod1, bsmod1 + nfft[0]), g_b2.assign(bsmod2, bsmod2 + nfft[1]), g_b3.assign(bsmod3, bsmod3 + nfft[2]);
    st.qgrid = g_qgrid.data(), st.bsmod1 = g_b1.data(), st.bsmod2 = g_b2.data(), st.bsmod3 = g_b3.data();
    st.igrid = nullptr, st.thetai1 = st.thetai2 = st.thetai3 = nullptr;
+   g_unit.deviceptrUpdate(st, 0);
+   g_unit2 = PMEUnit::open();
+   PME& s2 = *g_unit2;
+   g_qgrid2.assign(2 * g_k, 0);
+   s2 = st, s2.qgrid = g_qgrid2.data();
+   g_unit2.deviceptrUpdate(s2, 0);
+   g_cur = g_qgrid.data();
    g_rpole.assign(10 * (size_t)n, 0), g_cmp.assign(10 * (size_t)n, 0);
    rpole = reinterpret_cast<real(*)[MPL_TOTAL]>(g_rpole.data());
    cmp = reinterpret_cast<real(*)[10]>(g_cmp.data());
@@ -96,8 +146,8 @@ int ref_pme_open(int natoms, const double* xyz, const double* lvec9, const doubl
 }
 
 long long ref_pme_grid_size(void) { return (long long)g_k; }
-void ref_pme_qgrid_get(double* out) { std::memcpy(out, g_qgrid.data(), sizeof(double) * 2 * g_k); }      // [n3][n2][n1][re,im]
-void ref_pme_qgrid_set(const double* in) { std::memcpy(g_qgrid.data(), in, sizeof(double) * 2 * g_k); }
+void ref_pme_qgrid_get(double* out) { std::memcpy(out, g_cur, sizeof(double) * 2 * g_k); }      // [n3][n2][n1][re,im]
+void ref_pme_qgrid_set(const double* in) { std::memcpy(g_cur, in, sizeof(double) * 2 * g_k); }
 
 void ref_pme_rpole_to_cmp(const double* rp, double* out)
 {
@@ -177,6 +227,72 @@ int ref_frames_torque(int natoms, const double* xyz, const int* zax, const doubl
    for (int q = 0; q < 6; ++q)
       vir6[q] = vb[0][q];
    trqx = trqy = trqz = nullptr, vir_trq = nullptr;
+   return 0;
+}
+}
+
+// ---- reciprocal-space energy / gradient / torque / virial of the permanent multipoles (empoleChgpenEwaldRecip_acc, AMOEBA branch:
+//      use_cf = 0) and of the induced dipoles incl. the self term (epolarEwaldRecipSelf_acc), calc::v1.  ref_pme_open must have been
+//      called; fft(forward) transforms the grid (ref_pme_qgrid_get / _set) in place, unnormalised in both directions.  The polar
+//      call reuses cmp / fmp / cphi / fphi left by the multipole call, as the reference does (epolarrecip.cu:419-420).
+extern "C" {
+static std::vector<real> r_fmp, r_fphi, r_cphi, r_fuind, r_fuinp, r_fd1, r_fd2, r_cphidp, r_fphidp;
+static v_prec r_vm[1][8];      // vir_m: the convolution virial of the multipole call, subtracted again by the polar call (epolarewald.cpp:505-510)
+
+int ref_recip_mpole(ref_fft_fn fft, const double* rpole_in, double* e, double* grad, double* trq, double* vir6)
+{
+   g_fft = fft;
+   const size_t N = (size_t)n;
+   std::memcpy(g_rpole.data(), rpole_in, sizeof(double) * 10 * N);
+   rpoleToCmp_acc();
+   r_fmp.assign(10 * N, 0), r_fphi.assign(20 * N, 0), r_cphi.assign(10 * N, 0);
+   fmp = reinterpret_cast<real(*)[10]>(r_fmp.data()), fphi = reinterpret_cast<real(*)[20]>(r_fphi.data());
+   cphi = reinterpret_cast<real(*)[10]>(r_cphi.data());
+   std::vector<real> gx(N, 0), gy(N, 0), gz(N, 0), tx(N, 0), ty(N, 0), tz(N, 0);
+   demx = gx.data(), demy = gy.data(), demz = gz.data(), trqx = tx.data(), trqy = ty.data(), trqz = tz.data();
+   e_prec eb[1] = {0};
+   v_prec vb[1][8] = {{0}};
+   std::memset(r_vm, 0, sizeof r_vm);
+   em = eb, vir_em = vb, vir_m = r_vm, pot = nullptr;
+   epme_unit = g_unit;
+   empoleChgpenEwaldRecip_acc(calc::v1, 0);
+   *e = eb[0];
+   for (size_t i = 0; i < N; ++i) {
+      grad[3 * i] = gx[i], grad[3 * i + 1] = gy[i], grad[3 * i + 2] = gz[i];
+      trq[3 * i] = tx[i], trq[3 * i + 1] = ty[i], trq[3 * i + 2] = tz[i];
+   }
+   for (int q = 0; q < 6; ++q)
+      vir6[q] = vb[0][q];
+   demx = demy = demz = trqx = trqy = trqz = nullptr, em = nullptr, vir_em = nullptr, vir_m = nullptr;
+   return 0;
+}
+
+int ref_recip_polar(ref_fft_fn fft, const double* ud, const double* up, double* e, double* grad, double* trq, double* vir6)
+{
+   g_fft = fft;
+   const size_t N = (size_t)n;
+   if (r_fmp.size() != 10 * N)
+      return 2;      // ref_recip_mpole first
+   r_fuind.assign(3 * N, 0), r_fuinp.assign(3 * N, 0), r_fd1.assign(10 * N, 0), r_fd2.assign(10 * N, 0);
+   r_cphidp.assign(10 * N, 0), r_fphidp.assign(20 * N, 0);
+   fuind = reinterpret_cast<real(*)[3]>(r_fuind.data()), fuinp = reinterpret_cast<real(*)[3]>(r_fuinp.data());
+   fdip_phi1 = reinterpret_cast<real(*)[10]>(r_fd1.data()), fdip_phi2 = reinterpret_cast<real(*)[10]>(r_fd2.data());
+   cphidp = reinterpret_cast<real(*)[10]>(r_cphidp.data()), fphidp = reinterpret_cast<real(*)[20]>(r_fphidp.data());
+   std::vector<real> gx(N, 0), gy(N, 0), gz(N, 0), tx(N, 0), ty(N, 0), tz(N, 0);
+   depx = gx.data(), depy = gy.data(), depz = gz.data(), trqx = tx.data(), trqy = ty.data(), trqz = tz.data();
+   e_prec eb[1] = {0};
+   v_prec vb[1][8] = {{0}};
+   ep = eb, vir_ep = vb, vir_m = r_vm;
+   ppme_unit = g_unit, pvpme_unit = g_unit2, epme_unit = g_unit;
+   epolarEwaldRecipSelf_acc(calc::v1, reinterpret_cast<const real(*)[3]>(ud), reinterpret_cast<const real(*)[3]>(up));
+   *e = eb[0];
+   for (size_t i = 0; i < N; ++i) {
+      grad[3 * i] = gx[i], grad[3 * i + 1] = gy[i], grad[3 * i + 2] = gz[i];
+      trq[3 * i] = tx[i], trq[3 * i + 1] = ty[i], trq[3 * i + 2] = tz[i];
+   }
+   for (int q = 0; q < 6; ++q)
+      vir6[q] = vb[0][q];
+   depx = depy = depz = trqx = trqy = trqz = nullptr, ep = nullptr, vir_ep = nullptr, vir_m = nullptr;
    return 0;
 }
 }

@@ -33,6 +33,15 @@ inline Atom load(const double* rp, int i)
 }
 #define MP(a) a.c, a.dx, a.dy, a.dz, a.qxx, a.qxy, a.qxz, a.qyy, a.qyz, a.qzz
 
+// pairwise virial sums {xx, xy, xz, yy, yz, zz} of the multipole and polarization forces, formed as empoleewald.cpp:100-107 and
+// epolarewald.cpp:163-170 do; null = not wanted (set by ref_realspace_virial around a ref_realspace_eval call)
+double *s_vm = nullptr, *s_vp = nullptr;
+inline void add_virial(double* v, real xr, real yr, real zr, real fx, real fy, real fz)
+{
+   v[0] += -xr * fx, v[1] += -0.5f * (yr * fx + xr * fy), v[2] += -0.5f * (zr * fx + xr * fz);
+   v[3] += -yr * fy, v[4] += -0.5f * (zr * fy + yr * fz), v[5] += -zr * fz;
+}
+
 template <class ETYP>
 void one_pair(int i, int k, real r2, real xr, real yr, real zr, real ms, real ds, real ps, real us, const Atom& A, const Atom& B,
    const double* pdamp, real pga, const double* ud, const double* up, real f, real aewald, double* em, double* ep, double* gm, double* tm,
@@ -46,6 +55,8 @@ void one_pair(int i, int k, real r2, real xr, real yr, real zr, real ms, real ds
    *em += e;
    gm[3 * i] += pg.frcx, gm[3 * i + 1] += pg.frcy, gm[3 * i + 2] += pg.frcz;
    gm[3 * k] -= pg.frcx, gm[3 * k + 1] -= pg.frcy, gm[3 * k + 2] -= pg.frcz;
+   if (s_vm)
+      add_virial(s_vm, xr, yr, zr, pg.frcx, pg.frcy, pg.frcz);
    for (int q = 0; q < 3; ++q)
       tm[3 * i + q] += pg.ttmi[q], tm[3 * k + q] += pg.ttmk[q];
    // ---- permanent field, d and p scalings
@@ -74,6 +85,8 @@ void one_pair(int i, int k, real r2, real xr, real yr, real zr, real ms, real ds
    *ep += e;
    gp[3 * i] += pp.frcx, gp[3 * i + 1] += pp.frcy, gp[3 * i + 2] += pp.frcz;
    gp[3 * k] -= pp.frcx, gp[3 * k + 1] -= pp.frcy, gp[3 * k + 2] -= pp.frcz;
+   if (s_vp)
+      add_virial(s_vp, xr, yr, zr, pp.frcx, pp.frcy, pp.frcz);
    for (int q = 0; q < 3; ++q)
       ufld[3 * i + q] += pp.ufldi[q], ufld[3 * k + q] += pp.ufldk[q];
    for (int q = 0; q < 6; ++q)
@@ -118,6 +131,16 @@ extern "C" int ref_realspace_eval(int n, long long npair, const int* pi, const i
          tp[3 * i + 2] = a.dy * u[0] - a.dx * u[1] + a.qyz * d[3] - a.qxz * d[4] + 2 * a.qxy * (d[0] - d[2]) + (a.qyy - a.qxx) * d[1];
       }
    return 0;
+}
+
+// Ask the next ref_realspace_eval calls to add the pairwise virial sums into vm6 / vp6 (zeroed here; null switches it off again).
+extern "C" void ref_realspace_virial(double* vm6, double* vp6)
+{
+   s_vm = vm6, s_vp = vp6;
+   if (vm6)
+      std::memset(vm6, 0, 6 * sizeof(double));
+   if (vp6)
+      std::memset(vp6, 0, 6 * sizeof(double));
 }
 
 // B-spline weights and their first three derivatives of order-5 PME at fractional offsets w[0..m): bsplgen<4> of

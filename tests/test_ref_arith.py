@@ -46,26 +46,28 @@ def test_realspace_oracle_equals_reference_arithmetic_small(ref, blob):
     """pair_mpole / pair_polar / pair_dfield / pair_ufield (EWALD pass + NON_EWALD (scale-1) pass, as the reference's loops
     do) against the oracle's tensor-contraction formulation on every local-frame deck: orthogonal, monoclinic, triclinic
     cells, Ewald and non-Ewald, with 1-2...1-5 and group scaling."""
-    from oracle.amoeba_ref import Oracle, V4
+    from oracle.amoeba_ref import Oracle, V1
     s = _load(blob)
     o = Oracle(s)
     o.rotpole()
     if s.use_polar:
         o.induce()
     r = ref.realspace(o, o.uind if s.use_polar else None, o.uinp if s.use_polar else None)
-    rs = o._real_space(V4, s.use_mpole, s.use_polar)
+    rs = o._real_space(V1, s.use_mpole, s.use_polar)
     fd, fp = o.dfield(real_only=True)
     tol = 1e-11
     if s.use_mpole:
         assert abs(r["em"] - rs["em"]) <= tol * max(1.0, abs(rs["em"]))
         assert np.abs(r["gm"] - rs["gm"]).max() <= tol * max(1.0, np.abs(rs["gm"]).max())
         assert np.abs(r["tm"] - rs["tm"]).max() <= tol * max(1.0, np.abs(rs["tm"]).max())
+        assert np.abs(r["vm"] - rs["vm"]).max() <= tol * max(1.0, np.abs(rs["vm"]).max())      # pairwise virial, empoleewald.cpp:100-107
     assert np.abs(r["fd"] - fd).max() <= tol and np.abs(r["fp"] - fp).max() <= tol
     if s.use_polar:
         ufd, ufp = o.ufield(o.uind, o.uinp, real_only=True)
         assert abs(r["ep"] - rs["ep"]) <= tol * max(1.0, abs(rs["ep"]))
         assert np.abs(r["gp"] - rs["gp"]).max() <= tol * max(1.0, np.abs(rs["gp"]).max())
         assert np.abs(r["tp"] - rs["tp"]).max() <= tol * max(1.0, np.abs(rs["tp"]).max())
+        assert np.abs(r["vp"] - rs["vp"]).max() <= tol * max(1.0, np.abs(rs["vp"]).max())      # epolarewald.cpp:163-170
         assert np.abs(r["ufd"] - ufd).max() <= tol and np.abs(r["ufp"] - ufp).max() <= tol
 
 
@@ -201,18 +203,19 @@ def test_dhfr2_energy_and_dipoles_by_reference_operators(ref):
     reference's compiled code, on the full dhfr2 deck (15 s): converged induced dipoles, multipole and polarization energies
     and the gradient against the oracle fixture the CUDA path is held to (tests/golden/dhfr2_oracle.npz).  This is what pins
     dhfr2 parity -- for which the reference tree holds no golden -- to the reference's own arithmetic."""
-    from oracle.amoeba_ref import V4
+    from oracle.amoeba_ref import V1
     from oracle.ref_oracle import RefOracle
     s = _load("dhfr2.npz")
     z = np.load(os.path.join(GOLDEN, "dhfr2_oracle.npz"))
     r = RefOracle(s)
-    e = r.energy(V4)
+    e = r.energy(V1)
     assert r.niter == int(z["niter"]) == 7
     assert abs(e["em"] - float(z["em"])) <= 1e-12 * abs(float(z["em"]))
     assert abs(e["ep"] - float(z["ep"])) <= 1e-12 * abs(float(z["ep"]))
     assert np.sqrt(((r.uind - z["uind"]) ** 2).mean()) * 4.803206802 <= 1e-12          # Debye
     assert np.sqrt(((r.uinp - z["uinp"]) ** 2).mean()) * 4.803206802 <= 1e-12
     assert np.abs(e["grad"] - z["grad"]).max() <= 1e-10
+    assert np.abs(e["virial"] - z["virial"]).max() <= 1e-11 * np.abs(z["virial"]).max()
 
 
 @pytest.mark.parametrize("blob", ["lf_local_frame_2.npz", "lf_local_frame3_2.npz", "lf_triclinic.npz", "dhfr2.npz"])
@@ -233,3 +236,40 @@ def test_local_frames_equal_reference(ref, blob):
     v0 = o.torque(trq, g0, True)
     assert np.abs(g1 - g0).max() <= 1e-11 * max(1.0, np.abs(g0).max())
     assert np.abs(v1 - v0).max() <= 1e-11 * max(1.0, np.abs(v0).max())
+
+
+@pytest.mark.parametrize("blob", ["lf_local_frame_2.npz", "lf_local_frame3_2.npz", "lf_triclinic.npz", "water30.npz", "dhfr2.npz"])
+def test_reciprocal_assembly_equals_reference(ref, blob):
+    """Per-atom reciprocal energy / gradient / torque / virial assembly: the reference's host translation units
+    src/acc/hippo/empole.cpp (empoleChgpenEwaldRecip_acc, AMOEBA branch) and src/acc/amoeba/epolarewald.cpp
+    (epolarEwaldRecipSelf_acc incl. the self term and the structure-factor virial), compiled unmodified, against the oracle's
+    empole_recip / epolar_recip_self -- the last pieces of the dhfr2 parity chain that were ours alone.  Induced dipoles are
+    random (the assembly is linear in them), so no PCG run is needed; the FFT is numpy's on both sides."""
+    from oracle.amoeba_ref import V1, Oracle
+    if not ref.available("pme"):
+        pytest.skip("oracle/_ref/libref_pme.so not built")
+    s = _load(blob)
+    if not s.use_ewald:
+        pytest.skip("no reciprocal space in this deck")
+    o = Oracle(s)
+    o.rotpole()
+    rp = o._ensure_rpole()
+    P = ref.RefPME(o)
+    rng = np.random.default_rng(11)
+    o.uind, o.uinp = rng.normal(size=(s.n, 3)) * 0.05, rng.normal(size=(s.n, 3)) * 0.05
+
+    def close(a, b, tol=1e-12):
+        a, b = np.asarray(a), np.asarray(b)
+        assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max())
+    m0 = o.empole_recip(V1)
+    m1 = ref.recip_mpole(P, rp)
+    assert abs(m1["e"] - m0["e"]) <= 1e-12 * max(1.0, abs(m0["e"]))
+    close(m1["g"], m0["g"])
+    close(m1["t"], m0["t"])
+    close(m1["v"], m0["v"])
+    p0 = o.epolar_recip_self(V1)
+    p1 = ref.recip_polar(P, o.uind, o.uinp)
+    assert abs(p1["e"] - p0["e"]) <= 1e-12 * max(1.0, abs(p0["e"]))
+    close(p1["g"], p0["g"])
+    close(p1["t"], p0["t"])
+    close(p1["v"], p0["v"], 1e-11)
