@@ -197,6 +197,45 @@ MD_WORKLOAD = ("example/dhfr2 AMOEBA DHFR 23558 atoms (amoebabio09): dynamic 2 f
 MD_DT_PS, MD_NRESPA, MD_KELVIN, MD_TAU, MD_SEED = 0.002, 4, 298.0, 0.2, 20261017
 
 
+def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, timeout_s=150):
+    """The reference's own CUDA kernels (oracle/_ref/libref_cuda.so: its src/cu/**/*.cu compiled unmodified for sm_100 with its
+    release flags, oracle/ref_cuda.cu) on dhfr2 on the same GPU, in a CHILD process with a hard time limit, after our own
+    measurements are complete: ms per mpoleInit + induce() and per fused energy+gradient+virial step (which contains an
+    induce()), checked against the committed float64 oracle fixture.  SURVEY 8(d)'s "1.5x comparator"; the reference
+    executable itself cannot be linked in this image (Fortran).  Never raises: a missing library, a failure or a timeout is
+    reported in the block."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")
+    if not os.path.isfile(lib):
+        return {"unavailable": "oracle/_ref/libref_cuda.so not built (make -C oracle cuda needs /root/reference)"}
+    cmd = [sys.executable, "-m", "oracle.ref_cuda_bridge", os.path.join(GOLDEN, "dhfr2.npz"),
+           "--fixture", os.path.join(GOLDEN, "dhfr2_oracle.npz"), "--reps", "30", "--warmup", "5"]
+    try:
+        r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"unavailable": f"comparator child exceeded {timeout_s} s"}
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": f"comparator child could not start: {e}"}
+    if r.returncode != 0:
+        tail = (r.stderr or r.stdout or "").strip().splitlines()[-1:] or [""]
+        return {"unavailable": f"comparator child exit {r.returncode}: {tail[0][:200]}"}
+    try:
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:      # noqa: BLE001
+        return {"unavailable": "comparator child printed no JSON"}
+    par = out.get("parity") or {}
+    # the reference computes in mixed precision: float pair math, fixed-point sums (the same tolerances our mixed build is held to)
+    out["parity_ok"] = bool(par and par["esum_rel"] < 1e-5 and par["uind_rms_debye"] < 1e-4 and par["grad_rms"] < 1e-2)
+    out["build"] = "reference src/cu/**/*.cu unmodified, nvcc -O3 --use_fast_math sm_100, mixed precision (oracle/Makefile: cuda)"
+    out["timing"] = "CUDA events on the reference's stream around each call, 30 calls after 5 warm-up, no L2 flush, same process-exclusive GPU"
+    if ours_induce_ms:
+        out["ours_induce_ms"] = ours_induce_ms
+        out["induce_speedup_vs_ref_cuda"] = out["induce_ms"]["median"] / ours_induce_ms
+    if ours_energy_ms:
+        out["ours_energy_ms"] = ours_energy_ms
+        out["energy_speedup_vs_ref_cuda"] = out["energy_ms"]["median"] / ours_energy_ms
+    return out
+
+
 def cpu_dynamics_sample(system):
     """One MD step of the CPU oracle on a bounded sample: the electrostatics sample of cpu_oracle_sample (full induce(),
     reciprocal space, a slice of the real-space pairs scaled up) + the full vdW oracle + nrespa evaluations of the
@@ -426,6 +465,8 @@ def run_dynamics(args, rank, world, local_rank):
                                     "note": "the reference EXECUTABLE cannot be linked here (no Fortran compiler); kind 'reference' = its own "
                                             "pair functions and PME translation unit compiled in place and run serially, as its host build "
                                             "does (OpenACC pragmas ignored by g++); reported, not a target"}
+        if not args.no_cpu and not args.no_ref_cuda and world == 1:
+            line["ref_cuda"] = ref_cuda_sample(ours_induce_ms=float(np.median(ms_induce)))
         print(json.dumps(line))
     a.close()
     if dist is not None:
@@ -634,6 +675,8 @@ def run_ours(args, rank, world, local_rank):
                                     "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
                                     "note": "vectorised-numpy port on one core, about two orders of magnitude slower than the reference's "
                                             "compiled host build would be (it cannot be linked here: no Fortran compiler); reported, not a target"}
+        if not args.no_cpu and not args.no_ref_cuda and world == 1 and args.workload == "dhfr2" and not args.vdw:
+            line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step))
         print(json.dumps(line))
     a.close()
     if dist is not None:
@@ -647,6 +690,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the reference-CUDA comparator leg (oracle/_ref/libref_cuda.so)")
     ap.add_argument("--workload", default="dhfr2", choices=sorted(WORKLOADS))
     ap.add_argument("--vdw", action="store_true", help="also evaluate the buffered 14-7 vdW term (SURVEY 8f rank 1) in every step")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas also for the large workloads")

@@ -1,0 +1,33 @@
+"""The reference's own CUDA kernels (oracle/_ref/libref_cuda.so = its src/cu/**/*.cu compiled unmodified, oracle/ref_cuda.cu)
+run on the GPU on dhfr2 and held to the same float64 oracle fixture as our path -- the comparator of SURVEY section 8(d).
+It runs in a child process (the reference keeps its state in process globals and uses the legacy default stream)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="comparator built at the end of round 1 after the GPU budget was spent: its first run on a GPU is pending",
+                   strict=False)
+def test_reference_cuda_kernels_on_dhfr2_match_the_oracle_fixture():
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")
+    if not os.path.isfile(lib):
+        pytest.skip("oracle/_ref/libref_cuda.so not built (make -C oracle cuda)")
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_cuda_bridge", os.path.join(GOLDEN, "dhfr2.npz"), "--fixture",
+                        os.path.join(GOLDEN, "dhfr2_oracle.npz"), "--reps", "5", "--warmup", "2"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=240)
+    assert r.returncode == 0, (r.stderr or r.stdout)[-800:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    print("reference CUDA on dhfr2:", json.dumps(out))
+    p = out["parity"]
+    # mixed precision (float pair math, fixed-point sums): the tolerances our own mixed build is held to in test_gpu_parity.py
+    assert p["esum_rel"] < 1e-5
+    assert p["uind_rms_debye"] < 1e-4
+    assert p["grad_rms"] < 1e-2
+    assert out["induce_ms"]["median"] > 0 and out["energy_ms"]["median"] > out["induce_ms"]["median"]
