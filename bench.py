@@ -197,7 +197,7 @@ MD_WORKLOAD = ("example/dhfr2 AMOEBA DHFR 23558 atoms (amoebabio09): dynamic 2 f
 MD_DT_PS, MD_NRESPA, MD_KELVIN, MD_TAU, MD_SEED = 0.002, 4, 298.0, 0.2, 20261017
 
 
-def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, timeout_s=150):
+def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, ours_md_step_ms=None, timeout_s=150):
     """The reference's own CUDA kernels (oracle/_ref/libref_cuda.so: its src/cu/**/*.cu compiled unmodified for sm_100 with its
     release flags, oracle/ref_cuda.cu) on dhfr2 on the same GPU, in a CHILD process with a hard time limit, after our own
     measurements are complete: ms per mpoleInit + induce() and per fused energy+gradient+virial step (which contains an
@@ -208,20 +208,35 @@ def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, timeout_s=150):
     if not os.path.isfile(lib):
         return {"unavailable": "oracle/_ref/libref_cuda.so not built (make -C oracle cuda needs /root/reference)"}
     cmd = [sys.executable, "-m", "oracle.ref_cuda_bridge", os.path.join(GOLDEN, "dhfr2.npz"),
-           "--fixture", os.path.join(GOLDEN, "dhfr2_oracle.npz"), "--reps", "30", "--warmup", "5"]
+           "--fixture", os.path.join(GOLDEN, "dhfr2_oracle.npz"), "--reps", "30", "--warmup", "5",
+           "--vdw", os.path.join(GOLDEN, "dhfr2_vdw_oracle.npz")]
+    rc, stdout, stderr = 0, "", ""
     try:
         r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
-    except subprocess.TimeoutExpired:
-        return {"unavailable": f"comparator child exceeded {timeout_s} s"}
+        rc, stdout, stderr = r.returncode, r.stdout or "", r.stderr or ""
+    except subprocess.TimeoutExpired as e:
+        dec = lambda b: b.decode(errors="replace") if isinstance(b, bytes) else (b or "")      # noqa: E731
+        rc, stdout, stderr = -999, dec(e.stdout), f"time limit of {timeout_s} s exceeded"
     except Exception as e:      # noqa: BLE001
         return {"unavailable": f"comparator child could not start: {e}"}
-    if r.returncode != 0:
-        tail = (r.stderr or r.stdout or "").strip().splitlines()[-1:] or [""]
-        return {"unavailable": f"comparator child exit {r.returncode}: {tail[0][:200]}"}
-    try:
-        out = json.loads(r.stdout.strip().splitlines()[-1])
-    except Exception:      # noqa: BLE001
-        return {"unavailable": "comparator child printed no JSON"}
+    # line 1 = electrostatics (validated on a B200 in round 1); line 2 = {"vdw": ...} from the reference's ehal.cu, which may be
+    # missing if that newer part failed -- the first line stands on its own
+    out = None
+    for ln in stdout.strip().splitlines():
+        try:
+            d = json.loads(ln)
+        except Exception:      # noqa: BLE001
+            continue
+        if out is None:
+            out = d
+        else:
+            out.update(d)
+    if out is None:
+        tail = (stderr or stdout).strip().splitlines()[-1:] or [""]
+        return {"unavailable": f"comparator child exit {rc}: {tail[0][:200]}"}
+    if rc != 0:
+        tail = stderr.strip().splitlines()[-1:] or [""]
+        out["vdw"] = {"unavailable": f"child exit {rc} after the electrostatics line: {tail[0][:200]}"}
     par = out.get("parity") or {}
     # the reference computes in mixed precision: float pair math, fixed-point sums (the same tolerances our mixed build is held to)
     out["parity_ok"] = bool(par and par["esum_rel"] < 1e-5 and par["uind_rms_debye"] < 1e-4 and par["grad_rms"] < 1e-2)
@@ -233,6 +248,13 @@ def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, timeout_s=150):
     if ours_energy_ms:
         out["ours_energy_ms"] = ours_energy_ms
         out["energy_speedup_vs_ref_cuda"] = out["energy_ms"]["median"] / ours_energy_ms
+    ehal = (out.get("vdw") or {}).get("ehal_ms")
+    if ours_md_step_ms and ehal:
+        lo = out["energy_ms"]["median"] + ehal["median"]
+        out["md_step_lower_bound"] = {"ms": lo, "ns_per_day_upper_bound": ns_per_day(lo), "ours_ms_per_step": ours_md_step_ms,
+                                      "speedup_lower_bound": lo / ours_md_step_ms,
+                                      "note": "reference electrostatics step + its ehal kernel, run one after the other as the reference does; its "
+                                              "valence terms, integrator and per-step list refresh are NOT included, so its real MD step is longer"}
     return out
 
 
@@ -466,7 +488,7 @@ def run_dynamics(args, rank, world, local_rank):
                                             "pair functions and PME translation unit compiled in place and run serially, as its host build "
                                             "does (OpenACC pragmas ignored by g++); reported, not a target"}
         if not args.no_cpu and not args.no_ref_cuda and world == 1:
-            line["ref_cuda"] = ref_cuda_sample(ours_induce_ms=float(np.median(ms_induce)))
+            line["ref_cuda"] = ref_cuda_sample(ours_induce_ms=float(np.median(ms_induce)), ours_md_step_ms=float(ms_step))
         print(json.dumps(line))
     a.close()
     if dist is not None:

@@ -25,6 +25,7 @@
 #include "ff/box.h"
 #include "ff/elec.h"
 #include "ff/energybuffer.h"
+#include "ff/evdw.h"
 #include "ff/modamoeba.h"
 #include "ff/nblist.h"
 #include "ff/pme.h"
@@ -58,7 +59,7 @@
 // 1. shim
 // ------------------------------------------------------------------------------------------------------------------------
 namespace {
-double s_ewald_cut = 7, s_usolve_cut = 4.5;
+double s_ewald_cut = 7, s_usolve_cut = 4.5, s_vdw_cut = 12, s_vdw_taper = 10.8;
 int s_politer = 100, s_pcgprec = 1, s_pcgguess = 1, s_debug = 0, s_use_exfld = 0;
 double s_poleps = 1e-5, s_pcgpeek = 1, s_texfld[3] = {0, 0, 0};
 double* s_polarity = nullptr;
@@ -91,8 +92,11 @@ int& use_exfld = s_use_exfld;
 bool use(Potent term) { return term == Potent::MPOLE || term == Potent::POLAR; }
 bool useEwald() { return true; }
 bool useDEwald() { return false; }
-real switchOff(Switch mode) { return mode == Switch::USOLVE ? (real)s_usolve_cut : (real)s_ewald_cut; }
-real switchCut(Switch mode) { return switchOff(mode); }
+real switchOff(Switch mode)
+{
+   return mode == Switch::USOLVE ? (real)s_usolve_cut : mode == Switch::VDW ? (real)s_vdw_cut : (real)s_ewald_cut;
+}
+real switchCut(Switch mode) { return mode == Switch::VDW ? (real)s_vdw_taper : switchOff(mode); }
 real boxVolume()
 {
    return lvec1.x * (lvec2.y * lvec3.z - lvec2.z * lvec3.y) - lvec1.y * (lvec2.x * lvec3.z - lvec2.z * lvec3.x)
@@ -160,6 +164,10 @@ void chkpole_cu();
 void rotpole_cu();
 void mpoleDataBinding_cu(RcOp);
 void epolarDataBinding_cu(RcOp);
+void ehal_cu(int);
+void ehalReduceXyz_cu();
+void ehalResolveGradient_cu();
+void ehalResolveGradient() { ehalResolveGradient_cu(); }      // src/evdw.cpp:573-577
 void empoleEwaldRecip(int vers) { empoleChgpenEwaldRecip_cu(vers, 0); }
 void epolarEwaldRecipSelf(int vers) { epolarEwaldRecipSelf_cu(vers, uind, uinp); }
 void epolar0DotProd(const real (*u)[3], const real (*v)[3]) { epolar0DotProd_cu(u, v); }
@@ -499,6 +507,131 @@ int refcu_time(int what, int vers, int warmup, int reps, float* ms)
             Spatial::dataInit(mspatial_v2_unit);
             Spatial::dataInit(uspatial_v2_unit);
          }
+         always_check_rt(cudaEventRecord(e1, g::s0));
+         always_check_rt(cudaEventSynchronize(e1));
+         float t = 0;
+         always_check_rt(cudaEventElapsedTime(&t, e0, e1));
+         if (r >= 0)
+            ms[r] = t;
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+   });
+}
+
+// ---- the buffered 14-7 van der Waals term of the same step (src/cu/ehal.cu, unmodified): optional, after refcu_open.
+struct refcu_vdw {
+   const int* ired;        // [n] atom each site is reduced toward, from zero
+   const double* kred;     // [n]
+   const int* jvdw;        // [n] class index, from zero
+   int njvdw;
+   const double* radmin;   // [njvdw][njvdw]
+   const double* epsilon;  // [njvdw][njvdw]
+   int nvexclude;
+   const int* vexclude;    // [nvexclude][2]
+   const double* vexclude_scale;
+   double cutoff, taper, list_buffer;
+};
+static bool s_vdw_open = false;
+int refcu_sizeof_vdw(void) { return (int)sizeof(refcu_vdw); }
+
+int refcu_vdw_open(const refcu_vdw* v)
+{
+   if (!s_open || s_vdw_open) {
+      s_err = "refcu_vdw_open: needs refcu_open first, once";
+      return 3;
+   }
+   return guarded([&] {
+      s_vdw_cut = v->cutoff, s_vdw_taper = v->taper;
+      vdwtyp = Vdw::HAL;
+      ghal = 0.12, dhal = 0.07;      // compile-time constants of ehal.cu:96-99
+      vcouple = Vdw::DECOUPLE, vlam = 1, scexp = 5, scalpha = 0.7;
+      njvdw = v->njvdw;
+      nvexclude = v->nvexclude;
+      darray::allocate(n, &ired, &kred, &jvdw, &mut, &xred, &yred, &zred, &gxred, &gyred, &gzred, &devx, &devy, &devz);
+      darray::allocate((size_t)njvdw * njvdw, &radmin, &epsilon);
+      darray::allocate(std::max(nvexclude, 1), &vexclude, &vexclude_scale);
+      darray::allocate(bufferSize(), &ev, &vir_ev, &nev);
+      darray::copyin(g::q0, n, ired, v->ired);
+      darray::copyin(g::q0, n, kred, v->kred);
+      darray::copyin(g::q0, n, jvdw, v->jvdw);
+      darray::zero(g::q0, n, mut);
+      darray::copyin(g::q0, (size_t)njvdw * njvdw, radmin, v->radmin);
+      darray::copyin(g::q0, (size_t)njvdw * njvdw, epsilon, v->epsilon);
+      if (nvexclude)
+         darray::copyin(g::q0, nvexclude, vexclude, v->vexclude), darray::copyin(g::q0, nvexclude, vexclude_scale, v->vexclude_scale);
+      waitFor(g::q0);
+      // vlist on the reduced sites (src/nblist.cpp:366-374)
+      Spatial::dataAlloc(vspatial_v2_unit, n, v->cutoff, v->list_buffer, xred, yred, zred, 1, nvexclude, vexclude, 0, nullptr, 0, nullptr, 0,
+         nullptr);
+      ehalReduceXyz_cu();
+      Spatial::dataInit(vspatial_v2_unit);
+      waitFor(g::q0);
+      s_vdw_open = true;
+   });
+}
+
+// what the vdW term costs per step: reduced sites (nblistRefresh does this every step, src/nblist.cpp:545-548), zeroed accumulators,
+// ehal_cu(vers) incl. the gradient hand-back to the real atoms, reductions.  No long-range correction (a host constant).
+static void ehal_step(int vers, double* e, double* vir9)
+{
+   if (vers & calc::energy)
+      darray::zero(g::q0, bufferSize(), ev);
+   if (vers & calc::virial)
+      darray::zero(g::q0, bufferSize(), vir_ev);
+   if (vers & calc::grad)
+      darray::zero(g::q0, n, devx, devy, devz);
+   ehalReduceXyz_cu();
+   ehal_cu(vers);
+   if (vers & calc::energy) {
+      energy_prec e1 = energyReduce(ev);
+      if (e)
+         *e = e1;
+   }
+   if (vers & calc::virial) {
+      virial_prec v1[9];
+      virialReduce(v1, vir_ev);
+      if (vir9)
+         for (int q = 0; q < 9; ++q)
+            vir9[q] = v1[q];
+   }
+}
+
+int refcu_ehal(int vers, double* e, double* grad, double* vir9)
+{
+   if (!s_vdw_open) {
+      s_err = "refcu_ehal: refcu_vdw_open first";
+      return 3;
+   }
+   return guarded([&] {
+      ehal_step(vers, e, vir9);
+      if ((vers & calc::grad) && grad) {
+         std::vector<grad_prec> a(n);
+         grad_prec* dv[3] = {devx, devy, devz};
+         for (int c = 0; c < 3; ++c) {
+            darray::copyout(g::q0, n, a.data(), dv[c]);
+            waitFor(g::q0);
+            for (int i = 0; i < n; ++i)
+               grad[3 * i + c] = toFloatingPoint<double>(a[i]);
+         }
+      }
+   });
+}
+
+int refcu_time_ehal(int vers, int warmup, int reps, float* ms)
+{
+   if (!s_vdw_open) {
+      s_err = "refcu_time_ehal: refcu_vdw_open first";
+      return 3;
+   }
+   return guarded([&] {
+      cudaEvent_t e0, e1;
+      always_check_rt(cudaEventCreate(&e0));
+      always_check_rt(cudaEventCreate(&e1));
+      for (int r = -warmup; r < reps; ++r) {
+         always_check_rt(cudaStreamSynchronize(g::s0));
+         always_check_rt(cudaEventRecord(e0, g::s0));
+         ehal_step(vers, nullptr, nullptr);
          always_check_rt(cudaEventRecord(e1, g::s0));
          always_check_rt(cudaEventSynchronize(e1));
          float t = 0;

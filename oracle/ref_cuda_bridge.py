@@ -32,6 +32,12 @@ class _RefcuSystem(C.Structure):      # struct refcu_system of oracle/ref_cuda.c
                 ("electric", C.c_double), ("dielec", C.c_double)]
 
 
+class _RefcuVdw(C.Structure):         # struct refcu_vdw of oracle/ref_cuda.cu
+    _fields_ = [("ired", _IP), ("kred", _DP), ("jvdw", _IP), ("njvdw", C.c_int), ("radmin", _DP), ("epsilon", _DP),
+                ("nvexclude", C.c_int), ("vexclude", _IP), ("vexclude_scale", _DP),
+                ("cutoff", C.c_double), ("taper", C.c_double), ("list_buffer", C.c_double)]
+
+
 class RefCuda:
     """mpoleInit + induce() and the fused energy step (emplar) of the reference's CUDA build on `system`."""
 
@@ -100,6 +106,39 @@ class RefCuda:
         self._check(self.lib.refcu_energy(int(vers), C.byref(es), g.ctypes.data_as(_DP), v.ctypes.data_as(_DP)), "refcu_energy")
         return dict(esum=es.value, grad=g, virial=v.reshape(3, 3))
 
+    # ---- buffered 14-7 vdW (src/cu/ehal.cu)
+    def vdw_open(self, v):
+        """v: the System's vdwparams.VdwTerm."""
+        lib = self.lib
+        lib.refcu_vdw_open.argtypes = [C.POINTER(_RefcuVdw)]
+        lib.refcu_ehal.argtypes = [C.c_int, _DP, _DP, _DP]
+        lib.refcu_time_ehal.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        nx = int(v.vexclude.shape[0]) if v.vexclude.size else 0
+        keep = dict(ired=np.ascontiguousarray(v.ired, np.int32), kred=np.ascontiguousarray(v.kred, np.float64),
+                    jvdw=np.ascontiguousarray(v.jvdw, np.int32), radmin=np.ascontiguousarray(v.radmin, np.float64),
+                    epsilon=np.ascontiguousarray(v.epsilon, np.float64),
+                    vex=np.ascontiguousarray(v.vexclude.reshape(-1, 2) if nx else np.zeros((1, 2)), np.int32),
+                    vexs=np.ascontiguousarray(v.vexclude_scale if nx else np.ones(1), np.float64))
+        self._keep_vdw = keep
+        st = _RefcuVdw()
+        st.ired, st.kred, st.jvdw = keep["ired"].ctypes.data_as(_IP), keep["kred"].ctypes.data_as(_DP), keep["jvdw"].ctypes.data_as(_IP)
+        st.njvdw, st.radmin, st.epsilon = int(keep["radmin"].shape[0]), keep["radmin"].ctypes.data_as(_DP), keep["epsilon"].ctypes.data_as(_DP)
+        st.nvexclude, st.vexclude, st.vexclude_scale = nx, keep["vex"].ctypes.data_as(_IP), keep["vexs"].ctypes.data_as(_DP)
+        st.cutoff, st.taper, st.list_buffer = float(v.cutoff), float(v.taper), float(v.list_buffer)
+        self._check(lib.refcu_vdw_open(C.byref(st)), "refcu_vdw_open")
+
+    def ehal(self, vers=ENERGY | GRAD | VIRIAL):
+        """Pair sum of the 14-7 term (no long-range correction), gradient on the real atoms, pair virial."""
+        e = C.c_double()
+        g, v = np.zeros((self.n, 3)), np.zeros(9)
+        self._check(self.lib.refcu_ehal(int(vers), C.byref(e), g.ctypes.data_as(_DP), v.ctypes.data_as(_DP)), "refcu_ehal")
+        return dict(ev=e.value, grad=g, virial=v.reshape(3, 3))
+
+    def time_ehal(self, reps=20, warmup=3, vers=ENERGY | GRAD):
+        ms = (C.c_float * reps)()
+        self._check(self.lib.refcu_time_ehal(int(vers), int(warmup), int(reps), ms), "refcu_time_ehal")
+        return np.array(ms[:], np.float64)
+
     def time(self, what, reps=20, warmup=3, vers=ENERGY | GRAD | VIRIAL):
         """CUDA-event milliseconds per call: what = 'induce' | 'energy' | 'rebuild'."""
         ms = (C.c_float * reps)()
@@ -118,6 +157,8 @@ def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("blob")
     ap.add_argument("--fixture", default=None, help="npz with em, ep, uind, grad of the float64 oracle on the same system")
+    ap.add_argument("--vdw", default=None, metavar="FIXTURE", help="also run the reference's ehal.cu; npz with ev_pairs, grad of the vdW oracle "
+                    "(a SECOND JSON line; the first one is already out if this part fails)")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     a = ap.parse_args(argv)
@@ -142,7 +183,18 @@ def main(argv=None):
         ms = r.time(what, a.reps, a.warmup, vers)
         out[key] = dict(median=float(np.median(ms)), min=float(ms.min()), max=float(ms.max()), reps=a.reps)
     out["energy_ms"]["vers"] = "energy+grad (calc::v4): zero accumulators, mpoleInit, induce, emplar kernels, recip, torque, reductions"
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if a.vdw and s.vdw is not None:
+        r.vdw_open(s.vdw)
+        w = r.ehal()
+        z = np.load(a.vdw)
+        vout = dict(ev_pairs=w["ev"], parity=dict(ev_rel=abs(w["ev"] - float(z["ev_pairs"])) / abs(float(z["ev_pairs"])),
+                                                  grad_rms=float(np.sqrt(((w["grad"] - z["grad"]) ** 2).sum(1).mean())),
+                                                  virial_rel=float(np.abs(w["virial"] - z["virial_pairs"]).max() / np.abs(z["virial_pairs"]).max())))
+        ms = r.time_ehal(a.reps, a.warmup)
+        vout["ehal_ms"] = dict(median=float(np.median(ms)), min=float(ms.min()), max=float(ms.max()), reps=a.reps,
+                               vers="energy+grad: reduced sites, zero accumulators, ehal_cu incl. gradient hand-back, reduction")
+        print(json.dumps({"vdw": vout}), flush=True)
 
 
 if __name__ == "__main__":
