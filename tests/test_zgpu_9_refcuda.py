@@ -31,3 +31,22 @@ def test_reference_cuda_kernels_on_dhfr2_match_the_oracle_fixture():
     assert p["grad_rms"] < 5e-4
     assert p["virial_rel"] < 1e-5
     assert out["induce_ms"]["median"] > 0 and out["energy_ms"]["median"] > out["induce_ms"]["median"]
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="the ehal.cu part of the comparator was added after the round-1 GPU budget was spent: first GPU run pending",
+                   strict=False)
+def test_reference_cuda_ehal_on_dhfr2_matches_the_vdw_oracle_fixture():
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")
+    if not os.path.isfile(lib):
+        pytest.skip("oracle/_ref/libref_cuda.so not built (make -C oracle cuda)")
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_cuda_bridge", os.path.join(GOLDEN, "dhfr2.npz"), "--reps", "5", "--warmup", "2",
+                        "--vdw", os.path.join(GOLDEN, "dhfr2_vdw_oracle.npz")], cwd=ROOT, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, (r.stderr or r.stdout)[-800:]
+    lines = [json.loads(ln) for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    v = lines[-1]["vdw"]
+    print("reference CUDA ehal on dhfr2:", json.dumps(v))
+    assert v["parity"]["ev_rel"] < 5e-6
+    assert v["parity"]["grad_rms"] < 5e-4
+    assert v["parity"]["virial_rel"] < 1e-4
+    assert v["ehal_ms"]["median"] > 0
