@@ -50,3 +50,23 @@ def test_reference_cuda_ehal_on_dhfr2_matches_the_vdw_oracle_fixture():
     assert v["parity"]["grad_rms"] < 5e-4
     assert v["parity"]["virial_rel"] < 1e-4
     assert v["ehal_ms"]["median"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="drop-in library (reference front-ends + integration/apx_adapter.cpp + libapx) was built after the round-1 GPU "
+                          "budget was spent: first GPU run pending", strict=False)
+def test_reference_front_ends_run_on_our_kernels_through_the_adapter():
+    """tinker::induce / dfield / ufield / sparsePrecondApply of the reference's unmodified src/amoeba/{induce,field}.cpp, linked
+    with the adapter instead of its kernels: dipoles and energies against the oracle fixture, operators against the C ABI."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libref_dropin.so")
+    if not os.path.isfile(lib):
+        pytest.skip("oracle/_ref/libref_dropin.so not built (make -C oracle dropin)")
+    r = subprocess.run([sys.executable, "-m", "oracle.ref_dropin_bridge", os.path.join(GOLDEN, "dhfr2.npz"), "--fixture",
+                        os.path.join(GOLDEN, "dhfr2_oracle.npz")], cwd=ROOT, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, (r.stderr or r.stdout)[-800:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    print("reference front-ends on libapx:", json.dumps(out))
+    o, c = out["vs_oracle"], out["vs_c_abi"]
+    assert o["uind_rms_debye"] < 2e-6 and o["udir_rms_debye"] < 2e-6      # float round trip of the reference's globals on top of 1e-6
+    assert o["em_rel"] < 2e-6 and o["ep_rel"] < 2e-6 and o["grad_rms"] < 1e-4
+    assert max(c.values()) < 1e-6

@@ -262,6 +262,51 @@ def dist_plan(w3_sorted, bounds, world, rank, range_frac, precision="mixed"):
     return si[:so[-1]].copy(), so, ri[:ro[-1]].copy(), ro
 
 
+def system_struct(system):
+    """(apx_system filled from a System, list of the numpy arrays it points into) -- what mpoleData / epolarData / pmeData
+    upload; also used by the drop-in test scaffolding (oracle/ref_dropin.cpp)."""
+    s = _ApxSystem()
+    keep = []
+
+    def f64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return _dp(a)
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int))
+
+    s.n = system.n
+    s.xyz = f64(system.xyz)
+    s.lvec = (C.c_double * 9)(*np.asarray(system.lvec, float).ravel())
+    s.pole = f64(system.pole)
+    s.zaxis = i32(system.zaxis)
+    s.polarity = f64(system.polarity)
+    s.thole = f64(system.thole)
+    s.pdamp = f64(system.pdamp)
+    s.jpolar = i32(system.jpolar)
+    s.njpolar = int(system.thlval.shape[0])
+    s.thlval = f64(system.thlval)
+    s.nmdpu = int(system.mdpuexclude.shape[0])
+    s.mdpu_ik = i32(system.mdpuexclude.reshape(-1, 2) if s.nmdpu else np.zeros((1, 2)))
+    s.mdpu_scale = f64(system.mdpuexclude_scale.reshape(-1, 4) if s.nmdpu else np.ones((1, 4)))
+    s.use_ewald, s.use_mpole, s.use_polar = int(system.use_ewald), int(system.use_mpole), int(system.use_polar)
+    s.poltyp_mutual = 0 if system.poltyp == "DIRECT" else 1
+    s.aewald = system.aewald
+    s.nfft = (C.c_int * 3)(*[int(v) for v in system.nfft])
+    s.bsorder = system.bsorder
+    s.cutoff = float(system.ewald_cutoff)
+    s.usolve_cutoff = float(system.usolve_cutoff)
+    s.list_buffer = float(system.list_buffer)
+    s.poleps, s.politer, s.uaccel = system.poleps, system.politer, system.uaccel
+    s.pcgprec, s.pcgguess, s.pcgpeek = int(system.pcgprec), int(system.pcgguess), system.pcgpeek
+    s.electric, s.dielec = system.electric, system.dielec
+    s.polpred = UPRED[str(getattr(system, "polpred", "NONE") or "NONE").upper()]
+    return s, keep
+
+
 class Amoeba:
     """One electrostatics context on one GPU (the reference's initialize()/finish() pair).
 
@@ -277,45 +322,7 @@ class Amoeba:
         self.system = system
         self.n = system.n
         self.precision = precision
-        s = _ApxSystem()
-        keep = []
-
-        def f64(a):
-            a = np.ascontiguousarray(a, dtype=np.float64)
-            keep.append(a)
-            return _dp(a)
-
-        def i32(a):
-            a = np.ascontiguousarray(a, dtype=np.int32)
-            keep.append(a)
-            return a.ctypes.data_as(C.POINTER(C.c_int))
-
-        s.n = system.n
-        s.xyz = f64(system.xyz)
-        s.lvec = (C.c_double * 9)(*np.asarray(system.lvec, float).ravel())
-        s.pole = f64(system.pole)
-        s.zaxis = i32(system.zaxis)
-        s.polarity = f64(system.polarity)
-        s.thole = f64(system.thole)
-        s.pdamp = f64(system.pdamp)
-        s.jpolar = i32(system.jpolar)
-        s.njpolar = int(system.thlval.shape[0])
-        s.thlval = f64(system.thlval)
-        s.nmdpu = int(system.mdpuexclude.shape[0])
-        s.mdpu_ik = i32(system.mdpuexclude.reshape(-1, 2) if s.nmdpu else np.zeros((1, 2)))
-        s.mdpu_scale = f64(system.mdpuexclude_scale.reshape(-1, 4) if s.nmdpu else np.ones((1, 4)))
-        s.use_ewald, s.use_mpole, s.use_polar = int(system.use_ewald), int(system.use_mpole), int(system.use_polar)
-        s.poltyp_mutual = 0 if system.poltyp == "DIRECT" else 1
-        s.aewald = system.aewald
-        s.nfft = (C.c_int * 3)(*[int(v) for v in system.nfft])
-        s.bsorder = system.bsorder
-        s.cutoff = float(system.ewald_cutoff)
-        s.usolve_cutoff = float(system.usolve_cutoff)
-        s.list_buffer = float(system.list_buffer)
-        s.poleps, s.politer, s.uaccel = system.poleps, system.politer, system.uaccel
-        s.pcgprec, s.pcgguess, s.pcgpeek = int(system.pcgprec), int(system.pcgguess), system.pcgpeek
-        s.electric, s.dielec = system.electric, system.dielec
-        s.polpred = UPRED[str(getattr(system, "polpred", "NONE") or "NONE").upper()]
+        s, keep = system_struct(system)
         self.ctx = C.c_void_p()
         if dist is None:
             rc = self.lib.apx_create(C.byref(s), device, C.byref(self.ctx))
