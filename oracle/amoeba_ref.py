@@ -28,9 +28,11 @@ what tests/test_oracle_golden.py checks against the reference's own golden vecto
 
 PARITY PINNING: pinned against the reference's golden vectors for the 22-/18-atom
 local-frame systems and the 2684-atom water box (tolerance 1e-4..1e-3, the precision the
-goldens are printed with).  dhfr2 itself has NO golden in the reference tree:
-"parity unpinned" for dhfr2-size absolute values; there the oracle is the f64 statement
-of the same, small-system-pinned algorithm.
+goldens are printed with).  dhfr2 itself has NO golden in the reference tree (SURVEY §4);
+its dhfr2-size values are pinned by outputs of the reference itself run here: the reference's
+host arithmetic compiled in place (oracle/_ref, tests/test_ref_arith.py: 1e-11 .. 1e-13) and
+the reference's own CUDA build on a B200 (oracle/ref_cuda.cu, tests/test_zgpu_9_refcuda.py:
+6.6e-7 energy, 3.9e-7 D dipoles, 4.9e-5 gradient against tests/golden/dhfr2_oracle.npz).
 """
 from __future__ import annotations
 
