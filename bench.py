@@ -197,19 +197,33 @@ MD_WORKLOAD = ("example/dhfr2 AMOEBA DHFR 23558 atoms (amoebabio09): dynamic 2 f
 MD_DT_PS, MD_NRESPA, MD_KELVIN, MD_TAU, MD_SEED = 0.002, 4, 298.0, 0.2, 20261017
 
 
-def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, ours_md_step_ms=None, timeout_s=150):
+def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, ours_md_step_ms=None, timeout_s=150, system=None, ours_esum=None):
     """The reference's own CUDA kernels (oracle/_ref/libref_cuda.so: its src/cu/**/*.cu compiled unmodified for sm_100 with its
     release flags, oracle/ref_cuda.cu) on dhfr2 on the same GPU, in a CHILD process with a hard time limit, after our own
     measurements are complete: ms per mpoleInit + induce() and per fused energy+gradient+virial step (which contains an
     induce()), checked against the committed float64 oracle fixture.  SURVEY 8(d)'s "1.5x comparator"; the reference
     executable itself cannot be linked in this image (Fortran).  Never raises: a missing library, a failure or a timeout is
-    reported in the block."""
+    reported in the block.  system: another workload (a replicated box) -- written to a temporary blob for the child; there
+    is no oracle fixture at those sizes, so the block carries the relative difference of the reference's E to ours."""
     lib = os.path.join(ROOT, "oracle", "_ref", "libref_cuda.so")
     if not os.path.isfile(lib):
         return {"unavailable": "oracle/_ref/libref_cuda.so not built (make -C oracle cuda needs /root/reference)"}
     cmd = [sys.executable, "-m", "oracle.ref_cuda_bridge", os.path.join(GOLDEN, "dhfr2.npz"),
            "--fixture", os.path.join(GOLDEN, "dhfr2_oracle.npz"), "--reps", "30", "--warmup", "5",
            "--vdw", os.path.join(GOLDEN, "dhfr2_vdw_oracle.npz")]
+    if system is not None:
+        try:
+            import tempfile
+            import tinker_gpu_b200 as tg
+            keep = (system.vdw, system.valence)
+            system.vdw = system.valence = None
+            blob = os.path.join(tempfile.mkdtemp(prefix="apx_refcuda_"), "system.npz")
+            tg.save_system(blob, system)
+            system.vdw, system.valence = keep
+        except Exception as e:      # noqa: BLE001
+            return {"unavailable": f"could not write the system blob for the comparator: {e}"}
+        cmd = [sys.executable, "-m", "oracle.ref_cuda_bridge", blob, "--reps", "10", "--warmup", "3"]
+        timeout_s = max(timeout_s, 300)
     rc, stdout, stderr = 0, "", ""
     try:
         r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout_s)
@@ -237,9 +251,12 @@ def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, ours_md_step_ms=No
     if rc != 0:
         tail = stderr.strip().splitlines()[-1:] or [""]
         out["vdw"] = {"unavailable": f"child exit {rc} after the electrostatics line: {tail[0][:200]}"}
+    if ours_esum is not None and "esum" in out:
+        out["esum_rel_vs_ours"] = abs(out["esum"] - ours_esum) / abs(ours_esum)
     par = out.get("parity") or {}
     # the reference computes in mixed precision: float pair math, fixed-point sums (the same tolerances our mixed build is held to)
-    out["parity_ok"] = bool(par and par["esum_rel"] < 1e-5 and par["uind_rms_debye"] < 1e-4 and par["grad_rms"] < 1e-2)
+    out["parity_ok"] = (bool(par["esum_rel"] < 1e-5 and par["uind_rms_debye"] < 1e-4 and par["grad_rms"] < 1e-2) if par
+                        else (bool(out["esum_rel_vs_ours"] < 1e-5) if "esum_rel_vs_ours" in out else None))
     out["build"] = "reference src/cu/**/*.cu unmodified, nvcc -O3 --use_fast_math sm_100, mixed precision (oracle/Makefile: cuda)"
     out["timing"] = "CUDA events on the reference's stream around each call, 30 calls after 5 warm-up, no L2 flush, same process-exclusive GPU"
     if ours_induce_ms:
@@ -697,8 +714,13 @@ def run_ours(args, rank, world, local_rank):
                                     "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
                                     "note": "vectorised-numpy port on one core, about two orders of magnitude slower than the reference's "
                                             "compiled host build would be (it cannot be linked here: no Fortran compiler); reported, not a target"}
-        if not args.no_cpu and not args.no_ref_cuda and world == 1 and args.workload == "dhfr2" and not args.vdw:
-            line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step))
+        if not args.no_cpu and not args.no_ref_cuda and world == 1 and not args.vdw:
+            if args.workload == "dhfr2":
+                line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step))
+            else:
+                system.xyz = xyz0
+                a.set_positions(xyz0)
+                line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step), system=system, ours_esum=float(a.energy(calc.v0)["esum"]))
         print(json.dumps(line))
     a.close()
     if dist is not None:
