@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round for the reference-CUDA comparator and the drop-in (about 3 GPU-minutes on one B200):
 #   gpurun --timeout 600 -- 'bash tools/gpu_refcuda.sh'
-# 1. the three comparator / drop-in tests (two are xfail until they have run once: an XPASS here means remove the marker);
+# 1. the three comparator / drop-in tests (all three passed their first runs in round 1, profiles/r01_refcuda*.json, r01_dropin*.json);
 # 2. ours vs the reference's CUDA build in one job, same conditions, on dhfr2, the 96k water box and the 424k protein box;
 # 3. the reference's launch list for one induce() + one energy step on dhfr2 (ncu, times cold-cache: shares only).
 mkdir -p gpurun_out
