@@ -5,7 +5,7 @@
 # 2. ours vs the reference's CUDA build in one job, same conditions, on dhfr2, the 96k water box and the 424k protein box;
 # 3. the reference's launch list for one induce() + one energy step on dhfr2 (ncu, times cold-cache: shares only).
 mkdir -p gpurun_out
-python -m pytest tests/test_zgpu_9_refcuda.py -m gpu -q -rxXs > gpurun_out/refcuda_tests.log 2>&1
+python -m pytest tests/test_zgpu_9_refcuda.py tests/test_polpair_golden.py -m gpu -q -rxXs > gpurun_out/refcuda_tests.log 2>&1      # polpair: XPASS = remove its xfail marker
 tail -5 gpurun_out/refcuda_tests.log
 for w in dhfr2 water96k dhfr424k; do
    timeout 300 python tools/same_job_compare.py 30 $w > gpurun_out/samejob_$w.json 2> gpurun_out/samejob_$w.err
