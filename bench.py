@@ -258,7 +258,9 @@ def ref_cuda_sample(ours_induce_ms=None, ours_energy_ms=None, ours_md_step_ms=No
     out["parity_ok"] = (bool(par["esum_rel"] < 1e-5 and par["uind_rms_debye"] < 1e-4 and par["grad_rms"] < 1e-2) if par
                         else (bool(out["esum_rel_vs_ours"] < 1e-5) if "esum_rel_vs_ours" in out else None))
     out["build"] = "reference src/cu/**/*.cu unmodified, nvcc -O3 --use_fast_math sm_100, mixed precision (oracle/Makefile: cuda)"
-    out["timing"] = "CUDA events on the reference's stream around each call, 30 calls after 5 warm-up, no L2 flush, same process-exclusive GPU"
+    out["timing"] = (f"CUDA events on the reference's stream around each call, {(out.get('induce_ms') or {}).get('reps', '?')} calls after "
+                     "warm-up, back to back (warm L2, which favours the reference: ours are timed with the L2 flushed), same GPU, right after "
+                     "our own measurements")
     if ours_induce_ms:
         out["ours_induce_ms"] = ours_induce_ms
         out["induce_speedup_vs_ref_cuda"] = out["induce_ms"]["median"] / ours_induce_ms
