@@ -728,9 +728,13 @@ def run_ours(args, rank, world, local_rank):
             if args.workload == "dhfr2":
                 line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step))
             else:
-                system.xyz = xyz0
-                a.set_positions(xyz0)
-                line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step), system=system, ours_esum=float(a.energy(calc.v0)["esum"]))
+                try:
+                    system.xyz = xyz0
+                    a.set_positions(xyz0)
+                    e_ours = float(a.energy(calc.v0)["esum"])
+                except Exception:      # noqa: BLE001
+                    e_ours = None
+                line["ref_cuda"] = ref_cuda_sample(ours_energy_ms=float(ms_step), system=system, ours_esum=e_ours)
         print(json.dumps(line))
     a.close()
     if dist is not None:
