@@ -55,6 +55,7 @@ void set_box(apx_ctx* c, const double* lvec)
    for (int i = 0; i < 9; ++i) {
       b.l[i] = (real)lvec[i];
       b.r[i] = (real)inv[i];
+      b.q[i] = (real)(lvec[i] / 4294967296.0);
    }
    b.lx = (real)lvec[0];
    b.ly = (real)lvec[4];
@@ -66,6 +67,7 @@ void set_box(apx_ctx* c, const double* lvec)
    b.orthogonal = off < 1e-12 ? 1 : 0;
    b.volume = (real)fabs(det);
    memcpy(c->opt.lvec, lvec, sizeof(double) * 9);
+   memcpy(c->recip_d, inv, sizeof(double) * 9);
 }
 
 template <class T, class S>
@@ -245,6 +247,7 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    if (c->nexcl > 0) {
       upload(c, c->excl_ik, sys->mdpu_ik, 2 * (size_t)c->nexcl);
       upload(c, c->excl_sc, sys->mdpu_scale, 4 * (size_t)c->nexcl);
+      upload(c, c->excl_sc_d, sys->mdpu_scale, 4 * (size_t)c->nexcl);
       c->excl_s.ensure(c->nexcl);
       for (int e = 0; e < c->nexcl; ++e)
          if (sys->mdpu_scale[4 * e + 3] != 1.0)
@@ -258,6 +261,12 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    c->permtmp.ensure(np);
    c->cubtmp.ensure(1 << 20);
    c->posd.ensure(np);
+#ifdef APX_DOUBLE
+   c->posq = c->posd.p;
+#else
+   c->posq_buf.ensure(np);
+   c->posq = c->posq_buf.p;
+#endif
    c->tpj.ensure(np);
    c->mp0.ensure(np);
    c->mp1.ensure(np);
@@ -376,8 +385,10 @@ void apx_destroy(apx_ctx* c)
       &c->polarity_o, &c->thole_o, &c->pdamp_o, &c->thlval, &c->excl_sc, &c->qfac, &c->bsmod1, &c->bsmod2, &c->bsmod3};
    for (auto* v : vecs)
       v->release();
+   c->excl_sc_d.release();
    c->xyz_d.release(), c->xyz_ref.release(), c->zaxis.release(), c->jpolar_o.release(), c->excl_ik.release();
    c->perm.release(), c->inv.release(), c->sortkey.release(), c->sortkey2.release(), c->permtmp.release(), c->cubtmp.release();
+   c->posq_buf.release();
    c->posd.release(), c->tpj.release(), c->mp0.release(), c->mp1.release(), c->mp2.release(), c->mpx_a.release(), c->mpx_b.release();
    c->blk_ctr.release(), c->blk_ext.release(), c->excl_s.release(), c->flags.release(), c->scal.release();
    c->rows.vstart.release(), c->rows.vcnt.release(), c->rows.vnbr.release(), c->rows.nbr.release();
@@ -401,6 +412,7 @@ int apx_set_positions(apx_ctx* c, const double* xyz)
    c->mpole_inited = 0;
    c->mpole_pme_valid = 0;
    c->induced_valid = 0;
+   c->md_forces_valid = 0;
    apx_list_refresh(c, false);
    API_END
 }
@@ -413,6 +425,7 @@ int apx_set_box(apx_ctx* c, const double lvec[9])
    apx_pcg_graphs_invalidate(c);
    apx_pme_setup(c);
    c->mpole_inited = 0;
+   c->md_forces_valid = 0;
    apx_list_refresh(c, true);
    API_END
 }
@@ -548,6 +561,7 @@ int apx_evalence(apx_ctx* c, int vers, apx_valence_result* out)
    CUDA_CHECK(cudaSetDevice(c->device));
    if (!apx_valence_on(c))
       APX_THROW("apx_evalence: no valence terms attached (apx_valence_attach)");
+   c->md_forces_valid = 0;
    apx_valence_enqueue(c, vers, c->stream, true);
    apx_valence_fetch(c, c->stream);
    CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -616,6 +630,7 @@ int apx_evdw(apx_ctx* c, int vers, apx_energy_result* out)
    if (!c->vdw.on)
       APX_THROW("apx_evdw: no vdW term attached (apx_vdw_attach)");
    ensure_ready(c);
+   c->md_forces_valid = 0;
    CUDA_CHECK(cudaMemsetAsync(c->arena_e.p, 0, c->arena_e_bytes, c->stream));
    apx_vdw_launch(c, vers);
    apx_vdw_join(c);

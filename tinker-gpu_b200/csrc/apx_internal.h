@@ -31,6 +31,17 @@ struct real3 {
    real x, y, z;
 };
 
+// Sorted per-step positions as the pair kernels read them.  Mixed build: 32-bit FRACTIONAL coordinates (resolution
+// L / 2^32 = 1.4e-8 A at 62 A) + the Thole damping length as float bits: the separation of a pair is an integer
+// subtraction that wraps (= the minimum image, exactly), converted to float AFTER the subtraction -- 2e-7 A for a 3 A pair
+// where wrapped float coordinates lose 4e-6 A each (tests/test_pairmath_host.py measures what that
+// is worth in force error).  Double build: wrapped Cartesian coordinates + pdamp, as posd.
+#ifdef APX_DOUBLE
+typedef real4 pos_t;
+#else
+typedef uint4 pos_t;
+#endif
+
 #define APX_WARP 32
 #define APX_BLOCK 128
 
@@ -84,6 +95,7 @@ struct Box {
    real ilx, ily, ilz;
    real l[9];               // lvec rows
    real r[9];               // recip rows
+   real q[9];               // l / 2^32: Cartesian separation from a difference of 32-bit fractional coordinates
    int orthogonal;
    real volume;
 };
@@ -198,6 +210,8 @@ struct apx_ctx {
    int thole_table = 0;                  // 1: per-pair lookup needed (polpair present)
    DevBuf<int> excl_ik;                  // [nx][2] caller order
    DevBuf<real> excl_sc;                 // [nx][4]
+   DevBuf<double> excl_sc_d;             // [nx][4] the same scale factors in double, for the listed-pair pass of mplar.cu
+   double recip_d[9] = {0};              // reciprocal cell vectors in double (rows), set with the box
    int nexcl = 0;
    int nexcl_u = 0;                      // exclusions whose u-scale != 1 (none in stock AMOEBA)
 
@@ -208,7 +222,9 @@ struct apx_ctx {
    DevBuf<int> permtmp;
    DevBuf<char> cubtmp;
    size_t cubtmp_bytes = 0;
-   DevBuf<real4> posd;                   // {x,y,z wrapped, pdamp}
+   DevBuf<real4> posd;                   // {x,y,z wrapped, pdamp}: list build / compaction, block boxes
+   DevBuf<uint4> posq_buf;               // mixed build: pos_t array (32-bit fractional coordinates + pdamp bits)
+   pos_t* posq = nullptr;                // what the pair kernels and the spline tables read (double build: = posd)
    DevBuf<real4> tpj;                    // {thole, polarity, 1/polarity, jpolar bits}
    DevBuf<real4> mp0, mp1;               // rpole {c,dx,dy,dz}, {qxx,qxy,qxz,qyy}
    DevBuf<real2> mp2;                    // {qyz,qzz}
@@ -302,6 +318,8 @@ struct apx_ctx {
    const int* skip = nullptr;            // device flag: kernels of speculative CG iterations return at once when set
    int mpole_inited = 0;
    int induced_valid = 0;
+   int md_forces_valid = 0;              // the accumulators hold the integrator's saved fast + slow forces at the current positions:
+                                         // cleared by every public call that rewrites them (md.cu recomputes them when clear)
 };
 
 #define APX_COUNT_LAUNCH(ctx) ((ctx)->stats.kernel_launches++)

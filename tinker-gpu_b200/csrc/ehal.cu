@@ -468,9 +468,12 @@ void apx_vdw_refresh(apx_ctx* c, bool rebuilt)
       APX_COUNT_LAUNCH(c);
    }
    apx_block_boxes(c, V.pred, V.ctr, V.ext);
+   // The Verlet range is NOT clipped to half the cell: a row lists partner k once, whichever image is nearest, and the pair
+   // kernel takes the minimum image of the current positions, so off <= L/2 < off + buffer loses no pair -- whereas a clipped
+   // range with the unclipped buffer/2 rebuild criterion could (a pair just outside the clipped range may enter the cutoff
+   // between rebuilds).  The block-box test is a lower bound on the minimum-image distance for any range.
    const real range = V.off + (real)c->opt.list_buffer;
-   const real half = (real)(0.5 * std::min(std::min(c->opt.lvec[0], c->opt.lvec[4]), c->opt.lvec[8]));
-   apx_rows_build_on(c, V.rows, V.pred, V.ctr, V.ext, std::min(range, half), V.exoff, V.exlist, V.exrange, false);
+   apx_rows_build_on(c, V.rows, V.pred, V.ctr, V.ext, range, V.exoff, V.exlist, V.exrange, false);
    c->stats.nverlet_vdw = V.rows.nverlet;
 }
 

@@ -26,31 +26,42 @@ __device__ __forceinline__ int as_int(real w)
 #endif
 }
 
+// An exclusion pass corrects pairs the row pass visited: membership must be decided exactly as the per-step compaction of
+// the rows decides it (rows.cu: k_rows_compact, minimum image of the wrapped float coordinates), not from the more
+// accurate separation the math uses -- a pair within rounding of the cutoff must not be corrected without being visited.
+__device__ __forceinline__ bool excl_in_rows(const Box& box, const real4* __restrict__ posd, int i, int k, real cut2)
+{
+   const real4 a = posd[i], b = posd[k];
+   real dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+   apx_image(box, dx, dy, dz);
+   return dx * dx + dy * dy + dz * dz <= cut2;
+}
+
 // -------------------------------------------------------------------------------------------
 // ufield: field of (ud, up) at every atom, Ewald real space or plain Thole-damped Coulomb
 // -------------------------------------------------------------------------------------------
 template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
-   const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const int* __restrict__ cnt, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F, const int* __restrict__ skip)
 {
    if (skip && skip[1])
       return;
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
-      const real4 pi = posd[i];
+      const pos_t pi = posq[i];
       const real4 qi = tpj[i];
       const int beg = vstart[i];
       const int len = act ? cnt[i] : 0;
       V3 fdi = v3(0, 0, 0), fpi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
-         const int k = nbr[beg + q];
-         const real4 pk = posd[k];
+         const int k = nbr[beg + q] & ROW_INDEX_MASK;
+         const pos_t pk = posq[k];
          const real4 qk = tpj[k];
          V3 a, b;
          load_dp(U, k, a, b);
-         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-         apx_image(box, dx, dy, dz);
+         real dx, dy, dz;
+         pair_delta(box, pi, pk, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
          const real rinv = r_rsqrt(r2);
          const real r = r2 * rinv, rr2 = rinv * rinv;
@@ -59,7 +70,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int a0, int a1, Box 
          if (EWALD)
             radial_ewald<3>(r, rinv, rr2, aewald, bn);
          const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-         thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+         thole_one_minus_lambda<3>(r, pos_w(pi), pos_w(pk), pg, om);
          const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
          const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
          const V3 R = v3(dx, dy, dz);
@@ -79,7 +90,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows(int a0, int a1, Box 
 // halves of the packed dipoles live in three different arrays.  k_uf_records interleaves what a pair needs
 // into ONE 48-byte record per atom, rec[3s] = (x,y,z,pdamp), rec[3s+1] = (d.x,d.y,d.z,p.x),
 // rec[3s+2] = (p.y,p.z,thole,polarity): two sectors and three 16-byte loads per neighbour.
-__global__ void k_uf_records(int n, const real4* __restrict__ posd, const real4* __restrict__ tpj, const real4* __restrict__ U,
+__global__ void k_uf_records(int n, const pos_t* __restrict__ posq, const real4* __restrict__ tpj, const real4* __restrict__ U,
    real4* __restrict__ rec, const int* __restrict__ skip)
 {
    if (skip && skip[1])
@@ -91,7 +102,7 @@ __global__ void k_uf_records(int n, const real4* __restrict__ posd, const real4*
    real4 b = U[2 * s + 1];
    b.z = q.x;
    b.w = q.y;
-   rec[3 * s] = posd[s];
+   rec[3 * s] = pos_as_real4(posq[s]);
    rec[3 * s + 1] = U[2 * s];
    rec[3 * s + 2] = b;
 }
@@ -105,16 +116,17 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows_rec(int a0, int a1, 
       return;
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
-      const real4 pi = rec[3 * i];
+      const pos_t pi = real4_as_pos(rec[3 * i]);
       const real thi = rec[3 * i + 2].z;
       const int beg = vstart[i];
       const int len = act ? cnt[i] : 0;
       V3 fdi = v3(0, 0, 0), fpi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
-         const int k = nbr[beg + q];
-         const real4 pk = rec[3 * k], ua = rec[3 * k + 1], ub = rec[3 * k + 2];
-         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-         apx_image(box, dx, dy, dz);
+         const int k = nbr[beg + q] & ROW_INDEX_MASK;
+         const pos_t pk = real4_as_pos(rec[3 * k]);
+         const real4 ua = rec[3 * k + 1], ub = rec[3 * k + 2];
+         real dx, dy, dz;
+         pair_delta(box, pi, pk, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
          const real rinv = r_rsqrt(r2);
          const real r = r2 * rinv, rr2 = rinv * rinv;
@@ -122,7 +134,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows_rec(int a0, int a1, 
          radial_coulomb<3>(rinv, rr2, rr);
          if (EWALD)
             radial_ewald<3>(r, rinv, rr2, aewald, bn);
-         thole_one_minus_lambda<3>(r, pi.w, pk.w, min(thi, ub.z), om);
+         thole_one_minus_lambda<3>(r, pos_w(pi), pos_w(pk), min(thi, ub.z), om);
          const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
          const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
          const V3 R = v3(dx, dy, dz);
@@ -138,7 +150,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_ufield_rows_rec(int a0, int a1, 
 
 // exclusion pass for ufield (only pairs whose u-scale != 1; empty for stock AMOEBA)
 template <bool TABLE>
-__global__ void k_ufield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_ufield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd, const pos_t* __restrict__ posq,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ U, real4* __restrict__ F)
 {
    int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,18 +162,18 @@ __global__ void k_ufield_excl(int nx, int a0, int a1, Box box, real cut2, const 
    const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;   // each GPU corrects its own atoms
    if (!own_i && !own_k)
       return;
-   real4 pi = posd[p.i], pk = posd[p.k];
-   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-   apx_image(box, dx, dy, dz);
-   real r2 = dx * dx + dy * dy + dz * dz;
-   if (r2 > cut2)
+   if (!excl_in_rows(box, posd, p.i, p.k, cut2))
       return;
+   const pos_t pi = posq[p.i], pk = posq[p.k];
+   real dx, dy, dz;
+   pair_delta(box, pi, pk, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
    real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
    real rr[3], om[3];
    radial_coulomb<3>(rinv, rr2, rr);
    real4 qi = tpj[p.i], qk = tpj[p.k];
    real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-   thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+   thole_one_minus_lambda<3>(r, pos_w(pi), pos_w(pk), pg, om);
    real B1 = p.u * (1 - om[1]) * rr[1], B2 = p.u * (1 - om[2]) * rr[2];
    V3 R = v3(dx, dy, dz);
    V3 udi, upi, udk, upk;
@@ -188,24 +200,24 @@ __device__ __forceinline__ Mpole load_mpole(const real4* mp0, const real4* mp1, 
 
 template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
-   const int* __restrict__ cnt, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const int* __restrict__ cnt, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
    const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign)
 {
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
-      const real4 pi = posd[i];
+      const pos_t pi = posq[i];
       const real4 qi = tpj[i];
       const int beg = vstart[i];
       const int len = act ? cnt[i] : 0;
       V3 fi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
-         const int k = nbr[beg + q];
-         const real4 pk = posd[k];
+         const int k = nbr[beg + q] & ROW_INDEX_MASK;
+         const pos_t pk = posq[k];
          const real4 qk = tpj[k];
          const Mpole mk = load_mpole(mp0, mp1, mp2, k);
-         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-         apx_image(box, dx, dy, dz);
+         real dx, dy, dz;
+         pair_delta(box, pi, pk, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
          const real rinv = r_rsqrt(r2);
          const real r = r2 * rinv, rr2 = rinv * rinv;
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box 
          if (EWALD)
             radial_ewald<4>(r, rinv, rr2, aewald, bn);
          const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-         thole_one_minus_lambda<4>(r, pi.w, pk.w, pg, om);
+         thole_one_minus_lambda<4>(r, pos_w(pi), pos_w(pk), pg, om);
          const real B1 = (EWALD ? bn[1] : rr[1]) - om[1] * rr[1];
          const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
          const real B3 = (EWALD ? bn[3] : rr[3]) - om[3] * rr[3];
@@ -235,7 +247,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box 
 
 // d-correction goes to fd, (p - d) correction to the delta array fpd
 template <bool TABLE>
-__global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd, const pos_t* __restrict__ posq,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0,
    const real4* __restrict__ mp1, const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd)
 {
@@ -248,18 +260,18 @@ __global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const 
    const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;
    if (!own_i && !own_k)
       return;
-   real4 pi = posd[p.i], pk = posd[p.k];
-   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-   apx_image(box, dx, dy, dz);
-   real r2 = dx * dx + dy * dy + dz * dz;
-   if (r2 > cut2)
+   if (!excl_in_rows(box, posd, p.i, p.k, cut2))
       return;
+   const pos_t pi = posq[p.i], pk = posq[p.k];
+   real dx, dy, dz;
+   pair_delta(box, pi, pk, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
    real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
    real rr[4], om[4];
    radial_coulomb<4>(rinv, rr2, rr);
    real4 qi = tpj[p.i], qk = tpj[p.k];
    real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-   thole_one_minus_lambda<4>(r, pi.w, pk.w, pg, om);
+   thole_one_minus_lambda<4>(r, pos_w(pi), pos_w(pk), pg, om);
    real L1 = (1 - om[1]) * rr[1], L2 = (1 - om[2]) * rr[2], L3 = (1 - om[3]) * rr[3];
    V3 R = v3(dx, dy, dz);
    Mpole mi = load_mpole(mp0, mp1, mp2, p.i), mk = load_mpole(mp0, mp1, mp2, p.k);
@@ -282,7 +294,7 @@ __global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const 
 // -------------------------------------------------------------------------------------------
 template <bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int ntot, Box box, real udiag, const int* __restrict__ vstart,
-   const int* __restrict__ cntu, const int* __restrict__ nbr, const real4* __restrict__ posd, const real4* __restrict__ tpj,
+   const int* __restrict__ cntu, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z, double* __restrict__ slot,
    const int* __restrict__ skip, PcgTest T)
 {
@@ -331,26 +343,26 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int
    double dot_d = 0, dot_p = 0;
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
-      const real4 pi = posd[i];
+      const pos_t pi = posq[i];
       const real4 qi = tpj[i];
       const int beg = vstart[i];
       const int len = (act && cntu) ? cntu[i] : 0;
       V3 zdi = v3(0, 0, 0), zpi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
-         const int k = nbr[beg + q];
-         const real4 pk = posd[k];
+         const int k = nbr[beg + q] & ROW_INDEX_MASK;
+         const pos_t pk = posq[k];
          const real4 qk = tpj[k];
          V3 a, b;
          load_dp(Rv, k, a, b);
-         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-         apx_image(box, dx, dy, dz);
+         real dx, dy, dz;
+         pair_delta(box, pi, pk, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
          const real rinv = r_rsqrt(r2);
          const real r = r2 * rinv, rr2 = rinv * rinv;
          real rr[3], om[3];
          radial_coulomb<3>(rinv, rr2, rr);
          const real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-         thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+         thole_one_minus_lambda<3>(r, pos_w(pi), pos_w(pk), pg, om);
          const real pp = qi.y * qk.y;
          const real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
          const V3 R = v3(dx, dy, dz);
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int
 }
 
 template <bool TABLE>
-__global__ void k_precond_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd,
+__global__ void k_precond_excl(int nx, int a0, int a1, Box box, real cut2, const PairExcl* __restrict__ ex, const real4* __restrict__ posd, const pos_t* __restrict__ posq,
    const real4* __restrict__ tpj, const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z,
    const int* __restrict__ skip)
 {
@@ -390,18 +402,18 @@ __global__ void k_precond_excl(int nx, int a0, int a1, Box box, real cut2, const
    const bool own_i = p.i >= a0 && p.i < a1, own_k = p.k >= a0 && p.k < a1;
    if (!own_i && !own_k)
       return;
-   real4 pi = posd[p.i], pk = posd[p.k];
-   real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-   apx_image(box, dx, dy, dz);
-   real r2 = dx * dx + dy * dy + dz * dz;
-   if (r2 > cut2)
+   if (!excl_in_rows(box, posd, p.i, p.k, cut2))
       return;
+   const pos_t pi = posq[p.i], pk = posq[p.k];
+   real dx, dy, dz;
+   pair_delta(box, pi, pk, dx, dy, dz);
+   real r2 = dx * dx + dy * dy + dz * dz;
    real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
    real rr[3], om[3];
    radial_coulomb<3>(rinv, rr2, rr);
    real4 qi = tpj[p.i], qk = tpj[p.k];
    real pg = TABLE ? thlval[as_int(qi.w) * nj + as_int(qk.w)] : min(qi.x, qk.x);
-   thole_one_minus_lambda<3>(r, pi.w, pk.w, pg, om);
+   thole_one_minus_lambda<3>(r, pos_w(pi), pos_w(pk), pg, om);
    real pp = qi.y * qk.y * p.u;
    real B1 = pp * (1 - om[1]) * rr[1], B2 = pp * (1 - om[2]) * rr[2];
    V3 R = v3(dx, dy, dz);
@@ -451,7 +463,7 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    // hardware fills the SMs in: the FFT CTAs of the other stream (512 threads, 33 KB) must always find room
    const size_t uf_smem = (size_t)c->uf_smem_kb * 1024;
 #define LAUNCH_UF(E, T)                                                                                                   \
-   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd, c->tpj,  \
+   k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq, c->tpj,  \
       c->thlval, c->opt.njpolar, U, F, c->skip)
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
@@ -468,7 +480,7 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    if (!tb && c->use_records) {
       // records of every atom a row can reach: the whole system (halo atoms included on several GPUs)
       c->uf_rec.ensure(3 * (size_t)c->npad);
-      k_uf_records<<<(c->n + 255) / 256, 256, 0, st>>>(c->n, c->posd, c->tpj, U, c->uf_rec, c->skip);
+      k_uf_records<<<(c->n + 255) / 256, 256, 0, st>>>(c->n, c->posq, c->tpj, U, c->uf_rec, c->skip);
       APX_COUNT_LAUNCH(c);
       if (ew)
          k_ufield_rows_rec<true, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->uf_rec, F, c->skip);
@@ -487,9 +499,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    if (c->nexcl_u > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_ufield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
+         k_ufield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval, c->opt.njpolar, U, F);
       else
-         k_ufield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar, U, F);
+         k_ufield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval, c->opt.njpolar, U, F);
       APX_COUNT_LAUNCH(c);
    }
 }
@@ -503,7 +515,7 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    bool tb = c->thole_table != 0;
    int grid = rows_grid<DF_G>(c);
 #define LAUNCH_DF(E, T)                                                                                                   \
-   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posd,  \
+   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq,  \
       c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, ew ? 0 : 1)
    // (rows may all be empty for a tiny system: the kernel still initialises fd / fpd)
    if (ew && tb) LAUNCH_DF(true, true);
@@ -515,10 +527,10 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    if (c->nexcl > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       else
-         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval,
+         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       APX_COUNT_LAUNCH(c);
    }
@@ -541,19 +553,19 @@ void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const P
    const int* cu = sparse ? L.cntu.p : nullptr;
    double* s1 = excl ? nullptr : slot;
    if (tb)
-      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
          c->opt.njpolar, Rv, Z, s1, c->skip, T);
    else
-      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posd, c->tpj, c->thlval,
+      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
          c->opt.njpolar, Rv, Z, s1, c->skip, T);
    APX_COUNT_LAUNCH(c);
    if (excl) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+         k_precond_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval, c->opt.njpolar,
             Rv, Z, c->skip);
       else
-         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->tpj, c->thlval, c->opt.njpolar,
+         k_precond_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval, c->opt.njpolar,
             Rv, Z, c->skip);
       APX_COUNT_LAUNCH(c);
       if (slot) {

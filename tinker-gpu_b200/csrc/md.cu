@@ -182,6 +182,24 @@ static void md_positions_changed(apx_ctx* c)
    apx_list_refresh(c, false);
 }
 
+// kick-off (RespaIntegrator::KickOff, src/md/integrator.cpp:205-222): fast gradient into the valence accumulator, slow gradient
+// into gx/gy/gz at the current positions.  The reference keeps private gx1/gx2 copies; here the saved forces live in the shared
+// accumulators, so any public call that rewrites them (energy, evdw, empole, epolar, evalence, set_positions, set_box) clears
+// md_forces_valid and the next apx_md_steps starts by recomputing them.
+static void md_kickoff_forces(apx_ctx* c)
+{
+   cudaStream_t st = c->stream;
+   if (!c->list_valid)
+      apx_list_refresh(c, true);
+   if (apx_valence_on(c)) {
+      apx_valence_enqueue(c, APX_ENERGY | APX_GRAD, st, true);
+      apx_valence_fetch(c, st);
+   }
+   apx_energy_result r;
+   apx_energy_impl_md(c, APX_V4, &r);
+   c->md_forces_valid = 1;
+}
+
 void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const apx_md_config* cfg)
 {
    if (c->dist.on)
@@ -217,20 +235,21 @@ void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const a
       CUDA_CHECK(cudaEventCreate(&M.t1));
    }
    cudaStream_t st = c->stream;
+   // the step graphs bake dt / dt_a into their kick and drift nodes: a second init must not replay the old coefficients
+   for (auto it = c->step_graphs.begin(); it != c->step_graphs.end();) {
+      if (it->first >= 0x3000 && it->first < 0x4000) {
+         if (it->second.exec)
+            cudaGraphExecDestroy(it->second.exec);
+         it = c->step_graphs.erase(it);
+      } else
+         ++it;
+   }
    CUDA_CHECK(cudaMemcpyAsync(M.vel.p, v.data(), sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
    CUDA_CHECK(cudaMemcpyAsync(M.massinv.p, mi.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
    CUDA_CHECK(cudaMemcpyAsync(M.mass.p, mass, sizeof(double) * n, cudaMemcpyHostToDevice, st));
    CUDA_CHECK(cudaMemsetAsync(M.sc.p, 0, sizeof(double) * 8, st));
    CUDA_CHECK(cudaStreamSynchronize(st));
-   // kick-off (RespaIntegrator::KickOff): fast gradient into the valence accumulator, slow gradient into gx/gy/gz
-   if (!c->list_valid)
-      apx_list_refresh(c, true);
-   if (apx_valence_on(c)) {
-      apx_valence_enqueue(c, APX_ENERGY | APX_GRAD, st, true);
-      apx_valence_fetch(c, st);
-   }
-   apx_energy_result r;
-   apx_energy_impl_md(c, APX_V4, &r);
+   md_kickoff_forces(c);
    // kinetic energy of the starting velocities
    md_kick(c, false, true, 0.0, 0.0, 0.0);
    k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, 0, M.nfree, M.dt, 1.0, 1.0, M.seed, 0ull, M.vel, M.sc);
@@ -253,6 +272,8 @@ void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out)
    memset(&r, 0, sizeof(r));
    apx_valence_result vr;
    memset(&vr, 0, sizeof(vr));
+   if (!c->md_forces_valid && nsteps > 0)
+      md_kickoff_forces(c);
    cudaEventRecord(M.t0, st);
    for (int s = 0; s < nsteps; ++s) {
       if (apx_graph_begin(c, 0x3000 + nr)) {
@@ -271,6 +292,7 @@ void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out)
       if (val)
          apx_valence_fetch(c, st);
       apx_energy_impl_md(c, APX_V4, &r);                                    // slow force: induce + emplar + ehal
+      c->md_forces_valid = 1;
       md_kick(c, false, true, 0.5 * dta, 0.5 * dt, 0.0);                    // velR2 + sum m v^2
       k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, M.thermostat, M.nfree, dt, M.tautemp > 0 ? M.tautemp : 1.0, M.kelvin, M.seed,
          M.step + 1, M.vel, M.sc);

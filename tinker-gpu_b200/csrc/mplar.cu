@@ -80,7 +80,7 @@ struct MplarArgs {
    const int* vstart;     // directed neighbor rows (rows.cu)
    const int* rcnt;
    const int* nbr;
-   const real4* posd;
+   const pos_t* posq;
    const real4* tpj;
    const real* thlval;
    int nj, table;
@@ -89,7 +89,7 @@ struct MplarArgs {
    const real2* mp2;
    const real* ud;
    const real* up;
-   int do_m, do_p, mutual, do_e, do_v, do_a, pair_ep;
+   int do_m, do_p, mutual, do_e, do_v, do_a, pair_ep, ewald;
    fixed_t* gx;
    fixed_t* gy;
    fixed_t* gz;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
    int nem = 0;
    ROWS_FOREACH_ATOM(G, A.a0, A.a1, i, l, act)
    {
-      const real4 pi = A.posd[i];
+      const pos_t pi = A.posq[i];
       const real4 qi = A.tpj[i];
       const Mpole mi = load_mpole(A.mp0, A.mp1, A.mp2, i);
       V3 udi = v3(0, 0, 0), upi = v3(0, 0, 0);
@@ -124,11 +124,13 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
       real emr = 0, epr = 0, v0 = 0, v1 = 0, v2 = 0, v3_ = 0, v4 = 0, v5 = 0;
       for (int q = l; q < len; q += G) {
          const int k = A.nbr[beg + q];
-         const real4 pk = A.posd[k];
+         if (k < 0)      // ROW_LISTED_FLAG: the pair belongs to k_mplar_listed
+            continue;
+         const pos_t pk = A.posq[k];
          const real4 qk = A.tpj[k];
          const Mpole mk = load_mpole(A.mp0, A.mp1, A.mp2, k);
-         real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-         apx_image(A.box, dx, dy, dz);
+         real dx, dy, dz;
+         pair_delta(A.box, pi, pk, dx, dy, dz);
          const real r2 = dx * dx + dy * dy + dz * dz;
          const real rinv = r_rsqrt(r2);
          const real r = r2 * rinv, rr2 = rinv * rinv;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
             const V3 ukp = v3(A.up[3 * k], A.up[3 * k + 1], A.up[3 * k + 2]);
             real om[6];
             const real pg = A.table ? A.thlval[as_int(qi.w) * A.nj + as_int(qk.w)] : min(qi.x, qk.x);
-            thole_one_minus_lambda<6>(r, pi.w, pk.w, pg, om);
+            thole_one_minus_lambda<6>(r, pos_w(pi), pos_w(pk), pg, om);
             #pragma unroll
             for (int j = 1; j < 5; ++j)
                B[j] -= om[j] * rr[j];
@@ -235,100 +237,144 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_mplar_rows(MplarArgs A)
    }
 }
 
-// exclusion pass: (scale-1) * undamped (m) or Thole-only (d,p,u) hierarchies
-template <bool DO_G>
-__global__ void k_mplar_excl(int nx, const PairExcl* __restrict__ ex, MplarArgs A)
+// Listed pairs (the exclusion / scaling table mdpuexclude: bonded-range and same-polarization-group pairs), evaluated ONCE
+// with their true scale factors and in DOUBLE in both builds:  B_n = bn_n - (1 - s lambda_n) rr_n.
+// The row pass skips these pairs (ROW_LISTED_FLAG).  Why not "all scales 1 in the row pass + (s-1) correction" as the field
+// kernels do: for a bonded pair at 1 A both parts are ~100 kcal/mol/A and cancel to a few; in float that cancellation alone
+// costs 1e-5 kcal/mol/A RMS of force error, the whole north-star tolerance (tests/test_pairmath_host.py measures it on the
+// CPU with this very header).  There are ~8 listed pairs per atom against ~140 unlisted ones, so double costs nothing here.
+// Separation from the caller-order f64 coordinates through perm[] with a double-precision minimum image.
+struct ListedD {
+   double l[9], r[9];     // cell vectors / reciprocal vectors (rows)
+   const double* xyz;     // [n][3] caller order
+   const int* perm;       // sorted slot -> caller index
+   const double* sc;      // [nx][4] m, d, p, u of listed pair e (same order as the PairExcl records)
+   double cut2, aewald, f;
+};
+
+__device__ __forceinline__ pm64::Mpole load_mpole_d(const real4* mp0, const real4* mp1, const real2* mp2, int s)
 {
+   real4 a = mp0[s], b = mp1[s];
+   real2 c = mp2[s];
+   pm64::Mpole m;
+   m.c = a.x, m.dx = a.y, m.dy = a.z, m.dz = a.w;
+   m.qxx = b.x, m.qxy = b.y, m.qxz = b.z, m.qyy = b.w, m.qyz = c.x, m.qzz = c.y;
+   return m;
+}
+__device__ __forceinline__ pm64::V3 load3_d(const real* v, int s) { return pm64::v3((double)v[3 * s], (double)v[3 * s + 1], (double)v[3 * s + 2]); }
+__device__ __forceinline__ void atomic_fixed3_d(fixed_t* gx, fixed_t* gy, fixed_t* gz, int s, pm64::V3 v)
+{
+   atomic_fixed_d(gx + s, v.x);
+   atomic_fixed_d(gy + s, v.y);
+   atomic_fixed_d(gz + s, v.z);
+}
+
+template <bool DO_G>
+__global__ void __launch_bounds__(128) k_mplar_listed(int nx, const PairExcl* __restrict__ ex, MplarArgs A, ListedD D)
+{
+   typedef pm64::V3 W3;
    int e = blockIdx.x * blockDim.x + threadIdx.x;
    double em = 0, ep = 0, v[6] = {0, 0, 0, 0, 0, 0};
    int dn = 0;
    if (e < nx) {
-      PairExcl p = ex[e];
-      real4 pi = A.posd[p.i], pk = A.posd[p.k];
-      real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
-      apx_image(A.box, dx, dy, dz);
-      real r2 = dx * dx + dy * dy + dz * dz;
+      const PairExcl p = ex[e];
       // several GPUs: a pair is handled by the owner(s) of its atoms, each writing only to its own
       // atom; the owner of p.i also books the pair's energy, virial and count
       const bool own_i = p.i >= A.a0 && p.i < A.a1, own_k = p.k >= A.a0 && p.k < A.a1;
-      if (r2 <= A.cut2 && (own_i || own_k)) {
-         real rinv = r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
-         real rr[6], B[6];
-         radial_coulomb<6>(rinv, rr2, rr);
-         V3 R = v3(dx, dy, dz);
-         Mpole mi = load_mpole(A.mp0, A.mp1, A.mp2, p.i), mk = load_mpole(A.mp0, A.mp1, A.mp2, p.k);
-         V3 g = v3(0, 0, 0), tqi = v3(0, 0, 0), tqk = v3(0, 0, 0);
-         if (own_i && (A.do_m ? p.m == (real)-1 : p.p == (real)-1))
-            dn = -1;
-         if (A.do_m && p.m != 0) {
+      double Rx = 0, Ry = 0, Rz = 0, r2 = 1e300;
+      if (own_i || own_k) {
+         const int ci = D.perm[p.i], ck = D.perm[p.k];
+         const double d0 = D.xyz[3 * ck] - D.xyz[3 * ci], d1 = D.xyz[3 * ck + 1] - D.xyz[3 * ci + 1], d2 = D.xyz[3 * ck + 2] - D.xyz[3 * ci + 2];
+         double f1 = d0 * D.r[0] + d1 * D.r[1] + d2 * D.r[2];
+         double f2 = d0 * D.r[3] + d1 * D.r[4] + d2 * D.r[5];
+         double f3 = d0 * D.r[6] + d1 * D.r[7] + d2 * D.r[8];
+         f1 -= rint(f1), f2 -= rint(f2), f3 -= rint(f3);
+         Rx = f1 * D.l[0] + f2 * D.l[1] + f3 * D.l[2];
+         Ry = f1 * D.l[3] + f2 * D.l[4] + f3 * D.l[5];
+         Rz = f1 * D.l[6] + f2 * D.l[7] + f3 * D.l[8];
+         r2 = Rx * Rx + Ry * Ry + Rz * Rz;
+      }
+      if (r2 <= D.cut2) {
+         const double sm = D.sc[4 * e], sd = D.sc[4 * e + 1], sp = D.sc[4 * e + 2], su = D.sc[4 * e + 3];
+         const double rinv = pm64::r_rsqrt(r2), r = r2 * rinv, rr2 = rinv * rinv;
+         double rr[6], bn[6], B[6];
+         pm64::radial_coulomb<6>(rinv, rr2, rr);
+         if (A.ewald)
+            pm64::radial_ewald<6>(r, rinv, rr2, D.aewald, bn);
+         else {
             #pragma unroll
             for (int q = 0; q < 6; ++q)
-               B[q] = p.m * rr[q];
-            V3 g1, t1, t2;
-            real U = pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
+               bn[q] = rr[q];
+         }
+         const W3 R = pm64::v3(Rx, Ry, Rz);
+         const pm64::Mpole mi = load_mpole_d(A.mp0, A.mp1, A.mp2, p.i), mk = load_mpole_d(A.mp0, A.mp1, A.mp2, p.k);
+         W3 g = pm64::v3(0, 0, 0), tqi = pm64::v3(0, 0, 0), tqk = pm64::v3(0, 0, 0);
+         if (own_i && (A.do_m ? sm != 0.0 : sp != 0.0))
+            dn = 1;
+         if (A.do_m) {
+            #pragma unroll
+            for (int q = 0; q < 6; ++q)
+               B[q] = bn[q] - (1.0 - sm) * rr[q];
+            W3 g1, t1, t2;
+            const double U = pm64::pair_mm<DO_G>(R, mi, mk, B, g1, t1, t2);
             if (own_i)
-               em = (double)(A.f * U);
+               em = D.f * U;
             if (DO_G) {
                g += g1;
                tqi += t1;
                tqk += t2;
             }
          }
-         if (A.do_p && (p.d != 0 || p.p != 0 || p.u != 0)) {
-            real om[6];
-            real4 qi = A.tpj[p.i], qk = A.tpj[p.k];
-            real pg = A.table ? A.thlval[as_int(qi.w) * A.nj + as_int(qk.w)] : min(qi.x, qk.x);
-            thole_one_minus_lambda<6>(r, pi.w, pk.w, pg, om);
-            real L[6];
+         if (A.do_p) {
+            double om[6], lam[6];
+            const real4 qi = A.tpj[p.i], qk = A.tpj[p.k];
+            const double pg = A.table ? (double)A.thlval[as_int(qi.w) * A.nj + as_int(qk.w)] : (double)min(qi.x, qk.x);
+            pm64::thole_one_minus_lambda<6>(r, (double)pos_w(A.posq[p.i]), (double)pos_w(A.posq[p.k]), pg, om);
             #pragma unroll
             for (int q = 0; q < 6; ++q)
-               L[q] = (1 - om[q]) * rr[q];
-            L[0] = 0;
-            V3 udi = v3(A.ud[3 * p.i], A.ud[3 * p.i + 1], A.ud[3 * p.i + 2]), upi = v3(A.up[3 * p.i], A.up[3 * p.i + 1], A.up[3 * p.i + 2]);
-            V3 udk = v3(A.ud[3 * p.k], A.ud[3 * p.k + 1], A.ud[3 * p.k + 2]), upk = v3(A.up[3 * p.k], A.up[3 * p.k + 1], A.up[3 * p.k + 2]);
+               lam[q] = (1.0 - om[q]) * rr[q];
+            const W3 udi = load3_d(A.ud, p.i), upi = load3_d(A.up, p.i), udk = load3_d(A.ud, p.k), upk = load3_d(A.up, p.k);
             // p-scaled: permanent with ud ; d-scaled: permanent with up
             for (int pass = 0; pass < 2; ++pass) {
-               real sc = pass == 0 ? p.p : p.d;
-               if (sc == 0)
-                  continue;
+               const double sc = pass == 0 ? sp : sd;
                #pragma unroll
                for (int q = 0; q < 6; ++q)
-                  B[q] = (real)0.5 * sc * L[q];
-               V3 uk = pass == 0 ? udk : upk, ui = pass == 0 ? udi : upi;
-               V3 g1, g2, t1, t2;
-               real U = pair_mu<DO_G>(R, mi, uk, B, g1, t1) + pair_um<DO_G>(R, ui, mk, B, g2, t2);
+                  B[q] = 0.5 * (bn[q] - rr[q] + sc * lam[q]);
+               const W3 uk = pass == 0 ? udk : upk, ui = pass == 0 ? udi : upi;
+               W3 g1, g2, t1, t2;
+               const double U = pm64::pair_mu<DO_G>(R, mi, uk, B, g1, t1) + pm64::pair_um<DO_G>(R, ui, mk, B, g2, t2);
                if (pass == 0 && A.pair_ep && own_i)
-                  ep = (double)(A.f * U);
+                  ep = D.f * U;
                if (DO_G) {
                   g += g1 + g2;
                   tqi += t1;
                   tqk += t2;
                }
             }
-            if (DO_G && A.mutual && p.u != 0) {
+            if (DO_G && A.mutual) {
                #pragma unroll
                for (int q = 0; q < 6; ++q)
-                  B[q] = (real)0.5 * p.u * L[q];
-               g += pair_uu_grad(R, udi, upk, B) + pair_uu_grad(R, upi, udk, B);
+                  B[q] = 0.5 * (bn[q] - rr[q] + su * lam[q]);
+               g += pm64::pair_uu_grad(R, udi, upk, B) + pm64::pair_uu_grad(R, upi, udk, B);
             }
          }
          if (DO_G) {
-            g = A.f * g;
+            g = D.f * g;
             if (own_i) {
-               atomic_fixed3(A.gx, A.gy, A.gz, p.i, (real)-1 * g);
-               atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.i, A.f * tqi);
+               atomic_fixed3_d(A.gx, A.gy, A.gz, p.i, -1.0 * g);
+               atomic_fixed3_d(A.trq, A.trq + 1, A.trq + 2, 3 * p.i, D.f * tqi);
             }
             if (own_k) {
-               atomic_fixed3(A.gx, A.gy, A.gz, p.k, g);
-               atomic_fixed3(A.trq, A.trq + 1, A.trq + 2, 3 * p.k, A.f * tqk);
+               atomic_fixed3_d(A.gx, A.gy, A.gz, p.k, g);
+               atomic_fixed3_d(A.trq, A.trq + 1, A.trq + 2, 3 * p.k, D.f * tqk);
             }
             if (A.do_v && own_i) {
-               v[0] = (double)(R.x * g.x);
-               v[1] = (double)((real)0.5 * (R.y * g.x + R.x * g.y));
-               v[2] = (double)((real)0.5 * (R.z * g.x + R.x * g.z));
-               v[3] = (double)(R.y * g.y);
-               v[4] = (double)((real)0.5 * (R.z * g.y + R.y * g.z));
-               v[5] = (double)(R.z * g.z);
+               v[0] = R.x * g.x;
+               v[1] = 0.5 * (R.y * g.x + R.x * g.y);
+               v[2] = 0.5 * (R.z * g.x + R.x * g.z);
+               v[3] = R.y * g.y;
+               v[4] = 0.5 * (R.z * g.y + R.y * g.z);
+               v[5] = R.z * g.z;
             }
          }
       }
@@ -694,6 +740,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    do_p = do_p && c->opt.use_polar;
    const bool ewald = c->opt.use_ewald != 0;
    const bool pair_ep = do_e && do_a;          // ANALYZE: pairwise polarization energy; otherwise dot product
+   c->md_forces_valid = 0;                     // the accumulators are rewritten (md.cu sets the flag again after its own calls)
    cudaEventRecord(c->ev2, st);
    if (apx_graph_begin(c, 0x1000)) {
       apx_rotpole(c);      // mpoleInit(vers) runs on every energy() call in the reference (src/amoeba/emplar.cpp:12)
@@ -740,7 +787,8 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    A.vstart = c->rows.vstart;
    A.rcnt = c->rows.cnt;
    A.nbr = c->rows.nbr;
-   A.posd = c->posd;
+   A.posq = c->posq;
+   A.ewald = ewald ? 1 : 0;
    A.tpj = c->tpj;
    A.thlval = c->thlval;
    A.nj = c->opt.njpolar;
@@ -772,9 +820,14 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       else k_mplar_rows<false, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
       APX_COUNT_LAUNCH(c);
       if (c->nexcl > 0) {
+         ListedD D;
+         for (int q = 0; q < 9; ++q)
+            D.l[q] = c->opt.lvec[q], D.r[q] = c->recip_d[q];
+         D.xyz = c->xyz_d, D.perm = c->perm, D.sc = c->excl_sc_d;
+         D.cut2 = c->opt.cutoff * c->opt.cutoff, D.aewald = c->opt.aewald, D.f = c->opt.electric / c->opt.dielec;
          int g = (c->nexcl + 127) / 128;
-         if (do_g) k_mplar_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A);
-         else k_mplar_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A);
+         if (do_g) k_mplar_listed<true><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A, D);
+         else k_mplar_listed<false><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A, D);
          APX_COUNT_LAUNCH(c);
       }
    }

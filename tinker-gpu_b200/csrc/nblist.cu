@@ -55,22 +55,25 @@ __global__ void k_sortkeys(int n, Box b, int nslab, const double* __restrict__ x
 
 // per-step: wrapped positions into sorted slots (also used at rebuild)
 __global__ void k_gather_pos(int n, int npad, Box b, const double* __restrict__ xyz, const int* __restrict__ perm,
-   const real* __restrict__ pdamp, real4* __restrict__ posd)
+   const real* __restrict__ pdamp, real4* __restrict__ posd, pos_t* __restrict__ posq)
 {
    int s = blockIdx.x * blockDim.x + threadIdx.x;
    if (s >= npad)
       return;
    real4 o;
+   unsigned q1 = 0, q2 = 0, q3 = 0;
    if (s < n) {
       int i = perm[s];
-      real fx, fy, fz;
-      wrap_pos(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], o.x, o.y, o.z, fx, fy, fz);
+      wrap_pos_q(b, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], o.x, o.y, o.z, q1, q2, q3);
       o.w = pdamp[i];
    } else {
       o.x = o.y = o.z = 0;
       o.w = 0;
    }
    posd[s] = o;
+#ifndef APX_DOUBLE
+   posq[s] = make_uint4(q1, q2, q3, __float_as_uint(o.w));
+#endif
 }
 
 __global__ void k_gather_static(int n, int npad, const int* __restrict__ perm, int* __restrict__ inv,
@@ -172,7 +175,7 @@ void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext)
 void apx_update_sorted_positions(apx_ctx* c)
 {
    int g = (c->npad + 255) / 256;
-   k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);
+   k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
    APX_COUNT_LAUNCH(c);
    apx_pme_fill_theta(c);
 }
@@ -219,7 +222,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
       c->a0 = 0, c->a1 = n;
    // 2. sorted copies of per-atom data
    int g = (c->npad + 255) / 256;
-   k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd);
+   k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
    k_gather_static<<<g, 256, 0, c->stream>>>(n, c->npad, c->perm, c->inv, c->thole_o, c->polarity_o, c->jpolar_o, c->tpj);
    if (c->nexcl)
       k_excl_sorted<<<(c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_ik, c->excl_sc, c->inv, c->excl_s);

@@ -68,20 +68,21 @@ struct Stencil {
 // 16 real4 per atom -- [5*d + p] = {theta and its first three derivatives} of stencil point p along
 // axis d (15 entries), [15] = the three stencil origins as integer bit patterns (bsplineFill of the
 // reference, src/cu/pme.cu, keeps the same information as thetai1..3 + igrid).
-__global__ void k_theta_fill(int n, Box b, int n1, int n2, int n3, const real4* __restrict__ posd, real4* __restrict__ theta)
+__global__ void k_theta_fill(int n, Box b, int n1, int n2, int n3, const pos_t* __restrict__ posq, real4* __restrict__ theta)
 {
    int t = blockIdx.x * blockDim.x + threadIdx.x;
    int s = t >> 2, d = t & 3;
    if (s >= n)
       return;
-   real4 pos = posd[s];
+   const pos_t pos = posq[s];
+   int nf[3] = {n1, n2, n3};
+   int ig[3];
+   real ww[3];
+#ifdef APX_DOUBLE
    real f[3];
    f[0] = pos.x * b.r[0] + pos.y * b.r[1] + pos.z * b.r[2];
    f[1] = pos.x * b.r[3] + pos.y * b.r[4] + pos.z * b.r[5];
    f[2] = pos.x * b.r[6] + pos.y * b.r[7] + pos.z * b.r[8];
-   int nf[3] = {n1, n2, n3};
-   int ig[3];
-   real ww[3];
    #pragma unroll
    for (int q = 0; q < 3; ++q) {
       real w = f[q] + (real)0.5;
@@ -93,6 +94,20 @@ __global__ void k_theta_fill(int n, Box b, int n1, int n2, int n3, const real4* 
       ii -= 4;
       ig[q] = ii < 0 ? ii + nf[q] : ii;
    }
+#else
+   // 32-bit fractional coordinates: w = f + 1/2 (mod 1) is an integer add that wraps, nfft*w a 32x32 -> 64 bit product whose
+   // high word is the grid cell and whose low word is the position inside the cell, exact to 2^-32 of a cell (float positions
+   // lose 4e-6 of a cell at nfft = 64, which shows up in the reciprocal-space forces)
+   const unsigned qq[3] = {pos.x, pos.y, pos.z};
+   #pragma unroll
+   for (int q = 0; q < 3; ++q) {
+      const unsigned qs = qq[q] + 0x80000000u;
+      int ii = (int)__umulhi(qs, (unsigned)nf[q]);
+      ww[q] = (real)(qs * (unsigned)nf[q]) * (real)2.3283064365386963e-10;
+      ii -= 4;
+      ig[q] = ii < 0 ? ii + nf[q] : ii;
+   }
+#endif
    if (d < 3) {
       real th[5][4];
       bspline5(d == 0 ? ww[0] : (d == 1 ? ww[1] : ww[2]), th);
@@ -818,7 +833,7 @@ void apx_pme_fill_theta(apx_ctx* c)
    const int a0 = c->a0, no = c->a1 - c->a0;
    c->theta.ensure(16 * (size_t)c->npad);
    if (no > 0)
-      k_theta_fill<<<(4 * no + 127) / 128, 128, 0, c->stream>>>(no, c->box, c->nfft1, c->nfft2, c->nfft3, c->posd + a0,
+      k_theta_fill<<<(4 * no + 127) / 128, 128, 0, c->stream>>>(no, c->box, c->nfft1, c->nfft2, c->nfft3, c->posq + a0,
          c->theta + 16 * (size_t)a0);
    APX_COUNT_LAUNCH(c);
 }

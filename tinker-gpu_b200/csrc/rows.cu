@@ -12,6 +12,7 @@
 //                     the preconditioner range (usolve-cutoff) first
 #include "apx_internal.h"
 #include "pairmath.cuh"
+#include "rows.cuh"
 #include <cub/cub.cuh>
 #include <algorithm>
 
@@ -211,10 +212,10 @@ __global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real
          continue;
       for (int q0 = beg; q0 < end; q0 += 32) {
          int q = q0 + lane;
-         int k = q < end ? vnbr[q] : -1;
+         const int k = q < end ? vnbr[q] : 0;      // may carry ROW_LISTED_FLAG: copied as is
          bool ok = false;
-         if (k >= 0) {
-            real4 pk = posd[k];
+         if (q < end) {
+            real4 pk = posd[k & ROW_INDEX_MASK];
             real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
             apx_image(b, dx, dy, dz);
             real r2 = dx * dx + dy * dy + dz * dz;
@@ -237,11 +238,41 @@ __global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real
       }
    }
 }
+// One thread per listed pair and direction: find k in the (ascending) Verlet row of i and set the flag bit.  Runs once per list
+// build, before anything reads the rows; a pair farther apart than the Verlet range is simply not found.
+__global__ void k_rows_flag_listed(int nx, const PairExcl* __restrict__ ex, int a0, int a1, const int* __restrict__ vstart,
+   int* __restrict__ vnbr)
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= 2 * nx)
+      return;
+   const PairExcl p = ex[t >> 1];
+   const int i = (t & 1) ? p.k : p.i, k = (t & 1) ? p.i : p.k;
+   if (i < a0 || i >= a1)
+      return;
+   int lo = vstart[i], hi = vstart[i + 1] - 1;
+   while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const int v = vnbr[mid] & ROW_INDEX_MASK;      // (two listed pairs never share a slot, so a concurrent flag is harmless)
+      if (v == k) {
+         vnbr[mid] = (int)((unsigned)k | ROW_LISTED_FLAG);
+         return;
+      }
+      if (v < k)
+         lo = mid + 1;
+      else
+         hi = mid - 1;
+   }
+}
 } // namespace
 
 void apx_rows_build(apx_ctx* c)
 {
    apx_rows_build_on(c, c->rows, c->posd, c->blk_ctr, c->blk_ext, c->list_cutoff + c->list_buffer, nullptr, nullptr, 0, true);
+   if (c->nexcl > 0) {
+      k_rows_flag_listed<<<(2 * c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_s, c->a0, c->a1, c->rows.vstart, c->rows.vnbr);
+      APX_COUNT_LAUNCH(c);
+   }
 }
 
 // Verlet rows of the positions `pos` (sorted order, block boxes ctr/ext) within `range`.  exoff/exlist: optional CSR (caller

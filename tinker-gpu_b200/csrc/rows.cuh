@@ -5,6 +5,11 @@
 #include "pairmath.cuh"
 
 #define ROWS_BLOCK 128
+// Row entries of the electrostatics list carry a flag in the sign bit: the pair is LISTED in the exclusion / scaling table
+// (mdpuexclude).  The field kernels mask it off; the fused energy kernel skips flagged entries, because listed pairs are
+// evaluated once, with their true scale factors, in double by the exclusion pass (mplar.cu).
+#define ROW_INDEX_MASK 0x7fffffff
+#define ROW_LISTED_FLAG 0x80000000u
 
 // for (atoms a0 <= i < a1 of this lane group): `i` = atom (clamped to a1-1), `l` = lane in group,
 // `act` = i is real.  [a0,a1) is the sorted range this GPU owns (the whole system on one GPU).
