@@ -7,7 +7,7 @@
  * the ~200-line adapter TU that defines the reference's *_cu symbols on top of it.
  *
  * Each entry point cites the reference interface it replaces.  All pointers are plain
- * host pointers unless the name ends in _dev.  Arrays are in the CALLER's atom order
+ * host pointers unless the name ends in _dev (device memory, see the block further down).  Arrays are in the CALLER's atom order
  * (the library keeps its own spatially sorted copies).  Return value: 0 on success,
  * non-zero on error with the message available from apx_last_error() -- the C-ABI
  * image of the reference's TINKER_THROW / FatalError (include/tool/error.h:16-45).
@@ -265,6 +265,33 @@ int apx_md_get_state(apx_ctx* ctx, double* xyz /* [n][3] or NULL */, double* vel
 
 /* copyGradient: src/egvop.cpp:64-111 (fixed -> double, caller's order) */
 int apx_get_gradient(apx_ctx* ctx, double* grad /* [n][3] */);
+
+/* ---- device-pointer entry points: what the reference's *_cu operators are handed (csrc/devio.cu).
+ * Arrays are DEVICE memory in the caller's atom order.  elem_bytes: 4 = float, 8 = double (the reference's `real`,
+ * include/ff/precision.h).  `stream` is the caller's cudaStream_t (NULL = the legacy default stream; the reference's g::s0):
+ * the call is ordered after the work already enqueued there and its results are visible to what is enqueued there next.
+ * Nothing is staged through host memory; outputs that the reference ACCUMULATES into (gradient, energy and virial buffers:
+ * SURVEY.md 8b "Ownership", src/energy.cpp:333-446) are added to, never assigned.  Single-GPU contexts only. */
+enum { APX_DEV_FIXED = 0, APX_DEV_I32 = 1, APX_DEV_F32 = 4, APX_DEV_F64 = 8 }; /* 2^32 fixed point in unsigned long long (grad_prec / energy
+                                                                 buffers of the mixed build, include/ff/precision.h:68-106) */
+/* copyPosToXyz + nblistRefresh from the reference's x, y, z device arrays (include/ff/atom.h:39-45) */
+int apx_set_positions_dev(apx_ctx* ctx, const void* x, const void* y, const void* z, int elem_bytes, void* stream);
+/* dfieldEwaldRecipSelfP2_cu + dfieldEwaldReal_cu / dfieldNonEwald_cu: src/amoeba/field.cpp:8-63 */
+int apx_dfield_dev(apx_ctx* ctx, void* field, void* fieldp, int elem_bytes, void* stream);
+/* ufieldEwaldRecipSelfP1_cu + ufieldEwaldReal_cu / ufieldNonEwald_cu: src/amoeba/field.cpp:67-117 */
+int apx_ufield_dev(apx_ctx* ctx, const void* uind, const void* uinp, void* field, void* fieldp, int elem_bytes, void* stream);
+/* sparsePrecondApply_cu / diagPrecond_cu: src/amoeba/induce.cpp:12-25 */
+int apx_precond_dev(apx_ctx* ctx, const void* rsd, const void* rsdp, void* zrsd, void* zrsdp, int elem_bytes, void* stream);
+/* induceMutualPcg1_cu(uind, uinp): src/amoeba/induce.cpp:73; udir / udirp may be NULL */
+int apx_induce_dev(apx_ctx* ctx, void* uind, void* uinp, void* udir, void* udirp, int elem_bytes, void* stream);
+int apx_get_uind_dev(apx_ctx* ctx, void* uind, void* uinp, void* udir, void* udirp, int elem_bytes, void* stream);
+/* g[i] += dE/dx_i of the last energy / empole / epolar / evdw call: what emplar_cu, epolar*_cu, ehal_cu do to
+ * gx_elec / gx_vdw (src/amoeba/emplar.cpp:10-28, src/energy.cpp:443-444); kind = APX_DEV_* */
+int apx_add_gradient_dev(apx_ctx* ctx, void* gx, void* gy, void* gz, int kind, void* stream);
+/* dst[q] += vals[q], q < count <= 16: one slot of an energy buffer (count 1), of a virial buffer (count 6: xx yx zx yy zy
+ * zz, src/energybuffer.cpp:81-94) or of a count buffer (APX_DEV_I32), which energyReduce / virialReduce / countReduce then
+ * sum (src/energy.cpp:345-348,371-374) */
+int apx_add_scalars_dev(apx_ctx* ctx, void* dst, const double* vals, int count, int kind, void* stream);
 
 /* PME operators exposed for parity tests: gridMpole/gridUind + fftfront + pmeConv + fftback
  * + fphiMpole/fphiUind2 (src/pme.cpp:229-351).  Output in fractional coordinates. */

@@ -11,7 +11,8 @@
 //
 // State convention: the reference keeps its arrays in process-global device pointers (include/ff/modamoeba.h); libapx keeps
 // its own resident copies behind the context.  Where a front-end reads a global after the call (uind / uinp / udir / udirp,
-// field / fieldp work arrays, the gradient and energy accumulators), the stub copies the library's result into it.
+// field / fieldp work arrays) the stub has the library write it device to device; the gradient, energy and virial
+// accumulators are ADDED to on the device (the *_dev entry points of include/apx.h) -- no stub stages through host memory.
 #include "apx.h"
 #include "ff/amoeba/induce.h"
 #include "ff/atom.h"
@@ -19,8 +20,9 @@
 #include "ff/modamoeba.h"
 #include "ff/pme.h"
 #include "tool/darray.h"
+#include "tool/cudalib.h"
 #include "tool/error.h"
-#include <vector>
+#include <type_traits>
 
 namespace tinker {
 static apx_ctx* g_apx = nullptr;
@@ -50,44 +52,48 @@ apx_ctx* apxAdapterContext() { return g_apx; }
 void apxAdapterSetPositions(const double* xyz) { chk(apx_set_positions(g_apx, xyz)); }
 
 namespace {
-struct Host3 {      // host double [n][3] staging of one of the reference's device real [n][3] arrays
-   std::vector<double> v;
-   Host3()
-      : v(3 * (size_t)n)
-   {}
-   void from(const real (*dev)[3])
-   {
-      darray::copyout(g::q0, n, v.data(), dev);
-      waitFor(g::q0);
-   }
-   void to(real (*dev)[3]) const { darray::copyin(g::q0, n, dev, v.data()); }
-};
+constexpr int EB = (int)sizeof(real);      // element size of the reference's real (*)[3] device arrays
+// grad_prec / the energy and virial buffer element of this build (include/ff/precision.h:68-106, ff/energybuffer.h)
+template <class T>
+constexpr int devKind()
+{
+   return std::is_same<T, fixed>::value ? APX_DEV_FIXED : (sizeof(T) == 4 ? APX_DEV_F32 : APX_DEV_F64);
 }
+void* stream0() { return (void*)g::s0; }      // the stream the reference's front-ends enqueue on
+}
+
+// copyPosToXyz + nblistRefresh (src/nblist.cpp:521) from the reference's own x / y / z device arrays: no host copy
+void apxAdapterRefreshPositions() { chk(apx_set_positions_dev(g_apx, x, y, z, EB, stream0())); }
+
+// ---- *DataBinding_cu (src/cu/amoeba/binding.cu:11-52, called from src/elec.cpp:53 and src/amoeba/epolar.cpp:24): the
+//      reference mirrors its device pointers into __device__ globals (d::rpole, d::pdamp, ...) for its own kernels.  The
+//      library keeps its state behind the context, so there is nothing to bind -- but the symbols must exist once
+//      src/cu/amoeba/binding.cu is dropped from the build.
+void mpoleDataBinding_cu(RcOp) {}
+void epolarDataBinding_cu(RcOp) {}
 
 // ---- src/amoeba/mpole.cpp:8-26
 void chkpole_cu() {}      // chkpole + rotpole + rpoleToCmp are one kernel inside the library (frames.cu)
 void rotpole_cu() { chk(apx_mpole_init(g_apx)); }
 void rpoleToCmp_cu() {}
-void torque_cu(int, grad_prec*, grad_prec*, grad_prec*) {}      // inside apx_energy / apx_empole / apx_epolar
+// torque(vers, demx, demy, demz) (src/amoeba/emplar.cpp:20): the library's energy operators already turned the torques
+// into forces and booked their virial with the pair virial, so the reference's torque arrays and vir_trq stay as mpoleInit
+// zeroed them and the front-end's virialReduce(vir_trq) adds nothing
+void torque_cu(int, grad_prec*, grad_prec*, grad_prec*) {}
 
 // ---- src/amoeba/field.cpp:8-117.  The front-end composes the reciprocal part from fine-grained PME operators and then calls
 //      the real-space sweep; the library's operator contains all of it, so the last call of each sequence does the work and
 //      the earlier ones have nothing left to do (the PME dispatchers of src/pme.cpp resolve to the empty stubs further down).
+//      The field arrays are ASSIGNED here because the front-end's own sequence starts by zeroing them (darray::zero in
+//      dfieldEwaldRecipSelfP2 / ufieldEwaldRecipSelfP1's callers, field.cpp:26,86) and the stubs that would have accumulated
+//      the reciprocal part are empty.
 void dfieldEwaldRecipSelfP2_cu(real (*)[3]) {}
-void dfieldEwaldReal_cu(real (*field)[3], real (*fieldp)[3])
-{
-   Host3 a, b;
-   chk(apx_dfield(g_apx, a.v.data(), b.v.data()));
-   a.to(field), b.to(fieldp);
-}
+void dfieldEwaldReal_cu(real (*field)[3], real (*fieldp)[3]) { chk(apx_dfield_dev(g_apx, field, fieldp, EB, stream0())); }
 void dfieldNonEwald_cu(real (*field)[3], real (*fieldp)[3]) { dfieldEwaldReal_cu(field, fieldp); }
 void ufieldEwaldRecipSelfP1_cu(const real (*)[3], const real (*)[3], real (*)[3], real (*)[3]) {}
 void ufieldEwaldReal_cu(const real (*ud)[3], const real (*up)[3], real (*field)[3], real (*fieldp)[3])
 {
-   Host3 u, p, a, b;
-   u.from(ud), p.from(up);
-   chk(apx_ufield(g_apx, u.v.data(), p.v.data(), a.v.data(), b.v.data()));
-   a.to(field), b.to(fieldp);
+   chk(apx_ufield_dev(g_apx, ud, up, field, fieldp, EB, stream0()));
 }
 void ufieldNonEwald_cu(const real (*ud)[3], const real (*up)[3], real (*field)[3], real (*fieldp)[3])
 {
@@ -97,10 +103,7 @@ void ufieldNonEwald_cu(const real (*ud)[3], const real (*up)[3], real (*field)[3
 // ---- src/amoeba/induce.cpp:12-73
 void sparsePrecondApply_cu(const real (*rsd)[3], const real (*rsdp)[3], real (*zrsd)[3], real (*zrsdp)[3])
 {
-   Host3 r, q, a, b;
-   r.from(rsd), q.from(rsdp);
-   chk(apx_precond(g_apx, r.v.data(), q.v.data(), a.v.data(), b.v.data()));
-   a.to(zrsd), b.to(zrsdp);
+   chk(apx_precond_dev(g_apx, rsd, rsdp, zrsd, zrsdp, EB, stream0()));
 }
 void diagPrecond_cu(const real (*rsd)[3], const real (*rsdp)[3], real (*zrsd)[3], real (*zrsdp)[3])
 {
@@ -110,64 +113,66 @@ void ulspredSaveP1_cu(real (*)[3], real (*)[3], const real (*)[3], const real (*
 void ulspredSum_cu(real (*)[3], real (*)[3]) {}
 void induceMutualPcg1_cu(real (*ud)[3], real (*up)[3])
 {
-   chk(apx_induce(g_apx));
-   Host3 a, b;
-   chk(apx_get_uind(g_apx, a.v.data(), b.v.data()));
-   a.to(ud), b.to(up);
-   if (udir && udirp) {      // epolar0DotProd and the OPT / print paths read the direct dipoles
-      chk(apx_get_udir(g_apx, a.v.data(), b.v.data()));
-      a.to(udir), b.to(udirp);
-   }
-   waitFor(g::q0);
+   // epolar0DotProd and the OPT / print paths read the direct dipoles: handed back with the solution, device to device
+   chk(apx_induce_dev(g_apx, ud, up, udir, udirp, EB, stream0()));
 }
 
-// ---- src/amoeba/emplar.cpp:9, empole.cpp:53-71, epolar.cpp:515-655: the library reduces on the device and hands the totals
-//      back; the front-ends' own accumulators receive them (energy_em / energy_ep / virial_em, and the gradient as the
-//      fixed-point or floating grad_prec the build uses)
-static void store_gradient(grad_prec* gx, grad_prec* gy, grad_prec* gz)
+// ---- src/amoeba/emplar.cpp:9, empole.cpp:53-71, epolar.cpp:515-655.  Contract (SURVEY 8b "Ownership",
+//      src/energy.cpp:333-446): the operator ADDS its energy to one slot of the term's energy buffer, its virial to one slot of
+//      the virial buffer and its gradient to the term's gradient arrays, all on the device; energy() reduces the buffers
+//      (energyReduce / virialReduce -> esum, vir) and sums gx_elec into gx.  In a non-analyze run em / ep alias eng_buf_elec,
+//      vir_em / vir_ep alias vir_buf_elec and demx / depx alias gx_elec, so anything assigned instead of added would wipe the
+//      other electrostatic terms.  The analyze-mode host scalars (energy_em ...) are NOT touched here: the reference's
+//      front-ends fill them from the buffers themselves (empole.cpp:118-137, epolar.cpp:621-647).
+static void hand_back(int vers, const apx_energy_result& r, double e, EnergyBuffer eb, VirialBuffer vb, grad_prec* gx_, grad_prec* gy_,
+   grad_prec* gz_)
 {
-   if (!gx)
-      return;
-   std::vector<double> g(3 * (size_t)n);
-   chk(apx_get_gradient(g_apx, g.data()));
-   std::vector<grad_prec> c[3];
-   for (int k = 0; k < 3; ++k) {
-      c[k].resize(n);
-      for (int i = 0; i < n; ++i) {
-#if TINKER_DETERMINISTIC_FORCE
-         c[k][i] = static_cast<grad_prec>(static_cast<long long>(g[3 * (size_t)i + k] * 0x100000000ull));
-#else
-         c[k][i] = static_cast<grad_prec>(g[3 * (size_t)i + k]);
-#endif
-      }
+   if ((vers & calc::energy) && eb)
+      chk(apx_add_scalars_dev(g_apx, eb, &e, 1, devKind<EnergyBufferTraits::type>(), stream0()));
+   if ((vers & calc::virial) && vb) {
+      // xx yx zx yy zy zz (src/energybuffer.cpp:81-94)
+      const double v6[6] = {r.virial[0], r.virial[1], r.virial[2], r.virial[4], r.virial[5], r.virial[8]};
+      chk(apx_add_scalars_dev(g_apx, &vb[0][0], v6, 6, devKind<VirialBufferTraits::type>(), stream0()));
    }
-   darray::copyin(g::q0, n, gx, c[0].data());
-   darray::copyin(g::q0, n, gy, c[1].data());
-   darray::copyin(g::q0, n, gz, c[2].data());
-   waitFor(g::q0);
+   if ((vers & calc::grad) && gx_)
+      chk(apx_add_gradient_dev(g_apx, gx_, gy_, gz_, devKind<grad_prec>(), stream0()));
 }
-static void run(int (*op)(apx_ctx*, int, apx_energy_result*), int vers, bool mpole, bool polar)
+void emplar_cu(int vers)
 {
    apx_energy_result r;
-   chk(op(g_apx, vers, &r));
-   if (mpole)
-      energy_em = r.em;
-   if (polar)
-      energy_ep = r.ep;
-   if (vers & calc::virial)
-      for (int i = 0; i < 9; ++i)
-         (mpole ? virial_em : virial_ep)[i] = r.virial[i];
-   if (vers & calc::grad)
-      mpole ? store_gradient(demx, demy, demz) : store_gradient(depx, depy, depz);
+   chk(apx_energy(g_apx, vers, &r));
+   // fused term: em and ep are one buffer in the only mode emplar runs in (src/energy.cpp:262-270: !analyz)
+   hand_back(vers, r, r.em + r.ep, em, vir_em, demx, demy, demz);
 }
-void emplar_cu(int vers) { run(apx_energy, vers, true, true); }
-void empoleEwaldRealSelf_cu(int vers) { run(apx_empole, vers, true, false); }
-void empoleNonEwald_cu(int vers) { run(apx_empole, vers, true, false); }
+void empoleEwaldRealSelf_cu(int vers)
+{
+   apx_energy_result r;
+   chk(apx_empole(g_apx, vers, &r));
+   hand_back(vers, r, r.em, em, vir_em, demx, demy, demz);
+   if ((vers & calc::analyz) && nem)      // interaction count into slot 0 of the count buffer (countReduce sums it)
+   {
+      const double c1 = (double)r.nem;
+      chk(apx_add_scalars_dev(g_apx, nem, &c1, 1, APX_DEV_I32, stream0()));
+   }
+}
+void empoleNonEwald_cu(int vers) { empoleEwaldRealSelf_cu(vers); }
 void empoleChgpenEwaldRecip_cu(int, int) {}      // contained in apx_empole
-void epolarEwaldReal_cu(int vers, const real (*)[3], const real (*)[3]) { run(apx_epolar, vers, false, true); }
-void epolarNonEwald_cu(int vers, const real (*)[3], const real (*)[3]) { run(apx_epolar, vers, false, true); }
+void epolarEwaldReal_cu(int vers, const real (*)[3], const real (*)[3])
+{
+   apx_energy_result r;
+   chk(apx_epolar(g_apx, vers, &r));
+   // without calc::analyz the front-end takes the energy from epolar0DotProd (epolar.cpp:651-655), which is part of apx_epolar:
+   // handed back here either way, the dot-product stub below adds nothing
+   hand_back(vers, r, r.ep, ep, vir_ep, depx, depy, depz);
+   if ((vers & calc::analyz) && nep) {
+      const double c1 = (double)r.nep;
+      chk(apx_add_scalars_dev(g_apx, nep, &c1, 1, APX_DEV_I32, stream0()));
+   }
+}
+void epolarNonEwald_cu(int vers, const real (*a)[3], const real (*b)[3]) { epolarEwaldReal_cu(vers, a, b); }
 void epolarEwaldRecipSelf_cu(int, const real (*)[3], const real (*)[3]) {}      // contained in apx_epolar
 void epolar0DotProd_cu(const real (*)[3], const real (*)[3]) {}                // contained in apx_epolar / apx_energy
+void epolarPairwiseExtfield_cu(const real (*)[3]) {}                            // no external field in the library
 
 // ---- src/pme.cpp:221-347: fine-grained PME operators -- fused inside the library's field / energy operators
 void bsplineFill_cu(PMEUnit, int) {}

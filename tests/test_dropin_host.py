@@ -1,5 +1,5 @@
 """Host-side checks of the drop-in demonstration (oracle/_ref/libref_dropin.so): the reference's unmodified front-ends
-src/amoeba/field.cpp and induce.cpp link against integration/apx_adapter.cpp + libapx with no reference CUDA kernel in the
+src/amoeba/field.cpp, induce.cpp, emplar.cpp, mpole.cpp and its energy-buffer reductions src/energybuffer.cpp link against integration/apx_adapter.cpp + libapx with no reference CUDA kernel in the
 library; every `*_cu` symbol those front-ends call is defined by the adapter; without a GPU the open call reports an error."""
 import ctypes as C
 import os
@@ -18,8 +18,9 @@ CU_SYMBOLS = ["induceMutualPcg1_cu", "sparsePrecondApply_cu", "diagPrecond_cu", 
               "emplar_cu", "empoleEwaldRealSelf_cu", "empoleNonEwald_cu", "empoleChgpenEwaldRecip_cu", "epolarEwaldReal_cu",
               "epolarNonEwald_cu", "epolarEwaldRecipSelf_cu", "epolar0DotProd_cu", "torque_cu", "chkpole_cu", "rotpole_cu", "rpoleToCmp_cu",
               "bsplineFill_cu", "gridMpole_cu", "gridUind_cu", "pmeConv_cu", "fphiMpole_cu", "fphiUind_cu", "fphiUind2_cu", "cmpToFmp_cu",
-              "cuindToFuind_cu", "fphiToCphi_cu"]
-FRONT_ENDS = ["tinker::induce(", "tinker::dfield(", "tinker::ufield(", "tinker::sparsePrecondApply(", "tinker::diagPrecond("]
+              "cuindToFuind_cu", "fphiToCphi_cu", "mpoleDataBinding_cu", "epolarDataBinding_cu", "epolarPairwiseExtfield_cu"]
+FRONT_ENDS = ["tinker::induce(", "tinker::dfield(", "tinker::ufield(", "tinker::sparsePrecondApply(", "tinker::diagPrecond(",
+              "tinker::emplar(", "tinker::mpoleInit(", "tinker::torque(", "tinker::energyReduce(", "tinker::virialReduce("]
 
 
 def _nm():
@@ -34,7 +35,7 @@ def test_library_resolves_with_the_adapter_instead_of_the_reference_kernels():
     for s in FRONT_ENDS:
         assert s in out, s
     # no kernel of the reference is in this library: its pair / PME kernels carry these names
-    for k in ("pcgUdirV2", "dfield_cu1", "ufield_cu1", "emplar_cu1a", "gridPut_cu", "sparsePrecond_cu1"):
+    for k in ("pcgUdirV2", "dfield_cu1", "ufield_cu1", "emplar_cu1a", "gridPut_cu", "sparsePrecond_cu1", "torque_cu1", "rotpoleNorm"):
         assert k not in subprocess.run(["nm", "-C", LIB], capture_output=True, text=True).stdout, k
     ldd = subprocess.run(["ldd", LIB], capture_output=True, text=True).stdout
     assert "libapx.so" in ldd and "not found" not in ldd.split("libapx.so")[1].splitlines()[0]

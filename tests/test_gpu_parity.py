@@ -291,3 +291,63 @@ def test_triclinic_cell(precision):
     assert np.abs(u1 - o.uind).max() * DEBYE < tol["u"] and np.abs(u2 - o.uinp).max() * DEBYE < tol["u"]
     assert r["pcg_iterations"] == o.niter
     a.close()
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_device_pointer_entry_points(dtype):
+    """The _dev entry points (include/apx.h, csrc/devio.cu) -- what the adapter hands the reference's device arrays to --
+    against the host-pointer entry points on the same context: same operators, no host staging, and the accumulate contract
+    of the gradient / energy hand-back (SURVEY 8b "Ownership")."""
+    import torch
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    s = tg.load_system(os.path.join(GOLDEN, "water30.npz"))
+    a = _amoeba(s, "mixed")
+    td = getattr(torch, dtype)
+    tol = 2e-7 if dtype == "float32" else 1e-12
+    dev = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=td, device="cuda")      # noqa: E731
+    new = lambda: torch.zeros(s.n, 3, dtype=td, device="cuda")      # noqa: E731
+    rel = lambda t, ref: float(np.abs(t.double().cpu().numpy() - ref).max() / np.abs(ref).max())      # noqa: E731
+    # positions from the reference's separate x / y / z device arrays
+    xyz = np.array(s.xyz) + 0.01
+    a.set_positions_dev(dev(xyz[:, 0]), dev(xyz[:, 1]), dev(xyz[:, 2]))
+    r1 = a.energy(calc.v0)
+    a.set_positions(xyz if dtype == "float64" else xyz.astype(np.float32).astype(np.float64))
+    r0 = a.energy(calc.v0)
+    assert abs(r1["esum"] - r0["esum"]) < 1e-9 * abs(r0["esum"])
+    a.set_positions(s.xyz)
+    # operators
+    f0, f1 = a.dfield()
+    d0, d1 = new(), new()
+    a.dfield_dev(d0, d1)
+    assert rel(d0, f0) < tol and rel(d1, f1) < tol
+    rng = np.random.default_rng(3)
+    ud, up = rng.normal(size=(s.n, 3)) * 0.05, rng.normal(size=(s.n, 3)) * 0.05
+    if dtype == "float32":
+        ud, up = ud.astype(np.float32).astype(np.float64), up.astype(np.float32).astype(np.float64)
+    g0, g1 = a.ufield(ud, up)
+    a.ufield_dev(dev(ud), dev(up), d0, d1)
+    assert rel(d0, g0) < 5e-6 and rel(d1, g1) < 5e-6      # float atomics on the PME grid: not bit-reproducible run to run
+    z0, z1 = a.sparsePrecondApply(ud, up)
+    a.precond_dev(dev(ud), dev(up), d0, d1)
+    assert rel(d0, z0) < tol and rel(d1, z1) < tol
+    u0, u1 = new(), new()
+    a.induce_dev(u0, u1, d0, d1)
+    h0, h1 = a.uind()
+    k0, k1 = a.udir()
+    assert rel(u0, h0) < tol and rel(u1, h1) < tol and rel(d0, k0) < tol and rel(d1, k1) < tol
+    # hand-back: added to what the caller's accumulators already hold
+    r = a.energy(calc.v1)
+    g = r["grad"]
+    gx = [torch.full((s.n,), 7 << 32, dtype=torch.int64, device="cuda") for _ in range(3)]      # 7.0 in 2^32 fixed point
+    a.add_gradient_dev(*gx)
+    back = np.stack([(t.cpu().numpy().astype(np.float64) / 2.0 ** 32) for t in gx], axis=1) - 7.0
+    assert np.abs(back - g).max() < 1e-9
+    gf = [torch.full((s.n,), 7.0, dtype=td, device="cuda") for _ in range(3)]
+    a.add_gradient_dev(*gf)
+    back = np.stack([t.double().cpu().numpy() for t in gf], axis=1) - 7.0
+    assert np.abs(back - g).max() < (2e-5 if dtype == "float32" else 1e-9)
+    eb = torch.full((4,), 5 << 32, dtype=torch.int64, device="cuda")
+    a.add_scalars_dev(eb, [r["esum"]])
+    assert abs(eb[0].item() / 2.0 ** 32 - 5.0 - r["esum"]) < 1e-8 * abs(r["esum"]) and eb[1].item() == 5 << 32
+    a.close()

@@ -199,6 +199,15 @@ def load_library(precision="mixed"):
         "apx_md_init": [_DP, _DP, C.POINTER(MdConfig)], "apx_md_steps": [C.c_int, C.POINTER(MdReport)],
         "apx_md_get_state": [_DP, _DP],
         "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        # device-pointer entry points (csrc/devio.cu): pointers as integers, element size, caller's stream
+        "apx_set_positions_dev": [C.c_void_p] * 3 + [C.c_int, C.c_void_p],
+        "apx_dfield_dev": [C.c_void_p] * 2 + [C.c_int, C.c_void_p],
+        "apx_ufield_dev": [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
+        "apx_precond_dev": [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
+        "apx_induce_dev": [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
+        "apx_get_uind_dev": [C.c_void_p] * 4 + [C.c_int, C.c_void_p],
+        "apx_add_gradient_dev": [C.c_void_p] * 3 + [C.c_int, C.c_void_p],
+        "apx_add_scalars_dev": [C.c_void_p, _DP, C.c_int, C.c_int, C.c_void_p],
     }.items():
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p] + args
@@ -514,6 +523,58 @@ class Amoeba:
         g = self._out(self.n, 3)
         self._chk(self.lib.apx_get_gradient(self.ctx, _dp(g)))
         return g
+
+    # -- device-pointer entry points: arguments are torch CUDA tensors (device memory, caller's atom order, float32 or
+    #    float64), ordered on torch's current stream -- what the reference's *_cu operators are handed (csrc/devio.cu)
+    @staticmethod
+    def _dev(*tensors):
+        import torch
+        eb = None
+        for t in tensors:
+            if t is None:
+                continue
+            assert t.is_cuda and t.is_contiguous(), "device-pointer entry points take contiguous CUDA tensors"
+            assert t.dtype in (torch.float32, torch.float64)
+            assert eb in (None, t.element_size()), "one element type per call"
+            eb = t.element_size()
+        return eb, torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def set_positions_dev(self, x, y, z):
+        eb, st = self._dev(x, y, z)
+        self._chk(self.lib.apx_set_positions_dev(self.ctx, self._p(x), self._p(y), self._p(z), eb, st))
+
+    def dfield_dev(self, field, fieldp):
+        eb, st = self._dev(field, fieldp)
+        self._chk(self.lib.apx_dfield_dev(self.ctx, self._p(field), self._p(fieldp), eb, st))
+
+    def ufield_dev(self, uind, uinp, field, fieldp):
+        eb, st = self._dev(uind, uinp, field, fieldp)
+        self._chk(self.lib.apx_ufield_dev(self.ctx, self._p(uind), self._p(uinp), self._p(field), self._p(fieldp), eb, st))
+
+    def precond_dev(self, rsd, rsdp, zrsd, zrsdp):
+        eb, st = self._dev(rsd, rsdp, zrsd, zrsdp)
+        self._chk(self.lib.apx_precond_dev(self.ctx, self._p(rsd), self._p(rsdp), self._p(zrsd), self._p(zrsdp), eb, st))
+
+    def induce_dev(self, uind, uinp, udir=None, udirp=None):
+        eb, st = self._dev(uind, uinp, udir, udirp)
+        self._chk(self.lib.apx_induce_dev(self.ctx, self._p(uind), self._p(uinp), self._p(udir), self._p(udirp), eb, st))
+
+    def add_gradient_dev(self, gx, gy, gz):
+        """g += dE/dx of the last energy call; int64 tensors = the 2^32 fixed-point grad_prec of the reference's mixed build."""
+        import torch
+        kind = {torch.int64: 0, torch.float32: 4, torch.float64: 8}[gx.dtype]
+        self._chk(self.lib.apx_add_gradient_dev(self.ctx, gx.data_ptr(), gy.data_ptr(), gz.data_ptr(), kind,
+                                                torch.cuda.current_stream().cuda_stream))
+
+    def add_scalars_dev(self, dst, vals):
+        import torch
+        kind = {torch.int64: 0, torch.int32: 1, torch.float32: 4, torch.float64: 8}[dst.dtype]
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        self._chk(self.lib.apx_add_scalars_dev(self.ctx, dst.data_ptr(), _dp(vals), len(vals), kind, torch.cuda.current_stream().cuda_stream))
 
     # -- PME operators (fractional potentials), for parity tests
     def pme_mpole_fphi(self):

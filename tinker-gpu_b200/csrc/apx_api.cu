@@ -15,6 +15,8 @@ ApxComm* apx_make_local_comm(int rank, int world, void* hub);
 
 static thread_local std::string g_err;
 
+void apx_set_last_error(const std::string& msg) { g_err = msg; }
+
 void apx_throw(const char* file, int line, const std::string& msg)
 {
    const char* base = strrchr(file, '/');
@@ -397,6 +399,10 @@ void apx_destroy(apx_ctx* c)
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
    c->theta.release(), c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();
+   if (c->ev_dev_in) {
+      cudaEventDestroy(c->ev_dev_in);
+      cudaEventDestroy(c->ev_dev_out);
+   }
    cudaEventDestroy(c->ev_fork);
    cudaEventDestroy(c->ev_join);
    cudaStreamDestroy(c->stream2);

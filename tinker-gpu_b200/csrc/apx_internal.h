@@ -247,6 +247,7 @@ struct apx_ctx {
    int uf_ctas = 8, uf_smem_kb = 0;      // residency of the ufield rows beside the PME chain (APX_UF_CTAS, APX_UF_SMEM)
    cudaStream_t stream2 = nullptr;       // real-space operator of an iteration runs here, beside the PME chain
    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+   cudaEvent_t ev_dev_in = nullptr, ev_dev_out = nullptr;   // ordering of the _dev entry points against the caller's stream (devio.cu)
    DevBuf<double> scal;                  // PCG scalars (sum, sump, a, ap, sum1, sump1, epsd, epsp ...)
    double* scal_h = nullptr;             // pinned
    int last_iters = 6;
