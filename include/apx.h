@@ -189,6 +189,10 @@ int apx_nccl_unique_id(const char* nccl_lib, void* out128);
 void* apx_local_hub_create(int world);
 void apx_local_hub_destroy(void* hub);
 int apx_get_dist_info(apx_ctx* ctx, int* info8 /* rank, world, a0, a1, halo atoms, planes, halo planes lo, hi */);
+/* per-phase device time of the decomposed path since the previous call (ms): [0] halo exchanges of per-atom vectors,
+ * [1] forward slab FFTs (plane reduction, 2-D FFTs, transpose, 1-D FFTs), [2] inverse slab FFTs, [3] scalar all-reduces,
+ * [4..7] their call counts.  on: keep collecting.  Call after apx_synchronize. */
+int apx_dist_profile(apx_ctx* ctx, int on, double* out8);
 /* host-only: halo plan of `rank` from the sorted atoms' PME z-coordinates and the ranks' sorted ranges */
 int apx_dist_plan(int n, const float* w3_sorted, const int* bounds, int world, int rank, double range_frac, int* send_idx,
    int* send_off, int* recv_idx, int* recv_off);

@@ -40,10 +40,7 @@ namespace pm64 {
 #include "pairmath_host_eval.inc"
 }
 
-namespace {
-struct BoxD {
-   double l[9], r[9];
-};
+namespace {      // (BoxD: apx_internal.h)
 void invert3(const double* m, double* inv)
 {
    double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
@@ -96,10 +93,11 @@ extern "C" int pairmath_host_mplar(int mode, int n, long long npair, const int* 
    std::vector<float> ga(48 * (size_t)n, 0.0f), ta(48 * (size_t)n, 0.0f);
    std::vector<int> slot(n, 0);
    std::vector<double> gd(3 * (size_t)n, 0.0), td(3 * (size_t)n, 0.0);
-   float lf[9], qs[9];
+   float lf[9], qs[9], qlo[9];
    for (int a = 0; a < 9; ++a) {
       lf[a] = (float)b.l[a];
       qs[a] = (float)(b.l[a] / 4294967296.0);
+      qlo[a] = (float)(b.l[a] / 4294967296.0 - (double)qs[a]);      // Box::qlo (csrc/apx_api.cu: set_box)
    }
    float rf[9];
    for (int a = 0; a < 9; ++a)
@@ -126,7 +124,8 @@ extern "C" int pairmath_host_mplar(int mode, int n, long long npair, const int* 
          for (int a = 0; a < 3; ++a)
             df[a] = (float)(int32_t)(qf[3 * (size_t)k + a] - qf[3 * (size_t)i + a]);
          for (int a = 0; a < 3; ++a)
-            Rf[a] = df[0] * qs[3 * a] + df[1] * qs[3 * a + 1] + df[2] * qs[3 * a + 2];
+            Rf[a] = df[0] * qs[3 * a] + df[1] * qs[3 * a + 1] + df[2] * qs[3 * a + 2]
+               + (df[0] * qlo[3 * a] + df[1] * qlo[3 * a + 1] + df[2] * qlo[3 * a + 2]);      // pair_delta (csrc/pairmath.cuh)
       } else {
          float d[3], f[3];
          for (int a = 0; a < 3; ++a)

@@ -320,14 +320,14 @@ def test_device_pointer_entry_points(dtype):
     f0, f1 = a.dfield()
     d0, d1 = new(), new()
     a.dfield_dev(d0, d1)
-    assert rel(d0, f0) < tol and rel(d1, f1) < tol
+    assert rel(d0, f0) < 5e-6 and rel(d1, f1) < 5e-6      # recomputed: float atomics on the PME grid are not bit-reproducible
     rng = np.random.default_rng(3)
     ud, up = rng.normal(size=(s.n, 3)) * 0.05, rng.normal(size=(s.n, 3)) * 0.05
     if dtype == "float32":
         ud, up = ud.astype(np.float32).astype(np.float64), up.astype(np.float32).astype(np.float64)
     g0, g1 = a.ufield(ud, up)
     a.ufield_dev(dev(ud), dev(up), d0, d1)
-    assert rel(d0, g0) < 5e-6 and rel(d1, g1) < 5e-6      # float atomics on the PME grid: not bit-reproducible run to run
+    assert rel(d0, g0) < 5e-6 and rel(d1, g1) < 5e-6
     z0, z1 = a.sparsePrecondApply(ud, up)
     a.precond_dev(dev(ud), dev(up), d0, d1)
     assert rel(d0, z0) < tol and rel(d1, z1) < tol
@@ -335,7 +335,7 @@ def test_device_pointer_entry_points(dtype):
     a.induce_dev(u0, u1, d0, d1)
     h0, h1 = a.uind()
     k0, k1 = a.udir()
-    assert rel(u0, h0) < tol and rel(u1, h1) < tol and rel(d0, k0) < tol and rel(d1, k1) < tol
+    assert rel(u0, h0) < tol and rel(u1, h1) < tol and rel(d0, k0) < tol and rel(d1, k1) < tol      # copies of one solve
     # hand-back: added to what the caller's accumulators already hold
     r = a.energy(calc.v1)
     g = r["grad"]

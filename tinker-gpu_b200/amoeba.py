@@ -155,6 +155,9 @@ _DP = C.POINTER(C.c_double)
 
 
 def library_path(precision="mixed"):
+    # APX_LIBRARY_MIXED: another build of the mixed library (diagnostic variants, tools/diag_precision.py)
+    if precision == "mixed" and os.environ.get("APX_LIBRARY_MIXED"):
+        return os.environ["APX_LIBRARY_MIXED"]
     return os.path.join(HERE, "libapx.so" if precision == "mixed" else "libapx_f64.so")
 
 

@@ -58,6 +58,7 @@ void set_box(apx_ctx* c, const double* lvec)
       b.l[i] = (real)lvec[i];
       b.r[i] = (real)inv[i];
       b.q[i] = (real)(lvec[i] / 4294967296.0);
+      b.qlo[i] = (real)(lvec[i] / 4294967296.0 - (double)b.q[i]);
    }
    b.lx = (real)lvec[0];
    b.ly = (real)lvec[4];
@@ -211,6 +212,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
       c->uf_ctas = std::max(1, atoi(e));
    if (const char* e = getenv("APX_UF_SMEM"))
       c->uf_smem_kb = std::max(0, std::min(40, atoi(e)));
+   if (const char* e = getenv("APX_DIAG_SKIP"))
+      c->diag_skip = atoi(e);
    if (const char* e = getenv("APX_NO_GRAPH"))
       c->use_graph = atoi(e) ? 0 : 1;
    set_box(c, sys->lvec);

@@ -96,8 +96,16 @@ struct Box {
    real l[9];               // lvec rows
    real r[9];               // recip rows
    real q[9];               // l / 2^32: Cartesian separation from a difference of 32-bit fractional coordinates
+   real qlo[9];             // l / 2^32 - q in double: the product (difference x l / 2^32) is formed from the two parts
    int orthogonal;
    real volume;
+};
+
+// The cell in double: wrapping of the caller's f64 coordinates into fractional coordinates must not see the float-rounded
+// reciprocal vectors of Box (1/L in float is off by up to 6e-8 relative: at |x| = 15 A that moves an atom by 1e-6 A, and
+// inconsistently with the listed pairs, which are formed from the f64 coordinates directly)
+struct BoxD {
+   double l[9], r[9];
 };
 
 // Directed per-atom neighbor rows in sorted order (rows.cu).  vnbr holds the Verlet rows
@@ -147,6 +155,11 @@ struct DistState {
    int plans_ok = 0;
    DevBuf<cplx> tbuf, sbuf, tbuf2, hbuf;  // transposed grid [n3][py][n1], pack buffer, cross-virial copy, halo planes
    long long halo_atoms = 0;
+   // per-phase device time of the decomposed path (apx_dist_profile): event pairs on the main stream around every halo
+   // exchange (kind 0), forward slab FFT with its plane reduction and transpose (1), inverse (2), scalar all-reduce (3)
+   int prof_on = 0, prof_used = 0;
+   std::vector<cudaEvent_t> prof_ev;
+   std::vector<int> prof_kind;
 };
 
 // ---- buffered 14-7 vdW term (ehal.cu)
@@ -319,9 +332,18 @@ struct apx_ctx {
    const int* skip = nullptr;            // device flag: kernels of speculative CG iterations return at once when set
    int mpole_inited = 0;
    int induced_valid = 0;
+   int diag_skip = 0;                    // APX_DIAG_SKIP (diagnostics only): 1 = no real-space pair kernels in energy(), 2 = no reciprocal force kernels
    int md_forces_valid = 0;              // the accumulators hold the integrator's saved fast + slow forces at the current positions:
                                          // cleared by every public call that rewrites them (md.cu recomputes them when clear)
 };
+
+inline BoxD apx_box_d(const apx_ctx* c)
+{
+   BoxD b;
+   for (int q = 0; q < 9; ++q)
+      b.l[q] = c->opt.lvec[q], b.r[q] = c->recip_d[q];
+   return b;
+}
 
 #define APX_COUNT_LAUNCH(ctx) ((ctx)->stats.kernel_launches++)
 
@@ -340,6 +362,8 @@ void apx_dist_pme_destroy(apx_ctx* c);
 void apx_dist_fft_forward(apx_ctx* c, cplx* tb);                   // local grid (halo-reduced) -> transformed slab tb
 void apx_dist_fft_inverse(apx_ctx* c, cplx* tb);                   // tb -> local grid including halo planes
 void apx_dist_destroy(apx_ctx* c);
+int apx_dist_prof_begin(apx_ctx* c, int kind, cudaStream_t st);      // -1 when profiling is off
+void apx_dist_prof_end(apx_ctx* c, int slot, cudaStream_t st);
 // ---- ehal.cu
 void apx_vdw_attach_impl(apx_ctx* c, const apx_vdw* v);
 void apx_vdw_refresh(apx_ctx* c, bool rebuilt);                    // reduced sites (every step), rows (at list rebuild)

@@ -742,11 +742,36 @@ void apx_dist_after_sort(apx_ctx* c)
    D.halo_atoms = (long long)ri.size();
 }
 
+int apx_dist_prof_begin(apx_ctx* c, int kind, cudaStream_t st)
+{
+   DistState& D = c->dist;
+   if (!D.prof_on)
+      return -1;
+   if (D.prof_used + 2 > (int)D.prof_ev.size()) {
+      const size_t old = D.prof_ev.size();
+      D.prof_ev.resize(old + 256);
+      D.prof_kind.resize(old + 256);
+      for (size_t k = old; k < D.prof_ev.size(); ++k)
+         CUDA_CHECK(cudaEventCreate(&D.prof_ev[k]));
+   }
+   const int slot = D.prof_used;
+   D.prof_used += 2;
+   D.prof_kind[slot] = kind;
+   cudaEventRecord(D.prof_ev[slot], st);
+   return slot;
+}
+void apx_dist_prof_end(apx_ctx* c, int slot, cudaStream_t st)
+{
+   if (slot >= 0)
+      cudaEventRecord(c->dist.prof_ev[slot + 1], st);
+}
+
 // V[halo atoms] <- the owners' values; V is a packed (d,p) array (2 real4 per atom, dp.cuh)
 void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st)
 {
    DistState& D = c->dist;
    const int G = D.world;
+   const int pslot = apx_dist_prof_begin(c, 0, st);
    const int ns = D.send_off[G], nr = D.recv_off[G];
    if (ns > 0) {
       k_halo_pack<<<(2 * ns + 255) / 256, 256, 0, st>>>(ns, D.send_idx, V, D.sendbuf);
@@ -764,9 +789,15 @@ void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st)
       k_halo_unpack<<<(2 * nr + 255) / 256, 256, 0, st>>>(nr, D.recv_idx, D.recvbuf, V);
       APX_COUNT_LAUNCH(c);
    }
+   apx_dist_prof_end(c, pslot, st);
 }
 
-void apx_dist_allreduce_f64(apx_ctx* c, double* p, size_t n) { c->dist.comm->allreduce(p, n, 0, c->stream); }
+void apx_dist_allreduce_f64(apx_ctx* c, double* p, size_t n)
+{
+   const int pslot = apx_dist_prof_begin(c, 3, c->stream);
+   c->dist.comm->allreduce(p, n, 0, c->stream);
+   apx_dist_prof_end(c, pslot, c->stream);
+}
 void apx_dist_allreduce_u64(apx_ctx* c, unsigned long long* p, size_t n) { c->dist.comm->allreduce(p, n, 1, c->stream); }
 void apx_dist_allreduce_i32(apx_ctx* c, int* p, size_t n) { c->dist.comm->allreduce(p, n, 2, c->stream); }
 
@@ -856,6 +887,7 @@ void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
    const int prev = (D.rank + G - 1) % G, next = (D.rank + 1) % G;
    cudaStream_t st = c->stream;
    cplx* g = c->qgrid.p;
+   const int pslot = apx_dist_prof_begin(c, 1, st);
    // 1. halo planes go to the slabs they belong to and are summed there
    {
       std::vector<ApxComm::Op> sends = {{prev, g, D.hl * plane * sizeof(cplx)}, {next, g + (size_t)(D.hl + D.pz) * plane, D.hu * plane * sizeof(cplx)}};
@@ -880,6 +912,7 @@ void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
    }
    exec_fft(D.plan1d, tb, CUFFT_FORWARD);
    c->stats.kernel_launches += 3;
+   apx_dist_prof_end(c, pslot, st);
 }
 
 // tb -> potential on my planes and on the halo planes my atoms' stencils reach
@@ -892,6 +925,7 @@ void apx_dist_fft_inverse(apx_ctx* c, cplx* tb)
    cudaStream_t st = c->stream;
    cplx* g = c->qgrid.p;
    cplx* mine = g + (size_t)D.hl * plane;
+   const int pslot = apx_dist_prof_begin(c, 2, st);
    exec_fft(D.plan1d, tb, CUFFT_INVERSE);
    const size_t tot = (size_t)D.pz * plane, blk = (size_t)D.pz * D.py * n1;
    {
@@ -911,11 +945,15 @@ void apx_dist_fft_inverse(apx_ctx* c, cplx* tb)
       comm_exchange(c, sends, recvs, st);
    }
    c->stats.kernel_launches += 1;
+   apx_dist_prof_end(c, pslot, st);
 }
 
 void apx_dist_destroy(apx_ctx* c)
 {
    DistState& D = c->dist;
+   for (auto& e : D.prof_ev)
+      cudaEventDestroy(e);
+   D.prof_ev.clear();
    apx_dist_pme_destroy(c);
    delete D.comm;
    D.comm = nullptr;
@@ -985,6 +1023,29 @@ int apx_nccl_unique_id(const char* lib, void* out128)
       g_dist_err = e.what();
       return 1;
    }
+   return 0;
+}
+
+// per-phase device time of the decomposed path: on = 1 starts collecting (and empties the record), the second call
+// returns, in ms summed over everything since: [0] halo exchanges of per-atom vectors, [1] forward slab FFTs (plane
+// reduction + 2-D FFT + transpose + 1-D FFT), [2] inverse slab FFTs, [3] scalar all-reduces, [4..7] their call counts.
+// The caller must have synchronised the context.
+int apx_dist_profile(apx_ctx* c, int on, double* out8)
+{
+   DistState& D = c->dist;
+   if (out8) {
+      for (int q = 0; q < 8; ++q)
+         out8[q] = 0;
+      for (int k = 0; k + 1 < D.prof_used; k += 2) {
+         float ms = 0;
+         if (cudaEventElapsedTime(&ms, D.prof_ev[k], D.prof_ev[k + 1]) == cudaSuccess) {
+            out8[D.prof_kind[k]] += ms;
+            out8[4 + D.prof_kind[k]] += 1;
+         }
+      }
+   }
+   D.prof_used = 0;
+   D.prof_on = on ? 1 : 0;
    return 0;
 }
 

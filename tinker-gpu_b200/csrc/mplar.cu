@@ -812,7 +812,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    A.ebuf = c->ebuf;
    A.cnt = c->cnt;
    A.cnt2 = c->cnt.p + 1;
-   if (c->rows.nverlet > 0 && (do_m || do_p) && (do_g || do_e)) {
+   if (c->rows.nverlet > 0 && (do_m || do_p) && (do_g || do_e) && !(c->diag_skip & 1)) {
       int grid = rows_grid<MP_G>(c);
       if (do_g && ewald) k_mplar_rows<true, true, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
       else if (do_g) k_mplar_rows<true, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
@@ -836,7 +836,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
       RecipX X = make_recipx(c);
       int g = std::max(1, (no + 127) / 128);
       const size_t o = (size_t)a0;
-      if (do_m) {
+      if (do_m && !(c->diag_skip & 2)) {
          if (do_g)
             k_recip_mpole<true><<<g, 128, 0, st>>>(no, X, c->f_elec, (real)c->opt.aewald, do_e, do_v, c->mp0 + o, c->mp1 + o, c->mp2 + o,
                c->fmp + 10 * o, c->fphi + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
@@ -845,7 +845,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
                c->fmp + 10 * o, c->fphi + 20 * o, c->gx + o, c->gy + o, c->gz + o, c->trqf + 3 * o, c->dbuf);
          APX_COUNT_LAUNCH(c);
       }
-      if (do_p && (do_g || pair_ep)) {
+      if (do_p && (do_g || pair_ep) && !(c->diag_skip & 2)) {
          if (do_g)
             apx_pme_uind_fphi(c, c->uind, c->uinp, true);
          if (do_g)

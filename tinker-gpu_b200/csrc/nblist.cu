@@ -54,7 +54,7 @@ __global__ void k_sortkeys(int n, Box b, int nslab, const double* __restrict__ x
 }
 
 // per-step: wrapped positions into sorted slots (also used at rebuild)
-__global__ void k_gather_pos(int n, int npad, Box b, const double* __restrict__ xyz, const int* __restrict__ perm,
+__global__ void k_gather_pos(int n, int npad, BoxD b, const double* __restrict__ xyz, const int* __restrict__ perm,
    const real* __restrict__ pdamp, real4* __restrict__ posd, pos_t* __restrict__ posq)
 {
    int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,7 +175,7 @@ void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext)
 void apx_update_sorted_positions(apx_ctx* c)
 {
    int g = (c->npad + 255) / 256;
-   k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
+   k_gather_pos<<<g, 256, 0, c->stream>>>(c->n, c->npad, apx_box_d(c), c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
    APX_COUNT_LAUNCH(c);
    apx_pme_fill_theta(c);
 }
@@ -222,7 +222,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
       c->a0 = 0, c->a1 = n;
    // 2. sorted copies of per-atom data
    int g = (c->npad + 255) / 256;
-   k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, c->box, c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
+   k_gather_pos<<<g, 256, 0, c->stream>>>(n, c->npad, apx_box_d(c), c->xyz_d, c->perm, c->pdamp_o, c->posd, c->posq);
    k_gather_static<<<g, 256, 0, c->stream>>>(n, c->npad, c->perm, c->inv, c->thole_o, c->polarity_o, c->jpolar_o, c->tpj);
    if (c->nexcl)
       k_excl_sorted<<<(c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_ik, c->excl_sc, c->inv, c->excl_s);

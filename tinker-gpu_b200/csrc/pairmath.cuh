@@ -43,14 +43,16 @@ __device__ __forceinline__ void pair_delta(const Box& b, const pos_t& pi, const 
    apx_image(b, dx, dy, dz);
 #else
    const real f1 = (real)(int)(pk.x - pi.x), f2 = (real)(int)(pk.y - pi.y), f3 = (real)(int)(pk.z - pi.z);
+   // l / 2^32 in two floats: without the low part every separation would carry the same relative rounding error of the
+   // cell edge (up to 6e-8) -- a coherent error, the cell 4e-6 A too large, not a random one
    if (b.orthogonal) {
-      dx = f1 * b.q[0];
-      dy = f2 * b.q[4];
-      dz = f3 * b.q[8];
+      dx = fmaf(f1, b.q[0], f1 * b.qlo[0]);
+      dy = fmaf(f2, b.q[4], f2 * b.qlo[4]);
+      dz = fmaf(f3, b.q[8], f3 * b.qlo[8]);
    } else {
-      dx = f1 * b.q[0] + f2 * b.q[1] + f3 * b.q[2];
-      dy = f1 * b.q[3] + f2 * b.q[4] + f3 * b.q[5];
-      dz = f1 * b.q[6] + f2 * b.q[7] + f3 * b.q[8];
+      dx = f1 * b.q[0] + f2 * b.q[1] + f3 * b.q[2] + (f1 * b.qlo[0] + f2 * b.qlo[1] + f3 * b.qlo[2]);
+      dy = f1 * b.q[3] + f2 * b.q[4] + f3 * b.q[5] + (f1 * b.qlo[3] + f2 * b.qlo[4] + f3 * b.qlo[5]);
+      dz = f1 * b.q[6] + f2 * b.q[7] + f3 * b.q[8] + (f1 * b.qlo[6] + f2 * b.qlo[7] + f3 * b.qlo[8]);
    }
 #endif
 }
