@@ -266,6 +266,9 @@ int apx_md_init(apx_ctx* ctx, const double* mass, const double* vel, const apx_m
 /* nsteps x BasicIntegrator::dynamic(istep, dt) */
 int apx_md_steps(apx_ctx* ctx, int nsteps, apx_md_report* out);
 int apx_md_get_state(apx_ctx* ctx, double* xyz /* [n][3] or NULL */, double* vel /* [n][3] or NULL */);
+/* positions / velocities from host buffers (a host-side driver that owns x and v; pinned memory makes the copies true DMA).
+ * forces_valid != 0: xyz is what the last apx_md_steps left, the saved forces still apply; 0: they are recomputed. */
+int apx_md_set_state(apx_ctx* ctx, const double* xyz, const double* vel, int forces_valid);
 
 /* copyGradient: src/egvop.cpp:64-111 (fixed -> double, caller's order) */
 int apx_get_gradient(apx_ctx* ctx, double* grad /* [n][3] */);

@@ -200,7 +200,7 @@ def load_library(precision="mixed"):
         "apx_valence_attach": [C.POINTER(_ApxValence)], "apx_evalence": [C.c_int, C.POINTER(ValenceResult)],
         "apx_get_valence_gradient": [_DP],
         "apx_md_init": [_DP, _DP, C.POINTER(MdConfig)], "apx_md_steps": [C.c_int, C.POINTER(MdReport)],
-        "apx_md_get_state": [_DP, _DP],
+        "apx_md_get_state": [_DP, _DP], "apx_md_set_state": [_DP, _DP, C.c_int],
         "apx_upred_set": [C.c_int], "apx_upred_count": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
         # device-pointer entry points (csrc/devio.cu): pointers as integers, element size, caller's stream
         "apx_set_positions_dev": [C.c_void_p] * 3 + [C.c_int, C.c_void_p],

@@ -622,6 +622,14 @@ int apx_md_get_state(apx_ctx* c, double* xyz, double* vel)
    API_END
 }
 
+int apx_md_set_state(apx_ctx* c, const double* xyz, const double* vel, int forces_valid)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   apx_md_set_state_impl(c, xyz, vel, forces_valid);
+   API_END
+}
+
 int apx_vdw_attach(apx_ctx* c, const apx_vdw* v)
 {
    API_BEGIN

@@ -389,6 +389,7 @@ void apx_valence_destroy(apx_ctx* c);
 void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const apx_md_config* cfg);
 void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out);
 void apx_md_get_state_impl(apx_ctx* c, double* xyz, double* vel);
+void apx_md_set_state_impl(apx_ctx* c, const double* xyz, const double* vel, int forces_valid);
 void apx_md_destroy(apx_ctx* c);
 // ---- rows.cu
 void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort

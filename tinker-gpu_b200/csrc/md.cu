@@ -332,6 +332,25 @@ void apx_md_get_state_impl(apx_ctx* c, double* xyz, double* vel)
    CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
+// integrator state from host buffers (a host-side driver that keeps x and v itself: the e2e leg of bench.py).  forces_valid != 0:
+// the positions are the ones the last apx_md_steps call left (handed back unchanged), so the saved forces still apply;
+// otherwise they are recomputed at the start of the next apx_md_steps.
+void apx_md_set_state_impl(apx_ctx* c, const double* xyz, const double* vel, int forces_valid)
+{
+   if (!c->md || !c->md->on)
+      APX_THROW("apx_md_set_state before apx_md_init");
+   const size_t b = sizeof(double) * 3 * (size_t)c->n;
+   if (xyz)
+      CUDA_CHECK(cudaMemcpyAsync(c->xyz_d.p, xyz, b, cudaMemcpyHostToDevice, c->stream));
+   if (vel)
+      CUDA_CHECK(cudaMemcpyAsync(c->md->vel.p, vel, b, cudaMemcpyHostToDevice, c->stream));
+   if (xyz && !forces_valid) {
+      c->md_forces_valid = 0;
+      c->mpole_inited = 0, c->mpole_pme_valid = 0, c->induced_valid = 0;
+      apx_list_refresh(c, false);
+   }
+}
+
 void apx_md_destroy(apx_ctx* c)
 {
    if (!c->md)
