@@ -62,8 +62,16 @@ constexpr int devKind()
 void* stream0() { return (void*)g::s0; }      // the stream the reference's front-ends enqueue on
 }
 
-// copyPosToXyz + nblistRefresh (src/nblist.cpp:521) from the reference's own x / y / z device arrays: no host copy
-void apxAdapterRefreshPositions() { chk(apx_set_positions_dev(g_apx, x, y, z, EB, stream0())); }
+// copyPosToXyz + nblistRefresh (src/nblist.cpp:521) from the reference's own device arrays, no host copy: the integrator's
+// xpos / ypos / zpos (pos_prec: double also in the mixed build, include/ff/atom.h:39-45) when they exist -- the float copies
+// x / y / z have lost 4e-6 A at 60 A, which alone costs 2e-5 kcal/mol/A of force accuracy -- else x / y / z
+void apxAdapterRefreshPositions()
+{
+   if (xpos && ypos && zpos)
+      chk(apx_set_positions_dev(g_apx, xpos, ypos, zpos, (int)sizeof(pos_prec), stream0()));
+   else
+      chk(apx_set_positions_dev(g_apx, x, y, z, EB, stream0()));
+}
 
 // ---- *DataBinding_cu (src/cu/amoeba/binding.cu:11-52, called from src/elec.cpp:53 and src/amoeba/epolar.cpp:24): the
 //      reference mirrors its device pointers into __device__ globals (d::rpole, d::pdamp, ...) for its own kernels.  The

@@ -174,6 +174,7 @@ int dropin_open(const apx_system* sys, double list_buffer_of_usolve)
       cudalibData(RcOp::ALLOC);                              // the reference's own streams g::s0 / g::s1, queues and reduction scratch
       // coordinates as the reference holds them (include/ff/atom.h:39-45): the adapter reads these device arrays
       darray::allocate(n, &x, &y, &z);
+      darray::allocate(n, &xpos, &ypos, &zpos);      // the integrator's coordinates (mdData, pos_prec)
       {
          std::vector<double> cx(n), cy(n), cz(n);
          for (int i = 0; i < n; ++i)
@@ -181,6 +182,9 @@ int dropin_open(const apx_system* sys, double list_buffer_of_usolve)
          darray::copyin(g::q0, n, x, cx.data());
          darray::copyin(g::q0, n, y, cy.data());
          darray::copyin(g::q0, n, z, cz.data());
+         darray::copyin(g::q0, n, xpos, cx.data());
+         darray::copyin(g::q0, n, ypos, cy.data());
+         darray::copyin(g::q0, n, zpos, cz.data());
          waitFor(g::q0);
       }
       s_ewald_cut = sys->cutoff;
@@ -320,6 +324,9 @@ int dropin_set_xyz(const double* xyz)
       darray::copyin(g::q0, n, x, cx.data());
       darray::copyin(g::q0, n, y, cy.data());
       darray::copyin(g::q0, n, z, cz.data());
+      darray::copyin(g::q0, n, xpos, cx.data());
+      darray::copyin(g::q0, n, ypos, cy.data());
+      darray::copyin(g::q0, n, zpos, cz.data());
       waitFor(g::q0);
       apxAdapterRefreshPositions();
    });

@@ -193,7 +193,8 @@ def test_dhfr2_vs_oracle_fixture(precision):
     assert _rms(d1 - fx["udir"]) * DEBYE < tol["u"] and _rms(d2 - fx["udirp"]) * DEBYE < tol["u"]
     assert np.abs(r["virial"] - fx["virial"]).max() < tol["v"] * np.abs(fx["virial"]).max()
     assert r["pcg_iterations"] == int(fx["niter"])
-    assert a.stats()["npairs_m"] == int(fx["npairs"])
+    # the list is cut from float coordinates (4e-6 A at 60 A): of the 1.6 M pairs the one or two within that of 7 A may differ
+    assert abs(a.stats()["npairs_m"] - int(fx["npairs"])) <= 3
     a.close()
 
 
@@ -314,7 +315,7 @@ def test_device_pointer_entry_points(dtype):
     r1 = a.energy(calc.v0)
     a.set_positions(xyz if dtype == "float64" else xyz.astype(np.float32).astype(np.float64))
     r0 = a.energy(calc.v0)
-    assert abs(r1["esum"] - r0["esum"]) < 1e-9 * abs(r0["esum"])
+    assert abs(r1["esum"] - r0["esum"]) < 2e-8 * abs(r0["esum"])      # two evaluations: float atomics on the PME grid
     a.set_positions(s.xyz)
     # operators
     f0, f1 = a.dfield()

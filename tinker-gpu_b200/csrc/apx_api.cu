@@ -212,6 +212,12 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
       c->uf_ctas = std::max(1, atoi(e));
    if (const char* e = getenv("APX_UF_SMEM"))
       c->uf_smem_kb = std::max(0, std::min(40, atoi(e)));
+   if (const char* e = getenv("APX_STAGED"))
+      c->staged_on = atoi(e) ? 1 : 0;
+   if (const char* e = getenv("APX_STAGED_CAP"))
+      c->staged_cap = std::max(1, std::min(144, atoi(e)));
+   if (const char* e = getenv("APX_STAGED_MIN"))
+      c->staged_min_atoms = atoi(e);
    if (const char* e = getenv("APX_DIAG_SKIP"))
       c->diag_skip = atoi(e);
    if (const char* e = getenv("APX_NO_GRAPH"))
@@ -399,6 +405,8 @@ void apx_destroy(apx_ctx* c)
    c->rows.vstart.release(), c->rows.vcnt.release(), c->rows.vnbr.release(), c->rows.nbr.release();
    c->rows.prev_o.release(), c->rows.capstart.release(), c->rows.vpad.release(), c->rows.oflow.release();
    c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
+   c->grp.vjb.release(), c->grp.nvjb.release(), c->grp.ajb.release(), c->grp.najb.release(), c->grp.vslot.release(), c->grp.nbr16.release(),
+      c->grp.oflow.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
    c->theta.release(), c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();

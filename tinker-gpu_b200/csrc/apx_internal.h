@@ -132,6 +132,15 @@ struct RowList {
    int have_prev = 0;
 };
 
+// Groups of 64 sorted atoms with their j-blocks and 16-bit slot rows (staged.cu)
+struct GroupList {
+   int ok = 0, ngrp = 0;
+   DevBuf<int> vjb, nvjb;                // [ngrp][SG_VJB_CAP] Verlet j-blocks (ascending), their number
+   DevBuf<int> ajb, najb;                // the blocks still holding a partner inside the cutoff this step
+   DevBuf<unsigned short> vslot, nbr16;  // Verlet rows / per-step rows in slot form, same offsets as RowList::vnbr / nbr
+   DevBuf<int> oflow;
+};
+
 struct PairExcl {           // exclusion pair in SORTED indices with (scale-1) factors
    int i, k;
    real m, d, p, u;
@@ -245,6 +254,10 @@ struct apx_ctx {
    DevBuf<PairExcl> excl_s;              // exclusions in sorted indices
    real list_cutoff = 0, list_buffer = 0;
    RowList rows;
+   GroupList grp;                        // staged real-space operator (staged.cu)
+   int staged_on = 1;                    // APX_STAGED=0: row kernels only
+   int staged_cap = 64;                  // APX_STAGED_CAP: j-blocks of a group staged in shared memory (1.5 KB each)
+   int staged_min_atoms = 0;             // APX_STAGED_MIN: systems smaller than this keep the row operator
    int list_valid = 0;
    DevBuf<int> flags;                    // device flags: [0] rebuild-needed, [1] pcg done, [2] iter ...
    int* flags_h = nullptr;               // pinned mirror
@@ -396,6 +409,11 @@ void apx_rows_build(apx_ctx* c);      // Verlet rows, after the spatial sort
 void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bctr, const real4* bext, real range, const int* exoff,
    const int* exlist, real exrange, bool want_compact);
 void apx_rows_compact(apx_ctx* c, bool count);    // per-step compaction to r <= cutoff
+// ---- staged.cu
+bool apx_staged_usable(const apx_ctx* c);
+void apx_group_build(apx_ctx* c);                                 // after apx_rows_build
+void apx_rows_compact_grouped(apx_ctx* c, bool count);            // replaces apx_rows_compact when the groups are usable
+void apx_ufield_staged(apx_ctx* c, cudaStream_t st, real4* F);    // F = real-space field of the records in c->uf_rec
 // ---- frames.cu
 void apx_rotpole(apx_ctx* c);
 void apx_torque(apx_ctx* c, bool do_v);

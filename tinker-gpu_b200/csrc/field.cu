@@ -482,7 +482,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       c->uf_rec.ensure(3 * (size_t)c->npad);
       k_uf_records<<<(c->n + 255) / 256, 256, 0, st>>>(c->n, c->posq, c->tpj, U, c->uf_rec, c->skip);
       APX_COUNT_LAUNCH(c);
-      if (ew)
+      if (apx_staged_usable(c) && c->n >= c->staged_min_atoms)
+         apx_ufield_staged(c, st, F);      // records staged in shared memory by bulk copies (staged.cu)
+      else if (ew)
          k_ufield_rows_rec<true, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->uf_rec, F, c->skip);
       else
          k_ufield_rows_rec<false, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->uf_rec, F, c->skip);

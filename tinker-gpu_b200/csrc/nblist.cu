@@ -202,7 +202,8 @@ void apx_list_refresh(apx_ctx* c, bool force)
       return;
    }
    // the captured graphs hold the row buffers' addresses: they stay valid across a rebuild unless a buffer had to grow
-   const void* before[6] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p};
+   const void* before[11] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
+      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr};
    cudaEventRecord(c->ev2, c->stream);
    // 1. sort along the Morton curve
    const int nslab = c->dist.on ? c->dist.world : 1;
@@ -249,8 +250,9 @@ void apx_list_refresh(apx_ctx* c, bool force)
    c->mpole_inited = 0;     // sorted multipoles must be regenerated in the new order
    if (c->vdw.on)
       apx_vdw_refresh(c, true);
-   const void* after[6] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p};
-   for (int q = 0; q < 6; ++q)
+   const void* after[11] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
+      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr};
+   for (int q = 0; q < 11; ++q)
       if (before[q] != after[q]) {
          apx_pcg_graphs_invalidate(c);
          break;

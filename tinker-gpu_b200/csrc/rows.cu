@@ -273,6 +273,7 @@ void apx_rows_build(apx_ctx* c)
       k_rows_flag_listed<<<(2 * c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_s, c->a0, c->a1, c->rows.vstart, c->rows.vnbr);
       APX_COUNT_LAUNCH(c);
    }
+   apx_group_build(c);      // 64-atom groups, their j-blocks and slot rows for the staged operator (staged.cu)
 }
 
 // Verlet rows of the positions `pos` (sorted order, block boxes ctr/ext) within `range`.  exoff/exlist: optional CSR (caller
@@ -343,6 +344,14 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
          nullptr, L.vstart, L.vnbr, c->perm, exoff, exlist, exr2, nullptr);
    if (c->rows_onepass && !c->dist.on && a0 == 0 && a1 == n) {
       L.prev_o.ensure(n);
+      if (!L.have_prev) {
+         // what the NEXT (one-pass) build needs is allocated now, with the head-room of its padded slots: a cudaMalloc of
+         // tens of MB inside a later MD step costs milliseconds (measured: 10 ms on the first rebuild of a dhfr2 run)
+         const int slack = c->rows_onepass == 2 ? 0 : 1;
+         L.capstart.ensure(n + 1);
+         L.oflow.ensure(1);
+         L.vpad.ensure((size_t)(slack ? (long long)total + total / 8 + 16ll * n : (long long)total) + 64);
+      }
       k_rows_save_counts<<<(n + 255) / 256, 256, 0, c->stream>>>(n, c->perm, L.vcnt, L.prev_o);
       L.prev_total = total;
       L.have_prev = 1;
@@ -353,6 +362,10 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
 
 void apx_rows_compact(apx_ctx* c, bool count)
 {
+   if (apx_staged_usable(c)) {
+      apx_rows_compact_grouped(c, count);
+      return;
+   }
    RowList& L = c->rows;
    const int no = c->a1 - c->a0;
    const real cut = c->list_cutoff;
