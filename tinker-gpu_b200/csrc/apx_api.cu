@@ -212,6 +212,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
       c->uf_ctas = std::max(1, atoi(e));
    if (const char* e = getenv("APX_UF_SMEM"))
       c->uf_smem_kb = std::max(0, std::min(40, atoi(e)));
+   if (const char* e = getenv("APX_TLIST"))
+      c->tlist_on = atoi(e) ? 1 : 0;
    if (const char* e = getenv("APX_STAGED"))
       c->staged_on = atoi(e) ? 1 : 0;
    if (const char* e = getenv("APX_STAGED_CAP"))

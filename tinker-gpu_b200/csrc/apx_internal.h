@@ -255,7 +255,12 @@ struct apx_ctx {
    real list_cutoff = 0, list_buffer = 0;
    RowList rows;
    GroupList grp;                        // staged real-space operator (staged.cu)
-   int staged_on = 1;                    // APX_STAGED=0: row kernels only
+   int staged_on = 0;                    // APX_STAGED=1: staged operator (measured slower than the rows, profiles/r02d_*; kept for A/B)
+   // ---- stored-tensor real-space operator (tlist.cu): one real4 per directed pair inside the cutoff, written once per induce()
+   DevBuf<real4> tl_T;                   // same offsets as rows.nbr: {B1 (LSB = sign of B2), sqrt|B2| R}
+   DevBuf<real4> tl_P;                   // preconditioner tensors of the first cntu entries of every row
+   int tlist_on = 1;                     // APX_TLIST=0: recompute the pair geometry in every operator application (field.cu)
+   int tl_valid = 0;                     // tl_T / tl_P belong to the current positions and rows
    int staged_cap = 64;                  // APX_STAGED_CAP: j-blocks of a group staged in shared memory (1.5 KB each)
    int staged_min_atoms = 0;             // APX_STAGED_MIN: systems smaller than this keep the row operator
    int list_valid = 0;
@@ -414,6 +419,11 @@ bool apx_staged_usable(const apx_ctx* c);
 void apx_group_build(apx_ctx* c);                                 // after apx_rows_build
 void apx_rows_compact_grouped(apx_ctx* c, bool count);            // replaces apx_rows_compact when the groups are usable
 void apx_ufield_staged(apx_ctx* c, cudaStream_t st, real4* F);    // F = real-space field of the records in c->uf_rec
+// tlist.cu
+bool apx_tlist_usable(const apx_ctx* c);
+void apx_tlist_reserve(apx_ctx* c);                               // after apx_rows_build: buffers sized to the Verlet rows
+void apx_tlist_build(apx_ctx* c, cudaStream_t st);                // tensors of the current rows and positions
+void apx_ufield_tlist(apx_ctx* c, cudaStream_t st, const real4* U, real4* F);
 // ---- frames.cu
 void apx_rotpole(apx_ctx* c);
 void apx_torque(apx_ctx* c, bool do_v);

@@ -465,6 +465,10 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
 #define LAUNCH_UF(E, T)                                                                                                   \
    k_ufield_rows<E, T, UF_G><<<grid, ROWS_BLOCK, uf_smem, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq, c->tpj,  \
       c->thlval, c->opt.njpolar, U, F, c->skip)
+   // stored-tensor operator (tlist.cu): the first application after the positions changed writes the tensors
+   const bool tl = apx_tlist_usable(c);
+   if (tl && !c->tl_valid)
+      apx_tlist_build(c, st);
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
    const bool ext = c->capturing && c->graph_key_open >= 0 && (c->graph_key_open & 0x2000) && c->uf_ev.size() >= 2;
@@ -477,7 +481,9 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       c->uf_used += 2;
       cudaEventRecord(c->uf_ev[slot], st);
    }
-   if (!tb && c->use_records) {
+   if (tl) {
+      apx_ufield_tlist(c, st, U, F);
+   } else if (!tb && c->use_records) {
       // records of every atom a row can reach: the whole system (halo atoms included on several GPUs)
       c->uf_rec.ensure(3 * (size_t)c->npad);
       k_uf_records<<<(c->n + 255) / 256, 256, 0, st>>>(c->n, c->posq, c->tpj, U, c->uf_rec, c->skip);

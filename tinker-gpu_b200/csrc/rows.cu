@@ -19,7 +19,6 @@
 #define FULL 0xffffffffu
 
 namespace {
-#define RB_W 4      // warps sharing one i-block: each takes 32/RB_W of its atoms
 
 // bounding boxes of super-blocks (32 consecutive blocks = 1024 sorted atoms): first level of the
 // search, so a warp looks at nblk/32 boxes instead of nblk before it descends
@@ -61,101 +60,191 @@ __device__ __forceinline__ bool boxes_within(const Box& b, real4 ci, real4 ei, r
    return dx * dx + dy * dy + dz * dz <= range2;
 }
 
-// RB_W warps per i-block; lane j of a warp keeps the running length of the row of atom 32*ib + j
-// (only the atoms of this warp's share, and only atoms inside the owned range [a0,a1))
-// MODE 0: count only (vcnt).  MODE 1: fill exact rows at vstart.  MODE 2: fill padded slots [vstart[s], vstart[s+1]) AND count:
-// a row that outgrows its slot raises *oflow and stops writing, the count stays exact.
+// One CTA (4 warps) per i-block.  MODE 0: count only (vcnt).  MODE 1: fill exact rows at vstart.  MODE 2: fill padded slots
+// [vstart[s], vstart[s+1]) AND count: a row that outgrows its slot raises *oflow and is not written, the count stays exact.
+//
+//   candidates   the CTA culls the super-block boxes (128 per round), then the 32 blocks of every surviving super-block (one
+//                super-block per warp), and appends the surviving j-blocks IN ASCENDING ORDER to a shared list; every
+//                RB_CAP candidates (and at the end) the chunk is processed:
+//   pass A       the warps split the CANDIDATES: lane = one j-atom; j-atoms outside the range of the i-block's box and
+//                i-atoms outside the range of the j-block's box are dropped before any pair is tested; for the remaining
+//                i-atoms (position broadcast from shared memory) one ballot per (candidate, i-atom) gives the 32-bit mask of
+//                listed j-atoms, kept in shared memory -- every distance is computed once, by one warp;
+//   pass B       the warps split the I-ATOMS: the row length of the chunk is the popcount sum of the atom's masks, and the
+//                set bits are written at running offsets (k ascending, as k_rows_flag_listed's binary search expects).
+// The previous version gave each of an i-block's 4 warps a quarter of its ATOMS: each warp repeated the whole candidate
+// search and walked every candidate once per atom (505 us + 1090 us for the two lists of dhfr2, profiles/r02e_trace_md.txt).
+#define RB_THREADS 128
+#define RB_CAP 256      // candidate j-blocks per chunk: 32 KB of masks
+
 template <int MODE>
-__global__ void __launch_bounds__(128) k_rows_build(int n, int nblk, int nsb, int a0, int a1, Box b, real range,
+__global__ void __launch_bounds__(RB_THREADS) k_rows_build(int n, int nblk, int nsb, int a0, int a1, Box b, real range,
    const real4* __restrict__ posd, const real4* __restrict__ ctr, const real4* __restrict__ ext, const real4* __restrict__ sctr,
    const real4* __restrict__ sext, int* __restrict__ vcnt, const int* __restrict__ vstart, int* __restrict__ vnbr,
    const int* __restrict__ perm, const int* __restrict__ exoff, const int* __restrict__ exlist, real exr2, int* __restrict__ oflow)
 {
-   constexpr bool FILL = MODE != 0;
-   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-   const int ib = a0 / 32 + gw / RB_W, sub = gw % RB_W;
-   const int lane = threadIdx.x & 31;
+   __shared__ real4 s_pi[32];
+   __shared__ unsigned s_mask[RB_CAP][32];
+   __shared__ int s_cand[RB_CAP];
+   __shared__ int s_sb[RB_THREADS];
+   __shared__ int s_wcount[4];
+   __shared__ int s_row[32];      // running row length of every i-atom
+   __shared__ int s_base[32], s_room[32];
+   const int ib = a0 / 32 + blockIdx.x;
    if (ib >= nblk || ib * 32 >= a1)
       return;
+   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
    const real range2 = range * range;
    const real4 ci = ctr[ib], ei = ext[ib];
-   const int si = ib * 32 + lane;
-   const real4 pi = posd[min(si, n - 1)];
-   // atoms of this i-block handled by this warp
-   const int q0 = max(sub * (32 / RB_W), a0 - ib * 32);
-   const int q1 = min(min((sub + 1) * (32 / RB_W), n - ib * 32), a1 - ib * 32);
-   if (q0 >= q1)
-      return;
-   int mycount = 0;
-   const int mybase = (FILL && si < n) ? vstart[si] : 0;
-   const int mycap = (MODE == 2 && si < n) ? vstart[si + 1] - vstart[si] : 0;
+   // i-atoms of this block that get a row: inside the system and inside the owned range [a0, a1)
+   const int q0 = max(0, a0 - ib * 32), q1 = min(32, min(n, a1) - ib * 32);
+   if (t < 32) {
+      const int si = ib * 32 + t;
+      s_pi[t] = posd[min(si, n - 1)];
+      s_row[t] = 0;
+      const bool real_i = t >= q0 && t < q1;
+      s_base[t] = (MODE != 0 && real_i) ? vstart[si] : 0;
+      s_room[t] = (MODE == 2 && real_i) ? vstart[si + 1] - vstart[si] : 0x7fffffff;
+   }
+   __syncthreads();
    const unsigned lt = (1u << lane) - 1;
-   for (int sb0 = 0; sb0 < nsb; sb0 += 32) {
-      const int sb = sb0 + lane;
-      unsigned sm = __ballot_sync(FULL, sb < nsb && boxes_within(b, ci, ei, sctr[min(sb, nsb - 1)], sext[min(sb, nsb - 1)], range2));
-      while (sm) {
-         const int kb0 = (sb0 + __ffs(sm) - 1) * 32;
-         sm &= sm - 1;
-         const int kb = kb0 + lane;
-         unsigned hm = __ballot_sync(FULL, kb < nblk && boxes_within(b, ci, ei, ctr[min(kb, nblk - 1)], ext[min(kb, nblk - 1)], range2));
-         while (hm) {
-            int j = __ffs(hm) - 1;
-            hm &= hm - 1;
-            int s = (kb0 + j) * 32 + lane;
-            real4 pk = posd[min(s, n - 1)];
-            bool in = false;
-            if (s < n) {
-               real dx = pk.x - ci.x, dy = pk.y - ci.y, dz = pk.z - ci.z;
-               apx_image(b, dx, dy, dz);
-               dx = max((real)0, fabs(dx) - ei.x);
-               dy = max((real)0, fabs(dy) - ei.y);
-               dz = max((real)0, fabs(dz) - ei.z);
-               in = dx * dx + dy * dy + dz * dz <= range2;
+   const unsigned qmask = (q1 >= 32 ? 0xffffffffu : ((1u << q1) - 1)) & ~((1u << q0) - 1);
+   int ncand = 0;      // uniform across the CTA
+
+   auto process = [&](int nc) {
+      // ---- pass A: masks
+      for (int c = w; c < nc; c += 4) {
+         const int kb = s_cand[c];
+         const int s = kb * 32 + lane;
+         const real4 pk = posd[min(s, n - 1)];
+         bool in = false;
+         if (s < n) {
+            real dx = pk.x - ci.x, dy = pk.y - ci.y, dz = pk.z - ci.z;
+            apx_image(b, dx, dy, dz);
+            dx = max((real)0, fabs(dx) - ei.x);
+            dy = max((real)0, fabs(dy) - ei.y);
+            dz = max((real)0, fabs(dz) - ei.z);
+            in = dx * dx + dy * dy + dz * dz <= range2;
+         }
+         unsigned im = 0;
+         if (__ballot_sync(FULL, in)) {
+            const real4 ck = ctr[kb], ek = ext[kb], pq = s_pi[lane];
+            real dx = pq.x - ck.x, dy = pq.y - ck.y, dz = pq.z - ck.z;
+            apx_image(b, dx, dy, dz);
+            dx = max((real)0, fabs(dx) - ek.x);
+            dy = max((real)0, fabs(dy) - ek.y);
+            dz = max((real)0, fabs(dz) - ek.z);
+            im = __ballot_sync(FULL, dx * dx + dy * dy + dz * dz <= range2) & qmask;
+         }
+         unsigned mine = 0;
+         while (im) {
+            const int q = __ffs(im) - 1;
+            im &= im - 1;
+            const real4 pq = s_pi[q];
+            real dx = pk.x - pq.x, dy = pk.y - pq.y, dz = pk.z - pq.z;
+            apx_image(b, dx, dy, dz);
+            const real r2q = dx * dx + dy * dy + dz * dz;
+            bool ok = in && s != ib * 32 + q && r2q <= range2;
+            if (exoff && __any_sync(FULL, ok && r2q <= exr2)) {
+               // pairs that never interact (vdW 1-2/1-3 with scale 0) are left out of the rows for good:
+               // exclusion is topology, so it is tested at list build, not in the pair kernel
+               const int cq = perm[ib * 32 + q];
+               const int eb = exoff[cq], ee = exoff[cq + 1];
+               if (ok && r2q <= exr2) {
+                  const int ck = perm[s];
+                  for (int e = eb; e < ee; ++e)
+                     if (exlist[e] == ck)
+                        ok = false;
+               }
             }
-            if (!__ballot_sync(FULL, in))
-               continue;
-            for (int q = q0; q < q1; ++q) {
-               real dx = pk.x - __shfl_sync(FULL, pi.x, q), dy = pk.y - __shfl_sync(FULL, pi.y, q),
-                    dz = pk.z - __shfl_sync(FULL, pi.z, q);
-               apx_image(b, dx, dy, dz);
-               const real r2q = dx * dx + dy * dy + dz * dz;
-               bool ok = in && s != ib * 32 + q && r2q <= range2;
-               if (exoff && __any_sync(FULL, ok && r2q <= exr2)) {
-                  // pairs that never interact (vdW 1-2/1-3 with scale 0) are left out of the rows for good:
-                  // exclusion is topology, so it is tested at list build, not in the pair kernel
-                  const int ci = perm[ib * 32 + q];
-                  const int eb = exoff[ci], ee = exoff[ci + 1];
-                  if (ok && r2q <= exr2) {
-                     const int ck = perm[s];
-                     for (int e = eb; e < ee; ++e)
-                        if (exlist[e] == ck)
-                           ok = false;
-                  }
+            const unsigned m = __ballot_sync(FULL, ok);
+            if (lane == q)
+               mine = m;
+         }
+         s_mask[c][lane] = mine;
+      }
+      __syncthreads();
+      // ---- pass B: rows
+      for (int q = w * 8; q < w * 8 + 8; ++q) {
+         if (!((qmask >> q) & 1u))
+            continue;
+         int tot = 0;
+         for (int c = lane; c < nc; c += 32)
+            tot += __popc(s_mask[c][q]);
+         #pragma unroll
+         for (int o = 16; o > 0; o >>= 1)
+            tot += __shfl_xor_sync(FULL, tot, o);
+         const int have = s_row[q];
+         if (MODE != 0 && tot > 0) {
+            if (have + tot <= s_room[q]) {
+               int off = s_base[q] + have;
+               for (int c = 0; c < nc; ++c) {
+                  const unsigned m = s_mask[c][q];
+                  if ((m >> lane) & 1u)
+                     vnbr[off + __popc(m & lt)] = s_cand[c] * 32 + lane;
+                  off += __popc(m);
                }
-               unsigned m = __ballot_sync(FULL, ok);
-               if (MODE == 1) {
-                  int off = __shfl_sync(FULL, mybase + mycount, q);
-                  if (ok)
-                     vnbr[off + __popc(m & lt)] = s;
-               }
-               if (MODE == 2) {
-                  const int off = __shfl_sync(FULL, mybase + mycount, q);
-                  const int room = __shfl_sync(FULL, mycap - mycount, q);
-                  if (__popc(m) <= room) {
-                     if (ok)
-                        vnbr[off + __popc(m & lt)] = s;
-                  } else if (lane == 0) {
-                     *oflow = 1;
-                  }
-               }
-               if (lane == q)
-                  mycount += __popc(m);
+            } else if (lane == 0) {
+               *oflow = 1;
+               s_room[q] = -1;      // the row stays unwritten from here on
             }
+         }
+         __syncwarp();
+         if (lane == 0)
+            s_row[q] = have + tot;
+      }
+      __syncthreads();
+   };
+
+   for (int sb0 = 0; sb0 < nsb; sb0 += RB_THREADS) {
+      // super-blocks within range, ascending
+      const int sb = sb0 + t;
+      const bool hit = sb < nsb && boxes_within(b, ci, ei, sctr[min(sb, nsb - 1)], sext[min(sb, nsb - 1)], range2);
+      const unsigned hm = __ballot_sync(FULL, hit);
+      if (lane == 0)
+         s_wcount[w] = __popc(hm);
+      __syncthreads();
+      int before = 0, nsbhit = 0;
+      #pragma unroll
+      for (int k = 0; k < 4; ++k) {
+         before += k < w ? s_wcount[k] : 0;
+         nsbhit += s_wcount[k];
+      }
+      if (hit)
+         s_sb[before + __popc(hm & lt)] = sb;
+      __syncthreads();
+      // their blocks, one super-block per warp and round
+      for (int j0 = 0; j0 < nsbhit; j0 += 4) {
+         const int j = j0 + w;
+         unsigned bm = 0;
+         int kb = 0;
+         if (j < nsbhit) {
+            kb = s_sb[j] * 32 + lane;
+            bm = __ballot_sync(FULL, kb < nblk && boxes_within(b, ci, ei, ctr[min(kb, nblk - 1)], ext[min(kb, nblk - 1)], range2));
+         }
+         if (lane == 0)
+            s_wcount[w] = __popc(bm);
+         __syncthreads();
+         int pre = 0, add = 0;
+         #pragma unroll
+         for (int k = 0; k < 4; ++k) {
+            pre += k < w ? s_wcount[k] : 0;
+            add += s_wcount[k];
+         }
+         if ((bm >> lane) & 1u)
+            s_cand[ncand + pre + __popc(bm & lt)] = kb;
+         ncand += add;
+         __syncthreads();
+         if (ncand > RB_CAP - 128) {
+            process(ncand);
+            ncand = 0;
          }
       }
    }
-   if (MODE != 1 && lane >= q0 && lane < q1)
-      vcnt[si] = mycount;
+   if (ncand > 0)
+      process(ncand);
+   if (MODE != 1 && t < 32 && ((qmask >> t) & 1u))
+      vcnt[ib * 32 + t] = s_row[t];
 }
 
 // padded slot sizes from the previous build's row lengths (caller order): +12.5 % + 16 entries (slack 0: exactly the old length)
@@ -273,6 +362,7 @@ void apx_rows_build(apx_ctx* c)
       k_rows_flag_listed<<<(2 * c->nexcl + 255) / 256, 256, 0, c->stream>>>(c->nexcl, c->excl_s, c->a0, c->a1, c->rows.vstart, c->rows.vnbr);
       APX_COUNT_LAUNCH(c);
    }
+   apx_tlist_reserve(c);    // stored pair tensors of the operator (tlist.cu), same offsets as the rows
    apx_group_build(c);      // 64-atom groups, their j-blocks and slot rows for the staged operator (staged.cu)
 }
 
@@ -284,7 +374,7 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
    const int n = c->n, nblk = c->nblk, nsb = (nblk + 31) / 32;
    const int a0 = c->a0, a1 = c->a1;
    const int nib = a1 > a0 ? (a1 + 31) / 32 - a0 / 32 : 0;      // i-blocks that hold owned atoms
-   const int grid = std::max(1, (nib * RB_W * 32 + 127) / 128);
+   const int grid = std::max(1, nib);      // one CTA per i-block
    const real exr2 = exrange * exrange;
    L.vstart.ensure(n + 1);
    L.vcnt.ensure(n + 1);
@@ -315,11 +405,11 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
       scan(L.vcnt.p, L.capstart.p);
       CUDA_CHECK(cudaMemsetAsync(L.vcnt.p, 0, sizeof(int) * (n + 1), c->stream));
       CUDA_CHECK(cudaMemsetAsync(L.oflow.p, 0, sizeof(int), c->stream));
-      k_rows_build<2><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext, L.vcnt, L.capstart,
+      k_rows_build<2><<<grid, RB_THREADS, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext, L.vcnt, L.capstart,
          L.vpad, c->perm, exoff, exlist, exr2, L.oflow);
       c->stats.kernel_launches += 2;
    } else {
-      k_rows_build<0><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+      k_rows_build<0><<<grid, RB_THREADS, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
          L.vcnt, nullptr, nullptr, c->perm, exoff, exlist, exr2, nullptr);
    }
    scan(L.vcnt.p, L.vstart.p);
@@ -340,7 +430,7 @@ void apx_rows_build_on(apx_ctx* c, RowList& L, const real4* pos, const real4* bc
       filled = true;
    }
    if (!filled)      // two-pass path, or a row outgrew its slot: the counts are exact either way
-      k_rows_build<1><<<grid, 128, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
+      k_rows_build<1><<<grid, RB_THREADS, 0, c->stream>>>(n, nblk, nsb, a0, a1, c->box, range, pos, bctr, bext, L.sctr, L.sext,
          nullptr, L.vstart, L.vnbr, c->perm, exoff, exlist, exr2, nullptr);
    if (c->rows_onepass && !c->dist.on && a0 == 0 && a1 == n) {
       L.prev_o.ensure(n);
