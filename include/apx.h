@@ -166,6 +166,7 @@ typedef struct apx_stats {
    long long npairs_u;     /* pairs inside the preconditioner range at the last list build */
    float ms_ehal;          /* device time of the vdW row kernel of the last evaluation */
    long long nverlet_vdw;  /* directed entries of the vdW Verlet rows */
+   int energy_retries;     /* evaluations repeated because the solver's first, unawaited batch of iterations did not converge */
 } apx_stats;
 
 const char* apx_last_error(void);

@@ -116,3 +116,32 @@ def test_tlist_with_thole_table():
         a.close()
     assert abs(res[True]["esum"] - res[False]["esum"]) < 1e-6 * abs(res[False]["esum"])
     assert res[True]["pcg_iterations"] == res[False]["pcg_iterations"]
+
+
+def test_deferred_solver_batch_and_retry():
+    """energy() enqueues the solver's first batch of iterations and the energy epilogue without waiting for the convergence flag
+    (csrc/pcg.cu, csrc/mplar.cu: energy_once).  APX_PCG_FIRST_BATCH=3 makes that batch too short on purpose: the evaluation must
+    notice, repeat itself with a solver that waits for its batches, and return the same energies, forces and iteration count."""
+    import subprocess
+    import sys
+    import json
+    code = ("import os,sys,json,numpy as np;sys.path.insert(0,%r);import tinker_gpu_b200 as tg;from tinker_gpu_b200.amoeba import Amoeba,calc;"
+            "s=tg.load_system(%r);a=Amoeba(s,'mixed',device=0,vdw=False);out=[];\n"
+            "for j in range(4):\n"
+            "    a.set_positions(np.array(s.xyz)+0.01*j)\n"
+            "    r=a.energy(calc.v1)\n"
+            "    out.append(dict(esum=r['esum'],it=r['pcg_iterations'],g=float(np.abs(r['grad']).sum()),v=float(np.abs(r['virial']).sum())))\n"
+            "st=a.stats();a.close();print(json.dumps(dict(out=out,retries=st['energy_retries'])))"
+            % (ROOT, os.path.join(GOLDEN, "water30.npz")))
+    res = {}
+    for forced in ("0", "3"):
+        env = dict(os.environ, APX_PCG_FIRST_BATCH=forced)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        res[forced] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["0"]["retries"] == 0
+    assert res["3"]["retries"] >= 2      # every evaluation after the first (eager) one
+    for x, y in zip(res["0"]["out"], res["3"]["out"]):
+        assert x["it"] == y["it"]
+        assert abs(x["esum"] - y["esum"]) < 2e-8 * abs(x["esum"])
+        assert abs(x["g"] - y["g"]) < 1e-6 * x["g"] and abs(x["v"] - y["v"]) < 1e-6 * x["v"]

@@ -147,7 +147,7 @@ class Stats(C.Structure):
     _fields_ = [("ms_induce", C.c_float), ("ms_energy", C.c_float), ("ms_list", C.c_float), ("ms_ufield_real", C.c_float),
                 ("pcg_iterations", C.c_int), ("kernel_launches", C.c_int), ("list_rebuilds", C.c_int),
                 ("nverlet", C.c_longlong), ("npairs_m", C.c_longlong), ("npairs_u", C.c_longlong),
-                ("ms_ehal", C.c_float), ("nverlet_vdw", C.c_longlong)]
+                ("ms_ehal", C.c_float), ("nverlet_vdw", C.c_longlong), ("energy_retries", C.c_int)]
 
 
 _LIBS = {}

@@ -212,6 +212,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
       c->uf_ctas = std::max(1, atoi(e));
    if (const char* e = getenv("APX_UF_SMEM"))
       c->uf_smem_kb = std::max(0, std::min(40, atoi(e)));
+   if (const char* e = getenv("APX_LOOP"))
+      c->use_loop = atoi(e) ? 1 : 0;
    if (const char* e = getenv("APX_TLIST"))
       c->tlist_on = atoi(e) ? 1 : 0;
    if (const char* e = getenv("APX_STAGED"))
@@ -766,6 +768,7 @@ int apx_stats_reset(apx_ctx* c)
    API_BEGIN
    c->stats.kernel_launches = 0;
    c->stats.list_rebuilds = 0;
+   c->stats.energy_retries = 0;
    API_END
 }
 

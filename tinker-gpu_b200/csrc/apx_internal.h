@@ -269,6 +269,7 @@ struct apx_ctx {
 
    // ---- fields / CG vectors, sorted order, [npad][3]
    DevBuf<real> field, fieldp, udir, udirp, uind, uinp;
+   DevBuf<real> field_rs;                // real-space part of the permanent field while the PME part is computed beside it
    DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
    DevBuf<real4> pk_p, pk_r, pk_z, pk_v, pk_f;   // packed (d,p) pairs, dp.cuh: direction, residual, M r, A p, real-space field
    DevBuf<real4> uf_rec;                 // [npad][3] interleaved neighbour records of the ufield rows (field.cu)
@@ -330,6 +331,14 @@ struct apx_ctx {
       int launches;
    };
    std::vector<PcgGraph> graphs;
+   // the PCG loop as ONE graph: a conditional WHILE node whose body is one iteration; the preconditioner kernel ends the loop
+   // from the device when the stopping rule is met (pcg.cu)
+   cudaGraphExec_t loop_exec = nullptr;
+   int loop_launches = 0;          // kernels of ours per iteration of the body
+   int loop_warm = 0;
+   int use_loop = 0;               // APX_LOOP=1: the WHILE-node loop (measured: +16 us per iteration on this driver, profiles/r02h)
+   int pcg_n = 0, pcg_n_slack = 0; // iterations in the first batch of a solve (largest count seen recently)
+   int induce_pending = 0, induce_pending_predict = 0;      // a deferred solve awaits apx_induce_finish
    int use_graph = 1;
    int capturing = 0;
    // ---- CUDA graphs of the fixed launch sequences around the solver (pcg.cu: apx_graph_begin/end): mpoleInit + zeroing,
@@ -366,7 +375,8 @@ inline BoxD apx_box_d(const apx_ctx* c)
 #define APX_COUNT_LAUNCH(ctx) ((ctx)->stats.kernel_launches++)
 
 // ---- nblist.cu
-void apx_list_refresh(apx_ctx* c, bool force);
+void apx_list_refresh(apx_ctx* c, bool force, int known_moved = -1);
+void apx_list_check_enqueue(apx_ctx* c, cudaStream_t st, double* seq = nullptr);
 void apx_update_sorted_positions(apx_ctx* c);
 // ---- dist.cu
 void apx_dist_after_sort(apx_ctx* c);                              // ownership bounds + halo plan (at list rebuild)
@@ -435,7 +445,8 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev);                   // fills fmp, fp
 void apx_pme_zero_grid(apx_ctx* c);
 void apx_pme_spread_dp(apx_ctx* c, const real4* U);              // grid += spread of a packed dipole pair
 void apx_pme_convolve(apx_ctx* c);                               // FFT, influence function, inverse FFT
-void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot);
+void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot,
+   const int* itp = nullptr);
 void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool full20);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 // ---- fft64.cu
@@ -443,10 +454,12 @@ bool apx_fft64_usable(const apx_ctx* c);
 void apx_fft64_setup(apx_ctx* c);
 void apx_fft64_convolve(apx_ctx* c);                             // grid <- IFFT(qfac * FFT(grid))
 // ---- field.cu
-void apx_dfield_real(apx_ctx* c, real* fd, real* fp);
+void apx_dfield_real(apx_ctx* c, cudaStream_t st, real* fd, real* fp, bool assign);
 void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F);    // F = real-space field of U (assigned)
 struct PcgTest {          // convergence test fused into the preconditioner kernel of iteration `it` (it = 0: none)
    int it = 0, miniter = 0, politer = 0;
+   const int* itp = nullptr;       // device-side loop (pcg.cu): the iteration number is *itp, `slot` is the slot of iteration 1
+   unsigned long long cond = 0;    // conditional handle of the WHILE node the iterations run in: set to 0 on convergence
    real poleps = 0, debye = 0, pcgpeek = 0;
    const double* slot = nullptr;   // slot of iteration it (r.r in quantities 4,5)
    double* result = nullptr;       // [0] eps, [1] iteration
@@ -455,9 +468,22 @@ struct PcgTest {          // convergence test fused into the preconditioner kern
    real* up = nullptr;
 };
 void apx_precond_dp(apx_ctx* c, const real4* R, real4* Z, double* slot, const PcgTest* test = nullptr);   // Z = M R ; partial R.Z -> slot
+// iteration-relative scalar slots: with itp the kernels of an iteration find their slot themselves, base + PCG_SLOT (*itp - 1)
+#define PCG_SLOT_DOUBLES 96
+#ifdef __CUDACC__
+__device__ __forceinline__ double* pcg_slot_of(double* base, const int* itp)
+{
+   return itp ? base + (size_t)PCG_SLOT_DOUBLES * (*itp - 1) : base;
+}
+__device__ __forceinline__ const double* pcg_slot_of(const double* base, const int* itp)
+{
+   return itp ? base + (size_t)PCG_SLOT_DOUBLES * (*itp - 1) : base;
+}
+#endif
 void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp);
 // ---- pcg.cu
-void apx_induce_impl(apx_ctx* c);
+bool apx_induce_impl(apx_ctx* c, bool defer = false);      // true: apx_induce_finish is pending (after the caller's synchronisation)
+bool apx_induce_finish(apx_ctx* c);                         // false: not converged in the deferred batch, redo without defer
 void apx_pcg_graphs_invalidate(apx_ctx* c);
 // if (apx_graph_begin(c, key)) { enqueue the region on c->stream; apx_graph_end(c, key); }
 // first call: runs eagerly (lazy allocations happen); second: captured, instantiated, launched; later: replayed.

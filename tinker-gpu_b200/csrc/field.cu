@@ -15,6 +15,7 @@
 #include "pairmath.cuh"
 #include "rows.cuh"
 #include "dp.cuh"
+#include "tlist.cuh"
 
 namespace {
 __device__ __forceinline__ int as_int(real w)
@@ -202,7 +203,7 @@ template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
-   const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign)
+   const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign, real4* __restrict__ T)
 {
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
@@ -231,6 +232,10 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box 
          const real B2 = (EWALD ? bn[2] : rr[2]) - om[2] * rr[2];
          const real B3 = (EWALD ? bn[3] : rr[3]) - om[3] * rr[3];
          fi += mpole_field(v3(dx, dy, dz), mk, B1, B2, B3, (real)-1);
+         // the mutual-field operator of the solver that follows needs exactly these B1, B2 and R for this pair, in every one of
+         // its applications: store them once (tlist.cu)
+         if (T)
+            T[beg + q] = tl_pack(B1, B2, dx, dy, dz);
       }
       fi = group_sum3<G>(fi);
       if (l == 0 && act) {
@@ -304,6 +309,11 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int
    // it is met the kernel applies the peek step u += peek*alpha*r instead of z = M r, and the last
    // CTA raises the stop flag (so no CTA of this grid can see it early).
    bool done = false;
+   if (T.itp) {      // device-side loop: this kernel belongs to iteration *itp, its slots follow from it
+      T.it = *T.itp;
+      T.slot = pcg_slot_of(T.slot, T.itp);
+      slot = slot ? pcg_slot_of(slot, T.itp) : nullptr;
+   }
    if (T.it > 0) {
       double rr2_[2];
       pcg_q_block<2>(T.slot, 4, rr2_);
@@ -336,6 +346,8 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int
             T.flags[3] = 0;
             __threadfence();
             T.flags[1] = 1;
+            if (T.cond)
+               cudaGraphSetConditional((cudaGraphConditionalHandle)T.cond, 0);      // leave the WHILE node (pcg.cu)
          }
       }
       return;
@@ -428,8 +440,9 @@ __global__ void k_precond_excl(int nx, int a0, int a1, Box box, real cut2, const
 
 // partial R.Z after an exclusion pass changed Z (only needed when u-scale exclusions exist)
 __global__ void k_dot_dp(int n, const real4* __restrict__ A, const real4* __restrict__ Bv, double* __restrict__ slot,
-   const int* __restrict__ skip)
+   const int* __restrict__ skip, const int* __restrict__ itp)
 {
+   slot = pcg_slot_of(slot, itp);
    if (skip && skip[1])
       return;
    int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -514,17 +527,19 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    }
 }
 
-// fd accumulates the common field + d corrections; fpd receives the (p - d) delta only
-void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
+// fd accumulates (assign = false) or receives (assign = true) the common field + d corrections; fpd receives the (p - d) delta
+// only.  With the stored-tensor operator in use the row pass also writes the pair tensors of the mutual field (tlist.cu).
+void apx_dfield_real(apx_ctx* c, cudaStream_t st, real* fd, real* fpd, bool assign)
 {
    RowList& L = c->rows;
    real cut = (real)c->opt.cutoff;
    bool ew = c->opt.use_ewald != 0;
    bool tb = c->thole_table != 0;
    int grid = rows_grid<DF_G>(c);
-#define LAUNCH_DF(E, T)                                                                                                   \
-   k_dfield_rows<E, T, DF_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq,  \
-      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, ew ? 0 : 1)
+   real4* T = (apx_tlist_usable(c) && c->opt.use_polar && c->opt.poltyp_mutual) ? c->tl_T.p : nullptr;
+#define LAUNCH_DF(E, T_)                                                                                                  \
+   k_dfield_rows<E, T_, DF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq,  \
+      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, assign ? 1 : 0, T)
    // (rows may all be empty for a tiny system: the kernel still initialises fd / fpd)
    if (ew && tb) LAUNCH_DF(true, true);
    else if (ew) LAUNCH_DF(true, false);
@@ -532,13 +547,15 @@ void apx_dfield_real(apx_ctx* c, real* fd, real* fpd)
    else LAUNCH_DF(false, false);
    APX_COUNT_LAUNCH(c);
 #undef LAUNCH_DF
+   if (T)
+      c->tl_valid = 1;
    if (c->nexcl > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
-         k_dfield_excl<true><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
+         k_dfield_excl<true><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       else
-         k_dfield_excl<false><<<g, 128, 0, c->stream>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
+         k_dfield_excl<false><<<g, 128, 0, st>>>(c->nexcl, c->a0, c->a1, c->box, cut * cut, c->excl_s, c->posd, c->posq, c->tpj, c->thlval,
             c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd);
       APX_COUNT_LAUNCH(c);
    }
@@ -577,7 +594,7 @@ void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const P
             Rv, Z, c->skip);
       APX_COUNT_LAUNCH(c);
       if (slot) {
-         k_dot_dp<<<(c->a1 - c->a0 + 127) / 128, 128, 0, c->stream>>>(c->a1 - c->a0, Rv + 2 * c->a0, Z + 2 * c->a0, slot, c->skip);
+         k_dot_dp<<<(c->a1 - c->a0 + 127) / 128, 128, 0, c->stream>>>(c->a1 - c->a0, Rv + 2 * c->a0, Z + 2 * c->a0, slot, c->skip, T.itp);
          APX_COUNT_LAUNCH(c);
       }
    }

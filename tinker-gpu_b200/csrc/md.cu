@@ -15,6 +15,7 @@
 // next evaluation, so no separate copy / zero passes exist (the reference copies gx -> gx1/gx2 three arrays at a time).
 // All per-atom passes are HBM streams of 24 (x) + 24 (v) + 24..48 (g) + 8 (1/m) B per atom: ~3 MB at dhfr2, L2-resident.
 #include "apx_internal.h"
+#include <chrono>
 #include <cmath>
 #include <cstring>
 
@@ -26,6 +27,8 @@ struct MdState {
    DevBuf<double> sc;      // [0] sum m v^2 of this step, [1] eksum (kcal/mol) after the thermostat, [2] temperature, [3] last scale
    double* sc_h = nullptr;
    cudaEvent_t t0 = nullptr, t1 = nullptr;
+   int graph_has_check = 0;      // the captured step graph contains the neighbour-list test
+   int seq_host = 0;             // sequence number the next published list test will carry (device copy: sc[7])
 };
 
 namespace {
@@ -174,12 +177,12 @@ static void md_kick(apx_ctx* c, bool drift, bool kin, double cf, double cs, doub
    APX_COUNT_LAUNCH(c);
 }
 
-static void md_positions_changed(apx_ctx* c)
+static void md_positions_changed(apx_ctx* c, int known_moved)
 {
    c->mpole_inited = 0;
    c->mpole_pme_valid = 0;
    c->induced_valid = 0;
-   apx_list_refresh(c, false);
+   apx_list_refresh(c, false, known_moved);
 }
 
 // kick-off (RespaIntegrator::KickOff, src/md/integrator.cpp:205-222): fast gradient into the valence accumulator, slow gradient
@@ -248,6 +251,8 @@ void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const a
    CUDA_CHECK(cudaMemcpyAsync(M.massinv.p, mi.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
    CUDA_CHECK(cudaMemcpyAsync(M.mass.p, mass, sizeof(double) * n, cudaMemcpyHostToDevice, st));
    CUDA_CHECK(cudaMemsetAsync(M.sc.p, 0, sizeof(double) * 8, st));
+   M.seq_host = 0;
+   c->flags_h[7] = 0;
    CUDA_CHECK(cudaStreamSynchronize(st));
    md_kickoff_forces(c);
    // kinetic energy of the starting velocities
@@ -276,6 +281,7 @@ void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out)
       md_kickoff_forces(c);
    cudaEventRecord(M.t0, st);
    for (int s = 0; s < nsteps; ++s) {
+      bool check_async = false;
       if (apx_graph_begin(c, 0x3000 + nr)) {
          k_md_zero1<<<1, 1, 0, st>>>(M.sc.p);
          APX_COUNT_LAUNCH(c);
@@ -284,11 +290,41 @@ void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out)
             apx_valence_enqueue(c, APX_GRAD, st, false);                    // energy(grad, RESPA_FAST)
             md_kick(c, true, false, dta, 0.0, dta);                         // velR0(dta) + pos(dta)
          }
+         // the neighbour-list test of the new positions on the second stream, BESIDE the last valence evaluation: its answer
+         // is in host memory before that kernel ends, so the host round trip that decides "refresh or rebuild" costs the GPU
+         // nothing (it used to idle ~15 us per step waiting for it)
+         check_async = c->list_valid != 0;
+         if (check_async) {
+            CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+            apx_list_check_enqueue(c, c->stream2, M.sc.p + 7);
+            CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
+         }
          if (val)
             apx_valence_enqueue(c, APX_ENERGY | APX_GRAD, st, false);       // fast force at the new positions
+         if (check_async)
+            CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));
          apx_graph_end(c, 0x3000 + nr);
+         M.graph_has_check = check_async ? 1 : 0;
+      } else
+         check_async = M.graph_has_check != 0;
+      int moved = -1;
+      if (check_async) {
+         // spin on the sequence number the side branch publishes into pinned memory (k_list_publish)
+         const int want = ++M.seq_host;
+         volatile int* fh = c->flags_h;
+         const auto t_begin = std::chrono::steady_clock::now();
+         long spins = 0;
+         while (fh[7] != want) {
+            if ((++spins & 0xfff) == 0 && std::chrono::steady_clock::now() - t_begin > std::chrono::seconds(20)) {
+               CUDA_CHECK(cudaStreamSynchronize(st));
+               if (fh[7] != want)
+                  APX_THROW("apx_md_steps: the neighbour-list test never reported back");
+            }
+         }
+         moved = fh[6] != 0 ? 1 : 0;
       }
-      md_positions_changed(c);                                              // copyPosToXyz(true): list check / rebuild
+      md_positions_changed(c, moved);                                       // copyPosToXyz(true): list check / rebuild
       if (val)
          apx_valence_fetch(c, st);
       apx_energy_impl_md(c, APX_V4, &r);                                    // slow force: induce + emplar + ehal

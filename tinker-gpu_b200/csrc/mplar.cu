@@ -729,7 +729,22 @@ void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p);
 
+static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer);
+
+// energy(vers) of the electrostatic terms (+ vdW / valence when attached).  The first attempt never waits for the GPU between
+// the solver and the energy epilogue (the solver's first batch of iterations is sized from recent solves); should that batch
+// not have converged -- the iteration count grew -- the evaluation is simply repeated with a solver that waits for its batches.
+// Every accumulator is zeroed at the top of an attempt, so the repetition is exact.
 void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val)
+{
+   if (!energy_once(c, vers, do_m, do_p, out, do_vdw, do_val, true)) {
+      c->stats.energy_retries++;
+      if (!energy_once(c, vers, do_m, do_p, out, do_vdw, do_val, false))
+         APX_THROW("energy: the induced-dipole solver did not finish");
+   }
+}
+
+static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer)
 {
    const int n = c->n;
    const int a0 = c->a0, no = c->a1 - c->a0, n3 = 3 * no;      // per-atom passes run on the owned range
@@ -760,9 +775,12 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    if (do_val)
       apx_valence_launch(c, vers);
    // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
+   // (with the device-side loop the solve is only enqueued here: nothing waits for the convergence flag, the epilogue below is
+   //  enqueued behind it, and the solver's host-side bookkeeping runs after the one synchronisation of this function)
    int iters = 0;
+   bool induce_deferred = false;
    if (do_p) {
-      apx_induce_impl(c);
+      induce_deferred = apx_induce_impl(c, defer);
       iters = c->stats.pcg_iterations;
    } else if (ewald) {
       apx_pme_mpole(c, true);
@@ -898,6 +916,11 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    CUDA_CHECK(cudaMemcpyAsync(c->red_h, c->ebuf.p, tail, cudaMemcpyDeviceToHost, st));
    cudaEventRecord(c->ev3, st);
    CUDA_CHECK(cudaStreamSynchronize(st));
+   if (induce_deferred) {
+      if (!apx_induce_finish(c))      // iteration count, timings, predictor history, the not-converged error
+         return false;
+      iters = c->stats.pcg_iterations;
+   }
    const fixed_t* eb = reinterpret_cast<const fixed_t*>(c->red_h);
    const double* db = reinterpret_cast<const double*>(c->red_h + ((char*)c->dbuf.p - (char*)c->ebuf.p));
    const int* cn = reinterpret_cast<const int*>(c->red_h + ((char*)c->cnt.p - (char*)c->ebuf.p));
@@ -958,6 +981,7 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    apx_valence_set_in_total(c, do_val && do_g ? 1 : 0);
    if (out)
       *out = r;
+   return true;
 }
 
 void apx_energy_impl_md(apx_ctx* c, int vers, apx_energy_result* out)

@@ -215,12 +215,44 @@ void apx_update_sorted_positions(apx_ctx* c)
    apx_pme_fill_theta(c);
 }
 
-void apx_list_refresh(apx_ctx* c, bool force)
+// one thread: the answer of k_check_moved and a sequence number into host-mapped pinned memory (host[6] = moved, host[7] = seq).
+// The host of an MD step spins on the sequence number instead of synchronising a stream: the kernel sits in a side branch of
+// the step graph, beside the last valence evaluation (md.cu)
+__global__ void k_list_publish(const int* __restrict__ flag, double* __restrict__ seq, volatile int* host)
+{
+   const double s = *seq + 1.0;
+   *seq = s;
+   host[6] = *flag;
+   __threadfence_system();
+   host[7] = (int)s;
+}
+
+// the moved-more-than-buffer/2 test on stream `st`.  seq == nullptr: its answer is copied to flags_h[0] (valid once `st` has
+// got there); otherwise it is published with a sequence number (k_list_publish)
+void apx_list_check_enqueue(apx_ctx* c, cudaStream_t st, double* seq)
+{
+   const int n = c->n;
+   const double lim = 0.5 * c->opt.list_buffer;
+   CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), st));
+   k_check_moved<<<(n + 255) / 256, 256, 0, st>>>(n, c->xyz_d, c->xyz_ref, lim * lim, c->flags);
+   APX_COUNT_LAUNCH(c);
+   if (seq) {
+      k_list_publish<<<1, 1, 0, st>>>(c->flags, seq, c->flags_h);
+      APX_COUNT_LAUNCH(c);
+   } else
+      CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+}
+
+// known_moved: -1 = run the test here; 0 / 1 = the caller already has its answer (md.cu runs it beside the last valence
+// evaluation of the inner RESPA level)
+void apx_list_refresh(apx_ctx* c, bool force, int known_moved)
 {
    int n = c->n;
    bool rebuild = force || !c->list_valid;
    c->tl_valid = 0;      // positions changed: the stored pair tensors (tlist.cu) are rebuilt by the next operator application
-   if (!rebuild) {
+   if (!rebuild && known_moved >= 0)
+      rebuild = known_moved != 0;
+   else if (!rebuild) {
       // moved more than buffer/2 since the last build?  (src/nblist.cpp:521-531)
       double lim = 0.5 * c->opt.list_buffer;
       CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream));
@@ -290,6 +322,8 @@ void apx_list_refresh(apx_ctx* c, bool force)
       c->grp.vslot.p, c->grp.nbr16.p, c->grp.vjb.p, c->grp.ajb.p, c->grp.ok ? (const void*)c : nullptr, c->tl_T.p, c->tl_P.p};
    for (int q = 0; q < 13; ++q)
       if (before[q] != after[q]) {
+         if (getenv("APX_TRACE_GRAPHS"))
+            fprintf(stderr, "[apx] list rebuild moved buffer %d (%p -> %p)\n", q, before[q], after[q]);
          apx_pcg_graphs_invalidate(c);
          break;
       }

@@ -25,11 +25,12 @@
 #include "dp.cuh"
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace {
 // udir = alpha E_d ; udirp = alpha (E_d + delta_p) ; fieldp = E_d + delta ; initial guess u = udir.
 // P receives the packed guess (or the packed field when there is no guess: r0 = E).
-__global__ void k_udir(int n, const real4* __restrict__ tpj, const real* __restrict__ fd, real* __restrict__ fpd,
+__global__ void k_udir(int n, const real4* __restrict__ tpj, real* __restrict__ fd, const real* __restrict__ fr, real* __restrict__ fpd,
    real* __restrict__ udir, real* __restrict__ udirp, real* __restrict__ uind, real* __restrict__ uinp, real4* __restrict__ P,
    int guess)
 {
@@ -38,6 +39,11 @@ __global__ void k_udir(int n, const real4* __restrict__ tpj, const real* __restr
       return;
    real pol = tpj[s].y;
    V3 ed = v3(fd[3 * s], fd[3 * s + 1], fd[3 * s + 2]);
+   if (fr) {
+      // the real-space part was computed beside the reciprocal part (apx_dfield_full): the sum is the field
+      ed += v3(fr[3 * s], fr[3 * s + 1], fr[3 * s + 2]);
+      fd[3 * s] = ed.x, fd[3 * s + 1] = ed.y, fd[3 * s + 2] = ed.z;
+   }
    V3 ep = ed + v3(fpd[3 * s], fpd[3 * s + 1], fpd[3 * s + 2]);
    fpd[3 * s] = ep.x, fpd[3 * s + 1] = ep.y, fpd[3 * s + 2] = ep.z;
    V3 a = pol * ed, b = pol * ep;
@@ -60,11 +66,20 @@ __global__ void k_udir(int n, const real4* __restrict__ tpj, const real* __restr
 
 // K1: direction update p = z + b p (pcgP3, src/cu/induce.cu:172-190); b = r.z(new) / r.z(old) from the
 // sub-slotted sums, b = 0 with p = 0 on the first iteration
-__global__ void __launch_bounds__(256) k_pcg_dir(int n, const int* __restrict__ flags, real4* __restrict__ P,
-   const real4* __restrict__ Z, const double* __restrict__ slot_prev, const double* __restrict__ slot_cur)
+__global__ void __launch_bounds__(256) k_pcg_dir(int n, int* __restrict__ flags, real4* __restrict__ P,
+   const real4* __restrict__ Z, const double* __restrict__ slot_prev, const double* __restrict__ slot_cur, int device_loop)
 {
    if (flags[1])
       return;
+   int it = 0;
+   if (device_loop) {
+      // device-side loop: the iteration number lives in flags[4]; this kernel opens iteration flags[4] + 1 (slot_cur = slot of
+      // iteration 1) and its last CTA publishes the new number for the other kernels of the iteration -- every CTA has read
+      // the old one before it takes its ticket
+      it = flags[4] + 1;
+      slot_cur += (size_t)PCG_SLOT * (it - 1);
+      slot_prev = it >= 2 ? slot_cur - PCG_SLOT : nullptr;
+   }
    real b = 0, bp = 0;
    if (slot_prev) {
       double o[2], c2[2];
@@ -75,25 +90,36 @@ __global__ void __launch_bounds__(256) k_pcg_dir(int n, const int* __restrict__ 
       bp = o[1] != 0.0 ? (real)(c2[1] / o[1]) : (real)0;
    }
    int s = blockIdx.x * blockDim.x + threadIdx.x;
-   if (s >= n)
-      return;
-   V3 zd, zp, pd, pp;
-   load_dp(Z, s, zd, zp);
-   if (slot_prev) {
-      load_dp(P, s, pd, pp);
-      zd += b * pd;
-      zp += bp * pp;
+   if (s < n) {
+      V3 zd, zp, pd, pp;
+      load_dp(Z, s, zd, zp);
+      if (slot_prev) {
+         load_dp(P, s, pd, pp);
+         zd += b * pd;
+         zp += bp * pp;
+      }
+      store_dp(P, s, zd, zp);
    }
-   store_dp(P, s, zd, zp);
+   if (device_loop) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         const unsigned t = atomicAdd((unsigned*)&flags[5], 1u);
+         if (t == gridDim.x - 1) {
+            flags[5] = 0;
+            flags[4] = it;
+         }
+      }
+   }
 }
 
 // K4: u += a p ; r -= a Ap (zero where alpha == 0) ; partial r.r ; zero the PME grid
 __global__ void __launch_bounds__(256) k_pcg_update(int n, const int* __restrict__ flags, const real4* __restrict__ tpj,
    const real4* __restrict__ P, const real4* __restrict__ V, real4* __restrict__ R, real* __restrict__ ud, real* __restrict__ up,
-   double* __restrict__ slot, real4* __restrict__ grid4, size_t ngrid4)
+   double* __restrict__ slot, real4* __restrict__ grid4, size_t ngrid4, const int* __restrict__ itp)
 {
    if (flags[1])
       return;
+   slot = pcg_slot_of(slot, itp);
    int s = blockIdx.x * blockDim.x + threadIdx.x;
    double e1 = 0, e2 = 0;
    double q4[4];
@@ -249,11 +275,25 @@ void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p)
 void apx_dfield_full(apx_ctx* c, bool want_ev)
 {
    const int a0 = c->a0, no = c->a1 - c->a0;
-   if (c->opt.use_ewald)
+   const real* fr = nullptr;
+   if (c->opt.use_ewald && !c->dist.on) {
+      // the real-space rows (second stream) beside the PME round trip of the multipoles (main stream): 60 us and 130 us at
+      // dhfr2 that used to run one after the other; the rows ASSIGN their own buffer, k_udir adds the two parts
+      c->field_rs.ensure(3 * (size_t)c->npad);
+      fr = c->field_rs.p;
+      CUDA_CHECK(cudaEventRecord(c->ev_fork, c->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+      apx_dfield_real(c, c->stream2, c->field_rs, c->fieldp, true);
+      CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
       apx_pme_mpole(c, want_ev);                 // ASSIGNS c->field = recip + self
-   apx_dfield_real(c, c->field, c->fieldp);      // adds to (Ewald) or assigns (no Ewald) field; zeroes fieldp first
-   k_udir<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->tpj + a0, c->field + 3 * a0, c->fieldp + 3 * a0, c->udir + 3 * a0,
-      c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0, c->opt.pcgguess ? 1 : 0);
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+   } else {
+      if (c->opt.use_ewald)
+         apx_pme_mpole(c, want_ev);              // ASSIGNS c->field = recip + self
+      apx_dfield_real(c, c->stream, c->field, c->fieldp, !c->opt.use_ewald);      // adds to (Ewald) or assigns (no Ewald) field
+   }
+   k_udir<<<(no + 255) / 256, 256, 0, c->stream>>>(no, c->tpj + a0, c->field + 3 * a0, fr ? fr + 3 * a0 : nullptr, c->fieldp + 3 * a0,
+      c->udir + 3 * a0, c->udirp + 3 * a0, c->uind + 3 * a0, c->uinp + 3 * a0, c->pk_p + 2 * a0, c->opt.pcgguess ? 1 : 0);
    APX_COUNT_LAUNCH(c);
 }
 
@@ -265,14 +305,15 @@ static void field_of_dp(apx_ctx* c, const real4* U, bool spread)
    if (c->dist.on)
       apx_dist_halo(c, const_cast<real4*>(U), st);      // neighbours' dipoles from the GPUs that own them
    CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+   // the spread heads the critical path (spread -> FFTs -> gather) and goes in first: launched after the rows, its CTAs waited
+   // 13 us for the operator's grid to drain (profiles/r02f_trace_md.txt); the operator is only needed by the gather
+   if (c->opt.use_ewald && spread)
+      apx_pme_spread_dp(c, U);
    CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
    apx_ufield_real_dp(c, c->stream2, U, c->pk_f);
    CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
-   if (c->opt.use_ewald) {
-      if (spread)
-         apx_pme_spread_dp(c, U);
+   if (c->opt.use_ewald)
       apx_pme_convolve(c);
-   }
    CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));
 }
 
@@ -296,10 +337,11 @@ __global__ void k_mask_dp(int n, const real4* __restrict__ tpj, real4* __restric
       store_dp(V, s, v3(0, 0, 0), v3(0, 0, 0));
 }
 __global__ void k_nonewald_ap(int n, const int* __restrict__ flags, const real4* __restrict__ tpj, const real4* __restrict__ P,
-   const real4* __restrict__ F, real4* __restrict__ V, double* __restrict__ slot)
+   const real4* __restrict__ F, real4* __restrict__ V, double* __restrict__ slot, const int* __restrict__ itp)
 {
    if (flags[1])
       return;
+   slot = pcg_slot_of(slot, itp);
    int s = blockIdx.x * blockDim.x + threadIdx.x;
    double x = 0, y = 0;
    if (s < n) {
@@ -363,6 +405,9 @@ void apx_pcg_graphs_invalidate(apx_ctx* c)
    for (auto& g : c->graphs)
       cudaGraphExecDestroy(g.exec);
    c->graphs.clear();
+   if (c->loop_exec)
+      cudaGraphExecDestroy(c->loop_exec);
+   c->loop_exec = nullptr;
    for (auto& kv : c->step_graphs)
       if (kv.second.exec)
          cudaGraphExecDestroy(kv.second.exec);
@@ -410,7 +455,42 @@ void apx_graph_end(apx_ctx* c, int key)
    CUDA_CHECK(cudaGraphLaunch(G.exec, c->stream));      // the captured work has not run yet
 }
 
-void apx_induce_impl(apx_ctx* c)
+static void upred_save(apx_ctx* c);
+static void induce_epilogue(apx_ctx* c, int used, bool predict)
+{
+   {
+      // mean device time of the real-space ufield launches that did work (speculative launches after
+      // convergence return immediately and are excluded): 1 for r0 + one per iteration
+      int used_pairs = std::min(c->uf_used / 2, used + ((c->opt.pcgguess || predict) ? 1 : 0));
+      float tot = 0;
+      for (int k = 0; k < used_pairs; ++k) {
+         float ms = 0;
+         cudaEventElapsedTime(&ms, c->uf_ev[2 * k], c->uf_ev[2 * k + 1]);
+         tot += ms;
+      }
+      c->stats.ms_ufield_real = used_pairs ? tot / used_pairs : 0;
+   }
+   c->stats.pcg_iterations = used;
+   c->last_iters = used;
+   // length of the first batch of the next solves: the largest count seen, lowered by one after 50 solves that needed less
+   if (used >= c->pcg_n) {
+      c->pcg_n = used;
+      c->pcg_n_slack = 0;
+   } else if (++c->pcg_n_slack >= 50) {
+      c->pcg_n -= 1;
+      c->pcg_n_slack = 0;
+   }
+   c->stats.ms_induce = 0;
+   cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
+   c->scal_h[2] = c->scal_h[0];
+   upred_save(c);
+   if (used >= c->opt.politer && !(c->scal_h[0] < c->opt.poleps))
+      APX_THROW("INDUCE  --  Warning, Induced Dipoles are not Converged");   // pcg.cu:180-184
+}
+
+// defer = true (energy(), mplar.cu): when the iterations run as the device-side loop nothing here waits for the GPU -- the caller
+// enqueues what follows the solve, synchronises once, and then calls apx_induce_finish.  Returns true when a finish is pending.
+bool apx_induce_impl(apx_ctx* c, bool defer)
 {
    const int n = c->n, n3 = 3 * n;
    const int a0 = c->a0, no = c->a1 - c->a0;      // owned range: every per-atom pass below runs on it
@@ -441,7 +521,7 @@ void apx_induce_impl(apx_ctx* c)
       cudaEventRecord(c->ev1, st);
       CUDA_CHECK(cudaStreamSynchronize(st));
       cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
-      return;
+      return false;
    }
    const int politer = c->opt.politer;
    const int miniter = std::min(3, n);
@@ -503,6 +583,10 @@ void apx_induce_impl(apx_ctx* c)
    }
    if (ewald)
       c->mpole_pme_valid = 1;
+   // the prologue applied the operator (and with it built the pair tensors) whether it ran eagerly or as a replayed graph:
+   // the host flag must say so, or the capture of the first iteration would bake a second build into its graph
+   if (apx_tlist_usable(c))
+      c->tl_valid = 1;      // (written by the permanent-field rows of the prologue, field.cu)
    if (graphable && c->use_graph && !dist && (c->opt.pcgguess) && c->uf_used == 0)
       c->uf_used = 2;      // the r0 operator launch inside the graph was timed through external event nodes
    int iter = 0;
@@ -513,56 +597,123 @@ void apx_induce_impl(apx_ctx* c)
    T.miniter = miniter, T.politer = politer;
    T.poleps = (real)c->opt.poleps, T.debye = (real)4.803206802, T.pcgpeek = (real)c->opt.pcgpeek;
    T.result = result, T.flags = c->flags, T.ud = c->uind, T.up = c->uinp;
-   auto enqueue_iteration = [&](int it) {
-      double* slot = c->scal.p + (size_t)PCG_SLOT * (it - 1);
-      k_pcg_dir<<<g1, 256, 0, st>>>(no, c->flags, c->pk_p + 2 * a0, c->pk_z + 2 * a0, it >= 2 ? slot - PCG_SLOT : nullptr, slot);
+   // one iteration.  loop = false: iteration `it`, slots addressed by the host.  loop = true: the body of the device-side loop --
+   // the iteration number lives in flags[4] (k_pcg_dir advances it), every kernel finds its slots from it
+   auto enqueue_iteration = [&](int it, bool loop, unsigned long long cond) {
+      const int* itp = loop ? c->flags.p + 4 : nullptr;
+      double* slot = loop ? c->scal.p : c->scal.p + (size_t)PCG_SLOT * (it - 1);
+      k_pcg_dir<<<g1, 256, 0, st>>>(no, c->flags, c->pk_p + 2 * a0, c->pk_z + 2 * a0, (!loop && it >= 2) ? slot - PCG_SLOT : nullptr, slot,
+         loop ? 1 : 0);
       APX_COUNT_LAUNCH(c);
       field_of_dp(c, c->pk_p, true);
       if (ewald)
-         apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot);
+         apx_pme_gather_dp(c, 2, c->pk_p, c->pk_f, nullptr, nullptr, c->pk_v, slot, itp);
       else {
-         k_nonewald_ap<<<g1, 256, 0, st>>>(no, c->flags, c->tpj + a0, c->pk_p + 2 * a0, c->pk_f + 2 * a0, c->pk_v + 2 * a0, slot);
+         k_nonewald_ap<<<g1, 256, 0, st>>>(no, c->flags, c->tpj + a0, c->pk_p + 2 * a0, c->pk_f + 2 * a0, c->pk_v + 2 * a0, slot, itp);
          APX_COUNT_LAUNCH(c);
       }
       if (dist)
          apx_dist_allreduce_f64(c, slot + 2 * PCG_NSUB, 2 * PCG_NSUB);        // p.Ap over all GPUs
       k_pcg_update<<<g1, 256, 0, st>>>(no, c->flags, c->tpj + a0, c->pk_p + 2 * a0, c->pk_v + 2 * a0, c->pk_r + 2 * a0,
-         c->uind + 3 * a0, c->uinp + 3 * a0, slot, (real4*)c->qgrid.p, ngrid4);
+         c->uind + 3 * a0, c->uinp + 3 * a0, slot, (real4*)c->qgrid.p, ngrid4, itp);
       APX_COUNT_LAUNCH(c);
       if (dist) {
          apx_dist_allreduce_f64(c, slot + 4 * PCG_NSUB, 2 * PCG_NSUB);        // r.r
          apx_dist_halo(c, c->pk_r, st);                                       // residuals of the preconditioner's neighbours
       }
-      T.it = it;
+      T.it = loop ? 0 : it;
       T.slot = slot;
+      T.itp = itp;
+      T.cond = cond;
       apx_precond_dp(c, c->pk_r, c->pk_z, slot + PCG_SLOT, &T);
       if (dist)
          apx_dist_allreduce_f64(c, slot + PCG_SLOT, 2 * PCG_NSUB);            // r.z entering the next iteration
    };
+   // ---- the loop on the device: ONE graph whose only node is a conditional WHILE node with one iteration as its body.  The
+   // preconditioner kernel of the iteration that meets the stopping rule sets the condition to 0 (field.cu: k_precond_rows);
+   // no batch sizes to guess, no launches after convergence, no graph per (first iteration, batch length), and the host does
+   // not have to look at the convergence flag before it enqueues what follows.  First solve of a context: host-driven and
+   // eager (plans, scratch buffers), like every other graph region.
+   const bool use_loop = c->use_graph && c->use_loop && !dist;
+   if (use_loop && !c->loop_exec && c->loop_warm) {
+      if (trace_graphs())
+         fprintf(stderr, "[apx] capturing the pcg loop body\n");
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaGraphCreate(&g, 0));
+      cudaGraphConditionalHandle h;
+      CUDA_CHECK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      np.conditional.handle = h;
+      np.conditional.type = cudaGraphCondTypeWhile;
+      np.conditional.size = 1;
+      cudaGraphNode_t node;
+      CUDA_CHECK(cudaGraphAddNode(&node, g, nullptr, 0, &np));
+      cudaGraph_t body = np.conditional.phGraph_out[0];
+      const int before = c->stats.kernel_launches;
+      c->capturing = 1;
+      CUDA_CHECK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+      enqueue_iteration(0, true, (unsigned long long)h);
+      cudaGraph_t out = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &out);
+      c->capturing = 0;
+      if (e != cudaSuccess)
+         APX_THROW(std::string("PCG loop capture failed: ") + cudaGetErrorString(e));
+      c->loop_launches = c->stats.kernel_launches - before;
+      c->stats.kernel_launches = before;
+      CUDA_CHECK(cudaGraphInstantiate(&c->loop_exec, g, 0));
+      cudaGraphDestroy(g);
+   }
+   if (use_loop && c->loop_exec) {
+      CUDA_CHECK(cudaGraphLaunch(c->loop_exec, st));
+      CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      cudaEventRecord(c->ev1, st);
+      c->skip = nullptr;
+      c->induce_pending = 1;
+      c->induce_pending_predict = predict ? 1 : 0;
+      if (defer)
+         return true;
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      (void)apx_induce_finish(c);
+      return false;
+   }
+   // ---- default: iterations in batches, every batch ONE graph.  After the first (eager) solve of a context the iterations are
+   // "generic" -- the iteration number lives on the device, so the graph of an N-iteration batch serves any first iteration:
+   // one capture per batch length instead of one per (first iteration, length), which used to put a 1-8 ms capture into MD
+   // steps whenever the iteration count moved (profiles/r02g: steps 5-6 of the timed window).  The first batch has the
+   // largest iteration count seen recently (c->pcg_n); kernels of iterations past convergence return at once.  With defer
+   // the host does not wait for that batch: the caller enqueues the energy epilogue behind it and synchronises once.
+   const bool generic = c->use_graph && !dist && !use_loop && c->loop_warm;
+   c->loop_warm = 1;
+   if (generic) {
+      batch = std::max(1, std::min(c->pcg_n > 0 ? c->pcg_n : c->last_iters, politer));
+      static const int forced = getenv("APX_PCG_FIRST_BATCH") ? atoi(getenv("APX_PCG_FIRST_BATCH")) : 0;      // tests: force the retry path
+      if (forced > 0)
+         batch = std::min(forced, politer);
+   }
+   bool first_batch = true;
    while (!done) {
       int nit = std::min(batch, politer - iter);
-      if (c->use_graph && !dist) {
-         // one CUDA graph per (first iteration, batch length): the fork/join with the second stream and
-         // every launch of the batch replay as a single submission
+      if (generic) {
          apx_ctx::PcgGraph* G = nullptr;
          for (auto& g : c->graphs)
-            if (g.it0 == iter + 1 && g.nit == nit)
+            if (g.it0 == 0 && g.nit == nit)
                G = &g;
          if (!G) {
             if (trace_graphs())
-               fprintf(stderr, "[apx] capturing pcg graph (first iteration %d, %d iterations)\n", iter + 1, nit);
+               fprintf(stderr, "[apx] capturing generic pcg graph (%d iterations)\n", nit);
             int before = c->stats.kernel_launches;
             c->capturing = 1;
             CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             for (int b = 0; b < nit; ++b)
-               enqueue_iteration(iter + 1 + b);
+               enqueue_iteration(0, true, 0);
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             c->capturing = 0;
             if (e != cudaSuccess)
                APX_THROW(std::string("PCG graph capture failed: ") + cudaGetErrorString(e));
             apx_ctx::PcgGraph ng;
-            ng.it0 = iter + 1, ng.nit = nit;
+            ng.it0 = 0, ng.nit = nit;
             ng.launches = c->stats.kernel_launches - before;
             c->stats.kernel_launches = before;
             CUDA_CHECK(cudaGraphInstantiate(&ng.exec, graph, 0));
@@ -575,35 +726,42 @@ void apx_induce_impl(apx_ctx* c)
          iter += nit;
       } else {
          for (int b = 0; b < nit; ++b)
-            enqueue_iteration(++iter);
+            enqueue_iteration(++iter, false, 0);
       }
       CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
       CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
       cudaEventRecord(c->ev1, st);
+      if (generic && defer && first_batch && iter < politer) {
+         c->skip = nullptr;
+         c->induce_pending = 2;
+         c->induce_pending_predict = predict ? 1 : 0;
+         return true;
+      }
+      first_batch = false;
       CUDA_CHECK(cudaStreamSynchronize(st));
       done = c->flags_h[1] != 0 || iter >= politer;
       batch = 2;
    }
    c->skip = nullptr;
-   int used = c->flags_h[2] > 0 ? c->flags_h[2] : iter;
-   {
-      // mean device time of the real-space ufield launches that did work (speculative launches after
-      // convergence return immediately and are excluded): 1 for r0 + one per iteration
-      int used_pairs = std::min(c->uf_used / 2, used + ((c->opt.pcgguess || predict) ? 1 : 0));
-      float tot = 0;
-      for (int k = 0; k < used_pairs; ++k) {
-         float ms = 0;
-         cudaEventElapsedTime(&ms, c->uf_ev[2 * k], c->uf_ev[2 * k + 1]);
-         tot += ms;
-      }
-      c->stats.ms_ufield_real = used_pairs ? tot / used_pairs : 0;
+   induce_epilogue(c, c->flags_h[2] > 0 ? c->flags_h[2] : iter, predict);
+   return false;
+}
+
+// what follows the solve on the host once its results are visible (after a stream synchronisation).  false: the deferred first
+// batch did not converge -- the caller redoes the evaluation with a solve that waits for its batches
+bool apx_induce_finish(apx_ctx* c)
+{
+   if (!c->induce_pending)
+      return true;
+   const int kind = c->induce_pending;
+   c->induce_pending = 0;
+   if (kind == 2 && c->flags_h[1] == 0) {
+      c->pcg_n += 1;
+      return false;
    }
-   c->stats.pcg_iterations = used;
-   c->last_iters = used;
-   c->stats.ms_induce = 0;
-   cudaEventElapsedTime(&c->stats.ms_induce, c->ev0, c->ev1);
-   c->scal_h[2] = c->scal_h[0];
-   upred_save(c);
-   if (used >= politer && !(c->scal_h[0] < c->opt.poleps))
-      APX_THROW("INDUCE  --  Warning, Induced Dipoles are not Converged");   // pcg.cu:180-184
+   const int used = c->flags_h[2] > 0 ? c->flags_h[2] : c->opt.politer;
+   if (kind == 1)
+      c->stats.kernel_launches += c->loop_launches * used;
+   induce_epilogue(c, used, c->induce_pending_predict != 0);
+   return true;
 }

@@ -588,7 +588,7 @@ template <int EPI, int LG>
 __global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl, real selfterm,
    const real4* __restrict__ theta, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
    const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
-   double* __restrict__ slot, const int* __restrict__ skip)
+   double* __restrict__ slot, const int* __restrict__ skip, const int* __restrict__ itp)
 {
    if (skip && skip[1])
       return;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(128) k_gather_dp(int n, Xform X, int n1, int n
       }
    }
    if (EPI == 2)
-      pcg_block_add2(dot_d, dot_p, slot, 2, 3);
+      pcg_block_add2(dot_d, dot_p, pcg_slot_of(slot, itp), 2, 3);
 }
 
 // --- host side ---------------------------------------------------------------------------------
@@ -931,7 +931,7 @@ void apx_pme_convolve(apx_ctx* c)
 }
 
 // epi 0: fd/fp plain out ; 1: OUT = residual ; 2: OUT = Ap with partial dots into slot
-void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot)
+void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real* fd, real* fp, real4* OUT, double* slot, const int* itp)
 {
    const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
@@ -941,7 +941,7 @@ void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real
 #define GATHER_DP(E)                                                                                                       \
    k_gather_dp<E, PME_LG><<<g, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),           \
       c->theta + 16 * (size_t)a0, c->tpj + a0, c->qgrid, U + 2 * (size_t)a0, F ? F + 2 * (size_t)a0 : nullptr,                 \
-      fd ? fd + 3 * (size_t)a0 : nullptr, fp ? fp + 3 * (size_t)a0 : nullptr, OUT ? OUT + 2 * (size_t)a0 : nullptr, slot, c->skip)
+      fd ? fd + 3 * (size_t)a0 : nullptr, fp ? fp + 3 * (size_t)a0 : nullptr, OUT ? OUT + 2 * (size_t)a0 : nullptr, slot, c->skip, itp)
    if (no > 0) {
       if (epi == 0) GATHER_DP(0);
       else if (epi == 1) GATHER_DP(1);

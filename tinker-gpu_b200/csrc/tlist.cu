@@ -20,6 +20,8 @@
 #include "pairmath.cuh"
 #include "rows.cuh"
 #include "dp.cuh"
+#include "tlist.cuh"
+#include <algorithm>
 
 namespace {
 __device__ __forceinline__ int tl_as_int(real w)
@@ -30,46 +32,16 @@ __device__ __forceinline__ int tl_as_int(real w)
    return __float_as_int(w);
 #endif
 }
-// B1 with the sign of B2 in its lowest mantissa bit
-__device__ __forceinline__ real tl_tag(real b1, bool neg)
-{
-#ifdef APX_DOUBLE
-   long long u = __double_as_longlong(b1);
-   u = (u & ~1ll) | (neg ? 1ll : 0ll);
-   return __longlong_as_double(u);
-#else
-   unsigned u = __float_as_uint(b1);
-   u = (u & ~1u) | (neg ? 1u : 0u);
-   return __uint_as_float(u);
-#endif
-}
-// v with its sign flipped when the tag bit of b1 is set
-__device__ __forceinline__ real tl_signed(real v, real b1)
-{
-#ifdef APX_DOUBLE
-   return __longlong_as_double(__double_as_longlong(v) ^ (__double_as_longlong(b1) << 63));
-#else
-   return __uint_as_float(__float_as_uint(v) ^ (__float_as_uint(b1) << 31));
-#endif
-}
-// streaming load of a tensor entry (read once per application, never reused: keep it out of L1)
+// load of a tensor entry: read once per application, but read again by the NEXT application -- at dhfr2 size the whole
+// tensor list (53 MB) stays in L2 between the 8 applications of an induce(), so no evict-first hint (ld.global.cs)
 __device__ __forceinline__ real4 tl_ld(const real4* p)
 {
 #ifdef APX_DOUBLE
    return *p;
 #else
-   return __ldcs(p);
+   return __ldg(p);
 #endif
 }
-__device__ __forceinline__ real4 tl_pack(real B1, real B2, real dx, real dy, real dz)
-{
-   const real s = sqrt(fabs(B2));
-   real4 t;
-   t.x = tl_tag(B1, B2 < 0);
-   t.y = s * dx, t.z = s * dy, t.w = s * dz;
-   return t;
-}
-
 // ---- build: one pass over the compacted rows, same lane groups as the operator -----------------------------------------------
 template <bool EWALD, bool TABLE, bool PRECOND, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_tlist_build(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
@@ -127,6 +99,21 @@ __device__ __forceinline__ void tl_apply(const real4 t, const real4 ua, const re
 // lane.  MLP = true makes every FMA of the body depend on ALL its loads through real data flow: the loaded words are OR-ed
 // together, AND-ed with a kernel argument that is zero at run time, and the (zero) result is XOR-ed into the first factor of
 // each entry -- 9 logic instructions per 4 entries, and all 16 loads are in flight before the first FMA can issue.
+// the neighbour's packed dipole pair (32 bytes, 32-byte aligned) in ONE 256-bit load (LDG.E.256, new with sm_100): the gathers
+// are what bounds this kernel at dhfr2 size -- every lane of a gather touches another cache line and L1 looks up one line per
+// cycle, so two 128-bit gathers per entry cost 64 cycles per warp row (22 us per launch at 160 atoms per SM), one costs 32
+__device__ __forceinline__ void tl_gather(const real4* __restrict__ U, int k, real4& ua, real4& ub)
+{
+#ifdef APX_DOUBLE
+   ua = U[2 * k];
+   ub = U[2 * k + 1];
+#else
+   asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+       : "=f"(ua.x), "=f"(ua.y), "=f"(ua.z), "=f"(ua.w), "=f"(ub.x), "=f"(ub.y), "=f"(ub.z), "=f"(ub.w)
+       : "l"(U + 2 * (size_t)k));
+#endif
+}
+
 template <int G, int UNROLL, bool MLP>
 __device__ __forceinline__ void tl_row(const int* __restrict__ nbr, const real4* __restrict__ T, const real4* __restrict__ U, int beg,
    int len, int l, unsigned zero, V3& fd, V3& fp)
@@ -142,16 +129,14 @@ __device__ __forceinline__ void tl_row(const int* __restrict__ nbr, const real4*
       for (int j = 0; j < UNROLL; ++j)
          t[j] = tl_ld(T + beg + q + j * G);
       #pragma unroll
-      for (int j = 0; j < UNROLL; ++j) {
-         ua[j] = U[2 * k[j]];
-         ub[j] = U[2 * k[j] + 1];
-      }
+      for (int j = 0; j < UNROLL; ++j)
+         tl_gather(U, k[j], ua[j], ub[j]);
 #ifndef APX_DOUBLE
       if (MLP) {
          unsigned x = 0;
          #pragma unroll
          for (int j = 0; j < UNROLL; ++j)
-            x |= __float_as_uint(t[j].y) | __float_as_uint(ua[j].x) | __float_as_uint(ub[j].x);
+            x |= __float_as_uint(t[j].y) | __float_as_uint(ua[j].x);
          x &= zero;
          #pragma unroll
          for (int j = 0; j < UNROLL; ++j)
@@ -165,7 +150,9 @@ __device__ __forceinline__ void tl_row(const int* __restrict__ nbr, const real4*
    for (; q < len; q += G) {
       const int k = nbr[beg + q] & ROW_INDEX_MASK;
       const real4 t = tl_ld(T + beg + q);
-      tl_apply(t, U[2 * k], U[2 * k + 1], fd, fp);
+      real4 ua, ub;
+      tl_gather(U, k, ua, ub);
+      tl_apply(t, ua, ub, fd, fp);
    }
 }
 
@@ -226,8 +213,14 @@ void apx_ufield_tlist(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    RowList& L = c->rows;
    // APX_TL_MODE (A/B on hardware): bit 0 = forced memory-level parallelism, bit 1 = 16 lanes per atom instead of 8
    static const int mode = getenv("APX_TL_MODE") ? atoi(getenv("APX_TL_MODE")) : 1;
+   // CTAs per SM (APX_TL_CTAS): the operator runs beside the spread -> FFT chain of the main stream, which is the critical
+   // path and whose 512-thread FFT CTAs need a quarter of an SM's registers at once; a grid that fills every SM makes them
+   // wait for it to drain (profiles/r02g_trace_md.txt: the forward FFT started 8 us late and ran at a third of its speed)
+   // (large systems are bandwidth bound in every kernel: there the operator wants all the bytes in flight it can get)
+   static const int ctas_env = getenv("APX_TL_CTAS") ? std::max(1, atoi(getenv("APX_TL_CTAS"))) : 0;
+   const int ctas = ctas_env ? ctas_env : (c->n >= 200000 ? 16 : 6);
 #define LAUNCH_TL(G_, M_)                                                                                                 \
-   k_ufield_tl<G_, 4, M_><<<rows_grid<G_>(c, 16), ROWS_BLOCK, 0, st>>>(c->a0, c->a1, L.vstart, L.cnt, L.nbr, c->tl_T, U, F, c->skip, 0u)
+   k_ufield_tl<G_, 4, M_><<<rows_grid<G_>(c, ctas), ROWS_BLOCK, 0, st>>>(c->a0, c->a1, L.vstart, L.cnt, L.nbr, c->tl_T, U, F, c->skip, 0u)
    switch (mode & 3) {
    case 0: LAUNCH_TL(8, false); break;
    case 1: LAUNCH_TL(8, true); break;
