@@ -135,7 +135,7 @@ def test_deferred_solver_batch_and_retry():
             % (ROOT, os.path.join(GOLDEN, "water30.npz")))
     res = {}
     for forced in ("0", "3"):
-        env = dict(os.environ, APX_PCG_FIRST_BATCH=forced)
+        env = dict(os.environ, APX_PCG_FIRST_BATCH=forced, APX_LOOP="0")
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr[-800:]
         res[forced] = json.loads(r.stdout.strip().splitlines()[-1])
@@ -145,3 +145,27 @@ def test_deferred_solver_batch_and_retry():
         assert x["it"] == y["it"]
         assert abs(x["esum"] - y["esum"]) < 2e-8 * abs(x["esum"])
         assert abs(x["g"] - y["g"]) < 1e-6 * x["g"] and abs(x["v"] - y["v"]) < 1e-6 * x["v"]
+
+
+def test_while_node_loop_matches_batches():
+    """APX_LOOP=1: the PCG iterations as the body of a conditional WHILE graph node that the preconditioner kernel leaves from
+    the device -- same iteration counts and results as the default iteration batches."""
+    import subprocess
+    import sys
+    import json
+    code = ("import os,sys,json,numpy as np;sys.path.insert(0,%r);import tinker_gpu_b200 as tg;from tinker_gpu_b200.amoeba import Amoeba,calc;"
+            "s=tg.load_system(%r);a=Amoeba(s,'mixed',device=0,vdw=False);out=[];\n"
+            "for j in range(4):\n"
+            "    a.set_positions(np.array(s.xyz)+0.01*j)\n"
+            "    r=a.energy(calc.v1)\n"
+            "    out.append(dict(esum=r['esum'],it=r['pcg_iterations'],g=float(np.abs(r['grad']).sum())))\n"
+            "a.close();print(json.dumps(out))"
+            % (ROOT, os.path.join(GOLDEN, "water30.npz")))
+    res = {}
+    for loop in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, APX_LOOP=loop), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        res[loop] = json.loads(r.stdout.strip().splitlines()[-1])
+    for x, y in zip(res["0"], res["1"]):
+        assert x["it"] == y["it"]
+        assert abs(x["esum"] - y["esum"]) < 2e-8 * abs(x["esum"]) and abs(x["g"] - y["g"]) < 1e-6 * x["g"]

@@ -260,7 +260,8 @@ struct apx_ctx {
    DevBuf<real4> tl_T;                   // same offsets as rows.nbr: {B1 (LSB = sign of B2), sqrt|B2| R}
    DevBuf<real4> tl_P;                   // preconditioner tensors of the first cntu entries of every row
    int tlist_on = 1;                     // APX_TLIST=0: recompute the pair geometry in every operator application (field.cu)
-   int tl_valid = 0;                     // tl_T / tl_P belong to the current positions and rows
+   int tl_valid = 0;                     // tl_T belongs to the current positions and rows
+   int tl_p_valid = 0;                   // ... and so does tl_P (written by the permanent-field rows only)
    int staged_cap = 64;                  // APX_STAGED_CAP: j-blocks of a group staged in shared memory (1.5 KB each)
    int staged_min_atoms = 0;             // APX_STAGED_MIN: systems smaller than this keep the row operator
    int list_valid = 0;
@@ -336,8 +337,10 @@ struct apx_ctx {
    cudaGraphExec_t loop_exec = nullptr;
    int loop_launches = 0;          // kernels of ours per iteration of the body
    int loop_warm = 0;
-   int use_loop = 0;               // APX_LOOP=1: the WHILE-node loop (measured: +16 us per iteration on this driver, profiles/r02h)
+   int use_loop = 0;               // APX_LOOP=1: the WHILE-node loop instead of generic iteration batches (same median step,
+                                   // 3 % slower in batches of steps on this driver: profiles/r02j)
    int pcg_n = 0, pcg_n_slack = 0; // iterations in the first batch of a solve (largest count seen recently)
+   int vdw_fork_vers = -1;         // >= 0: energy() wants apx_induce_impl to fork the vdW stream after its prologue (mplar.cu)
    int induce_pending = 0, induce_pending_predict = 0;      // a deferred solve awaits apx_induce_finish
    int use_graph = 1;
    int capturing = 0;

@@ -203,7 +203,8 @@ template <bool EWALD, bool TABLE, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
    const int* __restrict__ cnt, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ mp0, const real4* __restrict__ mp1,
-   const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign, real4* __restrict__ T)
+   const real2* __restrict__ mp2, real* __restrict__ fd, real* __restrict__ fpd, int assign, real4* __restrict__ T,
+   real4* __restrict__ P, const int* __restrict__ cntu)
 {
    ROWS_FOREACH_ATOM(G, a0, a1, i, l, act)
    {
@@ -211,6 +212,7 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box 
       const real4 qi = tpj[i];
       const int beg = vstart[i];
       const int len = act ? cnt[i] : 0;
+      const int lenu = (P && act) ? cntu[i] : 0;
       V3 fi = v3(0, 0, 0);
       for (int q = l; q < len; q += G) {
          const int k = nbr[beg + q] & ROW_INDEX_MASK;
@@ -236,6 +238,10 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_dfield_rows(int a0, int a1, Box 
          // its applications: store them once (tlist.cu)
          if (T)
             T[beg + q] = tl_pack(B1, B2, dx, dy, dz);
+         if (q < lenu) {      // ... and the preconditioner's tensor of the pairs inside usolve-cutoff (the first cntu entries)
+            const real pp = qi.y * qk.y;
+            P[beg + q] = tl_pack(pp * (1 - om[1]) * rr[1], pp * (1 - om[2]) * rr[2], dx, dy, dz);
+         }
       }
       fi = group_sum3<G>(fi);
       if (l == 0 && act) {
@@ -297,11 +303,11 @@ __global__ void k_dfield_excl(int nx, int a0, int a1, Box box, real cut2, const 
 // sparse preconditioner: z += alpha_i alpha_k T_thole(r) r_k  over the pairs inside usolve-cutoff
 // (the first cntu entries of every row)
 // -------------------------------------------------------------------------------------------
-template <bool TABLE, int G>
+template <bool TABLE, int G, bool PLIST>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int ntot, Box box, real udiag, const int* __restrict__ vstart,
    const int* __restrict__ cntu, const int* __restrict__ nbr, const pos_t* __restrict__ posq, const real4* __restrict__ tpj,
    const real* __restrict__ thlval, int nj, const real4* __restrict__ Rv, real4* __restrict__ Z, double* __restrict__ slot,
-   const int* __restrict__ skip, PcgTest T)
+   const int* __restrict__ skip, PcgTest T, const real4* __restrict__ PL)
 {
    if (skip && skip[1])
       return;
@@ -360,6 +366,17 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_precond_rows(int a0, int a1, int
       const int beg = vstart[i];
       const int len = (act && cntu) ? cntu[i] : 0;
       V3 zdi = v3(0, 0, 0), zpi = v3(0, 0, 0);
+      if (PLIST) {
+         // stored tensors (written by the permanent-field rows of this induce(), tlist.cuh): 16 + 4 bytes streamed and one
+         // 32-byte gather per pair instead of recomputing the Thole-damped tensor
+         for (int q = l; q < len; q += G) {
+            const int k = nbr[beg + q] & ROW_INDEX_MASK;
+            const real4 t = tl_ld(PL + beg + q);
+            real4 ra, rb;
+            tl_gather(Rv, k, ra, rb);
+            tl_apply(t, ra, rb, zdi, zpi);
+         }
+      } else
       for (int q = l; q < len; q += G) {
          const int k = nbr[beg + q] & ROW_INDEX_MASK;
          const pos_t pk = posq[k];
@@ -537,9 +554,10 @@ void apx_dfield_real(apx_ctx* c, cudaStream_t st, real* fd, real* fpd, bool assi
    bool tb = c->thole_table != 0;
    int grid = rows_grid<DF_G>(c);
    real4* T = (apx_tlist_usable(c) && c->opt.use_polar && c->opt.poltyp_mutual) ? c->tl_T.p : nullptr;
+   real4* P = (T && c->opt.pcgprec && c->opt.usolve_cutoff > 0) ? c->tl_P.p : nullptr;
 #define LAUNCH_DF(E, T_)                                                                                                  \
    k_dfield_rows<E, T_, DF_G><<<grid, ROWS_BLOCK, 0, st>>>(c->a0, c->a1, c->box, (real)c->opt.aewald, L.vstart, L.cnt, L.nbr, c->posq,  \
-      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, assign ? 1 : 0, T)
+      c->tpj, c->thlval, c->opt.njpolar, c->mp0, c->mp1, c->mp2, fd, fpd, assign ? 1 : 0, T, P, L.cntu)
    // (rows may all be empty for a tiny system: the kernel still initialises fd / fpd)
    if (ew && tb) LAUNCH_DF(true, true);
    else if (ew) LAUNCH_DF(true, false);
@@ -548,7 +566,7 @@ void apx_dfield_real(apx_ctx* c, cudaStream_t st, real* fd, real* fpd, bool assi
    APX_COUNT_LAUNCH(c);
 #undef LAUNCH_DF
    if (T)
-      c->tl_valid = 1;
+      c->tl_valid = 1, c->tl_p_valid = P ? 1 : 0;
    if (c->nexcl > 0) {
       int g = (c->nexcl + 127) / 128;
       if (tb)
@@ -577,12 +595,16 @@ void apx_precond_dp(apx_ctx* c, const real4* Rv, real4* Z, double* slot, const P
    int grid = rows_grid<PC_G>(c);
    const int* cu = sparse ? L.cntu.p : nullptr;
    double* s1 = excl ? nullptr : slot;
-   if (tb)
-      k_precond_rows<true, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
-         c->opt.njpolar, Rv, Z, s1, c->skip, T);
+   const bool pl = sparse && apx_tlist_usable(c) && c->tl_p_valid && c->tl_P.p;
+   if (pl)
+      k_precond_rows<false, PC_G, true><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
+         c->opt.njpolar, Rv, Z, s1, c->skip, T, c->tl_P);
+   else if (tb)
+      k_precond_rows<true, PC_G, false><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
+         c->opt.njpolar, Rv, Z, s1, c->skip, T, nullptr);
    else
-      k_precond_rows<false, PC_G><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
-         c->opt.njpolar, Rv, Z, s1, c->skip, T);
+      k_precond_rows<false, PC_G, false><<<grid, ROWS_BLOCK, 0, c->stream>>>(c->a0, c->a1, c->n, c->box, udiag, L.vstart, cu, L.nbr, c->posq, c->tpj, c->thlval,
+         c->opt.njpolar, Rv, Z, s1, c->skip, T, nullptr);
    APX_COUNT_LAUNCH(c);
    if (excl) {
       int g = (c->nexcl + 127) / 128;

@@ -767,9 +767,16 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    c->mpole_inited = 1;
    c->mpole_pme_valid = 0;
    // ---- vdW term on its own stream, beside everything below (joins before the reductions)
+   // APX_VDW_AT: where the vdW stream forks from the main stream.  0 = here, beside the solver's prologue (permanent field:
+   // throughput-bound kernels that the vdW rows slow down); 1 = after the prologue, beside the PCG iterations (latency-bound
+   // chains that leave most of every SM idle); 2 = after the solver, beside the energy epilogue
    do_vdw = do_vdw && c->vdw.on;
-   if (do_vdw)
+   static const int vdw_at = getenv("APX_VDW_AT") ? atoi(getenv("APX_VDW_AT")) : 1;
+   c->vdw_fork_vers = -1;
+   if (do_vdw && (vdw_at == 0 || !do_p || c->dist.on))
       apx_vdw_launch(c, vers);
+   else if (do_vdw && vdw_at == 1)
+      c->vdw_fork_vers = vers;      // apx_induce_impl forks it between its prologue and its iterations
    // ---- valence terms, likewise (evalence.cu)
    do_val = do_val && apx_valence_on(c);
    if (do_val)
@@ -784,6 +791,12 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
       iters = c->stats.pcg_iterations;
    } else if (ewald) {
       apx_pme_mpole(c, true);
+   }
+   if (do_vdw && do_p && !c->dist.on && vdw_at == 2)
+      apx_vdw_launch(c, vers);
+   if (c->vdw_fork_vers >= 0) {      // (direct polarization: no iterations to fork beside)
+      apx_vdw_launch(c, c->vdw_fork_vers);
+      c->vdw_fork_vers = -1;
    }
    if (dist && do_p) {
       // converged dipoles of the neighbours owned by other GPUs

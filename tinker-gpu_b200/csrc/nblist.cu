@@ -249,7 +249,7 @@ void apx_list_refresh(apx_ctx* c, bool force, int known_moved)
 {
    int n = c->n;
    bool rebuild = force || !c->list_valid;
-   c->tl_valid = 0;      // positions changed: the stored pair tensors (tlist.cu) are rebuilt by the next operator application
+   c->tl_valid = 0, c->tl_p_valid = 0;      // positions changed: the stored pair tensors (tlist.cu) are rebuilt by the next operator application
    if (!rebuild && known_moved >= 0)
       rebuild = known_moved != 0;
    else if (!rebuild) {
@@ -263,10 +263,14 @@ void apx_list_refresh(apx_ctx* c, bool force, int known_moved)
       rebuild = c->flags_h[0] != 0;
    }
    if (!rebuild) {
-      apx_update_sorted_positions(c);
-      apx_rows_compact(c, false);
-      if (c->vdw.on)
-         apx_vdw_refresh(c, false);
+      // per-step refresh: sorted positions, spline tables, rows cut to the cutoff, vdW sites -- a fixed sequence, one graph
+      if (apx_graph_begin(c, 0x5000 | (c->vdw.on ? 1 : 0))) {
+         apx_update_sorted_positions(c);
+         apx_rows_compact(c, false);
+         if (c->vdw.on)
+            apx_vdw_refresh(c, false);
+         apx_graph_end(c, 0x5000 | (c->vdw.on ? 1 : 0));
+      }
       return;
    }
    // the captured graphs hold the row buffers' addresses: they stay valid across a rebuild unless a buffer had to grow

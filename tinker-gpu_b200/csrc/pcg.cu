@@ -506,7 +506,7 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
          CUDA_CHECK(cudaEventCreate(&e));
    }
    c->uf_used = 0;
-   c->tl_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence (and with it
+   c->tl_valid = 0, c->tl_p_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence (and with it
                          // the captured graphs) does not depend on what ran before
    cudaEventRecord(c->ev0, st);
    const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;   // the predictor replaces the direct guess once its ring is full
@@ -586,7 +586,12 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    // the prologue applied the operator (and with it built the pair tensors) whether it ran eagerly or as a replayed graph:
    // the host flag must say so, or the capture of the first iteration would bake a second build into its graph
    if (apx_tlist_usable(c))
-      c->tl_valid = 1;      // (written by the permanent-field rows of the prologue, field.cu)
+      c->tl_valid = 1, c->tl_p_valid = c->tl_P.p ? 1 : 0;      // (written by the permanent-field rows of the prologue, field.cu)
+   if (c->vdw_fork_vers >= 0) {
+      // energy() asked for the vdW term to start here: beside the iterations, whose short dependent kernels leave the SMs idle
+      apx_vdw_launch(c, c->vdw_fork_vers);
+      c->vdw_fork_vers = -1;
+   }
    if (graphable && c->use_graph && !dist && (c->opt.pcgguess) && c->uf_used == 0)
       c->uf_used = 2;      // the r0 operator launch inside the graph was timed through external event nodes
    int iter = 0;
@@ -634,35 +639,46 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    // no batch sizes to guess, no launches after convergence, no graph per (first iteration, batch length), and the host does
    // not have to look at the convergence flag before it enqueues what follows.  First solve of a context: host-driven and
    // eager (plans, scratch buffers), like every other graph region.
-   const bool use_loop = c->use_graph && c->use_loop && !dist;
+   bool use_loop = c->use_graph && c->use_loop && !dist;
    if (use_loop && !c->loop_exec && c->loop_warm) {
       if (trace_graphs())
          fprintf(stderr, "[apx] capturing the pcg loop body\n");
+      // (a driver without conditional nodes: the first failing call switches this context to the generic batches below)
       cudaGraph_t g = nullptr;
-      CUDA_CHECK(cudaGraphCreate(&g, 0));
-      cudaGraphConditionalHandle h;
-      CUDA_CHECK(cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault));
+      cudaGraphConditionalHandle h = 0;
       cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
-      np.conditional.handle = h;
-      np.conditional.type = cudaGraphCondTypeWhile;
-      np.conditional.size = 1;
       cudaGraphNode_t node;
-      CUDA_CHECK(cudaGraphAddNode(&node, g, nullptr, 0, &np));
-      cudaGraph_t body = np.conditional.phGraph_out[0];
-      const int before = c->stats.kernel_launches;
-      c->capturing = 1;
-      CUDA_CHECK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-      enqueue_iteration(0, true, (unsigned long long)h);
-      cudaGraph_t out = nullptr;
-      cudaError_t e = cudaStreamEndCapture(st, &out);
-      c->capturing = 0;
-      if (e != cudaSuccess)
-         APX_THROW(std::string("PCG loop capture failed: ") + cudaGetErrorString(e));
-      c->loop_launches = c->stats.kernel_launches - before;
-      c->stats.kernel_launches = before;
-      CUDA_CHECK(cudaGraphInstantiate(&c->loop_exec, g, 0));
-      cudaGraphDestroy(g);
+      bool ok = cudaGraphCreate(&g, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&h, g, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+      if (ok) {
+         np.conditional.handle = h;
+         np.conditional.type = cudaGraphCondTypeWhile;
+         np.conditional.size = 1;
+         ok = cudaGraphAddNode(&node, g, nullptr, 0, &np) == cudaSuccess;
+      }
+      cudaGraph_t body = ok ? np.conditional.phGraph_out[0] : nullptr;
+      ok = ok && cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+         const int before = c->stats.kernel_launches;
+         c->capturing = 1;
+         enqueue_iteration(0, true, (unsigned long long)h);
+         cudaGraph_t out = nullptr;
+         ok = cudaStreamEndCapture(st, &out) == cudaSuccess;
+         c->capturing = 0;
+         c->loop_launches = c->stats.kernel_launches - before;
+         c->stats.kernel_launches = before;
+         ok = ok && cudaGraphInstantiate(&c->loop_exec, g, 0) == cudaSuccess;
+      }
+      if (g)
+         cudaGraphDestroy(g);
+      if (!ok) {
+         (void)cudaGetLastError();
+         c->loop_exec = nullptr;
+         c->use_loop = 0;
+         if (trace_graphs())
+            fprintf(stderr, "[apx] conditional graph nodes unavailable: generic iteration batches instead\n");
+      }
    }
+   use_loop = use_loop && c->use_loop;
    if (use_loop && c->loop_exec) {
       CUDA_CHECK(cudaGraphLaunch(c->loop_exec, st));
       CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -695,17 +711,16 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    while (!done) {
       int nit = std::min(batch, politer - iter);
       if (generic) {
-         apx_ctx::PcgGraph* G = nullptr;
-         for (auto& g : c->graphs)
-            if (g.it0 == 0 && g.nit == nit)
-               G = &g;
-         if (!G) {
+         auto find_or_capture = [&](int len) -> apx_ctx::PcgGraph* {
+            for (auto& g : c->graphs)
+               if (g.it0 == 0 && g.nit == len)
+                  return &g;
             if (trace_graphs())
-               fprintf(stderr, "[apx] capturing generic pcg graph (%d iterations)\n", nit);
+               fprintf(stderr, "[apx] capturing generic pcg graph (%d iterations)\n", len);
             int before = c->stats.kernel_launches;
             c->capturing = 1;
             CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int b = 0; b < nit; ++b)
+            for (int b = 0; b < len; ++b)
                enqueue_iteration(0, true, 0);
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -713,14 +728,24 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
             if (e != cudaSuccess)
                APX_THROW(std::string("PCG graph capture failed: ") + cudaGetErrorString(e));
             apx_ctx::PcgGraph ng;
-            ng.it0 = 0, ng.nit = nit;
+            ng.it0 = 0, ng.nit = len;
             ng.launches = c->stats.kernel_launches - before;
             c->stats.kernel_launches = before;
             CUDA_CHECK(cudaGraphInstantiate(&ng.exec, graph, 0));
             cudaGraphDestroy(graph);
             c->graphs.push_back(ng);
-            G = &c->graphs.back();
+            return &c->graphs.back();
+         };
+         if (first_batch && c->graphs.empty()) {
+            // the iteration count of an MD run wanders by one: the neighbouring batch lengths are captured now, with the first,
+            // instead of 2 ms into some later step
+            c->graphs.reserve(16);
+            if (nit + 1 <= politer)
+               find_or_capture(nit + 1);
+            if (nit > 1)
+               find_or_capture(nit - 1);
          }
+         apx_ctx::PcgGraph* G = find_or_capture(nit);
          CUDA_CHECK(cudaGraphLaunch(G->exec, st));
          c->stats.kernel_launches += G->launches;
          iter += nit;

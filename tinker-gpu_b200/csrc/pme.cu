@@ -292,6 +292,184 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n
    }
 }
 
+#ifndef APX_DOUBLE
+// ---- second generation of the induced-dipole spread / gather (mixed build, even nfft1) ---------------------------------------
+// What ncu said about the kernels above at 1 M atoms (profiles/r01j_water1m_ncu_full_summary.txt): 7-8 % of the HBM roofline with
+// 2-3 times the algorithmic DRAM traffic.  Two causes, both removed here:
+//   * the per-atom spline table: 256 B per atom and launch, against 16 B of fractional coordinates.  Lanes 0..2 of an atom's
+//     group evaluate the order-5 weights and first derivatives of one axis each (40 flops) into shared memory instead;
+//   * one 8-byte reduction per grid point and atom.  Grid points that are neighbours in x are neighbours in memory, so the
+//     five x-points of a stencil row are covered by THREE 16-byte aligned pairs (one padding point of weight 0): 75 vector
+//     reductions (REDG.E.ADD.F32x4) per atom instead of 125, and 75 16-byte loads in the gather.  nfft1 even: a pair never
+//     straddles the periodic wrap.
+// weights and first derivatives only (dipoles): th[p] = {theta_p, theta'_p}
+__device__ __forceinline__ void bspline5_01(real w, real2 th[5])
+{
+   const real a2_0 = 1 - w, a2_1 = w;
+   const real a3_0 = (real)0.5 * (1 - w) * a2_0, a3_1 = (real)0.5 * ((w + 1) * a2_0 + (2 - w) * a2_1), a3_2 = (real)0.5 * w * a2_1;
+   const real t3 = (real)(1.0 / 3.0);
+   const real a4_0 = t3 * (1 - w) * a3_0, a4_1 = t3 * ((w + 2) * a3_0 + (2 - w) * a3_1), a4_2 = t3 * ((w + 1) * a3_1 + (3 - w) * a3_2),
+              a4_3 = t3 * w * a3_2;
+   th[0] = make_float2((real)0.25 * (1 - w) * a4_0, -a4_0);
+   th[1] = make_float2((real)0.25 * ((w + 3) * a4_0 + (2 - w) * a4_1), a4_0 - a4_1);
+   th[2] = make_float2((real)0.25 * ((w + 2) * a4_1 + (3 - w) * a4_2), a4_1 - a4_2);
+   th[3] = make_float2((real)0.25 * ((w + 1) * a4_2 + (4 - w) * a4_3), a4_2 - a4_3);
+   th[4] = make_float2((real)0.25 * w * a4_3, a4_3);
+}
+
+// lanes 0..2 of the group: axis l of atom s -> sth[axis][0..4] (+ two zero pads [5], [6] so that th[ix + 1] is defined for
+// ix = -1 .. 5), stencil origin -> sorg[axis]
+__device__ __forceinline__ void stencil_fill(const pos_t pos, int l, int n1, int n2, int n3, real2 (*sth)[8], int* sorg)
+{
+   if (l < 3) {
+      const unsigned q = l == 0 ? pos.x : (l == 1 ? pos.y : pos.z);
+      const unsigned nf = (unsigned)(l == 0 ? n1 : (l == 1 ? n2 : n3));
+      const unsigned qs = q + 0x80000000u;
+      int ii = (int)__umulhi(qs, nf);
+      const real w = (real)(qs * nf) * (real)2.3283064365386963e-10;
+      ii -= 4;
+      sorg[l] = ii < 0 ? ii + (int)nf : ii;
+      real2 th[5];
+      bspline5_01(w, th);
+      sth[l][0] = make_float2(0, 0);
+      #pragma unroll
+      for (int p = 0; p < 5; ++p)
+         sth[l][p + 1] = th[p];
+      sth[l][6] = make_float2(0, 0);
+   }
+   __syncwarp();
+}
+
+template <int LG>
+__global__ void __launch_bounds__(128) k_spread_dp2(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
+   const pos_t* __restrict__ posq, const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
+{
+   if (skip && skip[1])
+      return;
+   __shared__ real2 sth[128 / LG][3][8];
+   __shared__ int sorg[128 / LG][4];
+   const int l = threadIdx.x & (LG - 1), gib = threadIdx.x / LG;
+   const int s_ = blockIdx.x * (128 / LG) + gib;
+   const bool act = s_ < n;
+   const int s = act ? s_ : n - 1;
+   stencil_fill(posq[s], l, n1, n2, n3, sth[gib], sorg[gib]);
+   if (!act)
+      return;
+   const int i1 = sorg[gib][0], i2 = sorg[gib][1], i3 = sorg[gib][2];
+   V3 d, q;
+   load_dp(U, s, d, q);
+   real fd[3], fp[3];
+   #pragma unroll
+   for (int f = 0; f < 3; ++f) {
+      fd[f] = X.a[0][f] * d.x + X.a[1][f] * d.y + X.a[2][f] * d.z;
+      fp[f] = X.a[0][f] * q.x + X.a[1][f] * q.y + X.a[2][f] * q.z;
+   }
+   const int x0 = i1 & ~1;          // aligned pair holding the first stencil point
+   const int off = i1 - x0;         // 0 or 1: stencil index of point x0 + j is j - off
+   for (int it = l; it < 75; it += LG) {
+      const int row = it / 3, pr = it - 3 * row;
+      const int iz = row / 5, iy = row - 5 * iz;
+      const int zl = zlocal(i3 + iz, n3, zbase);
+      if (zl >= nzl)
+         continue;
+      const real2 u = sth[gib][1][iy + 1], v = sth[gib][2][iz + 1];
+      const int j0 = 2 * pr - off;      // stencil index of the pair's first point: -1 .. 4
+      const real2 t0 = sth[gib][0][j0 + 1], t1 = sth[gib][0][j0 + 2];
+      const real uv = u.x * v.x, duv = u.y * v.x, udv = u.x * v.y;
+      // value of point j:  fd . (t'_j u v, t_j u' v, t_j u v')
+      const real a0 = t0.y * uv, b0 = t0.x * duv, c0 = t0.x * udv;
+      const real a1 = t1.y * uv, b1 = t1.x * duv, c1 = t1.x * udv;
+      float4 val;
+      val.x = fd[0] * a0 + fd[1] * b0 + fd[2] * c0;
+      val.y = fp[0] * a0 + fp[1] * b0 + fp[2] * c0;
+      val.z = fd[0] * a1 + fd[1] * b1 + fd[2] * c1;
+      val.w = fp[0] * a1 + fp[1] * b1 + fp[2] * c1;
+      int x = x0 + 2 * pr;
+      x = x >= n1 ? x - n1 : x;
+      cplx* g = &grid[((size_t)zl * n2 + wrapi(i2 + iy, n2)) * n1 + x];
+      asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(g), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
+   }
+}
+
+template <int EPI, int LG>
+__global__ void __launch_bounds__(128) k_gather_dp2(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl, real selfterm,
+   const pos_t* __restrict__ posq, const real4* __restrict__ tpj, const cplx* __restrict__ grid, const real4* __restrict__ U,
+   const real4* __restrict__ F, real* __restrict__ out_d, real* __restrict__ out_p, real4* __restrict__ OUT,
+   double* __restrict__ slot, const int* __restrict__ skip, const int* __restrict__ itp)
+{
+   if (skip && skip[1])
+      return;
+   __shared__ real2 sth[128 / LG][3][8];
+   __shared__ int sorg[128 / LG][4];
+   const int l = threadIdx.x & (LG - 1), gib = threadIdx.x / LG;
+   const int s_ = blockIdx.x * (128 / LG) + gib;
+   const bool act = s_ < n;
+   const int s = act ? s_ : n - 1;
+   double dot_d = 0, dot_p = 0;
+   stencil_fill(posq[s], l, n1, n2, n3, sth[gib], sorg[gib]);
+   const int i1 = sorg[gib][0], i2 = sorg[gib][1], i3 = sorg[gib][2];
+   const int x0 = i1 & ~1, off = i1 - x0;
+   real fd[3] = {0, 0, 0}, fp[3] = {0, 0, 0};
+   for (int it = l; it < 75; it += LG) {
+      const int row = it / 3, pr = it - 3 * row;
+      const int iz = row / 5, iy = row - 5 * iz;
+      const int zl = min(zlocal(i3 + iz, n3, zbase), nzl - 1);
+      int x = x0 + 2 * pr;
+      x = x >= n1 ? x - n1 : x;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(&grid[((size_t)zl * n2 + wrapi(i2 + iy, n2)) * n1 + x]));
+      const real2 u = sth[gib][1][iy + 1], v = sth[gib][2][iz + 1];
+      const int j0 = 2 * pr - off;
+      const real2 t0 = sth[gib][0][j0 + 1], t1 = sth[gib][0][j0 + 2];
+      const real uv = u.x * v.x, duv = u.y * v.x, udv = u.x * v.y;
+      const real a = t0.y * g.x + t1.y * g.z, b = t0.x * g.x + t1.x * g.z;      // d grid: sum of t' g and of t g over the pair
+      const real ap = t0.y * g.y + t1.y * g.w, bp = t0.x * g.y + t1.x * g.w;    // p grid
+      fd[0] += a * uv, fd[1] += b * duv, fd[2] += b * udv;
+      fp[0] += ap * uv, fp[1] += bp * duv, fp[2] += bp * udv;
+   }
+   #pragma unroll
+   for (int q = 0; q < 3; ++q) {
+      #pragma unroll
+      for (int o = LG / 2; o > 0; o >>= 1) {
+         fd[q] += __shfl_xor_sync(0xffffffffu, fd[q], o);
+         fp[q] += __shfl_xor_sync(0xffffffffu, fp[q], o);
+      }
+   }
+   if (l == 0 && act) {
+      V3 ud, up;
+      load_dp(U, s, ud, up);
+      V3 cd = v3(X.a[0][0] * fd[0] + X.a[0][1] * fd[1] + X.a[0][2] * fd[2], X.a[1][0] * fd[0] + X.a[1][1] * fd[1] + X.a[1][2] * fd[2],
+         X.a[2][0] * fd[0] + X.a[2][1] * fd[1] + X.a[2][2] * fd[2]);
+      V3 cp = v3(X.a[0][0] * fp[0] + X.a[0][1] * fp[1] + X.a[0][2] * fp[2], X.a[1][0] * fp[0] + X.a[1][1] * fp[1] + X.a[1][2] * fp[2],
+         X.a[2][0] * fp[0] + X.a[2][1] * fp[1] + X.a[2][2] * fp[2]);
+      V3 ed = selfterm * ud - cd, ep = selfterm * up - cp;
+      if (F) {
+         V3 a, b;
+         load_dp(F, s, a, b);
+         ed += a;
+         ep += b;
+      }
+      if (EPI == 0) {
+         out_d[3 * s] = ed.x, out_d[3 * s + 1] = ed.y, out_d[3 * s + 2] = ed.z;
+         out_p[3 * s] = ep.x, out_p[3 * s + 1] = ep.y, out_p[3 * s + 2] = ep.z;
+      } else if (EPI == 1) {
+         if (tpj[s].y == 0) {
+            ed = v3(0, 0, 0);
+            ep = v3(0, 0, 0);
+         }
+         store_dp(OUT, s, ed, ep);
+      } else {
+         real pinv = tpj[s].z;
+         V3 vd = pinv * ud - ed, vp = pinv * up - ep;
+         store_dp(OUT, s, vd, vp);
+         dot_d = (double)ud.x * vd.x + (double)ud.y * vd.y + (double)ud.z * vd.z;
+         dot_p = (double)up.x * vp.x + (double)up.y * vp.y + (double)up.z * vp.z;
+      }
+   }
+   if (EPI == 2)
+      pcg_block_add2(dot_d, dot_p, pcg_slot_of(slot, itp), 2, 3);
+}
+#endif
+
 // --- influence function ------------------------------------------------------------------------
 // (all three kernels below index a slab [k3][k2 in y0..y0+ny)[k1] of the transformed grid: the whole
 //  grid on one GPU, the rows this GPU holds after the transpose of the slab FFT otherwise)
@@ -777,6 +955,14 @@ inline real selfterm(apx_ctx* c)
 // elements of the grid this GPU holds in real space (all planes, or its slab + halo planes) and of
 // the transformed slab it multiplies by the influence function
 inline size_t nlocal(apx_ctx* c) { return (size_t)c->nfft1 * c->nfft2 * c->nzl; }
+#ifndef APX_DOUBLE
+// second-generation dipole spread / gather (pairs of x-points, splines evaluated in the kernel): APX_PME_GEN2=0 for the first
+inline bool pme_gen2(const apx_ctx* c)
+{
+   static const int on = getenv("APX_PME_GEN2") ? atoi(getenv("APX_PME_GEN2")) : 1;
+   return on && (c->nfft1 % 2) == 0;
+}
+#endif
 inline size_t nconv(apx_ctx* c) { return (size_t)c->nfft1 * c->qny * c->nfft3; }
 inline cplx* conv_grid(apx_ctx* c) { return c->dist.on ? c->dist.tbuf.p : c->qgrid.p; }
 } // namespace
@@ -912,6 +1098,14 @@ void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 {
    const int a0 = c->a0, no = c->a1 - c->a0;
    Xform X = make_xform(c);
+#ifndef APX_DOUBLE
+   if (no > 0 && pme_gen2(c)) {
+      k_spread_dp2<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
+         c->posq + a0, U + 2 * (size_t)a0, c->qgrid, c->skip);
+      APX_COUNT_LAUNCH(c);
+      return;
+   }
+#endif
    if (no > 0)
       k_spread_dp<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
          c->theta + 16 * (size_t)a0, U + 2 * (size_t)a0, c->qgrid, c->skip);
@@ -942,6 +1136,20 @@ void apx_pme_gather_dp(apx_ctx* c, int epi, const real4* U, const real4* F, real
    k_gather_dp<E, PME_LG><<<g, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),           \
       c->theta + 16 * (size_t)a0, c->tpj + a0, c->qgrid, U + 2 * (size_t)a0, F ? F + 2 * (size_t)a0 : nullptr,                 \
       fd ? fd + 3 * (size_t)a0 : nullptr, fp ? fp + 3 * (size_t)a0 : nullptr, OUT ? OUT + 2 * (size_t)a0 : nullptr, slot, c->skip, itp)
+#ifndef APX_DOUBLE
+#define GATHER_DP2(E)                                                                                                      \
+   k_gather_dp2<E, PME_LG><<<g, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),          \
+      c->posq + a0, c->tpj + a0, c->qgrid, U + 2 * (size_t)a0, F ? F + 2 * (size_t)a0 : nullptr,                               \
+      fd ? fd + 3 * (size_t)a0 : nullptr, fp ? fp + 3 * (size_t)a0 : nullptr, OUT ? OUT + 2 * (size_t)a0 : nullptr, slot, c->skip, itp)
+   if (no > 0 && pme_gen2(c)) {
+      if (epi == 0) GATHER_DP2(0);
+      else if (epi == 1) GATHER_DP2(1);
+      else GATHER_DP2(2);
+      APX_COUNT_LAUNCH(c);
+      return;
+   }
+#undef GATHER_DP2
+#endif
    if (no > 0) {
       if (epi == 0) GATHER_DP(0);
       else if (epi == 1) GATHER_DP(1);

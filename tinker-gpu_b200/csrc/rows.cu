@@ -282,7 +282,11 @@ __global__ void __launch_bounds__(128) k_rows_pack(int n, const int* __restrict_
       vnbr[dst + q] = vpad[src + q];
 }
 
-// one warp per atom: two sweeps over its Verlet row (positions stay in L1 between them)
+// one warp per atom.  Rows of up to 32 * RC_R entries (all of them at AMOEBA densities: ~300 entries at 9 A) are read ONCE --
+// index, position and class (inside usolve-cutoff / inside the cutoff / outside) of every entry stay in registers, so the
+// RC_R dependent index -> position round trips of a lane overlap -- and written in two groups, the preconditioner's pairs
+// first.  Longer rows take two sweeps (positions stay in L1 between them).
+#define RC_R 16
 __global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real cut2, real ucut2, const real4* __restrict__ posd,
    const int* __restrict__ vstart, const int* __restrict__ vnbr, int* __restrict__ nbr, int* __restrict__ cnt,
    int* __restrict__ cntu, unsigned long long* __restrict__ total)
@@ -296,27 +300,66 @@ __global__ void __launch_bounds__(128) k_rows_compact(int a0, int n, Box b, real
    const unsigned lt = (1u << lane) - 1;
    int out = beg;
    int nu = 0;
-   for (int sweep = 0; sweep < 2; ++sweep) {
-      if (sweep == 0 && ucut2 <= 0)
-         continue;
-      for (int q0 = beg; q0 < end; q0 += 32) {
-         int q = q0 + lane;
-         const int k = q < end ? vnbr[q] : 0;      // may carry ROW_LISTED_FLAG: copied as is
-         bool ok = false;
+   if (end - beg <= 32 * RC_R) {
+      int kk[RC_R];
+      unsigned char cls[RC_R];
+      #pragma unroll
+      for (int j = 0; j < RC_R; ++j) {
+         const int q = beg + 32 * j + lane;
+         kk[j] = q < end ? vnbr[q] : 0;      // may carry ROW_LISTED_FLAG: copied as is
+      }
+      int n1 = 0;
+      #pragma unroll
+      for (int j = 0; j < RC_R; ++j) {
+         const int q = beg + 32 * j + lane;
+         cls[j] = 0;
          if (q < end) {
-            real4 pk = posd[k & ROW_INDEX_MASK];
+            const real4 pk = posd[kk[j] & ROW_INDEX_MASK];
             real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
             apx_image(b, dx, dy, dz);
-            real r2 = dx * dx + dy * dy + dz * dz;
-            ok = sweep == 0 ? r2 <= ucut2 : (r2 > ucut2 && r2 <= cut2);
+            const real r2 = dx * dx + dy * dy + dz * dz;
+            cls[j] = r2 <= ucut2 ? 1 : (r2 <= cut2 ? 2 : 0);
          }
-         unsigned m = __ballot_sync(FULL, ok);
-         if (ok)
-            nbr[out + __popc(m & lt)] = k;
-         out += __popc(m);
+         n1 += __popc(__ballot_sync(FULL, cls[j] == 1));
       }
-      if (sweep == 0)
-         nu = out - beg;
+      nu = n1;
+      int o1 = beg, o2 = beg + n1;
+      #pragma unroll
+      for (int j = 0; j < RC_R; ++j) {
+         if (beg + 32 * j >= end)
+            break;
+         const unsigned m1 = __ballot_sync(FULL, cls[j] == 1), m2 = __ballot_sync(FULL, cls[j] == 2);
+         if (cls[j] == 1)
+            nbr[o1 + __popc(m1 & lt)] = kk[j];
+         else if (cls[j] == 2)
+            nbr[o2 + __popc(m2 & lt)] = kk[j];
+         o1 += __popc(m1);
+         o2 += __popc(m2);
+      }
+      out = o2;
+   } else {
+      for (int sweep = 0; sweep < 2; ++sweep) {
+         if (sweep == 0 && ucut2 <= 0)
+            continue;
+         for (int q0 = beg; q0 < end; q0 += 32) {
+            int q = q0 + lane;
+            const int k = q < end ? vnbr[q] : 0;
+            bool ok = false;
+            if (q < end) {
+               real4 pk = posd[k & ROW_INDEX_MASK];
+               real dx = pk.x - pi.x, dy = pk.y - pi.y, dz = pk.z - pi.z;
+               apx_image(b, dx, dy, dz);
+               real r2 = dx * dx + dy * dy + dz * dz;
+               ok = sweep == 0 ? r2 <= ucut2 : (r2 > ucut2 && r2 <= cut2);
+            }
+            unsigned m = __ballot_sync(FULL, ok);
+            if (ok)
+               nbr[out + __popc(m & lt)] = k;
+            out += __popc(m);
+         }
+         if (sweep == 0)
+            nu = out - beg;
+      }
    }
    if (lane == 0) {
       cnt[i] = out - beg;

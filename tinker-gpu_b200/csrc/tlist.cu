@@ -32,16 +32,6 @@ __device__ __forceinline__ int tl_as_int(real w)
    return __float_as_int(w);
 #endif
 }
-// load of a tensor entry: read once per application, but read again by the NEXT application -- at dhfr2 size the whole
-// tensor list (53 MB) stays in L2 between the 8 applications of an induce(), so no evict-first hint (ld.global.cs)
-__device__ __forceinline__ real4 tl_ld(const real4* p)
-{
-#ifdef APX_DOUBLE
-   return *p;
-#else
-   return __ldg(p);
-#endif
-}
 // ---- build: one pass over the compacted rows, same lane groups as the operator -----------------------------------------------
 template <bool EWALD, bool TABLE, bool PRECOND, int G>
 __global__ void __launch_bounds__(ROWS_BLOCK) k_tlist_build(int a0, int a1, Box box, real aewald, const int* __restrict__ vstart,
@@ -81,39 +71,11 @@ __global__ void __launch_bounds__(ROWS_BLOCK) k_tlist_build(int a0, int a1, Box 
    }
 }
 
-// ---- apply: F_i = sum_k T_ik (ud_k, up_k) ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void tl_apply(const real4 t, const real4 ua, const real4 ub, V3& fd, V3& fp)
-{
-   const real sd = tl_signed(t.y * ua.x + t.z * ua.y + t.w * ua.z, t.x);
-   const real sp = tl_signed(t.y * ua.w + t.z * ub.x + t.w * ub.y, t.x);
-   fd.x += sd * t.y - t.x * ua.x;
-   fd.y += sd * t.z - t.x * ua.y;
-   fd.z += sd * t.w - t.x * ua.z;
-   fp.x += sp * t.y - t.x * ua.w;
-   fp.y += sp * t.z - t.x * ub.x;
-   fp.z += sp * t.w - t.x * ub.y;
-}
-
 // Memory-level parallelism.  ptxas sinks every load of an unrolled body next to its first use (40 registers, one entry in
 // flight per lane; volatile asm loads and compiler barriers do not stop it), which serialises 2 x UNROLL memory round trips per
 // lane.  MLP = true makes every FMA of the body depend on ALL its loads through real data flow: the loaded words are OR-ed
 // together, AND-ed with a kernel argument that is zero at run time, and the (zero) result is XOR-ed into the first factor of
 // each entry -- 9 logic instructions per 4 entries, and all 16 loads are in flight before the first FMA can issue.
-// the neighbour's packed dipole pair (32 bytes, 32-byte aligned) in ONE 256-bit load (LDG.E.256, new with sm_100): the gathers
-// are what bounds this kernel at dhfr2 size -- every lane of a gather touches another cache line and L1 looks up one line per
-// cycle, so two 128-bit gathers per entry cost 64 cycles per warp row (22 us per launch at 160 atoms per SM), one costs 32
-__device__ __forceinline__ void tl_gather(const real4* __restrict__ U, int k, real4& ua, real4& ub)
-{
-#ifdef APX_DOUBLE
-   ua = U[2 * k];
-   ub = U[2 * k + 1];
-#else
-   asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-       : "=f"(ua.x), "=f"(ua.y), "=f"(ua.z), "=f"(ua.w), "=f"(ub.x), "=f"(ub.y), "=f"(ub.z), "=f"(ub.w)
-       : "l"(U + 2 * (size_t)k));
-#endif
-}
-
 template <int G, int UNROLL, bool MLP>
 __device__ __forceinline__ void tl_row(const int* __restrict__ nbr, const real4* __restrict__ T, const real4* __restrict__ U, int beg,
    int len, int l, unsigned zero, V3& fd, V3& fp)
@@ -187,7 +149,9 @@ void apx_tlist_reserve(apx_ctx* c)
    if (!c->tlist_on)
       return;
    c->tl_T.ensure((size_t)c->rows.nverlet + 32);
-   c->tl_valid = 0;
+   if (c->opt.use_polar && c->opt.pcgprec && c->opt.usolve_cutoff > 0)
+      c->tl_P.ensure((size_t)c->rows.nverlet + 32);
+   c->tl_valid = 0, c->tl_p_valid = 0;
 }
 
 #define TL_G 8
