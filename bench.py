@@ -562,7 +562,7 @@ def run_dynamics(args, rank, world, local_rank):
                    # medians, and the list-rebuild steps reported separately
                    "ms_per_step_median": float(np.median(ms_steps)), "ms_per_induce_median": float(np.median(ms_induce)),
                    "ms_steps": [round(float(m), 3) for m in ms_steps], "rebuilt": [int(r) for r in rebuilt],
-                   "ms_list_rebuild_last": st.get("ms_list"),
+                   "ms_list_rebuild_last": st.get("ms_list"), "solver_batch_misses": st.get("energy_retries"),
                    "ms_per_step_without_rebuild": float(np.mean([m for m, r in zip(ms_steps, rebuilt) if not r])) if not all(rebuilt) else None,
                    "ms_per_step_with_rebuild": float(np.mean([m for m, r in zip(ms_steps, rebuilt) if r])) if any(rebuilt) else None,
                    "batch": {"value": ns_per_day(ms_batch, world), "unit": "ns/day", "ms_per_step": ms_batch,

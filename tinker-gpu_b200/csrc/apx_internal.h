@@ -341,6 +341,7 @@ struct apx_ctx {
                                    // 3 % slower in batches of steps on this driver: profiles/r02j)
    int pcg_n = 0, pcg_n_slack = 0; // iterations in the first batch of a solve (largest count seen recently)
    int vdw_fork_vers = -1;         // >= 0: energy() wants apx_induce_impl to fork the vdW stream after its prologue (mplar.cu)
+   int induce_iter_launched = 0;   // iterations enqueued by the deferred first batch
    int induce_pending = 0, induce_pending_predict = 0;      // a deferred solve awaits apx_induce_finish
    int use_graph = 1;
    int capturing = 0;
@@ -349,7 +350,9 @@ struct apx_ctx {
    struct StepGraph {
       cudaGraphExec_t exec = nullptr;
       int launches = 0, warm = 0;
+      int conditional = 0;      // the region is the body of an IF node keyed on a device flag (apx_graph_begin with cond_flag)
    };
+   cudaGraph_t cond_outer = nullptr;     // graph under construction that owns the IF node whose body is being captured
    std::map<int, StepGraph> step_graphs;
    int graph_key_open = -1, graph_launches_before = 0;
    unsigned char* red_h = nullptr;       // pinned: one copy brings every reduced scalar of a step to the host
@@ -486,11 +489,16 @@ __device__ __forceinline__ const double* pcg_slot_of(const double* base, const i
 void apx_precond_apply(apx_ctx* c, const real* rd, const real* rp, real* zd, real* zp);
 // ---- pcg.cu
 bool apx_induce_impl(apx_ctx* c, bool defer = false);      // true: apx_induce_finish is pending (after the caller's synchronisation)
+void apx_induce_resume(apx_ctx* c);                         // after a finish that returned false: more iterations, waiting for them
 bool apx_induce_finish(apx_ctx* c);                         // false: not converged in the deferred batch, redo without defer
 void apx_pcg_graphs_invalidate(apx_ctx* c);
 // if (apx_graph_begin(c, key)) { enqueue the region on c->stream; apx_graph_end(c, key); }
 // first call: runs eagerly (lazy allocations happen); second: captured, instantiated, launched; later: replayed.
-bool apx_graph_begin(apx_ctx* c, int key);
+// cond_flag != nullptr: the captured region becomes the body of a conditional IF node that runs only when *cond_flag != 0 at
+// that point of the stream (a one-thread kernel ahead of the node reads the flag) -- work enqueued behind a solver that may
+// not have converged yet.  apx_graph_is_conditional tells whether the replayed graph really has that form.
+bool apx_graph_begin(apx_ctx* c, int key, const int* cond_flag = nullptr);
+bool apx_graph_is_conditional(apx_ctx* c, int key);
 void apx_graph_end(apx_ctx* c, int key);
 void apx_upred_configure(apx_ctx* c, int polpred);             // sets opt.polpred, sizes and empties the ring
 void apx_pack_dp(apx_ctx* c, const real* d, const real* p, real4* out);

@@ -738,7 +738,6 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
 void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val)
 {
    if (!energy_once(c, vers, do_m, do_p, out, do_vdw, do_val, true)) {
-      c->stats.energy_retries++;
       if (!energy_once(c, vers, do_m, do_p, out, do_vdw, do_val, false))
          APX_THROW("energy: the induced-dipole solver did not finish");
    }
@@ -771,7 +770,7 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    // throughput-bound kernels that the vdW rows slow down); 1 = after the prologue, beside the PCG iterations (latency-bound
    // chains that leave most of every SM idle); 2 = after the solver, beside the energy epilogue
    do_vdw = do_vdw && c->vdw.on;
-   static const int vdw_at = getenv("APX_VDW_AT") ? atoi(getenv("APX_VDW_AT")) : 1;
+   static const int vdw_at = getenv("APX_VDW_AT") ? atoi(getenv("APX_VDW_AT")) : 0;      // measured on dhfr2 MD: 1.20 / 1.25 / 1.29 ms per step for 0 / 1 / 2
    c->vdw_fork_vers = -1;
    if (do_vdw && (vdw_at == 0 || !do_p || c->dist.on))
       apx_vdw_launch(c, vers);
@@ -805,8 +804,13 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
       apx_unpack_dp_all(c, c->pk_p, c->uind, c->uinp);
    }
    // ---- real space, reciprocal space, torques: one fixed launch sequence per (vers, terms) -> one CUDA graph
-   const int ekey = 0x4000 | (vers & 0xff) | (do_m ? 0x100 : 0) | (do_p ? 0x200 : 0);
-   const bool eager = apx_graph_begin(c, ekey);
+   // Behind a deferred solve the region is the body of an IF node keyed on the solver's convergence flag: should the first batch
+   // of iterations not have converged, nothing of it runs, the accumulators keep what the vdW / valence terms put there, and
+   // the region is simply launched again once the remaining iterations are done (below).
+   const bool cond_epilogue = do_p && c->opt.poltyp_mutual && !dist && c->use_graph != 0;
+   const int ekey = 0x4000 | (vers & 0xff) | (do_m ? 0x100 : 0) | (do_p ? 0x200 : 0) | (cond_epilogue ? 0x800 : 0);
+   auto epilogue = [&]() {
+   const bool eager = apx_graph_begin(c, ekey, cond_epilogue ? c->flags.p + 1 : nullptr);
    if (eager) {
    MplarArgs A;
    A.a0 = c->a0;
@@ -910,6 +914,8 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    }
    apx_graph_end(c, ekey);
    }
+   };
+   epilogue();
    if (do_vdw)
       apx_vdw_join(c);
    if (do_val)
@@ -930,8 +936,17 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    cudaEventRecord(c->ev3, st);
    CUDA_CHECK(cudaStreamSynchronize(st));
    if (induce_deferred) {
-      if (!apx_induce_finish(c))      // iteration count, timings, predictor history, the not-converged error
-         return false;
+      if (!apx_induce_finish(c)) {      // iteration count, timings, predictor history, the not-converged error
+         // the unawaited first batch of iterations did not converge
+         c->stats.energy_retries++;
+         if (!apx_graph_is_conditional(c, ekey))
+            return false;      // the epilogue ran on unconverged dipoles: the caller repeats the whole evaluation
+         apx_induce_resume(c);      // the rest of the iterations, waited for
+         epilogue();                // its IF node did not fire the first time: the accumulators are as the other terms left them
+         CUDA_CHECK(cudaMemcpyAsync(c->red_h, c->ebuf.p, tail, cudaMemcpyDeviceToHost, st));
+         cudaEventRecord(c->ev3, st);
+         CUDA_CHECK(cudaStreamSynchronize(st));
+      }
       iters = c->stats.pcg_iterations;
    }
    const fixed_t* eb = reinterpret_cast<const fixed_t*>(c->red_h);

@@ -414,7 +414,18 @@ void apx_pcg_graphs_invalidate(apx_ctx* c)
    c->step_graphs.clear();
 }
 
-bool apx_graph_begin(apx_ctx* c, int key)
+__global__ void k_set_cond(const int* __restrict__ flag, cudaGraphConditionalHandle h)
+{
+   cudaGraphSetConditional(h, *flag != 0 ? 1u : 0u);
+}
+
+bool apx_graph_is_conditional(apx_ctx* c, int key)
+{
+   auto it = c->step_graphs.find(key);
+   return it != c->step_graphs.end() && it->second.exec && it->second.conditional;
+}
+
+bool apx_graph_begin(apx_ctx* c, int key, const int* cond_flag)
 {
    c->graph_key_open = -1;
    if (!c->use_graph || c->dist.on || c->capturing)
@@ -430,9 +441,50 @@ bool apx_graph_begin(apx_ctx* c, int key)
       return true;
    }
    if (trace_graphs())
-      fprintf(stderr, "[apx] capturing step graph 0x%x\n", key);
+      fprintf(stderr, "[apx] capturing step graph 0x%x%s\n", key, cond_flag ? " (conditional)" : "");
    c->graph_key_open = key;
    c->graph_launches_before = c->stats.kernel_launches;
+   c->cond_outer = nullptr;
+   G.conditional = 0;
+   if (cond_flag) {
+      // outer graph: [k_set_cond] -> [IF node]; the region is captured into the IF node's body
+      cudaGraph_t g = nullptr;
+      cudaGraphConditionalHandle h = 0;
+      bool ok = cudaGraphCreate(&g, 0) == cudaSuccess && cudaGraphConditionalHandleCreate(&h, g, 0, cudaGraphCondAssignDefault) == cudaSuccess;
+      cudaGraphNode_t first = nullptr, cnode = nullptr;
+      if (ok) {
+         ok = cudaStreamBeginCaptureToGraph(c->stream, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+         if (ok) {
+            k_set_cond<<<1, 1, 0, c->stream>>>(cond_flag, h);
+            cudaGraph_t out = nullptr;
+            ok = cudaStreamEndCapture(c->stream, &out) == cudaSuccess;
+         }
+      }
+      if (ok) {
+         size_t nn = 1;
+         ok = cudaGraphGetNodes(g, &first, &nn) == cudaSuccess && nn == 1;
+      }
+      cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+      if (ok) {
+         np.conditional.handle = h;
+         np.conditional.type = cudaGraphCondTypeIf;
+         np.conditional.size = 1;
+         ok = cudaGraphAddNode(&cnode, g, &first, 1, &np) == cudaSuccess;
+      }
+      if (ok)
+         ok = cudaStreamBeginCaptureToGraph(c->stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+      if (ok) {
+         c->cond_outer = g;
+         c->capturing = 1;
+         G.conditional = 1;
+         return true;
+      }
+      (void)cudaGetLastError();
+      if (g)
+         cudaGraphDestroy(g);
+      if (trace_graphs())
+         fprintf(stderr, "[apx] conditional graph nodes unavailable: plain graph for 0x%x\n", key);
+   }
    c->capturing = 1;
    CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
    return true;
@@ -450,6 +502,10 @@ void apx_graph_end(apx_ctx* c, int key)
       APX_THROW(std::string("step graph capture failed: ") + cudaGetErrorString(e));
    apx_ctx::StepGraph& G = c->step_graphs[key];
    G.launches = c->stats.kernel_launches - c->graph_launches_before;
+   if (c->cond_outer) {      // `graph` is the body of the IF node: the outer graph is what gets instantiated
+      graph = c->cond_outer;
+      c->cond_outer = nullptr;
+   }
    CUDA_CHECK(cudaGraphInstantiate(&G.exec, graph, 0));
    cudaGraphDestroy(graph);
    CUDA_CHECK(cudaGraphLaunch(G.exec, c->stream));      // the captured work has not run yet
@@ -490,29 +546,39 @@ static void induce_epilogue(apx_ctx* c, int used, bool predict)
 
 // defer = true (energy(), mplar.cu): when the iterations run as the device-side loop nothing here waits for the GPU -- the caller
 // enqueues what follows the solve, synchronises once, and then calls apx_induce_finish.  Returns true when a finish is pending.
-bool apx_induce_impl(apx_ctx* c, bool defer)
+static bool induce_core(apx_ctx* c, int mode);
+bool apx_induce_impl(apx_ctx* c, bool defer) { return induce_core(c, defer ? 1 : 0); }
+// the deferred first batch did not converge (apx_induce_finish returned false): more iterations, in batches the host waits for
+void apx_induce_resume(apx_ctx* c) { (void)induce_core(c, 2); }
+
+// mode 0: solve and wait.  1: deferred (see above).  2: resume after an unconverged deferred batch -- no prologue
+static bool induce_core(apx_ctx* c, int mode)
 {
+   const bool defer = mode == 1, resume = mode == 2;
    const int n = c->n, n3 = 3 * n;
    const int a0 = c->a0, no = c->a1 - c->a0;      // owned range: every per-atom pass below runs on it
    const int g1 = (no + 255) / 256;
    const bool dist = c->dist.on != 0;
    cudaStream_t st = c->stream;
    const bool ewald = c->opt.use_ewald != 0;
-   if (!c->mpole_inited)
-      apx_rotpole(c);
-   if (c->uf_ev.empty()) {
-      c->uf_ev.resize(64);
-      for (auto& e : c->uf_ev)
-         CUDA_CHECK(cudaEventCreate(&e));
+   if (!resume) {
+      if (!c->mpole_inited)
+         apx_rotpole(c);
+      if (c->uf_ev.empty()) {
+         c->uf_ev.resize(64);
+         for (auto& e : c->uf_ev)
+            CUDA_CHECK(cudaEventCreate(&e));
+      }
+      c->uf_used = 0;
+      c->tl_valid = 0, c->tl_p_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence
+                                               // (and with it the captured graphs) does not depend on what ran before
+      cudaEventRecord(c->ev0, st);
+      c->stats.pcg_iterations = 0;
+      c->induced_valid = 1;
    }
-   c->uf_used = 0;
-   c->tl_valid = 0, c->tl_p_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence (and with it
-                         // the captured graphs) does not depend on what ran before
-   cudaEventRecord(c->ev0, st);
-   const bool predict = c->maxualt > 0 && c->nualt >= c->maxualt;   // the predictor replaces the direct guess once its ring is full
-   c->stats.pcg_iterations = 0;
-   c->induced_valid = 1;
-   if (!c->opt.poltyp_mutual) {
+   // the predictor replaces the direct guess once its ring is full
+   const bool predict = resume ? c->induce_pending_predict != 0 : (c->maxualt > 0 && c->nualt >= c->maxualt);
+   if (!resume && !c->opt.poltyp_mutual) {
       // DIRECT polarization: u = alpha E
       (void)n3;
       apx_dfield_full(c, true);
@@ -532,7 +598,7 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    // sequence unless the predictor supplies this step's coefficients by value
    const bool graphable = !predict;
    const int gkey = 0x2000 | (c->opt.pcgguess ? 1 : 0);
-   if (!graphable || apx_graph_begin(c, gkey)) {
+   if (!resume && (!graphable || apx_graph_begin(c, gkey))) {
       apx_dfield_full(c, true);
       CUDA_CHECK(cudaMemsetAsync(c->arena_p.p, 0, c->arena_p_bytes, st));      // scal + flags
       // the predictor replaces the direct guess once its ring is full (pcg.cu:26-31)
@@ -581,20 +647,20 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
       if (graphable)
          apx_graph_end(c, gkey);
    }
-   if (ewald)
+   if (ewald && !resume)
       c->mpole_pme_valid = 1;
    // the prologue applied the operator (and with it built the pair tensors) whether it ran eagerly or as a replayed graph:
    // the host flag must say so, or the capture of the first iteration would bake a second build into its graph
    if (apx_tlist_usable(c))
       c->tl_valid = 1, c->tl_p_valid = c->tl_P.p ? 1 : 0;      // (written by the permanent-field rows of the prologue, field.cu)
-   if (c->vdw_fork_vers >= 0) {
+   if (c->vdw_fork_vers >= 0 && !resume) {
       // energy() asked for the vdW term to start here: beside the iterations, whose short dependent kernels leave the SMs idle
       apx_vdw_launch(c, c->vdw_fork_vers);
       c->vdw_fork_vers = -1;
    }
-   if (graphable && c->use_graph && !dist && (c->opt.pcgguess) && c->uf_used == 0)
+   if (!resume && graphable && c->use_graph && !dist && (c->opt.pcgguess) && c->uf_used == 0)
       c->uf_used = 2;      // the r0 operator launch inside the graph was timed through external event nodes
-   int iter = 0;
+   int iter = resume ? c->induce_iter_launched : 0;
    bool done = false;
    c->skip = c->flags.p;
    int batch = std::max(1, std::min(c->last_iters, politer));
@@ -639,7 +705,7 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    // no batch sizes to guess, no launches after convergence, no graph per (first iteration, batch length), and the host does
    // not have to look at the convergence flag before it enqueues what follows.  First solve of a context: host-driven and
    // eager (plans, scratch buffers), like every other graph region.
-   bool use_loop = c->use_graph && c->use_loop && !dist;
+   bool use_loop = c->use_graph && c->use_loop && !dist && !resume;
    if (use_loop && !c->loop_exec && c->loop_warm) {
       if (trace_graphs())
          fprintf(stderr, "[apx] capturing the pcg loop body\n");
@@ -699,15 +765,17 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
    // steps whenever the iteration count moved (profiles/r02g: steps 5-6 of the timed window).  The first batch has the
    // largest iteration count seen recently (c->pcg_n); kernels of iterations past convergence return at once.  With defer
    // the host does not wait for that batch: the caller enqueues the energy epilogue behind it and synchronises once.
-   const bool generic = c->use_graph && !dist && !use_loop && c->loop_warm;
+   const bool generic = resume || (c->use_graph && !dist && !use_loop && c->loop_warm);
    c->loop_warm = 1;
-   if (generic) {
+   if (resume)
+      batch = 2;
+   else if (generic) {
       batch = std::max(1, std::min(c->pcg_n > 0 ? c->pcg_n : c->last_iters, politer));
       static const int forced = getenv("APX_PCG_FIRST_BATCH") ? atoi(getenv("APX_PCG_FIRST_BATCH")) : 0;      // tests: force the retry path
       if (forced > 0)
          batch = std::min(forced, politer);
    }
-   bool first_batch = true;
+   bool first_batch = !resume;
    while (!done) {
       int nit = std::min(batch, politer - iter);
       if (generic) {
@@ -744,6 +812,7 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
                find_or_capture(nit + 1);
             if (nit > 1)
                find_or_capture(nit - 1);
+            find_or_capture(2);      // (the continuation batches of a solve that outgrows its first batch)
          }
          apx_ctx::PcgGraph* G = find_or_capture(nit);
          CUDA_CHECK(cudaGraphLaunch(G->exec, st));
@@ -760,6 +829,7 @@ bool apx_induce_impl(apx_ctx* c, bool defer)
          c->skip = nullptr;
          c->induce_pending = 2;
          c->induce_pending_predict = predict ? 1 : 0;
+         c->induce_iter_launched = iter;
          return true;
       }
       first_batch = false;
@@ -780,10 +850,8 @@ bool apx_induce_finish(apx_ctx* c)
       return true;
    const int kind = c->induce_pending;
    c->induce_pending = 0;
-   if (kind == 2 && c->flags_h[1] == 0) {
-      c->pcg_n += 1;
-      return false;
-   }
+   if (kind == 2 && c->flags_h[1] == 0)
+      return false;      // (apx_induce_resume carries on; its bookkeeping raises pcg_n)
    const int used = c->flags_h[2] > 0 ? c->flags_h[2] : c->opt.politer;
    if (kind == 1)
       c->stats.kernel_launches += c->loop_launches * used;
