@@ -847,12 +847,21 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    A.ebuf = c->ebuf;
    A.cnt = c->cnt;
    A.cnt2 = c->cnt.p + 1;
+   // The real-space rows (100 us at dhfr2) on the second stream, beside the reciprocal-space part of the epilogue (PME round
+   // trip of the converged dipoles + the per-atom reciprocal kernels, 60 us): every accumulator they share is fixed-point or
+   // double atomics, so the two branches commute.  They join before the torques are resolved.
+   const bool fork_rows = ewald && !dist;
+   cudaStream_t rs = fork_rows ? c->stream2 : st;
+   if (fork_rows) {
+      CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+      CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+   }
    if (c->rows.nverlet > 0 && (do_m || do_p) && (do_g || do_e) && !(c->diag_skip & 1)) {
       int grid = rows_grid<MP_G>(c);
-      if (do_g && ewald) k_mplar_rows<true, true, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
-      else if (do_g) k_mplar_rows<true, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
-      else if (ewald) k_mplar_rows<false, true, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
-      else k_mplar_rows<false, false, MP_G><<<grid, ROWS_BLOCK, 0, st>>>(A);
+      if (do_g && ewald) k_mplar_rows<true, true, MP_G><<<grid, ROWS_BLOCK, 0, rs>>>(A);
+      else if (do_g) k_mplar_rows<true, false, MP_G><<<grid, ROWS_BLOCK, 0, rs>>>(A);
+      else if (ewald) k_mplar_rows<false, true, MP_G><<<grid, ROWS_BLOCK, 0, rs>>>(A);
+      else k_mplar_rows<false, false, MP_G><<<grid, ROWS_BLOCK, 0, rs>>>(A);
       APX_COUNT_LAUNCH(c);
       if (c->nexcl > 0) {
          ListedD D;
@@ -861,11 +870,13 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
          D.xyz = c->xyz_d, D.perm = c->perm, D.sc = c->excl_sc_d;
          D.cut2 = c->opt.cutoff * c->opt.cutoff, D.aewald = c->opt.aewald, D.f = c->opt.electric / c->opt.dielec;
          int g = (c->nexcl + 127) / 128;
-         if (do_g) k_mplar_listed<true><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A, D);
-         else k_mplar_listed<false><<<g, 128, 0, st>>>(c->nexcl, c->excl_s, A, D);
+         if (do_g) k_mplar_listed<true><<<g, 128, 0, rs>>>(c->nexcl, c->excl_s, A, D);
+         else k_mplar_listed<false><<<g, 128, 0, rs>>>(c->nexcl, c->excl_s, A, D);
          APX_COUNT_LAUNCH(c);
       }
    }
+   if (fork_rows)
+      CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
    // ---- reciprocal space + self
    if (ewald) {
       RecipX X = make_recipx(c);
@@ -901,6 +912,8 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
          }
       }
    }
+   if (fork_rows)
+      CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_join, 0));
    if (do_p && do_e && !pair_ep) {
       k_ep_dot<<<std::max(1, (n3 + 255) / 256), 256, 0, st>>>(n3, c->f_elec, c->tpj + a0, c->uind + 3 * (size_t)a0, c->udirp + 3 * (size_t)a0,
          c->dbuf);

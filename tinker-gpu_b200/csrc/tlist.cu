@@ -182,7 +182,11 @@ void apx_ufield_tlist(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    // wait for it to drain (profiles/r02g_trace_md.txt: the forward FFT started 8 us late and ran at a third of its speed)
    // (large systems are bandwidth bound in every kernel: there the operator wants all the bytes in flight it can get)
    static const int ctas_env = getenv("APX_TL_CTAS") ? std::max(1, atoi(getenv("APX_TL_CTAS"))) : 0;
-   const int ctas = ctas_env ? ctas_env : (c->n >= 200000 ? 16 : 6);
+   // Decomposed runs: NO cap -- a capped grid is a persistent one (every CTA strides over atoms until the kernel ends), and
+   // the exchange kernels and FFTs of the main stream then wait for the whole operator although their stream has priority
+   // (profiles/r02m_trace_water1m_n2.txt: 326 us of operator in front of a 600 us PME chain that is mostly NVLink traffic).
+   // Short-lived CTAs hand their SM slots to the higher-priority work as they retire.
+   const int ctas = ctas_env ? ctas_env : (c->dist.on ? (1 << 20) : (c->n >= 200000 ? 16 : 6));
 #define LAUNCH_TL(G_, M_)                                                                                                 \
    k_ufield_tl<G_, 4, M_><<<rows_grid<G_>(c, ctas), ROWS_BLOCK, 0, st>>>(c->a0, c->a1, L.vstart, L.cnt, L.nbr, c->tl_T, U, F, c->skip, 0u)
    switch (mode & 3) {
