@@ -118,13 +118,13 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def load_ncu_traffic(kernel_prefix):
+def load_ncu_traffic(kernel_prefix, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this same command (profiles/*_ncu_full.json; cold-cache replays)."""
+    `ncu --set full` capture of this same command (profiles/*<workload>_ncu_full.json; cold-cache replays)."""
     best = None
     pdir = os.path.join(ROOT, "profiles")
     for fn in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
-        if fn.endswith("_ncu_full.json"):
+        if fn.endswith(f"{workload}_ncu_full.json"):
             d = json.load(open(os.path.join(pdir, fn)))
             for k, v in d.items():
                 if k.startswith(kernel_prefix):
@@ -141,6 +141,11 @@ def load_peaks():
 
 
 # ------------------------------------------------------------------------------------------------
+# host threads of the CPU legs: the pair sweeps of the reference's operators are cut into that many slices (oracle/ref_oracle.py);
+# the reference's own host build runs them serially (OpenACC pragmas without an accelerator), so this is an upper bound of it
+CPU_THREADS = max(1, min(64, os.cpu_count() or 1))
+
+
 def cpu_oracle_sample(system, full=False):
     """Time the CPU path on one core.  With oracle/_ref present (the reference's own pair functions and PME translation unit
     compiled in place) the WHOLE electrostatics step -- induce() to polar-eps, real-space and reciprocal energy and gradient,
@@ -151,7 +156,7 @@ def cpu_oracle_sample(system, full=False):
     from oracle.amoeba_ref import Oracle, V4
     if all(ref_bridge.available(k) for k in ("realspace", "pme")) and not full:
         from oracle.ref_oracle import RefOracle
-        o = RefOracle(system)
+        o = RefOracle(system, threads=CPU_THREADS)
         o.pairs(system.ewald_cutoff)                 # neighbour search (scipy cKDTree) outside the timed region, like the GPU list
         o.pairs(system.usolve_cutoff)
         t0 = time.perf_counter()
@@ -163,7 +168,7 @@ def cpu_oracle_sample(system, full=False):
         o.empole_recip(V4)
         o.epolar_recip_self(V4)
         t_rest = time.perf_counter() - t0
-        desc = (f"reference operators on one core (oracle/_ref: include/seq pair_mpole/pair_polar/pair_dfield/pair_ufield and "
+        desc = (f"reference operators, pair sweeps on {CPU_THREADS} host threads (PME operators and the numpy FFT on one) (oracle/_ref: include/seq pair_mpole/pair_polar/pair_dfield/pair_ufield and "
                 f"src/acc/pme.cpp compiled in place, g++ -O2, double) driven by the oracle's PCG loop, numpy FFT: full induce() "
                 f"({o.niter} iterations) + real-space and reciprocal energy/gradient over all {o.pairs(system.ewald_cutoff)[0].shape[0]} pairs")
         return 1e3 * (t_ind + t_rest), 1e3 * t_ind, desc, "reference"
@@ -192,23 +197,42 @@ def cpu_oracle_sample(system, full=False):
 
 
 def roofline_block(uf_flops, uf_bytes, uf_ms, fp32_peak, hbm_peak, peak_src, sm_clk, npairs, traffic):
-    """The dominant kernel is the real-space CG operator, a pair kernel: SURVEY 8(d) assigns pair kernels to the FP32 CUDA-core
-    roofline (148 SMs x 128 lanes x 2 x f_SM; no dense contraction, so not the tensor peak).  `achieved` = ALGORITHMIC flops (130
-    per pair inside the cutoff, each pair counted once although the directed rows evaluate it from both ends) / device time
-    of the launch.  The HBM view of the same launch is the side key: the working set of dhfr2 is L2-resident."""
+    """The dominant kernel is the real-space CG operator.  Round 2 turned it from a pair kernel that recomputed the pair geometry
+    in every application (FP32-bound by SURVEY 8(d)'s assignment; 6-13 % of that roofline, issue-bound) into a stored-tensor
+    sparse matrix-vector product (csrc/tlist.cu): per directed pair it STREAMS 16 B of tensor + 4 B of index and gathers a
+    32-byte dipole pair -- a bandwidth-bound kernel, so the roofline is the measured HBM copy bandwidth.  `achieved` =
+    ALGORITHMIC bytes (20 B per directed pair, both directions stored, + 72 B per atom of vectors and row offsets; the gathers
+    are not counted, they hit L1 / L2) / device time of the launch, timed IN SITU, i.e. beside the PME spread of the other
+    stream.  At dhfr2 the whole stream (66 MB) is L2-resident between applications, so there the fraction is of a roofline the
+    kernel does not touch; the 1 M-atom box (BASELINE configs[3]; ncu: 3.24 GB of DRAM traffic per launch) is where it is one.
+    The FP32 view SURVEY 8(d) prescribes for pair kernels is kept as a side key for comparison with round 1."""
     tf = uf_flops / (uf_ms * 1e-3) / 1e12 if uf_ms > 0 else 0.0
     gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
-    return {"kernel": "real-space CG operator (field.cu: ufield rows / staged blocks, 1 launch per PCG iteration)", "bound": "fp32",
-            "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak if fp32_peak else 0.0,
-            "traffic": traffic[0] if traffic else None,
-            "traffic_source": ("profiles/" + traffic[1] + " (ncu --set full, cold-cache replay)") if traffic else None,
-            "flop_per_pair": 130, "pairs": int(npairs), "directed_pairs_evaluated": int(2 * npairs), "ms_per_launch": uf_ms,
-            "ms_per_launch_source": "CUDA events around the operator launches of the timed steps (external event nodes inside the graph)",
-            "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_clk:.0f} MHz (SM clock sampled during the timed region; "
-                           f"MEASURED_PEAKS.json {peak_src})",
-            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else 0.0,
-                    "algorithmic_bytes": uf_bytes,
-                    "note": "algorithmic bytes / launch time against the measured copy bandwidth; not what bounds this kernel"}}
+    tl = os.environ.get("APX_TLIST", "1") != "0"
+    hbm = {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else 0.0, "algorithmic_bytes": uf_bytes}
+    fp32 = {"achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf / fp32_peak if fp32_peak else 0.0, "flop_per_pair": 130,
+            "note": "130 flop per pair inside the cutoff (SURVEY 8d, the recomputing pair kernel) / launch time: the work the stored "
+                    "tensors avoid is still counted, for comparison with round 1 (0.064)",
+            "peak_source": f"148 SMs x 128 FP32 lanes x 2 flop x {sm_clk:.0f} MHz (SM clock sampled during the timed region)"}
+    common = {"kernel": "real-space CG operator (csrc/tlist.cu: k_ufield_tl, stored pair tensors; 1 launch per PCG iteration)" if tl
+                        else "real-space CG operator (csrc/field.cu: k_ufield_rows_rec, pair geometry recomputed; APX_TLIST=0)",
+              "traffic": traffic[0] if traffic else None,
+              "traffic_source": ("profiles/" + traffic[1] + " (ncu --set full, cold-cache replay)") if traffic else None,
+              "pairs": int(npairs), "directed_pairs": int(2 * npairs), "ms_per_launch": uf_ms,
+              "ms_per_launch_source": "CUDA events around the operator launch of the second PCG iteration of every timed step (external "
+                                      "event nodes inside the iteration-batch graph): in situ, beside the PME spread of the main stream",
+              "peak_source": f"MEASURED_PEAKS.json ({peak_src})"}
+    if tl:
+        return dict(common, bound="hbm", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=hbm["frac"], algorithmic_bytes=uf_bytes, fp32=fp32)
+    return dict(common, bound="fp32", achieved=tf, peak=fp32_peak, unit="TFLOP/s", frac=fp32["frac"], hbm=hbm)
+
+
+def operator_bytes(n, npairs):
+    """Algorithmic bytes of one application of the real-space operator: 16 B tensor + 4 B index per directed pair (stored-tensor
+    form; the recomputing form reads 4 B index + a 48 B record it gathers), 32 B in + 32 B out + 8 B of row offsets per atom."""
+    if os.environ.get("APX_TLIST", "1") != "0":
+        return (16 + 4) * 2 * npairs + (32 + 32 + 8) * n
+    return (16 + 16 + 24 + 48) * n + 4 * 2 * npairs
 
 
 MD_METRIC = "ns/day & ms/induce() AMOEBA DHFR 23.5k atoms (dynamic, 2 fs RESPA, NVT)"
@@ -384,7 +408,7 @@ def run_reference_dynamics(args, rank, world):
         "config": {"workload": MD_WORKLOAD, "steps_requested": args.steps, "warmup_requested": args.warmup, "cap": cap,
                    "note": "CPU arm: the reference executable needs gfortran (absent); its own operators compiled in place (oracle/_ref) -- or, "
                            "without them, the oracle ports -- are timed instead, one core"},
-        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": 1, "kind": kind, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": CPU_THREADS if kind == "reference" else 1, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
@@ -541,11 +565,11 @@ def run_dynamics(args, rank, world, local_rank):
         hbm_peak, sm_max, peak_src = load_peaks()
         npairs = max(1, st["npairs_m"])
         uf_ms = float(np.mean(ms_uf)) if ms_uf else 0.0
-        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 2 * npairs
+        uf_bytes = operator_bytes(n, npairs)
         uf_flops = 130.0 * npairs
         achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max
-        traffic = load_ncu_traffic("k_ufield_rows")
+        traffic = load_ncu_traffic("k_ufield_tl", "dhfr2")
         fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         line = {
             "metric": MD_METRIC, "value": ns_per_day(ms_step, world), "unit": "ns/day", "n_gpus": world, "steps": args.steps,
@@ -585,7 +609,7 @@ def run_dynamics(args, rank, world, local_rank):
         }
         if not args.no_cpu:
             ms_cpu, ms_cpu_ind, desc, kind = cpu_dynamics_sample(system)
-            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": kind, "sample": desc,
+            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": CPU_THREADS if kind == "reference" else 1, "kind": kind, "sample": desc,
                                     "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
                                     "note": "the reference EXECUTABLE cannot be linked here (no Fortran compiler); kind 'reference' = its own "
                                             "pair functions and PME translation unit compiled in place and run serially, as its host build "
@@ -743,7 +767,7 @@ def run_reference(args, rank, world):
         "warmup": warm, "ms_per_step": ms_step, "ms_per_induce": float(np.mean(ms_ind)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "reference input deck example/dhfr2 (blob tests/golden/dhfr2.npz)",
         "config": {"workload": WORKLOAD, "steps_requested": args.steps, "warmup_requested": args.warmup, "cap": cap, "note": "CPU arm: the reference executable needs gfortran (absent); its operators compiled in place (oracle/_ref) or the oracle port are timed instead"},
-        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": 1, "kind": kind, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "ns/day", "cores": CPU_THREADS if kind == "reference" else 1, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": "ns/day", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -872,11 +896,11 @@ def run_ours(args, rank, world, local_rank):
         uf_ms = float(np.mean(ms_uf)) if ms_uf else 0.0
         # real-space ufield row kernel: algorithmic bytes = read (pos,pdamp,thole,ud,up) + rmw (field d,p) per atom
         # + one 4-byte neighbor index per directed pair
-        uf_bytes = (16 + 16 + 24 + 48) * n + 4 * 2 * npairs
+        uf_bytes = operator_bytes(n, npairs)
         uf_flops = 130.0 * npairs
         achieved_gbs = uf_bytes / (uf_ms * 1e-3) / 1e9 if uf_ms > 0 else 0.0
         sm_clk = (clocks or {}).get("sm_mhz") or sm_max
-        traffic = load_ncu_traffic("k_ufield_rows") if args.workload == "dhfr2" else None
+        traffic = load_ncu_traffic("k_ufield_tl", args.workload)
         fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         wl_desc = WORKLOADS[args.workload][4]
         metric = METRIC if args.workload == "dhfr2" else METRIC.replace("AMOEBA DHFR 23.5k atoms", wl_desc.split(",")[0])
@@ -910,7 +934,7 @@ def run_ours(args, rank, world, local_rank):
                            "cutoff": float(system.vdw.cutoff), "note": "ehal runs on its own stream beside induce()"}
         if not args.no_cpu and args.workload == "dhfr2":
             ms_cpu, ms_cpu_ind, desc, kind = cpu_oracle_sample(system)
-            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": 1, "kind": kind, "sample": desc,
+            line["cpu_baseline"] = {"value": ns_per_day(ms_cpu), "unit": "ns/day", "cores": CPU_THREADS if kind == "reference" else 1, "kind": kind, "sample": desc,
                                     "ms_per_step": ms_cpu, "ms_per_induce": ms_cpu_ind,
                                     "note": "vectorised-numpy port on one core, about two orders of magnitude slower than the reference's "
                                             "compiled host build would be (it cannot be linked here: no Fortran compiler); reported, not a target"}

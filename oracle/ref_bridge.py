@@ -33,9 +33,12 @@ def valence(system):
     return dict(energy=e8, grad=g, virial=v9.reshape(3, 3))
 
 
-def realspace(oracle, ud=None, up=None):
+def realspace(oracle, ud=None, up=None, threads=1):
     """Real-space multipole / polarization energies, gradients, torques and the d/p permanent and mutual fields from the
-    reference's pair_mpole / pair_polar / pair_dfield / pair_ufield over the oracle's own pair list and scale factors."""
+    reference's pair_mpole / pair_polar / pair_dfield / pair_ufield over the oracle's own pair list and scale factors.
+    threads > 1 (bench.py's CPU legs): the pair list in contiguous slices on that many host threads, sums added; the pairwise
+    virial (a process-global accumulator in the shim) is then not collected."""
+    from concurrent.futures import ThreadPoolExecutor
     lib = C.CDLL(os.path.join(HERE, "_ref", "libref_realspace.so"))
     lib.ref_realspace_eval.argtypes = [C.c_int, C.c_longlong, _IP, _IP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, C.c_double, C.c_double,
                                        C.c_int, _DP, _DP] + [_DP] * 8
@@ -48,24 +51,42 @@ def realspace(oracle, ud=None, up=None):
     i32, k32 = np.ascontiguousarray(i, np.int32), np.ascontiguousarray(k, np.int32)
     R = np.ascontiguousarray(R, np.float64)
     pd = np.ascontiguousarray(s.pdamp, np.float64)
-    em, ep = C.c_double(), C.c_double()
-    out = {nm: np.zeros((n, 3)) for nm in ("gm", "tm", "gp", "tp", "fd", "fp", "ufd", "ufp")}
+    names = ("gm", "tm", "gp", "tp", "fd", "fp", "ufd", "ufp")
     u1 = None if ud is None else np.ascontiguousarray(ud, np.float64)
     u2 = None if up is None else np.ascontiguousarray(up, np.float64)
     vm6, vp6 = np.zeros(6), np.zeros(6)
     lib.ref_realspace_virial.argtypes = [_DP, _DP]
     lib.ref_realspace_virial.restype = None
-    lib.ref_realspace_virial(_dp(vm6), _dp(vp6))
-    rc = lib.ref_realspace_eval(n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(R), _dp(sc), _dp(rp), _dp(pd), _dp(pga),
-                                None if u1 is None else _dp(u1), None if u2 is None else _dp(u2), float(oracle.f), float(s.aewald),
-                                int(bool(s.use_ewald)), C.byref(em), C.byref(ep), *[_dp(out[nm]) for nm in ("gm", "tm", "gp", "tp", "fd", "fp", "ufd", "ufp")])
-    lib.ref_realspace_virial(None, None)
-    if rc != 0:
-        raise RuntimeError(f"ref_realspace_eval failed ({rc})")
+
+    def sweep(lo, hi):
+        em, ep = C.c_double(), C.c_double()
+        o = {nm: np.zeros((n, 3)) for nm in names}
+        rc = lib.ref_realspace_eval(n, hi - lo, i32[lo:hi].ctypes.data_as(_IP), k32[lo:hi].ctypes.data_as(_IP), _dp(R[lo:hi]), _dp(sc[lo:hi]), _dp(rp),
+                                    _dp(pd), _dp(pga[lo:hi]), None if u1 is None else _dp(u1), None if u2 is None else _dp(u2), float(oracle.f),
+                                    float(s.aewald), int(bool(s.use_ewald)), C.byref(em), C.byref(ep), *[_dp(o[nm]) for nm in names])
+        if rc != 0:
+            raise RuntimeError(f"ref_realspace_eval failed ({rc})")
+        o.update(em=em.value, ep=ep.value)
+        return o
+
+    T = max(1, min(int(threads), len(i32) // 4096 or 1))
+    if T == 1:
+        lib.ref_realspace_virial(_dp(vm6), _dp(vp6))
+        out = sweep(0, len(i32))
+        lib.ref_realspace_virial(None, None)
+    else:
+        lib.ref_realspace_virial(None, None)
+        cuts = np.linspace(0, len(i32), T + 1).astype(int)
+        with ThreadPoolExecutor(T) as ex:
+            parts = list(ex.map(lambda t: sweep(int(cuts[t]), int(cuts[t + 1])), range(T)))
+        out = parts[0]
+        for q in parts[1:]:
+            for nm in names + ("em", "ep"):
+                out[nm] = out[nm] + q[nm]
 
     def sym(v):
         return np.array([[v[0], v[1], v[2]], [v[1], v[3], v[4]], [v[2], v[4], v[5]]])
-    out.update(em=em.value, ep=ep.value, npair=len(i32), vm=sym(vm6), vp=sym(vp6))
+    out.update(npair=len(i32), vm=sym(vm6), vp=sym(vp6))
     return out
 
 

@@ -11,6 +11,7 @@ CPU baseline bench.py times ("reference arithmetic, one core") -- about 20x fast
 """
 import ctypes as C
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -22,8 +23,9 @@ _IP = C.POINTER(C.c_int)
 
 
 class RefOracle(Oracle):
-    def __init__(self, system, chunk=20000):
+    def __init__(self, system, chunk=20000, threads=1):
         super().__init__(system, chunk)
+        self.threads = threads      # > 1: the pair sweeps run on that many host threads (bench.py's CPU legs only)
         self._rs = C.CDLL(os.path.join(ref_bridge.HERE, "_ref", "libref_realspace.so"))
         self._rs.ref_field_real.argtypes = [C.c_int, C.c_int, C.c_longlong, _IP, _IP, _DP, _DP, _DP, _DP, _DP, _DP, _DP, C.c_double, C.c_int,
                                             _DP, _DP]
@@ -56,9 +58,25 @@ class RefOracle(Oracle):
         dp = ref_bridge._dp
         u1 = None if ud is None else np.ascontiguousarray(ud, np.float64)
         u2 = None if up is None else np.ascontiguousarray(up, np.float64)
-        self._rs.ref_field_real(mode, self.n, len(i), i.ctypes.data_as(_IP), k.ctypes.data_as(_IP), dp(R), dp(sc), dp(rp), dp(pd), dp(pga),
-                                None if u1 is None else dp(u1), None if u2 is None else dp(u2), float(self.s.aewald), int(bool(self.s.use_ewald)),
-                                dp(fd), dp(fp))
+
+        def sweep(lo, hi, ofd, ofp):
+            self._rs.ref_field_real(mode, self.n, hi - lo, i[lo:hi].ctypes.data_as(_IP), k[lo:hi].ctypes.data_as(_IP), dp(R[lo:hi]), dp(sc[lo:hi]),
+                                    dp(rp), dp(pd), dp(pga[lo:hi]), None if u1 is None else dp(u1), None if u2 is None else dp(u2),
+                                    float(self.s.aewald), int(bool(self.s.use_ewald)), dp(ofd), dp(ofp))
+
+        T = max(1, min(int(self.threads), len(i) // 4096 or 1))
+        if T == 1:
+            sweep(0, len(i), fd, fp)
+            return fd, fp
+        # bench.py's CPU legs: the pair list cut into T contiguous slices, one host thread each (ctypes releases the GIL), partial
+        # fields summed -- the reference's host build runs this loop serially, so this is MORE than its CPU path can do
+        cuts = np.linspace(0, len(i), T + 1).astype(int)
+        parts = [(np.zeros((self.n, 3)), np.zeros((self.n, 3))) for _ in range(T)]
+        with ThreadPoolExecutor(T) as ex:
+            list(ex.map(lambda t: sweep(int(cuts[t]), int(cuts[t + 1]), parts[t][0], parts[t][1]), range(T)))
+        for a, b in parts:
+            fd += a
+            fp += b
         return fd, fp
 
     # ---- local frames (src/acc/amoeba/rotpole.cpp, torque.cpp)
@@ -136,7 +154,7 @@ class RefOracle(Oracle):
         return ref_bridge.recip_polar(self._rpme(), self.uind, self.uinp)
 
     def _real_space(self, vers, do_m, do_p):
-        r = ref_bridge.realspace(self, self.uind if do_p else None, self.uinp if do_p else None)
+        r = ref_bridge.realspace(self, self.uind if do_p else None, self.uinp if do_p else None, threads=self.threads)
         i, k, R, sc, pga, pd = self._pairs_c()
         return dict(em=r["em"] if do_m else 0.0, ep=r["ep"] if do_p else 0.0, nem=int((sc[:, 0] != 0).sum()), nep=int((sc[:, 2] != 0).sum()),
                     gm=r["gm"], gp=r["gp"], tm=r["tm"], tp=r["tp"], vm=r["vm"], vp=r["vp"])

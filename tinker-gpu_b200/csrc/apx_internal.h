@@ -340,7 +340,10 @@ struct apx_ctx {
    int use_loop = 0;               // APX_LOOP=1: the WHILE-node loop instead of generic iteration batches (same median step,
                                    // 3 % slower in batches of steps on this driver: profiles/r02j)
    int pcg_n = 0, pcg_n_slack = 0; // iterations in the first batch of a solve (largest count seen recently)
+   int uf_ext_iter = 0;            // capture of a batch: the operator launch being enqueued gets external timing events (slots 2,3)
+   int uf_iter_timed = 0;          // the batch graph launched by this solve carries them
    int vdw_fork_vers = -1;         // >= 0: energy() wants apx_induce_impl to fork the vdW stream after its prologue (mplar.cu)
+   int epend_deferred = 0;         // energy_once stage 1 -> 2: the solve of the pending evaluation was deferred
    int induce_iter_launched = 0;   // iterations enqueued by the deferred first batch
    int induce_pending = 0, induce_pending_predict = 0;      // a deferred solve awaits apx_induce_finish
    int use_graph = 1;
@@ -352,6 +355,7 @@ struct apx_ctx {
       int launches = 0, warm = 0;
       int conditional = 0;      // the region is the body of an IF node keyed on a device flag (apx_graph_begin with cond_flag)
    };
+   int cond_nodes_ok = -1;               // conditional graph nodes on this driver: -1 not tried yet, 1 work, 0 unavailable
    cudaGraph_t cond_outer = nullptr;     // graph under construction that owns the IF node whose body is being captured
    std::map<int, StepGraph> step_graphs;
    int graph_key_open = -1, graph_launches_before = 0;
@@ -507,3 +511,5 @@ void apx_ufield_full(apx_ctx* c, const real* ud, const real* up, real* fd, real*
 // ---- mplar.cu
 void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw = false, bool do_val = false);
 void apx_energy_impl_md(apx_ctx* c, int vers, apx_energy_result* out);      // slow level of the integrator: electrostatics + vdW
+void apx_energy_md_enqueue(apx_ctx* c, int vers);
+bool apx_energy_md_collect(apx_ctx* c, int vers, apx_energy_result* out);      // true: a solver-batch miss was repaired here

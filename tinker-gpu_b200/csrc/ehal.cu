@@ -103,7 +103,14 @@ __device__ __forceinline__ void r_sqrt_pair(real r2, real& r, real& rinv)
    rinv = 1.0 / r;
 }
 #else
-__device__ __forceinline__ real r_rcp(real x) { return __frcp_rn(x); }
+// 1/x for the two denominators of the 14-7 function (both > 0.0049): hardware reciprocal + one Newton step, without the special-case
+// paths of the correctly rounded __frcp_rn (8 instructions and a branch each, twice per listed pair)
+__device__ __forceinline__ real r_rcp(real x)
+{
+   real y;
+   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+   return fmaf(y, fmaf(-x, y, 1.0f), y);
+}
 // r enters the energy in the 7th power: the 2-ulp hardware rsqrt gets one Newton step (two FMAs)
 __device__ __forceinline__ void r_sqrt_pair(real r2, real& r, real& rinv)
 {

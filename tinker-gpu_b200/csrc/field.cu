@@ -501,11 +501,13 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
       apx_tlist_build(c, st);
    // device-time the dominant kernel: one event pair per launch, read back by induce()
    int slot = -1;
-   const bool ext = c->capturing && c->graph_key_open >= 0 && (c->graph_key_open & 0x2000) && c->uf_ev.size() >= 2;
+   const bool ext_iter = c->capturing && c->uf_ext_iter && c->uf_ev.size() >= 4;      // one iteration of a captured batch (pcg.cu): slots 2,3
+   const bool ext = ext_iter || (c->capturing && c->graph_key_open >= 0 && (c->graph_key_open & 0x2000) && c->uf_ev.size() >= 2);
    if (ext) {
-      // inside the captured prologue of induce(): external event nodes, so every replay times this launch (slots 0,1)
-      slot = 0;
-      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[0], st, cudaEventRecordExternal));
+      // inside the captured prologue of induce() (slots 0,1) or a captured iteration (slots 2,3): external event nodes, so
+      // every replay still times this launch
+      slot = ext_iter ? 2 : 0;
+      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[slot], st, cudaEventRecordExternal));
    } else if (!c->capturing && c->uf_used + 2 <= (int)c->uf_ev.size()) {
       slot = c->uf_used;
       c->uf_used += 2;
@@ -529,7 +531,7 @@ void apx_ufield_real_dp(apx_ctx* c, cudaStream_t st, const real4* U, real4* F)
    else if (tb) LAUNCH_UF(false, true);
    else LAUNCH_UF(false, false);
    if (slot >= 0 && ext)
-      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[1], st, cudaEventRecordExternal));
+      CUDA_CHECK(cudaEventRecordWithFlags(c->uf_ev[slot + 1], st, cudaEventRecordExternal));
    else if (slot >= 0)
       cudaEventRecord(c->uf_ev[slot + 1], st);
    APX_COUNT_LAUNCH(c);

@@ -123,10 +123,13 @@ struct Rng {
 
 // bussiThermostat (src/mdpt.cpp:41-71): c = exp(-dt/tau), d = (1-c)(T0/T)/nfree, scale^2 = c + (s + r^2) d + 2 r sqrt(c d)
 // with r ~ N(0,1), s ~ chi^2(nfree-1).  thermostat == 0: only the kinetic energy / temperature are published.
+// The step number that keys the random stream lives on the device (sc[6], advanced by the last CTA when `advance` is set): the
+// kernel can then sit in a captured graph, behind work the host has not waited for.
 __global__ void k_md_thermo(int n, int thermostat, int nfree, double dt, double tautemp, double kelvin, unsigned long long seed,
-   unsigned long long step, double* __restrict__ vel, double* __restrict__ sc)
+   int advance, double* __restrict__ vel, double* __restrict__ sc)
 {
    __shared__ double sh_scale;
+   const unsigned long long step = advance ? (unsigned long long)sc[6] + 1ull : 0ull;
    if (threadIdx.x == 0) {
       const double eksum = 0.5 * sc[0] / EKCAL;
       double temp = 2.0 * eksum / ((double)nfree * GASCONST);
@@ -157,6 +160,17 @@ __global__ void k_md_thermo(int n, int thermostat, int nfree, double dt, double 
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n && scale != 1.0) {
       vel[3 * (size_t)i] *= scale, vel[3 * (size_t)i + 1] *= scale, vel[3 * (size_t)i + 2] *= scale;
+   }
+   if (advance) {
+      // every CTA has read sc[6] before it takes its ticket
+      __syncthreads();
+      if (threadIdx.x == 0) {
+         const double t = atomicAdd(&sc[5], 1.0);
+         if (t == (double)(gridDim.x - 1)) {
+            sc[5] = 0;
+            sc[6] = (double)step;
+         }
+      }
    }
 }
 
@@ -240,7 +254,7 @@ void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const a
    cudaStream_t st = c->stream;
    // the step graphs bake dt / dt_a into their kick and drift nodes: a second init must not replay the old coefficients
    for (auto it = c->step_graphs.begin(); it != c->step_graphs.end();) {
-      if (it->first >= 0x3000 && it->first < 0x4000) {
+      if ((it->first >= 0x3000 && it->first < 0x4000) || (it->first >= 0x6000 && it->first < 0x7000)) {
          if (it->second.exec)
             cudaGraphExecDestroy(it->second.exec);
          it = c->step_graphs.erase(it);
@@ -257,7 +271,7 @@ void apx_md_init_impl(apx_ctx* c, const double* mass, const double* vel, const a
    md_kickoff_forces(c);
    // kinetic energy of the starting velocities
    md_kick(c, false, true, 0.0, 0.0, 0.0);
-   k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, 0, M.nfree, M.dt, 1.0, 1.0, M.seed, 0ull, M.vel, M.sc);
+   k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, 0, M.nfree, M.dt, 1.0, 1.0, M.seed, 0, M.vel, M.sc);
    APX_COUNT_LAUNCH(c);
    CUDA_CHECK(cudaStreamSynchronize(st));
    M.on = 1;
@@ -327,12 +341,33 @@ void apx_md_steps_impl(apx_ctx* c, int nsteps, apx_md_report* out)
       md_positions_changed(c, moved);                                       // copyPosToXyz(true): list check / rebuild
       if (val)
          apx_valence_fetch(c, st);
-      apx_energy_impl_md(c, APX_V4, &r);                                    // slow force: induce + emplar + ehal
+      // slow force (induce + emplar + ehal), closing half-kick, thermostat.  Once the graphs exist nothing between them waits
+      // for the GPU: the energy evaluation is only enqueued, the kick and the thermostat follow it as the body of an IF node
+      // keyed on the solver's convergence flag (like the energy epilogue, mplar.cu), ONE synchronisation ends the step.  A
+      // solver batch that was too short leaves both IF nodes idle; the collect step finishes the solve and the epilogue, and the
+      // tail is launched again.
+      const int tkey = 0x6000 + nr;
+      const int* cflag = (c->opt.use_polar && c->opt.poltyp_mutual) ? c->flags.p + 1 : nullptr;
+      auto tail = [&]() {
+         if (apx_graph_begin(c, tkey, cflag)) {
+            md_kick(c, false, true, 0.5 * dta, 0.5 * dt, 0.0);              // velR2 + sum m v^2
+            k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, M.thermostat, M.nfree, dt, M.tautemp > 0 ? M.tautemp : 1.0, M.kelvin, M.seed,
+               1, M.vel, M.sc);
+            APX_COUNT_LAUNCH(c);
+            apx_graph_end(c, tkey);
+         }
+      };
+      if (c->cond_nodes_ok == 1 && apx_graph_is_conditional(c, tkey)) {
+         apx_energy_md_enqueue(c, APX_V4);
+         tail();
+         CUDA_CHECK(cudaStreamSynchronize(st));
+         if (apx_energy_md_collect(c, APX_V4, &r))
+            tail();      // (its IF node did not fire behind the unconverged batch)
+      } else {
+         apx_energy_impl_md(c, APX_V4, &r);
+         tail();
+      }
       c->md_forces_valid = 1;
-      md_kick(c, false, true, 0.5 * dta, 0.5 * dt, 0.0);                    // velR2 + sum m v^2
-      k_md_thermo<<<(n + 255) / 256, 256, 0, st>>>(n, M.thermostat, M.nfree, dt, M.tautemp > 0 ? M.tautemp : 1.0, M.kelvin, M.seed,
-         M.step + 1, M.vel, M.sc);
-      APX_COUNT_LAUNCH(c);
       M.step++;
    }
    cudaEventRecord(M.t1, st);

@@ -729,7 +729,10 @@ void apx_dfield_full(apx_ctx* c, bool want_ev);
 void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6);
 void apx_unpack_dp_all(apx_ctx* c, const real4* in, real* d, real* p);
 
-static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer);
+// stage 0: the whole evaluation.  1: enqueue everything up to the copy of the reduced scalars, do not wait (md.cu puts the closing
+// kick and the thermostat behind it before it synchronises).  2: the rest of a stage-1 call, after the caller's synchronisation.
+static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer,
+   int stage = 0);
 
 // energy(vers) of the electrostatic terms (+ vdW / valence when attached).  The first attempt never waits for the GPU between
 // the solver and the energy epilogue (the solver's first batch of iterations is sized from recent solves); should that batch
@@ -743,7 +746,8 @@ void apx_energy_impl(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_resu
    }
 }
 
-static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer)
+static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_result* out, bool do_vdw, bool do_val, bool defer,
+   int stage)
 {
    const int n = c->n;
    const int a0 = c->a0, no = c->a1 - c->a0, n3 = 3 * no;      // per-atom passes run on the owned range
@@ -754,6 +758,11 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    do_p = do_p && c->opt.use_polar;
    const bool ewald = c->opt.use_ewald != 0;
    const bool pair_ep = do_e && do_a;          // ANALYZE: pairwise polarization energy; otherwise dot product
+   do_vdw = do_vdw && c->vdw.on;
+   do_val = do_val && apx_valence_on(c);
+   int iters = 0;
+   bool induce_deferred = false;
+   if (stage != 2) {
    c->md_forces_valid = 0;                     // the accumulators are rewritten (md.cu sets the flag again after its own calls)
    cudaEventRecord(c->ev2, st);
    if (apx_graph_begin(c, 0x1000)) {
@@ -769,7 +778,6 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    // APX_VDW_AT: where the vdW stream forks from the main stream.  0 = here, beside the solver's prologue (permanent field:
    // throughput-bound kernels that the vdW rows slow down); 1 = after the prologue, beside the PCG iterations (latency-bound
    // chains that leave most of every SM idle); 2 = after the solver, beside the energy epilogue
-   do_vdw = do_vdw && c->vdw.on;
    static const int vdw_at = getenv("APX_VDW_AT") ? atoi(getenv("APX_VDW_AT")) : 0;      // measured on dhfr2 MD: 1.20 / 1.25 / 1.29 ms per step for 0 / 1 / 2
    c->vdw_fork_vers = -1;
    if (do_vdw && (vdw_at == 0 || !do_p || c->dist.on))
@@ -777,14 +785,11 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    else if (do_vdw && vdw_at == 1)
       c->vdw_fork_vers = vers;      // apx_induce_impl forks it between its prologue and its iterations
    // ---- valence terms, likewise (evalence.cu)
-   do_val = do_val && apx_valence_on(c);
    if (do_val)
       apx_valence_launch(c, vers);
    // ---- induced dipoles (also runs the permanent PME round trip -> fmp, fphi, conv E/virial)
    // (with the device-side loop the solve is only enqueued here: nothing waits for the convergence flag, the epilogue below is
    //  enqueued behind it, and the solver's host-side bookkeeping runs after the one synchronisation of this function)
-   int iters = 0;
-   bool induce_deferred = false;
    if (do_p) {
       induce_deferred = apx_induce_impl(c, defer);
       iters = c->stats.pcg_iterations;
@@ -804,6 +809,10 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
       apx_unpack_dp_all(c, c->pk_p, c->uind, c->uinp);
    }
    // ---- real space, reciprocal space, torques: one fixed launch sequence per (vers, terms) -> one CUDA graph
+   } else {
+      induce_deferred = c->epend_deferred != 0;
+      iters = c->stats.pcg_iterations;
+   }
    // Behind a deferred solve the region is the body of an IF node keyed on the solver's convergence flag: should the first batch
    // of iterations not have converged, nothing of it runs, the accumulators keep what the vdW / valence terms put there, and
    // the region is simply launched again once the remaining iterations are done (below).
@@ -928,6 +937,8 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    apx_graph_end(c, ekey);
    }
    };
+   const size_t tail = (size_t)((char*)(c->cnt.p + 4) - (char*)c->ebuf.p);
+   if (stage != 2) {
    epilogue();
    if (do_vdw)
       apx_vdw_join(c);
@@ -944,9 +955,12 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    }
    // ---- reductions to the host (energy.cpp:334-384)
    // ebuf, dbuf and cnt sit back to back at the end of the accumulator arena: ONE copy into pinned memory
-   const size_t tail = (size_t)((char*)(c->cnt.p + 4) - (char*)c->ebuf.p);
    CUDA_CHECK(cudaMemcpyAsync(c->red_h, c->ebuf.p, tail, cudaMemcpyDeviceToHost, st));
    cudaEventRecord(c->ev3, st);
+   c->epend_deferred = induce_deferred ? 1 : 0;
+   }
+   if (stage == 1)
+      return true;
    CUDA_CHECK(cudaStreamSynchronize(st));
    if (induce_deferred) {
       if (!apx_induce_finish(c)) {      // iteration count, timings, predictor history, the not-converged error
@@ -1028,6 +1042,25 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
 void apx_energy_impl_md(apx_ctx* c, int vers, apx_energy_result* out)
 {
    apx_energy_impl(c, vers, true, true, out, true, false);
+}
+
+// The same evaluation in two halves for the integrator (md.cu): everything enqueued, nothing awaited; then, after the caller has
+// put its own work behind it and synchronised, the host-side rest.  The second half returns true when the solver's first batch
+// had not converged and the iterations / the epilogue had to be finished there (the caller's conditional work did not run).
+void apx_energy_md_enqueue(apx_ctx* c, int vers)
+{
+   (void)energy_once(c, vers, true, true, nullptr, true, false, true, 1);
+}
+bool apx_energy_md_collect(apx_ctx* c, int vers, apx_energy_result* out)
+{
+   const int misses = c->stats.energy_retries;
+   if (!energy_once(c, vers, true, true, out, true, false, true, 2)) {
+      // (only without conditional graph nodes: the epilogue ran on unconverged dipoles -- evaluate again, waiting for the solver)
+      if (!energy_once(c, vers, true, true, out, true, false, false, 0))
+         APX_THROW("energy: the induced-dipole solver did not finish");
+      return true;
+   }
+   return c->stats.energy_retries != misses;
 }
 
 void apx_grad_to_caller(apx_ctx* c, double* dev_out)

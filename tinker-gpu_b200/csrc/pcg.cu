@@ -477,8 +477,10 @@ bool apx_graph_begin(apx_ctx* c, int key, const int* cond_flag)
          c->cond_outer = g;
          c->capturing = 1;
          G.conditional = 1;
+         c->cond_nodes_ok = 1;
          return true;
       }
+      c->cond_nodes_ok = 0;
       (void)cudaGetLastError();
       if (g)
          cudaGraphDestroy(g);
@@ -514,7 +516,13 @@ void apx_graph_end(apx_ctx* c, int key)
 static void upred_save(apx_ctx* c);
 static void induce_epilogue(apx_ctx* c, int used, bool predict)
 {
-   {
+   if (c->uf_iter_timed && c->uf_ev.size() >= 4 && used >= 2) {
+      // graph path: the operator launch of the second iteration (external event nodes of the batch graph) -- the launch
+      // of the prologue runs beside the vdW rows and is not what the other 7 look like
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->uf_ev[2], c->uf_ev[3]);
+      c->stats.ms_ufield_real = ms;
+   } else {
       // mean device time of the real-space ufield launches that did work (speculative launches after
       // convergence return immediately and are excluded): 1 for r0 + one per iteration
       int used_pairs = std::min(c->uf_used / 2, used + ((c->opt.pcgguess || predict) ? 1 : 0));
@@ -570,6 +578,7 @@ static bool induce_core(apx_ctx* c, int mode)
             CUDA_CHECK(cudaEventCreate(&e));
       }
       c->uf_used = 0;
+      c->uf_iter_timed = 0;
       c->tl_valid = 0, c->tl_p_valid = 0;      // one tensor build per induce(), by its first operator application: the launch sequence
                                                // (and with it the captured graphs) does not depend on what ran before
       cudaEventRecord(c->ev0, st);
@@ -788,8 +797,11 @@ static bool induce_core(apx_ctx* c, int mode)
             int before = c->stats.kernel_launches;
             c->capturing = 1;
             CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            for (int b = 0; b < len; ++b)
+            for (int b = 0; b < len; ++b) {
+               c->uf_ext_iter = b == std::min(1, len - 1) ? 1 : 0;      // the second iteration's operator launch is timed (steady state)
                enqueue_iteration(0, true, 0);
+            }
+            c->uf_ext_iter = 0;
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamEndCapture(st, &graph);
             c->capturing = 0;
@@ -815,6 +827,8 @@ static bool induce_core(apx_ctx* c, int mode)
             find_or_capture(2);      // (the continuation batches of a solve that outgrows its first batch)
          }
          apx_ctx::PcgGraph* G = find_or_capture(nit);
+         if (first_batch)
+            c->uf_iter_timed = 1;
          CUDA_CHECK(cudaGraphLaunch(G->exec, st));
          c->stats.kernel_launches += G->launches;
          iter += nit;
