@@ -182,7 +182,11 @@ void apx_destroy(apx_ctx* ctx);
  * the box into z-slabs, exchanges halo dipoles and PME planes and reduces energies/forces, so every
  * entry point below is then COLLECTIVE: all ranks call it, in the same order, and all receive the
  * complete result.  transport "nccl": handle = the 128-byte id from apx_nccl_unique_id() of rank 0,
- * nccl_lib = path of the libnccl.so.2 the process uses (NULL: default search).  transport "local":
+ * nccl_lib = path of the libnccl.so.2 the process uses (NULL: default search); the bulk exchanges (halo vectors, PME planes,
+ * FFT transposes) and the solver's scalar all-reduces then run as the library's own kernels writing into the peers'
+ * CUDA-IPC-mapped buffers over NVLink (APX_DIST_P2P=3, default; 2 = windowed push/pull, 0 = NCCL send/recv), NCCL keeps
+ * the start-up handshake and the large force reduction.  transport "direct": the same peer-memory kernels with no NCCL at
+ * all; handle = 16 bytes of job id shared by the ranks (processes of one node), nccl_lib = NULL.  transport "local":
  * handle = apx_local_hub_create(world); the ranks are host threads of one process sharing a GPU. */
 int apx_create_dist(const apx_system* sys, int device, int rank, int world, const char* transport, const void* handle,
    const char* nccl_lib, apx_ctx** out);

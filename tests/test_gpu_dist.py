@@ -128,3 +128,18 @@ def test_operators_collective():
             assert np.abs(o[k][0] - ref[k][0]).max() < 1e-10
             assert np.abs(o[k][1] - ref[k][1]).max() < 1e-10
         assert np.abs(o[3] - ref[3]).max() < 1e-10
+
+
+@pytest.mark.parametrize("world,precision", [(2, "mixed"), (3, "double")])
+def test_direct_transport_between_processes(world, precision):
+    """The peer-memory transport of real multi-GPU runs (dist.cu DirectComm: CUDA IPC registered buffers, one kernel per
+    exchange, flag-based all-reduce; no NCCL) with one PROCESS per rank.  On a one-GPU box the processes share the device and
+    their exchange kernels alternate by time slice; the result must match the single-GPU path like the in-process ranks do."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "direct_check.py"), "--world", str(world), "--blob", "water30",
+                        "--precision", precision, "--timeout", "400"], capture_output=True, text=True, timeout=450)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert len(lines) == 3 and all(ln.endswith("OK") for ln in lines), r.stdout[-2000:]

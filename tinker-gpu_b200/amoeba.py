@@ -323,7 +323,8 @@ class Amoeba:
     """One electrostatics context on one GPU (the reference's initialize()/finish() pair).
 
     dist=(rank, world, transport, handle): this context is one rank of a spatially decomposed system on
-    `world` GPUs (transport "nccl": handle = nccl_unique_id() of rank 0; "local": handle = LocalHub).
+    `world` GPUs (transport "nccl": handle = nccl_unique_id() of rank 0; "direct": handle = a job id shared by the ranks,
+    peer memory without NCCL; "local": handle = LocalHub).
     Every method is then collective (all ranks call it in the same order)."""
 
     def __init__(self, system: System, precision: str = "mixed", device: int = 0, dist=None, vdw: bool = False,
@@ -344,6 +345,11 @@ class Amoeba:
                 self._hub = handle
                 h = C.c_void_p(handle.handle)
                 rc = self.lib.apx_create_dist(C.byref(s), device, rank, world, b"local", h, None, C.byref(self.ctx))
+            elif transport == "direct":
+                # peer memory only (CUDA IPC between the processes of one node), no NCCL: handle = 16+ bytes of job id
+                self._idbuf = C.create_string_buffer(bytes(handle).ljust(128, b"\0"), 128)
+                rc = self.lib.apx_create_dist(C.byref(s), device, rank, world, b"direct", C.cast(self._idbuf, C.c_void_p),
+                                              None, C.byref(self.ctx))
             else:
                 self._idbuf = C.create_string_buffer(bytes(handle), 128)
                 rc = self.lib.apx_create_dist(C.byref(s), device, rank, world, b"nccl", C.cast(self._idbuf, C.c_void_p),

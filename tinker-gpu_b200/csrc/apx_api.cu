@@ -12,6 +12,7 @@ void apx_grad_to_caller(apx_ctx* c, double* dev_out);
 struct ApxComm;
 ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* unique_id);
 ApxComm* apx_make_local_comm(int rank, int world, void* hub);
+ApxComm* apx_make_direct_comm(int rank, int world, const void* job_id);
 
 static thread_local std::string g_err;
 
@@ -171,6 +172,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
       std::string t = transport ? transport : "nccl";
       if (t == "nccl")
          c->dist.comm = apx_make_nccl_comm(rank, world, nccl_lib, handle);
+      else if (t == "direct")
+         c->dist.comm = apx_make_direct_comm(rank, world, handle);
       else if (t == "local")
          c->dist.comm = apx_make_local_comm(rank, world, const_cast<void*>(handle));
       else

@@ -31,6 +31,7 @@
 #include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
 
 // ------------------------------------------------------------------------------------------------
 // transports
@@ -105,21 +106,89 @@ NcclApi* nccl_api(const char* path)
          apx_throw(__FILE__, __LINE__, std::string(#expr) + ": " + (api)->GetErrorString(r__));                          \
    } while (0)
 
+// ---- start-up exchange of small host blobs between the ranks of one node without NCCL (transport "direct"): every
+// rank drops its blob into /dev/shm under a name derived from the job id and polls for the others'.  Round k files
+// are removed by their owner once round k+1 has been read (every rank has then finished reading round k).
+struct FileRendezvous {
+   std::string prefix;
+   int rank = 0, world = 1;
+   unsigned round = 0;
+   std::string name(int r, unsigned rd) const { return prefix + "_" + std::to_string(rd) + "_" + std::to_string(r); }
+   void gather(const void* mine, size_t bytes, void* all)
+   {
+      ++round;
+      const std::string fin = name(rank, round), tmp = fin + ".tmp";
+      FILE* f = fopen(tmp.c_str(), "wb");
+      if (!f || fwrite(mine, 1, bytes, f) != bytes)
+         APX_THROW("rendezvous: cannot write " + tmp);
+      fclose(f);
+      if (rename(tmp.c_str(), fin.c_str()) != 0)
+         APX_THROW("rendezvous: cannot publish " + fin);
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int r = 0; r < world; ++r) {
+         char* dst = static_cast<char*>(all) + (size_t)r * bytes;
+         if (r == rank) {
+            memcpy(dst, mine, bytes);
+            continue;
+         }
+         const std::string fn = name(r, round);
+         for (;;) {
+            FILE* g = fopen(fn.c_str(), "rb");
+            if (g) {
+               const size_t got = fread(dst, 1, bytes, g);
+               fclose(g);
+               if (got == bytes)
+                  break;
+            }
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+               APX_THROW("rendezvous: rank " + std::to_string(r) + " did not show up within 120 s (" + fn + ")");
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+         }
+      }
+      if (round > 1)
+         remove(name(rank, round - 1).c_str());
+   }
+};
+
 struct NcclComm : ApxComm {
    NcclApi* api = nullptr;
    ncclComm_t comm = nullptr;
+   FileRendezvous* rdv = nullptr;      // set instead of `comm` by the NCCL-free transport
    ~NcclComm() override
    {
       if (comm)
          api->CommDestroy(comm);
+      delete rdv;
+   }
+   void need_nccl(const char* what) const
+   {
+      if (!comm)
+         APX_THROW(std::string("transport \"direct\" has no NCCL communicator: ") + what);
+   }
+   // every rank's blob of `bytes` host bytes, concatenated by rank (start-up only: synchronises the host)
+   void gather_bytes(const void* mine, size_t bytes, void* all)
+   {
+      if (rdv) {
+         rdv->gather(mine, bytes, all);
+         return;
+      }
+      char* dev = nullptr;
+      CUDA_CHECK(cudaMalloc(&dev, bytes * (world + 1)));
+      CUDA_CHECK(cudaMemcpy(dev + bytes * world, mine, bytes, cudaMemcpyHostToDevice));
+      NCCL_CHECK(api, api->AllGather(dev + bytes * world, dev, bytes, ncclChar, comm, nullptr));
+      CUDA_CHECK(cudaStreamSynchronize(nullptr));
+      CUDA_CHECK(cudaMemcpy(all, dev, bytes * world, cudaMemcpyDeviceToHost));
+      cudaFree(dev);
    }
    void allreduce(void* p, size_t n, int dtype, cudaStream_t st) override
    {
+      need_nccl("all-reduce");
       ncclDataType_t t = dtype == 0 ? ncclFloat64 : (dtype == 1 ? ncclUint64 : ncclInt32);
       NCCL_CHECK(api, api->AllReduce(p, p, n, t, ncclSum, comm, st));
    }
    void exchange(const std::vector<Op>& sends, const std::vector<Op>& recvs, cudaStream_t st) override
    {
+      need_nccl("send/recv");
       NCCL_CHECK(api, api->GroupStart());
       for (const Op& o : sends)
          NCCL_CHECK(api, api->Send(o.ptr, o.bytes, ncclChar, o.peer, comm, st));
@@ -270,14 +339,8 @@ struct P2pComm : NcclComm {
       Handles mine;
       CUDA_CHECK(cudaIpcGetMemHandle(&mine.w, win));
       CUDA_CHECK(cudaIpcGetMemHandle(&mine.f, flg));
-      Handles* dev = nullptr;
-      CUDA_CHECK(cudaMalloc(&dev, sizeof(Handles) * (world + 1)));
-      CUDA_CHECK(cudaMemcpy(dev + world, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
-      NCCL_CHECK(api, api->AllGather(dev + world, dev, sizeof(Handles), ncclChar, comm, nullptr));
-      CUDA_CHECK(cudaStreamSynchronize(nullptr));
       std::vector<Handles> all(world);
-      CUDA_CHECK(cudaMemcpy(all.data(), dev, sizeof(Handles) * world, cudaMemcpyDeviceToHost));
-      cudaFree(dev);
+      gather_bytes(&mine, sizeof(Handles), all.data());
       peer_win.assign(world, nullptr);
       peer_flg.assign(world, nullptr);
       for (int r = 0; r < world; ++r) {
@@ -305,13 +368,12 @@ struct P2pComm : NcclComm {
             if (peer_win[r]) cudaIpcCloseMemHandle(peer_win[r]);
             if (peer_flg[r]) cudaIpcCloseMemHandle(peer_flg[r]);
          }
-      // every peer must have unmapped before the owner frees: the NCCL communicator is still alive here
-      int* d = nullptr;
-      if (cudaMalloc(&d, sizeof(int)) == cudaSuccess) {
-         cudaMemset(d, 0, sizeof(int));
-         api->AllReduce(d, d, 1, ncclInt32, ncclSum, comm, nullptr);
-         cudaStreamSynchronize(nullptr);
-         cudaFree(d);
+      // every peer must have unmapped before the owner frees: the communicator / rendezvous is still alive here
+      try {
+         char one = 0;
+         std::vector<char> all(world);
+         gather_bytes(&one, 1, all.data());
+      } catch (...) {
       }
       cudaFree(win);
       cudaFree(flg);
@@ -452,6 +514,406 @@ struct P2pComm : NcclComm {
          Q.set_val = seq;
          Q.counters = counters + 16;
          k_xfer<<<grid, 256, 0, st>>>(Q);
+      }
+   }
+};
+
+// ---- direct transport (APX_DIST_P2P=3, the default for 2..8 GPUs; also transport "direct", which has no NCCL at all)
+//
+// The windowed exchange above costs, per transpose of the slab FFT, a pack kernel, a push into the peer's window, a pull
+// out of my window and an unpack kernel: the 36 MB block crosses HBM five times and NVLink once, in four launches with
+// two cross-GPU flag waits (profiles/r02m_trace_water1m_n2.txt: 144 us of a 1550 us CG iteration per transpose, 24 % of
+// the step in k_xfer).  Here the buffers an exchange lands in (PME planes, transposed slab, halo planes, the packed
+// per-atom vectors) are REGISTERED: every rank maps the peers' allocations through CUDA IPC once, and ONE kernel per
+// exchange writes every message straight to its final place in the peer's memory over NVLink -- strided chunk by chunk
+// for the transposes (the transpose IS the address arithmetic of the copy), atom by atom for the per-atom halos (sorted
+// indices are global, so the sender's index list is the receiver's).  Protocol, sequence numbers only grow:
+//   arrive[from]  block 0 of my exchange kernel k tells every rank that will write to me "my stream has reached exchange
+//                 k": every earlier kernel of mine has finished with the destination buffers, they may be overwritten;
+//   (copy)        a CTA waits for its peer's arrive >= k, copies its share of the message, and the last CTA serving a
+//                 peer raises
+//   ready[from]   in the peer's memory; block 0 ends by waiting for ready >= k from every rank that writes to me, so the
+//                 kernel that follows on my stream sees the data.
+// No window, no second copy, no acknowledge round trip; self-addressed blocks are moved by the same kernel.  Small
+// all-reduces (the solver's scalars) use the same flags: one CTA stores its values into a slot of every peer, raises the
+// peer's flag, waits for the peers' and sums the slots in rank order -- every rank gets the same bits.
+#define DX_MAX_MSG 24
+#define DX_FLAG_ARRIVE 0
+#define DX_FLAG_READY 16
+#define DX_FLAG_AR 32
+#define DX_FLAG_WORDS 64
+#define DAR_MAX 512              // elements of one small all-reduce
+struct DxMsg {
+   const char* src;
+   char* dst;
+   unsigned long long src_stride, dst_stride;      // bytes between consecutive chunks
+   unsigned chunk16;                               // kind 0: 16-byte units per chunk
+   unsigned nchunks;                               // kind 0: chunks; kind 1: atoms
+   const int* idx;                                 // kind 1: 32-byte items at 32 * idx[j] on both sides
+   int peer, cta0, nctas, kind;
+};
+struct DxTable {
+   DxMsg m[DX_MAX_MSG];
+   int nmsg, rank, world;
+   unsigned seq;
+   unsigned recv_mask;                             // ranks that write to me in this exchange
+   volatile unsigned* peer_flags[16];              // peers' flag blocks, mapped
+   volatile unsigned* my_flags;
+   int peer_ctas[16];
+   unsigned* counters;                             // [16] arrival counters, self-resetting
+};
+
+__device__ __forceinline__ unsigned long long dx_now()
+{
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+   return t;
+}
+// a peer that never shows up must not hang the GPU: after 30 s the kernel traps and the host call fails
+__device__ __forceinline__ void dx_wait(const volatile unsigned* f, unsigned want)
+{
+   if ((int)(*f - want) >= 0)
+      return;
+   const unsigned long long t0 = dx_now();
+   while ((int)(*f - want) < 0) {
+      __nanosleep(64);
+      if (dx_now() - t0 > 30000000000ull)
+         __trap();
+   }
+}
+
+__global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T)
+{
+   __shared__ int s_msg;
+   const int tid = threadIdx.x;
+   const bool gate = blockIdx.x == 0 && tid < T.world && ((T.recv_mask >> tid) & 1u);
+   if (gate)
+      T.peer_flags[tid][DX_FLAG_ARRIVE + T.rank] = T.seq;
+   if (tid == 0) {
+      int k = 0;
+      while (k < T.nmsg - 1 && (int)blockIdx.x >= T.m[k].cta0 + T.m[k].nctas)
+         ++k;
+      s_msg = k;
+      const int p = T.m[k].peer;
+      if (T.nmsg > 0 && p != T.rank) {
+         dx_wait(T.my_flags + DX_FLAG_ARRIVE + p, T.seq);
+         __threadfence_system();
+      }
+   }
+   __syncthreads();
+   if (T.nmsg > 0) {
+      const DxMsg& M = T.m[s_msg];
+      const int part = (int)blockIdx.x - M.cta0;
+      if (M.kind == 0) {
+         const unsigned long long n16 = (unsigned long long)M.chunk16 * M.nchunks;
+         const unsigned long long per = (n16 + M.nctas - 1) / M.nctas;
+         const unsigned long long b0 = per * part, b1 = b0 + per < n16 ? b0 + per : n16;
+         const unsigned c16 = M.chunk16;
+         auto src_of = [&](unsigned long long q) {
+            const unsigned long long ch = q / c16;
+            return reinterpret_cast<const uint4*>(M.src + ch * M.src_stride) + (q - ch * c16);
+         };
+         auto dst_of = [&](unsigned long long q) {
+            const unsigned long long ch = q / c16;
+            return reinterpret_cast<uint4*>(M.dst + ch * M.dst_stride) + (q - ch * c16);
+         };
+         unsigned long long q = b0 + tid;
+         const unsigned bd = blockDim.x;
+         for (; q + 3 * bd < b1; q += 4 * bd) {      // four independent 16-byte transfers in flight per thread
+            const uint4 v0 = __ldcg(src_of(q)), v1 = __ldcg(src_of(q + bd)), v2 = __ldcg(src_of(q + 2 * bd)), v3 = __ldcg(src_of(q + 3 * bd));
+            *dst_of(q) = v0, *dst_of(q + bd) = v1, *dst_of(q + 2 * bd) = v2, *dst_of(q + 3 * bd) = v3;
+         }
+         for (; q < b1; q += bd)
+            *dst_of(q) = __ldcg(src_of(q));
+      } else {
+         const unsigned n2 = 2u * M.nchunks;           // two 16-byte halves per atom
+         const unsigned per = (n2 + M.nctas - 1) / M.nctas;
+         const unsigned b0 = per * part, b1 = b0 + per < n2 ? b0 + per : n2;
+         for (unsigned q = b0 + tid; q < b1; q += blockDim.x) {
+            const size_t o = 2 * (size_t)M.idx[q >> 1] + (q & 1u);
+            reinterpret_cast<uint4*>(M.dst)[o] = __ldcg(reinterpret_cast<const uint4*>(M.src) + o);
+         }
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (tid == 0 && M.peer != T.rank) {
+         const int p = M.peer;
+         const unsigned old = atomicInc(&T.counters[p], (unsigned)T.peer_ctas[p] - 1);
+         if (old == (unsigned)T.peer_ctas[p] - 1) {
+            __threadfence_system();
+            T.peer_flags[p][DX_FLAG_READY + T.rank] = T.seq;
+         }
+      }
+   }
+   if (gate) {
+      dx_wait(T.my_flags + DX_FLAG_READY + tid, T.seq);
+      __threadfence_system();
+   }
+}
+
+struct DarTable {
+   char* peer_stage[16];                 // peers' staging areas, mapped: [parity][from][DAR_MAX] 8-byte slots
+   const char* my_stage;
+   volatile unsigned* peer_flags[16];
+   volatile unsigned* my_flags;
+   int rank, world;
+   unsigned seq;
+};
+template <class V>
+__global__ void __launch_bounds__(DAR_MAX) k_dar(V* __restrict__ data, int n, const __grid_constant__ DarTable A)
+{
+   const int tid = threadIdx.x;
+   const size_t par = (size_t)(A.seq & 1u) * 16;
+   V mine = 0;
+   if (tid < n) {
+      mine = data[tid];
+      for (int p = 0; p < A.world; ++p)
+         if (p != A.rank)
+            reinterpret_cast<V*>(A.peer_stage[p] + (par + A.rank) * DAR_MAX * 8)[tid] = mine;
+   }
+   __threadfence_system();
+   __syncthreads();
+   if (tid < A.world && tid != A.rank) {
+      A.peer_flags[tid][DX_FLAG_AR + A.rank] = A.seq;
+      dx_wait(A.my_flags + DX_FLAG_AR + tid, A.seq);
+      __threadfence_system();
+   }
+   __syncthreads();
+   if (tid < n) {
+      V s = 0;
+      for (int r = 0; r < A.world; ++r)      // rank order: the same bits on every rank
+         s += r == A.rank ? mine : reinterpret_cast<const volatile V*>(A.my_stage + (par + r) * DAR_MAX * 8)[tid];
+      data[tid] = s;
+   }
+}
+
+struct DirectComm : P2pComm {
+   struct Region {
+      char* base = nullptr;
+      size_t size = 0;
+      char* peer[16] = {};
+   };
+   struct Mapping {
+      cudaIpcMemHandle_t h;
+      char* p;
+      int used;
+   };
+   std::vector<Region> regions;
+   std::vector<Mapping> maps[16];
+   std::vector<void*> wanted;           // pointers (anywhere inside their allocations) the next sync registers
+   bool dirty = true;
+   char* dmem = nullptr;                // my flag block + all-reduce staging, written by the peers
+   char* peer_dmem[16] = {};
+   unsigned* dcounters = nullptr;
+   unsigned dseq = 0, arseq = 0;
+   int total_ctas = 592;                // CTAs of one exchange kernel, shared out by bytes
+   bool dok = false;
+   static constexpr size_t FLAG_BYTES = 256;
+   static constexpr size_t STAGE_BYTES = (size_t)2 * 16 * DAR_MAX * 8;
+
+   typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+   range_fn addr_range = nullptr;
+
+   void dsetup()
+   {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+         APX_THROW("direct transport: cuMemGetAddressRange is not available");
+      addr_range = reinterpret_cast<range_fn>(fn);
+      CUDA_CHECK(cudaMalloc(&dmem, FLAG_BYTES + STAGE_BYTES));
+      CUDA_CHECK(cudaMemset(dmem, 0, FLAG_BYTES + STAGE_BYTES));
+      CUDA_CHECK(cudaMalloc(&dcounters, sizeof(unsigned) * 16));
+      CUDA_CHECK(cudaMemset(dcounters, 0, sizeof(unsigned) * 16));
+      CUDA_CHECK(cudaDeviceSynchronize());
+      cudaIpcMemHandle_t mine;
+      CUDA_CHECK(cudaIpcGetMemHandle(&mine, dmem));
+      std::vector<cudaIpcMemHandle_t> all(world);
+      gather_bytes(&mine, sizeof(mine), all.data());
+      for (int r = 0; r < world; ++r) {
+         if (r == rank) {
+            peer_dmem[r] = dmem;
+            continue;
+         }
+         void* a = nullptr;
+         CUDA_CHECK(cudaIpcOpenMemHandle(&a, all[r], cudaIpcMemLazyEnablePeerAccess));
+         peer_dmem[r] = static_cast<char*>(a);
+      }
+      if (const char* e = getenv("APX_DX_CTAS"))
+         total_ctas = std::max(8, std::min(4096, atoi(e)));
+      dok = true;
+   }
+   ~DirectComm() override
+   {
+      if (!dok)
+         return;
+      cudaDeviceSynchronize();
+      for (int r = 0; r < world; ++r) {
+         if (r == rank)
+            continue;
+         if (peer_dmem[r])
+            cudaIpcCloseMemHandle(peer_dmem[r]);
+         for (Mapping& m : maps[r])
+            cudaIpcCloseMemHandle(m.p);
+      }
+      try {      // (owners free only after every peer has unmapped)
+         char one = 0;
+         std::vector<char> all(world);
+         gather_bytes(&one, 1, all.data());
+      } catch (...) {
+      }
+      cudaFree(dmem);
+      cudaFree(dcounters);
+   }
+
+   // collective: (re)register the allocations behind `wanted`; mappings of allocations no region uses any more are closed
+   void sync_regions()
+   {
+      struct Rec {
+         cudaIpcMemHandle_t h;
+         unsigned long long size;
+         int valid;
+      };
+      const int nr = (int)wanted.size();
+      std::vector<Rec> mine(nr), all((size_t)nr * world);
+      regions.assign(nr, Region());
+      for (int k = 0; k < nr; ++k) {
+         memset(&mine[k], 0, sizeof(Rec));
+         if (!wanted[k])
+            continue;
+         unsigned long long base = 0;
+         size_t size = 0;
+         if (addr_range(&base, &size, (unsigned long long)(uintptr_t)wanted[k]) != 0)
+            APX_THROW("direct transport: pointer does not belong to a device allocation");
+         regions[k].base = reinterpret_cast<char*>((uintptr_t)base);
+         regions[k].size = size;
+         CUDA_CHECK(cudaIpcGetMemHandle(&mine[k].h, regions[k].base));
+         mine[k].size = size;
+         mine[k].valid = 1;
+      }
+      CUDA_CHECK(cudaDeviceSynchronize());      // nothing of mine is in flight towards a mapping that is about to be closed
+      if (nr)
+         gather_bytes(mine.data(), sizeof(Rec) * nr, all.data());
+      for (int r = 0; r < world; ++r) {
+         for (Mapping& m : maps[r])
+            m.used = 0;
+         for (int k = 0; k < nr; ++k) {
+            if (r == rank) {
+               regions[k].peer[r] = regions[k].base;
+               continue;
+            }
+            const Rec& R = all[(size_t)r * nr + k];
+            if (!R.valid)
+               continue;
+            Mapping* hit = nullptr;
+            for (Mapping& m : maps[r])
+               if (memcmp(&m.h, &R.h, sizeof(R.h)) == 0)
+                  hit = &m;
+            if (!hit) {
+               void* a = nullptr;
+               CUDA_CHECK(cudaIpcOpenMemHandle(&a, R.h, cudaIpcMemLazyEnablePeerAccess));
+               maps[r].push_back({R.h, static_cast<char*>(a), 0});
+               hit = &maps[r].back();
+            }
+            hit->used = 1;
+            regions[k].peer[r] = hit->p;
+         }
+         for (size_t q = 0; q < maps[r].size();)
+            if (!maps[r][q].used) {
+               cudaIpcCloseMemHandle(maps[r][q].p);
+               maps[r].erase(maps[r].begin() + q);
+            } else
+               ++q;
+      }
+      dirty = false;
+   }
+   // the address, in `peer`'s memory, of what `mine` is in my memory (same offset in the peer's registered allocation)
+   char* remote(const void* mine, int peer) const
+   {
+      const char* q = static_cast<const char*>(mine);
+      for (const Region& R : regions)
+         if (R.base && q >= R.base && q < R.base + R.size) {
+            if (!R.peer[peer])
+               break;
+            return R.peer[peer] + (q - R.base);
+         }
+      APX_THROW("direct transport: destination buffer is not registered");
+      return nullptr;
+   }
+
+   struct Msg {            // one message of an exchange, in terms of MY buffers: dst is translated to the peer's
+      int peer;
+      const void* src;
+      void* dst;
+      size_t chunk_bytes, nchunks, src_stride, dst_stride;
+      const int* idx = nullptr;      // per-atom scatter (nchunks atoms of 32 bytes) when set
+   };
+   void xchg(const std::vector<Msg>& msgs, unsigned recv_mask, cudaStream_t st)
+   {
+      if (dirty)
+         sync_regions();
+      ++dseq;
+      if (msgs.empty() && !recv_mask)
+         return;
+      if ((int)msgs.size() > DX_MAX_MSG)
+         APX_THROW("direct transport: too many messages in one exchange");
+      DxTable T;
+      memset(&T, 0, sizeof(T));
+      size_t total = 0;
+      for (const Msg& m : msgs)
+         total += m.idx ? m.nchunks * 32 : m.chunk_bytes * m.nchunks;
+      int grid = 0;
+      for (const Msg& m : msgs) {
+         DxMsg& M = T.m[T.nmsg++];
+         const size_t bytes = m.idx ? m.nchunks * 32 : m.chunk_bytes * m.nchunks;
+         M.src = static_cast<const char*>(m.src);
+         M.dst = m.peer == rank ? static_cast<char*>(m.dst) : remote(m.dst, m.peer);
+         M.src_stride = m.src_stride, M.dst_stride = m.dst_stride;
+         if (!m.idx && (m.chunk_bytes % 16 || m.src_stride % 16 || m.dst_stride % 16 || ((uintptr_t)M.src | (uintptr_t)M.dst) % 16))
+            APX_THROW("direct transport: messages must be 16-byte aligned");
+         M.chunk16 = (unsigned)(m.chunk_bytes / 16);
+         M.nchunks = (unsigned)m.nchunks;
+         M.idx = m.idx;
+         M.kind = m.idx ? 1 : 0;
+         M.peer = m.peer;
+         M.cta0 = grid;
+         M.nctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)total_ctas * bytes / std::max<size_t>(total, 1), bytes / 16384 + 1));
+         grid += M.nctas;
+         T.peer_ctas[m.peer] += M.nctas;
+      }
+      T.rank = rank, T.world = world, T.seq = dseq, T.recv_mask = recv_mask & ~(1u << rank);
+      for (int p = 0; p < world; ++p)
+         T.peer_flags[p] = reinterpret_cast<volatile unsigned*>(peer_dmem[p]);
+      T.my_flags = reinterpret_cast<volatile unsigned*>(dmem);
+      T.counters = dcounters;
+      k_dxchg<<<std::max(grid, 1), 256, 0, st>>>(T);
+   }
+
+   void allreduce(void* p, size_t n, int dtype, cudaStream_t st) override
+   {
+      const size_t es = dtype == 2 ? 4 : 8;
+      if (n > DAR_MAX && comm) {
+         NcclComm::allreduce(p, n, dtype, st);
+         return;
+      }
+      for (size_t o = 0; o < n; o += DAR_MAX) {      // (more than one pass only without NCCL: tests on small systems)
+         const int m = (int)std::min<size_t>(DAR_MAX, n - o);
+         DarTable A;
+         memset(&A, 0, sizeof(A));
+         for (int r = 0; r < world; ++r) {
+            A.peer_stage[r] = peer_dmem[r] + FLAG_BYTES;
+            A.peer_flags[r] = reinterpret_cast<volatile unsigned*>(peer_dmem[r]);
+         }
+         A.my_stage = dmem + FLAG_BYTES;
+         A.my_flags = reinterpret_cast<volatile unsigned*>(dmem);
+         A.rank = rank, A.world = world, A.seq = ++arseq;
+         char* q = static_cast<char*>(p) + o * es;
+         if (dtype == 0)
+            k_dar<double><<<1, DAR_MAX, 0, st>>>((double*)q, m, A);
+         else if (dtype == 1)
+            k_dar<unsigned long long><<<1, DAR_MAX, 0, st>>>((unsigned long long*)q, m, A);
+         else
+            k_dar<int><<<1, DAR_MAX, 0, st>>>((int*)q, m, A);
       }
    }
 };
@@ -688,6 +1150,41 @@ __global__ void k_transpose_unpack(int pz, int n2, int n1, int py, const cplx* _
    planes[i] = buf[(((size_t)r * pz + z) * py + yl) * n1 + x];
 }
 
+// both halo-plane sums of the forward transform in one launch
+__global__ void k_grid_add2(size_t m1, const cplx* __restrict__ s1, cplx* __restrict__ d1, size_t m2, const cplx* __restrict__ s2,
+   cplx* __restrict__ d2)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   const cplx* s = s1;
+   cplx* d = d1;
+   if (i >= m1) {
+      i -= m1;
+      if (i >= m2)
+         return;
+      s = s2, d = d2;
+   }
+   cplx a = d[i], b = s[i];
+   a.x += b.x;
+   a.y += b.y;
+   d[i] = a;
+}
+
+// the direct transport of this context, with the buffers its exchanges land in registered (a collective re-registration
+// follows whenever one of them has moved: sizes, and with them reallocations, are the same on every rank)
+DirectComm* direct_of(apx_ctx* c)
+{
+   DirectComm* dc = dynamic_cast<DirectComm*>(c->dist.comm);
+   if (!dc || !dc->dok)
+      return nullptr;
+   void* w[] = {c->qgrid.p, c->dist.tbuf.p, c->dist.hbuf.p, c->pk_p.p, c->pk_r.p};
+   const size_t nw = sizeof(w) / sizeof(w[0]);
+   if (dc->wanted.size() != nw || !std::equal(w, w + nw, dc->wanted.begin())) {
+      dc->wanted.assign(w, w + nw);
+      dc->dirty = true;
+   }
+   return dc;
+}
+
 inline void exec_fft(cufftHandle plan, cplx* p, int dir)
 {
 #ifdef APX_DOUBLE
@@ -773,6 +1270,24 @@ void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st)
    const int G = D.world;
    const int pslot = apx_dist_prof_begin(c, 0, st);
    const int ns = D.send_off[G], nr = D.recv_off[G];
+   if (DirectComm* dc = direct_of(c)) {
+      // every halo atom goes straight from my V to the same slot of the neighbour's V
+      std::vector<DirectComm::Msg> msgs;
+      unsigned recv_mask = 0;
+      for (int r = 0; r < G; ++r) {
+         if (D.send_off[r + 1] > D.send_off[r]) {
+            DirectComm::Msg m{r, V, V, 32, (size_t)(D.send_off[r + 1] - D.send_off[r]), 0, 0};
+            m.idx = D.send_idx.p + D.send_off[r];
+            msgs.push_back(m);
+         }
+         if (D.recv_off[r + 1] > D.recv_off[r])
+            recv_mask |= 1u << r;
+      }
+      dc->xchg(msgs, recv_mask, st);
+      APX_COUNT_LAUNCH(c);
+      apx_dist_prof_end(c, pslot, st);
+      return;
+   }
    if (ns > 0) {
       k_halo_pack<<<(2 * ns + 255) / 256, 256, 0, st>>>(ns, D.send_idx, V, D.sendbuf);
       APX_COUNT_LAUNCH(c);
@@ -888,6 +1403,31 @@ void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
    cudaStream_t st = c->stream;
    cplx* g = c->qgrid.p;
    const int pslot = apx_dist_prof_begin(c, 1, st);
+   if (DirectComm* dc = direct_of(c)) {
+      // 1. my halo planes land in the neighbours' hbuf and are summed into the planes they belong to
+      const size_t pb = plane * sizeof(cplx);
+      std::vector<DirectComm::Msg> h = {{prev, g, D.hbuf.p, D.hl * pb, 1, 0, 0},
+         {next, g + (size_t)(D.hl + D.pz) * plane, D.hbuf.p + D.hl * plane, D.hu * pb, 1, 0, 0}};
+      dc->xchg(h, (1u << prev) | (1u << next), st);
+      const size_t m1 = D.hl * plane, m2 = D.hu * plane;
+      k_grid_add2<<<(unsigned)((m1 + m2 + 255) / 256), 256, 0, st>>>(m1, D.hbuf.p, g + (size_t)D.pz * plane, m2, D.hbuf.p + D.hl * plane,
+         g + (size_t)D.hl * plane);
+      cplx* mine = g + (size_t)D.hl * plane;
+      // 2. 2-D transforms of my planes; 3. the transpose is the address arithmetic of ONE copy kernel: rows y of rank r's
+      // share of every plane go to [k3 = my planes][y local to r][x] of r's slab; 4. 1-D transforms along z
+      exec_fft(D.plan2d, mine, CUFFT_FORWARD);
+      const size_t chunk = (size_t)D.py * n1 * sizeof(cplx), blk = (size_t)D.pz * D.py * n1;
+      std::vector<DirectComm::Msg> t;
+      for (int q = 0; q < G; ++q) {
+         const int r = (D.rank + q) % G;      // my own block first, then the peers in ring order: no two ranks start on the same target
+         t.push_back({r, mine + (size_t)r * D.py * n1, tb + (size_t)D.rank * blk, chunk, (size_t)D.pz, pb, chunk});
+      }
+      dc->xchg(t, (1u << G) - 1u, st);
+      exec_fft(D.plan1d, tb, CUFFT_FORWARD);
+      c->stats.kernel_launches += 6;
+      apx_dist_prof_end(c, pslot, st);
+      return;
+   }
    // 1. halo planes go to the slabs they belong to and are summed there
    {
       std::vector<ApxComm::Op> sends = {{prev, g, D.hl * plane * sizeof(cplx)}, {next, g + (size_t)(D.hl + D.pz) * plane, D.hu * plane * sizeof(cplx)}};
@@ -926,6 +1466,25 @@ void apx_dist_fft_inverse(apx_ctx* c, cplx* tb)
    cplx* g = c->qgrid.p;
    cplx* mine = g + (size_t)D.hl * plane;
    const int pslot = apx_dist_prof_begin(c, 2, st);
+   if (DirectComm* dc = direct_of(c)) {
+      exec_fft(D.plan1d, tb, CUFFT_INVERSE);
+      const size_t pb = plane * sizeof(cplx);
+      const size_t chunk = (size_t)D.py * n1 * sizeof(cplx), blk = (size_t)D.pz * D.py * n1;
+      std::vector<DirectComm::Msg> t;
+      for (int q = 0; q < G; ++q) {
+         const int r = (D.rank + q) % G;
+         t.push_back({r, tb + (size_t)r * blk, mine + (size_t)D.rank * D.py * n1, chunk, (size_t)D.pz, chunk, pb});
+      }
+      dc->xchg(t, (1u << G) - 1u, st);
+      exec_fft(D.plan2d, mine, CUFFT_INVERSE);
+      // my top hl planes are the low halo of the next slab, my bottom hu planes the high halo of the previous one
+      std::vector<DirectComm::Msg> h = {{next, g + (size_t)D.pz * plane, g, D.hl * pb, 1, 0, 0},
+         {prev, mine, g + (size_t)(D.hl + D.pz) * plane, D.hu * pb, 1, 0, 0}};
+      dc->xchg(h, (1u << prev) | (1u << next), st);
+      c->stats.kernel_launches += 5;
+      apx_dist_prof_end(c, pslot, st);
+      return;
+   }
    exec_fft(D.plan1d, tb, CUFFT_INVERSE);
    const size_t tot = (size_t)D.pz * plane, blk = (size_t)D.pz * D.py * n1;
    {
@@ -973,10 +1532,12 @@ ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* un
    // measured on the 1 M-atom box (profiles/r01p..., r01s..., r01v..x): 2 GPUs 22.3 ms over NCCL, 21.5 with copy-engine
    // windows (mode 1), 21.3 with the fused push/pull kernels (mode 2); 4 GPUs 13.0 (NCCL), 15.3 (mode 1: the per-peer copies
    // of one exchange serialise on one stream), 13.0 (mode 2).  Default: mode 2 at 2 GPUs, NCCL beyond (8 GPUs not yet run).
-   int p2p = world == 2 ? 2 : 0;
+   // Round 2: mode 3 (direct transport, one kernel per exchange writing into the peers' registered buffers) is the default.
+   int p2p = 3;
    if (const char* e = getenv("APX_DIST_P2P"))
       p2p = atoi(e);
-   P2pComm* cm = new P2pComm();
+   DirectComm* dcm = p2p >= 3 && world <= 16 ? new DirectComm() : nullptr;
+   P2pComm* cm = dcm ? dcm : new P2pComm();
    cm->api = api;
    cm->rank = rank;
    cm->world = world;
@@ -991,7 +1552,35 @@ ApxComm* apx_make_nccl_comm(int rank, int world, const char* lib, const void* un
       if (const char* e = getenv("APX_DIST_WINDOW_MB"))
          mb = (size_t)std::max(1, atoi(e));
       cm->setup(mb << 20);
+      if (dcm)
+         dcm->dsetup();
    }
+   return cm;
+}
+
+// transport "direct": peer memory only, no NCCL anywhere -- ranks are processes of one node (one per GPU, or several sharing
+// a GPU in tests), the 128-byte job id names the /dev/shm rendezvous through which the IPC handles travel at start-up
+ApxComm* apx_make_direct_comm(int rank, int world, const void* job_id)
+{
+   if (world > 16)
+      APX_THROW("direct transport supports at most 16 ranks");
+   DirectComm* cm = new DirectComm();
+   cm->rank = rank;
+   cm->world = world;
+   cm->fused = 1;
+   cm->rdv = new FileRendezvous();
+   cm->rdv->rank = rank, cm->rdv->world = world;
+   static const char hex[] = "0123456789abcdef";
+   std::string key;
+   const unsigned char* b = static_cast<const unsigned char*>(job_id);
+   for (int k = 0; k < 16; ++k)
+      key += hex[b[k] >> 4], key += hex[b[k] & 15];
+   cm->rdv->prefix = "/dev/shm/apx_" + key;
+   size_t mb = 16;
+   if (const char* e = getenv("APX_DIST_WINDOW_MB"))
+      mb = (size_t)std::max(1, atoi(e));
+   cm->setup(mb << 20);
+   cm->dsetup();
    return cm;
 }
 
