@@ -692,14 +692,18 @@ def run_strong_child(args, rank, world, local_rank):
         st = a.stats()
         it = float(np.mean(iters))
         napp = max(1.0, float(prof[5]) / args.steps)      # PME round trips per step: iterations + r0 + permanent + converged dipoles
-        p2p = os.environ.get("APX_DIST_P2P", "2" if world == 2 else "0")
+        p2p = os.environ.get("APX_DIST_P2P", "3")
         out = {
             "workload": WORKLOADS[STRONG_WORKLOAD][4] + ", energy+gradient of the electrostatics path", "atoms": int(system.n),
             "n_gpus": world, "scaling": "strong", "steps": args.steps, "warmup": W,
             "parallelism": "single GPU" if world == 1 else f"spatial decomposition over {world} GPUs: z-slabs, halo exchange of dipoles per CG "
                                                            "iteration, slab PME FFT with all-to-all transposes",
             "transport": "none" if world == 1 else {"0": "NCCL grouped send/recv", "1": "CUDA-IPC peer windows, copy engines",
-                                                    "2": "CUDA-IPC peer windows, fused push/pull kernels (k_xfer)"}.get(p2p, p2p),
+                                                    "2": "CUDA-IPC peer windows, fused push/pull kernels (k_xfer)",
+                                                    "3": "direct: one kernel per exchange writes strided / per-atom messages into the "
+                                                         "peers' CUDA-IPC-registered buffers over NVLink (k_dxchg), flag-based scalar "
+                                                         "all-reduce (k_dar); NCCL only for the start-up handshake and the force reduction"
+                                                    }.get(p2p, p2p),
             "ms_per_step": vals[0], "ms_per_induce": vals[1], "pcg_iterations": it,
             "timing": "CUDA events on the library stream around each apx_energy call, barrier before every step, mean of steps, max over "
                       "ranks; working set 1.2 GB >> L2, no flush needed",
@@ -904,7 +908,7 @@ def run_ours(args, rank, world, local_rank):
         fp32_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         wl_desc = WORKLOADS[args.workload][4]
         metric = METRIC if args.workload == "dhfr2" else METRIC.replace("AMOEBA DHFR 23.5k atoms", wl_desc.split(",")[0])
-        par = "single GPU" if world == 1 else (f"spatial decomposition over {world} GPUs (z-slabs, NCCL halo exchange + slab FFT all-to-all)"
+        par = "single GPU" if world == 1 else (f"spatial decomposition over {world} GPUs (z-slabs, peer-memory halo exchange + slab FFT all-to-all transposes, dist.cu)"
                                                 if decomposed else f"replicas x{world}")
         if args.vdw:
             metric = metric.replace("electrostatics hot path only", "electrostatics hot path + buffered 14-7 vdW")

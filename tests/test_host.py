@@ -44,6 +44,17 @@ def test_parameter_assignment_local_frames():
     assert s.mexclude.shape[0] == s.dpexclude.shape[0] == 33 and s.uexclude.shape[0] == 0
 
 
+@needs_ref
+@pytest.mark.parametrize("extra", ["octahedron\na-axis 30.0\n", "dodecahedron\na-axis 30.0\n", "ewald\n"])
+def test_unsupported_cells_are_refused(extra):
+    """Truncated-octahedron / dodecahedron cells and non-periodic Ewald exist in the reference (include/ff/image.h:49-65,
+    src/cu/pme.cu:966-969) but not here: the reader must say so instead of running them as an ordinary box."""
+    import tinker_gpu_b200 as tg
+    with pytest.raises(ValueError):
+        tg.load_tinker(os.path.join(REFERENCE, "test/file/local_frame/local_frame.xyz"), key_text="parameters amoeba09\n" + extra,
+                       prm_path=os.path.join(REFERENCE, "test/file/commit_6fe8e913/amoeba09.prm"))
+
+
 def test_polarization_groups_and_scales():
     import tinker_gpu_b200 as tg
     s = tg.load_system(os.path.join(GOLDEN, "water30.npz"))

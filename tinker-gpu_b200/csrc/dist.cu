@@ -561,6 +561,7 @@ struct DxTable {
    volatile unsigned* my_flags;
    int peer_ctas[16];
    unsigned* counters;                             // [16] arrival counters, self-resetting
+   unsigned long long* trace;                      // APX_DX_TRACE: {entry, peers arrived (latest), copies done (latest), all data in} in ns
 };
 
 __device__ __forceinline__ unsigned long long dx_now()
@@ -589,6 +590,8 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
    const bool gate = blockIdx.x == 0 && tid < T.world && ((T.recv_mask >> tid) & 1u);
    if (gate)
       T.peer_flags[tid][DX_FLAG_ARRIVE + T.rank] = T.seq;
+   if (T.trace && blockIdx.x == 0 && tid == 0)
+      T.trace[0] = dx_now();
    if (tid == 0) {
       int k = 0;
       while (k < T.nmsg - 1 && (int)blockIdx.x >= T.m[k].cta0 + T.m[k].nctas)
@@ -598,6 +601,8 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
       if (T.nmsg > 0 && p != T.rank) {
          dx_wait(T.my_flags + DX_FLAG_ARRIVE + p, T.seq);
          __threadfence_system();
+         if (T.trace)
+            atomicMax(T.trace + 1, dx_now());
       }
    }
    __syncthreads();
@@ -605,19 +610,20 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
       const DxMsg& M = T.m[s_msg];
       const int part = (int)blockIdx.x - M.cta0;
       if (M.kind == 0) {
-         const unsigned long long n16 = (unsigned long long)M.chunk16 * M.nchunks;
-         const unsigned long long per = (n16 + M.nctas - 1) / M.nctas;
-         const unsigned long long b0 = per * part, b1 = b0 + per < n16 ? b0 + per : n16;
+         // (messages are far below 64 GB: 32-bit unit counts keep the chunk / offset split a 32-bit division)
+         const unsigned n16 = M.chunk16 * M.nchunks;
+         const unsigned per = (n16 + M.nctas - 1) / M.nctas;
+         const unsigned b0 = per * part, b1 = b0 + per < n16 ? b0 + per : n16;
          const unsigned c16 = M.chunk16;
-         auto src_of = [&](unsigned long long q) {
-            const unsigned long long ch = q / c16;
+         auto src_of = [&](unsigned q) {
+            const unsigned ch = q / c16;
             return reinterpret_cast<const uint4*>(M.src + ch * M.src_stride) + (q - ch * c16);
          };
-         auto dst_of = [&](unsigned long long q) {
-            const unsigned long long ch = q / c16;
+         auto dst_of = [&](unsigned q) {
+            const unsigned ch = q / c16;
             return reinterpret_cast<uint4*>(M.dst + ch * M.dst_stride) + (q - ch * c16);
          };
-         unsigned long long q = b0 + tid;
+         unsigned q = b0 + tid;
          const unsigned bd = blockDim.x;
          for (; q + 3 * bd < b1; q += 4 * bd) {      // four independent 16-byte transfers in flight per thread
             const uint4 v0 = __ldcg(src_of(q)), v1 = __ldcg(src_of(q + bd)), v2 = __ldcg(src_of(q + 2 * bd)), v3 = __ldcg(src_of(q + 3 * bd));
@@ -636,6 +642,8 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
       }
       __threadfence_system();
       __syncthreads();
+      if (T.trace && tid == 0)
+         atomicMax(T.trace + 2, dx_now());
       if (tid == 0 && M.peer != T.rank) {
          const int p = M.peer;
          const unsigned old = atomicInc(&T.counters[p], (unsigned)T.peer_ctas[p] - 1);
@@ -648,6 +656,108 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
    if (gate) {
       dx_wait(T.my_flags + DX_FLAG_READY + tid, T.seq);
       __threadfence_system();
+      if (T.trace)
+         atomicMax(T.trace + 3, dx_now());
+   }
+}
+
+// ---- the same exchange with the bulk-copy engine (TMA) doing the moving: one warp per CTA, whose lane 0 streams 16 KB tiles
+// global -> shared (cp.async.bulk + mbarrier) -> global in the peer's memory (cp.async.bulk.global.shared), four tiles in flight.
+// Measured (tools/probe/p2p_bw.cu, profiles/r02s_p2p_bw.txt): 16 such CTAs already move 18 MB at the 525 GB/s the 256-thread
+// copy loop reaches with 148; in situ the wide CTAs of k_dxchg had to queue behind the resident CTAs of the real-space operator
+// on stream2 (APX_DX_TRACE: the last CTA of a grid-halo exchange started 30 us after the first), a 32-thread CTA with no
+// registers to speak of is scheduled at once and the copy engine does not compete for issue slots.
+#define DXB_TILE 16384
+#define DXB_STAGES 4
+__device__ __forceinline__ unsigned dx_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(32) k_dxchg_bulk(const __grid_constant__ DxTable T)
+{
+   extern __shared__ __align__(128) char dxb_sm[];
+   __shared__ unsigned long long bar[DXB_STAGES];
+   const int tid = threadIdx.x;
+   const bool gate = blockIdx.x == 0 && tid < T.world && ((T.recv_mask >> tid) & 1u);
+   if (gate)
+      T.peer_flags[tid][DX_FLAG_ARRIVE + T.rank] = T.seq;
+   if (T.trace && blockIdx.x == 0 && tid == 0)
+      T.trace[0] = dx_now();
+   if (tid == 0 && T.nmsg > 0) {
+      int k = 0;
+      while (k < T.nmsg - 1 && (int)blockIdx.x >= T.m[k].cta0 + T.m[k].nctas)
+         ++k;
+      const DxMsg& M = T.m[k];
+      const int p = M.peer;
+      for (int s = 0; s < DXB_STAGES; ++s)
+         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(dx_smem(&bar[s])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      if (p != T.rank) {
+         dx_wait(T.my_flags + DX_FLAG_ARRIVE + p, T.seq);
+         __threadfence_system();
+         if (T.trace)
+            atomicMax(T.trace + 1, dx_now());
+      }
+      // tiles of this message: chunk c, tile j of the chunk (the last one of a chunk may be short)
+      const unsigned cbytes = M.chunk16 * 16u;
+      const unsigned tpc = (cbytes + DXB_TILE - 1) / DXB_TILE;
+      const unsigned ntile = tpc * M.nchunks;
+      const unsigned part = blockIdx.x - M.cta0, stride = M.nctas;
+      auto tile_of = [&](unsigned t, const char*& sp, char*& dp, unsigned& nb) {
+         const unsigned ch = t / tpc, j = t - ch * tpc;
+         const unsigned off = j * DXB_TILE;
+         nb = cbytes - off < DXB_TILE ? cbytes - off : DXB_TILE;
+         sp = M.src + ch * M.src_stride + off;
+         dp = M.dst + ch * M.dst_stride + off;
+      };
+      auto load = [&](unsigned t, int s) {
+         const char* sp;
+         char* dp;
+         unsigned nb;
+         tile_of(t, sp, dp, nb);
+         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dx_smem(&bar[s])), "r"(nb) : "memory");
+         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dx_smem(dxb_sm + s * DXB_TILE)),
+            "l"(sp), "r"(nb), "r"(dx_smem(&bar[s])) : "memory");
+      };
+      unsigned phase = 0;      // bit s: parity the next wait on stage s expects
+      unsigned issued = part;
+      for (int s = 0; s < DXB_STAGES && issued < ntile; ++s, issued += stride)
+         load(issued, s);
+      int s = 0;
+      for (unsigned t = part; t < ntile; t += stride) {
+         unsigned done = 0;
+         while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done)
+                         : "r"(dx_smem(&bar[s])), "r"((phase >> s) & 1u) : "memory");
+         phase ^= 1u << s;
+         const char* sp;
+         char* dp;
+         unsigned nb;
+         tile_of(t, sp, dp, nb);
+         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dp), "r"(dx_smem(dxb_sm + s * DXB_TILE)), "r"(nb) : "memory");
+         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+         if (issued < ntile) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the store has read the stage: refill it
+            load(issued, s);
+            issued += stride;
+         }
+         s = s + 1 == DXB_STAGES ? 0 : s + 1;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence_system();
+      if (T.trace)
+         atomicMax(T.trace + 2, dx_now());
+      if (p != T.rank) {
+         const unsigned old = atomicInc(&T.counters[p], (unsigned)T.peer_ctas[p] - 1);
+         if (old == (unsigned)T.peer_ctas[p] - 1) {
+            __threadfence_system();
+            T.peer_flags[p][DX_FLAG_READY + T.rank] = T.seq;
+         }
+      }
+   }
+   __syncwarp();
+   if (gate) {
+      dx_wait(T.my_flags + DX_FLAG_READY + tid, T.seq);
+      __threadfence_system();
+      if (T.trace)
+         atomicMax(T.trace + 3, dx_now());
    }
 }
 
@@ -706,7 +816,12 @@ struct DirectComm : P2pComm {
    char* peer_dmem[16] = {};
    unsigned* dcounters = nullptr;
    unsigned dseq = 0, arseq = 0;
-   int total_ctas = 592;                // CTAs of one exchange kernel, shared out by bytes
+   unsigned long long* trace = nullptr;      // APX_DX_TRACE=1: 4 timestamps per exchange, ring of TRACE_N
+   static constexpr int TRACE_N = 4096;
+   std::vector<int> trace_tag;
+   int bulk = 1;                        // APX_DX_BULK: strided messages through the bulk-copy engine (k_dxchg_bulk)
+   int bulk_ctas = 64;                  // APX_DX_BULK_CTAS: one-warp CTAs of one bulk exchange
+   int total_ctas = 296;                // CTAs of one exchange kernel, shared out by bytes (measured at 2 GPUs: 296 16.6 ms, 592 16.9, 1184 17.2)
    bool dok = false;
    static constexpr size_t FLAG_BYTES = 256;
    static constexpr size_t STAGE_BYTES = (size_t)2 * 16 * DAR_MAX * 8;
@@ -741,6 +856,16 @@ struct DirectComm : P2pComm {
       }
       if (const char* e = getenv("APX_DX_CTAS"))
          total_ctas = std::max(8, std::min(4096, atoi(e)));
+      if (const char* e = getenv("APX_DX_BULK"))
+         bulk = atoi(e);
+      if (const char* e = getenv("APX_DX_BULK_CTAS"))
+         bulk_ctas = std::max(2, std::min(1024, atoi(e)));
+      CUDA_CHECK(cudaFuncSetAttribute(k_dxchg_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, DXB_STAGES * DXB_TILE));
+      if (getenv("APX_DX_TRACE") && atoi(getenv("APX_DX_TRACE"))) {
+         CUDA_CHECK(cudaMalloc(&trace, sizeof(unsigned long long) * 4 * TRACE_N));
+         CUDA_CHECK(cudaMemset(trace, 0, sizeof(unsigned long long) * 4 * TRACE_N));
+         trace_tag.assign(TRACE_N, -1);
+      }
       dok = true;
    }
    ~DirectComm() override
@@ -748,6 +873,8 @@ struct DirectComm : P2pComm {
       if (!dok)
          return;
       cudaDeviceSynchronize();
+      if (trace)
+         dump_trace();
       for (int r = 0; r < world; ++r) {
          if (r == rank)
             continue;
@@ -764,6 +891,32 @@ struct DirectComm : P2pComm {
       }
       cudaFree(dmem);
       cudaFree(dcounters);
+   }
+
+   // per kind of exchange (tag): mean us from kernel entry to "every peer has arrived", to "my copies are done", to "all data in"
+   void dump_trace()
+   {
+      std::vector<unsigned long long> h(4 * (size_t)TRACE_N);
+      if (cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+         return;
+      static const char* names[] = {"per-atom halo", "grid halo (forward)", "transpose (forward)", "transpose (inverse)", "grid halo (inverse)"};
+      for (int tag = 0; tag < 5; ++tag) {
+         double a = 0, b = 0, d = 0;
+         int m = 0;
+         const int last = (int)std::min<unsigned>(dseq, TRACE_N);
+         for (int k = last / 2; k < last; ++k) {      // second half of the record: warm
+            if (trace_tag[k] != tag || !h[4 * k] || !h[4 * k + 3])
+               continue;
+            const double t0 = (double)h[4 * k];
+            a += (h[4 * k + 1] ? (double)h[4 * k + 1] - t0 : 0), b += (double)h[4 * k + 2] - t0, d += (double)h[4 * k + 3] - t0;
+            ++m;
+         }
+         if (m)
+            fprintf(stderr, "[apx dx trace] rank %d %-20s n=%4d  peers arrived +%6.1f us  copies done +%6.1f us  all data in +%6.1f us\n", rank,
+               names[tag], m, 1e-3 * a / m, 1e-3 * b / m, 1e-3 * d / m);
+      }
+      cudaFree(trace);
+      trace = nullptr;
    }
 
    // collective: (re)register the allocations behind `wanted`; mappings of allocations no region uses any more are closed
@@ -848,7 +1001,7 @@ struct DirectComm : P2pComm {
       size_t chunk_bytes, nchunks, src_stride, dst_stride;
       const int* idx = nullptr;      // per-atom scatter (nchunks atoms of 32 bytes) when set
    };
-   void xchg(const std::vector<Msg>& msgs, unsigned recv_mask, cudaStream_t st)
+   void xchg(const std::vector<Msg>& msgs, unsigned recv_mask, cudaStream_t st, int tag = 0)
    {
       if (dirty)
          sync_regions();
@@ -860,8 +1013,13 @@ struct DirectComm : P2pComm {
       DxTable T;
       memset(&T, 0, sizeof(T));
       size_t total = 0;
-      for (const Msg& m : msgs)
+      bool strided = !msgs.empty();
+      for (const Msg& m : msgs) {
          total += m.idx ? m.nchunks * 32 : m.chunk_bytes * m.nchunks;
+         strided = strided && !m.idx;
+      }
+      const bool use_bulk = bulk && strided;
+      const size_t budget = use_bulk ? (size_t)bulk_ctas : (size_t)total_ctas;
       int grid = 0;
       for (const Msg& m : msgs) {
          DxMsg& M = T.m[T.nmsg++];
@@ -869,6 +1027,8 @@ struct DirectComm : P2pComm {
          M.src = static_cast<const char*>(m.src);
          M.dst = m.peer == rank ? static_cast<char*>(m.dst) : remote(m.dst, m.peer);
          M.src_stride = m.src_stride, M.dst_stride = m.dst_stride;
+         if (!m.idx && bytes / 16 >= 0xffffffffull)
+            APX_THROW("direct transport: message too large");
          if (!m.idx && (m.chunk_bytes % 16 || m.src_stride % 16 || m.dst_stride % 16 || ((uintptr_t)M.src | (uintptr_t)M.dst) % 16))
             APX_THROW("direct transport: messages must be 16-byte aligned");
          M.chunk16 = (unsigned)(m.chunk_bytes / 16);
@@ -877,7 +1037,8 @@ struct DirectComm : P2pComm {
          M.kind = m.idx ? 1 : 0;
          M.peer = m.peer;
          M.cta0 = grid;
-         M.nctas = (int)std::max<size_t>(1, std::min<size_t>((size_t)total_ctas * bytes / std::max<size_t>(total, 1), bytes / 16384 + 1));
+         const size_t gran = use_bulk ? (size_t)DXB_TILE * DXB_STAGES : 16384;
+         M.nctas = (int)std::max<size_t>(1, std::min<size_t>(budget * bytes / std::max<size_t>(total, 1), bytes / gran + 1));
          grid += M.nctas;
          T.peer_ctas[m.peer] += M.nctas;
       }
@@ -886,7 +1047,14 @@ struct DirectComm : P2pComm {
          T.peer_flags[p] = reinterpret_cast<volatile unsigned*>(peer_dmem[p]);
       T.my_flags = reinterpret_cast<volatile unsigned*>(dmem);
       T.counters = dcounters;
-      k_dxchg<<<std::max(grid, 1), 256, 0, st>>>(T);
+      if (trace && dseq <= (unsigned)TRACE_N) {
+         T.trace = trace + 4 * (size_t)(dseq - 1);
+         trace_tag[dseq - 1] = tag;
+      }
+      if (use_bulk)
+         k_dxchg_bulk<<<std::max(grid, 1), 32, DXB_STAGES * DXB_TILE, st>>>(T);
+      else
+         k_dxchg<<<std::max(grid, 1), 256, 0, st>>>(T);
    }
 
    void allreduce(void* p, size_t n, int dtype, cudaStream_t st) override
@@ -1408,7 +1576,7 @@ void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
       const size_t pb = plane * sizeof(cplx);
       std::vector<DirectComm::Msg> h = {{prev, g, D.hbuf.p, D.hl * pb, 1, 0, 0},
          {next, g + (size_t)(D.hl + D.pz) * plane, D.hbuf.p + D.hl * plane, D.hu * pb, 1, 0, 0}};
-      dc->xchg(h, (1u << prev) | (1u << next), st);
+      dc->xchg(h, (1u << prev) | (1u << next), st, 1);
       const size_t m1 = D.hl * plane, m2 = D.hu * plane;
       k_grid_add2<<<(unsigned)((m1 + m2 + 255) / 256), 256, 0, st>>>(m1, D.hbuf.p, g + (size_t)D.pz * plane, m2, D.hbuf.p + D.hl * plane,
          g + (size_t)D.hl * plane);
@@ -1422,7 +1590,7 @@ void apx_dist_fft_forward(apx_ctx* c, cplx* tb)
          const int r = (D.rank + q) % G;      // my own block first, then the peers in ring order: no two ranks start on the same target
          t.push_back({r, mine + (size_t)r * D.py * n1, tb + (size_t)D.rank * blk, chunk, (size_t)D.pz, pb, chunk});
       }
-      dc->xchg(t, (1u << G) - 1u, st);
+      dc->xchg(t, (1u << G) - 1u, st, 2);
       exec_fft(D.plan1d, tb, CUFFT_FORWARD);
       c->stats.kernel_launches += 6;
       apx_dist_prof_end(c, pslot, st);
@@ -1475,12 +1643,12 @@ void apx_dist_fft_inverse(apx_ctx* c, cplx* tb)
          const int r = (D.rank + q) % G;
          t.push_back({r, tb + (size_t)r * blk, mine + (size_t)D.rank * D.py * n1, chunk, (size_t)D.pz, chunk, pb});
       }
-      dc->xchg(t, (1u << G) - 1u, st);
+      dc->xchg(t, (1u << G) - 1u, st, 3);
       exec_fft(D.plan2d, mine, CUFFT_INVERSE);
       // my top hl planes are the low halo of the next slab, my bottom hu planes the high halo of the previous one
       std::vector<DirectComm::Msg> h = {{next, g + (size_t)D.pz * plane, g, D.hl * pb, 1, 0, 0},
          {prev, mine, g + (size_t)(D.hl + D.pz) * plane, D.hu * pb, 1, 0, 0}};
-      dc->xchg(h, (1u << prev) | (1u << next), st);
+      dc->xchg(h, (1u << prev) | (1u << next), st, 4);
       c->stats.kernel_launches += 5;
       apx_dist_prof_end(c, pslot, st);
       return;

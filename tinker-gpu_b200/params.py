@@ -547,9 +547,18 @@ def build_system(xyz: XYZ, key: KeyFile, ff: ForceField) -> System:
         c = key.get_float("C-AXIS", 0.0) or a
         al, be, ga = key.get_float("ALPHA", 90.0), key.get_float("BETA", 90.0), key.get_float("GAMMA", 90.0)
     use_bounds = a > 0
+    # Cells this library does not implement are REFUSED rather than silently run as something else: the
+    # truncated octahedron / rhombic dodecahedron images (include/ff/image.h:49-65,126; pmeConv's expterm = 0 for odd k1+k2+k3,
+    # src/cu/pme.cu:966-969) and non-periodic Ewald (the 1 - cos(pi L sqrt(hsq)) factor of the same kernel).
+    for word in ("OCTAHEDRON", "DODECAHEDRON"):
+        if khas(word):
+            raise ValueError(f"{word} cells are not supported (orthogonal, monoclinic and triclinic cells are)")
 
     # --- cutoffs.f / kewald.f
     use_ewald = khas("EWALD")
+    if use_ewald and not use_bounds:
+        raise ValueError("EWALD without a periodic cell (A-AXIS ...) is not supported: the reference's non-periodic Ewald "
+                         "correction (src/cu/pme.cu:966-969) is not implemented")
     use_list = khas("NEIGHBOR-LIST") or khas("MPOLE-LIST")
     ewaldcut = 7.0
     mpolecut = 9.0 if use_bounds else 1.0e12
