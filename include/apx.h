@@ -316,6 +316,11 @@ int apx_pme_uind_fphi(apx_ctx* ctx, const double* uind, const double* uinp, doub
    apx_set_native_fft(ctx, 0) forces cuFFT instead of the fused 64^3 kernels (fft64.cu). */
 int apx_pme_convolve_grid(apx_ctx* ctx, const double* grid_in, double* grid_out);
 int apx_set_native_fft(apx_ctx* ctx, int on);
+/* Deterministic PME spreading: charge / dipole contributions are summed onto the grid as 2^32 fixed-point integers (64-bit
+ * integer reductions, order independent) instead of float reductions; results are then bit-reproducible from run to run.
+ * Off by default (the float vector reductions are ~3x cheaper; the reference's spreading, src/cu/pme.cu:14-255, is float
+ * atomics as well).  APX_PME_FIXED=1 in the environment turns it on for every context. */
+int apx_set_pme_fixed_point(apx_ctx* ctx, int on);
 
 int apx_get_stats(apx_ctx* ctx, apx_stats* out);
 int apx_stats_reset(apx_ctx* ctx);

@@ -357,3 +357,35 @@ def test_device_pointer_entry_points(dtype):
     a.add_scalars_dev(eb, [r["esum"]])
     assert abs(eb[0].item() / 2.0 ** 32 - 5.0 - r["esum"]) < 1e-8 * abs(r["esum"]) and eb[1].item() == 5 << 32
     a.close()
+
+
+def test_fixed_point_spreading_is_deterministic_and_agrees():
+    """Deterministic PME spreading (apx_set_pme_fixed_point; north star: "fixed-point atomics for spreading onto the PME
+    grid"): contributions summed as 2^32 fixed-point integers.  (1) the operators that consist of one spread -> FFT -> gather
+    round trip plus the fixed-order row kernels -- ufield() -- must return the SAME BITS on every call, on a fresh context
+    too; (2) energy, gradient and induced dipoles must agree with the float-reduction path well inside the north-star
+    tolerances (the rounding step is 2.3e-10 per contribution)."""
+    import tinker_gpu_b200 as tg
+    from tinker_gpu_b200.amoeba import calc
+    s = tg.load_system(os.path.join(GOLDEN, "water30.npz"))
+    a = _amoeba(s, "mixed")
+    r0 = a.energy(calc.v1)
+    u0, p0 = a.uind()
+    a.set_pme_fixed_point(True)
+    r1 = a.energy(calc.v1)
+    u1, p1 = a.uind()
+    assert abs(r1["esum"] - r0["esum"]) < 1e-7 * abs(r0["esum"])
+    assert _rms(r1["grad"] - r0["grad"]) < 2e-6
+    assert _rms(u1 - u0) * DEBYE < 1e-7
+    assert r1["pcg_iterations"] == r0["pcg_iterations"]
+    # ufield(): spread -> FFT -> gather plus the fixed-order row kernels.  (dfield() also runs the exclusion pass, whose few
+    # float corrections per atom are added atomically: reproducible only to the last bit or two, so it is not asserted here.)
+    fields = [a.ufield(u0, p0) for _ in range(3)]
+    a.close()
+    b = _amoeba(s, "mixed")
+    b.set_pme_fixed_point(True)
+    b.induce()
+    fields.append(b.ufield(u0, p0))
+    b.close()
+    for f in fields[1:]:
+        assert np.array_equal(f[0], fields[0][0]) and np.array_equal(f[1], fields[0][1])

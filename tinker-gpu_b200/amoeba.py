@@ -193,7 +193,7 @@ def load_library(precision="mixed"):
         "apx_energy": [C.c_int, C.POINTER(EnergyResult)], "apx_empole": [C.c_int, C.POINTER(EnergyResult)],
         "apx_epolar": [C.c_int, C.POINTER(EnergyResult)], "apx_get_gradient": [_DP],
         "apx_pme_mpole_fphi": [_DP], "apx_pme_uind_fphi": [_DP, _DP, _DP, _DP],
-        "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int],
+        "apx_pme_convolve_grid": [_DP, _DP], "apx_set_native_fft": [C.c_int], "apx_set_pme_fixed_point": [C.c_int],
         "apx_get_stats": [C.POINTER(Stats)], "apx_stats_reset": [], "apx_synchronize": [],
         "apx_get_dist_info": [C.POINTER(C.c_int)],
         "apx_vdw_attach": [C.POINTER(_ApxVdw)], "apx_evdw": [C.c_int, C.POINTER(EnergyResult)],
@@ -607,6 +607,10 @@ class Amoeba:
 
     def set_native_fft(self, on):
         self._chk(self.lib.apx_set_native_fft(self.ctx, int(bool(on))))
+
+    def set_pme_fixed_point(self, on):
+        """Deterministic PME spreading (64-bit fixed-point integer sums on the grid); see include/apx.h."""
+        self._chk(self.lib.apx_set_pme_fixed_point(self.ctx, int(bool(on))))
 
     def stats(self):
         s = Stats()

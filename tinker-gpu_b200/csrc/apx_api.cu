@@ -205,6 +205,8 @@ static void create_impl(const apx_system* sys, int device, int rank, int world, 
    memset(&c->stats, 0, sizeof(c->stats));
    c->stats.npairs_m = -1;
    c->f_elec = (real)(sys->electric / sys->dielec);
+   if (const char* e = getenv("APX_PME_FIXED"))
+      c->pme_fixed = atoi(e) ? 1 : 0;
    if (const char* e = getenv("APX_NO_NATIVE_FFT"))
       c->native_fft = atoi(e) ? 0 : 1;
    if (const char* e = getenv("APX_ROWS_ONEPASS"))
@@ -414,6 +416,7 @@ void apx_destroy(apx_ctx* c)
    c->rows.cnt.release(), c->rows.cntu.release(), c->rows.total.release();
    c->grp.vjb.release(), c->grp.nvjb.release(), c->grp.ajb.release(), c->grp.najb.release(), c->grp.vslot.release(), c->grp.nbr16.release(),
       c->grp.oflow.release();
+   c->qfix.release();
    c->qgrid.release(), c->qgrid2.release(), c->gx.release(), c->gy.release(), c->gz.release(), c->trqf.release();
    c->ebuf.release(), c->dbuf.release(), c->cnt.release(), c->io_a.release(), c->io_b.release(), c->io_c.release(), c->io_d.release();
    c->theta.release(), c->pk_p.release(), c->pk_r.release(), c->pk_z.release(), c->pk_v.release(), c->pk_f.release();
@@ -799,6 +802,18 @@ int apx_set_native_fft(apx_ctx* c, int on)
    API_BEGIN
    c->native_fft = on ? 1 : 0;
    apx_pcg_graphs_invalidate(c);
+   API_END
+}
+
+int apx_set_pme_fixed_point(apx_ctx* c, int on)
+{
+   API_BEGIN
+   CUDA_CHECK(cudaSetDevice(c->device));
+   CUDA_CHECK(cudaStreamSynchronize(c->stream));
+   c->pme_fixed = on ? 1 : 0;
+   if (c->pme_fixed)
+      apx_pme_fixed_setup(c);
+   apx_pcg_graphs_invalidate(c);      // the captured launch sequences contain (or lack) the conversion kernel
    API_END
 }
 

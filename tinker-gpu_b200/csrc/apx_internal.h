@@ -272,6 +272,8 @@ struct apx_ctx {
    DevBuf<real> field, fieldp, udir, udirp, uind, uinp;
    DevBuf<real> field_rs;                // real-space part of the permanent field while the PME part is computed beside it
    DevBuf<real> rsd, rsdp, zrsd, zrsdp, conj, conjp, vec, vecp;
+   DevBuf<long long> qfix;      // deterministic spreading: fixed-point shadow of qgrid, two int64 per point (pme.cu)
+   int pme_fixed = 0;
    DevBuf<real4> pk_p, pk_r, pk_z, pk_v, pk_f;   // packed (d,p) pairs, dp.cuh: direction, residual, M r, A p, real-space field
    DevBuf<real4> uf_rec;                 // [npad][3] interleaved neighbour records of the ufield rows (field.cu)
    int rows_onepass = 1;                 // APX_ROWS_ONEPASS: 1 = one-pass list rebuild with padded rows (default), 2 = the same with zero slack
@@ -389,6 +391,7 @@ void apx_list_refresh(apx_ctx* c, bool force, int known_moved = -1);
 void apx_list_check_enqueue(apx_ctx* c, cudaStream_t st, double* seq = nullptr);
 void apx_update_sorted_positions(apx_ctx* c);
 // ---- dist.cu
+void apx_pme_fixed_setup(apx_ctx* c);                              // shadow grid of the deterministic spreading mode
 void apx_dist_after_sort(apx_ctx* c);                              // ownership bounds + halo plan (at list rebuild)
 void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st);         // V[halo atoms] <- owners' values
 void apx_dist_allreduce_f64(apx_ctx* c, double* p, size_t n);

@@ -549,7 +549,7 @@ struct DxMsg {
    unsigned long long src_stride, dst_stride;      // bytes between consecutive chunks
    unsigned chunk16;                               // kind 0: 16-byte units per chunk
    unsigned nchunks;                               // kind 0: chunks; kind 1: atoms
-   const int* idx;                                 // kind 1: 32-byte items at 32 * idx[j] on both sides
+   const int* idx;                                 // kind 1: items of chunk16 units at item index idx[j] on both sides
    int peer, cta0, nctas, kind;
 };
 struct DxTable {
@@ -632,11 +632,13 @@ __global__ void __launch_bounds__(256) k_dxchg(const __grid_constant__ DxTable T
          for (; q < b1; q += bd)
             *dst_of(q) = __ldcg(src_of(q));
       } else {
-         const unsigned n2 = 2u * M.nchunks;           // two 16-byte halves per atom
+         const unsigned c16 = M.chunk16;               // 16-byte units per atom: 2 (mixed build) or 4 (double build)
+         const unsigned n2 = c16 * M.nchunks;
          const unsigned per = (n2 + M.nctas - 1) / M.nctas;
          const unsigned b0 = per * part, b1 = b0 + per < n2 ? b0 + per : n2;
          for (unsigned q = b0 + tid; q < b1; q += blockDim.x) {
-            const size_t o = 2 * (size_t)M.idx[q >> 1] + (q & 1u);
+            const unsigned a = q / c16;
+            const size_t o = (size_t)c16 * M.idx[a] + (q - a * c16);
             reinterpret_cast<uint4*>(M.dst)[o] = __ldcg(reinterpret_cast<const uint4*>(M.src) + o);
          }
       }
@@ -999,7 +1001,7 @@ struct DirectComm : P2pComm {
       const void* src;
       void* dst;
       size_t chunk_bytes, nchunks, src_stride, dst_stride;
-      const int* idx = nullptr;      // per-atom scatter (nchunks atoms of 32 bytes) when set
+      const int* idx = nullptr;      // per-atom scatter (nchunks atoms of chunk_bytes each) when set
    };
    void xchg(const std::vector<Msg>& msgs, unsigned recv_mask, cudaStream_t st, int tag = 0)
    {
@@ -1015,7 +1017,7 @@ struct DirectComm : P2pComm {
       size_t total = 0;
       bool strided = !msgs.empty();
       for (const Msg& m : msgs) {
-         total += m.idx ? m.nchunks * 32 : m.chunk_bytes * m.nchunks;
+         total += m.chunk_bytes * m.nchunks;
          strided = strided && !m.idx;
       }
       const bool use_bulk = bulk && strided;
@@ -1023,7 +1025,7 @@ struct DirectComm : P2pComm {
       int grid = 0;
       for (const Msg& m : msgs) {
          DxMsg& M = T.m[T.nmsg++];
-         const size_t bytes = m.idx ? m.nchunks * 32 : m.chunk_bytes * m.nchunks;
+         const size_t bytes = m.chunk_bytes * m.nchunks;
          M.src = static_cast<const char*>(m.src);
          M.dst = m.peer == rank ? static_cast<char*>(m.dst) : remote(m.dst, m.peer);
          M.src_stride = m.src_stride, M.dst_stride = m.dst_stride;
@@ -1444,7 +1446,7 @@ void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st)
       unsigned recv_mask = 0;
       for (int r = 0; r < G; ++r) {
          if (D.send_off[r + 1] > D.send_off[r]) {
-            DirectComm::Msg m{r, V, V, 32, (size_t)(D.send_off[r + 1] - D.send_off[r]), 0, 0};
+            DirectComm::Msg m{r, V, V, 2 * sizeof(real4), (size_t)(D.send_off[r + 1] - D.send_off[r]), 0, 0};
             m.idx = D.send_idx.p + D.send_off[r];
             msgs.push_back(m);
          }

@@ -160,9 +160,38 @@ __device__ __forceinline__ int zlocal(int i, int n3, int zbase)
 }
 
 // --- spread ------------------------------------------------------------------------------------
+// Deterministic spreading (apx_set_pme_fixed_point, APX_PME_FIXED=1): the contributions are rounded to fixed point
+// (2^32 per unit in the mixed build, 2^40 in the double build) and summed with 64-bit INTEGER reductions into a shadow grid of
+// two int64 per point, which k_fix_to_grid converts into the float grid the FFT reads (and zeroes again).  Integer sums do
+// not depend on the order in which the atoms arrive, so the grid -- and with the fixed lane order of the gathers and the row
+// kernels everything computed from it -- is bit-reproducible from run to run; the float / vector reductions of the default
+// path are not (neither are the reference's, src/cu/pme.cu:14-255).  Cost: four 8-byte reductions where the default path
+// issues one 16-byte vector reduction.
+#ifdef APX_DOUBLE
+#define PME_FIX_SCALE 1099511627776.0      // 2^40
+#else
+#define PME_FIX_SCALE 4294967296.0         // 2^32
+#endif
+__device__ __forceinline__ void fix_add(long long* __restrict__ fix, size_t word, real v)
+{
+   atomicAdd(reinterpret_cast<unsigned long long*>(fix) + word, (unsigned long long)__double2ll_rn((double)v * PME_FIX_SCALE));
+}
+__global__ void k_fix_to_grid(size_t n, long long* __restrict__ fix, cplx* __restrict__ grid)
+{
+   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   longlong2 v = reinterpret_cast<longlong2*>(fix)[i];
+   reinterpret_cast<longlong2*>(fix)[i] = make_longlong2(0, 0);
+   cplx g;
+   g.x = (real)((double)v.x * (1.0 / PME_FIX_SCALE));
+   g.y = (real)((double)v.y * (1.0 / PME_FIX_SCALE));
+   grid[i] = g;
+}
+
 __global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
    const real4* __restrict__ theta, const real4* __restrict__ mp0, const real4* __restrict__ mp1, const real2* __restrict__ mp2,
-   real* __restrict__ fmp_out, cplx* __restrict__ grid)
+   real* __restrict__ fmp_out, cplx* __restrict__ grid, long long* __restrict__ fix)
 {
    __shared__ __align__(16) real sth[4][3][5][4];
    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -205,8 +234,13 @@ __global__ void __launch_bounds__(128) k_spread_mpole(int n, Xform X, int n1, in
       const real val = fm[0] * t0 * u0 * v0 + fm[1] * t1 * u0 * v0 + fm[2] * t0 * u1 * v0 + fm[3] * t0 * u0 * v1 + fm[4] * t2 * u0 * v0
          + fm[5] * t0 * u2 * v0 + fm[6] * t0 * u0 * v2 + fm[7] * t1 * u1 * v0 + fm[8] * t1 * u0 * v1 + fm[9] * t0 * u1 * v1;
       const int zl = zlocal(st.i3 + iz, n3, zbase);
-      if (zl < nzl)
-         atomicAdd(&grid[((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)].x, val);
+      if (zl < nzl) {
+         const size_t at = ((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1);
+         if (fix)
+            fix_add(fix, 2 * at, val);
+         else
+            atomicAdd(&grid[at].x, val);
+      }
    }
 }
 
@@ -250,7 +284,7 @@ __device__ __forceinline__ Stencil load_stencil_lg(const real4* __restrict__ the
 template <int LG>
 __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
    const real4* __restrict__ theta,
-   const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
+   const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip, long long* __restrict__ fix)
 {
    if (skip && skip[1])
       return;
@@ -283,6 +317,11 @@ __global__ void __launch_bounds__(128) k_spread_dp(int n, Xform X, int n1, int n
       if (zl >= nzl)
          continue;
       cplx* g = &grid[((size_t)zl * n2 + wrapi(st.i2 + iy, n2)) * n1 + wrapi(st.i1 + ix, n1)];
+      if (fix) {
+         fix_add(fix, 2 * (size_t)(g - grid), vd);
+         fix_add(fix, 2 * (size_t)(g - grid) + 1, vp);
+         continue;
+      }
 #ifdef APX_DOUBLE
       atomicAdd(&g->x, vd);
       atomicAdd(&g->y, vp);
@@ -342,7 +381,8 @@ __device__ __forceinline__ void stencil_fill(const pos_t pos, int l, int n1, int
 
 template <int LG>
 __global__ void __launch_bounds__(128) k_spread_dp2(int n, Xform X, int n1, int n2, int n3, int zbase, int nzl,
-   const pos_t* __restrict__ posq, const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip)
+   const pos_t* __restrict__ posq, const real4* __restrict__ U, cplx* __restrict__ grid, const int* __restrict__ skip,
+   long long* __restrict__ fix)
 {
    if (skip && skip[1])
       return;
@@ -387,6 +427,11 @@ __global__ void __launch_bounds__(128) k_spread_dp2(int n, Xform X, int n1, int 
       int x = x0 + 2 * pr;
       x = x >= n1 ? x - n1 : x;
       cplx* g = &grid[((size_t)zl * n2 + wrapi(i2 + iy, n2)) * n1 + x];
+      if (fix) {
+         const size_t w = 2 * (size_t)(g - grid);
+         fix_add(fix, w, val.x), fix_add(fix, w + 1, val.y), fix_add(fix, w + 2, val.z), fix_add(fix, w + 3, val.w);
+         continue;
+      }
       asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(g), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w) : "memory");
    }
 }
@@ -993,6 +1038,8 @@ void apx_pme_setup(apx_ctx* c)
       apx_fft64_setup(c);
    }
    c->qgrid.ensure(nlocal(c));
+   if (c->pme_fixed)
+      apx_pme_fixed_setup(c);
    c->qfac.ensure(nconv(c));
    int nf[3] = {c->nfft1, c->nfft2, c->nfft3};
    DevBuf<real>* bs[3] = {&c->bsmod1, &c->bsmod2, &c->bsmod3};
@@ -1009,6 +1056,17 @@ void apx_pme_setup(apx_ctx* c)
    k_make_qfac<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->qy0, c->qny, c->box, (real)pterm,
       (real)volterm, c->bsmod1, c->bsmod2, c->bsmod3, c->qfac);
    APX_COUNT_LAUNCH(c);
+}
+
+void apx_pme_fixed_setup(apx_ctx* c)
+{
+   if (!c->opt.use_ewald)
+      return;
+   const size_t K = nlocal(c);
+   if (c->qfix.cap < 2 * K) {
+      c->qfix.ensure(2 * K);
+      CUDA_CHECK(cudaMemsetAsync(c->qfix.p, 0, c->qfix.cap * sizeof(long long), c->stream));
+   }
 }
 
 // spline tables of the current positions (owned atoms); called whenever posd changes (nblist.cu)
@@ -1063,6 +1121,19 @@ static void fft_inverse(apx_ctx* c)
       fft(c, CUFFT_INVERSE);
 }
 
+// fixed-point shadow grid of the deterministic spreading mode (nullptr: float reductions straight into qgrid)
+static inline long long* pme_fix(apx_ctx* c) { return c->pme_fixed ? c->qfix.p : nullptr; }
+// shadow grid -> qgrid (assigns every point of the local planes, zeroes the shadow grid for the next spread); the solver's
+// kernels that return early once converged (skip flag) leave the shadow grid zero, so this stays idempotent
+static inline void pme_fix_flush(apx_ctx* c)
+{
+   if (!c->pme_fixed)
+      return;
+   const size_t K = nlocal(c);
+   k_fix_to_grid<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(K, c->qfix.p, c->qgrid.p);
+   APX_COUNT_LAUNCH(c);
+}
+
 // permanent multipoles: fills fmp, fphi and ASSIGNS field = recip + self part of dfield.
 // dbuf[16] = recip |Q|^2 energy, dbuf[17..22] = its virial (vir_m) when want_ev.
 void apx_pme_mpole(apx_ctx* c, bool want_ev)
@@ -1072,8 +1143,9 @@ void apx_pme_mpole(apx_ctx* c, bool want_ev)
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
    if (no > 0)
       k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
-         c->mp0 + a0, c->mp1 + a0, c->mp2 + a0, c->fmp + 10 * (size_t)a0, c->qgrid);
+         c->mp0 + a0, c->mp1 + a0, c->mp2 + a0, c->fmp + 10 * (size_t)a0, c->qgrid, pme_fix(c));
    APX_COUNT_LAUNCH(c);
+   pme_fix_flush(c);
    fft_forward(c);
    if (want_ev)
       CUDA_CHECK(cudaMemsetAsync(c->dbuf.p + 16, 0, 7 * sizeof(double), c->stream));
@@ -1101,15 +1173,17 @@ void apx_pme_spread_dp(apx_ctx* c, const real4* U)
 #ifndef APX_DOUBLE
    if (no > 0 && pme_gen2(c)) {
       k_spread_dp2<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
-         c->posq + a0, U + 2 * (size_t)a0, c->qgrid, c->skip);
+         c->posq + a0, U + 2 * (size_t)a0, c->qgrid, c->skip, pme_fix(c));
       APX_COUNT_LAUNCH(c);
+      pme_fix_flush(c);
       return;
    }
 #endif
    if (no > 0)
       k_spread_dp<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
-         c->theta + 16 * (size_t)a0, U + 2 * (size_t)a0, c->qgrid, c->skip);
+         c->theta + 16 * (size_t)a0, U + 2 * (size_t)a0, c->qgrid, c->skip, pme_fix(c));
    APX_COUNT_LAUNCH(c);
+   pme_fix_flush(c);
 }
 
 // forward FFT, influence function, inverse FFT
@@ -1168,8 +1242,9 @@ void apx_pme_uind_fphi(apx_ctx* c, const real* ud, const real* up, bool)
    apx_pack_dp(c, ud, up, c->pk_p);
    if (no > 0)
       k_spread_dp<PME_LG><<<(no + PME_APB - 1) / PME_APB, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl,
-         c->theta + 16 * (size_t)a0, c->pk_p + 2 * (size_t)a0, c->qgrid, nullptr);
+         c->theta + 16 * (size_t)a0, c->pk_p + 2 * (size_t)a0, c->qgrid, nullptr, pme_fix(c));
    APX_COUNT_LAUNCH(c);
+   pme_fix_flush(c);
    apx_pme_convolve(c);
    if (no > 0)
       k_gather<2><<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, selfterm(c),
@@ -1190,13 +1265,15 @@ void apx_pme_cross_virial(apx_ctx* c, real4* mpa, real4* mpb, double* out6)
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
    if (no > 0)
       k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
-         mpa + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid);
+         mpa + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid, pme_fix(c));
+   pme_fix_flush(c);
    fft_forward(c);
    CUDA_CHECK(cudaMemcpyAsync(second.p, conv_grid(c), K * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
    CUDA_CHECK(cudaMemsetAsync(c->qgrid.p, 0, nlocal(c) * sizeof(cplx), c->stream));
    if (no > 0)
       k_spread_mpole<<<(no + 3) / 4, 128, 0, c->stream>>>(no, X, c->nfft1, c->nfft2, c->nfft3, c->zbase, c->nzl, c->theta + 16 * (size_t)a0,
-         mpb + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid);
+         mpb + a0, c->mp1 + a0, c->mp2 + a0, nullptr, c->qgrid, pme_fix(c));
+   pme_fix_flush(c);
    fft_forward(c);
    double pterm = (M_PI / c->opt.aewald) * (M_PI / c->opt.aewald);
    k_cross_virial<<<(unsigned)((K + 255) / 256), 256, 0, c->stream>>>(c->nfft1, c->nfft2, c->nfft3, c->qy0, c->qny, c->box, (real)pterm,
