@@ -60,11 +60,10 @@ def _cuda_check(name, precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="added after the round-1 GPU budget was spent: first GPU run pending", strict=False)
 @pytest.mark.parametrize("precision", ["mixed", "double"])
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_path_reproduces_the_polpair_transcripts(name, precision):
-    """In a child process until it has run once on a GPU (a two-atom electrostatics context is new to the library)."""
+    """In a child process (a two-atom electrostatics context; green on the B200 since round 2, profiles/r02v_tests.log)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
