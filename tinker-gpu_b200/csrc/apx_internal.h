@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <functional>
 #include <map>
 #include <vector>
 
@@ -345,6 +346,9 @@ struct apx_ctx {
    int uf_ext_iter = 0;            // capture of a batch: the operator launch being enqueued gets external timing events (slots 2,3)
    int uf_iter_timed = 0;          // the batch graph launched by this solve carries them
    int vdw_fork_vers = -1;         // >= 0: energy() wants apx_induce_impl to fork the vdW stream after its prologue (mplar.cu)
+   std::function<void()> epi_tail;     // md.cu: closing half-kick + thermostat, enqueued inside the energy epilogue's IF body (mplar.cu)
+   int induce_copy_pending = 0;    // an unawaited solver batch left its flags on the device: apx_induce_copy_out
+   int epi_tail_ran = 0;           // the last epilogue launch contained (or replayed a graph that contains) epi_tail
    int epend_deferred = 0;         // energy_once stage 1 -> 2: the solve of the pending evaluation was deferred
    int induce_iter_launched = 0;   // iterations enqueued by the deferred first batch
    int induce_pending = 0, induce_pending_predict = 0;      // a deferred solve awaits apx_induce_finish
@@ -391,6 +395,7 @@ void apx_list_refresh(apx_ctx* c, bool force, int known_moved = -1);
 void apx_list_check_enqueue(apx_ctx* c, cudaStream_t st, double* seq = nullptr);
 void apx_update_sorted_positions(apx_ctx* c);
 // ---- dist.cu
+void apx_induce_copy_out(apx_ctx* c);                              // flags of an unawaited solver batch -> pinned memory
 void apx_pme_fixed_setup(apx_ctx* c);                              // shadow grid of the deterministic spreading mode
 void apx_dist_after_sort(apx_ctx* c);                              // ownership bounds + halo plan (at list rebuild)
 void apx_dist_halo(apx_ctx* c, real4* V, cudaStream_t st);         // V[halo atoms] <- owners' values
@@ -409,7 +414,8 @@ void apx_dist_prof_end(apx_ctx* c, int slot, cudaStream_t st);
 void apx_vdw_attach_impl(apx_ctx* c, const apx_vdw* v);
 void apx_vdw_refresh(apx_ctx* c, bool rebuilt);                    // reduced sites (every step), rows (at list rebuild)
 void apx_vdw_launch(apx_ctx* c, int vers);                         // enqueue ehal on the vdW stream (forked from the main stream)
-void apx_vdw_join(apx_ctx* c);                                     // main stream waits for it
+void apx_vdw_join(apx_ctx* c, bool copies = true);                 // main stream waits for it (+ its scalars -> pinned memory)
+void apx_vdw_copy_out(apx_ctx* c);
 void apx_vdw_collect(apx_ctx* c, int vers, apx_energy_result* r);  // after the main stream is synchronised: ev, nev, virial into r
 void apx_vdw_destroy(apx_ctx* c);
 void apx_block_boxes(apx_ctx* c, const real4* pos, real4* ctr, real4* ext);

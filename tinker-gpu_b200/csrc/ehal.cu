@@ -524,7 +524,8 @@ void apx_vdw_launch(apx_ctx* c, int vers)
    CUDA_CHECK(cudaEventRecord(V.ev_done, vs));
 }
 
-void apx_vdw_join(apx_ctx* c)
+// copies = false: only the stream dependency (the caller puts more work in front of the copies and calls apx_vdw_copy_out itself)
+void apx_vdw_join(apx_ctx* c, bool copies)
 {
    VdwState& V = c->vdw;
    CUDA_CHECK(cudaStreamWaitEvent(c->stream, V.ev_done, 0));
@@ -532,6 +533,13 @@ void apx_vdw_join(apx_ctx* c)
       apx_dist_allreduce_u64(c, V.vbuf.p, 8);
       apx_dist_allreduce_i32(c, V.vcnt.p, 2);
    }
+   if (copies)
+      apx_vdw_copy_out(c);
+}
+
+void apx_vdw_copy_out(apx_ctx* c)
+{
+   VdwState& V = c->vdw;
    // pinned landing zone behind the electrostatics scalars (apx_ctx::red_h)
    CUDA_CHECK(cudaMemcpyAsync(c->red_h + 2048, V.vbuf.p, sizeof(fixed_t) * 8, cudaMemcpyDeviceToHost, c->stream));
    CUDA_CHECK(cudaMemcpyAsync(c->red_h + 2048 + 64, V.vcnt.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, c->stream));

@@ -817,9 +817,19 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    // of iterations not have converged, nothing of it runs, the accumulators keep what the vdW / valence terms put there, and
    // the region is simply launched again once the remaining iterations are done (below).
    const bool cond_epilogue = do_p && c->opt.poltyp_mutual && !dist && c->use_graph != 0;
-   const int ekey = 0x4000 | (vers & 0xff) | (do_m ? 0x100 : 0) | (do_p ? 0x200 : 0) | (cond_epilogue ? 0x800 : 0);
+   // md.cu hands in the closing half-kick and the thermostat (c->epi_tail): behind a deferred solve they become part of the SAME
+   // IF-node body as the epilogue -- one graph launch less per MD step (the separate tail graph started ~40 us after the
+   // epilogue's last kernel, profiles/r02o_trace_md.txt).  They may only run where the epilogue is known to run on converged
+   // dipoles exactly once: inside the IF body, or eagerly behind a solve that was waited for; in every other case
+   // c->epi_tail_ran stays 0 and the caller launches its own tail.
+   const bool with_tail = (bool)c->epi_tail && cond_epilogue;
+   const int ekey = 0x4000 | (vers & 0xff) | (do_m ? 0x100 : 0) | (do_p ? 0x200 : 0) | (cond_epilogue ? 0x800 : 0) | (with_tail ? 0x10000 : 0);
+   if (stage != 2)
+      c->epi_tail_ran = 0;
    auto epilogue = [&]() {
    const bool eager = apx_graph_begin(c, ekey, cond_epilogue ? c->flags.p + 1 : nullptr);
+   if (!eager && with_tail && apx_graph_is_conditional(c, ekey))
+      c->epi_tail_ran = 1;
    if (eager) {
    MplarArgs A;
    A.a0 = c->a0;
@@ -934,14 +944,26 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
       APX_COUNT_LAUNCH(c);
       apx_torque(c, do_v);
    }
+   if (with_tail) {
+      const bool in_if = c->capturing && c->cond_outer != nullptr;
+      if (in_if || (!c->capturing && !induce_deferred)) {
+         c->epi_tail();
+         c->epi_tail_ran = 1;
+      }
+   }
    apx_graph_end(c, ekey);
    }
    };
    const size_t tail = (size_t)((char*)(c->cnt.p + 4) - (char*)c->ebuf.p);
    if (stage != 2) {
+   // (the kick inside the epilogue needs the vdW forces: their stream is joined first; it finished long ago, beside the prologue)
+   if (with_tail && do_vdw)
+      apx_vdw_join(c, false);
    epilogue();
-   if (do_vdw)
+   if (do_vdw && !with_tail)
       apx_vdw_join(c);
+   else if (do_vdw)
+      apx_vdw_copy_out(c);
    if (do_val)
       apx_valence_join(c);
    if (dist) {
@@ -955,6 +977,7 @@ static bool energy_once(apx_ctx* c, int vers, bool do_m, bool do_p, apx_energy_r
    }
    // ---- reductions to the host (energy.cpp:334-384)
    // ebuf, dbuf and cnt sit back to back at the end of the accumulator arena: ONE copy into pinned memory
+   apx_induce_copy_out(c);
    CUDA_CHECK(cudaMemcpyAsync(c->red_h, c->ebuf.p, tail, cudaMemcpyDeviceToHost, st));
    cudaEventRecord(c->ev3, st);
    c->epend_deferred = induce_deferred ? 1 : 0;

@@ -836,10 +836,16 @@ static bool induce_core(apx_ctx* c, int mode)
          for (int b = 0; b < nit; ++b)
             enqueue_iteration(++iter, false, 0);
       }
-      CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-      CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      const bool leave = generic && defer && first_batch && iter < politer;
+      // (an unawaited batch: the caller copies the flags out AFTER what it enqueues behind the solve -- apx_induce_copy_out --
+      // so that its graph follows the last iteration kernel directly instead of two 3 us copies and their gaps)
+      if (!leave) {
+         CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+         CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      }
       cudaEventRecord(c->ev1, st);
-      if (generic && defer && first_batch && iter < politer) {
+      if (leave) {
+         c->induce_copy_pending = 1;
          c->skip = nullptr;
          c->induce_pending = 2;
          c->induce_pending_predict = predict ? 1 : 0;
@@ -854,6 +860,18 @@ static bool induce_core(apx_ctx* c, int mode)
    c->skip = nullptr;
    induce_epilogue(c, c->flags_h[2] > 0 ? c->flags_h[2] : iter, predict);
    return false;
+}
+
+// convergence flag, iteration count and final residual of an unawaited batch -> pinned memory (enqueued by the caller behind its
+// own work; a no-op when the solver has already copied them)
+void apx_induce_copy_out(apx_ctx* c)
+{
+   if (!c->induce_copy_pending)
+      return;
+   c->induce_copy_pending = 0;
+   double* result = c->scal.p + (size_t)PCG_SLOT * (c->opt.politer + 3);
+   CUDA_CHECK(cudaMemcpyAsync(c->flags_h, c->flags.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+   CUDA_CHECK(cudaMemcpyAsync(c->scal_h, result, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 }
 
 // what follows the solve on the host once its results are visible (after a stream synchronisation).  false: the deferred first
