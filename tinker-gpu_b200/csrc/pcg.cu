@@ -304,11 +304,21 @@ static void field_of_dp(apx_ctx* c, const real4* U, bool spread)
    cudaStream_t st = c->stream;
    if (c->dist.on)
       apx_dist_halo(c, const_cast<real4*>(U), st);      // neighbours' dipoles from the GPUs that own them
-   CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
+   // Decomposed runs, APX_DIST_FORK_LATE=1: the operator starts only when the spread has FINISHED.  Measured at 8 GPUs
+   // (profiles/r02y_*, r02z_*): started together, the exchange after the spread sees its last CTA pass the peers' arrival flags
+   // 27-120 us after kernel entry; forked late that drops to 10 us -- and the same ~100 us reappear at the forward transpose,
+   // behind the 2-D FFTs, whose wide CTAs do not fit into the slots the operator's narrow CTAs free one at a time (stream
+   // priority picks among CTAs that FIT).  6.65 ms per step either way, so the default stays the earlier start.
+   static const int fork_late = getenv("APX_DIST_FORK_LATE") ? atoi(getenv("APX_DIST_FORK_LATE")) : 0;
+   const bool late = c->dist.on && fork_late && c->opt.use_ewald && spread;
+   if (!late)
+      CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
    // the spread heads the critical path (spread -> FFTs -> gather) and goes in first: launched after the rows, its CTAs waited
    // 13 us for the operator's grid to drain (profiles/r02f_trace_md.txt); the operator is only needed by the gather
    if (c->opt.use_ewald && spread)
       apx_pme_spread_dp(c, U);
+   if (late)
+      CUDA_CHECK(cudaEventRecord(c->ev_fork, st));
    CUDA_CHECK(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
    apx_ufield_real_dp(c, c->stream2, U, c->pk_f);
    CUDA_CHECK(cudaEventRecord(c->ev_join, c->stream2));
