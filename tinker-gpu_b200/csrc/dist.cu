@@ -8,19 +8,23 @@
 //     streaming work per step and needs no exchange.  Everything that costs -- neighbor rows,
 //     pair kernels, spreading, gathering, FFT, solver vectors -- is done for owned atoms/planes only.
 //   * halo exchange per operator application: the packed (d,p) vectors of the atoms within
-//     cutoff+buffer of a neighbour's slab go to that neighbour (pack kernel -> grouped send/recv ->
-//     unpack kernel).  Both sides derive the same index lists from the replicated coordinates, so
-//     no index traffic is needed.
+//     cutoff+buffer of a neighbour's slab go to that neighbour.  Both sides derive the same index
+//     lists from the replicated coordinates, so no index traffic is needed; sorted indices are global,
+//     so the direct transport writes every halo atom straight into the same slot of the peer's array.
 //   * slab-decomposed 3-D FFT: halo planes of the spread grid are summed into their owners, 2-D
 //     FFTs over the owned planes, an all-to-all transpose to [k3][k2 local][k1], 1-D FFTs along z,
 //     the influence function, and the way back; the potential's halo planes are then returned for
 //     the gather.
 //   * scalars of the solver: one small all-reduce per dot-product pair (3 per iteration).
 //
-// Two transports implement the same interface (ApxComm): NCCL over NVLink (one process per GPU,
-// symbols resolved at run time from the libnccl the host process already uses), and an in-process
-// transport for several ranks driven by host threads on ONE GPU, which lets the whole decomposition be
-// parity-tested against the single-GPU path on a one-GPU box.
+// Transports (ApxComm): (1) one process per GPU -- NCCL for the start-up handshake and the large force
+// reduction, and for everything else the library's own peer-memory kernels over NVLink: `DirectComm`
+// (default; exchange buffers registered through CUDA IPC, ONE kernel per exchange that writes into the
+// peers' memory, flag-based scalar all-reduce), `P2pComm` (windowed push / pull, APX_DIST_P2P=2 or 1) or
+// plain NCCL send/recv (APX_DIST_P2P=0); (2) transport "direct": DirectComm with no NCCL at all (IPC
+// handles through a /dev/shm rendezvous) -- used to test the process-per-rank path on a one-GPU box;
+// (3) an in-process transport for several ranks driven by host threads on ONE GPU, which lets the whole
+// decomposition be parity-tested against the single-GPU path without any inter-process machinery.
 #include "apx_internal.h"
 #include "dp.cuh"
 #include <nccl.h>
