@@ -341,9 +341,10 @@ def cpu_dynamics_sample(system):
     if kind == "reference":
         pr = vo.pairs(vo.reduced())                  # neighbour search outside the timed region, like the GPU's Verlet rows
         t0 = time.perf_counter()
-        hp = ref_bridge.hal_pairs(vo, pr)
+        hp = ref_bridge.hal_pairs(vo, pr, threads=CPU_THREADS)
         ms_vdw = 1e3 * (time.perf_counter() - t0)
-        vdw_desc = f"the reference's pair_hal_v2 over all {hp['npairs']} pairs within 12 A (oracle/_ref, {ms_vdw:.0f} ms incl. numpy gather of the pair data)"
+        vdw_desc = (f"the reference's pair_hal_v2 over all {hp['npairs']} pairs within 12 A on {CPU_THREADS} host threads (oracle/_ref, "
+                    f"{ms_vdw:.0f} ms incl. numpy gather of the pair data)")
     else:
         t0 = time.perf_counter()
         vo.ehal()

@@ -198,33 +198,55 @@ class RefPME:
         return self._call("ref_pme_fphi_uind2", [], [(self.n, 10), (self.n, 10)])
 
 
-def hal_pairs(vdw_oracle, pairs=None):
+def hal_pairs(vdw_oracle, pairs=None, threads=1):
     """ev, gradient on the reduced sites and virial of the 14-7 term from the reference's pair_hal_v2 over the vdW oracle's own
-    pair list (pairs = (i, k) to reuse a list found earlier)."""
+    pair list (pairs = (i, k) to reuse a list found earlier).  threads > 1 (bench.py's CPU legs only): the pair list is cut into
+    that many slices, each prepared and swept on its own host thread (numpy and ctypes release the GIL), partial sums added."""
     lib = C.CDLL(os.path.join(HERE, "_ref", "libref_realspace.so"))
     lib.ref_hal_pairs.argtypes = [C.c_int, C.c_longlong, _IP, _IP, _DP, _DP, _DP, C.c_double, C.c_double, C.c_double, C.c_double, _DP, _DP, _DP]
     o, v = vdw_oracle, vdw_oracle.v
     xr = o.reduced()
-    i, k = o.pairs(xr) if pairs is None else pairs
-    scale = np.ones(i.shape[0])
+    i_all, k_all = o.pairs(xr) if pairs is None else pairs
+    ex_sorted = ex_scale = None
     if v.vexclude.shape[0]:
-        code = i.astype(np.int64) * o.n + k
         ex = v.vexclude[:, 0].astype(np.int64) * o.n + v.vexclude[:, 1]
         order = np.argsort(ex)
-        pos = np.minimum(np.searchsorted(ex[order], code), ex.shape[0] - 1)
-        hit = ex[order][pos] == code
-        scale[hit] = v.vexclude_scale[order][pos[hit]]
-    keep = scale != 0
-    i, k, scale = i[keep], k[keep], scale[keep]
-    d = np.ascontiguousarray(o.image(xr[i] - xr[k]), np.float64)
-    rv = np.ascontiguousarray(v.radmin[v.jvdw[i], v.jvdw[k]], np.float64)
-    eps = np.ascontiguousarray(v.epsilon[v.jvdw[i], v.jvdw[k]] * scale, np.float64)
-    i32, k32 = np.ascontiguousarray(i, np.int32), np.ascontiguousarray(k, np.int32)
-    ev = C.c_double()
-    g, v9 = np.zeros((o.n, 3)), np.zeros(9)
-    lib.ref_hal_pairs(o.n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(d), _dp(rv), _dp(eps), float(v.taper), float(v.cutoff),
-                      float(v.ghal), float(v.dhal), C.byref(ev), _dp(g), _dp(v9))
-    return dict(ev=ev.value, gred=g, virial=v9.reshape(3, 3), npairs=len(i32))
+        ex_sorted, ex_scale = ex[order], v.vexclude_scale[order]
+
+    def sweep(lo, hi):
+        i, k = i_all[lo:hi], k_all[lo:hi]
+        scale = np.ones(i.shape[0])
+        if ex_sorted is not None:
+            code = i.astype(np.int64) * o.n + k
+            pos = np.minimum(np.searchsorted(ex_sorted, code), ex_sorted.shape[0] - 1)
+            hit = ex_sorted[pos] == code
+            scale[hit] = ex_scale[pos[hit]]
+        keep = scale != 0
+        i, k, scale = i[keep], k[keep], scale[keep]
+        d = np.ascontiguousarray(o.image(xr[i] - xr[k]), np.float64)
+        rv = np.ascontiguousarray(v.radmin[v.jvdw[i], v.jvdw[k]], np.float64)
+        eps = np.ascontiguousarray(v.epsilon[v.jvdw[i], v.jvdw[k]] * scale, np.float64)
+        i32, k32 = np.ascontiguousarray(i, np.int32), np.ascontiguousarray(k, np.int32)
+        ev = C.c_double()
+        g, v9 = np.zeros((o.n, 3)), np.zeros(9)
+        lib.ref_hal_pairs(o.n, len(i32), i32.ctypes.data_as(_IP), k32.ctypes.data_as(_IP), _dp(d), _dp(rv), _dp(eps), float(v.taper),
+                          float(v.cutoff), float(v.ghal), float(v.dhal), C.byref(ev), _dp(g), _dp(v9))
+        return ev.value, g, v9, len(i32)
+
+    npair = int(i_all.shape[0])
+    T = max(1, min(int(threads), npair // 65536 or 1))
+    if T == 1:
+        ev, g, v9, m = sweep(0, npair)
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        cuts = np.linspace(0, npair, T + 1).astype(int)
+        with ThreadPoolExecutor(T) as exr:
+            parts = list(exr.map(lambda t: sweep(int(cuts[t]), int(cuts[t + 1])), range(T)))
+        ev = sum(p[0] for p in parts)
+        g = sum(p[1] for p in parts)
+        v9 = sum(p[2] for p in parts)
+        m = sum(p[3] for p in parts)
+    return dict(ev=ev, gred=g, virial=v9.reshape(3, 3), npairs=m)
 
 
 def _frames_lib():

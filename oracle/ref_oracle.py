@@ -31,11 +31,44 @@ class RefOracle(Oracle):
                                             _DP, _DP]
         self._refpme = None
         self._plist = None
+        self._pmat = None
 
     def set_xyz(self, xyz):
         super().set_xyz(xyz)
         self._refpme = None
         self._plist = None
+        self._pmat = None
+
+    # ---- sparse preconditioner: BUILD once per set of positions, APPLY per iteration -- the split the reference makes
+    # (sparsePrecondBuild / sparsePrecondApply, src/acc/amoeba/induce.cpp:296-468: `minv`, 6 numbers per pair, is filled once per
+    # induce()).  Oracle.precond recomputes the pair tensors in every application, which is fine for a checker and made the
+    # CPU baseline of bench.py spend two thirds of its induce() there.  Same arithmetic, summed in CSR row order.
+    def precond(self, rd, rp_):
+        s = self.s
+        if not (s.pcgprec and s.usolve_cutoff > 0):
+            return super().precond(rd, rp_)
+        if getattr(self, "_pmat", None) is None:
+            from scipy import sparse
+            from .amoeba_ref import thole_lambda
+            i, k, R, r = self.pairs(s.usolve_cutoff)
+            sc = self._scales(i, k)
+            pdi, pdk, pga = self._pair_params(i, k)
+            lam = thole_lambda(r, pdi, pdk, pga, 3)
+            polik = s.polarity[i] * s.polarity[k]
+            rr3 = sc[:, 3] * lam[:, 1] * polik / r ** 3
+            rr5 = 3 * sc[:, 3] * lam[:, 2] * polik / r ** 5
+            M = np.einsum("pa,pb->pab", R, R) * rr5[:, None, None] - np.eye(3)[None] * rr3[:, None, None]      # symmetric 3x3 per pair
+            a = np.arange(3)
+            rows = np.concatenate([(3 * i[:, None, None] + a[None, :, None]) + 0 * a[None, None, :],
+                                   (3 * k[:, None, None] + a[None, :, None]) + 0 * a[None, None, :]]).ravel()
+            cols = np.concatenate([(3 * k[:, None, None] + a[None, None, :]) + 0 * a[None, :, None],
+                                   (3 * i[:, None, None] + a[None, None, :]) + 0 * a[None, :, None]]).ravel()
+            vals = np.concatenate([M, M]).ravel()
+            self._pmat = sparse.csr_matrix((vals, (rows, cols)), shape=(3 * self.n, 3 * self.n))
+        pol = s.polarity[:, None]
+        zd = s.uaccel * pol * rd + (self._pmat @ np.ascontiguousarray(rd).reshape(-1)).reshape(-1, 3)
+        zp = s.uaccel * pol * rp_ + (self._pmat @ np.ascontiguousarray(rp_).reshape(-1)).reshape(-1, 3)
+        return zd, zp
 
     # ---- shared inputs of the pair sweeps
     def _pairs_c(self):
