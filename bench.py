@@ -639,6 +639,17 @@ def run_strong_child(args, rank, world, local_rank):
     energy+gradient evaluation of the electrostatics path per step; N = 1 is the single-GPU path on the same box."""
     import ctypes as C
     import torch
+    if os.environ.get("APX_BENCH_STRONG_FAKE"):
+        # tests/test_bench_strong_spawn.py (CPU, gloo, 2 ranks under torchrun): only the plumbing of this leg -- the children's own
+        # rendezvous beside the parent job's, the cleaned environment, the STRONG line back to rank 0 -- without a GPU
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t)
+        if rank == 0:
+            print("STRONG " + json.dumps({"fake": True, "n_gpus": world, "sum_of_ranks": float(t)}), flush=True)
+        dist.destroy_process_group()
+        return
     from tinker_gpu_b200.amoeba import calc
     from tinker_gpu_b200.distributed import nccl_context
     torch.cuda.set_device(local_rank)
