@@ -198,6 +198,9 @@ int apx_get_dist_info(apx_ctx* ctx, int* info8 /* rank, world, a0, a1, halo atom
  * [1] forward slab FFTs (plane reduction, 2-D FFTs, transpose, 1-D FFTs), [2] inverse slab FFTs, [3] scalar all-reduces,
  * [4..7] their call counts.  on: keep collecting.  Call after apx_synchronize. */
 int apx_dist_profile(apx_ctx* ctx, int on, double* out8);
+/* host-only self-test of the /dev/shm rendezvous that carries the CUDA IPC handles of transport "direct" at start-up: `rounds`
+ * all-gathers of `bytes` bytes (round r sends mine[q] + r); out [world][bytes] = the last round.  0 on success. */
+int apx_rendezvous_selftest(const void* job_id16, int rank, int world, const void* mine, int bytes, int rounds, void* out);
 /* host-only: halo plan of `rank` from the sorted atoms' PME z-coordinates and the ranks' sorted ranges */
 int apx_dist_plan(int n, const float* w3_sorted, const int* bounds, int world, int rank, double range_frac, int* send_idx,
    int* send_off, int* recv_idx, int* recv_off);

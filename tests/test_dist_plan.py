@@ -94,3 +94,38 @@ def test_halo_exchange_world2_gloo(tmp_path):
     assert out.returncode == 0, out.stderr[-3000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESULT")][0].split()
     assert line[1] == "1" and int(line[2]) > 100
+
+
+_RDV_CHILD = r"""
+import ctypes, os, sys
+import numpy as np
+lib = ctypes.CDLL(sys.argv[1])
+job = bytes.fromhex(sys.argv[2]); rank = int(sys.argv[3]); world = int(sys.argv[4]); rounds = int(sys.argv[5])
+mine = np.arange(64, dtype=np.uint8) + 10 * rank
+out = np.zeros((world, 64), dtype=np.uint8)
+lib.apx_rendezvous_selftest.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+rc = lib.apx_rendezvous_selftest(job, rank, world, mine.ctypes.data, 64, rounds, out.ctypes.data)
+ok = rc == 0 and all(np.array_equal(out[r], (np.arange(64) + 10 * r + rounds - 1).astype(np.uint8)) for r in range(world))
+sys.exit(0 if ok else 1)
+"""
+
+
+def test_direct_transport_rendezvous_between_processes():
+    """The start-up exchange of transport "direct" (dist.cu FileRendezvous: the CUDA IPC handles travel through /dev/shm when
+    there is no NCCL): three PROCESSES, five rounds; every rank must end with every rank's blob of the last round, and a rank's
+    files of earlier rounds must be gone (removed once the following round has been read)."""
+    import glob
+    lib = os.path.join(ROOT, "tinker-gpu_b200", "libapx.so")
+    job = os.urandom(16).hex()
+    world, rounds = 3, 5
+    procs = [subprocess.Popen([sys.executable, "-c", _RDV_CHILD, lib, job, str(r), str(world), str(rounds)]) for r in range(world)]
+    try:
+        assert [p.wait(timeout=120) for p in procs] == [0] * world
+        left = sorted(os.path.basename(f) for f in glob.glob("/dev/shm/apx_" + job + "_*"))
+        assert left == [f"apx_{job}_{rounds}_{r}" for r in range(world)]      # only the last round's files remain
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for f in glob.glob("/dev/shm/apx_" + job + "_*"):
+            os.remove(f)

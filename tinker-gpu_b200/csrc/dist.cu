@@ -1831,6 +1831,32 @@ void apx_local_hub_destroy(void* h)
    delete hub;
 }
 
+// host-only: the start-up rendezvous of transport "direct" (no GPU needed; tests/test_dist_plan.py runs it between two processes):
+// `rounds` gathers of `bytes` bytes each; out receives the blobs of the last round, concatenated by rank
+int apx_rendezvous_selftest(const void* job_id16, int rank, int world, const void* mine, int bytes, int rounds, void* out)
+{
+   try {
+      FileRendezvous rdv;
+      rdv.rank = rank, rdv.world = world;
+      static const char hex[] = "0123456789abcdef";
+      std::string key;
+      const unsigned char* b = static_cast<const unsigned char*>(job_id16);
+      for (int k = 0; k < 16; ++k)
+         key += hex[b[k] >> 4], key += hex[b[k] & 15];
+      rdv.prefix = "/dev/shm/apx_" + key;
+      std::vector<char> blob((size_t)bytes);
+      for (int r = 0; r < rounds; ++r) {
+         for (int q = 0; q < bytes; ++q)
+            blob[q] = (char)(static_cast<const char*>(mine)[q] + r);      // every round carries different bytes
+         rdv.gather(blob.data(), (size_t)bytes, out);
+      }
+   } catch (const std::exception& e) {
+      g_dist_err = e.what();
+      return 1;
+   }
+   return 0;
+}
+
 // host-only: the halo plan of `rank` (no GPU needed; CPU tests run it under gloo with 2 ranks)
 int apx_dist_plan(int n, const float* w3_sorted, const int* bounds, int world, int rank, double range_frac, int* send_idx,
    int* send_off, int* recv_idx, int* recv_off)
